@@ -1,0 +1,308 @@
+// api.cu -- library state (error string, launch counter) and the small elementwise/layout kernels.
+#include <stdarg.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <atomic>
+
+#include "common.cuh"
+
+static thread_local char g_err[1024] = "";
+static std::atomic<long long> g_launches{0};
+
+void omr_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+void omr_count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+extern "C" int omr_abi_version(void) { return 1; }
+extern "C" const char* omr_last_error(void) { return g_err; }
+extern "C" long long omr_launch_count(void) { return g_launches.load(); }
+
+// ---- cast -----------------------------------------------------------------------------------
+template <typename TS, typename TD>
+__global__ void cast_kernel(const TS* __restrict__ s, TD* __restrict__ d, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) d[i] = from_f<TD>(to_f(s[i]));
+}
+
+static int grid_for(long long n, int threads, int per_thread = 4) {
+  long long b = cdiv(n, (long long)threads * per_thread);
+  if (b < 1) b = 1;
+  if (b > 148LL * 32) b = 148LL * 32;
+  return (int)b;
+}
+
+extern "C" int omr_cast(int src_dt, int dst_dt, const void* src, void* dst, long long n, omr_stream_t stream) {
+  if (n <= 0) return OMR_OK;
+  cudaStream_t st = as_stream(stream);
+  int g = grid_for(n, 256);
+  if (src_dt == OMR_F32 && dst_dt == OMR_BF16)
+    cast_kernel<float, bf16><<<g, 256, 0, st>>>((const float*)src, (bf16*)dst, n);
+  else if (src_dt == OMR_BF16 && dst_dt == OMR_F32)
+    cast_kernel<bf16, float><<<g, 256, 0, st>>>((const bf16*)src, (float*)dst, n);
+  else if (src_dt == OMR_F32 && dst_dt == OMR_F32)
+    cast_kernel<float, float><<<g, 256, 0, st>>>((const float*)src, (float*)dst, n);
+  else if (src_dt == OMR_BF16 && dst_dt == OMR_BF16)
+    cast_kernel<bf16, bf16><<<g, 256, 0, st>>>((const bf16*)src, (bf16*)dst, n);
+  else
+    OMR_REQUIRE(false, "omr_cast: bad dtypes %d -> %d", src_dt, dst_dt);
+  OMR_LAUNCHED();
+  return OMR_OK;
+}
+
+// ---- relu backward / add ------------------------------------------------------------------------
+template <typename T>
+__global__ void relu_bwd_kernel(const T* __restrict__ y, const T* __restrict__ dy, T* __restrict__ dx, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) dx[i] = to_f(y[i]) > 0.f ? dy[i] : from_f<T>(0.f);
+}
+extern "C" int omr_relu_bwd(int dt, const void* y, const void* dy, void* dx, long long n, omr_stream_t stream) {
+  if (n <= 0) return OMR_OK;
+  OMR_DISPATCH_DT(dt, T, (relu_bwd_kernel<T><<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(
+                             (const T*)y, (const T*)dy, (T*)dx, n)));
+  OMR_LAUNCHED();
+  return OMR_OK;
+}
+
+template <typename T>
+__global__ void add_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ o, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) o[i] = from_f<T>(to_f(a[i]) + to_f(b[i]));
+}
+extern "C" int omr_add(int dt, const void* a, const void* b, void* out, long long n, omr_stream_t stream) {
+  if (n <= 0) return OMR_OK;
+  OMR_DISPATCH_DT(dt, T, (add_kernel<T><<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(
+                             (const T*)a, (const T*)b, (T*)out, n)));
+  OMR_LAUNCHED();
+  return OMR_OK;
+}
+
+// ---- weight packing ---------------------------------------------------------------------------
+// w [Co,Ci,3,3] -> transpose==0: out[co][tap][ci] ; transpose==1: out[ci][tap][co]
+template <typename T>
+__global__ void pack_conv_w_kernel(const float* __restrict__ w, T* __restrict__ out, int Co, int Ci, int transpose) {
+  long long n = (long long)Co * Ci * 9;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    int tap = (int)(i % 9);
+    int ci = (int)((i / 9) % Ci);
+    int co = (int)(i / (9LL * Ci));
+    long long o = transpose ? ((long long)ci * 9 + tap) * Co + co : ((long long)co * 9 + tap) * Ci + ci;
+    out[o] = from_f<T>(w[i]);
+  }
+}
+extern "C" int omr_pack_conv_weight(int dt, const float* w, void* out, int Co, int Ci, int transpose,
+                                    omr_stream_t stream) {
+  long long n = (long long)Co * Ci * 9;
+  OMR_DISPATCH_DT(dt, T, (pack_conv_w_kernel<T><<<grid_for(n, 256, 1), 256, 0, as_stream(stream)>>>(
+                             w, (T*)out, Co, Ci, transpose)));
+  OMR_LAUNCHED();
+  return OMR_OK;
+}
+
+// w [C,1,3,3] -> out [tap][c]
+template <typename T>
+__global__ void pack_dw_w_kernel(const float* __restrict__ w, T* __restrict__ out, int C) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < C * 9) {
+    int tap = i % 9, c = i / 9;
+    out[tap * C + c] = from_f<T>(w[i]);
+  }
+}
+extern "C" int omr_pack_dw_weight(int dt, const float* w, void* out, int C, omr_stream_t stream) {
+  OMR_DISPATCH_DT(dt, T, (pack_dw_w_kernel<T><<<(int)cdiv(C * 9, 256), 256, 0, as_stream(stream)>>>(w, (T*)out, C)));
+  OMR_LAUNCHED();
+  return OMR_OK;
+}
+
+// ---- PE-2D add into the fused memory, row-block copy ------------------------------------------------
+template <typename T>
+__global__ void pe2d_add_kernel(const T* __restrict__ x, const float* __restrict__ pe, T* __restrict__ out, int B,
+                                int h, int w, int C, int pe_w, int out_rows, int row_off) {
+  // one thread per 4 channels
+  long long n4 = (long long)B * h * w * (C / 4);
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long stride = (long long)gridDim.x * blockDim.x;
+  int c4n = C / 4;
+  for (; i < n4; i += stride) {
+    int c4 = (int)(i % c4n);
+    long long r = i / c4n;
+    int p = (int)(r % ((long long)h * w));
+    int b = (int)(r / ((long long)h * w));
+    int ph = p / w, pw = p % w;
+    float v[4], e[4];
+    load4(x + ((long long)b * h * w + p) * C + c4 * 4, v);
+    load4(pe + ((long long)ph * pe_w + pw) * C + c4 * 4, e);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] += e[k];
+    store4(out + ((long long)b * out_rows + row_off + p) * C + c4 * 4, v);
+  }
+}
+extern "C" int omr_pe2d_add(int dt, const void* x, const float* pe, void* out, int B, int h, int w, int C, int pe_w,
+                            int out_rows, int row_off, omr_stream_t stream) {
+  OMR_REQUIRE(C % 4 == 0, "omr_pe2d_add: C must be a multiple of 4 (got %d)", C);
+  OMR_REQUIRE(w <= pe_w, "omr_pe2d_add: feature map wider than the PE table (%d > %d)", w, pe_w);
+  long long n4 = (long long)B * h * w * (C / 4);
+  if (n4 <= 0) return OMR_OK;
+  OMR_DISPATCH_DT(dt, T, (pe2d_add_kernel<T><<<grid_for(n4, 256, 1), 256, 0, as_stream(stream)>>>(
+                             (const T*)x, pe, (T*)out, B, h, w, C, pe_w, out_rows, row_off)));
+  OMR_LAUNCHED();
+  return OMR_OK;
+}
+
+template <typename T>
+__global__ void copy_rows_kernel(const T* __restrict__ src, T* __restrict__ dst, int B, int rows, int C, int src_rows,
+                                 int src_off) {
+  long long n4 = (long long)B * rows * (C / 4);
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long stride = (long long)gridDim.x * blockDim.x;
+  int c4n = C / 4;
+  for (; i < n4; i += stride) {
+    int c4 = (int)(i % c4n);
+    long long r = i / c4n;
+    int p = (int)(r % rows);
+    int b = (int)(r / rows);
+    float v[4];
+    load4(src + ((long long)b * src_rows + src_off + p) * C + c4 * 4, v);
+    store4(dst + ((long long)b * rows + p) * C + c4 * 4, v);
+  }
+}
+extern "C" int omr_copy_rows(int dt, const void* src, void* dst, int B, int rows, int C, int src_rows, int src_off,
+                             omr_stream_t stream) {
+  OMR_REQUIRE(C % 4 == 0, "omr_copy_rows: C must be a multiple of 4 (got %d)", C);
+  long long n4 = (long long)B * rows * (C / 4);
+  if (n4 <= 0) return OMR_OK;
+  OMR_DISPATCH_DT(dt, T, (copy_rows_kernel<T><<<grid_for(n4, 256, 1), 256, 0, as_stream(stream)>>>(
+                             (const T*)src, (T*)dst, B, rows, C, src_rows, src_off)));
+  OMR_LAUNCHED();
+  return OMR_OK;
+}
+
+// ---- masks -------------------------------------------------------------------------------------
+__global__ void key_bias_len_kernel(float* __restrict__ bias, const int* __restrict__ lens, int B, int S, int seg_off,
+                                    int seg_len, float value) {
+  long long n = (long long)B * seg_len;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    int j = (int)(i % seg_len), b = (int)(i / seg_len);
+    bias[(long long)b * S + seg_off + j] = (j >= lens[b]) ? value : 0.f;
+  }
+}
+extern "C" int omr_key_bias_from_lengths(float* bias, const int* lens, int B, int S, int seg_off, int seg_len,
+                                         float value, omr_stream_t stream) {
+  OMR_REQUIRE(seg_off >= 0 && seg_off + seg_len <= S, "omr_key_bias_from_lengths: segment out of range");
+  long long n = (long long)B * seg_len;
+  if (n <= 0) return OMR_OK;
+  key_bias_len_kernel<<<(int)cdiv(n, 256), 256, 0, as_stream(stream)>>>(bias, lens, B, S, seg_off, seg_len, value);
+  OMR_LAUNCHED();
+  return OMR_OK;
+}
+
+__global__ void key_bias_tok_kernel(float* __restrict__ bias, const long long* __restrict__ tok, long long n,
+                                    long long pad_id, float value) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) bias[i] = (tok[i] == pad_id) ? value : 0.f;
+}
+extern "C" int omr_key_bias_from_tokens(float* bias, const long long* tokens, long long n, long long pad_id,
+                                        float value, omr_stream_t stream) {
+  if (n <= 0) return OMR_OK;
+  key_bias_tok_kernel<<<(int)cdiv(n, 256), 256, 0, as_stream(stream)>>>(bias, tokens, n, pad_id, value);
+  OMR_LAUNCHED();
+  return OMR_OK;
+}
+
+// ---- embedding + PE-1D --------------------------------------------------------------------------
+template <typename T>
+__global__ void embed_pe_kernel(const long long* __restrict__ tok, const T* __restrict__ table,
+                                const float* __restrict__ pe, T* __restrict__ out, int B, int Tn, int D, int pos0) {
+  long long n4 = (long long)B * Tn * (D / 4);
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long stride = (long long)gridDim.x * blockDim.x;
+  int d4n = D / 4;
+  for (; i < n4; i += stride) {
+    int d4 = (int)(i % d4n);
+    long long r = i / d4n;
+    int t = (int)(r % Tn);
+    long long id = tok[r];
+    float v[4], e[4];
+    load4(table + id * D + d4 * 4, v);
+    load4(pe + (long long)(pos0 + t) * D + d4 * 4, e);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] += e[k];
+    store4(out + r * D + d4 * 4, v);
+  }
+}
+extern "C" int omr_embed_pe_fwd(int dt, const long long* tokens, const void* table, const float* pe, void* out, int B,
+                                int T_, int D, int pos0, omr_stream_t stream) {
+  OMR_REQUIRE(D % 4 == 0, "omr_embed_pe_fwd: D must be a multiple of 4");
+  long long n4 = (long long)B * T_ * (D / 4);
+  if (n4 <= 0) return OMR_OK;
+  OMR_DISPATCH_DT(dt, T, (embed_pe_kernel<T><<<grid_for(n4, 256, 1), 256, 0, as_stream(stream)>>>(
+                             tokens, (const T*)table, pe, (T*)out, B, T_, D, pos0)));
+  OMR_LAUNCHED();
+  return OMR_OK;
+}
+
+template <typename T>
+__global__ void embed_bwd_kernel(const long long* __restrict__ tok, const T* __restrict__ dout,
+                                 float* __restrict__ dtable, long long rows, int D, long long padding_idx) {
+  long long n = rows * D;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    long long r = i / D;
+    int d = (int)(i % D);
+    long long id = tok[r];
+    if (id != padding_idx) atomicAdd(dtable + id * D + d, to_f(dout[i]));
+  }
+}
+extern "C" int omr_embed_bwd(int dt, const long long* tokens, const void* dout, float* dtable, long long rows, int D,
+                             long long padding_idx, omr_stream_t stream) {
+  long long n = rows * D;
+  if (n <= 0) return OMR_OK;
+  OMR_DISPATCH_DT(dt, T, (embed_bwd_kernel<T><<<grid_for(n, 256, 1), 256, 0, as_stream(stream)>>>(
+                             tokens, (const T*)dout, dtable, rows, D, padding_idx)));
+  OMR_LAUNCHED();
+  return OMR_OK;
+}
+
+// ---- column sum (bias gradients) ----------------------------------------------------------------------
+// grid.x tiles columns by 32, grid.y splits rows; block (32, 8)
+template <typename T>
+__global__ void colsum_kernel(const T* __restrict__ x, long long rows, int N, long long ld, float* __restrict__ out) {
+  __shared__ float sm[8][33];
+  int c = blockIdx.x * 32 + threadIdx.x;
+  float acc = 0.f;
+  if (c < N) {
+    for (long long r = (long long)blockIdx.y * 8 + threadIdx.y; r < rows; r += (long long)gridDim.y * 8)
+      acc += to_f(x[r * ld + c]);
+  }
+  sm[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < N) {
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += sm[k][threadIdx.x];
+    atomicAdd(out + c, s);
+  }
+}
+extern "C" int omr_colsum(int dt, const void* x, long long rows, int N, long long ld, float* out, int accumulate,
+                          omr_stream_t stream) {
+  if (N <= 0) return OMR_OK;
+  cudaStream_t st = as_stream(stream);
+  if (!accumulate) OMR_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * N, st));
+  if (rows <= 0) return OMR_OK;
+  dim3 grid((unsigned)cdiv(N, 32), (unsigned)(rows >= 8 * 64 ? (cdiv(rows, 8 * 16) > 512 ? 512 : cdiv(rows, 8 * 16)) : 1));
+  dim3 block(32, 8);
+  OMR_DISPATCH_DT(dt, T, (colsum_kernel<T><<<grid, block, 0, st>>>((const T*)x, rows, N, ld, out)));
+  OMR_LAUNCHED();
+  return OMR_OK;
+}

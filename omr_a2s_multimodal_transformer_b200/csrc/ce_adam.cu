@@ -1,0 +1,170 @@
+// ce_adam.cu -- vocabulary softmax cross-entropy (forward / backward, HBM-bound row kernels) and the
+// fused multi-tensor Adam step that also refreshes the bf16 kernel-layout weight copies.
+#include "common.cuh"
+
+namespace {
+
+// one block per row: lse = log sum exp(logits), loss = lse - logit[target]
+template <typename T>
+__global__ void __launch_bounds__(256) ce_fwd_kernel(const T* __restrict__ logits, long long ld,
+                                                     const long long* __restrict__ targets, int V,
+                                                     long long ignore_index, float* __restrict__ row_loss,
+                                                     float* __restrict__ row_lse) {
+  __shared__ float sm[33];
+  const long long r = blockIdx.x;
+  const T* x = logits + r * ld;
+  float mx = -INFINITY;
+  for (int i = threadIdx.x; i < V; i += blockDim.x) mx = fmaxf(mx, to_f(x[i]));
+  mx = block_max(mx, sm);
+  float s = 0.f;
+  for (int i = threadIdx.x; i < V; i += blockDim.x) s += expf(to_f(x[i]) - mx);
+  s = block_sum(s, sm);
+  if (threadIdx.x == 0) {
+    float lse = mx + logf(s);
+    row_lse[r] = lse;
+    long long t = targets[r];
+    row_loss[r] = (t == ignore_index || t < 0 || t >= V) ? 0.f : lse - to_f(x[t]);
+  }
+}
+
+// single block: deterministic tree reduction of the per-row losses
+__global__ void __launch_bounds__(1024) ce_reduce_kernel(const float* __restrict__ row_loss,
+                                                         const long long* __restrict__ targets, long long rows,
+                                                         long long ignore_index, float* __restrict__ out) {
+  __shared__ float sm[33];
+  float s = 0.f, n = 0.f;
+  for (long long i = threadIdx.x; i < rows; i += blockDim.x) {
+    if (targets[i] != ignore_index) { s += row_loss[i]; n += 1.f; }
+  }
+  s = block_sum(s, sm);
+  n = block_sum(n, sm);
+  if (threadIdx.x == 0) {
+    out[0] = n > 0.f ? s / n : 0.f;  // torch returns nan for an all-ignored batch; never on the hot path
+    out[1] = n;
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) ce_bwd_kernel(const T* __restrict__ logits, long long ld,
+                                                     const long long* __restrict__ targets,
+                                                     const float* __restrict__ row_lse,
+                                                     const float* __restrict__ loss_out,
+                                                     const float* __restrict__ gscale, T* __restrict__ dlogits, int V,
+                                                     long long ignore_index) {
+  const long long r = blockIdx.x;
+  const long long t = targets[r];
+  const T* x = logits + r * ld;
+  T* d = dlogits + r * ld;
+  if (t == ignore_index) {
+    for (int i = threadIdx.x; i < V; i += blockDim.x) d[i] = from_f<T>(0.f);
+    return;
+  }
+  const float n = loss_out[1];
+  const float g = (gscale ? gscale[0] : 1.f) / (n > 0.f ? n : 1.f);
+  const float lse = row_lse[r];
+  for (int i = threadIdx.x; i < V; i += blockDim.x) {
+    float p = expf(to_f(x[i]) - lse);
+    d[i] = from_f<T>((p - (i == t ? 1.f : 0.f)) * g);
+  }
+}
+
+// ---- Adam ------------------------------------------------------------------------------------
+__global__ void adam_tick_kernel(int* step) { *step += 1; }
+
+__device__ __forceinline__ long long adam_shadow_index(long long i, int layout, int d0, int d1) {
+  if (layout == 1) {  // [Co,Ci,3,3] -> [Co,3,3,Ci]   (d0 = Co, d1 = Ci)
+    int tap = (int)(i % 9);
+    long long r = i / 9;
+    int ci = (int)(r % d1);
+    long long co = r / d1;
+    return (co * 9 + tap) * d1 + ci;
+  }
+  if (layout == 2) {  // [C,1,3,3] -> [3,3,C]   (d0 = C)
+    int tap = (int)(i % 9);
+    long long c = i / 9;
+    return (long long)tap * d0 + c;
+  }
+  if (layout == 3) {  // [Co,Ci,3,3] -> [Ci,3,3,Co]  (data-gradient operand)
+    int tap = (int)(i % 9);
+    long long r = i / 9;
+    int ci = (int)(r % d1);
+    long long co = r / d1;
+    return ((long long)ci * 9 + tap) * d0 + co;
+  }
+  if (layout == 4) {  // [R,C] -> [C,R] transpose  (d0 = R, d1 = C)
+    long long r = i / d1;
+    int c = (int)(i % d1);
+    return (long long)c * d0 + r;
+  }
+  return i;
+}
+
+__global__ void __launch_bounds__(256) adam_kernel(const omr_adam_entry* __restrict__ table, const int* __restrict__ step,
+                                                   double lr, double b1d, double b2d, double epsd, double gsd) {
+  const omr_adam_entry e = table[blockIdx.y];
+  if (e.grad == nullptr) return;
+  const int t = *step;
+  // bias corrections as torch.optim.Adam (single-tensor path): step_size = lr / (1 - b1^t),
+  // denom = sqrt(v) / sqrt(1 - b2^t) + eps ; computed in double like the Python reference
+  const float step_size = (float)(lr / (1.0 - pow(b1d, (double)t)));
+  const float bc2s = (float)sqrt(1.0 - pow(b2d, (double)t));
+  const float b1 = (float)b1d, b2 = (float)b2d, eps = (float)epsd, grad_scale = (float)gsd;
+  bf16* sh0 = (bf16*)e.shadow;
+  bf16* sh1 = (bf16*)e.shadow2;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < e.n; i += (long long)gridDim.x * blockDim.x) {
+    float g = e.grad[i] * grad_scale;
+    float m = e.exp_avg[i] = b1 * e.exp_avg[i] + (1.f - b1) * g;
+    float v = e.exp_avg_sq[i] = b2 * e.exp_avg_sq[i] + (1.f - b2) * g * g;
+    float p = e.param[i] - step_size * (m / (sqrtf(v) / bc2s + eps));
+    e.param[i] = p;
+    if (sh0) sh0[adam_shadow_index(i, e.layout, e.d0, e.d1)] = __float2bfloat16_rn(p);
+    if (sh1) sh1[adam_shadow_index(i, e.layout2, e.d0, e.d1)] = __float2bfloat16_rn(p);
+  }
+}
+
+}  // namespace
+
+extern "C" int omr_ce_fwd(int dt, const void* logits, long long ld, const long long* targets, long long rows, int V,
+                          long long ignore_index, float* row_loss, float* row_lse, omr_stream_t stream) {
+  if (rows <= 0) return OMR_OK;
+  OMR_REQUIRE(V > 0, "omr_ce_fwd: empty vocabulary");
+  OMR_DISPATCH_DT(dt, T, (ce_fwd_kernel<T><<<(unsigned)rows, 256, 0, as_stream(stream)>>>(
+                             (const T*)logits, ld, targets, V, ignore_index, row_loss, row_lse)));
+  OMR_LAUNCHED();
+  return OMR_OK;
+}
+
+extern "C" int omr_ce_reduce(const float* row_loss, const long long* targets, long long rows, long long ignore_index,
+                             float* loss_out, omr_stream_t stream) {
+  ce_reduce_kernel<<<1, 1024, 0, as_stream(stream)>>>(row_loss, targets, rows, ignore_index, loss_out);
+  OMR_LAUNCHED();
+  return OMR_OK;
+}
+
+extern "C" int omr_ce_bwd(int dt, const void* logits, long long ld, const long long* targets, const float* row_lse,
+                          const float* loss_out, const float* gscale, void* dlogits, long long rows, int V,
+                          long long ignore_index, omr_stream_t stream) {
+  if (rows <= 0) return OMR_OK;
+  OMR_DISPATCH_DT(dt, T, (ce_bwd_kernel<T><<<(unsigned)rows, 256, 0, as_stream(stream)>>>(
+                             (const T*)logits, ld, targets, row_lse, loss_out, gscale, (T*)dlogits, V, ignore_index)));
+  OMR_LAUNCHED();
+  return OMR_OK;
+}
+
+extern "C" int omr_adam_tick(int* step, omr_stream_t stream) {
+  adam_tick_kernel<<<1, 1, 0, as_stream(stream)>>>(step);
+  OMR_LAUNCHED();
+  return OMR_OK;
+}
+
+extern "C" int omr_adam_step(const omr_adam_entry* table, int n_tensors, long long max_n, const int* step, double lr,
+                             double beta1, double beta2, double eps, double grad_scale, omr_stream_t stream) {
+  if (n_tensors <= 0) return OMR_OK;
+  long long bx = cdiv(max_n, 256 * 4);
+  if (bx < 1) bx = 1;
+  if (bx > 64) bx = 64;
+  dim3 grid((unsigned)bx, (unsigned)n_tensors);
+  adam_kernel<<<grid, 256, 0, as_stream(stream)>>>(table, step, lr, beta1, beta2, eps, grad_scale);
+  OMR_LAUNCHED();
+  return OMR_OK;
+}

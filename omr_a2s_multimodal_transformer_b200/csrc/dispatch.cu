@@ -1,0 +1,99 @@
+// dispatch.cu -- C-ABI entry points that choose between the tcgen05/TMA kernels (bf16, eligible
+// shapes) and the exact-fp32 CUDA-core kernels.  There is no CPU fallback anywhere.
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "kernels.h"
+
+static int g_tc_enabled = -1;
+static bool tc_enabled() {
+  if (g_tc_enabled < 0) {
+    const char* e = getenv("OMR_FORCE_SIMT");
+    g_tc_enabled = (e && e[0] == '1') ? 0 : 1;
+  }
+  return g_tc_enabled == 1;
+}
+extern "C" int omr_tensor_core_path_enabled(void) { return tc_enabled() ? 1 : 0; }
+extern "C" void omr_set_tensor_core_path(int enabled) { g_tc_enabled = enabled ? 1 : 0; }
+
+extern "C" int omr_gemm(int in_dt, int out_dt, int transA, int transB, int M, int N, int K, const void* A,
+                        long long lda, long long strideA, const void* B, long long ldb, long long strideB, void* C,
+                        long long ldc, long long strideC, int batch, const float* bias, int bias_mode, int relu,
+                        int accumulate, omr_stream_t stream) {
+  OMR_REQUIRE(M >= 0 && N >= 0 && K >= 0 && batch >= 0, "omr_gemm: negative dimension");
+  if (M == 0 || N == 0 || batch == 0) return OMR_OK;
+  cudaStream_t st = as_stream(stream);
+  if (tc_enabled() && in_dt == OMR_BF16) {
+    int rc = omr_gemm_tc(out_dt, transA, transB, M, N, K, A, lda, strideA, B, ldb, strideB, C, ldc, strideC, batch, bias,
+                         bias_mode, relu, accumulate, st);
+    if (rc != OMR_TC_NOT_ELIGIBLE) return rc;
+  }
+  return omr_gemm_simt(in_dt, out_dt, transA, transB, M, N, K, A, lda, strideA, B, ldb, strideB, C, ldc, strideC, batch,
+                       bias, bias_mode, relu, accumulate, st);
+}
+
+extern "C" int omr_conv3x3_fwd(int dt, const void* x, const void* w, const float* bias, void* y, int N, int H, int W,
+                               int Ci, int Co, int sh, int sw, int relu, omr_stream_t stream) {
+  OMR_REQUIRE(N >= 0 && H > 0 && W > 0 && Ci > 0 && Co > 0 && sh > 0 && sw > 0, "omr_conv3x3_fwd: bad shape");
+  cudaStream_t st = as_stream(stream);
+  if (tc_enabled() && dt == OMR_BF16) {
+    int rc = omr_conv3x3_fwd_tc(x, w, bias, y, N, H, W, Ci, Co, sh, sw, relu, st);
+    if (rc != OMR_TC_NOT_ELIGIBLE) return rc;
+  }
+  return omr_conv3x3_fwd_simt(dt, x, w, bias, y, N, H, W, Ci, Co, sh, sw, relu, st);
+}
+
+extern "C" int omr_conv3x3_dgrad(int dt, const void* dy, const void* wT, void* dx, int N, int H, int W, int Ci, int Co,
+                                 int sh, int sw, omr_stream_t stream) {
+  OMR_REQUIRE(N >= 0 && H > 0 && W > 0 && Ci > 0 && Co > 0 && sh > 0 && sw > 0, "omr_conv3x3_dgrad: bad shape");
+  cudaStream_t st = as_stream(stream);
+  if (tc_enabled() && dt == OMR_BF16) {
+    int rc = omr_conv3x3_dgrad_tc(dy, wT, dx, N, H, W, Ci, Co, sh, sw, st);
+    if (rc != OMR_TC_NOT_ELIGIBLE) return rc;
+  }
+  return omr_conv3x3_dgrad_simt(dt, dy, wT, dx, N, H, W, Ci, Co, sh, sw, st);
+}
+
+extern "C" int omr_conv3x3_wgrad(int dt, const void* x, const void* dy, float* dw, float* db, int N, int H, int W,
+                                 int Ci, int Co, int sh, int sw, int accumulate, omr_stream_t stream) {
+  OMR_REQUIRE(N >= 0 && H > 0 && W > 0 && Ci > 0 && Co > 0 && sh > 0 && sw > 0, "omr_conv3x3_wgrad: bad shape");
+  cudaStream_t st = as_stream(stream);
+  int Ho = (H + sh - 1) / sh, Wo = (W + sw - 1) / sw;
+  if (db) {
+    int rc = omr_colsum(dt, dy, (long long)N * Ho * Wo, Co, Co, db, accumulate, stream);
+    if (rc) return rc;
+  }
+  if (tc_enabled() && dt == OMR_BF16) {
+    int rc = omr_conv3x3_wgrad_tc(x, dy, dw, N, H, W, Ci, Co, sh, sw, accumulate, st);
+    if (rc != OMR_TC_NOT_ELIGIBLE) return rc;
+  }
+  return omr_conv3x3_wgrad_simt(dt, x, dy, dw, N, H, W, Ci, Co, sh, sw, accumulate, st);
+}
+
+extern "C" int omr_attn_fwd(int dt, const void* q, long long q_bs, long long q_rs, const void* k, long long k_bs,
+                            long long k_rs, const void* v, long long v_bs, long long v_rs, void* o, long long o_bs,
+                            long long o_rs, float* lse, const float* key_bias, int B, int H, int Tq, int Tk, int hd,
+                            float scale, int causal, int window, const int* q_len, const int* kv_len, int quirk_mod,
+                            omr_stream_t stream) {
+  cudaStream_t st = as_stream(stream);
+  if (tc_enabled() && dt == OMR_BF16) {
+    int rc = omr_attn_fwd_tc(q, q_bs, q_rs, k, k_bs, k_rs, v, v_bs, v_rs, o, o_bs, o_rs, lse, key_bias, B, H, Tq, Tk, hd,
+                             scale, causal, window, q_len, kv_len, quirk_mod, st);
+    if (rc != OMR_TC_NOT_ELIGIBLE) return rc;
+  }
+  return omr_attn_fwd_simt(dt, q, q_bs, q_rs, k, k_bs, k_rs, v, v_bs, v_rs, o, o_bs, o_rs, lse, key_bias, B, H, Tq, Tk,
+                           hd, scale, causal, window, q_len, kv_len, quirk_mod, st);
+}
+
+extern "C" int omr_attn_bwd(int dt, const void* q, long long q_bs, long long q_rs, const void* k, long long k_bs,
+                            long long k_rs, const void* v, long long v_bs, long long v_rs, const void* o,
+                            long long o_bs, long long o_rs, const void* dout, long long do_bs, long long do_rs,
+                            const float* lse, void* dq, long long dq_bs, long long dq_rs, void* dk, long long dk_bs,
+                            long long dk_rs, void* dv, long long dv_bs, long long dv_rs, float* delta_ws,
+                            const float* key_bias, int B, int H, int Tq, int Tk, int hd, float scale, int causal,
+                            int window, const int* q_len, const int* kv_len, int quirk_mod, omr_stream_t stream) {
+  cudaStream_t st = as_stream(stream);
+  return omr_attn_bwd_simt(dt, q, q_bs, q_rs, k, k_bs, k_rs, v, v_bs, v_rs, o, o_bs, o_rs, dout, do_bs, do_rs, lse, dq,
+                           dq_bs, dq_rs, dk, dk_bs, dk_rs, dv, dv_bs, dv_rs, delta_ws, key_bias, B, H, Tq, Tk, hd, scale,
+                           causal, window, q_len, kv_len, quirk_mod, st);
+}
