@@ -57,6 +57,12 @@ int omr_cast(int src_dt, int dst_dt, const void* src, void* dst, long long n, om
 int omr_relu_bwd(int dt, const void* y, const void* dy, void* dx, long long n, omr_stream_t stream);
 /* out = a + b (residual add of the DSC blocks, encoder.py:287-289) */
 int omr_add(int dt, const void* a, const void* b, void* out, long long n, omr_stream_t stream);
+/* nn.Dropout / nn.Dropout2d (MixDropout, encoder.py:87-104; decoder dropouts p=0.1):
+ * y[i] = keep(seed, key(i)) ? x[i] / (1-p) : 0 with key(i) = i (element-wise) or, when channelwise,
+ * (i / per_sample) * C + (i % C) (one decision per (sample, channel) of an NHWC tensor).
+ * The mask is a pure function of (seed, key): calling it again on dy is the backward. */
+int omr_dropout(int dt, const void* x, void* y, long long n, int C, long long per_sample, float p, long long seed,
+                int channelwise, omr_stream_t stream);
 /* Conv2d weight [Co,Ci,3,3] fp32 -> kernel layout in dt (tap-major, channels innermost):
  * transpose == 0: [Co,3,3,Ci] (forward operand); transpose == 1: [Ci,3,3,Co] (data-gradient operand) */
 int omr_pack_conv_weight(int dt, const float* w, void* out, int Co, int Ci, int transpose, omr_stream_t stream);
@@ -112,9 +118,11 @@ int omr_key_bias_from_tokens(float* bias, const long long* tokens, long long n, 
 
 /* ---- decoder ------------------------------------------------------------------------- */
 /* nn.Embedding + PositionalEncoding1D (decoder.py:73-82,124,29-32):
- * out[b,t,:] = table[tok[b,t],:] + pe[pos0 + t,:] ; table in dt, pe fp32 [max_len,D] */
+ * out[b,t,:] = table[tok[b,t],:] + pe[pos0 + t,:] ; table in dt, pe fp32 [max_len,D].
+ * pos_dev (device int32 scalar, may be NULL) overrides pos0 so that a decode step can be replayed
+ * from a CUDA graph; the same convention holds for omr_kv_append / omr_attn_decode / omr_argmax_step. */
 int omr_embed_pe_fwd(int dt, const long long* tokens, const void* table, const float* pe, void* out, int B, int T, int D,
-                     int pos0, omr_stream_t stream);
+                     int pos0, const int* pos_dev, omr_stream_t stream);
 /* dtable[tok,:] += dout[b,t,:] for tok != padding_idx ; dtable fp32 [V,D] (must be pre-zeroed or accumulated) */
 int omr_embed_bwd(int dt, const long long* tokens, const void* dout, float* dtable, long long rows, int D,
                   long long padding_idx, omr_stream_t stream);
@@ -215,21 +223,22 @@ int omr_adam_step(const omr_adam_entry* table, int n_tensors, long long max_n, c
  * emit `eos_id` become finished.  out_tokens[b, step] = tok when out_tokens != NULL. */
 int omr_argmax_step(int dt, const void* logits, long long ld, int B, int V, long long* tok, float* val, int* finished,
                     long long eos_id, long long pad_id, long long* out_tokens, float* out_vals, int out_ld, int step,
-                    omr_stream_t stream);
+                    const int* step_dev, omr_stream_t stream);
 /* copy the new key/value rows of a decode step into the KV cache:
  * cache[b, pos, :] = src[b, :] for `width` elements ; src row stride src_rs, cache [B, Tmax, width] */
 int omr_kv_append(int dt, const void* src, long long src_rs, void* cache, int B, int Tmax, int width, int pos,
-                  omr_stream_t stream);
+                  const int* pos_dev, omr_stream_t stream);
 /* Single-query attention over a KV cache (one decode step; the KV-cached equivalent of re-running
  * the decoder on the growing prefix, model.py:184-186): for every (b,h)
  *   o[b, h*hd:] = softmax(scale * q[b,h] . K[b, j, h] + key_bias[b, j]) V[b, j, h],  j in [j_lo, Tk)
  * with j_lo = max(0, Tk-1-window) when window > 0 (decoder.py:191-217), else 0.
  * q element (b,h,d) at q[b*q_bs + h*hd + d]; K element (b,j,h,d) at k[b*k_bs + j*k_rs + h*hd + d].
+ * pos_dev != NULL: the live key count is *pos_dev + 1 and Tk only bounds it (graph replay).
  * ws: fp32 scratch, at least B*H*nsplit*(hd+2) floats with nsplit <= max(1, ceil(592/(B*H))). */
 int omr_attn_decode(int dt, const void* q, long long q_bs, const void* k, long long k_bs, long long k_rs,
                     const void* v, long long v_bs, long long v_rs, void* o, long long o_bs, const float* key_bias,
                     long long kb_bs, float* ws, long long ws_floats, int B, int H, int Tk, int hd, float scale,
-                    int window, omr_stream_t stream);
+                    int window, const int* pos_dev, omr_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,20 @@
+"""omr_a2s_multimodal_transformer_b200 -- B200-native (sm_100a) implementation of the hot path of
+mariaalfaroc/omr_a2s_multimodal_transformer: CNN image/spectrogram encoders -> 2-D PE + fusion ->
+transformer decoder -> vocabulary projection / cross-entropy -> batched greedy decoding.
+
+The Python classes mirror the reference's ``src/transformer`` surface; every operator runs in
+``libomr_b200.so`` (hand-written CUDA, C ABI in ``include/omr_b200.h``).  There is no CPU path.
+"""
+from .decoder import Decoder, PositionalEncoding1D
+from .encoder import HEIGHT_REDUCTION, WIDTH_REDUCTION, ConvBlock, DepthSepConv2D, DSCBlock, Encoder, MixDropout
+from .greedy import BatchedGreedyDecoder
+from .model import (EOS_TOKEN, NUM_CHANNELS, SOS_TOKEN, CrossAttention, MultimodalTransformer, PositionalEncoding2D,
+                    Transformer)
+from .optim import FusedAdam
+from .params import GradArena
+
+__all__ = [
+    "Decoder", "PositionalEncoding1D", "Encoder", "ConvBlock", "DSCBlock", "DepthSepConv2D", "MixDropout",
+    "PositionalEncoding2D", "CrossAttention", "Transformer", "MultimodalTransformer", "BatchedGreedyDecoder",
+    "FusedAdam", "GradArena", "HEIGHT_REDUCTION", "WIDTH_REDUCTION", "SOS_TOKEN", "EOS_TOKEN", "NUM_CHANNELS",
+]

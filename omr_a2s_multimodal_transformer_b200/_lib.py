@@ -20,6 +20,7 @@ _SIGS = {
     "omr_cast": "iippqp",
     "omr_relu_bwd": "ipppqp",
     "omr_add": "ipppqp",
+    "omr_dropout": "ippqiqfqip",
     "omr_pack_conv_weight": "ippiiip",
     "omr_pack_dw_weight": "ippip",
     "omr_conv3x3_fwd": "ippppiiiiiiiip",
@@ -34,7 +35,7 @@ _SIGS = {
     "omr_copy_rows": "ippiiiiip",
     "omr_key_bias_from_lengths": "ppiiiifp",
     "omr_key_bias_from_tokens": "ppqqfp",
-    "omr_embed_pe_fwd": "ippppiiiip",
+    "omr_embed_pe_fwd": "ippppiiiipp",
     "omr_embed_bwd": "ipppqiqp",
     "omr_gemm": "iiiiiiipqqpqqpqqipiiip",
     "omr_colsum": "ipqiqpip",
@@ -47,9 +48,9 @@ _SIGS = {
     "omr_ce_bwd": "ipqpppppqiqp",
     "omr_adam_tick": "pp",
     "omr_adam_step": "piqpdddddp",
-    "omr_argmax_step": "ipqiipppqqppiip",
-    "omr_kv_append": "ipqpiiiip",
-    "omr_attn_decode": "ipqpqqpqqpqpqpqiiiifip",
+    "omr_argmax_step": "ipqiipppqqppiipp",
+    "omr_kv_append": "ipqpiiiipp",
+    "omr_attn_decode": "ipqpqqpqqpqpqpqiiiifipp",
 }
 _CT = {"i": c_int, "q": c_longlong, "p": c_void_p, "f": c_float, "d": c_double}
 

@@ -222,7 +222,9 @@ extern "C" int omr_key_bias_from_tokens(float* bias, const long long* tokens, lo
 // ---- embedding + PE-1D --------------------------------------------------------------------------
 template <typename T>
 __global__ void embed_pe_kernel(const long long* __restrict__ tok, const T* __restrict__ table,
-                                const float* __restrict__ pe, T* __restrict__ out, int B, int Tn, int D, int pos0) {
+                                const float* __restrict__ pe, T* __restrict__ out, int B, int Tn, int D, int pos0,
+                                const int* __restrict__ pos_dev) {
+  if (pos_dev) pos0 = *pos_dev;
   long long n4 = (long long)B * Tn * (D / 4);
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long stride = (long long)gridDim.x * blockDim.x;
@@ -241,12 +243,12 @@ __global__ void embed_pe_kernel(const long long* __restrict__ tok, const T* __re
   }
 }
 extern "C" int omr_embed_pe_fwd(int dt, const long long* tokens, const void* table, const float* pe, void* out, int B,
-                                int T_, int D, int pos0, omr_stream_t stream) {
+                                int T_, int D, int pos0, const int* pos_dev, omr_stream_t stream) {
   OMR_REQUIRE(D % 4 == 0, "omr_embed_pe_fwd: D must be a multiple of 4");
   long long n4 = (long long)B * T_ * (D / 4);
   if (n4 <= 0) return OMR_OK;
   OMR_DISPATCH_DT(dt, T, (embed_pe_kernel<T><<<grid_for(n4, 256, 1), 256, 0, as_stream(stream)>>>(
-                             tokens, (const T*)table, pe, (T*)out, B, T_, D, pos0)));
+                             tokens, (const T*)table, pe, (T*)out, B, T_, D, pos0, pos_dev)));
   OMR_LAUNCHED();
   return OMR_OK;
 }
@@ -303,6 +305,35 @@ extern "C" int omr_colsum(int dt, const void* x, long long rows, int N, long lon
   dim3 grid((unsigned)cdiv(N, 32), (unsigned)(rows >= 8 * 64 ? (cdiv(rows, 8 * 16) > 512 ? 512 : cdiv(rows, 8 * 16)) : 1));
   dim3 block(32, 8);
   OMR_DISPATCH_DT(dt, T, (colsum_kernel<T><<<grid, block, 0, st>>>((const T*)x, rows, N, ld, out)));
+  OMR_LAUNCHED();
+  return OMR_OK;
+}
+
+// ---- dropout (recomputable from the seed: the same call applied to dy is the backward) -------------
+__device__ __forceinline__ uint32_t mix32(uint32_t a, uint32_t b) {
+  uint32_t h = a * 0x9E3779B1u ^ (b + 0x7F4A7C15u + (a << 6) + (a >> 2));
+  h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
+  return h;
+}
+template <typename T>
+__global__ void dropout_kernel(const T* __restrict__ x, T* __restrict__ y, long long n, int C, long long per_sample,
+                               float p, float scale, uint32_t seed, int channelwise) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    long long key = channelwise ? (i / per_sample) * C + (i % C) : i;
+    uint32_t h = mix32(seed ^ (uint32_t)(key >> 32) * 0x632BE5ABu, (uint32_t)key);
+    float u = (h >> 8) * (1.0f / 16777216.0f);
+    y[i] = u < p ? from_f<T>(0.f) : from_f<T>(to_f(x[i]) * scale);
+  }
+}
+extern "C" int omr_dropout(int dt, const void* x, void* y, long long n, int C, long long per_sample, float p,
+                           long long seed, int channelwise, omr_stream_t stream) {
+  OMR_REQUIRE(p >= 0.f && p < 1.f, "omr_dropout: p must be in [0,1) (got %f)", p);
+  OMR_REQUIRE(C > 0 && per_sample > 0, "omr_dropout: bad channel geometry");
+  if (n <= 0) return OMR_OK;
+  OMR_DISPATCH_DT(dt, T, (dropout_kernel<T><<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(
+                             (const T*)x, (T*)y, n, C, per_sample, p, 1.f / (1.f - p), (uint32_t)seed, channelwise)));
   OMR_LAUNCHED();
   return OMR_OK;
 }

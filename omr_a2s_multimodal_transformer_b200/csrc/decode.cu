@@ -12,7 +12,8 @@ struct DecArgs {
   long long q_bs, k_bs, k_rs, v_bs, v_rs, o_bs;
   const float* key_bias; long long kb_bs;
   float* ws_o; float* ws_ml;
-  int B, H, Tk, j_lo, chunk, nsplit;
+  int B, H, Tk, window, chunk, nsplit;
+  const int* pos_dev;  // when non-NULL the live key count is *pos_dev + 1 (Tk is then the sizing bound)
   float scale;
 };
 
@@ -36,10 +37,15 @@ __global__ void __launch_bounds__(128) attn_decode_partial_kernel(DecArgs a) {
   __shared__ float red[33];
   const int bh = blockIdx.x, b = bh / a.H, h = bh % a.H, sp = blockIdx.y;
   const int tid = threadIdx.x;
-  const int j0 = a.j_lo + sp * a.chunk;
+  int tk = a.pos_dev ? (*a.pos_dev + 1) : a.Tk;
+  if (tk > a.Tk) tk = a.Tk;
+  int j_lo = 0;
+  if (a.window > 0 && tk - 1 - a.window > 0) j_lo = tk - 1 - a.window;  // query position tk-1 sees keys >= tk-1-window
+  int j0 = sp * a.chunk;
   int j1 = j0 + a.chunk;
-  if (j1 > a.Tk) j1 = a.Tk;
-  const int n = j1 - j0;
+  if (j0 < j_lo) j0 = j_lo;
+  if (j1 > tk) j1 = tk;
+  const int n = j1 > j0 ? j1 - j0 : 0;
   const T* qp = (const T*)a.q + (long long)b * a.q_bs + h * HD;
   const T* kp = (const T*)a.k + (long long)b * a.k_bs + h * HD;
   const T* vp = (const T*)a.v + (long long)b * a.v_bs + h * HD;
@@ -102,7 +108,9 @@ __global__ void attn_decode_combine_kernel(DecArgs a) {
 
 template <typename T>
 __global__ void kv_append_kernel(const T* __restrict__ src, long long src_rs, T* __restrict__ cache, int B, int Tmax,
-                                 int width, int pos) {
+                                 int width, int pos, const int* __restrict__ pos_dev) {
+  if (pos_dev) pos = *pos_dev;
+  if (pos < 0 || pos >= Tmax) return;
   long long n = (long long)B * width;
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) {
@@ -116,7 +124,9 @@ __global__ void __launch_bounds__(256) argmax_step_kernel(const T* __restrict__ 
                                                           long long* __restrict__ tok, float* __restrict__ val,
                                                           int* __restrict__ finished, long long eos_id,
                                                           long long pad_id, long long* __restrict__ out_tokens,
-                                                          float* __restrict__ out_vals, int out_ld, int step) {
+                                                          float* __restrict__ out_vals, int out_ld, int step,
+                                                          const int* __restrict__ step_dev) {
+  if (step_dev) step = *step_dev;
   __shared__ float sv[256];
   __shared__ int si[256];
   const int b = blockIdx.x;
@@ -148,8 +158,8 @@ __global__ void __launch_bounds__(256) argmax_step_kernel(const T* __restrict__ 
     }
     tok[b] = t;
     if (val) val[b] = v;
-    if (out_tokens) out_tokens[(long long)b * out_ld + step] = t;
-    if (out_vals) out_vals[(long long)b * out_ld + step] = v;
+    if (out_tokens && step < out_ld) out_tokens[(long long)b * out_ld + step] = t;
+    if (out_vals && step < out_ld) out_vals[(long long)b * out_ld + step] = v;
   }
 }
 
@@ -158,34 +168,36 @@ __global__ void __launch_bounds__(256) argmax_step_kernel(const T* __restrict__ 
 extern "C" int omr_attn_decode(int dt, const void* q, long long q_bs, const void* k, long long k_bs, long long k_rs,
                                const void* v, long long v_bs, long long v_rs, void* o, long long o_bs,
                                const float* key_bias, long long kb_bs, float* ws, long long ws_floats, int B, int H,
-                               int Tk, int hd, float scale, int window, omr_stream_t stream) {
+                               int Tk, int hd, float scale, int window, const int* pos_dev, omr_stream_t stream) {
   OMR_REQUIRE(hd == HD, "omr_attn_decode: head_dim must be 64 (got %d)", hd);
   OMR_REQUIRE(((q_bs | k_bs | k_rs | v_bs | v_rs | o_bs) & 3) == 0, "omr_attn_decode: strides must be multiples of 4");
   if (B <= 0 || H <= 0 || Tk <= 0) return OMR_OK;
-  int j_lo = 0;
-  if (window > 0 && Tk - 1 - window > 0) j_lo = Tk - 1 - window;  // query position Tk-1 sees keys >= Tk-1-window
-  int n = Tk - j_lo;
   long long bh = (long long)B * H;
   int nsplit = (int)cdiv(148LL * 4, bh);
-  int max_split = (int)cdiv(n, 128);
+  int max_split = (int)cdiv(Tk, 128);
   if (nsplit > max_split) nsplit = max_split;
   if (nsplit < 1) nsplit = 1;
-  int chunk = (int)cdiv(n, nsplit);
-  nsplit = (int)cdiv(n, chunk);
+  int chunk = (int)cdiv(Tk, nsplit);
+  nsplit = (int)cdiv(Tk, chunk);
   OMR_REQUIRE(ws_floats >= bh * nsplit * (HD + 2), "omr_attn_decode: workspace too small (%lld < %lld floats)", ws_floats,
               bh * nsplit * (HD + 2));
   DecArgs a{};
   a.q = q; a.k = k; a.v = v; a.o = o; a.q_bs = q_bs; a.k_bs = k_bs; a.k_rs = k_rs; a.v_bs = v_bs; a.v_rs = v_rs;
   a.o_bs = o_bs; a.key_bias = key_bias; a.kb_bs = kb_bs; a.ws_o = ws; a.ws_ml = ws + bh * nsplit * HD;
-  a.B = B; a.H = H; a.Tk = Tk; a.j_lo = j_lo; a.chunk = chunk; a.nsplit = nsplit; a.scale = scale;
+  a.B = B; a.H = H; a.Tk = Tk; a.window = window; a.chunk = chunk; a.nsplit = nsplit; a.scale = scale;
+  a.pos_dev = pos_dev;
   size_t smem = sizeof(float) * (chunk + 2 * HD);
   OMR_REQUIRE(smem <= 200 * 1024, "omr_attn_decode: chunk too large");
   cudaStream_t st = as_stream(stream);
   dim3 grid((unsigned)bh, (unsigned)nsplit);
   OMR_DISPATCH_DT(dt, T, {
     if (smem > 48 * 1024) {
-      OMR_CUDA(cudaFuncSetAttribute(attn_decode_partial_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    200 * 1024));
+      static bool done = false;
+      if (!done) {
+        OMR_CUDA(cudaFuncSetAttribute(attn_decode_partial_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      200 * 1024));
+        done = true;
+      }
     }
     attn_decode_partial_kernel<T><<<grid, 128, smem, st>>>(a);
     omr_count_launch();
@@ -196,24 +208,24 @@ extern "C" int omr_attn_decode(int dt, const void* q, long long q_bs, const void
 }
 
 extern "C" int omr_kv_append(int dt, const void* src, long long src_rs, void* cache, int B, int Tmax, int width, int pos,
-                             omr_stream_t stream) {
-  OMR_REQUIRE(pos >= 0 && pos < Tmax, "omr_kv_append: position %d outside the cache (Tmax %d)", pos, Tmax);
+                             const int* pos_dev, omr_stream_t stream) {
+  OMR_REQUIRE(pos_dev || (pos >= 0 && pos < Tmax), "omr_kv_append: position %d outside the cache (Tmax %d)", pos, Tmax);
   long long n = (long long)B * width;
   if (n <= 0) return OMR_OK;
   OMR_DISPATCH_DT(dt, T, (kv_append_kernel<T><<<(unsigned)cdiv(n, 256), 256, 0, as_stream(stream)>>>(
-                             (const T*)src, src_rs, (T*)cache, B, Tmax, width, pos)));
+                             (const T*)src, src_rs, (T*)cache, B, Tmax, width, pos, pos_dev)));
   OMR_LAUNCHED();
   return OMR_OK;
 }
 
 extern "C" int omr_argmax_step(int dt, const void* logits, long long ld, int B, int V, long long* tok, float* val,
                                int* finished, long long eos_id, long long pad_id, long long* out_tokens,
-                               float* out_vals, int out_ld, int step, omr_stream_t stream) {
+                               float* out_vals, int out_ld, int step, const int* step_dev, omr_stream_t stream) {
   if (B <= 0) return OMR_OK;
   OMR_REQUIRE(V > 0, "omr_argmax_step: empty vocabulary");
   OMR_DISPATCH_DT(dt, T, (argmax_step_kernel<T><<<(unsigned)B, 256, 0, as_stream(stream)>>>(
                              (const T*)logits, ld, V, tok, val, finished, eos_id, pad_id, out_tokens, out_vals, out_ld,
-                             step)));
+                             step, step_dev)));
   OMR_LAUNCHED();
   return OMR_OK;
 }

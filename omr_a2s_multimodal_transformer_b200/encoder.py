@@ -1,0 +1,303 @@
+"""Convolutional image / spectrogram encoder on hand-written sm_100a kernels.
+
+Drop-in for the reference ``src/transformer/encoder.py`` (same class names, constructor arguments,
+state-dict keys and output semantics):
+
+* ``Encoder(in_channels, dropout=0.5)``: 5 ``ConvBlock``s (1->16->32->64->128->128, conv3 strides
+  (1,1),(2,2),(2,2),(2,2),(2,1)) + 4 ``DSCBlock``s with the conditional residual
+  (reference encoder.py:241-291); output ``[B,256,ceil(H/16),ceil(W/8)]``.
+* Activations are kept NHWC inside (the implicit-GEMM layout); the returned tensor has the reference's
+  NCHW *shape* with channels-last strides, so ``pos_2d(x).flatten(2).permute(0,2,1).contiguous()``
+  (reference model.py:145-147) is a zero-copy view chain.
+* Backward is composed explicitly from the data-/weight-gradient kernels (one autograd node per
+  encoder); parameter gradients are accumulated by the kernels straight into ``param.grad``.
+"""
+from __future__ import annotations
+
+import random
+from typing import Callable, List, Optional, Tuple, Union
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .params import ConvParams, WeightCache, grad_buf, resolve_dtype
+
+HEIGHT_REDUCTION = 16
+WIDTH_REDUCTION = 8
+IN_EPS = 1e-3  # nn.InstanceNorm2d(eps=0.001) at reference encoder.py:151-156, 210-215
+
+Tape = Optional[List[Callable[[torch.Tensor], Optional[torch.Tensor]]]]
+
+
+class _Ctx:
+    """Per-call execution context: compute dtype, weight cache, backward tape, training flags."""
+
+    def __init__(self, dtype: torch.dtype, cache: WeightCache, tape: Tape, training: bool, dropout: "DropoutPlan"):
+        self.dtype, self.cache, self.tape, self.training, self.dropout = dtype, cache, tape, training, dropout
+
+
+class DropoutPlan:
+    """Train-time MixDropout decisions (reference encoder.py:87-104,160-179): ONE position per block
+    (``random.randint(1, 3)``) and, there, element-wise Dropout(p) or channel-wise Dropout2d(p/2) with
+    probability 1/2 each.  The Python RNG draws are made even in eval mode, like the reference."""
+
+    def __init__(self, p: float, seed_fn: Callable[[], int]):
+        self.p, self.seed_fn = p, seed_fn
+
+    def draw(self) -> int:
+        return random.randint(1, 3)
+
+    def kind(self) -> bool:
+        return random.random() < 0.5
+
+
+def _maybe_dropout(x: torch.Tensor, c: _Ctx, here: bool) -> torch.Tensor:
+    if not (here and c.training and c.dropout.p > 0.0):
+        return x
+    elementwise = c.dropout.kind()
+    p = c.dropout.p if elementwise else c.dropout.p / 2
+    seed = c.dropout.seed_fn()
+    y = ops.dropout(x, p, seed, channelwise=not elementwise)
+    if c.tape is not None:
+        c.tape.append(lambda dy: ops.dropout(dy, p, seed, channelwise=not elementwise, inplace=True))
+    return y
+
+
+def _conv_step(x: torch.Tensor, cp: ConvParams, stride: Tuple[int, int], relu: bool, c: _Ctx, need_dx: bool) -> torch.Tensor:
+    wp = c.cache.get(cp.weight, "conv", c.dtype)
+    y = ops.conv3x3_fwd(x, wp, cp.bias, stride, relu)
+    if c.tape is not None:
+        in_hw = (x.shape[1], x.shape[2])
+
+        def bwd(dy: torch.Tensor) -> Optional[torch.Tensor]:
+            dz = ops.relu_bwd(y, dy, inplace=True) if relu else dy
+            if cp.weight.requires_grad:
+                ops.conv3x3_wgrad(x, dz, grad_buf(cp.weight), grad_buf(cp.bias), stride, accumulate=True)
+            if not need_dx:
+                return None
+            return ops.conv3x3_dgrad(dz, c.cache.get(cp.weight, "convT", c.dtype), in_hw, stride)
+
+        c.tape.append(bwd)
+    return y
+
+
+def _instnorm_step(x: torch.Tensor, c: _Ctx) -> torch.Tensor:
+    y, stats = ops.instnorm_fwd(x, IN_EPS)
+    if c.tape is not None:
+        c.tape.append(lambda dy: ops.instnorm_bwd(dy, x, stats))
+    return y
+
+
+def _dw_step(x: torch.Tensor, cp: ConvParams, c: _Ctx) -> torch.Tensor:
+    wp = c.cache.get(cp.weight, "dw", c.dtype)
+    y = ops.dwconv3x3_fwd(x, wp, cp.bias)
+    if c.tape is not None:
+
+        def bwd(dy: torch.Tensor) -> torch.Tensor:
+            if cp.weight.requires_grad:
+                ops.dwconv3x3_wgrad(x, dy, grad_buf(cp.weight), grad_buf(cp.bias), accumulate=True)
+            return ops.dwconv3x3_dgrad(dy, wp)
+
+        c.tape.append(bwd)
+    return y
+
+
+def _pw_step(x: torch.Tensor, cp: ConvParams, relu: bool, c: _Ctx) -> torch.Tensor:
+    n, h, w, ci = x.shape
+    co = cp.out_channels
+    wm = c.cache.get(cp.weight, "mat", c.dtype)
+    x2 = x.view(-1, ci)
+    y2 = ops.linear_fwd(x2, wm, cp.bias, relu=relu)
+    if c.tape is not None:
+
+        def bwd(dy: torch.Tensor) -> torch.Tensor:
+            dz = dy.view(-1, co)
+            if relu:
+                dz = ops.relu_bwd(y2, dz, inplace=True)
+            if cp.weight.requires_grad:
+                ops.linear_wgrad(x2, dz, grad_buf(cp.weight).view(co, ci), grad_buf(cp.bias), accumulate=True)
+            return ops.linear_dgrad(dz, wm).view(n, h, w, ci)
+
+        c.tape.append(bwd)
+    return y2.view(n, h, w, co)
+
+
+class DepthSepConv2D(nn.Module):
+    """Depthwise 3x3 (pad 1, stride 1) + pointwise 1x1 (reference encoder.py:12-84; the only
+    configuration the reference instantiates is kernel (3,3), stride (1,1), no inner activation)."""
+
+    def __init__(self, in_channels: int, out_channels: int, kernel_size: Tuple[int, int] = (3, 3), activation=None,
+                 padding: Union[bool, Tuple[int, int]] = True, stride: Union[int, Tuple[int, int]] = (1, 1),
+                 dilation: Union[int, Tuple[int, int]] = (1, 1)):
+        super().__init__()
+        if tuple(kernel_size) != (3, 3) or tuple(_pair(stride)) != (1, 1) or tuple(_pair(dilation)) != (1, 1) or activation:
+            raise NotImplementedError("DepthSepConv2D kernels cover the reference's configuration: 3x3, stride 1, dilation 1")
+        self.depth_conv = ConvParams(in_channels, in_channels, (3, 3), groups=in_channels)
+        self.point_conv = ConvParams(in_channels, out_channels, (1, 1))
+
+    def _run(self, x: torch.Tensor, relu: bool, c: _Ctx) -> torch.Tensor:
+        return _pw_step(_dw_step(x, self.depth_conv, c), self.point_conv, relu, c)
+
+
+def _pair(v):
+    return (v, v) if isinstance(v, int) else tuple(v)
+
+
+class MixDropout(nn.Module):
+    """Kept for surface compatibility (reference encoder.py:87-104); the decisions are drawn by
+    ``DropoutPlan`` and applied by the fused dropout kernel."""
+
+    def __init__(self, dropout_prob: float = 0.4, dropout_2d_prob: float = 0.2):
+        super().__init__()
+        self.dropout_prob, self.dropout_2d_prob = dropout_prob, dropout_2d_prob
+
+
+class ConvBlock(nn.Module):
+    """conv3x3+ReLU, conv3x3+ReLU, InstanceNorm, strided conv3x3+ReLU (reference encoder.py:107-181)."""
+
+    def __init__(self, in_c: int, out_c: int, stride=(1, 1), kernel: int = 3, activation=None, dropout: float = 0.5):
+        super().__init__()
+        if kernel != 3:
+            raise NotImplementedError("ConvBlock kernels cover the reference's configuration: kernel 3")
+        self.stride = _pair(stride)
+        self.conv1 = ConvParams(in_c, out_c, (3, 3))
+        self.conv2 = ConvParams(out_c, out_c, (3, 3))
+        self.conv3 = ConvParams(out_c, out_c, (3, 3))
+        self.dropout = MixDropout(dropout_prob=dropout, dropout_2d_prob=dropout / 2)
+
+    def _run(self, x: torch.Tensor, c: _Ctx, need_dx: bool) -> torch.Tensor:
+        pos = c.dropout.draw()
+        x = _conv_step(x, self.conv1, (1, 1), True, c, need_dx)
+        x = _maybe_dropout(x, c, pos == 1)
+        x = _conv_step(x, self.conv2, (1, 1), True, c, True)
+        x = _maybe_dropout(x, c, pos == 2)
+        x = _instnorm_step(x, c)
+        x = _conv_step(x, self.conv3, self.stride, True, c, True)
+        x = _maybe_dropout(x, c, pos == 3)
+        return x
+
+
+class DSCBlock(nn.Module):
+    """3x DepthSepConv2D, ReLU after the first two, InstanceNorm before the third
+    (reference encoder.py:184-238)."""
+
+    def __init__(self, in_c: int, out_c: int, stride=(2, 1), activation=None, dropout: float = 0.5):
+        super().__init__()
+        if _pair(stride) != (1, 1):
+            raise NotImplementedError("DSCBlock kernels cover the reference's configuration: stride (1,1)")
+        self.conv1 = DepthSepConv2D(in_c, out_c)
+        self.conv2 = DepthSepConv2D(out_c, out_c)
+        self.conv3 = DepthSepConv2D(out_c, out_c)
+        self.dropout = MixDropout(dropout_prob=dropout, dropout_2d_prob=dropout / 2)
+
+    def _run(self, x: torch.Tensor, c: _Ctx) -> torch.Tensor:
+        pos = c.dropout.draw()
+        x = self.conv1._run(x, True, c)
+        x = _maybe_dropout(x, c, pos == 1)
+        x = self.conv2._run(x, True, c)
+        x = _maybe_dropout(x, c, pos == 2)
+        x = _instnorm_step(x, c)
+        x = self.conv3._run(x, False, c)
+        x = _maybe_dropout(x, c, pos == 3)
+        return x
+
+
+class _EncoderFn(torch.autograd.Function):
+    """One autograd node for the whole encoder: forward records a tape of kernel-level backward
+    steps, backward replays it.  Parameter gradients are written by the kernels into ``param.grad``
+    (the parameters are listed as inputs only so that the node is part of the graph)."""
+
+    @staticmethod
+    def forward(ctx, x_nhwc: torch.Tensor, enc: "Encoder", dtype: torch.dtype, training: bool, *params):
+        tape: List = []
+        y = enc._run(x_nhwc, dtype, tape, training)
+        ctx.tape = tape
+        return y
+
+    @staticmethod
+    def backward(ctx, dy: torch.Tensor):
+        tape, ctx.tape = ctx.tape, None
+        if tape is None:
+            raise RuntimeError("encoder backward called twice (activations are released after the first pass)")
+        g: Optional[torch.Tensor] = dy.contiguous().clone()
+        while tape:
+            step = tape.pop()
+            g = step(g)
+        return (None, None, None, None) + tuple(None for _ in ctx.needs_input_grad[4:])
+
+
+class Encoder(nn.Module):
+    """Reference ``Encoder(in_channels, dropout=0.5)`` (encoder.py:241-291) on sm_100a kernels."""
+
+    def __init__(self, in_channels: int, dropout: float = 0.5, out_channels: int = 256):
+        super().__init__()
+        self.in_channels = in_channels
+        self.dropout_p = dropout
+        self.conv_blocks = nn.ModuleList(
+            [
+                ConvBlock(in_channels, 16, stride=(1, 1), dropout=dropout),
+                ConvBlock(16, 32, stride=(2, 2), dropout=dropout),
+                ConvBlock(32, 64, stride=(2, 2), dropout=dropout),
+                ConvBlock(64, 128, stride=(2, 2), dropout=dropout),
+                ConvBlock(128, 128, stride=(2, 1), dropout=dropout),
+            ]
+        )
+        self.dscblocks = nn.ModuleList(
+            [
+                DSCBlock(128, 128, stride=(1, 1), dropout=dropout),
+                DSCBlock(128, 128, stride=(1, 1), dropout=dropout),
+                DSCBlock(128, 128, stride=(1, 1), dropout=dropout),
+                DSCBlock(128, out_channels, stride=(1, 1), dropout=dropout),
+            ]
+        )
+        self.compute_dtype: Optional[torch.dtype] = None
+        self._wcache = WeightCache()
+        self._seed_state = 0x1234567
+
+    # -- plumbing ---------------------------------------------------------------------------------
+    def _next_seed(self) -> int:
+        self._seed_state = (self._seed_state * 6364136223846793005 + 1442695040888963407) & 0xFFFFFFFFFFFFFFFF
+        return (self._seed_state >> 17) & 0x7FFFFFFF
+
+    def _run(self, x: torch.Tensor, dtype: torch.dtype, tape: Tape, training: bool) -> torch.Tensor:
+        c = _Ctx(dtype, self._wcache, tape, training, DropoutPlan(self.dropout_p, self._next_seed))
+        for i, blk in enumerate(self.conv_blocks):
+            x = blk._run(x, c, need_dx=(i > 0))
+        for blk in self.dscblocks:
+            if tape is None:
+                xt = blk._run(x, c)
+                x = ops.add(x, xt) if x.shape == xt.shape else xt
+            else:
+                inner: List = []
+                ci = _Ctx(dtype, self._wcache, inner, training, c.dropout)
+                xt = blk._run(x, ci)
+                residual = x.shape == xt.shape
+
+                def bwd(dy: torch.Tensor, inner=inner, residual=residual) -> torch.Tensor:
+                    g = dy
+                    while inner:
+                        g = inner.pop()(g)
+                    return ops.add(g, dy) if residual else g
+
+                tape.append(bwd)
+                x = ops.add(x, xt) if residual else xt
+        return x
+
+    def forward_nhwc(self, x: torch.Tensor) -> torch.Tensor:
+        """x [B,C_in,H,W] float32 -> features [B,h,w,C_out] (NHWC, compute dtype)."""
+        ops._lib.require_cuda(x, "Encoder.forward")
+        dtype = resolve_dtype(self.compute_dtype)
+        b, cin, h, w = x.shape
+        if cin != self.in_channels:
+            raise RuntimeError(f"Encoder expects {self.in_channels} input channel(s), got {cin}")
+        x_nhwc = x.reshape(b, h, w, 1) if cin == 1 else x.permute(0, 2, 3, 1)
+        x_nhwc = ops.cast(x_nhwc.contiguous().float(), dtype)
+        params = [p for p in self.parameters()]
+        if torch.is_grad_enabled() and any(p.requires_grad for p in params):
+            return _EncoderFn.apply(x_nhwc, self, dtype, self.training, *params)
+        return self._run(x_nhwc, dtype, None, self.training)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        """Reference semantics: [B,C_in,H,W] -> [B,256,ceil(H/16),ceil(W/8)] (channels-last strides)."""
+        return self.forward_nhwc(x).permute(0, 3, 1, 2)

@@ -1,0 +1,153 @@
+"""Batched greedy autoregressive decoding with an in-HBM KV cache.
+
+Replaces the reference's batch-1 loop (``validation_step`` / ``get_pred_seq_and_pred_prob_seq``,
+reference model.py:170-199, 226-262, 592-617), which re-runs the whole decoder on the growing prefix
+and synchronises with the host at every token.  Here:
+
+* the cross-attention K/V of the encoder memory are projected ONCE per layer and stay resident;
+* self-attention K/V rows are appended to a per-layer cache ``[B, Tmax, 2*D]``;
+* one decode step is a fixed sequence of kernels that read the position from a device counter, so
+  it is captured in a CUDA graph once and replayed; EOS bookkeeping (``finished`` flags, PAD after
+  EOS) lives on the device and the host only polls it every ``poll_every`` steps;
+* the token stream is identical to the reference loop (first-max argmax, EOS emitted, at most
+  ``max_seq_len`` tokens); with ``attn_window > 0`` the cache is read through the same sliding window
+  as ``create_variable_window_mask`` (decoder.py:191-217).
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Tuple
+
+import torch
+
+from . import ops
+from .decoder import Decoder
+from .params import resolve_dtype
+
+
+class BatchedGreedyDecoder:
+    def __init__(self, decoder: Decoder, dtype: Optional[torch.dtype] = None):
+        self.dec = decoder
+        self.dtype = resolve_dtype(dtype if dtype is not None else decoder.compute_dtype)
+        self._graph = None
+        self._graph_key = None
+
+    # -- one decode step (all kernels read the position from the device counter ``pos``) ---------------
+    def _step(self, st) -> None:
+        dec, dtype = self.dec, self.dtype
+        c = dec._wcache
+        b, d, h = st["B"], dec.d_model, dec.nhead
+        hd = d // h
+        pos = st["pos"]
+        esz = st["x"].element_size()
+        table = c.get(dec.embedding.weight, "mat", dtype)
+        x = ops.embed_pe_fwd(st["tok"].view(b, 1), table, dec.pos_1d.pe.view(-1, d), 0, pos_dev=pos, out=st["x"])
+        x2 = x.view(b, d)
+        for li, L in enumerate(dec.transformer_decoder.layers):
+            sa, ca = L.self_attn, L.multihead_attn
+            w_in = c.get(sa.in_proj_weight, "mat", dtype)
+            w_o = c.get(sa.out_proj.weight, "mat", dtype)
+            wc_in = c.get(ca.in_proj_weight, "mat", dtype)
+            wc_o = c.get(ca.out_proj.weight, "mat", dtype)
+            w1 = c.get(L.linear1.weight, "mat", dtype)
+            w2 = c.get(L.linear2.weight, "mat", dtype)
+            qkv = ops.linear_fwd(x2, w_in, sa.in_proj_bias)  # [B,3D]
+            cache = st["self_kv"][li]  # [B,Tmax,2D]
+            ops.kv_append(qkv.data_ptr() + d * esz, 3 * d, cache, 0, dtype, pos_dev=pos)
+            o = torch.empty((b, d), dtype=dtype, device=x.device)
+            tmax = cache.shape[1]
+            ops.attn_decode(qkv.data_ptr(), 3 * d, cache.data_ptr(), tmax * 2 * d, 2 * d, cache.data_ptr() + d * esz,
+                            tmax * 2 * d, 2 * d, o, None, st["ws"], b, h, tmax, hd, dec.attn_window, dtype, pos_dev=pos)
+            a = ops.linear_fwd(o, w_o, sa.out_proj.bias)
+            x1, _, _ = ops.add_layernorm_fwd(a, x2, L.norm1.weight, L.norm1.bias, L.norm1.eps, False)
+            q = ops.linear_fwd(x1, wc_in[:d], ca.in_proj_bias[:d])
+            kv = st["cross_kv"][li]  # [B,S,2D]
+            s = kv.shape[1]
+            o2 = torch.empty((b, d), dtype=dtype, device=x.device)
+            ops.attn_decode(q.data_ptr(), d, kv.data_ptr(), s * 2 * d, 2 * d, kv.data_ptr() + d * esz, s * 2 * d, 2 * d, o2,
+                            st["mem_bias"], st["ws"], b, h, s, hd, 0, dtype)
+            cc = ops.linear_fwd(o2, wc_o, ca.out_proj.bias)
+            x2n, _, _ = ops.add_layernorm_fwd(cc, x1, L.norm2.weight, L.norm2.bias, L.norm2.eps, False)
+            hmid = ops.linear_fwd(x2n, w1, L.linear1.bias, relu=True)
+            f = ops.linear_fwd(hmid, w2, L.linear2.bias)
+            x2, _, _ = ops.add_layernorm_fwd(f, x2n, L.norm3.weight, L.norm3.bias, L.norm3.eps, False)
+        wout = c.get(dec.out_layer.weight, "mat", dtype)
+        logits = ops.linear_fwd(x2, wout, dec.out_layer.bias, out=st["logits"])
+        ops.argmax_step(logits, st["tok"], st["val"], st["finished"], st["eos"], st["pad"], st["out_tokens"],
+                        st["out_vals"], 0, step_dev=pos)
+        ops.tick(pos)
+
+    @torch.no_grad()
+    def decode(self, memory: torch.Tensor, sos: int, eos: int, pad: int = 0, max_steps: Optional[int] = None,
+               stop_at_eos: bool = True, use_graph: bool = True, poll_every: int = 64,
+               mem_bias: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        """memory [B,S,D] -> (tokens int64 [B,steps] (PAD after EOS), top logits fp32 [B,steps], lengths int64 [B])."""
+        dec, dtype = self.dec, self.dtype
+        ops._lib.require_cuda(memory, "greedy decode")
+        dev = memory.device
+        mem = ops.cast(memory.contiguous(), dtype)
+        b, s, d = mem.shape
+        steps = dec.max_seq_len if max_steps is None else min(int(max_steps), dec.max_seq_len)
+        c = dec._wcache
+        mem2 = mem.view(b * s, d)
+        cross_kv = []
+        for L in dec.transformer_decoder.layers:
+            ca = L.multihead_attn
+            wc_in = c.get(ca.in_proj_weight, "mat", dtype)
+            cross_kv.append(ops.linear_fwd(mem2, wc_in[d:], ca.in_proj_bias[d:]).view(b, s, 2 * d))
+        nl = len(cross_kv)
+        st = {
+            "B": b, "eos": int(eos), "pad": int(pad), "cross_kv": cross_kv, "mem_bias": mem_bias,
+            "self_kv": [torch.zeros((b, steps, 2 * d), dtype=dtype, device=dev) for _ in range(nl)],
+            "x": torch.empty((b, 1, d), dtype=dtype, device=dev),
+            "logits": torch.empty((b, dec.output_size), dtype=dtype, device=dev),
+            "tok": torch.full((b,), int(sos), dtype=torch.int64, device=dev),
+            "val": torch.zeros((b,), dtype=torch.float32, device=dev),
+            "finished": torch.zeros((b,), dtype=torch.int32, device=dev),
+            "out_tokens": torch.full((b, steps), int(pad), dtype=torch.int64, device=dev),
+            "out_vals": torch.zeros((b, steps), dtype=torch.float32, device=dev),
+            "pos": torch.zeros((1,), dtype=torch.int32, device=dev),
+            "ws": torch.empty(ops.attn_decode_ws_floats(b, dec.nhead), dtype=torch.float32, device=dev),
+        }
+        if not stop_at_eos:
+            st["eos"] = -1  # never matches: forced full-length decoding
+
+        def reset() -> None:
+            st["tok"].fill_(int(sos))
+            st["finished"].zero_()
+            st["pos"].zero_()
+            st["out_tokens"].fill_(int(pad))
+            st["out_vals"].zero_()
+
+        graph = None
+        if use_graph and steps > 2:
+            # warm-up on a side stream (sets kernel attributes, fills the weight cache), then capture one step
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                self._step(st)
+            torch.cuda.current_stream(dev).wait_stream(side)
+            reset()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                self._step(st)
+            reset()
+        done_steps = 0
+        for t in range(steps):
+            if graph is not None:
+                graph.replay()
+            else:
+                self._step(st)
+            done_steps = t + 1
+            if stop_at_eos and poll_every > 0 and done_steps % poll_every == 0 and done_steps < steps:
+                if bool(st["finished"].all().item()):
+                    break
+        toks = st["out_tokens"][:, :done_steps]
+        vals = st["out_vals"][:, :done_steps]
+        is_eos = toks == int(eos) if stop_at_eos else torch.zeros_like(toks, dtype=torch.bool)
+        first = torch.where(is_eos.any(dim=1), is_eos.float().argmax(dim=1) + 1, torch.full((b,), done_steps, device=dev))
+        return toks, vals, first.to(torch.int64)
+
+    @staticmethod
+    def to_lists(tokens: torch.Tensor, vals: torch.Tensor, lengths: torch.Tensor) -> Tuple[List[List[int]], List[List[float]]]:
+        tk, vl, ln = tokens.cpu().tolist(), vals.cpu().tolist(), lengths.cpu().tolist()
+        return [r[:n] for r, n in zip(tk, ln)], [r[:n] for r, n in zip(vl, ln)]

@@ -1,0 +1,388 @@
+"""Thin functional wrappers over the C ABI (``include/omr_b200.h``): one Python function per kernel
+entry point, taking/returning CUDA tensors.  No autograd here -- the backward passes are composed
+explicitly in ``encoder.py`` / ``decoder.py`` / ``model.py`` from these same wrappers.
+
+Tensors are NHWC for image-like data and [B,T,D] for sequences; ``x.dtype`` (float32 or bfloat16)
+selects the kernel storage type.  Everything is enqueued on the current torch CUDA stream.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import call, dt_code, ptr, stream_ptr
+
+NEG_INF = float("-inf")
+
+
+def _chk(t: torch.Tensor, name: str) -> torch.Tensor:
+    _lib.require_cuda(t, name)
+    if not t.is_contiguous():
+        raise RuntimeError(f"{name}: expected a contiguous tensor, got strides {t.stride()} for shape {tuple(t.shape)}")
+    return t
+
+
+def out_hw(h: int, w: int, stride: Tuple[int, int]) -> Tuple[int, int]:
+    return (h + stride[0] - 1) // stride[0], (w + stride[1] - 1) // stride[1]
+
+
+# ---- elementwise / layout ----------------------------------------------------------------------
+def cast(x: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    _chk(x, "cast")
+    if x.dtype == dtype:
+        return x
+    y = torch.empty_like(x, dtype=dtype)
+    call("omr_cast", dt_code(x.dtype), dt_code(dtype), ptr(x), ptr(y), x.numel(), stream_ptr())
+    return y
+
+
+def relu_bwd(y: torch.Tensor, dy: torch.Tensor, inplace: bool = False) -> torch.Tensor:
+    _chk(y, "relu_bwd.y"), _chk(dy, "relu_bwd.dy")
+    dx = dy if inplace else torch.empty_like(dy)
+    call("omr_relu_bwd", dt_code(y.dtype), ptr(y), ptr(dy), ptr(dx), y.numel(), stream_ptr())
+    return dx
+
+
+def add(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _chk(a, "add.a"), _chk(b, "add.b")
+    out = torch.empty_like(a) if out is None else out
+    call("omr_add", dt_code(a.dtype), ptr(a), ptr(b), ptr(out), a.numel(), stream_ptr())
+    return out
+
+
+def dropout(x: torch.Tensor, p: float, seed: int, channelwise: bool = False, inplace: bool = False) -> torch.Tensor:
+    """Seeded dropout; for NHWC tensors ``channelwise`` drops whole (sample, channel) planes (Dropout2d).
+    Applying it to a gradient with the same seed is the backward pass."""
+    _chk(x, "dropout")
+    y = x if inplace else torch.empty_like(x)
+    c = x.shape[-1]
+    per_sample = x.numel() // x.shape[0]
+    call("omr_dropout", dt_code(x.dtype), ptr(x), ptr(y), x.numel(), c, per_sample, float(p), int(seed), int(channelwise),
+         stream_ptr())
+    return y
+
+
+def pack_conv_weight(w: torch.Tensor, dtype: torch.dtype, transpose: bool) -> torch.Tensor:
+    """[Co,Ci,3,3] fp32 -> [Co,3,3,Ci] (transpose=False) or [Ci,3,3,Co] (transpose=True) in ``dtype``."""
+    _chk(w, "pack_conv_weight")
+    co, ci = w.shape[0], w.shape[1]
+    shape = (ci, 3, 3, co) if transpose else (co, 3, 3, ci)
+    out = torch.empty(shape, dtype=dtype, device=w.device)
+    call("omr_pack_conv_weight", dt_code(dtype), ptr(w), ptr(out), co, ci, int(transpose), stream_ptr())
+    return out
+
+
+def pack_dw_weight(w: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    _chk(w, "pack_dw_weight")
+    c = w.shape[0]
+    out = torch.empty((3, 3, c), dtype=dtype, device=w.device)
+    call("omr_pack_dw_weight", dt_code(dtype), ptr(w), ptr(out), c, stream_ptr())
+    return out
+
+
+# ---- convolutions ---------------------------------------------------------------------------------
+def conv3x3_fwd(x, wp, bias, stride=(1, 1), relu=False):
+    """x [N,H,W,Ci], wp [Co,3,3,Ci] (packed), bias fp32 [Co] -> y [N,Ho,Wo,Co]"""
+    _chk(x, "conv3x3_fwd.x"), _chk(wp, "conv3x3_fwd.w")
+    n, h, w, ci = x.shape
+    co = wp.shape[0]
+    ho, wo = out_hw(h, w, stride)
+    y = torch.empty((n, ho, wo, co), dtype=x.dtype, device=x.device)
+    call("omr_conv3x3_fwd", dt_code(x.dtype), ptr(x), ptr(wp), ptr(bias), ptr(y), n, h, w, ci, co, stride[0], stride[1],
+         int(relu), stream_ptr())
+    return y
+
+
+def conv3x3_dgrad(dy, wpt, in_hw, stride=(1, 1)):
+    """dy [N,Ho,Wo,Co], wpt [Ci,3,3,Co] -> dx [N,H,W,Ci]"""
+    _chk(dy, "conv3x3_dgrad.dy"), _chk(wpt, "conv3x3_dgrad.w")
+    n, _, _, co = dy.shape
+    ci = wpt.shape[0]
+    h, w = in_hw
+    dx = torch.empty((n, h, w, ci), dtype=dy.dtype, device=dy.device)
+    call("omr_conv3x3_dgrad", dt_code(dy.dtype), ptr(dy), ptr(wpt), ptr(dx), n, h, w, ci, co, stride[0], stride[1],
+         stream_ptr())
+    return dx
+
+
+def conv3x3_wgrad(x, dy, dw, db, stride=(1, 1), accumulate=True):
+    """accumulates dw [Co,Ci,3,3] fp32 and db [Co] fp32 (torch parameter layouts)"""
+    _chk(x, "conv3x3_wgrad.x"), _chk(dy, "conv3x3_wgrad.dy")
+    n, h, w, ci = x.shape
+    co = dy.shape[3]
+    call("omr_conv3x3_wgrad", dt_code(x.dtype), ptr(x), ptr(dy), ptr(dw), ptr(db), n, h, w, ci, co, stride[0], stride[1],
+         int(accumulate), stream_ptr())
+
+
+def dwconv3x3_fwd(x, wp, bias):
+    _chk(x, "dwconv3x3_fwd.x")
+    n, h, w, c = x.shape
+    y = torch.empty_like(x)
+    call("omr_dwconv3x3_fwd", dt_code(x.dtype), ptr(x), ptr(wp), ptr(bias), ptr(y), n, h, w, c, stream_ptr())
+    return y
+
+
+def dwconv3x3_dgrad(dy, wp):
+    _chk(dy, "dwconv3x3_dgrad.dy")
+    n, h, w, c = dy.shape
+    dx = torch.empty_like(dy)
+    call("omr_dwconv3x3_dgrad", dt_code(dy.dtype), ptr(dy), ptr(wp), ptr(dx), n, h, w, c, stream_ptr())
+    return dx
+
+
+def dwconv3x3_wgrad(x, dy, dw, db, accumulate=True):
+    _chk(x, "dwconv3x3_wgrad.x"), _chk(dy, "dwconv3x3_wgrad.dy")
+    n, h, w, c = x.shape
+    call("omr_dwconv3x3_wgrad", dt_code(x.dtype), ptr(x), ptr(dy), ptr(dw), ptr(db), n, h, w, c, int(accumulate),
+         stream_ptr())
+
+
+def instnorm_fwd(x, eps: float):
+    """x [N,H,W,C] -> (y, stats [N,C,2] fp32 = (mean, rstd))"""
+    _chk(x, "instnorm_fwd.x")
+    n, h, w, c = x.shape
+    y = torch.empty_like(x)
+    stats = torch.empty((n, c, 2), dtype=torch.float32, device=x.device)
+    call("omr_instnorm_fwd", dt_code(x.dtype), ptr(x), ptr(y), ptr(stats), n, h * w, c, float(eps), stream_ptr())
+    return y, stats
+
+
+def instnorm_bwd(dy, x, stats):
+    _chk(dy, "instnorm_bwd.dy"), _chk(x, "instnorm_bwd.x")
+    n, h, w, c = x.shape
+    dx = torch.empty_like(x)
+    ws = torch.empty((n, c, 2), dtype=torch.float32, device=x.device)
+    call("omr_instnorm_bwd", dt_code(x.dtype), ptr(dy), ptr(x), ptr(stats), ptr(dx), ptr(ws), n, h * w, c, stream_ptr())
+    return dx
+
+
+def pe2d_add(x, pe_nhwc, out, row_off: int):
+    """out[b, row_off + p, :] = x[b, p, :] + pe[p // w, p % w, :] ; x [B,h,w,C], out [B,S,C]"""
+    _chk(x, "pe2d_add.x"), _chk(out, "pe2d_add.out")
+    b, h, w, c = x.shape
+    if h > pe_nhwc.shape[0] or w > pe_nhwc.shape[1]:
+        raise RuntimeError(f"feature map {h}x{w} exceeds the positional-encoding table {tuple(pe_nhwc.shape[:2])}")
+    call("omr_pe2d_add", dt_code(x.dtype), ptr(x), ptr(pe_nhwc), ptr(out), b, h, w, c, pe_nhwc.shape[1], out.shape[1],
+         row_off, stream_ptr())
+    return out
+
+
+def copy_rows(src, row_off: int, rows: int):
+    """src [B,S,C] -> contiguous [B,rows,C] copy of src[:, row_off:row_off+rows]"""
+    _chk(src, "copy_rows.src")
+    b, s, c = src.shape
+    dst = torch.empty((b, rows, c), dtype=src.dtype, device=src.device)
+    call("omr_copy_rows", dt_code(src.dtype), ptr(src), ptr(dst), b, rows, c, s, row_off, stream_ptr())
+    return dst
+
+
+# ---- masks --------------------------------------------------------------------------------------
+def key_bias_from_lengths(bias, lens_i32, seg_off: int, seg_len: int, value: float):
+    _chk(bias, "key_bias_from_lengths.bias"), _chk(lens_i32, "key_bias_from_lengths.lens")
+    assert lens_i32.dtype == torch.int32
+    b, s = bias.shape
+    call("omr_key_bias_from_lengths", ptr(bias), ptr(lens_i32), b, s, seg_off, seg_len, float(value), stream_ptr())
+    return bias
+
+
+def key_bias_from_tokens(tokens, pad_id: int, value: float):
+    _chk(tokens, "key_bias_from_tokens.tokens")
+    assert tokens.dtype == torch.int64
+    bias = torch.empty(tokens.shape, dtype=torch.float32, device=tokens.device)
+    call("omr_key_bias_from_tokens", ptr(bias), ptr(tokens), tokens.numel(), pad_id, float(value), stream_ptr())
+    return bias
+
+
+# ---- decoder pieces -----------------------------------------------------------------------------
+def embed_pe_fwd(tokens, table, pe, pos0: int = 0, pos_dev=None, out=None):
+    """tokens int64 [B,T], table [V,D] (compute dtype), pe fp32 [max_len,D] -> [B,T,D]"""
+    _chk(tokens, "embed_pe_fwd.tokens"), _chk(table, "embed_pe_fwd.table")
+    b, t = tokens.shape
+    d = table.shape[1]
+    if pos0 + t > pe.shape[0]:
+        raise RuntimeError(f"sequence positions {pos0}..{pos0 + t} exceed the 1-D PE table ({pe.shape[0]})")
+    out = torch.empty((b, t, d), dtype=table.dtype, device=table.device) if out is None else out
+    call("omr_embed_pe_fwd", dt_code(table.dtype), ptr(tokens), ptr(table), ptr(pe), ptr(out), b, t, d, pos0, ptr(pos_dev),
+         stream_ptr())
+    return out
+
+
+def embed_bwd(tokens, dout, dtable, padding_idx: int):
+    _chk(tokens, "embed_bwd.tokens"), _chk(dout, "embed_bwd.dout")
+    call("omr_embed_bwd", dt_code(dout.dtype), ptr(tokens), ptr(dout), ptr(dtable), tokens.numel(), dout.shape[-1],
+         padding_idx, stream_ptr())
+
+
+def gemm(a, b, c, m, n, k, *, trans_a=False, trans_b=False, lda, ldb, ldc, batch=1, stride_a=0, stride_b=0, stride_c=0,
+         bias=None, bias_mode=0, relu=False, accumulate=False):
+    """C[b] = act(opA(A[b]) @ opB(B[b]) + bias) (+C[b]); see omr_gemm in include/omr_b200.h"""
+    call("omr_gemm", dt_code(a.dtype), dt_code(c.dtype), int(trans_a), int(trans_b), m, n, k, ptr(a), lda, stride_a,
+         ptr(b), ldb, stride_b, ptr(c), ldc, stride_c, batch, ptr(bias), bias_mode if bias is not None else 0, int(relu),
+         int(accumulate), stream_ptr())
+    return c
+
+
+def linear_fwd(x2d, w, bias=None, relu=False, out=None):
+    """x2d [M,K] @ w[N,K]^T (+bias) -> [M,N] (nn.Linear semantics; w rows may be a slice of a packed weight)"""
+    _chk(x2d, "linear_fwd.x")
+    m, k = x2d.shape
+    n = w.shape[0]
+    y = torch.empty((m, n), dtype=x2d.dtype, device=x2d.device) if out is None else out
+    gemm(x2d, w, y, m, n, k, trans_b=True, lda=k, ldb=w.stride(0), ldc=y.stride(0), bias=bias, bias_mode=1, relu=relu)
+    return y
+
+
+def linear_dgrad(dy2d, w, out=None):
+    """dx [M,K] = dy [M,N] @ w [N,K]"""
+    _chk(dy2d, "linear_dgrad.dy")
+    m, n = dy2d.shape
+    k = w.shape[1]
+    dx = torch.empty((m, k), dtype=dy2d.dtype, device=dy2d.device) if out is None else out
+    gemm(dy2d, w, dx, m, k, n, lda=n, ldb=w.stride(0), ldc=dx.stride(0))
+    return dx
+
+
+def linear_wgrad(x2d, dy2d, dw, db=None, accumulate=True):
+    """dw [N,K] (fp32, may be a row-slice view) += dy^T @ x ; db [N] += colsum(dy)"""
+    m, k = x2d.shape
+    n = dy2d.shape[1]
+    gemm(dy2d, x2d, dw, n, k, m, trans_a=True, lda=n, ldb=k, ldc=dw.stride(0), accumulate=accumulate)
+    if db is not None:
+        colsum(dy2d, db, accumulate=accumulate)
+
+
+def colsum(x2d, out, accumulate=True):
+    rows, n = x2d.shape
+    call("omr_colsum", dt_code(x2d.dtype), ptr(x2d), rows, n, x2d.stride(0), ptr(out), int(accumulate), stream_ptr())
+    return out
+
+
+class AttnSpec:
+    """Mask description shared by attention forward and backward."""
+
+    __slots__ = ("H", "hd", "scale", "causal", "window", "key_bias", "q_len", "kv_len", "quirk_mod")
+
+    def __init__(self, H, hd, causal=False, window=-1, key_bias=None, q_len=None, kv_len=None, quirk_mod=0):
+        self.H, self.hd = H, hd
+        self.scale = 1.0 / math.sqrt(hd)
+        self.causal, self.window = bool(causal), int(window) if window and window > 0 else 0
+        self.key_bias, self.q_len, self.kv_len, self.quirk_mod = key_bias, q_len, kv_len, quirk_mod
+
+
+def _view3(t, off, width):
+    """(base pointer incl. column offset, batch stride, row stride) of columns [off, off+width) of a [B,T,W] buffer"""
+    assert t.dim() == 3 and t.is_contiguous()
+    return t.data_ptr() + off * t.element_size(), t.stride(0), t.stride(1)
+
+
+def attn_fwd(qbuf, q_off, kbuf, k_off, vbuf, v_off, spec: AttnSpec):
+    """q = qbuf[:, :, q_off:q_off+H*hd] etc. -> (o [B,Tq,H*hd], lse [B,H,Tq] fp32)"""
+    b, tq, _ = qbuf.shape
+    tk = kbuf.shape[1]
+    d = spec.H * spec.hd
+    o = torch.empty((b, tq, d), dtype=qbuf.dtype, device=qbuf.device)
+    lse = torch.empty((b, spec.H, tq), dtype=torch.float32, device=qbuf.device)
+    qp, qbs, qrs = _view3(qbuf, q_off, d)
+    kp, kbs, krs = _view3(kbuf, k_off, d)
+    vp, vbs, vrs = _view3(vbuf, v_off, d)
+    call("omr_attn_fwd", dt_code(qbuf.dtype), qp, qbs, qrs, kp, kbs, krs, vp, vbs, vrs, ptr(o), o.stride(0), o.stride(1),
+         ptr(lse), ptr(spec.key_bias), b, spec.H, tq, tk, spec.hd, spec.scale, int(spec.causal), spec.window,
+         ptr(spec.q_len), ptr(spec.kv_len), spec.quirk_mod, stream_ptr())
+    return o, lse
+
+
+def attn_bwd(qbuf, q_off, kbuf, k_off, vbuf, v_off, o, do, lse, dqbuf, dq_off, dkbuf, dk_off, dvbuf, dv_off, spec: AttnSpec):
+    """writes dq/dk/dv into column ranges of the given gradient buffers (same layouts as the inputs)"""
+    _chk(do, "attn_bwd.do")
+    b, tq, _ = qbuf.shape
+    tk = kbuf.shape[1]
+    d = spec.H * spec.hd
+    qp, qbs, qrs = _view3(qbuf, q_off, d)
+    kp, kbs, krs = _view3(kbuf, k_off, d)
+    vp, vbs, vrs = _view3(vbuf, v_off, d)
+    dqp, dqbs, dqrs = _view3(dqbuf, dq_off, d)
+    dkp, dkbs, dkrs = _view3(dkbuf, dk_off, d)
+    dvp, dvbs, dvrs = _view3(dvbuf, dv_off, d)
+    delta = torch.empty((b, spec.H, tq), dtype=torch.float32, device=qbuf.device)
+    call("omr_attn_bwd", dt_code(qbuf.dtype), qp, qbs, qrs, kp, kbs, krs, vp, vbs, vrs, ptr(o), o.stride(0), o.stride(1),
+         ptr(do), do.stride(0), do.stride(1), ptr(lse), dqp, dqbs, dqrs, dkp, dkbs, dkrs, dvp, dvbs, dvrs, ptr(delta),
+         ptr(spec.key_bias), b, spec.H, tq, tk, spec.hd, spec.scale, int(spec.causal), spec.window, ptr(spec.q_len),
+         ptr(spec.kv_len), spec.quirk_mod, stream_ptr())
+
+
+def add_layernorm_fwd(x, res, gamma, beta, eps: float, save: bool):
+    """y = LN(x + res); returns (y, s, stats) with s = x + res (compute dtype) when save else (y, None, None)"""
+    _chk(x, "add_layernorm_fwd.x")
+    d = x.shape[-1]
+    rows = x.numel() // d
+    y = torch.empty_like(x)
+    s = torch.empty_like(x) if save else None
+    stats = torch.empty((rows, 2), dtype=torch.float32, device=x.device) if save else None
+    call("omr_add_layernorm_fwd", dt_code(x.dtype), ptr(x), ptr(res), ptr(gamma), ptr(beta), ptr(s), ptr(y), ptr(stats),
+         rows, d, float(eps), stream_ptr())
+    return y, s, stats
+
+
+def layernorm_bwd(dy, s, stats, gamma, dgamma, dbeta):
+    _chk(dy, "layernorm_bwd.dy")
+    d = dy.shape[-1]
+    rows = dy.numel() // d
+    ds = torch.empty_like(dy)
+    call("omr_layernorm_bwd", dt_code(dy.dtype), ptr(dy), ptr(s), ptr(stats), ptr(gamma), ptr(ds), ptr(dgamma), ptr(dbeta),
+         rows, d, stream_ptr())
+    return ds
+
+
+def ce_fwd(logits2d, targets, ignore_index: int):
+    """logits [rows, V] (row stride may exceed V), targets int64 [rows] -> (loss_out fp32 [2] = (mean loss, n_valid), row_lse)"""
+    rows, v = logits2d.shape
+    dev = logits2d.device
+    row_loss = torch.empty(rows, dtype=torch.float32, device=dev)
+    row_lse = torch.empty(rows, dtype=torch.float32, device=dev)
+    loss_out = torch.empty(2, dtype=torch.float32, device=dev)
+    call("omr_ce_fwd", dt_code(logits2d.dtype), ptr(logits2d), logits2d.stride(0), ptr(targets), rows, v, ignore_index,
+         ptr(row_loss), ptr(row_lse), stream_ptr())
+    call("omr_ce_reduce", ptr(row_loss), ptr(targets), rows, ignore_index, ptr(loss_out), stream_ptr())
+    return loss_out, row_lse
+
+
+def ce_bwd(logits2d, targets, row_lse, loss_out, gscale, ignore_index: int, inplace=True):
+    rows, v = logits2d.shape
+    d = logits2d if inplace else torch.empty_like(logits2d)
+    call("omr_ce_bwd", dt_code(logits2d.dtype), ptr(logits2d), logits2d.stride(0), ptr(targets), ptr(row_lse),
+         ptr(loss_out), ptr(gscale), ptr(d), rows, v, ignore_index, stream_ptr())
+    return d
+
+
+# ---- greedy decode helpers ------------------------------------------------------------------------
+def argmax_step(logits2d, tok, val, finished, eos_id, pad_id, out_tokens, out_vals, step, step_dev=None):
+    b, v = logits2d.shape
+    call("omr_argmax_step", dt_code(logits2d.dtype), ptr(logits2d), logits2d.stride(0), b, v, ptr(tok), ptr(val),
+         ptr(finished), eos_id, pad_id, ptr(out_tokens), ptr(out_vals),
+         out_tokens.shape[1] if out_tokens is not None else 0, step, ptr(step_dev), stream_ptr())
+
+
+def kv_append(src_ptr, src_rs, cache, pos, dtype, pos_dev=None):
+    b, tmax, width = cache.shape
+    call("omr_kv_append", dt_code(dtype), src_ptr, src_rs, ptr(cache), b, tmax, width, pos, ptr(pos_dev), stream_ptr())
+
+
+def attn_decode_ws_floats(b, h, hd=64):
+    nsplit = max(1, -(-592 // (b * h)))
+    return b * h * nsplit * (hd + 2)
+
+
+def attn_decode(q_ptr, q_bs, k_ptr, k_bs, k_rs, v_ptr, v_bs, v_rs, o, key_bias, ws, b, h, tk, hd, window, dtype,
+                pos_dev=None):
+    call("omr_attn_decode", dt_code(dtype), q_ptr, q_bs, k_ptr, k_bs, k_rs, v_ptr, v_bs, v_rs, ptr(o), o.stride(0),
+         ptr(key_bias), key_bias.stride(0) if key_bias is not None else 0, ptr(ws), ws.numel(), b, h, tk, hd,
+         1.0 / math.sqrt(hd), window if window and window > 0 else 0, ptr(pos_dev), stream_ptr())
+    return o
+
+
+def tick(counter_i32):
+    """*counter += 1 on the stream (device-side step/position counter)"""
+    call("omr_adam_tick", ptr(counter_i32), stream_ptr())

@@ -1,0 +1,101 @@
+"""Fused multi-tensor Adam (``torch.optim.Adam(lr=1e-4, betas=(0.9, 0.999), eps=1e-8, amsgrad=False)`` of
+reference model.py:134-139,475-483) as ONE kernel launch over all parameters.
+
+The kernel reads fp32 gradients, updates the fp32 master parameters and both moments, and -- when the
+model runs in bf16 -- refreshes the bf16 kernel-layout working copies of the weights in the same pass, so
+no separate cast/re-layout kernels run after the step.  The step counter lives on the device, which makes
+the whole optimizer step CUDA-graph capturable.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Iterable, List, Optional
+
+import torch
+
+from . import _lib
+from ._lib import call, ptr, stream_ptr
+
+
+class _AdamEntry(ctypes.Structure):
+    _fields_ = [
+        ("param", ctypes.c_void_p), ("grad", ctypes.c_void_p), ("exp_avg", ctypes.c_void_p),
+        ("exp_avg_sq", ctypes.c_void_p), ("shadow", ctypes.c_void_p), ("shadow2", ctypes.c_void_p),
+        ("n", ctypes.c_longlong), ("layout", ctypes.c_int), ("layout2", ctypes.c_int), ("d0", ctypes.c_int),
+        ("d1", ctypes.c_int),
+    ]
+
+
+class FusedAdam(torch.optim.Optimizer):
+    def __init__(self, params: Iterable[torch.nn.Parameter], lr: float = 1e-4, betas=(0.9, 0.999), eps: float = 1e-8,
+                 grad_scale: float = 1.0):
+        super().__init__(list(params), dict(lr=lr, betas=betas, eps=eps))
+        self.grad_scale = grad_scale
+        self._table = None
+        self._table_key = None
+        self._step_dev: Optional[torch.Tensor] = None
+        self._shadows = []  # callables returning [(param, shadow, layout, shadow2, layout2, d0, d1)]
+
+    def register_shadow_provider(self, fn) -> None:
+        """fn(param) -> (shadow, layout, shadow2, layout2, d0, d1) or None; lets the model hand over its
+        bf16 working copies so the kernel keeps them in sync."""
+        self._shadows.append(fn)
+        self._table = None
+
+    def _params(self) -> List[torch.nn.Parameter]:
+        return [p for g in self.param_groups for p in g["params"]]
+
+    def _build_table(self) -> None:
+        ps = [p for p in self._params() if p.requires_grad]
+        dev = ps[0].device
+        if self._step_dev is None or self._step_dev.device != dev:
+            self._step_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+        entries = (_AdamEntry * len(ps))()
+        key = []
+        for i, p in enumerate(ps):
+            st = self.state[p]
+            if "exp_avg" not in st:
+                st["exp_avg"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
+                st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
+            sh = None
+            for fn in self._shadows:
+                sh = fn(p)
+                if sh is not None:
+                    break
+            e = entries[i]
+            e.param, e.grad = p.data_ptr(), (p.grad.data_ptr() if p.grad is not None else None)
+            e.exp_avg, e.exp_avg_sq = st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr()
+            e.n = p.numel()
+            if sh is not None:
+                s1, l1, s2, l2, d0, d1 = sh
+                e.shadow, e.layout = (s1.data_ptr() if s1 is not None else None), l1
+                e.shadow2, e.layout2 = (s2.data_ptr() if s2 is not None else None), l2
+                e.d0, e.d1 = d0, d1
+            key.append((e.param, e.grad, e.shadow, e.shadow2))
+        raw = bytes(entries)
+        host = torch.frombuffer(bytearray(raw), dtype=torch.uint8)
+        self._table = host.to(dev)
+        self._table_key = key
+        self._n = len(ps)
+        self._max_n = max(p.numel() for p in ps)
+        self._ps = ps
+
+    def _table_stale(self) -> bool:
+        if self._table is None:
+            return True
+        for p, k in zip(self._ps, self._table_key):
+            g = p.grad.data_ptr() if p.grad is not None else None
+            if p.data_ptr() != k[0] or g != k[1]:
+                return True
+        return False
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = closure() if closure is not None else None
+        if self._table_stale():
+            self._build_table()
+        g = self.param_groups[0]
+        call("omr_adam_tick", ptr(self._step_dev), stream_ptr())
+        call("omr_adam_step", ptr(self._table), self._n, self._max_n, ptr(self._step_dev), float(g["lr"]),
+             float(g["betas"][0]), float(g["betas"][1]), float(g["eps"]), float(self.grad_scale), stream_ptr())
+        return loss

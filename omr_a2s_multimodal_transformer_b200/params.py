@@ -1,0 +1,161 @@
+"""Parameter-side plumbing shared by the encoder/decoder modules.
+
+* ``WeightCache`` keeps the kernel-layout working copies of the fp32 ``nn.Parameter``s (bf16 or fp32,
+  re-laid-out for the implicit-GEMM kernels) and refreshes them when a parameter's version changes.
+* ``grad_buf`` returns the fp32 gradient buffer of a parameter that the weight-gradient kernels
+  accumulate into directly (``param.grad``, created zero-filled on first use, or a slice of a
+  ``GradArena``).
+* ``GradArena`` lays all gradients of a model out in one flat fp32 buffer so that zeroing is one
+  memset and the data-parallel all-reduce can run on contiguous buckets.
+* ``resolve_dtype`` picks the kernel storage type (fp32 exact mode / bf16 tensor-core mode).
+"""
+from __future__ import annotations
+
+import os
+from typing import Dict, Iterable, List, Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import ops
+
+
+def resolve_dtype(explicit: Optional[torch.dtype]) -> torch.dtype:
+    """Explicit setting wins; else env OMR_COMPUTE_DTYPE; else bf16 under torch autocast (what
+    Lightning's ``precision="16-mixed"`` of the reference's train.py:153 enables), else fp32."""
+    if explicit is not None:
+        return explicit
+    env = os.environ.get("OMR_COMPUTE_DTYPE", "").lower()
+    if env in ("bf16", "bfloat16"):
+        return torch.bfloat16
+    if env in ("fp32", "float32"):
+        return torch.float32
+    if torch.is_autocast_enabled():
+        return torch.bfloat16
+    return torch.float32
+
+
+class WeightCache:
+    """kind: "conv" [Co,3,3,Ci] | "convT" [Ci,3,3,Co] | "dw" [3,3,C] | "mat" [N,K] (same order, 2-D)."""
+
+    def __init__(self) -> None:
+        self._c: Dict[Tuple[int, str, torch.dtype], Tuple[int, torch.Tensor]] = {}
+
+    def clear(self) -> None:
+        self._c.clear()
+
+    def get(self, p: torch.Tensor, kind: str, dtype: torch.dtype) -> torch.Tensor:
+        key = (id(p), kind, dtype)
+        ent = self._c.get(key)
+        ver = p._version
+        if ent is not None and ent[0] == ver and ent[1].device == p.device and ent[2] == p.data_ptr():
+            return ent[1]
+        t = self._pack(p.detach(), kind, dtype)
+        self._c[key] = (ver, t, p.data_ptr())
+        return t
+
+    def peek(self, p: torch.Tensor, kind: str, dtype: torch.dtype) -> Optional[torch.Tensor]:
+        ent = self._c.get((id(p), kind, dtype))
+        return None if ent is None else ent[1]
+
+    @staticmethod
+    def _pack(w: torch.Tensor, kind: str, dtype: torch.dtype) -> torch.Tensor:
+        if w.dtype != torch.float32:
+            raise TypeError("parameters must stay float32 (the kernels keep bf16 working copies themselves)")
+        w = w.contiguous()
+        if kind == "conv":
+            return ops.pack_conv_weight(w, dtype, transpose=False)
+        if kind == "convT":
+            return ops.pack_conv_weight(w, dtype, transpose=True)
+        if kind == "dw":
+            return ops.pack_dw_weight(w, dtype)
+        if kind == "mat":
+            w2 = w.reshape(w.shape[0], -1)
+            return w2 if dtype == torch.float32 else ops.cast(w2, dtype)
+        raise ValueError(kind)
+
+
+def grad_buf(p: nn.Parameter) -> torch.Tensor:
+    if p.grad is None:
+        p.grad = torch.zeros_like(p, memory_format=torch.contiguous_format)
+    return p.grad
+
+
+class GradArena:
+    """All gradients of ``params`` as views of one flat fp32 buffer (in the given order)."""
+
+    def __init__(self, params: Iterable[nn.Parameter]) -> None:
+        self.params: List[nn.Parameter] = [p for p in params if p.requires_grad]
+        if not self.params:
+            raise ValueError("GradArena: no trainable parameters")
+        dev = self.params[0].device
+        sizes = [(p.numel() + 63) // 64 * 64 for p in self.params]  # 256-byte aligned slots
+        self.offsets = [0]
+        for s in sizes:
+            self.offsets.append(self.offsets[-1] + s)
+        self.flat = torch.zeros(self.offsets[-1], dtype=torch.float32, device=dev)
+        for p, o in zip(self.params, self.offsets):
+            p.grad = self.flat[o : o + p.numel()].view_as(p)
+
+    def zero_(self) -> None:
+        self.flat.zero_()
+
+    def attached(self) -> bool:
+        return all(p.grad is not None and p.grad.data_ptr() == self.flat.data_ptr() + 4 * o
+                   for p, o in zip(self.params, self.offsets))
+
+    def reattach(self) -> None:
+        for p, o in zip(self.params, self.offsets):
+            p.grad = self.flat[o : o + p.numel()].view_as(p)
+
+
+# ---- parameter containers with torch-compatible names and default initialisation ---------------------
+class ConvParams(nn.Module):
+    """weight/bias of an nn.Conv2d / nn.Conv1d call site (same shapes, same default init)."""
+
+    def __init__(self, in_c: int, out_c: int, ksize: Tuple[int, ...], groups: int = 1) -> None:
+        super().__init__()
+        self.in_channels, self.out_channels, self.kernel_size, self.groups = in_c, out_c, tuple(ksize), groups
+        self.weight = nn.Parameter(torch.empty(out_c, in_c // groups, *ksize))
+        self.bias = nn.Parameter(torch.empty(out_c))
+        self.reset_parameters()
+
+    def reset_parameters(self) -> None:
+        nn.init.kaiming_uniform_(self.weight, a=5 ** 0.5)
+        fan_in = self.weight[0].numel()
+        bound = 1.0 / fan_in ** 0.5 if fan_in > 0 else 0.0
+        nn.init.uniform_(self.bias, -bound, bound)
+
+
+class LinearParams(nn.Module):
+    def __init__(self, in_f: int, out_f: int, zero_bias: bool = False) -> None:
+        super().__init__()
+        self.in_features, self.out_features = in_f, out_f
+        self.weight = nn.Parameter(torch.empty(out_f, in_f))
+        self.bias = nn.Parameter(torch.empty(out_f))
+        nn.init.kaiming_uniform_(self.weight, a=5 ** 0.5)
+        if zero_bias:
+            nn.init.zeros_(self.bias)
+        else:
+            bound = 1.0 / in_f ** 0.5
+            nn.init.uniform_(self.bias, -bound, bound)
+
+
+class LayerNormParams(nn.Module):
+    def __init__(self, d: int, eps: float = 1e-5) -> None:
+        super().__init__()
+        self.eps = eps
+        self.weight = nn.Parameter(torch.ones(d))
+        self.bias = nn.Parameter(torch.zeros(d))
+
+
+class MHAParams(nn.Module):
+    """Parameters of an nn.MultiheadAttention (packed in-proj): same names, same default init."""
+
+    def __init__(self, embed_dim: int, num_heads: int) -> None:
+        super().__init__()
+        self.embed_dim, self.num_heads, self.head_dim = embed_dim, num_heads, embed_dim // num_heads
+        self.in_proj_weight = nn.Parameter(torch.empty(3 * embed_dim, embed_dim))
+        self.in_proj_bias = nn.Parameter(torch.zeros(3 * embed_dim))
+        self.out_proj = LinearParams(embed_dim, embed_dim, zero_bias=True)
+        nn.init.xavier_uniform_(self.in_proj_weight)

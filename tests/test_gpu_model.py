@@ -1,0 +1,167 @@
+"""Module- and model-level parity (-m gpu): the CUDA modules against the oracle restatement
+(oracle/restate.py, itself pinned to the real reference) on the same synthetic weights and inputs.
+fp32 mode: logits/loss within 1e-4 relative, global gradient L2-rel within 1e-4 (north_star);
+bf16 mode: logits within 1e-2-class relative error, gradients by global L2-rel + cosine
+(SURVEY.md section 8c parity protocol)."""
+import pytest
+import torch
+
+from oracle import restate, synth
+from tests.helpers import build_multimodal, build_unimodal, grad_report, oracle_grads, rel_err
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.mark.parametrize("dtype,tolv", [(torch.float32, 1e-4), (torch.bfloat16, 4e-2)])
+@pytest.mark.parametrize("hw", [(64, 128), (50, 77)])
+def test_encoder_forward(dtype, tolv, hw):
+    import omr_a2s_multimodal_transformer_b200 as pkg
+
+    enc = pkg.Encoder(1)
+    sd = synth.synth_state_dict(enc.state_dict(), seed=5)
+    enc.load_state_dict(sd)
+    enc = enc.to(DEV).eval()
+    enc.compute_dtype = dtype
+    x = torch.rand(2, 1, *hw, generator=torch.Generator().manual_seed(1))
+    ref = restate.encoder_forward(sd, "", x)
+    with torch.no_grad():
+        out = enc(x.to(DEV))
+    assert out.shape == ref.shape
+    assert rel_err(out.float(), ref) < tolv
+
+
+@pytest.mark.parametrize("dtype,tol_logit,tol_grad", [(torch.float32, 1e-4, 2e-4), (torch.bfloat16, 3e-2, 8e-2)])
+@pytest.mark.parametrize("window", [-1, 5])
+def test_unimodal_logits_loss_grads(dtype, tol_logit, tol_grad, window):
+    m, sd, w2i = build_unimodal(window=window, dtype=dtype)
+    x, xl, y_in, y_out = synth.synth_unimodal_batch(3, 64, 128, [20, 12, 7], w2i)
+    ref_logits = restate.unimodal_forward(sd, x, xl, y_in, attn_window=window)
+    with torch.no_grad():
+        logits = m(x.to(DEV), xl.to(DEV), y_in.to(DEV))
+    assert logits.shape == ref_logits.shape
+    assert rel_err(logits.float(), ref_logits) < tol_logit
+    ref_loss, ref_g = oracle_grads(lambda s: restate.ce_loss(restate.unimodal_forward(s, x, xl, y_in, attn_window=window), y_out), sd)
+    m.zero_grad(set_to_none=True)
+    loss = m.decoder.loss(tgt=y_in.to(DEV), memory=m.encode(x.to(DEV)), memory_len=xl.to(DEV), targets=y_out.to(DEV))
+    loss.backward()
+    assert abs(float(loss) - ref_loss) < tol_logit * max(1.0, abs(ref_loss))
+    rep = grad_report(m, ref_g)
+    assert not rep["missing"], rep
+    assert rep["global_rel"] < tol_grad and rep["cos"] > 1 - tol_grad, rep
+    # gradients through the public forward() ([B,V,T] logits + torch CE) agree with the fused loss path
+    g_fused = {k: p.grad.clone() for k, p in m.named_parameters()}
+    m.zero_grad(set_to_none=True)
+    lg = m(x.to(DEV), xl.to(DEV), y_in.to(DEV))
+    torch.nn.functional.cross_entropy(lg.float(), y_out.to(DEV), ignore_index=0).backward()
+    rep2 = grad_report(m, {k: v.cpu() for k, v in g_fused.items()})
+    assert rep2["global_rel"] < (1e-4 if dtype == torch.float32 else 3e-2), rep2
+
+
+@pytest.mark.parametrize("dtype,tol_logit,tol_grad", [(torch.float32, 1e-4, 2e-4), (torch.bfloat16, 3e-2, 8e-2)])
+@pytest.mark.parametrize("mixer", ["concat", "attn_img", "attn_audio", "attn_both"])
+def test_multimodal_logits_loss_grads(dtype, tol_logit, tol_grad, mixer):
+    m, sd, w2i = build_multimodal(mixer=mixer, dtype=dtype)
+    xi, xli, xa, xla, y_in, y_out = synth.synth_multimodal_batch(3, (64, 128), (48, 96), [20, 12, 7], w2i)
+    ref_logits = restate.multimodal_forward(sd, xi, xli, xa, xla, y_in, mixer_type=mixer)
+    with torch.no_grad():
+        logits = m(xi.to(DEV), xli.to(DEV), xa.to(DEV), xla.to(DEV), y_in.to(DEV))
+    assert rel_err(logits.float(), ref_logits) < tol_logit
+    ref_loss, ref_g = oracle_grads(
+        lambda s: restate.ce_loss(restate.multimodal_forward(s, xi, xli, xa, xla, y_in, mixer_type=mixer), y_out), sd)
+    m.zero_grad(set_to_none=True)
+    mem, xl = m._memory(xi.to(DEV), xa.to(DEV), xli.to(DEV), xla.to(DEV), "both")
+    loss = m.decoder.loss(tgt=y_in.to(DEV), memory=mem, memory_len=xl, targets=y_out.to(DEV))
+    loss.backward()
+    assert abs(float(loss) - ref_loss) < tol_logit * max(1.0, abs(ref_loss))
+    rep = grad_report(m, ref_g)
+    assert not rep["missing"], rep
+    assert rep["global_rel"] < tol_grad and rep["cos"] > 1 - tol_grad, rep
+
+
+@pytest.mark.parametrize("modality", ["image", "audio"])
+def test_multimodal_single_modality_and_inference_masks(modality):
+    """teacher-forcing modality drop (float +1.0 length masks) and the mask-free inference path"""
+    m, sd, w2i = build_multimodal(dtype=torch.float32)
+    xi, xli, xa, xla, y_in, y_out = synth.synth_multimodal_batch(2, (64, 128), (48, 96), [15, 9], w2i)
+    ref = restate.decoder_forward(sd, "decoder.", y_in, *restate.multimodal_memory(sd, xi, xa, xli, xla, "concat", modality))
+    with torch.no_grad():
+        mem, xl = m._memory(xi.to(DEV), xa.to(DEV), xli.to(DEV), xla.to(DEV), modality)
+        out = m.decoder(tgt=y_in.to(DEV), memory=mem, memory_len=xl.to(DEV))
+        ref_nomask = restate.multimodal_forward(sd, xi, None, xa, None, y_in)
+        out_nomask = m(xi.to(DEV), None, xa.to(DEV), None, y_in.to(DEV))
+        mem2, xl2 = m.encoder_forward(xi.to(DEV), xa.to(DEV), xli.to(DEV), xla.to(DEV))
+        _, ref_mask = restate.multimodal_memory(sd, xi, xa, xli, xla)
+    assert rel_err(out, ref) < 1e-4
+    assert rel_err(out_nomask, ref_nomask) < 1e-4
+    assert xl2.dtype == torch.bool and torch.equal(xl2.cpu(), ref_mask)
+
+
+@pytest.mark.parametrize("window", [-1, 4])
+def test_greedy_tokens_identical_fp32(window):
+    """KV-cached batched greedy decode == the reference's full-prefix batch-1 loop, token for token"""
+    m, sd, w2i = build_unimodal(window=window, max_len=24, dtype=torch.float32)
+    x = torch.rand(3, 1, 64, 128, generator=torch.Generator().manual_seed(9))
+    sos, eos = w2i["<sos>"], w2i["<eos>"]
+    refs = []
+    for b in range(3):
+        mem = restate.encode_to_memory(sd, "encoder.", "pos_2d.pe", x[b:b + 1])
+        refs.append(restate.greedy_decode(sd, mem, sos, eos, 24, attn_window=window))
+    for use_graph in (False, True):
+        toks, vals, lens = m._decoder_runner().decode(m.encode(x.to(DEV)), sos, eos, 0, use_graph=use_graph)
+        seqs, probs = m._decoder_runner().to_lists(toks, vals, lens)
+        for b in range(3):
+            assert seqs[b] == refs[b][0], (use_graph, b, seqs[b], refs[b][0])
+            assert max(abs(p - q) for p, q in zip(probs[b], refs[b][1])) < 1e-3
+    # Lightning-style batch-1 entry points
+    m.validation_step((x[:1].to(DEV), torch.tensor([[sos, 3, 4, eos]], device=DEV)), 0)
+    assert [w2i[t] for t in m.YHat[0]] == refs[0][0] and m.Y[0] == ["tok3", "tok4", "<eos>"]
+    words, pr = m.get_pred_seq_and_pred_prob_seq(x[1:2].to(DEV))
+    assert [w2i[t] for t in words] == refs[1][0]
+    metrics = m.on_validation_epoch_end()
+    assert set(metrics) == {"sym-er", "seq-er"} and m.Y == []
+
+
+def test_greedy_multimodal_bf16_runs_and_eos_stops():
+    m, sd, w2i = build_multimodal(dtype=torch.bfloat16, max_len=16)
+    xi, _, xa, _, _, _ = synth.synth_multimodal_batch(4, (64, 128), (48, 96), [5, 5, 5, 5], w2i)
+    toks, vals, lens = m.greedy_decode_batch(xi.to(DEV), xa.to(DEV))
+    assert toks.shape[0] == 4 and toks.shape[1] <= 16 and int(lens.max()) <= 16
+    full, _, l2 = m.greedy_decode_batch(xi.to(DEV), xa.to(DEV), stop_at_eos=False)
+    assert full.shape == (4, 16) and l2.tolist() == [16] * 4
+
+
+def test_training_step_with_fused_adam_matches_oracle_adam():
+    m, sd, w2i = build_multimodal(dtype=torch.float32)
+    xi, xli, xa, xla, y_in, y_out = synth.synth_multimodal_batch(2, (64, 128), (48, 96), [12, 9], w2i)
+    sdg = {k: (v.clone().requires_grad_(True) if torch.is_floating_point(v) and not k.endswith(".pe") else v) for k, v in sd.items()}
+    params = [v for v in sdg.values() if v.requires_grad]
+    ref_opt = torch.optim.Adam(params, lr=1e-4)
+    opt = m.configure_optimizers()
+    for _ in range(2):
+        ref_opt.zero_grad()
+        restate.ce_loss(restate.multimodal_forward(sdg, xi, xli, xa, xla, y_in), y_out).backward()
+        ref_opt.step()
+        opt.zero_grad(set_to_none=True)
+        mem, xl = m._memory(xi.to(DEV), xa.to(DEV), xli.to(DEV), xla.to(DEV), "both")
+        m.decoder.loss(tgt=y_in.to(DEV), memory=mem, memory_len=xl, targets=y_out.to(DEV)).backward()
+        opt.step()
+    worst = max(rel_err(p, sdg[k]) for k, p in m.named_parameters())
+    assert worst < 1e-5, worst
+
+
+def test_train_mode_dropout_runs_and_is_stochastic():
+    m, sd, w2i = build_multimodal(dtype=torch.bfloat16)
+    m.train()
+    batch = tuple(t.to(DEV) for t in synth.synth_multimodal_batch(2, (64, 128), (48, 96), [12, 9], w2i))
+    l1 = m.training_step(batch, 0)
+    l1.backward()
+    l2 = m.training_step(batch, 1)
+    assert torch.isfinite(l1) and torch.isfinite(l2) and float(l1) != float(l2)
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in m.decoder.parameters())
+
+
+def test_cpu_tensor_raises():
+    m, _, w2i = build_unimodal()
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m.encoder(torch.zeros(1, 1, 32, 32))

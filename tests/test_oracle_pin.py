@@ -1,0 +1,93 @@
+"""CPU, build container only: pins oracle/restate.py against the REAL reference imported from
+/root/reference (skipped where the reference tree is absent, e.g. on the GPU box)."""
+import pytest
+import torch
+
+from oracle import restate, shim, synth
+
+pytestmark = pytest.mark.skipif(not shim.reference_available(), reason="/root/reference not present")
+
+
+def rel(a, b):
+    return float((a.double() - b.double()).norm() / (b.double().norm() + 1e-300))
+
+
+@pytest.fixture(scope="module")
+def ref():
+    return shim.load_reference()
+
+
+def test_encoder_and_pe_tables(ref):
+    enc = ref.Encoder(1).eval()
+    sd = synth.synth_state_dict(enc.state_dict(), seed=5)
+    enc.load_state_dict(sd)
+    x = torch.rand(2, 1, 50, 77, generator=torch.Generator().manual_seed(1))
+    with torch.no_grad():
+        assert rel(restate.encoder_forward(sd, "", x), enc(x)) < 5e-6
+    assert torch.equal(restate.pe2d_table(256, 8, 16), ref.PositionalEncoding2D(256, 8, 16).pe)
+    assert torch.equal(restate.pe1d_table(40, 256), ref.PositionalEncoding1D(40, 256).pe)
+
+
+@pytest.mark.parametrize("mixer", ["concat", "attn_both"])
+def test_multimodal_forward_and_grads(ref, mixer):
+    w2i, i2w = synth.tiny_vocab(97)
+    m = ref.MultimodalTransformer(64, 128, 48, 96, 40, w2i, i2w, mixer_type=mixer).eval()
+    sd = synth.synth_state_dict(m.state_dict(), seed=3)
+    m.load_state_dict(sd)
+    xi, xli, xa, xla, y_in, y_out = synth.synth_multimodal_batch(3, (64, 128), (48, 96), [20, 12, 7], w2i)
+    out = m(xi, xli, xa, xla, y_in)
+    m.compute_loss(out, y_out).backward()
+    sdg = {k: (v.clone().requires_grad_(True) if torch.is_floating_point(v) and not k.endswith(".pe") else v) for k, v in sd.items()}
+    mine = restate.multimodal_forward(sdg, xi, xli, xa, xla, y_in, mixer_type=mixer)
+    restate.ce_loss(mine, y_out).backward()
+    assert rel(mine, out) < 5e-6
+    num = den = 0.0
+    for k, p in m.named_parameters():
+        num += float((sdg[k].grad.double() - p.grad.double()).pow(2).sum())
+        den += float(p.grad.double().pow(2).sum())
+    assert (num / den) ** 0.5 < 1e-4
+
+
+@pytest.mark.parametrize("modality", ["image", "audio"])
+def test_single_modality_memory_and_masks(ref, modality, monkeypatch):
+    w2i, i2w = synth.tiny_vocab(97)
+    m = ref.MultimodalTransformer(64, 128, 48, 96, 40, w2i, i2w).eval()
+    sd = synth.synth_state_dict(m.state_dict(), seed=3)
+    m.load_state_dict(sd)
+    xi, xli, xa, xla, y_in, _ = synth.synth_multimodal_batch(2, (64, 128), (48, 96), [15, 9], w2i)
+    monkeypatch.setattr(m, "apply_teacher_forcing_modality", lambda: modality)
+    with torch.no_grad():
+        out = m(xi, xli, xa, xla, y_in, apply_teacher_forcing_modality=True)
+        mine = restate.multimodal_forward(sd, xi, xli, xa, xla, y_in, modality=modality)
+    assert rel(mine, out) < 5e-6
+
+
+@pytest.mark.parametrize("window", [-1, 5])
+def test_greedy_loop(ref, window):
+    w2i, i2w = synth.tiny_vocab(97)
+    m = ref.Transformer(64, 128, 20, w2i, i2w, attn_window=window).eval()
+    sd = synth.synth_state_dict(m.state_dict(), seed=4)
+    m.load_state_dict(sd)
+    x = torch.rand(1, 1, 64, 128, generator=torch.Generator().manual_seed(2))
+    m.Y, m.YHat = [], []
+    m.validation_step((x, torch.tensor([[w2i["<sos>"], 5, w2i["<eos>"]]])), 0)
+    mem = restate.encode_to_memory(sd, "encoder.", "pos_2d.pe", x)
+    toks, vals = restate.greedy_decode(sd, mem, w2i["<sos>"], w2i["<eos>"], 20, attn_window=window)
+    assert [w2i[t] for t in m.YHat[0]] == toks
+    words, probs = m.get_pred_seq_and_pred_prob_seq(x)
+    assert [w2i[t] for t in words] == toks and max(abs(a - b) for a, b in zip(probs, vals)) < 1e-4
+
+
+def test_state_dict_surface_matches(ref):
+    import omr_a2s_multimodal_transformer_b200 as pkg
+
+    w2i, i2w = synth.load_vocab()
+    for mixer in ["concat", "attn_img"]:
+        a = ref.MultimodalTransformer(361, 4412, 195, 808, 1268, w2i, i2w, mixer_type=mixer).state_dict()
+        b = pkg.MultimodalTransformer(361, 4412, 195, 808, 1268, w2i, i2w, mixer_type=mixer).state_dict()
+        assert list(a.keys()) == list(b.keys())
+        assert all(a[k].shape == b[k].shape and a[k].dtype == b[k].dtype for k in a)
+        assert all(torch.equal(a[k], b[k]) for k in a if k.endswith(".pe"))
+    a = ref.Transformer(128, 1024, 1268, w2i, i2w).state_dict()
+    b = pkg.Transformer(128, 1024, 1268, w2i, i2w).state_dict()
+    assert list(a.keys()) == list(b.keys()) and sum(v.numel() for k, v in b.items() if not k.endswith(".pe")) == 10128309
