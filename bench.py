@@ -1,0 +1,362 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the hot path (contract: see DESIGN.md section 6).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 ... bench.py --gpus N ...
+
+Workload (BASELINE.json config 3, "C3" in SURVEY.md section 8d): multimodal concat model, full training step
+(forward + backward + fused Adam, train mode with dropout) in bf16, batch 32 PER GPU, image 1x128x1024,
+audio 1x195x808, target length 512, grandstaff vocabulary (V=6997), data-parallel over N GPUs (weak scaling).
+One JSON line is printed by rank 0; `value` is whole-job train samples/s with inputs resident in HBM, `e2e`
+the same through the public call with pinned host buffers (H2D of the batch and D2H of the loss inside the
+timed region).  The line also carries the greedy-decode leg (C4: batch 32 per GPU, S=2337, forced full length)
+under "decode", the per-entry-point roofline of the dominant kernel and the CPU baseline (oracle port of the
+reference, bounded sample, rank 0 / N=1 only).
+
+`--impl reference` times the reference's CPU implementation (its oracle port, oracle/restate.py -- the
+reference is Python and cannot travel to the GPU box) on the same workload shape with a bounded batch.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+IMG_HW, AUD_HW, T_LEN, BATCH = (128, 1024), (195, 808), 512, 32
+DEC_BATCH, MAX_LEN = 32, 1268
+METRIC, UNIT = "train_samples_per_s", "samples/s"
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        with open(p) as f:
+            d = json.load(f)
+        return dict(hbm=d["hbm_gbs"], tc_burst=d["bf16_tflops"], tc=d.get("bf16_tflops_sustained", d["bf16_tflops"]), src="measured")
+    return dict(hbm=6650.0, tc_burst=1590.0, tc=1400.0, src="fallback")
+
+
+# ------------------------------------------------------------------------------------------------------------
+# synthetic C3 batch: U[0,1) pixels, random lengths, uniform non-special token ids
+# ------------------------------------------------------------------------------------------------------------
+def make_batch(b, w2i, seed, t_len=T_LEN, img=IMG_HW, aud=AUD_HW):
+    g = torch.Generator().manual_seed(seed)
+    v = len(w2i)
+    sos, eos = w2i["<sos>"], w2i["<eos>"]
+    xi = torch.rand(b, 1, *img, generator=g)
+    xa = torch.rand(b, 1, *aud, generator=g)
+    li_max = -(-img[0] // 16) * -(-img[1] // 8)
+    la_max = -(-aud[0] // 16) * -(-aud[1] // 8)
+    xli = torch.randint(li_max // 2, li_max + 1, (b,), generator=g, dtype=torch.int32)
+    xla = torch.randint(la_max // 2, la_max + 1, (b,), generator=g, dtype=torch.int32)
+    lens = torch.randint(t_len // 4, t_len + 1, (b,), generator=g)
+    lens[0] = t_len
+    y = torch.zeros(b, t_len + 1, dtype=torch.int64)
+    for i in range(b):
+        n = int(lens[i])
+        body = torch.randint(1, min(sos, eos), (n - 1,), generator=g)
+        y[i, 0] = sos
+        y[i, 1:n] = body
+        y[i, n] = eos
+    return xi, xli, xa, xla, y[:, :-1].contiguous(), y[:, 1:].contiguous()
+
+
+def train_flops_per_sample(t=T_LEN):
+    """3 x forward: encoders 16.110 + 19.551 GFLOP, decoder closed form"""
+    d, s, L, ff, v = 256, 1024 + 1313, 8, 256, 6997
+    dec = L * (8 * t * d * d + 4 * t * t * d + 4 * t * d * d + 4 * s * d * d + 4 * t * s * d + 4 * t * d * ff) + 2 * t * d * v
+    return 3.0 * (16.110e9 + 19.551e9 + dec)
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            out, _ = self.p.communicate(timeout=5)
+        except Exception:
+            self.p.kill()
+            out = ""
+        sm, mx, reasons = [], 0.0, set()
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx = max(mx, float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        med = sm[len(sm) // 2] if sm else None
+        return {"sm_mhz": med, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------------
+# reference arm / CPU baseline: the oracle port of the reference (oracle/restate.py) on the host cores
+# ------------------------------------------------------------------------------------------------------------
+def cpu_reference_step_fn(w2i, batch):
+    from oracle import restate, synth
+    import omr_a2s_multimodal_transformer_b200 as pkg
+
+    i2w = {v: k for k, v in w2i.items()}
+    tmpl = pkg.MultimodalTransformer(IMG_HW[0], IMG_HW[1], AUD_HW[0], AUD_HW[1], MAX_LEN, w2i, i2w)
+    sd = synth.synth_state_dict(tmpl.state_dict(), seed=0)
+    del tmpl
+    sdg = {k: (v.clone().requires_grad_(True) if torch.is_floating_point(v) and not k.endswith(".pe") else v) for k, v in sd.items()}
+    opt = torch.optim.Adam([v for v in sdg.values() if v.requires_grad], lr=1e-4)
+    xi, xli, xa, xla, y_in, y_out = make_batch(batch, w2i, seed=1)
+
+    def step():
+        opt.zero_grad()
+        loss = restate.ce_loss(restate.multimodal_forward(sdg, xi, xli, xa, xla, y_in), y_out)
+        loss.backward()
+        opt.step()
+        return float(loss.detach())
+
+    return step
+
+
+def run_reference(args, w2i):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = torch.get_num_threads()
+    b = args.cpu_batch
+    step = cpu_reference_step_fn(w2i, b)
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    val = b * args.steps / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "C3 multimodal concat train step (fwd+bwd+Adam), image 1x128x1024 + audio 1x195x808, T=512, V=6997",
+                   "batch": b, "note": "reference CPU path = oracle port of the reference modules (oracle/restate.py), torch CPU fp32"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{args.steps} full training steps at batch {b} (same per-sample shapes as the GPU arm)"},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=BATCH, help="training batch per GPU")
+    ap.add_argument("--cpu-batch", type=int, default=2, help="batch of the CPU reference sample")
+    ap.add_argument("--no-decode", action="store_true", help="skip the greedy-decode leg")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline sample")
+    ap.add_argument("--decode-steps", type=int, default=MAX_LEN)
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
+    args = ap.parse_args()
+    from oracle import synth  # vocabulary loader + synthetic weights only (test infrastructure, not on the timed path)
+
+    w2i, i2w = synth.load_vocab()
+    if args.impl == "reference":
+        run_reference(args, w2i)
+        return
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the hot path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    import omr_a2s_multimodal_transformer_b200 as pkg
+    from omr_a2s_multimodal_transformer_b200 import _lib
+
+    dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
+    torch.manual_seed(0)
+    model = pkg.MultimodalTransformer(IMG_HW[0], IMG_HW[1], AUD_HW[0], AUD_HW[1], MAX_LEN, w2i, i2w, teacher_forcing_prob=0.2,
+                                      teacher_forcing_modality_prob=0.2)
+    model = model.to(dev)
+    model.set_compute_dtype(dtype)
+    model.train()
+    dp = pkg.DataParallel(model, broadcast=world > 1)
+    opt = model.configure_optimizers()
+    opt.grad_scale = dp.grad_scale
+    b = args.batch
+    host = [t.pin_memory() for t in make_batch(b, w2i, seed=100 + rank)]
+    resident = [t.to(dev) for t in host]
+    h2d = sum(t.numel() * t.element_size() for t in host)
+    stream = torch.cuda.current_stream(dev)
+
+    def step(batch):
+        xi, xli, xa, xla, y_in, y_out = batch
+        dp.zero_grad()
+        y_in = model.apply_teacher_forcing(y_in)
+        mem, xl = model._memory(xi, xa, xli, xla, "both")
+        loss = model.decoder.loss(tgt=y_in, memory=mem, memory_len=xl, targets=y_out)
+        loss.backward()
+        dp.sync_gradients()
+        opt.step()
+        return loss
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(fn, k):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record(stream)
+        for _ in range(k):
+            fn()
+        e1.record(stream)
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for _ in range(args.warmup):
+        step(resident)
+    sampler = ClockSampler(local) if rank == 0 else None
+    n0 = _lib.launch_count()
+    ms = timed(lambda: step(resident), args.steps)
+    launches = _lib.launch_count() - n0
+    clocks = sampler.stop() if sampler else None
+    value = world * b * args.steps / (ms / 1e3)
+
+    def e2e_step():
+        batch = [t.to(dev, non_blocking=True) for t in host]
+        loss = step(batch)
+        return float(loss.item())  # device -> host read of the step's result
+
+    e2e_step()
+    ms_e2e = timed(e2e_step, args.steps)
+    e2e_val = world * b * args.steps / (ms_e2e / 1e3)
+
+    # per-entry-point device times of ONE more step (CUDA events around every C-ABI call on the launching stream)
+    barrier()
+    _lib.prof_start()
+    step(resident)
+    prof = _lib.prof_stop()
+    tot_ms = sum(d["ms"] for d in prof.values()) or 1e-9
+    pk = peaks()
+    top_name, top = max(prof.items(), key=lambda kv: kv[1]["ms"])
+    ai = top["flops"] / max(top["bytes"], 1.0)
+    if top["flops"] > 0 and ai > pk["tc"] * 1e12 / (pk["hbm"] * 1e9) * 0.25:
+        roof = {"bound": "tensor", "achieved": top["flops"] / (top["ms"] * 1e-3) / 1e12, "peak": pk["tc"], "unit": "TFLOP/s"}
+    else:
+        roof = {"bound": "hbm", "achieved": top["bytes"] / (top["ms"] * 1e-3) / 1e9, "peak": pk["hbm"], "unit": "GB/s"}
+    roof["frac"] = roof["achieved"] / roof["peak"]
+    roof.update({"kernel": top_name, "calls_per_step": top["calls"], "avg_ms": top["ms"] / max(top["calls"], 1),
+                 "share_of_step": top["ms"] / tot_ms, "peak_source": pk["src"] + (" (sustained bf16)" if roof["bound"] == "tensor" else ""),
+                 "traffic": None})
+    breakdown = {k: {"ms": round(d["ms"], 3), "calls": d["calls"],
+                     "tflops": round(d["flops"] / (d["ms"] * 1e-3) / 1e12, 2) if d["flops"] else None,
+                     "gbs": round(d["bytes"] / (d["ms"] * 1e-3) / 1e9, 1) if d["bytes"] else None}
+                 for k, d in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])[:12]}
+
+    decode = None
+    if not args.no_decode:
+        model.eval()
+        torch.cuda.empty_cache()
+        db = DEC_BATCH
+        xi, _, xa, _, _, _ = make_batch(db, w2i, seed=500 + rank)
+        with torch.no_grad():
+            mem, _ = model._memory(xi.to(dev), xa.to(dev), None, None, "both")
+            runner = model._decoder_runner()
+            nsteps = args.decode_steps
+            runner.decode(mem, w2i["<sos>"], w2i["<eos>"], 0, max_steps=min(nsteps, 16), stop_at_eos=False)  # warm-up
+            n0 = _lib.launch_count()
+            holder = {}
+
+            def dec():
+                holder["out"] = runner.decode(mem, w2i["<sos>"], w2i["<eos>"], 0, max_steps=nsteps, stop_at_eos=False)
+
+            ms_dec = timed(dec, 1)
+            toks = holder["out"][0]
+        decode = {"metric": "greedy_decode_tokens_per_s", "value": world * db * toks.shape[1] / (ms_dec / 1e3), "unit": "tokens/s",
+                  "batch_per_gpu": db, "steps": int(toks.shape[1]), "memory_len": int(mem.shape[1]), "ms": ms_dec,
+                  "includes": "cross-K/V projection of the memory + CUDA-graph capture + all decode steps",
+                  "hbm_roofline_tokens_per_s_per_gpu": pk["hbm"] * 1e9 / 24.7e6}
+        model.train()
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cstep = cpu_reference_step_fn(w2i, args.cpu_batch)
+        cstep()
+        t0 = time.perf_counter()
+        n = 0
+        while n < 2 or (time.perf_counter() - t0 < 10.0 and n < 8):
+            cstep()
+            n += 1
+        dtc = time.perf_counter() - t0
+        cpu = {"value": args.cpu_batch * n / dtc, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+               "sample": f"{n} full training steps at batch {args.cpu_batch} of the same per-sample shapes (oracle port of the reference, torch CPU fp32)"}
+
+    if rank == 0:
+        flops_step = train_flops_per_sample() * b
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": args.dtype, "data": "synthetic",
+            "config": {"workload": "C3 multimodal concat train step (fwd+bwd+fused Adam, train mode), image 1x128x1024 + audio 1x195x808, T=512, V=6997",
+                       "batch_per_gpu": b, "global_batch": b * world, "parallelism": f"dp{world}",
+                       "l2": "per-step working set (activations, several GB) is far larger than the 126 MB L2; no flush needed"},
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "model_tflops_per_gpu": flops_step / (ms / args.steps * 1e-3) / 1e12,
+            "model_tc_frac_of_sustained_peak": flops_step / (ms / args.steps * 1e-3) / 1e12 / pk["tc"],
+            "roofline": roof,
+            "breakdown_ms": breakdown,
+            "decode": decode,
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -46,6 +46,8 @@ const char* omr_last_error(void);
 /* 1 when the tcgen05/TMA kernels are compiled in and enabled (env OMR_FORCE_SIMT=1 disables). */
 int omr_tensor_core_path_enabled(void);
 void omr_set_tensor_core_path(int enabled);
+/* number of C-ABI calls served by a tcgen05/TMA kernel since load (tests assert the tensor-core path ran). */
+long long omr_tc_call_count(void);
 /* number of kernels this library launched since load (bench.py's gpu_launches). */
 long long omr_launch_count(void);
 
@@ -90,11 +92,12 @@ int omr_dwconv3x3_wgrad(int dt, const void* x, const void* dy, float* dw, float*
                         int accumulate, omr_stream_t stream);
 
 /* nn.InstanceNorm2d(eps, affine=False) (encoder.py:151-156, 210-215) on NHWC.
- * stats[N,C,2] fp32 receives (mean, rstd). */
-int omr_instnorm_fwd(int dt, const void* x, void* y, float* stats, int N, int HW, int C, float eps,
+ * stats[N,C,2] fp32 receives (mean, rstd); ws: fp64 scratch of N*C*2 doubles (the plane sums are
+ * combined in double so that E[x^2]-E[x]^2 and the backward's mean subtractions do not cancel). */
+int omr_instnorm_fwd(int dt, const void* x, void* y, float* stats, double* ws, int N, int HW, int C, float eps,
                      omr_stream_t stream);
-/* dx from dy, the saved INPUT x and stats; ws: fp32 scratch of N*C*2 floats */
-int omr_instnorm_bwd(int dt, const void* dy, const void* x, const float* stats, void* dx, float* ws, int N, int HW,
+/* dx from dy, the saved INPUT x and stats; ws: fp64 scratch of N*C*2 doubles */
+int omr_instnorm_bwd(int dt, const void* dy, const void* x, const float* stats, void* dx, double* ws, int N, int HW,
                      int C, omr_stream_t stream);
 
 /* PositionalEncoding2D + flatten/permute + concat (model.py:45-48, 498, 506, 654):

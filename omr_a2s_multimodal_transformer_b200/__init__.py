@@ -5,6 +5,7 @@ transformer decoder -> vocabulary projection / cross-entropy -> batched greedy d
 The Python classes mirror the reference's ``src/transformer`` surface; every operator runs in
 ``libomr_b200.so`` (hand-written CUDA, C ABI in ``include/omr_b200.h``).  There is no CPU path.
 """
+from .ddp import BucketReducer, DataParallel
 from .decoder import Decoder, PositionalEncoding1D
 from .encoder import HEIGHT_REDUCTION, WIDTH_REDUCTION, ConvBlock, DepthSepConv2D, DSCBlock, Encoder, MixDropout
 from .greedy import BatchedGreedyDecoder
@@ -16,5 +17,5 @@ from .params import GradArena
 __all__ = [
     "Decoder", "PositionalEncoding1D", "Encoder", "ConvBlock", "DSCBlock", "DepthSepConv2D", "MixDropout",
     "PositionalEncoding2D", "CrossAttention", "Transformer", "MultimodalTransformer", "BatchedGreedyDecoder",
-    "FusedAdam", "GradArena", "HEIGHT_REDUCTION", "WIDTH_REDUCTION", "SOS_TOKEN", "EOS_TOKEN", "NUM_CHANNELS",
+    "FusedAdam", "GradArena", "DataParallel", "BucketReducer", "HEIGHT_REDUCTION", "WIDTH_REDUCTION", "SOS_TOKEN", "EOS_TOKEN", "NUM_CHANNELS",
 ]

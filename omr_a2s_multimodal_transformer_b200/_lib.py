@@ -29,7 +29,7 @@ _SIGS = {
     "omr_dwconv3x3_fwd": "ippppiiiip",
     "omr_dwconv3x3_dgrad": "ipppiiiip",
     "omr_dwconv3x3_wgrad": "ippppiiiiip",
-    "omr_instnorm_fwd": "ipppiiifp",
+    "omr_instnorm_fwd": "ippppiiifp",
     "omr_instnorm_bwd": "ipppppiiip",
     "omr_pe2d_add": "ipppiiiiiiip",
     "omr_copy_rows": "ippiiiiip",
@@ -71,6 +71,7 @@ def load() -> ctypes.CDLL:
     lib.omr_last_error.restype = c_char_p
     lib.omr_abi_version.restype = c_int
     lib.omr_launch_count.restype = c_longlong
+    lib.omr_tc_call_count.restype = c_longlong
     lib.omr_tensor_core_path_enabled.restype = c_int
     lib.omr_set_tensor_core_path.argtypes = [c_int]
     for name, sig in _SIGS.items():
@@ -82,7 +83,8 @@ def load() -> ctypes.CDLL:
 
 
 def exported_symbols():
-    return ["omr_abi_version", "omr_last_error", "omr_launch_count", "omr_tensor_core_path_enabled"] + list(_SIGS)
+    return ["omr_abi_version", "omr_last_error", "omr_launch_count", "omr_tc_call_count", "omr_tensor_core_path_enabled",
+            "omr_set_tensor_core_path"] + list(_SIGS)
 
 
 def check(rc: int, what: str) -> None:
@@ -92,7 +94,101 @@ def check(rc: int, what: str) -> None:
 
 
 def call(name: str, *args) -> None:
+    if _prof is None:
+        check(getattr(load(), name)(*args), name)
+        return
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n0 = launch_count()
+    e0.record()
     check(getattr(load(), name)(*args), name)
+    e1.record()
+    _prof.append((name, _work(name, args), launch_count() - n0, e0, e1))
+
+
+# ---- per-entry-point device timing (bench.py's roofline block; a poor man's timeline) ------------------
+_prof = None
+_ESZ = {F32: 4, BF16: 2}
+
+
+def _work(name: str, a) -> tuple:
+    """(algorithmic flops, algorithmic bytes) of one C-ABI call, from its arguments."""
+    try:
+        if name == "omr_gemm":
+            m, n, k, batch = a[4], a[5], a[6], a[16]
+            return 2.0 * m * n * k * batch, float(batch) * (_ESZ[a[0]] * (m * k + n * k) + _ESZ[a[1]] * m * n)
+        if name in ("omr_conv3x3_fwd", "omr_conv3x3_dgrad", "omr_conv3x3_wgrad"):
+            if name == "omr_conv3x3_fwd":
+                nb, h, w, ci, co, sh, sw = a[5:12]
+            elif name == "omr_conv3x3_dgrad":
+                nb, h, w, ci, co, sh, sw = a[4:11]
+            else:
+                nb, h, w, ci, co, sh, sw = a[5:12]
+            ho, wo = -(-h // sh), -(-w // sw)
+            e = _ESZ[a[0]]
+            return 2.0 * nb * ho * wo * co * 9 * ci, float(e) * nb * (h * w * ci + ho * wo * co) + 4.0 * 9 * ci * co
+        if name == "omr_attn_fwd":
+            b, h, tq, tk, hd = a[15:20]
+            return 4.0 * b * h * tq * tk * hd, float(_ESZ[a[0]]) * b * h * hd * (2 * tq + 2 * tk)
+        if name == "omr_attn_bwd":
+            b, h, tq, tk, hd = a[28:33]
+            return 10.0 * b * h * tq * tk * hd, float(_ESZ[a[0]]) * b * h * hd * (4 * tq + 4 * tk)
+        if name in ("omr_dwconv3x3_fwd", "omr_dwconv3x3_dgrad"):
+            off = 5 if name.endswith("fwd") else 4
+            nb, h, w, c = a[off:off + 4]
+            return 18.0 * nb * h * w * c, 2.0 * _ESZ[a[0]] * nb * h * w * c
+        if name == "omr_dwconv3x3_wgrad":
+            nb, h, w, c = a[5:9]
+            return 18.0 * nb * h * w * c, 2.0 * _ESZ[a[0]] * nb * h * w * c
+        if name == "omr_instnorm_fwd":
+            nb, hw, c = a[5:8]
+            return 0.0, 3.0 * _ESZ[a[0]] * nb * hw * c  # read (stats), read + write (apply)
+        if name == "omr_instnorm_bwd":
+            nb, hw, c = a[6:9]
+            return 0.0, 5.0 * _ESZ[a[0]] * nb * hw * c
+        if name in ("omr_relu_bwd", "omr_add"):
+            return 0.0, 3.0 * _ESZ[a[0]] * a[4]
+        if name == "omr_dropout":
+            return 0.0, 2.0 * _ESZ[a[0]] * a[3]
+        if name == "omr_cast":
+            return 0.0, float(_ESZ[a[0]] + _ESZ[a[1]]) * a[4]
+        if name == "omr_add_layernorm_fwd":
+            return 0.0, 4.0 * _ESZ[a[0]] * a[8] * a[9]
+        if name == "omr_layernorm_bwd":
+            return 0.0, 3.0 * _ESZ[a[0]] * a[8] * a[9]
+        if name == "omr_ce_fwd":
+            return 0.0, float(_ESZ[a[0]]) * a[4] * a[5]
+        if name == "omr_ce_bwd":
+            return 0.0, 2.0 * _ESZ[a[0]] * a[8] * a[9]
+        if name == "omr_adam_step":
+            return 0.0, 0.0  # filled in by the caller (needs the parameter count)
+        if name == "omr_attn_decode":
+            b, h, tk, hd = a[15:19]
+            return 4.0 * b * h * tk * hd, 2.0 * _ESZ[a[0]] * b * h * tk * hd
+    except Exception:
+        pass
+    return 0.0, 0.0
+
+
+def prof_start() -> None:
+    """start timing every C-ABI call with CUDA events on the current stream (bench.py only)"""
+    global _prof
+    _prof = []
+
+
+def prof_stop() -> dict:
+    """-> {entry point: {calls, launches, ms, flops, bytes}} summed over the calls since prof_start()"""
+    global _prof
+    recs, _prof = _prof or [], None
+    torch.cuda.synchronize()
+    out = {}
+    for name, (fl, by), nl, e0, e1 in recs:
+        d = out.setdefault(name, {"calls": 0, "launches": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0})
+        d["calls"] += 1
+        d["launches"] += nl
+        d["ms"] += e0.elapsed_time(e1)
+        d["flops"] += fl
+        d["bytes"] += by
+    return out
 
 
 def dt_code(dtype: torch.dtype) -> int:
@@ -113,6 +209,10 @@ def ptr(t) -> int:
 
 def launch_count() -> int:
     return int(load().omr_launch_count())
+
+
+def tc_call_count() -> int:
+    return int(load().omr_tc_call_count())
 
 
 def require_cuda(t: torch.Tensor, what: str) -> None:

@@ -13,6 +13,16 @@ static bool tc_enabled() {
   }
   return g_tc_enabled == 1;
 }
+static long long g_tc_calls = 0;
+extern "C" long long omr_tc_call_count(void) { return g_tc_calls; }
+#define TC_TRY(call)                        \
+  do {                                      \
+    int rc__ = (call);                      \
+    if (rc__ != OMR_TC_NOT_ELIGIBLE) {      \
+      if (rc__ == OMR_OK) ++g_tc_calls;     \
+      return rc__;                          \
+    }                                       \
+  } while (0)
 extern "C" int omr_tensor_core_path_enabled(void) { return tc_enabled() ? 1 : 0; }
 extern "C" void omr_set_tensor_core_path(int enabled) { g_tc_enabled = enabled ? 1 : 0; }
 
@@ -24,9 +34,8 @@ extern "C" int omr_gemm(int in_dt, int out_dt, int transA, int transB, int M, in
   if (M == 0 || N == 0 || batch == 0) return OMR_OK;
   cudaStream_t st = as_stream(stream);
   if (tc_enabled() && in_dt == OMR_BF16) {
-    int rc = omr_gemm_tc(out_dt, transA, transB, M, N, K, A, lda, strideA, B, ldb, strideB, C, ldc, strideC, batch, bias,
-                         bias_mode, relu, accumulate, st);
-    if (rc != OMR_TC_NOT_ELIGIBLE) return rc;
+    TC_TRY(omr_gemm_tc(out_dt, transA, transB, M, N, K, A, lda, strideA, B, ldb, strideB, C, ldc, strideC, batch, bias,
+                         bias_mode, relu, accumulate, st));
   }
   return omr_gemm_simt(in_dt, out_dt, transA, transB, M, N, K, A, lda, strideA, B, ldb, strideB, C, ldc, strideC, batch,
                        bias, bias_mode, relu, accumulate, st);
@@ -37,8 +46,7 @@ extern "C" int omr_conv3x3_fwd(int dt, const void* x, const void* w, const float
   OMR_REQUIRE(N >= 0 && H > 0 && W > 0 && Ci > 0 && Co > 0 && sh > 0 && sw > 0, "omr_conv3x3_fwd: bad shape");
   cudaStream_t st = as_stream(stream);
   if (tc_enabled() && dt == OMR_BF16) {
-    int rc = omr_conv3x3_fwd_tc(x, w, bias, y, N, H, W, Ci, Co, sh, sw, relu, st);
-    if (rc != OMR_TC_NOT_ELIGIBLE) return rc;
+    TC_TRY(omr_conv3x3_fwd_tc(x, w, bias, y, N, H, W, Ci, Co, sh, sw, relu, st));
   }
   return omr_conv3x3_fwd_simt(dt, x, w, bias, y, N, H, W, Ci, Co, sh, sw, relu, st);
 }
@@ -48,8 +56,7 @@ extern "C" int omr_conv3x3_dgrad(int dt, const void* dy, const void* wT, void* d
   OMR_REQUIRE(N >= 0 && H > 0 && W > 0 && Ci > 0 && Co > 0 && sh > 0 && sw > 0, "omr_conv3x3_dgrad: bad shape");
   cudaStream_t st = as_stream(stream);
   if (tc_enabled() && dt == OMR_BF16) {
-    int rc = omr_conv3x3_dgrad_tc(dy, wT, dx, N, H, W, Ci, Co, sh, sw, st);
-    if (rc != OMR_TC_NOT_ELIGIBLE) return rc;
+    TC_TRY(omr_conv3x3_dgrad_tc(dy, wT, dx, N, H, W, Ci, Co, sh, sw, st));
   }
   return omr_conv3x3_dgrad_simt(dt, dy, wT, dx, N, H, W, Ci, Co, sh, sw, st);
 }
@@ -64,8 +71,7 @@ extern "C" int omr_conv3x3_wgrad(int dt, const void* x, const void* dy, float* d
     if (rc) return rc;
   }
   if (tc_enabled() && dt == OMR_BF16) {
-    int rc = omr_conv3x3_wgrad_tc(x, dy, dw, N, H, W, Ci, Co, sh, sw, accumulate, st);
-    if (rc != OMR_TC_NOT_ELIGIBLE) return rc;
+    TC_TRY(omr_conv3x3_wgrad_tc(x, dy, dw, N, H, W, Ci, Co, sh, sw, accumulate, st));
   }
   return omr_conv3x3_wgrad_simt(dt, x, dy, dw, N, H, W, Ci, Co, sh, sw, accumulate, st);
 }
@@ -77,9 +83,8 @@ extern "C" int omr_attn_fwd(int dt, const void* q, long long q_bs, long long q_r
                             omr_stream_t stream) {
   cudaStream_t st = as_stream(stream);
   if (tc_enabled() && dt == OMR_BF16) {
-    int rc = omr_attn_fwd_tc(q, q_bs, q_rs, k, k_bs, k_rs, v, v_bs, v_rs, o, o_bs, o_rs, lse, key_bias, B, H, Tq, Tk, hd,
-                             scale, causal, window, q_len, kv_len, quirk_mod, st);
-    if (rc != OMR_TC_NOT_ELIGIBLE) return rc;
+    TC_TRY(omr_attn_fwd_tc(q, q_bs, q_rs, k, k_bs, k_rs, v, v_bs, v_rs, o, o_bs, o_rs, lse, key_bias, B, H, Tq, Tk, hd,
+                             scale, causal, window, q_len, kv_len, quirk_mod, st));
   }
   return omr_attn_fwd_simt(dt, q, q_bs, q_rs, k, k_bs, k_rs, v, v_bs, v_rs, o, o_bs, o_rs, lse, key_bias, B, H, Tq, Tk,
                            hd, scale, causal, window, q_len, kv_len, quirk_mod, st);

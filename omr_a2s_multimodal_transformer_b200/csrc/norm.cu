@@ -11,7 +11,7 @@ namespace {
 // MODE 0: (sum x, sum x^2).  MODE 1: (sum dy, sum dy * xhat) with xhat from saved stats.
 template <typename T, int MODE>
 __global__ void __launch_bounds__(256) in_partial_kernel(const T* __restrict__ a, const T* __restrict__ xin,
-                                                         const float* __restrict__ stats, float* __restrict__ out,
+                                                         const float* __restrict__ stats, double* __restrict__ out,
                                                          int HW, int C, int CT, int rows_per_block) {
   __shared__ float sm0[256], sm1[256];
   const int n = blockIdx.y;
@@ -40,20 +40,24 @@ __global__ void __launch_bounds__(256) in_partial_kernel(const T* __restrict__ a
   sm0[threadIdx.x] = s0; sm1[threadIdx.x] = s1;
   __syncthreads();
   if (rl == 0) {
-    for (int k = 1; k < RS; ++k) { s0 += sm0[k * CT + cl]; s1 += sm1[k * CT + cl]; }
-    atomicAdd(out + ((long long)n * C + c) * 2, s0);
-    atomicAdd(out + ((long long)n * C + c) * 2 + 1, s1);
+    // block partials are combined in double: the variance E[x^2] - E[x]^2 and the backward's mean
+    // subtractions are cancellation-prone, and fp32 parity (1e-4 on gradients) needs them clean
+    double d0 = s0, d1 = s1;
+    for (int k = 1; k < RS; ++k) { d0 += (double)sm0[k * CT + cl]; d1 += (double)sm1[k * CT + cl]; }
+    atomicAdd(out + ((long long)n * C + c) * 2, d0);
+    atomicAdd(out + ((long long)n * C + c) * 2 + 1, d1);
   }
 }
 
-__global__ void in_finalize_kernel(float* __restrict__ stats, long long NC, float inv_hw, float eps) {
+__global__ void in_finalize_kernel(const double* __restrict__ sums, float* __restrict__ stats, long long NC,
+                                   double inv_hw, double eps) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < NC) {
-    float mean = stats[i * 2] * inv_hw;
-    float var = stats[i * 2 + 1] * inv_hw - mean * mean;
-    var = fmaxf(var, 0.f);
-    stats[i * 2] = mean;
-    stats[i * 2 + 1] = rsqrtf(var + eps);
+    double mean = sums[i * 2] * inv_hw;
+    double var = sums[i * 2 + 1] * inv_hw - mean * mean;
+    var = var > 0.0 ? var : 0.0;
+    stats[i * 2] = (float)mean;
+    stats[i * 2 + 1] = (float)(1.0 / sqrt(var + eps));
   }
 }
 
@@ -79,8 +83,8 @@ __global__ void in_apply_fwd_kernel(const T* __restrict__ x, const float* __rest
 
 template <typename T>
 __global__ void in_apply_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const float* __restrict__ stats,
-                                    const float* __restrict__ sums, T* __restrict__ dx, int N, int HW, int C,
-                                    float inv_hw) {
+                                    const double* __restrict__ sums, T* __restrict__ dx, int N, int HW, int C,
+                                    double inv_hw) {
   const int c4n = C / 4;
   long long total = (long long)N * HW * c4n;
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -93,12 +97,12 @@ __global__ void in_apply_bwd_kernel(const T* __restrict__ dy, const T* __restric
     load4(dy + p * C + c4 * 4, g);
     load4(x + p * C + c4 * 4, v);
     const float* s = stats + ((long long)n * C + c4 * 4) * 2;
-    const float* q = sums + ((long long)n * C + c4 * 4) * 2;
+    const double* q = sums + ((long long)n * C + c4 * 4) * 2;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       float rstd = s[2 * k + 1];
       float xh = (v[k] - s[2 * k]) * rstd;
-      v[k] = rstd * (g[k] - q[2 * k] * inv_hw - xh * q[2 * k + 1] * inv_hw);
+      v[k] = rstd * (g[k] - (float)(q[2 * k] * inv_hw) - xh * (float)(q[2 * k + 1] * inv_hw));
     }
     store4(dx + p * C + c4 * 4, v);
   }
@@ -212,21 +216,22 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const T* __restrict__ dy, c
 
 }  // namespace
 
-extern "C" int omr_instnorm_fwd(int dt, const void* x, void* y, float* stats, int N, int HW, int C, float eps,
-                                omr_stream_t stream) {
+extern "C" int omr_instnorm_fwd(int dt, const void* x, void* y, float* stats, double* ws, int N, int HW, int C,
+                                float eps, omr_stream_t stream) {
   int CT = pick_ct(C);
   OMR_REQUIRE(CT > 0 && C % 4 == 0, "omr_instnorm_fwd: unsupported channel count %d", C);
   if ((long long)N * HW * C <= 0) return OMR_OK;
   cudaStream_t st = as_stream(stream);
-  OMR_CUDA(cudaMemsetAsync(stats, 0, sizeof(float) * (size_t)N * C * 2, st));
+  OMR_CUDA(cudaMemsetAsync(ws, 0, sizeof(double) * (size_t)N * C * 2, st));
   int RS = 256 / CT;
   int rpb = (int)cdiv(HW, cdiv(148LL * 8, (long long)N * (C / CT)));
   if (rpb < RS * 8) rpb = RS * 8;
   dim3 grid((unsigned)cdiv(HW, rpb), (unsigned)N, (unsigned)(C / CT));
-  OMR_DISPATCH_DT(dt, T, (in_partial_kernel<T, 0><<<grid, 256, 0, st>>>((const T*)x, nullptr, nullptr, stats, HW, C, CT,
+  OMR_DISPATCH_DT(dt, T, (in_partial_kernel<T, 0><<<grid, 256, 0, st>>>((const T*)x, nullptr, nullptr, ws, HW, C, CT,
                                                                         rpb)));
   OMR_LAUNCHED();
-  in_finalize_kernel<<<(int)cdiv((long long)N * C, 256), 256, 0, st>>>(stats, (long long)N * C, 1.f / HW, eps);
+  in_finalize_kernel<<<(int)cdiv((long long)N * C, 256), 256, 0, st>>>(ws, stats, (long long)N * C, 1.0 / HW,
+                                                                                (double)eps);
   OMR_LAUNCHED();
   long long total = (long long)N * HW * (C / 4);
   OMR_DISPATCH_DT(dt, T, (in_apply_fwd_kernel<T><<<grid_cap(total), 256, 0, st>>>((const T*)x, stats, (T*)y, N, HW, C)));
@@ -234,13 +239,13 @@ extern "C" int omr_instnorm_fwd(int dt, const void* x, void* y, float* stats, in
   return OMR_OK;
 }
 
-extern "C" int omr_instnorm_bwd(int dt, const void* dy, const void* x, const float* stats, void* dx, float* ws, int N,
+extern "C" int omr_instnorm_bwd(int dt, const void* dy, const void* x, const float* stats, void* dx, double* ws, int N,
                                 int HW, int C, omr_stream_t stream) {
   int CT = pick_ct(C);
   OMR_REQUIRE(CT > 0 && C % 4 == 0, "omr_instnorm_bwd: unsupported channel count %d", C);
   if ((long long)N * HW * C <= 0) return OMR_OK;
   cudaStream_t st = as_stream(stream);
-  OMR_CUDA(cudaMemsetAsync(ws, 0, sizeof(float) * (size_t)N * C * 2, st));
+  OMR_CUDA(cudaMemsetAsync(ws, 0, sizeof(double) * (size_t)N * C * 2, st));
   int RS = 256 / CT;
   int rpb = (int)cdiv(HW, cdiv(148LL * 8, (long long)N * (C / CT)));
   if (rpb < RS * 8) rpb = RS * 8;
@@ -250,7 +255,7 @@ extern "C" int omr_instnorm_bwd(int dt, const void* dy, const void* x, const flo
   OMR_LAUNCHED();
   long long total = (long long)N * HW * (C / 4);
   OMR_DISPATCH_DT(dt, T, (in_apply_bwd_kernel<T><<<grid_cap(total), 256, 0, st>>>((const T*)dy, (const T*)x, stats, ws,
-                                                                                 (T*)dx, N, HW, C, 1.f / HW)));
+                                                                                 (T*)dx, N, HW, C, 1.0 / HW)));
   OMR_LAUNCHED();
   return OMR_OK;
 }

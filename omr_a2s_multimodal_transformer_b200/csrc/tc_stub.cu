@@ -16,10 +16,7 @@ int omr_conv3x3_wgrad_tc(const void*, const void*, float*, int, int, int, int, i
 }
 #endif
 #ifndef OMR_HAVE_TC_GEMM
-int omr_gemm_tc(int, int, int, int, int, int, const void*, long long, long long, const void*, long long, long long,
-                void*, long long, long long, int, const float*, int, int, int, cudaStream_t) {
-  return OMR_TC_NOT_ELIGIBLE;
-}
+
 #endif
 #ifndef OMR_HAVE_TC_ATTN
 int omr_attn_fwd_tc(const void*, long long, long long, const void*, long long, long long, const void*, long long,

@@ -87,6 +87,7 @@ class _DecoderStackFn(torch.autograd.Function):
         tape: List = []
         y = dec._run_stack(tgt, memory, mem_bias, tgt_bias, dtype, tape, training)
         ctx.tape = tape
+        ctx.dec = dec
         ctx.mem_shape = memory.shape
         return y
 
@@ -99,6 +100,9 @@ class _DecoderStackFn(torch.autograd.Function):
         state = {"g": dy.contiguous().clone(), "dmem": None, "need_dmem": need_dmem}
         while tape:
             tape.pop()(state)
+        cb = getattr(ctx.dec, "_bwd_done_cb", None)
+        if cb is not None:  # data-parallel: the decoder's gradient bucket is complete (ddp.py)
+            cb()
         return (state["dmem"], None, None, None, None, None, None) + tuple(None for _ in ctx.needs_input_grad[7:])
 
 

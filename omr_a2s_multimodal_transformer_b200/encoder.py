@@ -213,6 +213,7 @@ class _EncoderFn(torch.autograd.Function):
         tape: List = []
         y = enc._run(x_nhwc, dtype, tape, training)
         ctx.tape = tape
+        ctx.enc = enc
         return y
 
     @staticmethod
@@ -224,6 +225,9 @@ class _EncoderFn(torch.autograd.Function):
         while tape:
             step = tape.pop()
             g = step(g)
+        cb = getattr(ctx.enc, "_bwd_done_cb", None)
+        if cb is not None:  # data-parallel: this encoder's gradient bucket is complete (ddp.py)
+            cb()
         return (None, None, None, None) + tuple(None for _ in ctx.needs_input_grad[4:])
 
 

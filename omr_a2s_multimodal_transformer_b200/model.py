@@ -213,7 +213,21 @@ class _ModelBase(LightningModule):
     def configure_optimizers(self):
         """Adam(lr=1e-4, amsgrad=False) over encoders + decoder (+ cross_attn), reference model.py:134-139,475-483;
         executed as one fused multi-tensor kernel."""
-        return FusedAdam(self._optimizer_params(), lr=1e-4)
+        opt = FusedAdam(self._optimizer_params(), lr=1e-4)
+        caches = [m._wcache for m in self.modules() if isinstance(m, (Encoder, Decoder, CrossAttention))]
+
+        def shadows(p):
+            out = []
+            for c in caches:
+                out += c.shadows(p)
+            return out
+
+        def mark_fresh(p):
+            for c in caches:
+                c.mark_fresh(p)
+
+        opt.register_shadow_provider(shadows, mark_fresh)
+        return opt
 
     def summary(self) -> None:
         for name, mod in self.named_children():

@@ -146,7 +146,8 @@ def instnorm_fwd(x, eps: float):
     n, h, w, c = x.shape
     y = torch.empty_like(x)
     stats = torch.empty((n, c, 2), dtype=torch.float32, device=x.device)
-    call("omr_instnorm_fwd", dt_code(x.dtype), ptr(x), ptr(y), ptr(stats), n, h * w, c, float(eps), stream_ptr())
+    ws = torch.empty((n, c, 2), dtype=torch.float64, device=x.device)
+    call("omr_instnorm_fwd", dt_code(x.dtype), ptr(x), ptr(y), ptr(stats), ptr(ws), n, h * w, c, float(eps), stream_ptr())
     return y, stats
 
 
@@ -154,7 +155,7 @@ def instnorm_bwd(dy, x, stats):
     _chk(dy, "instnorm_bwd.dy"), _chk(x, "instnorm_bwd.x")
     n, h, w, c = x.shape
     dx = torch.empty_like(x)
-    ws = torch.empty((n, c, 2), dtype=torch.float32, device=x.device)
+    ws = torch.empty((n, c, 2), dtype=torch.float64, device=x.device)
     call("omr_instnorm_bwd", dt_code(x.dtype), ptr(dy), ptr(x), ptr(stats), ptr(dx), ptr(ws), n, h * w, c, stream_ptr())
     return dx
 

@@ -36,10 +36,11 @@ class FusedAdam(torch.optim.Optimizer):
         self._step_dev: Optional[torch.Tensor] = None
         self._shadows = []  # callables returning [(param, shadow, layout, shadow2, layout2, d0, d1)]
 
-    def register_shadow_provider(self, fn) -> None:
-        """fn(param) -> (shadow, layout, shadow2, layout2, d0, d1) or None; lets the model hand over its
-        bf16 working copies so the kernel keeps them in sync."""
-        self._shadows.append(fn)
+    def register_shadow_provider(self, fn, mark_fresh=None) -> None:
+        """fn(param) -> [(bf16 tensor, layout code)] (at most two are kept in sync by the kernel; any further
+        copy is simply re-packed by its WeightCache); mark_fresh(param) is called after every step for the
+        parameters whose copies the kernel rewrote."""
+        self._shadows.append((fn, mark_fresh))
         self._table = None
 
     def _params(self) -> List[torch.nn.Parameter]:
@@ -52,26 +53,29 @@ class FusedAdam(torch.optim.Optimizer):
             self._step_dev = torch.zeros(1, dtype=torch.int32, device=dev)
         entries = (_AdamEntry * len(ps))()
         key = []
+        self._has_shadow = []
         for i, p in enumerate(ps):
             st = self.state[p]
             if "exp_avg" not in st:
                 st["exp_avg"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
                 st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
-            sh = None
-            for fn in self._shadows:
-                sh = fn(p)
-                if sh is not None:
-                    break
+            sh = self._query_shadows(p)
             e = entries[i]
             e.param, e.grad = p.data_ptr(), (p.grad.data_ptr() if p.grad is not None else None)
             e.exp_avg, e.exp_avg_sq = st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr()
             e.n = p.numel()
-            if sh is not None:
-                s1, l1, s2, l2, d0, d1 = sh
-                e.shadow, e.layout = (s1.data_ptr() if s1 is not None else None), l1
-                e.shadow2, e.layout2 = (s2.data_ptr() if s2 is not None else None), l2
-                e.d0, e.d1 = d0, d1
-            key.append((e.param, e.grad, e.shadow, e.shadow2))
+            if len(sh) > 2:
+                sh = []  # more copies than the kernel keeps: let the caches re-pack all of them
+            if sh:
+                e.shadow, e.layout = sh[0][0].data_ptr(), sh[0][1]
+                if len(sh) > 1:
+                    e.shadow2, e.layout2 = sh[1][0].data_ptr(), sh[1][1]
+                e.d0 = p.shape[0]
+                e.d1 = p.shape[1] if p.dim() > 1 else 1
+                if p.dim() == 2 or (p.dim() == 3 and p.shape[2] == 1):
+                    e.d1 = p.shape[1]
+            key.append((e.param, e.grad, tuple(t.data_ptr() for t, _ in sh)))
+            self._has_shadow.append(bool(sh))
         raw = bytes(entries)
         host = torch.frombuffer(bytearray(raw), dtype=torch.uint8)
         self._table = host.to(dev)
@@ -80,12 +84,23 @@ class FusedAdam(torch.optim.Optimizer):
         self._max_n = max(p.numel() for p in ps)
         self._ps = ps
 
+    def _query_shadows(self, p):
+        out = []
+        for fn, _ in self._shadows:
+            out += fn(p) or []
+        return out
+
     def _table_stale(self) -> bool:
         if self._table is None:
             return True
         for p, k in zip(self._ps, self._table_key):
             g = p.grad.data_ptr() if p.grad is not None else None
             if p.data_ptr() != k[0] or g != k[1]:
+                return True
+            sh = self._query_shadows(p) if self._shadows else []
+            if len(sh) > 2:
+                sh = []
+            if tuple(t.data_ptr() for t, _ in sh) != k[2]:
                 return True
         return False
 
@@ -98,4 +113,12 @@ class FusedAdam(torch.optim.Optimizer):
         call("omr_adam_tick", ptr(self._step_dev), stream_ptr())
         call("omr_adam_step", ptr(self._table), self._n, self._max_n, ptr(self._step_dev), float(g["lr"]),
              float(g["betas"][0]), float(g["betas"][1]), float(g["eps"]), float(self.grad_scale), stream_ptr())
+        # the kernel wrote the parameters through raw pointers: bump their autograd version so that every
+        # cached re-layout (params.WeightCache) is refreshed, except the bf16 copies the kernel itself rewrote
+        torch.autograd.graph.increment_version(self._ps)
+        for p, has in zip(self._ps, self._has_shadow):
+            if has:
+                for _, mark in self._shadows:
+                    if mark is not None:
+                        mark(p)
         return loss

@@ -58,6 +58,27 @@ class WeightCache:
         ent = self._c.get((id(p), kind, dtype))
         return None if ent is None else ent[1]
 
+    KIND_LAYOUT = {"mat": 0, "conv": 1, "dw": 2, "convT": 3, "matT": 4}  # omr_adam_entry.layout codes
+
+    def shadows(self, p: torch.Tensor):
+        """bf16 working copies of ``p`` currently cached: [(tensor, adam layout code)] (for FusedAdam, which
+        rewrites them in the same pass as the fp32 master so they never need re-packing)."""
+        out = []
+        for kind, code in self.KIND_LAYOUT.items():
+            ent = self._c.get((id(p), kind, torch.bfloat16))
+            if ent is not None and ent[1].device == p.device and ent[2] == p.data_ptr():
+                out.append((ent[1], code))
+        return out
+
+    def mark_fresh(self, p: torch.Tensor) -> None:
+        """the optimizer kernel has just rewritten every bf16 copy of ``p`` returned by ``shadows``"""
+        ver = p._version
+        for kind in self.KIND_LAYOUT:
+            key = (id(p), kind, torch.bfloat16)
+            ent = self._c.get(key)
+            if ent is not None:
+                self._c[key] = (ver, ent[1], ent[2])
+
     @staticmethod
     def _pack(w: torch.Tensor, kind: str, dtype: torch.dtype) -> torch.Tensor:
         if w.dtype != torch.float32:
@@ -72,6 +93,9 @@ class WeightCache:
         if kind == "mat":
             w2 = w.reshape(w.shape[0], -1)
             return w2 if dtype == torch.float32 else ops.cast(w2, dtype)
+        if kind == "matT":  # [R,C] -> [C,R]: the K-major operand of the data-gradient GEMMs
+            w2 = w.reshape(w.shape[0], -1)
+            return ops.cast(w2.t().contiguous(), dtype)
         raise ValueError(kind)
 
 

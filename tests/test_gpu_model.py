@@ -7,13 +7,22 @@ import pytest
 import torch
 
 from oracle import restate, synth
-from tests.helpers import build_multimodal, build_unimodal, grad_report, oracle_grads, rel_err
+from tests.helpers import (build_multimodal, build_unimodal, grad_report, oracle_grads, oracle_truth_and_floors,
+                           rel_err)
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
 
-@pytest.mark.parametrize("dtype,tolv", [(torch.float32, 1e-4), (torch.bfloat16, 4e-2)])
+def _limits(dtype, truth):
+    """(logit tolerance, gradient tolerance): the north-star figure or a small multiple of the reference's own
+    precision noise floor on the same inputs, whichever is larger (see tests/helpers.oracle_truth_and_floors)."""
+    if dtype == torch.float32:
+        return max(1e-4, 4 * truth["floor_logits_fp32"]), max(1e-4, 4 * truth["floor_grads_fp32"])
+    return max(1e-2, 1.5 * truth["floor_logits_bf16"]), max(1e-2, 1.5 * truth["floor_grads_bf16"])
+
+
+@pytest.mark.parametrize("dtype,tolv", [(torch.float32, 1e-4), (torch.bfloat16, 1e-2)])
 @pytest.mark.parametrize("hw", [(64, 128), (50, 77)])
 def test_encoder_forward(dtype, tolv, hw):
     import omr_a2s_multimodal_transformer_b200 as pkg
@@ -24,51 +33,56 @@ def test_encoder_forward(dtype, tolv, hw):
     enc = enc.to(DEV).eval()
     enc.compute_dtype = dtype
     x = torch.rand(2, 1, *hw, generator=torch.Generator().manual_seed(1))
-    ref = restate.encoder_forward(sd, "", x)
+    ref = restate.encoder_forward(sd, "", x.double())
+    if dtype == torch.bfloat16:  # yardstick: the reference's own autocast-bf16 error on this input (27 bf16 layers, 9 INs)
+        with torch.no_grad(), torch.autocast("cpu", dtype=torch.bfloat16):
+            tolv = max(tolv, 1.25 * rel_err(restate.encoder_forward(sd, "", x).float(), ref))
     with torch.no_grad():
         out = enc(x.to(DEV))
     assert out.shape == ref.shape
     assert rel_err(out.float(), ref) < tolv
 
 
-@pytest.mark.parametrize("dtype,tol_logit,tol_grad", [(torch.float32, 1e-4, 2e-4), (torch.bfloat16, 3e-2, 8e-2)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("window", [-1, 5])
-def test_unimodal_logits_loss_grads(dtype, tol_logit, tol_grad, window):
+def test_unimodal_logits_loss_grads(dtype, window):
     m, sd, w2i = build_unimodal(window=window, dtype=dtype)
     x, xl, y_in, y_out = synth.synth_unimodal_batch(3, 64, 128, [20, 12, 7], w2i)
-    ref_logits = restate.unimodal_forward(sd, x, xl, y_in, attn_window=window)
+    truth = oracle_truth_and_floors(lambda s, dt: restate.unimodal_forward(s, x, xl, y_in, attn_window=window, dtype=dt), y_out, sd)
+    tol_logit, tol_grad = _limits(dtype, truth)
+    ref_logits, ref_loss, ref_g = truth["logits"], truth["loss"], truth["grads"]
     with torch.no_grad():
         logits = m(x.to(DEV), xl.to(DEV), y_in.to(DEV))
     assert logits.shape == ref_logits.shape
     assert rel_err(logits.float(), ref_logits) < tol_logit
-    ref_loss, ref_g = oracle_grads(lambda s: restate.ce_loss(restate.unimodal_forward(s, x, xl, y_in, attn_window=window), y_out), sd)
     m.zero_grad(set_to_none=True)
     loss = m.decoder.loss(tgt=y_in.to(DEV), memory=m.encode(x.to(DEV)), memory_len=xl.to(DEV), targets=y_out.to(DEV))
     loss.backward()
     assert abs(float(loss) - ref_loss) < tol_logit * max(1.0, abs(ref_loss))
     rep = grad_report(m, ref_g)
     assert not rep["missing"], rep
-    assert rep["global_rel"] < tol_grad and rep["cos"] > 1 - tol_grad, rep
+    assert rep["global_rel"] < tol_grad and rep["cos"] > 1 - tol_grad, (rep, tol_grad)
     # gradients through the public forward() ([B,V,T] logits + torch CE) agree with the fused loss path
     g_fused = {k: p.grad.clone() for k, p in m.named_parameters()}
     m.zero_grad(set_to_none=True)
     lg = m(x.to(DEV), xl.to(DEV), y_in.to(DEV))
     torch.nn.functional.cross_entropy(lg.float(), y_out.to(DEV), ignore_index=0).backward()
     rep2 = grad_report(m, {k: v.cpu() for k, v in g_fused.items()})
-    assert rep2["global_rel"] < (1e-4 if dtype == torch.float32 else 3e-2), rep2
+    assert rep2["global_rel"] < (1e-4 if dtype == torch.float32 else tol_grad), rep2
 
 
-@pytest.mark.parametrize("dtype,tol_logit,tol_grad", [(torch.float32, 1e-4, 2e-4), (torch.bfloat16, 3e-2, 8e-2)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("mixer", ["concat", "attn_img", "attn_audio", "attn_both"])
-def test_multimodal_logits_loss_grads(dtype, tol_logit, tol_grad, mixer):
+def test_multimodal_logits_loss_grads(dtype, mixer):
     m, sd, w2i = build_multimodal(mixer=mixer, dtype=dtype)
     xi, xli, xa, xla, y_in, y_out = synth.synth_multimodal_batch(3, (64, 128), (48, 96), [20, 12, 7], w2i)
-    ref_logits = restate.multimodal_forward(sd, xi, xli, xa, xla, y_in, mixer_type=mixer)
+    truth = oracle_truth_and_floors(
+        lambda s, dt: restate.multimodal_forward(s, xi, xli, xa, xla, y_in, mixer_type=mixer, dtype=dt), y_out, sd)
+    tol_logit, tol_grad = _limits(dtype, truth)
+    ref_logits, ref_loss, ref_g = truth["logits"], truth["loss"], truth["grads"]
     with torch.no_grad():
         logits = m(xi.to(DEV), xli.to(DEV), xa.to(DEV), xla.to(DEV), y_in.to(DEV))
     assert rel_err(logits.float(), ref_logits) < tol_logit
-    ref_loss, ref_g = oracle_grads(
-        lambda s: restate.ce_loss(restate.multimodal_forward(s, xi, xli, xa, xla, y_in, mixer_type=mixer), y_out), sd)
     m.zero_grad(set_to_none=True)
     mem, xl = m._memory(xi.to(DEV), xa.to(DEV), xli.to(DEV), xla.to(DEV), "both")
     loss = m.decoder.loss(tgt=y_in.to(DEV), memory=mem, memory_len=xl, targets=y_out.to(DEV))
@@ -76,7 +90,7 @@ def test_multimodal_logits_loss_grads(dtype, tol_logit, tol_grad, mixer):
     assert abs(float(loss) - ref_loss) < tol_logit * max(1.0, abs(ref_loss))
     rep = grad_report(m, ref_g)
     assert not rep["missing"], rep
-    assert rep["global_rel"] < tol_grad and rep["cos"] > 1 - tol_grad, rep
+    assert rep["global_rel"] < tol_grad and rep["cos"] > 1 - tol_grad, (rep, tol_grad)
 
 
 @pytest.mark.parametrize("modality", ["image", "audio"])
@@ -131,23 +145,55 @@ def test_greedy_multimodal_bf16_runs_and_eos_stops():
     assert full.shape == (4, 16) and l2.tolist() == [16] * 4
 
 
-def test_training_step_with_fused_adam_matches_oracle_adam():
+def test_fused_adam_kernel_matches_torch_adam_on_identical_gradients():
+    """the multi-tensor Adam kernel against torch.optim.Adam(lr=1e-4) fed the SAME gradients (3 steps)"""
+    m, sd, w2i = build_multimodal(dtype=torch.float32)
+    ref_p = {k: v.clone().to(DEV).requires_grad_(True) for k, v in sd.items() if torch.is_floating_point(v) and not k.endswith(".pe")}
+    ref_opt = torch.optim.Adam(list(ref_p.values()), lr=1e-4)
+    opt = m.configure_optimizers()
+    gen = torch.Generator().manual_seed(11)
+    for step in range(3):
+        for k, p in m.named_parameters():
+            g = (torch.randn(p.shape, generator=gen) * (10.0 ** (step - 3))).to(DEV)
+            p.grad = g.clone()
+            ref_p[k].grad = g.clone()
+        ref_opt.step()
+        opt.step()
+    worst = max(rel_err(p, ref_p[k]) for k, p in m.named_parameters())
+    assert worst < 1e-6, worst
+
+
+def test_training_step_with_fused_adam_follows_oracle_adam():
+    """two full steps (fwd + bwd + fused Adam) against the oracle + torch Adam.  Adam normalises every gradient
+    element to a +-lr step, so elements whose true gradient is zero (e.g. the key bias of every attention: a
+    constant added to all keys cancels in the softmax) move by rounding noise; the check is therefore on the
+    direction of the whole update and on the loss, not per element."""
     m, sd, w2i = build_multimodal(dtype=torch.float32)
     xi, xli, xa, xla, y_in, y_out = synth.synth_multimodal_batch(2, (64, 128), (48, 96), [12, 9], w2i)
     sdg = {k: (v.clone().requires_grad_(True) if torch.is_floating_point(v) and not k.endswith(".pe") else v) for k, v in sd.items()}
     params = [v for v in sdg.values() if v.requires_grad]
     ref_opt = torch.optim.Adam(params, lr=1e-4)
     opt = m.configure_optimizers()
+    losses, ref_losses = [], []
     for _ in range(2):
         ref_opt.zero_grad()
-        restate.ce_loss(restate.multimodal_forward(sdg, xi, xli, xa, xla, y_in), y_out).backward()
+        rl = restate.ce_loss(restate.multimodal_forward(sdg, xi, xli, xa, xla, y_in), y_out)
+        rl.backward()
         ref_opt.step()
+        ref_losses.append(float(rl.detach()))
         opt.zero_grad(set_to_none=True)
         mem, xl = m._memory(xi.to(DEV), xa.to(DEV), xli.to(DEV), xla.to(DEV), "both")
-        m.decoder.loss(tgt=y_in.to(DEV), memory=mem, memory_len=xl, targets=y_out.to(DEV)).backward()
+        loss = m.decoder.loss(tgt=y_in.to(DEV), memory=mem, memory_len=xl, targets=y_out.to(DEV))
+        loss.backward()
         opt.step()
-    worst = max(rel_err(p, sdg[k]) for k, p in m.named_parameters())
-    assert worst < 1e-5, worst
+        losses.append(float(loss))
+    assert max(abs(a - b) for a, b in zip(losses, ref_losses)) < 1e-4 * max(ref_losses), (losses, ref_losses)
+    dot = na = nb = 0.0
+    for k, p in m.named_parameters():
+        da = (p.detach().cpu().double() - sd[k].double()).reshape(-1)
+        db = (sdg[k].detach().double() - sd[k].double()).reshape(-1)
+        dot += float((da * db).sum()); na += float(da.pow(2).sum()); nb += float(db.pow(2).sum())
+    assert dot / (na * nb) ** 0.5 > 0.98, dot / (na * nb) ** 0.5
 
 
 def test_train_mode_dropout_runs_and_is_stochastic():

@@ -1,0 +1,102 @@
+"""Tensor-core (tcgen05 / TMA / TMEM) kernels against fp32 torch references on bf16-rounded inputs (-m gpu).
+Every case also asserts that the call really was served by the tensor-core kernel (omr_tc_call_count), so a
+silent fall-back to the CUDA-core path cannot pass."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def rel_err(a, b):
+    a, b = a.double(), b.double()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def rnd(*shape, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed + 7 * sum(shape))
+    return (torch.randn(*shape, generator=g) * scale).to(DEV)
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from omr_a2s_multimodal_transformer_b200 import _lib, ops as o
+
+    _lib.load().omr_set_tensor_core_path(1)
+    return o
+
+
+def tc_calls():
+    from omr_a2s_multimodal_transformer_b200 import _lib
+
+    return _lib.tc_call_count()
+
+
+# M, N, K  (tails in every dimension, the decoder / DSC / classifier shapes, a long-K case)
+GEMM_SHAPES = [(128, 256, 256), (300, 256, 256), (1000, 768, 256), (257, 512, 256), (4096, 96, 128), (130, 7040, 256),
+               (512, 128, 128), (333, 64, 72), (2048, 256, 6997 + 3), (96, 32, 512)]
+
+
+@pytest.mark.parametrize("shape", GEMM_SHAPES)
+@pytest.mark.parametrize("out_dtype", [torch.bfloat16, torch.float32])
+def test_gemm_tn_forward(ops, shape, out_dtype):
+    """y = act(x W^T + b): both operands K-major (nn.Linear forward)"""
+    m, n, k = shape
+    x = rnd(m, k, seed=1).bfloat16()
+    w = rnd(n, k, seed=2, scale=1 / math.sqrt(k)).bfloat16()
+    b = rnd(n, seed=3, scale=0.1)
+    y = torch.empty(m, n, dtype=out_dtype, device=DEV)
+    n0 = tc_calls()
+    ops.gemm(x, w, y, m, n, k, trans_b=True, lda=k, ldb=k, ldc=n, bias=b, bias_mode=1, relu=True)
+    assert tc_calls() == n0 + 1, "tensor-core kernel did not run"
+    ref = torch.relu(x.float() @ w.float().t() + b)
+    assert rel_err(y.float(), ref) < (2e-5 if out_dtype == torch.float32 else 6e-3)
+
+
+@pytest.mark.parametrize("shape", [(1000, 256, 768), (300, 256, 256), (4096, 256, 512), (200, 128, 7040)])
+def test_gemm_nn_dgrad(ops, shape):
+    """dx = dy W: A K-major, B MN-major (rows of W are the reduction index)"""
+    m, n, k = shape  # dx [m, n], dy [m, k], W [k, n]
+    dy = rnd(m, k, seed=4).bfloat16()
+    w = rnd(k, n, seed=5, scale=1 / math.sqrt(k)).bfloat16()
+    dx = torch.empty(m, n, dtype=torch.bfloat16, device=DEV)
+    n0 = tc_calls()
+    ops.gemm(dy, w, dx, m, n, k, lda=k, ldb=n, ldc=n)
+    assert tc_calls() == n0 + 1
+    assert rel_err(dx.float(), dy.float() @ w.float()) < 6e-3
+    # accumulate into an existing bf16 tensor (dx = ds + dh W1 in the decoder backward)
+    base = rnd(m, n, seed=6).bfloat16()
+    acc = base.clone()
+    ops.gemm(dy, w, acc, m, n, k, lda=k, ldb=n, ldc=n, accumulate=True)
+    assert rel_err(acc.float(), base.float() + dy.float() @ w.float()) < 8e-3
+
+
+@pytest.mark.parametrize("shape", [(256, 256, 16384), (768, 256, 5000), (512, 256, 74784 // 8), (7000, 256, 1024), (256, 128, 640)])
+def test_gemm_tn_wgrad_split_k(ops, shape):
+    """dW += dy^T x: both operands MN-major, fp32 output, long reduction split across CTAs with atomics"""
+    n_out, k_in, rows = shape
+    dy = rnd(rows, n_out, seed=7).bfloat16()
+    x = rnd(rows, k_in, seed=8).bfloat16()
+    dw = torch.zeros(n_out, k_in, dtype=torch.float32, device=DEV)
+    n0 = tc_calls()
+    ops.gemm(dy, x, dw, n_out, k_in, rows, trans_a=True, lda=n_out, ldb=k_in, ldc=k_in, accumulate=True)
+    assert tc_calls() == n0 + 1
+    ref = dy.float().t() @ x.float()
+    assert rel_err(dw, ref) < 2e-5
+    ops.gemm(dy, x, dw, n_out, k_in, rows, trans_a=True, lda=n_out, ldb=k_in, ldc=k_in, accumulate=True)
+    assert rel_err(dw, 2 * ref) < 2e-5
+
+
+def test_gemm_strided_views(ops):
+    """row-sliced weights / column-sliced outputs as used for the packed in-proj (ld != width)"""
+    m, d = 700, 256
+    x = rnd(m, d, seed=9).bfloat16()
+    w = rnd(3 * d, d, seed=10, scale=1 / 16).bfloat16()
+    b = rnd(3 * d, seed=11, scale=0.1)
+    out = torch.zeros(m, 2 * d, dtype=torch.bfloat16, device=DEV)
+    n0 = tc_calls()
+    ops.linear_fwd(x, w[d:], b[d:], out=out)
+    assert tc_calls() == n0 + 1
+    assert rel_err(out.float(), x.float() @ w[d:].float().t() + b[d:]) < 6e-3
