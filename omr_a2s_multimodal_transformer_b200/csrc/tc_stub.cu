@@ -3,20 +3,10 @@
 #include "common.cuh"
 #include "kernels.h"
 
-#ifndef OMR_HAVE_TC_CONV
-int omr_conv3x3_fwd_tc(const void*, const void*, const float*, void*, int, int, int, int, int, int, int, int,
-                       cudaStream_t) { return OMR_TC_NOT_ELIGIBLE; }
-int omr_conv3x3_dgrad_tc(const void*, const void*, void*, int, int, int, int, int, int, int, cudaStream_t) {
-  return OMR_TC_NOT_ELIGIBLE;
-}
-#endif
 #ifndef OMR_HAVE_TC_WGRAD
 int omr_conv3x3_wgrad_tc(const void*, const void*, float*, int, int, int, int, int, int, int, int, cudaStream_t) {
   return OMR_TC_NOT_ELIGIBLE;
 }
-#endif
-#ifndef OMR_HAVE_TC_GEMM
-
 #endif
 #ifndef OMR_HAVE_TC_ATTN
 int omr_attn_fwd_tc(const void*, long long, long long, const void*, long long, long long, const void*, long long,

@@ -100,3 +100,45 @@ def test_gemm_strided_views(ops):
     ops.linear_fwd(x, w[d:], b[d:], out=out)
     assert tc_calls() == n0 + 1
     assert rel_err(out.float(), x.float() @ w[d:].float().t() + b[d:]) < 6e-3
+
+
+# N, H, W, Ci, Co, stride  -- GrandStaff-like widths (multiples of 128 and the odd audio sizes), all channel pairs
+CONV_TC_CASES = [
+    (2, 8, 256, 16, 16, (1, 1)),
+    (1, 12, 300, 16, 32, (1, 1)),
+    (2, 9, 256, 32, 32, (2, 2)),
+    (1, 13, 101, 32, 64, (1, 1)),
+    (2, 10, 202, 64, 64, (2, 2)),
+    (1, 7, 128, 64, 128, (1, 1)),
+    (2, 16, 128, 128, 128, (2, 1)),
+    (1, 25, 101, 128, 128, (1, 1)),
+    (1, 5, 808, 16, 16, (1, 1)),
+    (3, 6, 20, 32, 32, (1, 1)),
+]
+
+
+@pytest.mark.parametrize("case", CONV_TC_CASES)
+def test_conv3x3_tc_fwd_dgrad(ops, case):
+    import torch.nn.functional as F
+
+    n, h, w, ci, co, st = case
+    x = rnd(n, ci, h, w, seed=21).bfloat16()
+    wt = rnd(co, ci, 3, 3, seed=22, scale=1.0 / math.sqrt(9 * ci))
+    b = rnd(co, seed=23, scale=0.1)
+    wq = wt.bfloat16().float()
+    xr = x.float().requires_grad_(True)
+    yr = F.relu(F.conv2d(xr, wq, b, stride=st, padding=1))
+    xn = x.permute(0, 2, 3, 1).contiguous()
+    wp = ops.pack_conv_weight(wt.contiguous(), torch.bfloat16, False)
+    wpt = ops.pack_conv_weight(wt.contiguous(), torch.bfloat16, True)
+    n0 = tc_calls()
+    y = ops.conv3x3_fwd(xn, wp, b, st, relu=True)
+    assert tc_calls() == n0 + 1, "tensor-core conv did not run"
+    assert rel_err(y.permute(0, 3, 1, 2).float(), yr) < 6e-3
+    gy = rnd(*yr.shape, seed=24).bfloat16()
+    (gx_ref,) = torch.autograd.grad(F.conv2d(xr, wq, None, stride=st, padding=1), xr, gy.float())
+    dy = gy.permute(0, 2, 3, 1).contiguous()
+    n0 = tc_calls()
+    dx = ops.conv3x3_dgrad(dy, wpt, (h, w), st)
+    assert tc_calls() == n0 + 1, "tensor-core dgrad did not run"
+    assert rel_err(dx.permute(0, 3, 1, 2).float(), gx_ref) < 6e-3
