@@ -3,11 +3,6 @@
 #include "common.cuh"
 #include "kernels.h"
 
-#ifndef OMR_HAVE_TC_WGRAD
-int omr_conv3x3_wgrad_tc(const void*, const void*, float*, int, int, int, int, int, int, int, int, cudaStream_t) {
-  return OMR_TC_NOT_ELIGIBLE;
-}
-#endif
 #ifndef OMR_HAVE_TC_ATTN
 int omr_attn_fwd_tc(const void*, long long, long long, const void*, long long, long long, const void*, long long,
                     long long, void*, long long, long long, float*, const float*, int, int, int, int, int, float, int,

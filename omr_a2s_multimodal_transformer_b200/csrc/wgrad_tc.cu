@@ -1,0 +1,221 @@
+// wgrad_tc.cu -- weight gradient of the 3x3 convolutions on the tcgen05 tensor cores.
+//
+//   dW[co, ci, kh, kw] (+)= sum over pixels p = (n, oh, ow) of  dY[p, co] * X[n, oh*sh + kh - 1, ow*sw + kw - 1, ci]
+//
+// i.e. nine GEMMs  [Co x P] * [P x Ci]  whose reduction dimension is the (huge) pixel axis.  Both operands are
+// NHWC activations, so both are "MN-major" for the tensor core (the channel index is contiguous inside a pixel
+// row); one shared-memory row = one pixel, fetched by 4-D TMA boxes -- the X box of tap (kh,kw) starts at the
+// shifted coordinate, with zero fill for the padding and element strides for strided convolutions, and the dY
+// box rows that fall outside the image are zero-filled, which makes every pixel tile a clean multiple of 16.
+// Each CTA owns a contiguous range of pixel tiles and a group of taps (all 9 when 9*Ci fp32 columns fit in
+// TMEM, else one kernel row of 3), accumulates them in TMEM across its whole range and finally adds its partial
+// sums to the fp32 gradient in the parameter's own [Co,Ci,3,3] layout with atomics.
+// Warp roles: 0-3 epilogue, 4 TMA producer, 5 MMA issuer + TMEM allocator.
+#include "kernels.h"
+#include "tc_common.cuh"
+
+namespace {
+
+using namespace tc;
+
+struct WgradArgs {
+  float* dw;
+  int N, Ci, Co;
+  int TH, TW, KP;  // pixel tile (KP = TH*TW, multiple of 16)
+  int tiles_h, tiles_w, num_tiles;
+  int sh, sw;
+  int taps_per_cta, tap_groups, ctas_per_group;
+  int rba, rbb, chunks_a, chunks_b;  // row bytes / channel chunks of the dY and X operands
+  int stage_bytes, stages;
+};
+
+__global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY,
+                                                          const __grid_constant__ CUtensorMap tmX, WgradArgs g) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + g.stages * g.stage_bytes);
+  uint64_t* empty_bar = full_bar + g.stages;
+  uint64_t* accum_bar = empty_bar + g.stages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int group = blockIdx.x / g.ctas_per_group;        // tap group
+  const int member = blockIdx.x - group * g.ctas_per_group;
+  const int tap0 = group * g.taps_per_cta;
+  const int ntap = g.taps_per_cta;
+  // contiguous range of pixel tiles of this CTA
+  const int per = (g.num_tiles + g.ctas_per_group - 1) / g.ctas_per_group;
+  const int t_begin = member * per;
+  int t_end = t_begin + per;
+  if (t_end > g.num_tiles) t_end = g.num_tiles;
+  const int ntiles = t_end > t_begin ? t_end - t_begin : 0;
+  const int cols = ntap * g.Ci;
+  const uint32_t tmem_cols = cols <= 32 ? 32 : (cols <= 64 ? 64 : (cols <= 128 ? 128 : (cols <= 256 ? 256 : 512)));
+  const int a_sub = g.KP * g.rba;  // bytes of one dY chunk tile
+  const int b_sub = g.KP * g.rbb;  // bytes of one X (tap, chunk) tile
+  const int a_bytes = g.chunks_a * a_sub;
+
+  if (warp == 4 && lane == 0) {
+    tma_prefetch_desc(&tmDY);
+    tma_prefetch_desc(&tmX);
+    for (int s = 0; s < g.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(accum_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 5) tmem_alloc(tmem_slot, tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      const uint32_t tx = (uint32_t)(a_bytes + ntap * g.chunks_b * b_sub);
+      for (int i = 0; i < ntiles; ++i) {
+        const int tile = t_begin + i;
+        const int tw = tile % g.tiles_w;
+        const int th = (tile / g.tiles_w) % g.tiles_h;
+        const int n = tile / (g.tiles_w * g.tiles_h);
+        const int oh0 = th * g.TH, ow0 = tw * g.TW;
+        const int s = i % g.stages;
+        const uint32_t ph = (i / g.stages) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        mbar_expect_tx(&full_bar[s], tx);
+        uint8_t* stage = smem + s * g.stage_bytes;
+        for (int c = 0; c < g.chunks_a; ++c) tma_load_4d(stage + c * a_sub, &tmDY, &full_bar[s], c * 64, ow0, oh0, n);
+        for (int t = 0; t < ntap; ++t) {
+          const int tap = tap0 + t, kh = tap / 3, kw = tap - kh * 3;
+          for (int c = 0; c < g.chunks_b; ++c)
+            tma_load_4d(stage + a_bytes + (t * g.chunks_b + c) * b_sub, &tmX, &full_bar[s], c * 64, ow0 * g.sw + kw - 1,
+                        oh0 * g.sh + kh - 1, n);
+        }
+      }
+    }
+  } else if (warp == 5) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(128, g.Ci, 1, 1);
+      const uint32_t lbo_a = g.chunks_a > 1 ? (uint32_t)a_sub : 0u;  // Co <= 64: every 64-wide M chunk aliases the real one
+      const uint32_t lbo_b = g.chunks_b > 1 ? (uint32_t)b_sub : 0u;
+      for (int i = 0; i < ntiles; ++i) {
+        const int s = i % g.stages;
+        const uint32_t ph = (i / g.stages) & 1;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + s * g.stage_bytes);
+        const uint32_t b_addr = a_addr + a_bytes;
+        for (int t = 0; t < ntap; ++t) {
+          const uint32_t bt = b_addr + t * g.chunks_b * b_sub;
+          for (int j = 0; j < g.KP / 16; ++j) {
+            const uint64_t ad = make_smem_desc(a_addr + j * 16 * g.rba, lbo_a, 8 * g.rba, g.rba);
+            const uint64_t bd = make_smem_desc(bt + j * 16 * g.rbb, lbo_b, 8 * g.rbb, g.rbb);
+            umma_bf16(tmem_base + (uint32_t)(t * g.Ci), ad, bd, idesc, (i > 0 || j > 0) ? 1u : 0u);
+          }
+        }
+        umma_commit(&empty_bar[s]);
+      }
+      umma_commit(accum_bar);
+    }
+  } else if (ntiles > 0) {
+    // ---- epilogue: thread = output channel co; add this CTA's partial sums into dW[co, ci, kh, kw] ----
+    mbar_wait(accum_bar, 0);
+    tc_fence_after();
+    const int co = warp * 32 + lane;
+    const bool ok = co < g.Co;
+    for (int t = 0; t < ntap; ++t) {
+      const int tap = tap0 + t;
+      for (int c0 = 0; c0 < g.Ci; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(t * g.Ci + c0), v);
+        tmem_ld_wait();
+        if (ok) {
+          float* dst = g.dw + ((long long)co * g.Ci + c0) * 9 + tap;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) atomicAdd(dst + j * 9, __uint_as_float(v[j]));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
+int g_sms = 0;
+int sms() {
+  if (!g_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_sms <= 0) g_sms = 148;
+  }
+  return g_sms;
+}
+
+}  // namespace
+
+int omr_conv3x3_wgrad_tc(const void* x, const void* dy, float* dw, int N, int H, int W, int Ci, int Co, int sh, int sw,
+                         int accumulate, cudaStream_t st) {
+  auto okc = [](int c) { return c == 16 || c == 32 || c == 64 || c == 128; };
+  if (!okc(Ci) || !okc(Co) || N < 1) return OMR_TC_NOT_ELIGIBLE;
+  if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(dy) & 15)) return OMR_TC_NOT_ELIGIBLE;
+  const int Ho = (H + sh - 1) / sh, Wo = (W + sw - 1) / sw;
+  WgradArgs g{};
+  g.dw = dw; g.N = N; g.Ci = Ci; g.Co = Co; g.sh = sh; g.sw = sw;
+  g.KP = Ci == 16 ? 128 : 64;
+  int TW = ((Wo + 15) / 16) * 16;
+  if (TW > g.KP) TW = g.KP;
+  g.TW = TW; g.TH = g.KP / TW;
+  if (g.KP % TW != 0) {  // TW in {16,32,48,64,...}: keep TH*TW a multiple of 16 that fits
+    g.TH = g.KP / TW;
+    g.KP = g.TH * TW;
+  }
+  if (g.TH * sh > 256 || g.TW * sw > 256) return OMR_TC_NOT_ELIGIBLE;
+  g.tiles_w = (Wo + g.TW - 1) / g.TW;
+  g.tiles_h = (Ho + g.TH - 1) / g.TH;
+  g.num_tiles = N * g.tiles_h * g.tiles_w;
+  g.taps_per_cta = (9 * Ci <= 512) ? 9 : 3;
+  g.tap_groups = 9 / g.taps_per_cta;
+  g.ctas_per_group = sms() / g.tap_groups;
+  if (g.ctas_per_group > g.num_tiles) g.ctas_per_group = g.num_tiles;
+  g.rba = (Co >= 64 ? 64 : Co) * 2; g.chunks_a = Co > 64 ? 2 : 1;
+  g.rbb = (Ci >= 64 ? 64 : Ci) * 2; g.chunks_b = Ci > 64 ? 2 : 1;
+  const int raw = g.KP * (g.rba * g.chunks_a + g.taps_per_cta * g.rbb * g.chunks_b);
+  g.stage_bytes = (raw + 1023) / 1024 * 1024;
+  g.stages = (200 * 1024) / g.stage_bytes;
+  if (g.stages > 4) g.stages = 4;
+  if (g.stages < 2) return OMR_TC_NOT_ELIGIBLE;
+  // every sub-tile must start on a swizzle-atom boundary (8 rows): KP is a multiple of 16 rows, so a_sub/b_sub are
+  // multiples of 16 * rb >= 512 B; the 128 B swizzle needs 1024 B: 16 rows * 128 B = 2048 ok, 64 B: 16*64 = 1024 ok,
+  // 32 B: atom is 256 B, 16*32 = 512 ok.
+  const int smem_bytes = g.stages * g.stage_bytes + 1024 + 256;
+
+  CUtensorMap tmDY, tmX;
+  {
+    unsigned long long dims[4] = {(unsigned long long)Co, (unsigned long long)Wo, (unsigned long long)Ho, (unsigned long long)N};
+    unsigned long long strides[3] = {(unsigned long long)Co * 2, (unsigned long long)Wo * Co * 2, (unsigned long long)Ho * Wo * Co * 2};
+    unsigned int box[4] = {(unsigned)(g.rba / 2), (unsigned)g.TW, (unsigned)g.TH, 1u};
+    int rc = omr_make_tensor_map(&tmDY, 2, dy, 4, dims, strides, box, nullptr, g.rba);
+    if (rc) return rc;
+    unsigned long long xd[4] = {(unsigned long long)Ci, (unsigned long long)W, (unsigned long long)H, (unsigned long long)N};
+    unsigned long long xs[3] = {(unsigned long long)Ci * 2, (unsigned long long)W * Ci * 2, (unsigned long long)H * W * Ci * 2};
+    unsigned int xb[4] = {(unsigned)(g.rbb / 2), (unsigned)(g.TW * sw), (unsigned)(g.TH * sh), 1u};
+    unsigned int es[4] = {1u, (unsigned)sw, (unsigned)sh, 1u};
+    rc = omr_make_tensor_map(&tmX, 2, x, 4, xd, xs, xb, es, g.rbb);
+    if (rc) return rc;
+  }
+  if (!accumulate) OMR_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)Co * Ci * 9, st));
+  static bool configured = false;
+  if (!configured) {
+    OMR_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    configured = true;
+  }
+  wgrad_tc_kernel<<<g.ctas_per_group * g.tap_groups, 192, smem_bytes, st>>>(tmDY, tmX, g);
+  OMR_LAUNCHED();
+  return OMR_OK;
+}

@@ -142,3 +142,28 @@ def test_conv3x3_tc_fwd_dgrad(ops, case):
     dx = ops.conv3x3_dgrad(dy, wpt, (h, w), st)
     assert tc_calls() == n0 + 1, "tensor-core dgrad did not run"
     assert rel_err(dx.permute(0, 3, 1, 2).float(), gx_ref) < 6e-3
+
+
+@pytest.mark.parametrize("case", CONV_TC_CASES + [(4, 64, 512, 16, 16, (1, 1)), (2, 32, 256, 64, 128, (2, 2))])
+def test_conv3x3_tc_wgrad(ops, case):
+    import torch.nn.functional as F
+
+    n, h, w, ci, co, st = case
+    x = rnd(n, ci, h, w, seed=31).bfloat16()
+    wt = rnd(co, ci, 3, 3, seed=32, scale=1.0 / math.sqrt(9 * ci)).requires_grad_(True)
+    yr = F.conv2d(x.float(), wt, None, stride=st, padding=1)
+    gy = rnd(*yr.shape, seed=33).bfloat16()
+    (gw_ref,) = torch.autograd.grad(yr, wt, gy.float())
+    xn = x.permute(0, 2, 3, 1).contiguous()
+    dy = gy.permute(0, 2, 3, 1).contiguous()
+    dw = torch.zeros(co, ci, 3, 3, dtype=torch.float32, device=DEV)
+    db = torch.zeros(co, dtype=torch.float32, device=DEV)
+    n0 = tc_calls()
+    ops.conv3x3_wgrad(xn, dy, dw, db, st, accumulate=True)
+    assert tc_calls() == n0 + 1, "tensor-core wgrad did not run"
+    assert rel_err(dw, gw_ref) < 1e-4
+    assert rel_err(db, gy.float().sum(dim=(0, 2, 3))) < 1e-4
+    ops.conv3x3_wgrad(xn, dy, dw, db, st, accumulate=True)
+    assert rel_err(dw, 2 * gw_ref) < 1e-4
+    ops.conv3x3_wgrad(xn, dy, dw, db, st, accumulate=False)
+    assert rel_err(dw, gw_ref) < 1e-4
