@@ -3,10 +3,3 @@
 #include "common.cuh"
 #include "kernels.h"
 
-#ifndef OMR_HAVE_TC_ATTN
-int omr_attn_fwd_tc(const void*, long long, long long, const void*, long long, long long, const void*, long long,
-                    long long, void*, long long, long long, float*, const float*, int, int, int, int, int, float, int,
-                    int, const int*, const int*, int, cudaStream_t) {
-  return OMR_TC_NOT_ELIGIBLE;
-}
-#endif

@@ -167,3 +167,65 @@ def test_conv3x3_tc_wgrad(ops, case):
     assert rel_err(dw, 2 * gw_ref) < 1e-4
     ops.conv3x3_wgrad(xn, dy, dw, db, st, accumulate=False)
     assert rel_err(dw, gw_ref) < 1e-4
+
+
+def _attn_ref(q, k, v, scale, causal, window, key_bias):
+    """q [B,Tq,H,64], k/v [B,Tk,H,64] fp32 -> (o [B,Tq,H*64], lse [B,H,Tq]) with the reference mask algebra"""
+    b, tq, h, d = q.shape
+    tk = k.shape[1]
+    s = torch.einsum("bthd,bshd->bhts", q, k) * scale
+    if key_bias is not None:
+        s = s + key_bias[:, None, None, :]
+    if causal:
+        i = torch.arange(tq, device=q.device)[:, None] + (tk - tq)
+        j = torch.arange(tk, device=q.device)[None, :]
+        ok = j <= i
+        if window > 0:
+            ok = ok & (j >= i - window)
+        s = s.masked_fill(~ok, float("-inf"))
+    lse = torch.logsumexp(s, dim=-1)
+    p = torch.softmax(s, dim=-1)
+    o = torch.einsum("bhts,bshd->bthd", p, v).reshape(b, tq, h * d)
+    return o, lse
+
+
+ATTN_CASES = [
+    # B, H, Tq, Tk, causal, window, bias kind
+    (2, 4, 300, 300, True, 0, "plus1"),
+    (1, 4, 512, 512, True, 100, None),
+    (2, 4, 200, 700, False, 0, "neginf"),
+    (1, 2, 129, 2337, False, 0, "plus1"),
+    (3, 4, 64, 64, True, 5, None),
+    (1, 4, 1, 37, False, 0, "neginf"),
+]
+
+
+@pytest.mark.parametrize("case", ATTN_CASES)
+def test_attention_fwd_tc(ops, case):
+    from omr_a2s_multimodal_transformer_b200.ops import AttnSpec
+
+    b, h, tq, tk, causal, window, bias_kind = case
+    d = h * 64
+    self_attn = tq == tk and causal
+    if self_attn:
+        qkv = rnd(b, tq, 3 * d, seed=41).bfloat16()
+        qb, kb_, vb, qo, ko, vo = qkv, qkv, qkv, 0, d, 2 * d
+    else:
+        qb = rnd(b, tq, d, seed=42).bfloat16()
+        kv = rnd(b, tk, 2 * d, seed=43).bfloat16()
+        kb_, vb, qo, ko, vo = kv, kv, 0, 0, d
+    key_bias = None
+    if bias_kind is not None:
+        lens = torch.randint(tk // 2, tk + 1, (b,), generator=torch.Generator().manual_seed(5)).to(DEV)
+        pad = torch.arange(tk, device=DEV)[None, :] >= lens[:, None]
+        key_bias = torch.zeros(b, tk, device=DEV).masked_fill(pad, 1.0 if bias_kind == "plus1" else float("-inf"))
+    spec = AttnSpec(h, 64, causal=causal, window=window, key_bias=key_bias)
+    n0 = tc_calls()
+    o, lse = ops.attn_fwd(qb, qo, kb_, ko, vb, vo, spec)
+    assert tc_calls() == n0 + 1, "tensor-core attention did not run"
+    q4 = qb[:, :, qo:qo + d].float().reshape(b, tq, h, 64)
+    k4 = kb_[:, :, ko:ko + d].float().reshape(b, tk, h, 64)
+    v4 = vb[:, :, vo:vo + d].float().reshape(b, tk, h, 64)
+    o_ref, lse_ref = _attn_ref(q4, k4, v4, 0.125, causal, window, key_bias)
+    assert rel_err(o.float(), o_ref) < 8e-3
+    assert float((lse - lse_ref).abs().max()) < 2e-3
