@@ -163,8 +163,10 @@ int omr_attn_fwd(int dt, const void* q, long long q_bs, long long q_rs, const vo
                  const void* v, long long v_bs, long long v_rs, void* o, long long o_bs, long long o_rs, float* lse,
                  const float* key_bias, int B, int H, int Tq, int Tk, int hd, float scale, int causal, int window,
                  const int* q_len, const int* kv_len, int quirk_mod, omr_stream_t stream);
-/* Backward: dq/dk/dv use the q/k/v strides of their own (dq_bs, ...).  delta_ws: fp32 [B,H,Tq] scratch.
- * dk/dv are written (not accumulated). */
+/* Backward: dq/dk/dv use the q/k/v strides of their own (dq_bs, ...).  delta_ws: fp32 scratch of
+ * B*H*Tq*65 + 4 floats (delta [B,H,Tq], then the fp32 dQ accumulators [B,H,Tq,64] of the tensor-core
+ * kernel, which adds the contributions of the key tiles with vector atomics).  dq/dk/dv are written
+ * (not accumulated). */
 int omr_attn_bwd(int dt, const void* q, long long q_bs, long long q_rs, const void* k, long long k_bs, long long k_rs,
                  const void* v, long long v_bs, long long v_rs, const void* o, long long o_bs, long long o_rs,
                  const void* dout, long long do_bs, long long do_rs, const float* lse, void* dq, long long dq_bs,

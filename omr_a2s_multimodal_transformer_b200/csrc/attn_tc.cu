@@ -308,3 +308,376 @@ int omr_attn_fwd_tc(const void* q, long long q_bs, long long q_rs, const void* k
   OMR_LAUNCHED();
   return OMR_OK;
 }
+
+// =================================================================================================================
+// Backward.  One CTA = one (batch, head, 128-key tile); K and V stay resident in shared memory and the CTA walks the
+// query tiles that can see them.  Everything is computed TRANSPOSED (rows = keys) so that each softmax thread owns
+// one key row and the probabilities land in shared memory directly in the operand layouts of the three gradient
+// GEMMs:
+//     S^T  = K Q^T                 M=128 keys, N=128 queries, K=64          (TMEM, recomputed)
+//     dP^T = V dO^T                same shape
+//     P^T  = exp2(scale*S^T + bias_k - lse_q)   dS^T = P^T o (dP^T - delta_q)   -- bf16 into two swizzled smem tiles
+//     dV  += P^T  dO               A = P^T  (K-major),  B = dO tile (MN-major)   accumulated in TMEM over the q tiles
+//     dK  += dS^T Q                A = dS^T (K-major),  B = Q  tile (MN-major)   accumulated in TMEM over the q tiles
+//     dQ_t = dS K                  A = dS^T read as an MN-major operand, B = K tile (MN-major); per q tile, added to an
+//                                  fp32 accumulation buffer with vector atomics (other key tiles add to the same rows)
+// A second tiny kernel scales the fp32 dQ sums and writes them in the caller's (strided, bf16) layout.
+// =================================================================================================================
+namespace {
+
+constexpr int BWD_SMEM = TILE * 10 + 1024 + 256;
+
+__device__ __forceinline__ void q_tile_range(const AttnTcArgs& a, int j0, int& qt0, int& qt1) {
+  const int nqt = (a.Tq + BQ - 1) / BQ;
+  qt0 = 0; qt1 = nqt;
+  if (a.causal) {
+    const int off = a.Tk - a.Tq;
+    int j_last = j0 + BKV - 1;
+    if (j_last > a.Tk - 1) j_last = a.Tk - 1;
+    const int tmin = j0 - off;  // t >= j - off
+    if (tmin > 0) qt0 = tmin / BQ;
+    if (a.window > 0) {
+      const int tmax = j_last - off + a.window;  // t <= j - off + window
+      if (tmax < 0) { qt1 = 0; return; }
+      const int e = tmax / BQ + 1;
+      if (e < qt1) qt1 = e;
+    }
+    if (qt0 > qt1) qt0 = qt1;
+  }
+}
+
+struct AttnBwdArgs {
+  AttnTcArgs f;        // o/lse fields: lse is the saved forward statistic
+  const float* delta;  // [B,H,Tq]
+  float* dq_acc;       // [B,H,Tq,64] fp32, zeroed
+  bf16* dk; long long dk_bs, dk_rs;
+  bf16* dv; long long dv_bs, dv_rs;
+  float scale;
+};
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+__global__ void __launch_bounds__(192, 1) attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
+                                                             const __grid_constant__ CUtensorMap tmK,
+                                                             const __grid_constant__ CUtensorMap tmV,
+                                                             const __grid_constant__ CUtensorMap tmDO, AttnBwdArgs g) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if (smem_u32(smem) & 1023u) __trap();
+  const AttnTcArgs& a = g.f;
+  uint8_t* sK = smem;
+  uint8_t* sV = smem + TILE;
+  uint8_t* sQ = smem + 2 * TILE;   // [2]
+  uint8_t* sDO = smem + 4 * TILE;  // [2]
+  uint8_t* sPT = smem + 6 * TILE;  // 2 chunks of 64 queries
+  uint8_t* sDS = smem + 8 * TILE;  // 2 chunks of 64 queries
+  float* sLse = reinterpret_cast<float*>(smem + 10 * TILE);  // [128] (already * log2e)
+  float* sDelta = sLse + 128;                               // [128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 10 * TILE + 1024);
+  uint64_t* kv_full = bars;
+  uint64_t* qd_full = bars + 1;   // [2]
+  uint64_t* qd_empty = bars + 3;  // [2]
+  uint64_t* sdp_full = bars + 5;  // S^T and dP^T ready
+  uint64_t* pds_full = bars + 6;  // P^T and dS^T written (count 4)
+  uint64_t* mma2_done = bars + 7; // dV, dK, dQ MMAs of this q tile complete
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int j0 = blockIdx.x * BKV, h = blockIdx.y, b = blockIdx.z;
+  int qt0, qt1;
+  q_tile_range(a, j0, qt0, qt1);
+  const int ntiles = qt1 - qt0;
+
+  if (warp == 4 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    tma_prefetch_desc(&tmDO);
+    mbar_init(kv_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&qd_full[s], 1);
+      mbar_init(&qd_empty[s], 1);
+    }
+    mbar_init(sdp_full, 1);
+    mbar_init(pds_full, 4);
+    mbar_init(mma2_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 5) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_ST = tmem_base, tmem_DPT = tmem_base + 128, tmem_DV = tmem_base + 256, tmem_DK = tmem_base + 320,
+                 tmem_DQ = tmem_base + 384;
+
+  if (warp == 4) {
+    if (lane == 0 && ntiles > 0) {
+      mbar_expect_tx(kv_full, 2 * TILE);
+      tma_load_3d(sK, &tmK, kv_full, h * HD, j0, b);
+      tma_load_3d(sV, &tmV, kv_full, h * HD, j0, b);
+      for (int i = 0; i < ntiles; ++i) {
+        const int s = i & 1;
+        mbar_wait(&qd_empty[s], ((i >> 1) & 1) ^ 1);
+        mbar_expect_tx(&qd_full[s], 2 * TILE);
+        tma_load_3d(sQ + s * TILE, &tmQ, &qd_full[s], h * HD, (qt0 + i) * BQ, b);
+        tma_load_3d(sDO + s * TILE, &tmDO, &qd_full[s], h * HD, (qt0 + i) * BQ, b);
+      }
+    }
+  } else if (warp == 5) {
+    if (lane == 0 && ntiles > 0) {
+      constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
+      constexpr uint32_t idesc_kn = make_idesc_bf16(128, 64, 0, 1);  // A K-major (P^T / dS^T), B MN-major
+      constexpr uint32_t idesc_mn = make_idesc_bf16(128, 64, 1, 1);  // A MN-major (dS), B MN-major
+      mbar_wait(kv_full, 0);
+      const uint32_t k_addr = smem_u32(sK), v_addr = smem_u32(sV), pt_addr = smem_u32(sPT), ds_addr = smem_u32(sDS);
+      for (int i = 0; i < ntiles; ++i) {
+        const int s = i & 1;
+        mbar_wait(&qd_full[s], (i >> 1) & 1);
+        tc_fence_after();
+        const uint32_t q_addr = smem_u32(sQ + s * TILE), do_addr = smem_u32(sDO + s * TILE);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          umma_bf16(tmem_ST, make_smem_desc(k_addr + j * 32, 16, 1024, 128), make_smem_desc(q_addr + j * 32, 16, 1024, 128), idesc_s,
+                    j > 0 ? 1u : 0u);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          umma_bf16(tmem_DPT, make_smem_desc(v_addr + j * 32, 16, 1024, 128), make_smem_desc(do_addr + j * 32, 16, 1024, 128), idesc_s,
+                    j > 0 ? 1u : 0u);
+        umma_commit(sdp_full);
+        mbar_wait(pds_full, i & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int j = 0; j < 8; ++j)  // dV += P^T dO
+          umma_bf16(tmem_DV, make_smem_desc(pt_addr + (j >> 2) * TILE + (j & 3) * 32, 16, 1024, 128),
+                    make_smem_desc(do_addr + j * 2048, 0, 1024, 128), idesc_kn, (i > 0 || j > 0) ? 1u : 0u);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)  // dK += dS^T Q
+          umma_bf16(tmem_DK, make_smem_desc(ds_addr + (j >> 2) * TILE + (j & 3) * 32, 16, 1024, 128),
+                    make_smem_desc(q_addr + j * 2048, 0, 1024, 128), idesc_kn, (i > 0 || j > 0) ? 1u : 0u);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)  // dQ_tile = dS K : A = dS^T tile read MN-major (M = queries: 2 chunks, K = key rows)
+          umma_bf16(tmem_DQ, make_smem_desc(ds_addr + j * 2048, TILE, 1024, 128), make_smem_desc(k_addr + j * 2048, 0, 1024, 128),
+                    idesc_mn, j > 0 ? 1u : 0u);
+        umma_commit(mma2_done);
+        umma_commit(&qd_empty[s]);
+      }
+    }
+  } else {
+    // ---- thread = key row (S^T, dP^T, dV, dK accumulators) and = query row for the dQ accumulator ----
+    const int r = warp * 32 + lane;
+    const int j = j0 + r;
+    const int off = a.Tk - a.Tq;
+    const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
+    const float bias = (a.key_bias && j < a.Tk) ? a.key_bias[(long long)b * a.Tk + j] * LOG2E : 0.f;
+    // queries that can see key j: t in [t_lo, t_hi]
+    int t_lo = 0, t_hi = a.Tq - 1;
+    if (a.causal) {
+      t_lo = max(0, j - off);
+      if (a.window > 0) t_hi = min(t_hi, j - off + a.window);
+    }
+    if (j >= a.Tk) t_hi = -1;
+    const long long stat_base = ((long long)b * a.H + h) * a.Tq;
+
+    auto dq_epilogue = [&](int q_tile) {
+      const int t = q_tile * BQ + r;
+      float* dst = g.dq_acc + (stat_base + t) * HD;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t v[32];
+        tmem_ld32(tmem_DQ + lane_addr + c * 32, v);
+        tmem_ld_wait();
+        if (t < a.Tq) {
+#pragma unroll
+          for (int e = 0; e < 32; e += 4)
+            red_add_v4(dst + c * 32 + e, __uint_as_float(v[e]), __uint_as_float(v[e + 1]), __uint_as_float(v[e + 2]),
+                       __uint_as_float(v[e + 3]));
+        }
+      }
+    };
+
+    for (int i = 0; i < ntiles; ++i) {
+      const int q0 = (qt0 + i) * BQ;
+      softmax_bar();  // readers of the previous tile's statistics are done
+      {
+        const int t = q0 + r;
+        sLse[r] = t < a.Tq ? a.lse[stat_base + t] * LOG2E : 0.f;
+        sDelta[r] = t < a.Tq ? g.delta[stat_base + t] : 0.f;
+      }
+      softmax_bar();
+      mbar_wait(sdp_full, i & 1);
+      tc_fence_after();
+      if (i > 0) {
+        mbar_wait(mma2_done, (i - 1) & 1);  // P^T / dS^T tiles are free again, dQ of the previous q tile is complete
+        tc_fence_after();
+        dq_epilogue(qt0 + i - 1);
+      }
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t sv[32], dv[32];
+        tmem_ld32(tmem_ST + lane_addr + c * 32, sv);
+        tmem_ld32(tmem_DPT + lane_addr + c * 32, dv);
+        tmem_ld_wait();
+        uint32_t pk[16], dk[16];
+#pragma unroll
+        for (int e = 0; e < 32; e += 2) {
+          const int t = q0 + c * 32 + e;
+          const float x0 = fmaf(__uint_as_float(sv[e]), a.scale_log2, bias) - sLse[c * 32 + e];
+          const float x1 = fmaf(__uint_as_float(sv[e + 1]), a.scale_log2, bias) - sLse[c * 32 + e + 1];
+          const float p0 = (t >= t_lo && t <= t_hi) ? exp2f(x0) : 0.f;
+          const float p1 = (t + 1 >= t_lo && t + 1 <= t_hi) ? exp2f(x1) : 0.f;
+          const float d0 = p0 * (__uint_as_float(dv[e]) - sDelta[c * 32 + e]);
+          const float d1 = p1 * (__uint_as_float(dv[e + 1]) - sDelta[c * 32 + e + 1]);
+          pk[e >> 1] = pack_bf16(p0, p1);
+          dk[e >> 1] = pack_bf16(d0, d1);
+        }
+        uint8_t* prow = sPT + (c >> 1) * TILE + r * 128;
+        uint8_t* drow = sDS + (c >> 1) * TILE + r * 128;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int sw = (((c & 1) * 4 + u) ^ (r & 7)) << 4;
+          *reinterpret_cast<uint4*>(prow + sw) = make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
+          *reinterpret_cast<uint4*>(drow + sw) = make_uint4(dk[4 * u], dk[4 * u + 1], dk[4 * u + 2], dk[4 * u + 3]);
+        }
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(pds_full);
+    }
+    if (ntiles > 0) {
+      mbar_wait(mma2_done, (ntiles - 1) & 1);
+      tc_fence_after();
+      dq_epilogue(qt0 + ntiles - 1);
+    }
+    // dK (x scale) and dV rows of this key
+    if (j < a.Tk) {
+      bf16* dkp = g.dk + (long long)b * g.dk_bs + (long long)j * g.dk_rs + h * HD;
+      bf16* dvp = g.dv + (long long)b * g.dv_bs + (long long)j * g.dv_rs + h * HD;
+      if (ntiles == 0) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          reinterpret_cast<uint4*>(dkp)[u] = make_uint4(0, 0, 0, 0);
+          reinterpret_cast<uint4*>(dvp)[u] = make_uint4(0, 0, 0, 0);
+        }
+      }
+    }
+    if (ntiles > 0) {
+#pragma unroll
+      for (int which = 0; which < 2; ++which) {
+        const float mul = which == 0 ? g.scale : 1.f;
+        bf16* dst = which == 0 ? g.dk + (long long)b * g.dk_bs + (long long)j * g.dk_rs + h * HD
+                               : g.dv + (long long)b * g.dv_bs + (long long)j * g.dv_rs + h * HD;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint32_t v[32];
+          tmem_ld32((which == 0 ? tmem_DK : tmem_DV) + lane_addr + c * 32, v);
+          tmem_ld_wait();
+          if (j < a.Tk) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              uint4 o4;
+              o4.x = pack_bf16(__uint_as_float(v[8 * u]) * mul, __uint_as_float(v[8 * u + 1]) * mul);
+              o4.y = pack_bf16(__uint_as_float(v[8 * u + 2]) * mul, __uint_as_float(v[8 * u + 3]) * mul);
+              o4.z = pack_bf16(__uint_as_float(v[8 * u + 4]) * mul, __uint_as_float(v[8 * u + 5]) * mul);
+              o4.w = pack_bf16(__uint_as_float(v[8 * u + 6]) * mul, __uint_as_float(v[8 * u + 7]) * mul);
+              reinterpret_cast<uint4*>(dst)[c * 4 + u] = o4;
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// delta[b,h,t] = sum_d dO * O ; one warp per (b,h,t)
+__global__ void attn_delta_tc_kernel(const bf16* __restrict__ o, long long o_bs, long long o_rs, const bf16* __restrict__ dO,
+                                     long long do_bs, long long do_rs, float* __restrict__ delta, int B, int H, int Tq) {
+  const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= (long long)B * H * Tq) return;
+  const int t = (int)(w % Tq);
+  const long long rr = w / Tq;
+  const int h = (int)(rr % H), b = (int)(rr / H);
+  const __nv_bfloat162 ov = *reinterpret_cast<const __nv_bfloat162*>(o + (long long)b * o_bs + (long long)t * o_rs + h * HD + 2 * lane);
+  const __nv_bfloat162 dv = *reinterpret_cast<const __nv_bfloat162*>(dO + (long long)b * do_bs + (long long)t * do_rs + h * HD + 2 * lane);
+  float s = __low2float(ov) * __low2float(dv) + __high2float(ov) * __high2float(dv);
+  s = warp_sum(s);
+  if (lane == 0) delta[w] = s;
+}
+
+// dq[b,t,h,:] = bf16(scale * dq_acc[b,h,t,:])
+__global__ void attn_dq_finalize_kernel(const float* __restrict__ acc, bf16* __restrict__ dq, long long dq_bs, long long dq_rs,
+                                        int B, int H, int Tq, float scale) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // one thread = 8 channels
+  if (i >= (long long)B * H * Tq * 8) return;
+  const int u = (int)(i & 7);
+  const long long row = i >> 3;
+  const int t = (int)(row % Tq);
+  const long long rr = row / Tq;
+  const int h = (int)(rr % H), b = (int)(rr / H);
+  const float4 x = *reinterpret_cast<const float4*>(acc + row * HD + u * 8);
+  const float4 y = *reinterpret_cast<const float4*>(acc + row * HD + u * 8 + 4);
+  uint4 o4;
+  o4.x = pack_bf16(x.x * scale, x.y * scale); o4.y = pack_bf16(x.z * scale, x.w * scale);
+  o4.z = pack_bf16(y.x * scale, y.y * scale); o4.w = pack_bf16(y.z * scale, y.w * scale);
+  *reinterpret_cast<uint4*>(dq + (long long)b * dq_bs + (long long)t * dq_rs + h * HD + u * 8) = o4;
+}
+
+}  // namespace
+
+// ws: fp32 scratch of B*H*Tq*(1 + 64) floats: delta [B,H,Tq] followed by the dQ accumulators [B,H,Tq,64]
+int omr_attn_bwd_tc(const void* q, long long q_bs, long long q_rs, const void* k, long long k_bs, long long k_rs,
+                    const void* v, long long v_bs, long long v_rs, const void* o, long long o_bs, long long o_rs,
+                    const void* dout, long long do_bs, long long do_rs, const float* lse, void* dq, long long dq_bs,
+                    long long dq_rs, void* dk, long long dk_bs, long long dk_rs, void* dv, long long dv_bs, long long dv_rs,
+                    float* ws, const float* key_bias, int B, int H, int Tq, int Tk, int hd, float scale, int causal,
+                    int window, const int* q_len, const int* kv_len, cudaStream_t st) {
+  if (hd != HD || q_len || kv_len || B < 1 || H < 1 || Tq < 1 || Tk < 1) return OMR_TC_NOT_ELIGIBLE;
+  auto al = [](const void* p, long long bs, long long rs) {
+    return (reinterpret_cast<uintptr_t>(p) & 15) == 0 && (bs * 2) % 16 == 0 && (rs * 2) % 16 == 0;
+  };
+  if (!al(q, q_bs, q_rs) || !al(k, k_bs, k_rs) || !al(v, v_bs, v_rs) || !al(o, o_bs, o_rs) || !al(dout, do_bs, do_rs) ||
+      !al(dq, dq_bs, dq_rs) || !al(dk, dk_bs, dk_rs) || !al(dv, dv_bs, dv_rs))
+    return OMR_TC_NOT_ELIGIBLE;
+  CUtensorMap tmQ, tmK, tmV, tmDO;
+  int rc = make_head_map(&tmQ, q, q_bs, q_rs, B, Tq, H, BQ);
+  if (rc) return rc;
+  rc = make_head_map(&tmK, k, k_bs, k_rs, B, Tk, H, BKV);
+  if (rc) return rc;
+  rc = make_head_map(&tmV, v, v_bs, v_rs, B, Tk, H, BKV);
+  if (rc) return rc;
+  rc = make_head_map(&tmDO, dout, do_bs, do_rs, B, Tq, H, BQ);
+  if (rc) return rc;
+  const long long rows = (long long)B * H * Tq;
+  float* delta = ws;
+  float* dq_acc = ws + ((rows + 3) / 4) * 4;  // keep the accumulators 16-byte aligned
+  OMR_CUDA(cudaMemsetAsync(dq_acc, 0, sizeof(float) * (size_t)rows * HD, st));
+  attn_delta_tc_kernel<<<(unsigned)((rows * 32 + 255) / 256), 256, 0, st>>>((const bf16*)o, o_bs, o_rs, (const bf16*)dout, do_bs, do_rs,
+                                                                            delta, B, H, Tq);
+  OMR_LAUNCHED();
+  AttnBwdArgs g{};
+  g.f = AttnTcArgs{nullptr, 0, 0, const_cast<float*>(lse), key_bias, B, H, Tq, Tk, scale * LOG2E, causal, window};
+  g.delta = delta; g.dq_acc = dq_acc;
+  g.dk = (bf16*)dk; g.dk_bs = dk_bs; g.dk_rs = dk_rs;
+  g.dv = (bf16*)dv; g.dv_bs = dv_bs; g.dv_rs = dv_rs;
+  g.scale = scale;
+  static bool configured = false;
+  if (!configured) {
+    OMR_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM));
+    configured = true;
+  }
+  dim3 grid((unsigned)((Tk + BKV - 1) / BKV), (unsigned)H, (unsigned)B);
+  attn_bwd_tc_kernel<<<grid, 192, BWD_SMEM, st>>>(tmQ, tmK, tmV, tmDO, g);
+  OMR_LAUNCHED();
+  attn_dq_finalize_kernel<<<(unsigned)((rows * 8 + 255) / 256), 256, 0, st>>>(dq_acc, (bf16*)dq, dq_bs, dq_rs, B, H, Tq, scale);
+  OMR_LAUNCHED();
+  return OMR_OK;
+}

@@ -98,6 +98,11 @@ extern "C" int omr_attn_bwd(int dt, const void* q, long long q_bs, long long q_r
                             const float* key_bias, int B, int H, int Tq, int Tk, int hd, float scale, int causal,
                             int window, const int* q_len, const int* kv_len, int quirk_mod, omr_stream_t stream) {
   cudaStream_t st = as_stream(stream);
+  if (tc_enabled() && dt == OMR_BF16) {
+    TC_TRY(omr_attn_bwd_tc(q, q_bs, q_rs, k, k_bs, k_rs, v, v_bs, v_rs, o, o_bs, o_rs, dout, do_bs, do_rs, lse, dq, dq_bs, dq_rs,
+                           dk, dk_bs, dk_rs, dv, dv_bs, dv_rs, delta_ws, key_bias, B, H, Tq, Tk, hd, scale, causal, window,
+                           q_len, kv_len, st));
+  }
   return omr_attn_bwd_simt(dt, q, q_bs, q_rs, k, k_bs, k_rs, v, v_bs, v_rs, o, o_bs, o_rs, dout, do_bs, do_rs, lse, dq,
                            dq_bs, dq_rs, dk, dk_bs, dk_rs, dv, dv_bs, dv_rs, delta_ws, key_bias, B, H, Tq, Tk, hd, scale,
                            causal, window, q_len, kv_len, quirk_mod, st);

@@ -42,3 +42,9 @@ int omr_attn_fwd_tc(const void* q, long long q_bs, long long q_rs, const void* k
                     const void* v, long long v_bs, long long v_rs, void* o, long long o_bs, long long o_rs, float* lse,
                     const float* key_bias, int B, int H, int Tq, int Tk, int hd, float scale, int causal, int window,
                     const int* q_len, const int* kv_len, int quirk_mod, cudaStream_t st);
+int omr_attn_bwd_tc(const void* q, long long q_bs, long long q_rs, const void* k, long long k_bs, long long k_rs,
+                    const void* v, long long v_bs, long long v_rs, const void* o, long long o_bs, long long o_rs,
+                    const void* dout, long long do_bs, long long do_rs, const float* lse, void* dq, long long dq_bs,
+                    long long dq_rs, void* dk, long long dk_bs, long long dk_rs, void* dv, long long dv_bs, long long dv_rs,
+                    float* ws, const float* key_bias, int B, int H, int Tq, int Tk, int hd, float scale, int causal,
+                    int window, const int* q_len, const int* kv_len, cudaStream_t st);

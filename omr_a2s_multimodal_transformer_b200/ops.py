@@ -307,7 +307,7 @@ def attn_bwd(qbuf, q_off, kbuf, k_off, vbuf, v_off, o, do, lse, dqbuf, dq_off, d
     dqp, dqbs, dqrs = _view3(dqbuf, dq_off, d)
     dkp, dkbs, dkrs = _view3(dkbuf, dk_off, d)
     dvp, dvbs, dvrs = _view3(dvbuf, dv_off, d)
-    delta = torch.empty((b, spec.H, tq), dtype=torch.float32, device=qbuf.device)
+    delta = torch.empty(b * spec.H * tq * 65 + 4, dtype=torch.float32, device=qbuf.device)  # delta + fp32 dQ accumulators
     call("omr_attn_bwd", dt_code(qbuf.dtype), qp, qbs, qrs, kp, kbs, krs, vp, vbs, vrs, ptr(o), o.stride(0), o.stride(1),
          ptr(do), do.stride(0), do.stride(1), ptr(lse), dqp, dqbs, dqrs, dkp, dkbs, dkrs, dvp, dvbs, dvrs, ptr(delta),
          ptr(spec.key_bias), b, spec.H, tq, tk, spec.hd, spec.scale, int(spec.causal), spec.window, ptr(spec.q_len),

@@ -229,3 +229,45 @@ def test_attention_fwd_tc(ops, case):
     o_ref, lse_ref = _attn_ref(q4, k4, v4, 0.125, causal, window, key_bias)
     assert rel_err(o.float(), o_ref) < 8e-3
     assert float((lse - lse_ref).abs().max()) < 2e-3
+
+
+@pytest.mark.parametrize("case", ATTN_CASES)
+def test_attention_bwd_tc(ops, case):
+    from omr_a2s_multimodal_transformer_b200.ops import AttnSpec
+
+    b, h, tq, tk, causal, window, bias_kind = case
+    d = h * 64
+    self_attn = tq == tk and causal
+    if self_attn:
+        qkv = rnd(b, tq, 3 * d, seed=41).bfloat16()
+        qb, kb_, vb, qo, ko, vo = qkv, qkv, qkv, 0, d, 2 * d
+    else:
+        qb = rnd(b, tq, d, seed=42).bfloat16()
+        kv = rnd(b, tk, 2 * d, seed=43).bfloat16()
+        kb_, vb, qo, ko, vo = kv, kv, 0, 0, d
+    key_bias = None
+    if bias_kind is not None:
+        lens = torch.randint(tk // 2, tk + 1, (b,), generator=torch.Generator().manual_seed(5)).to(DEV)
+        pad = torch.arange(tk, device=DEV)[None, :] >= lens[:, None]
+        key_bias = torch.zeros(b, tk, device=DEV).masked_fill(pad, 1.0 if bias_kind == "plus1" else float("-inf"))
+    spec = AttnSpec(h, 64, causal=causal, window=window, key_bias=key_bias)
+    o, lse = ops.attn_fwd(qb, qo, kb_, ko, vb, vo, spec)
+    do = rnd(b, tq, d, seed=44).bfloat16()
+    q4 = qb[:, :, qo:qo + d].float().reshape(b, tq, h, 64).requires_grad_(True)
+    k4 = kb_[:, :, ko:ko + d].float().reshape(b, tk, h, 64).requires_grad_(True)
+    v4 = vb[:, :, vo:vo + d].float().reshape(b, tk, h, 64).requires_grad_(True)
+    o_ref, _ = _attn_ref(q4, k4, v4, 0.125, causal, window, key_bias)
+    gq, gk, gv = torch.autograd.grad(o_ref, (q4, k4, v4), do.float())
+    if self_attn:
+        dqkv = torch.zeros_like(qkv)
+        dqb, dkb, dvb = dqkv, dqkv, dqkv
+    else:
+        dqb = torch.zeros_like(qb)
+        dkv = torch.zeros_like(kv)
+        dkb, dvb = dkv, dkv
+    n0 = tc_calls()
+    ops.attn_bwd(qb, qo, kb_, ko, vb, vo, o, do, lse, dqb, qo, dkb, ko, dvb, vo, spec)
+    assert tc_calls() == n0 + 1, "tensor-core attention backward did not run"
+    assert rel_err(dqb[:, :, qo:qo + d].float(), gq.reshape(b, tq, d)) < 1.5e-2
+    assert rel_err(dkb[:, :, ko:ko + d].float(), gk.reshape(b, tk, d)) < 1.5e-2
+    assert rel_err(dvb[:, :, vo:vo + d].float(), gv.reshape(b, tk, d)) < 1.5e-2
