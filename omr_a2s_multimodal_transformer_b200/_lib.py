@@ -102,7 +102,7 @@ def call(name: str, *args) -> None:
     e0.record()
     check(getattr(load(), name)(*args), name)
     e1.record()
-    _prof.append((name, _work(name, args), launch_count() - n0, e0, e1))
+    _prof.append((name, _work(name, args), launch_count() - n0, e0, e1, [a for a in args if isinstance(a, int) and abs(a) < (1 << 24)]))
 
 
 # ---- per-entry-point device timing (bench.py's roofline block; a poor man's timeline) ------------------
@@ -181,7 +181,13 @@ def prof_stop() -> dict:
     recs, _prof = _prof or [], None
     torch.cuda.synchronize()
     out = {}
-    for name, (fl, by), nl, e0, e1 in recs:
+    dump = os.environ.get("OMR_PROF_DUMP")
+    if dump:
+        with open(dump, "w") as f:
+            for name, (fl, by), nl, e0, e1, ints in recs:
+                ms = e0.elapsed_time(e1)
+                f.write(f"{name}\t{ms:.4f}\t{fl / (ms * 1e-3) / 1e12 if ms > 0 else 0:.1f}\t{by / (ms * 1e-3) / 1e9 if ms > 0 else 0:.0f}\t{ints}\n")
+    for name, (fl, by), nl, e0, e1, _ints in recs:
         d = out.setdefault(name, {"calls": 0, "launches": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0})
         d["calls"] += 1
         d["launches"] += nl

@@ -15,6 +15,8 @@
 //   stride 2 -> one launch per output parity class (1, 2, 2 or 4 taps each), written with a strided epilogue.
 // Warp roles: 0-3 epilogue (TMEM lanes 32w..32w+31), 4 TMA producer, 5 MMA issuer + TMEM allocator.
 #define OMR_HAVE_TC_CONV 1
+#include <stdlib.h>
+
 #include "kernels.h"
 #include "tc_common.cuh"
 
@@ -196,6 +198,154 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Halo variant for stride-1 convolutions with C_in <= 64 (the high-resolution layers, which are bound by L2->SM
+// traffic and TMA box rate, not by the tensor cores): per 128-pixel row tile ONE TMA box brings the 3 x (TW+2)
+// input pixels, and the nine taps are nine UMMA descriptors whose start address is shifted by whole pixel rows
+// ((dh+1)*(TW+2) + (dw+1) rows of RB bytes) inside that box -- the swizzle is a function of the shared-memory
+// address, so a row-shifted window of a TMA-written tile is still a valid K-major operand.  All nine weight taps
+// stay resident in shared memory for the life of the persistent CTA.  Input traffic per tile drops from 9 boxes
+// to 1 (3.05x the output pixels instead of 9x) and the per-tile TMA operations from 18 to 1.
+// ---------------------------------------------------------------------------------------------------------------
+template <int RB>
+__global__ void __launch_bounds__(192, 1) conv_halo_kernel(const __grid_constant__ CUtensorMap tmX,
+                                                           const __grid_constant__ CUtensorMap tmW, ConvTcArgs g, int wsub,
+                                                           int hsub, int stages) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sW = smem;                // 9 taps x wsub
+  uint8_t* sH = smem + 9 * wsub;     // stages x hsub
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sH + stages * hsub);
+  uint64_t* w_full = bars;
+  uint64_t* full_bar = bars + 1;
+  uint64_t* empty_bar = full_bar + stages;
+  uint64_t* tfull_bar = empty_bar + stages;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t tmem_cols = g.Cout * 2 <= 32 ? 32 : (g.Cout * 2 <= 64 ? 64 : (g.Cout * 2 <= 128 ? 128 : 256));
+  const int pitch = g.TW + 2;  // pixel rows per input image row inside the halo box
+
+  if (warp == 4 && lane == 0) {
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmW);
+    mbar_init(w_full, 1);
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull_bar[a], 1);
+      mbar_init(&tempty_bar[a], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 5) tmem_alloc(tmem_slot, tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      mbar_expect_tx(w_full, 9u * (uint32_t)g.Cout * RB);
+      for (int t = 0; t < 9; ++t) tma_load_2d(sW + t * wsub, &tmW, w_full, t * g.Cin, 0);
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++it) {
+        const int tw = tile % g.tiles_w;
+        const int th = (tile / g.tiles_w) % g.tiles_h;
+        const int n = tile / (g.tiles_w * g.tiles_h);
+        const int s = it % stages;
+        mbar_wait(&empty_bar[s], ((it / stages) & 1) ^ 1);
+        mbar_expect_tx(&full_bar[s], 3u * (uint32_t)pitch * RB);
+        tma_load_4d(sH + s * hsub, &tmX, &full_bar[s], 0, tw * g.TW - 1, th - 1, n);
+      }
+    }
+  } else if (warp == 5) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(128, g.Cout, 0, 0);
+      mbar_wait(w_full, 0);
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++it) {
+        const uint32_t a = it & 1, aph = (it >> 1) & 1;
+        mbar_wait(&tempty_bar[a], aph ^ 1);
+        const int s = it % stages;
+        mbar_wait(&full_bar[s], (it / stages) & 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + a * (uint32_t)g.Cout;
+        const uint32_t h_addr = smem_u32(sH + s * hsub), w_addr = smem_u32(sW);
+        uint32_t first = 1;
+        for (int t = 0; t < g.ntaps; ++t) {
+          const uint32_t a_addr = h_addr + (uint32_t)((g.dh[t] + 1) * pitch + (g.dw[t] + 1)) * RB;
+          const uint32_t b_addr = w_addr + (uint32_t)g.widx[t] * wsub;
+#pragma unroll
+          for (int j = 0; j < RB / 32; ++j) {
+            umma_bf16(d_tmem, make_smem_desc(a_addr + j * 32, 16, 8 * RB, RB), make_smem_desc(b_addr + j * 32, 16, 8 * RB, RB), idesc,
+                      first ? 0u : 1u);
+            first = 0;
+          }
+        }
+        umma_commit(&empty_bar[s]);
+        umma_commit(&tfull_bar[a]);
+      }
+    }
+  } else {
+    uint32_t it = 0;
+    const int r = warp * 32 + lane;  // pixel inside the row tile (TH == 1)
+    for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++it) {
+      const uint32_t a = it & 1, aph = (it >> 1) & 1;
+      const int tw = tile % g.tiles_w;
+      const int th = (tile / g.tiles_w) % g.tiles_h;
+      const int n = tile / (g.tiles_w * g.tiles_h);
+      const int gw = tw * g.TW + r;
+      const bool ok = r < g.TW && gw < g.GW;
+      bf16* dst = g.y + (((long long)n * g.OH + th) * g.OW + gw) * g.Cout;
+      mbar_wait(&tfull_bar[a], aph);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + a * (uint32_t)g.Cout + ((uint32_t)(warp * 32) << 16);
+      for (int c0 = 0; c0 < g.Cout; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(t_addr + c0, v);
+        tmem_ld_wait();
+        if (ok) {
+          float f[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            f[j] = __uint_as_float(v[j]);
+            if (g.bias) f[j] += __ldg(g.bias + c0 + j);
+            if (g.relu) f[j] = fmaxf(f[j], 0.f);
+          }
+          uint4 o0, o1;
+          o0.x = pack_bf16(f[0], f[1]); o0.y = pack_bf16(f[2], f[3]); o0.z = pack_bf16(f[4], f[5]); o0.w = pack_bf16(f[6], f[7]);
+          o1.x = pack_bf16(f[8], f[9]); o1.y = pack_bf16(f[10], f[11]); o1.z = pack_bf16(f[12], f[13]); o1.w = pack_bf16(f[14], f[15]);
+          uint4* d4 = reinterpret_cast<uint4*>(dst + c0);
+          d4[0] = o0;
+          d4[1] = o1;
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[a]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
+int g_halo_mode = -1;
+bool halo_enabled() {
+  if (g_halo_mode < 0) {
+    const char* e = getenv("OMR_CONV_HALO");
+    g_halo_mode = (e && e[0] == '0') ? 0 : 1;  // on unless explicitly disabled
+  }
+  return g_halo_mode == 1;
+}
+
 int g_num_sms = 0;
 int num_sms() {
   if (!g_num_sms) {
@@ -224,6 +374,50 @@ int launch_cfg(const CUtensorMap& tmX, const CUtensorMap& tmW, const ConvTcArgs&
 // One launch of the tap-GEMM.  x: [N, XH, XW, Cin] bf16; wpack: [Cout, 9*Cin] bf16 (tap-major, channels innermost).
 int run_taps(const void* x, int N, int XH, int XW, int Cin, const void* wpack, int Cout, ConvTcArgs a, cudaStream_t st) {
   const int rb = (Cin >= 64 ? 64 : Cin) * 2;
+  if (halo_enabled() && a.ish == 1 && a.isw == 1 && a.ntaps == 9 && Cin <= 64 && a.osh == 1 && a.osw == 1) {
+    const int TW = a.GW >= 128 ? 128 : a.GW;
+    const int pitch = TW + 2;
+    int rows = 3 * pitch;
+    if (rows < 2 * pitch + 2 + 128) rows = 2 * pitch + 2 + 128;
+    const int hsub = (rows * rb + 1023) / 1024 * 1024;
+    const int wsub = (Cout * rb + 1023) / 1024 * 1024;
+    int stages = (225 * 1024 - 1024 - 512 - 9 * wsub) / hsub;
+    if (stages > 4) stages = 4;
+    if (stages >= 2) {
+      ConvTcArgs h = a;
+      h.TH = 1; h.TW = TW;
+      h.tiles_w = (a.GW + TW - 1) / TW;
+      h.tiles_h = a.GH;
+      h.num_tiles = a.N * h.tiles_h * h.tiles_w;
+      h.Cin = Cin; h.Cout = Cout;
+      CUtensorMap tmX, tmW;
+      unsigned long long dims[4] = {(unsigned long long)Cin, (unsigned long long)XW, (unsigned long long)XH, (unsigned long long)N};
+      unsigned long long strides[3] = {(unsigned long long)Cin * 2, (unsigned long long)XW * Cin * 2, (unsigned long long)XH * XW * Cin * 2};
+      unsigned int box[4] = {(unsigned)Cin, (unsigned)pitch, 3u, 1u};
+      int rc = omr_make_tensor_map(&tmX, 2, x, 4, dims, strides, box, nullptr, rb);
+      if (rc) return rc;
+      unsigned long long wd[2] = {(unsigned long long)9 * Cin, (unsigned long long)Cout};
+      unsigned long long ws[1] = {(unsigned long long)9 * Cin * 2};
+      unsigned int wb[2] = {(unsigned)Cin, (unsigned)Cout};
+      rc = omr_make_tensor_map(&tmW, 2, wpack, 2, wd, ws, wb, nullptr, rb);
+      if (rc) return rc;
+      const int smem_bytes = 9 * wsub + stages * hsub + 1024 + 512;
+      const int grid = h.num_tiles < num_sms() ? h.num_tiles : num_sms();
+      static bool cfgd[3] = {false, false, false};
+      const int ci = rb == 32 ? 0 : (rb == 64 ? 1 : 2);
+      if (!cfgd[ci]) {
+        if (rb == 32) OMR_CUDA(cudaFuncSetAttribute(conv_halo_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        if (rb == 64) OMR_CUDA(cudaFuncSetAttribute(conv_halo_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        if (rb == 128) OMR_CUDA(cudaFuncSetAttribute(conv_halo_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        cfgd[ci] = true;
+      }
+      if (rb == 32) conv_halo_kernel<32><<<grid, 192, smem_bytes, st>>>(tmX, tmW, h, wsub, hsub, stages);
+      else if (rb == 64) conv_halo_kernel<64><<<grid, 192, smem_bytes, st>>>(tmX, tmW, h, wsub, hsub, stages);
+      else conv_halo_kernel<128><<<grid, 192, smem_bytes, st>>>(tmX, tmW, h, wsub, hsub, stages);
+      OMR_LAUNCHED();
+      return OMR_OK;
+    }
+  }
   // tile geometry: a TH x TW patch of the logical output grid, TH*TW <= 128
   int TW = a.GW >= 128 ? 128 : a.GW;
   int TH = 128 / TW;

@@ -70,6 +70,10 @@ extern "C" int omr_conv3x3_wgrad(int dt, const void* x, const void* dy, float* d
     int rc = omr_colsum(dt, dy, (long long)N * Ho * Wo, Co, Co, db, accumulate, stream);
     if (rc) return rc;
   }
+  if (Ci == 1) {  // first layer: K = 9, HBM-bound streaming kernel (both dtypes)
+    int rc1 = omr_conv3x3_wgrad_c1(dt, x, dy, dw, N, H, W, Co, sh, sw, accumulate, st);
+    if (rc1 != OMR_TC_NOT_ELIGIBLE) return rc1;
+  }
   if (tc_enabled() && dt == OMR_BF16) {
     TC_TRY(omr_conv3x3_wgrad_tc(x, dy, dw, N, H, W, Ci, Co, sh, sw, accumulate, st));
   }

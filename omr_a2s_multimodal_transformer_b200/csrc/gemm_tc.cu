@@ -120,21 +120,27 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
       umma_commit(accum_bar);  // accumulator complete
     }
   } else {
-    // ---- epilogue: warp w owns TMEM lanes / tile rows 32w .. 32w+31, one row per thread ----
+    // ---- epilogue: warp w owns TMEM lanes / tile rows 32w .. 32w+31 ----
+    // phase 1: thread = row: TMEM -> registers -> bias/ReLU -> output type -> this warp's staging rows in the
+    // (now idle) pipeline buffers, 16-byte units XOR-swizzled by the row so that neither phase bank-conflicts;
+    // phase 2: consecutive lanes write consecutive 16-byte units of a row -> fully coalesced global stores.
     mbar_wait(accum_bar, 0);
     tc_fence_after();
     const int row = m0 + warp * 32 + lane;
     const bool row_ok = row < g.M;
-    TO* crow = reinterpret_cast<TO*>(g.C) + (long long)row * g.ldc;
     const float brow = (g.bias_mode == 2 && row_ok) ? g.bias[row] : 0.f;
     const bool vec_ok = ((g.ldc * sizeof(TO)) % 16 == 0) && ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0);
+    constexpr int EPU = 16 / (int)sizeof(TO);      // elements per 16-byte unit
+    constexpr int U = BN / EPU;                    // units per staged row
+    constexpr int UMASK = U >= 8 ? 7 : (U - 1);
+    uint4* stage = reinterpret_cast<uint4*>(smem) + warp * 32 * U;
+    const bool staged = vec_ok && g.acc_mode != 2;
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
       if (n0 + c0 >= g.N) break;  // warp-uniform
       uint32_t r[32];
       tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, r);
       tmem_ld_wait();
-      if (!row_ok) continue;
       float v[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + brow;
@@ -151,53 +157,79 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
       }
       if (g.acc_mode == 2) {
         if constexpr (sizeof(TO) == 4) {
-          float* cf = reinterpret_cast<float*>(crow) + ncol;
+          if (row_ok) {
+            float* cf = reinterpret_cast<float*>(g.C) + (long long)row * g.ldc + ncol;
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (full || ncol + j < g.N) atomicAdd(cf + j, v[j]);
+            for (int j = 0; j < 32; ++j)
+              if (full || ncol + j < g.N) atomicAdd(cf + j, v[j]);
+          }
         }
         continue;
       }
-      if (full && vec_ok && (ncol % (16 / (int)sizeof(TO)) == 0)) {
+      if (staged) {
+        uint4* srow = stage + lane * U;
         if constexpr (sizeof(TO) == 4) {
-          float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(crow) + ncol);
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
-            float4 o = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-            if (g.acc_mode == 1) {
-              float4 old = dst[q];
-              o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
-            }
-            dst[q] = o;
+            const int u = c0 / EPU + q;
+            srow[u ^ (lane & UMASK)] = make_uint4(__float_as_uint(v[4 * q]), __float_as_uint(v[4 * q + 1]), __float_as_uint(v[4 * q + 2]),
+                                                  __float_as_uint(v[4 * q + 3]));
           }
         } else {
-          uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(crow) + ncol);
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            if (g.acc_mode == 1) {
-              uint4 old = dst[q];
-              const __nv_bfloat162* ob = reinterpret_cast<const __nv_bfloat162*>(&old);
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                v[8 * q + 2 * e] += __low2float(ob[e]);
-                v[8 * q + 2 * e + 1] += __high2float(ob[e]);
-              }
-            }
-            uint4 o;
-            o.x = pack_bf16(v[8 * q], v[8 * q + 1]);
-            o.y = pack_bf16(v[8 * q + 2], v[8 * q + 3]);
-            o.z = pack_bf16(v[8 * q + 4], v[8 * q + 5]);
-            o.w = pack_bf16(v[8 * q + 6], v[8 * q + 7]);
-            dst[q] = o;
+            const int u = c0 / EPU + q;
+            srow[u ^ (lane & UMASK)] = make_uint4(pack_bf16(v[8 * q], v[8 * q + 1]), pack_bf16(v[8 * q + 2], v[8 * q + 3]),
+                                                  pack_bf16(v[8 * q + 4], v[8 * q + 5]), pack_bf16(v[8 * q + 6], v[8 * q + 7]));
           }
         }
-      } else {
+      } else if (row_ok) {
+        TO* crow = reinterpret_cast<TO*>(g.C) + (long long)row * g.ldc;
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           if (ncol + j < g.N) {
             float o = v[j];
             if (g.acc_mode == 1) o += to_f(crow[ncol + j]);
             crow[ncol + j] = from_f<TO>(o);
+          }
+        }
+      }
+    }
+    if (staged) {
+      __syncwarp();
+      int ncols = g.N - n0;
+      if (ncols > BN) ncols = BN;
+      const int nunits = (ncols + EPU - 1) / EPU;  // units that hold at least one valid column
+#pragma unroll 1
+      for (int idx = lane; idx < 32 * U; idx += 32) {
+        const int rr = idx / U, u = idx - rr * U;
+        const int grow = m0 + warp * 32 + rr;
+        if (grow >= g.M || u >= nunits) continue;
+        uint4 val = stage[rr * U + (u ^ (rr & UMASK))];
+        TO* dst = reinterpret_cast<TO*>(g.C) + (long long)grow * g.ldc + n0 + u * EPU;
+        if ((u + 1) * EPU <= ncols) {
+          if (g.acc_mode == 1) {
+            const uint4 old = *reinterpret_cast<const uint4*>(dst);
+            if constexpr (sizeof(TO) == 4) {
+              val.x = __float_as_uint(__uint_as_float(val.x) + __uint_as_float(old.x));
+              val.y = __float_as_uint(__uint_as_float(val.y) + __uint_as_float(old.y));
+              val.z = __float_as_uint(__uint_as_float(val.z) + __uint_as_float(old.z));
+              val.w = __float_as_uint(__uint_as_float(val.w) + __uint_as_float(old.w));
+            } else {
+              const __nv_bfloat162* ob = reinterpret_cast<const __nv_bfloat162*>(&old);
+              __nv_bfloat162* nb = reinterpret_cast<__nv_bfloat162*>(&val);
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                nb[e] = __floats2bfloat162_rn(__low2float(nb[e]) + __low2float(ob[e]), __high2float(nb[e]) + __high2float(ob[e]));
+            }
+          }
+          *reinterpret_cast<uint4*>(dst) = val;
+        } else {  // the unit straddles N: element-wise tail
+          const TO* sv = reinterpret_cast<const TO*>(&val);
+          for (int e = 0; e < EPU && u * EPU + e < ncols; ++e) {
+            float o = to_f(sv[e]);
+            if (g.acc_mode == 1) o += to_f(dst[e]);
+            dst[e] = from_f<TO>(o);
           }
         }
       }

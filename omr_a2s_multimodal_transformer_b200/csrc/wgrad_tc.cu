@@ -11,6 +11,8 @@
 // TMEM, else one kernel row of 3), accumulates them in TMEM across its whole range and finally adds its partial
 // sums to the fp32 gradient in the parameter's own [Co,Ci,3,3] layout with atomics.
 // Warp roles: 0-3 epilogue, 4 TMA producer, 5 MMA issuer + TMEM allocator.
+#include <stdlib.h>
+
 #include "kernels.h"
 #include "tc_common.cuh"
 
@@ -27,6 +29,9 @@ struct WgradArgs {
   int taps_per_cta, tap_groups, ctas_per_group;
   int rba, rbb, chunks_a, chunks_b;  // row bytes / channel chunks of the dY and X operands
   int stage_bytes, stages;
+  // halo mode (stride 1): ONE X box of (TH+2) x (TW+2) pixels per chunk and stage; the nine taps are row-shifted
+  // descriptor windows into it (start row = (row + kh) * pitch + col + kw), so X is fetched ~1.6x instead of 9x
+  int halo, pitch, halo_rows;
 };
 
 __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY,
@@ -37,6 +42,8 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant_
   uint64_t* empty_bar = full_bar + g.stages;
   uint64_t* accum_bar = empty_bar + g.stages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+  uint32_t* s_aoff = tmem_slot + 2;  // [8]   A start-address offsets per k16 step (16-byte units)
+  uint32_t* s_boff = s_aoff + 8;     // [72]  B start-address offsets per (MMA group, k16 step)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int group = blockIdx.x / g.ctas_per_group;        // tap group
@@ -52,7 +59,7 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant_
   const int cols = ntap * g.Ci;
   const uint32_t tmem_cols = cols <= 32 ? 32 : (cols <= 64 ? 64 : (cols <= 128 ? 128 : (cols <= 256 ? 256 : 512)));
   const int a_sub = g.KP * g.rba;  // bytes of one dY chunk tile
-  const int b_sub = g.KP * g.rbb;  // bytes of one X (tap, chunk) tile
+  const int b_sub = (g.halo ? g.halo_rows : g.KP) * g.rbb;  // bytes of one X (tap, chunk) tile / of one halo chunk
   const int a_bytes = g.chunks_a * a_sub;
 
   if (warp == 4 && lane == 0) {
@@ -73,7 +80,8 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant_
 
   if (warp == 4) {
     if (lane == 0) {
-      const uint32_t tx = (uint32_t)(a_bytes + ntap * g.chunks_b * b_sub);
+      const uint32_t tx = g.halo ? (uint32_t)(a_bytes + g.chunks_b * (g.TH + 2) * g.pitch * g.rbb)
+                                 : (uint32_t)(a_bytes + ntap * g.chunks_b * b_sub);
       for (int i = 0; i < ntiles; ++i) {
         const int tile = t_begin + i;
         const int tw = tile % g.tiles_w;
@@ -86,33 +94,65 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant_
         mbar_expect_tx(&full_bar[s], tx);
         uint8_t* stage = smem + s * g.stage_bytes;
         for (int c = 0; c < g.chunks_a; ++c) tma_load_4d(stage + c * a_sub, &tmDY, &full_bar[s], c * 64, ow0, oh0, n);
-        for (int t = 0; t < ntap; ++t) {
-          const int tap = tap0 + t, kh = tap / 3, kw = tap - kh * 3;
-          for (int c = 0; c < g.chunks_b; ++c)
-            tma_load_4d(stage + a_bytes + (t * g.chunks_b + c) * b_sub, &tmX, &full_bar[s], c * 64, ow0 * g.sw + kw - 1,
-                        oh0 * g.sh + kh - 1, n);
+        if (g.halo) {
+          for (int c = 0; c < g.chunks_b; ++c) tma_load_4d(stage + a_bytes + c * b_sub, &tmX, &full_bar[s], c * 64, ow0 - 1, oh0 - 1, n);
+        } else {
+          for (int t = 0; t < ntap; ++t) {
+            const int tap = tap0 + t, kh = tap / 3, kw = tap - kh * 3;
+            for (int c = 0; c < g.chunks_b; ++c)
+              tma_load_4d(stage + a_bytes + (t * g.chunks_b + c) * b_sub, &tmX, &full_bar[s], c * 64, ow0 * g.sw + kw - 1,
+                          oh0 * g.sh + kh - 1, n);
+          }
         }
       }
     }
   } else if (warp == 5) {
+    // The MMA issuer is ONE thread: everything that can be hoisted out of its loop is.  All descriptors of a stage
+    // differ only in their 14-bit start-address field, so the per-(group, k-step) address offsets (in 16-byte units)
+    // are tabulated once by the whole warp and an MMA costs two table loads and two adds.
+    // "group" = one tcgen05.mma target: with the halo layout and Ci <= 64 the three kw taps of a kernel row are ONE
+    // MMA of N = 3*Ci (MN-major B whose three Ci-wide chunks are the same window shifted by one pixel row each:
+    // leading byte offset = one row), otherwise one tap (N = Ci).
+    const bool merge = g.halo && g.chunks_b == 1;
+    const int ngroup = merge ? ntap / 3 : ntap;
+    const int nj = g.KP / 16;
+    for (int idx = lane; idx < ngroup * nj + nj; idx += 32) {
+      if (idx < nj) {
+        s_aoff[idx] = (uint32_t)(idx * 16 * g.rba) >> 4;
+      } else {
+        const int e = idx - nj, m = e / nj, j = e - m * nj;
+        const int tap = tap0 + (merge ? 3 * m : m), kh = tap / 3, kw = tap - kh * 3;
+        uint32_t off;
+        if (g.halo) {
+          const int pr = (j * 16) / g.TW, pc = (j * 16) - pr * g.TW;
+          off = (uint32_t)((pr + kh) * g.pitch + pc + kw) * g.rbb;
+        } else {
+          off = (uint32_t)(m * g.chunks_b * b_sub + j * 16 * g.rbb);
+        }
+        s_boff[e] = off >> 4;
+      }
+    }
+    __syncwarp();
     if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(128, g.Ci, 1, 1);
+      const uint32_t nB = merge ? 3 * g.Ci : g.Ci;
+      const uint32_t idesc = make_idesc_bf16(128, nB, 1, 1);
       const uint32_t lbo_a = g.chunks_a > 1 ? (uint32_t)a_sub : 0u;  // Co <= 64: every 64-wide M chunk aliases the real one
-      const uint32_t lbo_b = g.chunks_b > 1 ? (uint32_t)b_sub : 0u;
+      const uint32_t lbo_b = merge ? (uint32_t)g.rbb : (g.chunks_b > 1 ? (uint32_t)b_sub : 0u);
+      const uint64_t a_hi = make_smem_desc(0, lbo_a, 8 * g.rba, g.rba);  // everything but the start address
+      const uint64_t b_hi = make_smem_desc(0, lbo_b, 8 * g.rbb, g.rbb);
       for (int i = 0; i < ntiles; ++i) {
         const int s = i % g.stages;
         const uint32_t ph = (i / g.stages) & 1;
         mbar_wait(&full_bar[s], ph);
         tc_fence_after();
-        const uint32_t a_addr = smem_u32(smem + s * g.stage_bytes);
-        const uint32_t b_addr = a_addr + a_bytes;
-        for (int t = 0; t < ntap; ++t) {
-          const uint32_t bt = b_addr + t * g.chunks_b * b_sub;
-          for (int j = 0; j < g.KP / 16; ++j) {
-            const uint64_t ad = make_smem_desc(a_addr + j * 16 * g.rba, lbo_a, 8 * g.rba, g.rba);
-            const uint64_t bd = make_smem_desc(bt + j * 16 * g.rbb, lbo_b, 8 * g.rbb, g.rbb);
-            umma_bf16(tmem_base + (uint32_t)(t * g.Ci), ad, bd, idesc, (i > 0 || j > 0) ? 1u : 0u);
-          }
+        const uint32_t a_lo = smem_u32(smem + s * g.stage_bytes) >> 4;
+        const uint32_t b_lo = a_lo + ((uint32_t)a_bytes >> 4);
+        const uint32_t acc0 = i > 0 ? 1u : 0u;
+        for (int m = 0; m < ngroup; ++m) {
+          const uint32_t d = tmem_base + (uint32_t)m * nB;
+          const uint32_t* bo = s_boff + m * nj;
+          for (int j = 0; j < nj; ++j)
+            umma_bf16(d, a_hi | (uint64_t)(a_lo + s_aoff[j]), b_hi | (uint64_t)(b_lo + bo[j]), idesc, j > 0 ? 1u : acc0);
         }
         umma_commit(&empty_bar[s]);
       }
@@ -146,6 +186,14 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant_
   }
 }
 
+int g_wgrad_halo = -1;
+bool wgrad_halo_enabled() {
+  if (g_wgrad_halo < 0) {
+    const char* e = getenv("OMR_WGRAD_HALO");
+    g_wgrad_halo = (e && e[0] == '0') ? 0 : 1;  // on unless explicitly disabled
+  }
+  return g_wgrad_halo == 1;
+}
 int g_sms = 0;
 int sms() {
   if (!g_sms) {
@@ -167,14 +215,20 @@ int omr_conv3x3_wgrad_tc(const void* x, const void* dy, float* dw, int N, int H,
   const int Ho = (H + sh - 1) / sh, Wo = (W + sw - 1) / sw;
   WgradArgs g{};
   g.dw = dw; g.N = N; g.Ci = Ci; g.Co = Co; g.sh = sh; g.sw = sw;
-  g.KP = Ci == 16 ? 128 : 64;
+  g.halo = (sh == 1 && sw == 1 && wgrad_halo_enabled()) ? 1 : 0;
+  g.KP = (Ci == 16 || g.halo) ? 128 : 64;
   int TW = ((Wo + 15) / 16) * 16;
   if (TW > g.KP) TW = g.KP;
+  if (g.halo && TW > 32 && Ho >= 4) TW = 32;  // 4 x 32 patches: the (TH+2) x (TW+2) halo is 1.6x the patch, not 3x
   g.TW = TW; g.TH = g.KP / TW;
   if (g.KP % TW != 0) {  // TW in {16,32,48,64,...}: keep TH*TW a multiple of 16 that fits
     g.TH = g.KP / TW;
     g.KP = g.TH * TW;
   }
+  g.pitch = g.TW + 2;
+  g.halo_rows = (g.TH + 2) * g.pitch;
+  // a shifted 16-row window may start up to 2*pitch+2 rows into the box: it always ends inside it
+  // ((TH-1+2)*pitch + (TW-16) + 2 + 16 <= (TH+2)*pitch)
   if (g.TH * sh > 256 || g.TW * sw > 256) return OMR_TC_NOT_ELIGIBLE;
   g.tiles_w = (Wo + g.TW - 1) / g.TW;
   g.tiles_h = (Ho + g.TH - 1) / g.TH;
@@ -185,7 +239,9 @@ int omr_conv3x3_wgrad_tc(const void* x, const void* dy, float* dw, int N, int H,
   if (g.ctas_per_group > g.num_tiles) g.ctas_per_group = g.num_tiles;
   g.rba = (Co >= 64 ? 64 : Co) * 2; g.chunks_a = Co > 64 ? 2 : 1;
   g.rbb = (Ci >= 64 ? 64 : Ci) * 2; g.chunks_b = Ci > 64 ? 2 : 1;
-  const int raw = g.KP * (g.rba * g.chunks_a + g.taps_per_cta * g.rbb * g.chunks_b);
+  const int raw = g.halo ? g.KP * g.rba * g.chunks_a + ((g.halo_rows * g.rbb + 1023) / 1024 * 1024) * g.chunks_b
+                         : g.KP * (g.rba * g.chunks_a + g.taps_per_cta * g.rbb * g.chunks_b);
+  if (g.halo) g.halo_rows = ((g.halo_rows * g.rbb + 1023) / 1024 * 1024) / g.rbb;  // chunk tiles stay 1 KB aligned
   g.stage_bytes = (raw + 1023) / 1024 * 1024;
   g.stages = (200 * 1024) / g.stage_bytes;
   if (g.stages > 4) g.stages = 4;
@@ -193,7 +249,7 @@ int omr_conv3x3_wgrad_tc(const void* x, const void* dy, float* dw, int N, int H,
   // every sub-tile must start on a swizzle-atom boundary (8 rows): KP is a multiple of 16 rows, so a_sub/b_sub are
   // multiples of 16 * rb >= 512 B; the 128 B swizzle needs 1024 B: 16 rows * 128 B = 2048 ok, 64 B: 16*64 = 1024 ok,
   // 32 B: atom is 256 B, 16*32 = 512 ok.
-  const int smem_bytes = g.stages * g.stage_bytes + 1024 + 256;
+  const int smem_bytes = g.stages * g.stage_bytes + 1024 + 512;
 
   CUtensorMap tmDY, tmX;
   {
@@ -204,7 +260,7 @@ int omr_conv3x3_wgrad_tc(const void* x, const void* dy, float* dw, int N, int H,
     if (rc) return rc;
     unsigned long long xd[4] = {(unsigned long long)Ci, (unsigned long long)W, (unsigned long long)H, (unsigned long long)N};
     unsigned long long xs[3] = {(unsigned long long)Ci * 2, (unsigned long long)W * Ci * 2, (unsigned long long)H * W * Ci * 2};
-    unsigned int xb[4] = {(unsigned)(g.rbb / 2), (unsigned)(g.TW * sw), (unsigned)(g.TH * sh), 1u};
+    unsigned int xb[4] = {(unsigned)(g.rbb / 2), (unsigned)(g.halo ? g.pitch : g.TW * sw), (unsigned)(g.halo ? g.TH + 2 : g.TH * sh), 1u};
     unsigned int es[4] = {1u, (unsigned)sw, (unsigned)sh, 1u};
     rc = omr_make_tensor_map(&tmX, 2, x, 4, xd, xs, xb, es, g.rbb);
     if (rc) return rc;

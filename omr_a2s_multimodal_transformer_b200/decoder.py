@@ -144,7 +144,8 @@ class _ProjCEFn(torch.autograd.Function):
         b, t, d = hidden.shape
         wm = dec._wcache.get(dec.out_layer.weight, "mat", dtype)
         h2 = hidden.reshape(b * t, d)
-        logits = ops.linear_fwd(h2, wm, dec.out_layer.bias)
+        # logits rows padded to a multiple of 64 elements (6997 -> 7040): 16-byte aligned rows for TMA / vector stores
+        logits = ops.linear_fwd(h2, wm, dec.out_layer.bias, out=ops.padded_rows(b * t, wm.shape[0], dtype, h2.device))
         tg = targets.reshape(-1).contiguous()
         loss_out, row_lse = ops.ce_fwd(logits, tg, ignore_index)
         ctx.dec, ctx.dtype, ctx.ignore = dec, dtype, ignore_index
@@ -426,7 +427,8 @@ class Decoder(nn.Module):
             return _ProjCEFn.apply(hidden, self, targets, ig, hidden.dtype, self.out_layer.weight, self.out_layer.bias)
         b, t, d = hidden.shape
         wm = self._wcache.get(self.out_layer.weight, "mat", hidden.dtype)
-        logits = ops.linear_fwd(hidden.reshape(b * t, d), wm, self.out_layer.bias)
+        logits = ops.linear_fwd(hidden.reshape(b * t, d), wm, self.out_layer.bias,
+                                out=ops.padded_rows(b * t, wm.shape[0], hidden.dtype, hidden.device))
         loss_out, _ = ops.ce_fwd(logits, targets.reshape(-1).contiguous(), ig)
         return loss_out[0].clone()
 

@@ -226,31 +226,47 @@ def gemm(a, b, c, m, n, k, *, trans_a=False, trans_b=False, lda, ldb, ldc, batch
     return c
 
 
+def _rows2d(t: torch.Tensor, name: str) -> torch.Tensor:
+    """2-D operand whose rows are contiguous (the row stride may exceed the width: column slices, padded rows)"""
+    _lib.require_cuda(t, name)
+    if t.dim() != 2 or (t.shape[1] > 1 and t.stride(1) != 1):
+        raise RuntimeError(f"{name}: expected a 2-D tensor with unit column stride, got shape {tuple(t.shape)} strides {t.stride()}")
+    return t
+
+
+def padded_rows(m: int, n: int, dtype: torch.dtype, device, multiple: int = 64) -> torch.Tensor:
+    """[m, n] view of a buffer whose row stride is rounded up to ``multiple`` elements: keeps rows 16-byte aligned for
+    TMA / vector stores when n is odd-sized (the 6997-wide vocabulary logits -> stride 7040)."""
+    ld = (n + multiple - 1) // multiple * multiple
+    return torch.empty((m, ld), dtype=dtype, device=device)[:, :n]
+
+
 def linear_fwd(x2d, w, bias=None, relu=False, out=None):
     """x2d [M,K] @ w[N,K]^T (+bias) -> [M,N] (nn.Linear semantics; w rows may be a slice of a packed weight)"""
-    _chk(x2d, "linear_fwd.x")
+    _rows2d(x2d, "linear_fwd.x")
     m, k = x2d.shape
     n = w.shape[0]
     y = torch.empty((m, n), dtype=x2d.dtype, device=x2d.device) if out is None else out
-    gemm(x2d, w, y, m, n, k, trans_b=True, lda=k, ldb=w.stride(0), ldc=y.stride(0), bias=bias, bias_mode=1, relu=relu)
+    gemm(x2d, w, y, m, n, k, trans_b=True, lda=x2d.stride(0), ldb=w.stride(0), ldc=y.stride(0), bias=bias, bias_mode=1, relu=relu)
     return y
 
 
 def linear_dgrad(dy2d, w, out=None):
     """dx [M,K] = dy [M,N] @ w [N,K]"""
-    _chk(dy2d, "linear_dgrad.dy")
+    _rows2d(dy2d, "linear_dgrad.dy")
     m, n = dy2d.shape
     k = w.shape[1]
     dx = torch.empty((m, k), dtype=dy2d.dtype, device=dy2d.device) if out is None else out
-    gemm(dy2d, w, dx, m, k, n, lda=n, ldb=w.stride(0), ldc=dx.stride(0))
+    gemm(dy2d, w, dx, m, k, n, lda=dy2d.stride(0), ldb=w.stride(0), ldc=dx.stride(0))
     return dx
 
 
 def linear_wgrad(x2d, dy2d, dw, db=None, accumulate=True):
     """dw [N,K] (fp32, may be a row-slice view) += dy^T @ x ; db [N] += colsum(dy)"""
+    _rows2d(x2d, "linear_wgrad.x"), _rows2d(dy2d, "linear_wgrad.dy")
     m, k = x2d.shape
     n = dy2d.shape[1]
-    gemm(dy2d, x2d, dw, n, k, m, trans_a=True, lda=n, ldb=k, ldc=dw.stride(0), accumulate=accumulate)
+    gemm(dy2d, x2d, dw, n, k, m, trans_a=True, lda=dy2d.stride(0), ldb=x2d.stride(0), ldc=dw.stride(0), accumulate=accumulate)
     if db is not None:
         colsum(dy2d, db, accumulate=accumulate)
 
