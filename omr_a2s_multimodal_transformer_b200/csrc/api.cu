@@ -296,12 +296,54 @@ __global__ void colsum_kernel(const T* __restrict__ x, long long rows, int N, lo
     atomicAdd(out + c, s);
   }
 }
+// vectorised variant: a thread owns 4 consecutive columns (one 8/16-byte load per row), 256 threads =
+// (N/4 column quads) x (row lanes); lanes are combined in shared memory, one atomic per column and block
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_vec_kernel(const T* __restrict__ x, long long rows, int N, long long ld,
+                                                         float* __restrict__ out, int rows_per_block) {
+  __shared__ float sm[256 * 4];
+  const int quads = N / 4;  // <= 256 and a divisor of 256
+  const int lanes = 256 / quads;
+  const int cq = threadIdx.x % quads, lane = threadIdx.x / quads;
+  const long long r0 = (long long)blockIdx.x * rows_per_block;
+  long long r1 = r0 + rows_per_block;
+  if (r1 > rows) r1 = rows;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (long long r = r0 + lane; r < r1; r += lanes) {
+    float v[4];
+    load4(x + r * ld + cq * 4, v);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) acc[k] += v[k];
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) sm[(lane * quads + cq) * 4 + k] = acc[k];
+  __syncthreads();
+  for (int c = threadIdx.x; c < N; c += 256) {
+    float s = 0.f;
+    for (int l = 0; l < lanes; ++l) s += sm[l * N + c];
+    atomicAdd(out + c, s);
+  }
+}
+
 extern "C" int omr_colsum(int dt, const void* x, long long rows, int N, long long ld, float* out, int accumulate,
                           omr_stream_t stream) {
   if (N <= 0) return OMR_OK;
   cudaStream_t st = as_stream(stream);
   if (!accumulate) OMR_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * N, st));
   if (rows <= 0) return OMR_OK;
+  {
+    const int esz = dt == OMR_F32 ? 4 : 2;
+    if (N % 4 == 0 && N <= 1024 && 256 % (N / 4) == 0 && (ld * esz) % (4 * esz) == 0 &&
+        (reinterpret_cast<uintptr_t>(x) % (4 * esz)) == 0) {
+      long long per = cdiv(rows, 148LL * 4);
+      const long long min_per = 256 / (N / 4) * 8;
+      if (per < min_per) per = min_per;
+      const unsigned blocks = (unsigned)cdiv(rows, per);
+      OMR_DISPATCH_DT(dt, T, (colsum_vec_kernel<T><<<blocks, 256, 0, st>>>((const T*)x, rows, N, ld, out, (int)per)));
+      OMR_LAUNCHED();
+      return OMR_OK;
+    }
+  }
   dim3 grid((unsigned)cdiv(N, 32), (unsigned)(rows >= 8 * 64 ? (cdiv(rows, 8 * 16) > 512 ? 512 : cdiv(rows, 8 * 16)) : 1));
   dim3 block(32, 8);
   OMR_DISPATCH_DT(dt, T, (colsum_kernel<T><<<grid, block, 0, st>>>((const T*)x, rows, N, ld, out)));
@@ -327,11 +369,43 @@ __global__ void dropout_kernel(const T* __restrict__ x, T* __restrict__ y, long 
     y[i] = u < p ? from_f<T>(0.f) : from_f<T>(to_f(x[i]) * scale);
   }
 }
+// same mask function, 4 elements per thread (8/16-byte accesses); needs n % 4 == 0 and, for the channel-wise form,
+// C % 4 == 0 so that a quad never straddles a sample/channel-row boundary
+template <typename T>
+__global__ void dropout_vec_kernel(const T* __restrict__ x, T* __restrict__ y, long long n4, int C, long long per_sample,
+                                   float p, float scale, uint32_t seed, int channelwise) {
+  long long i4 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i4 < n4; i4 += stride) {
+    const long long i = i4 * 4;
+    float v[4];
+    load4(x + i, v);
+    const long long key0 = channelwise ? (i / per_sample) * C + (i % C) : i;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const long long key = key0 + k;
+      const uint32_t h = mix32(seed ^ (uint32_t)(key >> 32) * 0x632BE5ABu, (uint32_t)key);
+      const float u = (h >> 8) * (1.0f / 16777216.0f);
+      v[k] = u < p ? 0.f : v[k] * scale;
+    }
+    store4(y + i, v);
+  }
+}
 extern "C" int omr_dropout(int dt, const void* x, void* y, long long n, int C, long long per_sample, float p,
                            long long seed, int channelwise, omr_stream_t stream) {
   OMR_REQUIRE(p >= 0.f && p < 1.f, "omr_dropout: p must be in [0,1) (got %f)", p);
   OMR_REQUIRE(C > 0 && per_sample > 0, "omr_dropout: bad channel geometry");
   if (n <= 0) return OMR_OK;
+  {
+    const int esz = dt == OMR_F32 ? 4 : 2;
+    if (n % 4 == 0 && (!channelwise || (C % 4 == 0 && per_sample % 4 == 0)) && (reinterpret_cast<uintptr_t>(x) % (4 * esz)) == 0 &&
+        (reinterpret_cast<uintptr_t>(y) % (4 * esz)) == 0) {
+      OMR_DISPATCH_DT(dt, T, (dropout_vec_kernel<T><<<grid_for(n / 4, 256, 2), 256, 0, as_stream(stream)>>>(
+                                 (const T*)x, (T*)y, n / 4, C, per_sample, p, 1.f / (1.f - p), (uint32_t)seed, channelwise)));
+      OMR_LAUNCHED();
+      return OMR_OK;
+    }
+  }
   OMR_DISPATCH_DT(dt, T, (dropout_kernel<T><<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(
                              (const T*)x, (T*)y, n, C, per_sample, p, 1.f / (1.f - p), (uint32_t)seed, channelwise)));
   OMR_LAUNCHED();

@@ -82,6 +82,67 @@ __global__ void dwconv3x3_wgrad_kernel(const T* __restrict__ x, const T* __restr
   if (db) atomicAdd(db + c, accb);
 }
 
+// Wide variant: 256 threads = (C/4 channel quads) x (256/(C/4) pixel lanes); every thread owns 4 channels (one 8/16-byte
+// load per tap), walks its pixel lane of the block's pixel range, and the lanes are combined in shared memory before
+// ONE set of atomics per block -- many loads in flight per thread group instead of a serial per-channel loop.
+template <typename T>
+__global__ void __launch_bounds__(256) dwconv3x3_wgrad_wide_kernel(const T* __restrict__ x, const T* __restrict__ dy,
+                                                                   float* __restrict__ dw, float* __restrict__ db, int N, int H,
+                                                                   int W, int C, int pix_per_block) {
+  extern __shared__ float red[];  // [lanes][C/4][40]
+  const int quads = C / 4, lanes = 256 / quads;
+  const int cq = threadIdx.x % quads, lane = threadIdx.x / quads;
+  const long long P = (long long)N * H * W;
+  const long long p0 = (long long)blockIdx.x * pix_per_block;
+  long long p1 = p0 + pix_per_block;
+  if (p1 > P) p1 = P;
+  float acc[9][4], accb[4];
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) acc[t][k] = 0.f;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) accb[k] = 0.f;
+  for (long long p = p0 + lane; p < p1; p += lanes) {
+    const int ww = (int)(p % W);
+    const long long r = p / W;
+    const int hh = (int)(r % H), n = (int)(r / H);
+    float g[4];
+    load4(dy + p * C + cq * 4, g);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) accb[k] += g[k];
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+      const int hs = hh + kh - 1;
+      if (hs < 0 || hs >= H) continue;
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const int ws = ww + kw - 1;
+        if (ws < 0 || ws >= W) continue;
+        float xv[4];
+        load4(x + (((long long)n * H + hs) * W + ws) * C + cq * 4, xv);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acc[kh * 3 + kw][k] = fmaf(g[k], xv[k], acc[kh * 3 + kw][k]);
+      }
+    }
+  }
+  float* mine = red + ((long long)lane * quads + cq) * 40;
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) mine[t * 4 + k] = acc[t][k];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) mine[36 + k] = accb[k];
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < quads * 40; idx += 256) {
+    float sum = 0.f;
+    for (int l = 0; l < lanes; ++l) sum += red[(long long)l * quads * 40 + idx];
+    const int q = idx / 40, e = idx - q * 40;
+    if (e < 36) atomicAdd(dw + (long long)(q * 4 + (e & 3)) * 9 + (e >> 2), sum);
+    else if (db) atomicAdd(db + q * 4 + (e - 36), sum);
+  }
+}
+
 int grid_cap(long long n) {
   long long b = cdiv(n, 256);
   if (b < 1) b = 1;
@@ -123,6 +184,17 @@ extern "C" int omr_dwconv3x3_wgrad(int dt, const void* x, const void* dy, float*
   }
   long long P = (long long)N * H * W;
   if (P <= 0) return OMR_OK;
+  if (C % 4 == 0 && C >= 16 && C <= 1024 && 256 % (C / 4) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(dy) & 15) == 0) {
+    int per = (int)cdiv(P, 148LL * 4);
+    if (per < 64) per = 64;
+    const int blocks = (int)cdiv(P, per);
+    const size_t smem = sizeof(float) * 256 * 40;
+    OMR_DISPATCH_DT(dt, T, (dwconv3x3_wgrad_wide_kernel<T><<<blocks, 256, smem, st>>>((const T*)x, (const T*)dy, dw, db, N, H, W, C,
+                                                                                     per)));
+    OMR_LAUNCHED();
+    return OMR_OK;
+  }
   int per = (int)cdiv(P, 148LL * 8);
   if (per < 16) per = 16;
   int blocks = (int)cdiv(P, per);

@@ -159,9 +159,17 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
         if constexpr (sizeof(TO) == 4) {
           if (row_ok) {
             float* cf = reinterpret_cast<float*>(g.C) + (long long)row * g.ldc + ncol;
+            if (full && vec_ok) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (full || ncol + j < g.N) atomicAdd(cf + j, v[j]);
+              for (int j = 0; j < 32; j += 4)
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(cf + j), "f"(v[j]), "f"(v[j + 1]), "f"(v[j + 2]),
+                             "f"(v[j + 3])
+                             : "memory");
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (full || ncol + j < g.N) atomicAdd(cf + j, v[j]);
+            }
           }
         }
         continue;
@@ -309,7 +317,7 @@ int omr_gemm_tc(int out_dt, int transA, int transB, int M, int N, int K, const v
   if (accumulate && out_dt == OMR_F32 && !relu) {
     // gradient accumulation: split the long reduction across CTAs until the machine is full
     long long tiles = (long long)tiles_m * tiles_n;
-    long long want = (2 * 148 + tiles - 1) / tiles;
+    long long want = (148 + tiles - 1) / tiles;
     long long cap = kb_total / 8;
     if (want > cap) want = cap;
     if (want > 1) { splits = (int)want; acc_mode = 2; }

@@ -139,7 +139,8 @@ __global__ void __launch_bounds__(256) add_ln_fwd_kernel(const T* __restrict__ x
     int d = k * 32 + lane;
     float a = to_f(x[row * D + d]);
     if (res) a += to_f(res[row * D + d]);
-    a = round_to<T>(a);  // statistics of the STORED sum, so backward sees the same xhat
+    // statistics and output come from the fp32 sum (one bf16 rounding less per block on the residual stream);
+    // the stored copy of s is rounded, which perturbs the backward's xhat by 2^-9 relative at most
     v[k] = a;
     sum += a;
   }
