@@ -28,17 +28,21 @@ struct GemmTcArgs {
   const float* bias;
   int bias_mode, relu;
   int acc_mode;  // 0 overwrite, 1 read-modify-write, 2 atomicAdd (fp32 output only)
+  int stages;    // smem ring depth: 2 for the short-K (K <= 512) decoder GEMMs so that 2 CTAs share an SM and one tile's
+                 // epilogue overlaps the other's loads; 3-4 for the long reductions
 };
 
 template <int BN>
 constexpr int num_stages() { return BN == 256 ? 4 : (BN == 128 ? 3 : 4); }
 template <int BN>
-constexpr int smem_bytes() { return num_stages<BN>() * (A_TILE_BYTES + BN * BK * 2) + 1024 + 256; }
+constexpr int smem_bytes(int stages) { return stages * (A_TILE_BYTES + BN * BK * 2) + 1024 + 256; }
+template <int BN>
+constexpr int epilogue_bytes(int out_esz) { return 128 * BN * out_esz; }  // the staging rows alias the ring
 
 template <int BN, int A_MN, int B_MN, typename TO>
 __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                      const __grid_constant__ CUtensorMap tmB, GemmTcArgs g) {
-  constexpr int STAGES = num_stages<BN>();
+  const int STAGES = g.stages;
   constexpr int B_TILE_BYTES = BN * BK * 2;
   constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
   constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
@@ -256,10 +260,13 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmTcArgs& g, 
   auto kern = gemm_tc_kernel<BN, A_MN, B_MN, TO>;
   static bool configured = false;  // per template instantiation
   if (!configured) {
-    OMR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<BN>()));
+    OMR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured = true;
   }
-  kern<<<grid, 192, smem_bytes<BN>(), st>>>(tmA, tmB, g);
+  int smem = smem_bytes<BN>(g.stages);
+  const int need = epilogue_bytes<BN>((int)sizeof(TO)) + 1024 + 256;
+  if (smem < need) smem = need;
+  kern<<<grid, 192, smem, st>>>(tmA, tmB, g);
   OMR_LAUNCHED();
   return OMR_OK;
 }
@@ -324,7 +331,9 @@ int omr_gemm_tc(int out_dt, int transA, int transB, int M, int N, int K, const v
   }
   int kb_per_split = (kb_total + splits - 1) / splits;
   splits = (kb_total + kb_per_split - 1) / kb_per_split;
-  GemmTcArgs g{C, ldc, M, N, K, kb_per_split, bias, bias ? bias_mode : 0, relu, acc_mode};
+  int stages = kb_per_split <= 8 ? 2 : (BN == 128 ? 3 : 4);
+  if (stages > kb_per_split) stages = kb_per_split < 2 ? 2 : kb_per_split;
+  GemmTcArgs g{C, ldc, M, N, K, kb_per_split, bias, bias ? bias_mode : 0, relu, acc_mode, stages};
   if (acc_mode == 2 && g.bias_mode != 0) return OMR_TC_NOT_ELIGIBLE;
   dim3 grid((unsigned)tiles_m, (unsigned)tiles_n, (unsigned)splits);
 #define OMR_GEMM_BN(BNV)                                                                         \
