@@ -190,6 +190,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline sample")
     ap.add_argument("--decode-steps", type=int, default=MAX_LEN)
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--no-graph", action="store_true", help="drive the step eagerly from Python instead of replaying CUDA graphs")
     args = ap.parse_args()
     from oracle import synth  # vocabulary loader + synthetic weights only (test infrastructure, not on the timed path)
 
@@ -243,13 +244,17 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    hostt = {}
+
     def timed(fn, k):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
+        t0 = time.perf_counter()
         e0.record(stream)
         for _ in range(k):
             fn()
         e1.record(stream)
+        hostt["issue_ms"] = (time.perf_counter() - t0) * 1e3 / k  # host time to ENQUEUE one step (no sync inside)
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
         if world > 1:
@@ -258,16 +263,29 @@ def main():
 
     for _ in range(args.warmup):
         step(resident)
+    stepper = None
+    launches_per_step = None
+    if not args.no_graph:
+        # the public fast path for static shapes: the whole step (fwd + bwd + all-reduce + Adam) as replayed CUDA graphs
+        n0 = _lib.launch_count()
+        stepper = pkg.GraphedTrainStep(step, resident, opt, variants=2, warmup=1)
+        launches_per_step = (_lib.launch_count() - n0) // 3  # 1 warm-up + 2 captured variants
+        for _ in range(args.warmup):
+            stepper()
+    run_resident = (lambda: stepper()) if stepper is not None else (lambda: step(resident))
     sampler = ClockSampler(local) if rank == 0 else None
     n0 = _lib.launch_count()
-    ms = timed(lambda: step(resident), args.steps)
-    launches = _lib.launch_count() - n0
+    ms = timed(run_resident, args.steps)
+    launches = (launches_per_step * args.steps) if stepper is not None else (_lib.launch_count() - n0)
+    host_issue_ms = hostt["issue_ms"]
     clocks = sampler.stop() if sampler else None
     value = world * b * args.steps / (ms / 1e3)
 
     def e2e_step():
-        batch = [t.to(dev, non_blocking=True) for t in host]
-        loss = step(batch)
+        if stepper is not None:
+            loss = stepper(host)  # pinned host batch -> static device inputs (async H2D), then one graph replay
+        else:
+            loss = step([t.to(dev, non_blocking=True) for t in host])
         return float(loss.item())  # device -> host read of the step's result
 
     e2e_step()
@@ -345,6 +363,8 @@ def main():
                        "l2": "per-step working set (activations, several GB) is far larger than the 126 MB L2; no flush needed"},
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches),
+            "step_driver": "cuda-graph replay (2 captured variants, device-side dropout seeds)" if stepper is not None else "eager python",
+            "host_issue_ms_per_step": host_issue_ms,
             "clocks": clocks,
             "model_tflops_per_gpu": flops_step / (ms / args.steps * 1e-3) / 1e12,
             "model_tc_frac_of_sustained_peak": flops_step / (ms / args.steps * 1e-3) / 1e12 / pk["tc"],

@@ -62,9 +62,11 @@ int omr_add(int dt, const void* a, const void* b, void* out, long long n, omr_st
 /* nn.Dropout / nn.Dropout2d (MixDropout, encoder.py:87-104; decoder dropouts p=0.1):
  * y[i] = keep(seed, key(i)) ? x[i] / (1-p) : 0 with key(i) = i (element-wise) or, when channelwise,
  * (i / per_sample) * C + (i % C) (one decision per (sample, channel) of an NHWC tensor).
- * The mask is a pure function of (seed, key): calling it again on dy is the backward. */
+ * The mask is a pure function of (seed, key): calling it again on dy is the backward.
+ * seed_offset (device int32 scalar, may be NULL) is mixed into the seed on the device: a CUDA-graph-captured
+ * training step passes its step counter here so that every replay draws fresh masks. */
 int omr_dropout(int dt, const void* x, void* y, long long n, int C, long long per_sample, float p, long long seed,
-                int channelwise, omr_stream_t stream);
+                int channelwise, const int* seed_offset, omr_stream_t stream);
 /* Conv2d weight [Co,Ci,3,3] fp32 -> kernel layout in dt (tap-major, channels innermost):
  * transpose == 0: [Co,3,3,Ci] (forward operand); transpose == 1: [Ci,3,3,Co] (data-gradient operand) */
 int omr_pack_conv_weight(int dt, const float* w, void* out, int Co, int Ci, int transpose, omr_stream_t stream);

@@ -8,6 +8,7 @@ The Python classes mirror the reference's ``src/transformer`` surface; every ope
 from .ddp import BucketReducer, DataParallel
 from .decoder import Decoder, PositionalEncoding1D
 from .encoder import HEIGHT_REDUCTION, WIDTH_REDUCTION, ConvBlock, DepthSepConv2D, DSCBlock, Encoder, MixDropout
+from .graph import GraphedTrainStep
 from .greedy import BatchedGreedyDecoder
 from .model import (EOS_TOKEN, NUM_CHANNELS, SOS_TOKEN, CrossAttention, MultimodalTransformer, PositionalEncoding2D,
                     Transformer)
@@ -17,5 +18,5 @@ from .params import GradArena
 __all__ = [
     "Decoder", "PositionalEncoding1D", "Encoder", "ConvBlock", "DSCBlock", "DepthSepConv2D", "MixDropout",
     "PositionalEncoding2D", "CrossAttention", "Transformer", "MultimodalTransformer", "BatchedGreedyDecoder",
-    "FusedAdam", "GradArena", "DataParallel", "BucketReducer", "HEIGHT_REDUCTION", "WIDTH_REDUCTION", "SOS_TOKEN", "EOS_TOKEN", "NUM_CHANNELS",
+    "FusedAdam", "GradArena", "GraphedTrainStep", "DataParallel", "BucketReducer", "HEIGHT_REDUCTION", "WIDTH_REDUCTION", "SOS_TOKEN", "EOS_TOKEN", "NUM_CHANNELS",
 ]

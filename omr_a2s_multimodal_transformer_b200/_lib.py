@@ -20,7 +20,7 @@ _SIGS = {
     "omr_cast": "iippqp",
     "omr_relu_bwd": "ipppqp",
     "omr_add": "ipppqp",
-    "omr_dropout": "ippqiqfqip",
+    "omr_dropout": "ippqiqfqipp",
     "omr_pack_conv_weight": "ippiiip",
     "omr_pack_dw_weight": "ippip",
     "omr_conv3x3_fwd": "ippppiiiiiiiip",

@@ -359,7 +359,8 @@ __device__ __forceinline__ uint32_t mix32(uint32_t a, uint32_t b) {
 }
 template <typename T>
 __global__ void dropout_kernel(const T* __restrict__ x, T* __restrict__ y, long long n, int C, long long per_sample,
-                               float p, float scale, uint32_t seed, int channelwise) {
+                               float p, float scale, uint32_t seed, int channelwise, const int* __restrict__ seed_off) {
+  if (seed_off) seed += (uint32_t)(*seed_off) * 0x9E3779B9u;
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long stride = (long long)gridDim.x * blockDim.x;
   for (; i < n; i += stride) {
@@ -373,7 +374,8 @@ __global__ void dropout_kernel(const T* __restrict__ x, T* __restrict__ y, long 
 // C % 4 == 0 so that a quad never straddles a sample/channel-row boundary
 template <typename T>
 __global__ void dropout_vec_kernel(const T* __restrict__ x, T* __restrict__ y, long long n4, int C, long long per_sample,
-                                   float p, float scale, uint32_t seed, int channelwise) {
+                                   float p, float scale, uint32_t seed, int channelwise, const int* __restrict__ seed_off) {
+  if (seed_off) seed += (uint32_t)(*seed_off) * 0x9E3779B9u;
   long long i4 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (; i4 < n4; i4 += stride) {
@@ -392,7 +394,7 @@ __global__ void dropout_vec_kernel(const T* __restrict__ x, T* __restrict__ y, l
   }
 }
 extern "C" int omr_dropout(int dt, const void* x, void* y, long long n, int C, long long per_sample, float p,
-                           long long seed, int channelwise, omr_stream_t stream) {
+                           long long seed, int channelwise, const int* seed_offset, omr_stream_t stream) {
   OMR_REQUIRE(p >= 0.f && p < 1.f, "omr_dropout: p must be in [0,1) (got %f)", p);
   OMR_REQUIRE(C > 0 && per_sample > 0, "omr_dropout: bad channel geometry");
   if (n <= 0) return OMR_OK;
@@ -401,13 +403,13 @@ extern "C" int omr_dropout(int dt, const void* x, void* y, long long n, int C, l
     if (n % 4 == 0 && (!channelwise || (C % 4 == 0 && per_sample % 4 == 0)) && (reinterpret_cast<uintptr_t>(x) % (4 * esz)) == 0 &&
         (reinterpret_cast<uintptr_t>(y) % (4 * esz)) == 0) {
       OMR_DISPATCH_DT(dt, T, (dropout_vec_kernel<T><<<grid_for(n / 4, 256, 2), 256, 0, as_stream(stream)>>>(
-                                 (const T*)x, (T*)y, n / 4, C, per_sample, p, 1.f / (1.f - p), (uint32_t)seed, channelwise)));
+                                 (const T*)x, (T*)y, n / 4, C, per_sample, p, 1.f / (1.f - p), (uint32_t)seed, channelwise, seed_offset)));
       OMR_LAUNCHED();
       return OMR_OK;
     }
   }
   OMR_DISPATCH_DT(dt, T, (dropout_kernel<T><<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(
-                             (const T*)x, (T*)y, n, C, per_sample, p, 1.f / (1.f - p), (uint32_t)seed, channelwise)));
+                             (const T*)x, (T*)y, n, C, per_sample, p, 1.f / (1.f - p), (uint32_t)seed, channelwise, seed_offset)));
   OMR_LAUNCHED();
   return OMR_OK;
 }

@@ -50,19 +50,50 @@ __global__ void __launch_bounds__(128) attn_decode_partial_kernel(DecArgs a) {
   const T* kp = (const T*)a.k + (long long)b * a.k_bs + h * HD;
   const T* vp = (const T*)a.v + (long long)b * a.v_bs + h * HD;
   const float* kb = a.key_bias ? a.key_bias + (long long)b * a.kb_bs : nullptr;
-  float q[HD];
+  // scores: thread = (key lane g of 16, 8-wide dim chunk c): one 16-byte load per key and thread (a warp covers four
+  // whole 128-byte key rows per instruction), 8-lane shuffle reduction, four keys in flight per thread
+  const int c = tid & 7, g = tid >> 3;
+  float q[8];
+  {
+    float t0[4], t1[4];
+    load4(qp + c * 8, t0);
+    load4(qp + c * 8 + 4, t1);
 #pragma unroll
-  for (int c = 0; c < HD / 4; ++c) {
-    float v[4];
-    load4(qp + c * 4, v);
-    q[c * 4] = v[0] * a.scale; q[c * 4 + 1] = v[1] * a.scale; q[c * 4 + 2] = v[2] * a.scale; q[c * 4 + 3] = v[3] * a.scale;
+    for (int e = 0; e < 4; ++e) { q[e] = t0[e] * a.scale; q[4 + e] = t1[e] * a.scale; }
   }
   float mx = -INFINITY;
-  for (int j = tid; j < n; j += 128) {
-    float s = dot64(kp + (long long)(j0 + j) * a.k_rs, q);
-    if (kb) s += kb[j0 + j];
-    sc[j] = s;
-    mx = fmaxf(mx, s);
+  for (int jb = 0; jb < n; jb += 64) {
+    float part[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int j = jb + u * 16 + g;
+      float kv[8];
+      if (j < n) {
+        const T* kr = kp + (long long)(j0 + j) * a.k_rs + c * 8;
+        load4(kr, *reinterpret_cast<float(*)[4]>(kv));
+        load4(kr + 4, *reinterpret_cast<float(*)[4]>(kv + 4));
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) kv[e] = 0.f;
+      }
+      float d = 0.f;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) d = fmaf(q[e], kv[e], d);
+      part[u] = d;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      float d = part[u];
+      d += __shfl_xor_sync(0xffffffffu, d, 1);
+      d += __shfl_xor_sync(0xffffffffu, d, 2);
+      d += __shfl_xor_sync(0xffffffffu, d, 4);
+      const int j = jb + u * 16 + g;
+      if (j < n) {
+        if (kb) d += kb[j0 + j];
+        if (c == 0) sc[j] = d;
+        mx = fmaxf(mx, d);
+      }
+    }
   }
   mx = block_max(mx, red);
   const float msafe = (mx == -INFINITY) ? 0.f : mx;
@@ -73,18 +104,46 @@ __global__ void __launch_bounds__(128) attn_decode_partial_kernel(DecArgs a) {
     sum += p;
   }
   sum = block_sum(sum, red);  // contains the __syncthreads that publishes sc[]
-  const int d = tid & 63, g = tid >> 6;
-  float acc = 0.f;
-  for (int j = g; j < n; j += 2) acc = fmaf(sc[j], to_f(vp[(long long)(j0 + j) * a.v_rs + d]), acc);
-  float* gs = sc + a.chunk;
+  // P V: thread = (key lane g of 16, 8-wide dim chunk c): 16 keys in flight per step with 16-byte loads, unrolled x4,
+  // so the cache stream is bandwidth- rather than latency-bound; the 16 key lanes are then combined in shared memory
+  float acc[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+  int j = g;
+  for (; j + 48 < n; j += 64) {
+    float v0[8], v1[8], v2[8], v3[8];
+    const T* r0 = vp + (long long)(j0 + j) * a.v_rs + c * 8;
+    const T* r1 = r0 + 16 * a.v_rs;
+    const T* r2 = r1 + 16 * a.v_rs;
+    const T* r3 = r2 + 16 * a.v_rs;
+    load4(r0, *reinterpret_cast<float(*)[4]>(v0)); load4(r0 + 4, *reinterpret_cast<float(*)[4]>(v0 + 4));
+    load4(r1, *reinterpret_cast<float(*)[4]>(v1)); load4(r1 + 4, *reinterpret_cast<float(*)[4]>(v1 + 4));
+    load4(r2, *reinterpret_cast<float(*)[4]>(v2)); load4(r2 + 4, *reinterpret_cast<float(*)[4]>(v2 + 4));
+    load4(r3, *reinterpret_cast<float(*)[4]>(v3)); load4(r3 + 4, *reinterpret_cast<float(*)[4]>(v3 + 4));
+    const float p0 = sc[j], p1 = sc[j + 16], p2 = sc[j + 32], p3 = sc[j + 48];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = fmaf(p0, v0[e], fmaf(p1, v1[e], fmaf(p2, v2[e], fmaf(p3, v3[e], acc[e]))));
+  }
+  for (; j < n; j += 16) {
+    float v0[8];
+    const T* r0 = vp + (long long)(j0 + j) * a.v_rs + c * 8;
+    load4(r0, *reinterpret_cast<float(*)[4]>(v0)); load4(r0 + 4, *reinterpret_cast<float(*)[4]>(v0 + 4));
+    const float p0 = sc[j];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = fmaf(p0, v0[e], acc[e]);
+  }
+  float* gs = sc + a.chunk;  // [16][64]
   __syncthreads();
-  if (g == 1) gs[d] = acc;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) gs[g * HD + c * 8 + e] = acc[e];
   __syncthreads();
-  if (g == 0) {
-    acc += gs[d];
+  if (tid < HD) {
+    float o = 0.f;
+#pragma unroll
+    for (int l = 0; l < 16; ++l) o += gs[l * HD + tid];
     long long w = ((long long)bh * a.nsplit + sp);
-    a.ws_o[w * HD + d] = acc;
-    if (d == 0) { a.ws_ml[w * 2] = mx; a.ws_ml[w * 2 + 1] = sum; }
+    a.ws_o[w * HD + tid] = o;
+    if (tid == 0) { a.ws_ml[w * 2] = mx; a.ws_ml[w * 2 + 1] = sum; }
   }
 }
 
@@ -186,7 +245,7 @@ extern "C" int omr_attn_decode(int dt, const void* q, long long q_bs, const void
   a.o_bs = o_bs; a.key_bias = key_bias; a.kb_bs = kb_bs; a.ws_o = ws; a.ws_ml = ws + bh * nsplit * HD;
   a.B = B; a.H = H; a.Tk = Tk; a.window = window; a.chunk = chunk; a.nsplit = nsplit; a.scale = scale;
   a.pos_dev = pos_dev;
-  size_t smem = sizeof(float) * (chunk + 2 * HD);
+  size_t smem = sizeof(float) * (chunk + 16 * HD);
   OMR_REQUIRE(smem <= 200 * 1024, "omr_attn_decode: chunk too large");
   cudaStream_t st = as_stream(stream);
   dim3 grid((unsigned)bh, (unsigned)nsplit);

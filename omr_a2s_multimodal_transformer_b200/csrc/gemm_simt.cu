@@ -97,8 +97,86 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(GemmArgs g) {
   }
 }
 
+// Skinny GEMM for the greedy-decode step (M = batch <= 32 rows per pass):  C[M,N] = act(A[M,K] W[N,K]^T + bias).
+// The problem is a weight stream (N*K elements read once), so it is spread over N/8 blocks instead of the 1-3 tiles a
+// 128-row tensor-core tile would give.  Per 256-wide K slab the block stages A (<= 32 x 256) and its 8 weight rows in
+// shared memory with coalesced 16-byte loads; then lane = row m, warp = 2 output columns: one conflict-free 16-byte
+// LDS of x, two broadcast LDS of w and 16 FMAs per 8 k -- no shuffles, no dependent global loads in the loop.
+constexpr int SK_KS = 256;          // K slab
+constexpr int SK_LDX = SK_KS + 8;   // padded row (elements) -> 16-byte units of consecutive rows land in distinct banks
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(128) gemm_skinny_kernel(GemmArgs g) {
+  __shared__ __align__(16) TI sx[32 * SK_LDX];
+  __shared__ __align__(16) TI sw[8 * SK_LDX];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nb = blockIdx.x * 8;
+  const TI* A = (const TI*)g.A;
+  const TI* B = (const TI*)g.B;
+  TO* C = (TO*)g.C;
+  constexpr int VEC = 16 / (int)sizeof(TI);  // elements per 16-byte unit
+  for (int mb = 0; mb < g.M; mb += 32) {
+    float acc[2] = {0.f, 0.f};
+    for (int k0 = 0; k0 < g.K; k0 += SK_KS) {
+      const int kn = g.K - k0 < SK_KS ? g.K - k0 : SK_KS;  // multiple of 8
+      const int units = kn / VEC;
+      __syncthreads();
+      for (int idx = threadIdx.x; idx < 32 * units; idx += 128) {
+        const int r = idx / units, u = idx - r * units;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (mb + r < g.M) v = *reinterpret_cast<const uint4*>(A + (long long)(mb + r) * g.lda + k0 + u * VEC);
+        *reinterpret_cast<uint4*>(sx + r * SK_LDX + u * VEC) = v;
+      }
+      for (int idx = threadIdx.x; idx < 8 * units; idx += 128) {
+        const int r = idx / units, u = idx - r * units;
+        const int n = nb + r < g.N ? nb + r : g.N - 1;
+        *reinterpret_cast<uint4*>(sw + r * SK_LDX + u * VEC) = *reinterpret_cast<const uint4*>(B + (long long)n * g.ldb + k0 + u * VEC);
+      }
+      __syncthreads();
+      const TI* xr = sx + lane * SK_LDX;
+      const TI* w0 = sw + (warp * 2) * SK_LDX;
+      const TI* w1 = w0 + SK_LDX;
+#pragma unroll 4
+      for (int k = 0; k < kn; k += 8) {
+        float x[8], a0[8], a1[8];
+        load4(xr + k, *reinterpret_cast<float(*)[4]>(x));
+        load4(xr + k + 4, *reinterpret_cast<float(*)[4]>(x + 4));
+        load4(w0 + k, *reinterpret_cast<float(*)[4]>(a0));
+        load4(w0 + k + 4, *reinterpret_cast<float(*)[4]>(a0 + 4));
+        load4(w1 + k, *reinterpret_cast<float(*)[4]>(a1));
+        load4(w1 + k + 4, *reinterpret_cast<float(*)[4]>(a1 + 4));
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          acc[0] = fmaf(x[e], a0[e], acc[0]);
+          acc[1] = fmaf(x[e], a1[e], acc[1]);
+        }
+      }
+    }
+    const int m = mb + lane;
+    if (m < g.M) {
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const int n = nb + warp * 2 + c;
+        if (n >= g.N) continue;
+        float v = acc[c];
+        if (g.bias_mode == 1) v += g.bias[n];
+        else if (g.bias_mode == 2) v += g.bias[m];
+        if (g.relu) v = fmaxf(v, 0.f);
+        const long long o = (long long)m * g.ldc + n;
+        if (g.accumulate) v += to_f(C[o]);
+        C[o] = from_f<TO>(v);
+      }
+    }
+  }
+}
+
 template <typename TI, typename TO>
 int launch_gemm(const GemmArgs& g, int transA, int transB, int batch, cudaStream_t st) {
+  if (batch == 1 && g.M <= 64 && transA == 0 && transB == 1 && g.K % 8 == 0 && g.lda % 8 == 0 && g.ldb % 8 == 0 &&
+      (reinterpret_cast<uintptr_t>(g.A) & 15) == 0 && (reinterpret_cast<uintptr_t>(g.B) & 15) == 0) {
+    gemm_skinny_kernel<TI, TO><<<(unsigned)cdiv(g.N, 8), 128, 0, st>>>(g);
+    OMR_LAUNCHED();
+    return OMR_OK;
+  }
   dim3 grid((unsigned)cdiv(g.N, BN), (unsigned)cdiv(g.M, BM), (unsigned)batch);
   if (transA == 0 && transB == 0) gemm_simt_kernel<TI, TO, 0, 0><<<grid, 256, 0, st>>>(g);
   else if (transA == 0 && transB == 1) gemm_simt_kernel<TI, TO, 0, 1><<<grid, 256, 0, st>>>(g);

@@ -296,8 +296,10 @@ int omr_gemm_tc(int out_dt, int transA, int transB, int M, int N, int K, const v
   if ((lda * 2) % 16 || (ldb * 2) % 16) return OMR_TC_NOT_ELIGIBLE;
   if ((reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15)) return OMR_TC_NOT_ELIGIBLE;
   if (out_dt != OMR_F32 && out_dt != OMR_BF16) return OMR_TC_NOT_ELIGIBLE;
-  // tiny problems stay on the CUDA-core kernel (launch/TMEM set-up would dominate)
+  // tiny problems stay on the CUDA-core kernels (launch/TMEM set-up would dominate), and so do the skinny forward
+  // GEMMs of the decode step (M <= 64): a 128-row tile would leave 1-3 CTAs to stream the whole weight matrix
   if ((long long)M * N * K < (1LL << 18)) return OMR_TC_NOT_ELIGIBLE;
+  if (M <= 64 && !a_mn && !b_mn && !accumulate) return OMR_TC_NOT_ELIGIBLE;
   int BN = N <= 32 ? 32 : (N <= 64 ? 64 : (N <= 128 ? 128 : 256));
   if (b_mn && BN < 64) BN = 64;
   if (a_mn && BN < 64) BN = 64;

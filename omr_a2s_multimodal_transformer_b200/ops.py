@@ -53,6 +53,11 @@ def add(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None) ->
     return out
 
 
+# device int32 scalar mixed into every dropout seed on the GPU (None: host seeds only).  A graph-captured training
+# step points this at its step counter so that replays draw fresh masks (graph.GraphedTrainStep).
+SEED_OFFSET_DEV: Optional[torch.Tensor] = None
+
+
 def dropout(x: torch.Tensor, p: float, seed: int, channelwise: bool = False, inplace: bool = False) -> torch.Tensor:
     """Seeded dropout; for NHWC tensors ``channelwise`` drops whole (sample, channel) planes (Dropout2d).
     Applying it to a gradient with the same seed is the backward pass."""
@@ -61,7 +66,7 @@ def dropout(x: torch.Tensor, p: float, seed: int, channelwise: bool = False, inp
     c = x.shape[-1]
     per_sample = x.numel() // x.shape[0]
     call("omr_dropout", dt_code(x.dtype), ptr(x), ptr(y), x.numel(), c, per_sample, float(p), int(seed), int(channelwise),
-         stream_ptr())
+         ptr(SEED_OFFSET_DEV), stream_ptr())
     return y
 
 
