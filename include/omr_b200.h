@@ -78,9 +78,13 @@ int omr_pack_dw_weight(int dt, const float* w, void* out, int C, omr_stream_t st
  * Ho = ceil(H/sh), Wo = ceil(W/sw); relu != 0 fuses the activation. */
 int omr_conv3x3_fwd(int dt, const void* x, const void* w, const float* bias, void* y, int N, int H, int W, int Ci,
                     int Co, int sh, int sw, int relu, omr_stream_t stream);
-/* dx[N,H,W,Ci] = conv3x3 data gradient of dy[N,Ho,Wo,Co] */
+/* dx[N,H,W,Ci] = conv3x3 data gradient of dy[N,Ho,Wo,Co].
+ * mask (same shape/type as dx, may be NULL): fused backward of the ReLU (and dropout) that PRODUCED this conv's
+ * input: dx = mask > 0 ? dx * mask_scale : 0, with mask = the conv's own forward input (a ReLU output, possibly
+ * passed through dropout, whose zeros cover both the inactive and the dropped elements) and mask_scale the
+ * dropout's 1/(1-p) (1 without dropout).  Saves the separate relu_bwd / dropout-backward passes. */
 int omr_conv3x3_dgrad(int dt, const void* dy, const void* w, void* dx, int N, int H, int W, int Ci, int Co, int sh,
-                      int sw, omr_stream_t stream);
+                      int sw, const void* mask, float mask_scale, omr_stream_t stream);
 /* dw[Co,Ci,3,3] (fp32, torch layout) and db[Co] (fp32) ; accumulate != 0 adds to dw/db */
 int omr_conv3x3_wgrad(int dt, const void* x, const void* dy, float* dw, float* db, int N, int H, int W, int Ci, int Co,
                       int sh, int sw, int accumulate, omr_stream_t stream);
@@ -98,9 +102,11 @@ int omr_dwconv3x3_wgrad(int dt, const void* x, const void* dy, float* dw, float*
  * combined in double so that E[x^2]-E[x]^2 and the backward's mean subtractions do not cancel). */
 int omr_instnorm_fwd(int dt, const void* x, void* y, float* stats, double* ws, int N, int HW, int C, float eps,
                      omr_stream_t stream);
-/* dx from dy, the saved INPUT x and stats; ws: fp64 scratch of N*C*2 doubles */
+/* dx from dy, the saved INPUT x and stats; ws: fp64 scratch of N*C*2 doubles.
+ * relu_mask != 0: x is a ReLU output (possibly after dropout); the result is additionally multiplied by
+ * (x > 0 ? mask_scale : 0), i.e. the backward of that ReLU/dropout is fused (see omr_conv3x3_dgrad). */
 int omr_instnorm_bwd(int dt, const void* dy, const void* x, const float* stats, void* dx, double* ws, int N, int HW,
-                     int C, omr_stream_t stream);
+                     int C, int relu_mask, float mask_scale, omr_stream_t stream);
 
 /* PositionalEncoding2D + flatten/permute + concat (model.py:45-48, 498, 506, 654):
  * out[b, row_off + p, c] = x[b, p, c] + pe[(p / w) * pe_w + (p % w), c]   for p < h*w

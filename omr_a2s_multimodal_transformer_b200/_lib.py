@@ -24,13 +24,13 @@ _SIGS = {
     "omr_pack_conv_weight": "ippiiip",
     "omr_pack_dw_weight": "ippip",
     "omr_conv3x3_fwd": "ippppiiiiiiiip",
-    "omr_conv3x3_dgrad": "ipppiiiiiiip",
+    "omr_conv3x3_dgrad": "ipppiiiiiiipfp",
     "omr_conv3x3_wgrad": "ippppiiiiiiiip",
     "omr_dwconv3x3_fwd": "ippppiiiip",
     "omr_dwconv3x3_dgrad": "ipppiiiip",
     "omr_dwconv3x3_wgrad": "ippppiiiiip",
     "omr_instnorm_fwd": "ippppiiifp",
-    "omr_instnorm_bwd": "ipppppiiip",
+    "omr_instnorm_bwd": "ipppppiiiifp",
     "omr_pe2d_add": "ipppiiiiiiip",
     "omr_copy_rows": "ippiiiiip",
     "omr_key_bias_from_lengths": "ppiiiifp",

@@ -6,6 +6,7 @@
 #include <atomic>
 
 #include "common.cuh"
+#include "kernels.h"
 
 static thread_local char g_err[1024] = "";
 static std::atomic<long long> g_launches{0};
@@ -66,6 +67,19 @@ extern "C" int omr_relu_bwd(int dt, const void* y, const void* dy, void* dx, lon
   if (n <= 0) return OMR_OK;
   OMR_DISPATCH_DT(dt, T, (relu_bwd_kernel<T><<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(
                              (const T*)y, (const T*)dy, (T*)dx, n)));
+  OMR_LAUNCHED();
+  return OMR_OK;
+}
+
+template <typename T>
+__global__ void relu_mask_scale_kernel(T* __restrict__ dx, const T* __restrict__ m, float scale, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) dx[i] = to_f(m[i]) > 0.f ? from_f<T>(to_f(dx[i]) * scale) : from_f<T>(0.f);
+}
+int omr_relu_mask_scale(int dt, void* dx, const void* mask, float scale, long long n, cudaStream_t st) {
+  if (n <= 0) return OMR_OK;
+  OMR_DISPATCH_DT(dt, T, (relu_mask_scale_kernel<T><<<grid_for(n, 256), 256, 0, st>>>((T*)dx, (const T*)mask, scale, n)));
   OMR_LAUNCHED();
   return OMR_OK;
 }

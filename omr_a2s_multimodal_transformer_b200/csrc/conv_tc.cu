@@ -37,6 +37,8 @@ struct ConvTcArgs {
   int ntaps;
   int dh[MAX_TAPS], dw[MAX_TAPS], widx[MAX_TAPS];
   int OH, OW, osh, osw, oph, opw;  // output tensor extent and the affine map grid -> output pixel
+  const bf16* mask;                // optional: out = mask > 0 ? out * mask_scale : 0 (same layout as y)
+  float mask_scale;
 };
 
 // RB: row bytes (= 2 * min(Cin, 64)); G: (tap, chunk) sub-tiles per pipeline stage
@@ -177,6 +179,19 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
             if (g.bias) f[j] += __ldg(g.bias + c0 + j);
             if (g.relu) f[j] = fmaxf(f[j], 0.f);
           }
+          if (g.mask) {  // fused ReLU / dropout backward of the layer that produced this conv's forward input
+            const uint4 m0 = reinterpret_cast<const uint4*>(g.mask + (dst - g.y) + c0)[0];
+            const uint4 m1 = reinterpret_cast<const uint4*>(g.mask + (dst - g.y) + c0)[1];
+            const __nv_bfloat162* mb0 = reinterpret_cast<const __nv_bfloat162*>(&m0);
+            const __nv_bfloat162* mb1 = reinterpret_cast<const __nv_bfloat162*>(&m1);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              f[2 * j] = __low2float(mb0[j]) > 0.f ? f[2 * j] * g.mask_scale : 0.f;
+              f[2 * j + 1] = __high2float(mb0[j]) > 0.f ? f[2 * j + 1] * g.mask_scale : 0.f;
+              f[8 + 2 * j] = __low2float(mb1[j]) > 0.f ? f[8 + 2 * j] * g.mask_scale : 0.f;
+              f[8 + 2 * j + 1] = __high2float(mb1[j]) > 0.f ? f[8 + 2 * j + 1] * g.mask_scale : 0.f;
+            }
+          }
           uint4 o0, o1;
           o0.x = pack_bf16(f[0], f[1]); o0.y = pack_bf16(f[2], f[3]); o0.z = pack_bf16(f[4], f[5]); o0.w = pack_bf16(f[6], f[7]);
           o1.x = pack_bf16(f[8], f[9]); o1.y = pack_bf16(f[10], f[11]); o1.z = pack_bf16(f[12], f[13]); o1.w = pack_bf16(f[14], f[15]);
@@ -315,6 +330,19 @@ __global__ void __launch_bounds__(192, 1) conv_halo_kernel(const __grid_constant
             f[j] = __uint_as_float(v[j]);
             if (g.bias) f[j] += __ldg(g.bias + c0 + j);
             if (g.relu) f[j] = fmaxf(f[j], 0.f);
+          }
+          if (g.mask) {  // fused ReLU / dropout backward of the layer that produced this conv's forward input
+            const uint4 m0 = reinterpret_cast<const uint4*>(g.mask + (dst - g.y) + c0)[0];
+            const uint4 m1 = reinterpret_cast<const uint4*>(g.mask + (dst - g.y) + c0)[1];
+            const __nv_bfloat162* mb0 = reinterpret_cast<const __nv_bfloat162*>(&m0);
+            const __nv_bfloat162* mb1 = reinterpret_cast<const __nv_bfloat162*>(&m1);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              f[2 * j] = __low2float(mb0[j]) > 0.f ? f[2 * j] * g.mask_scale : 0.f;
+              f[2 * j + 1] = __high2float(mb0[j]) > 0.f ? f[2 * j + 1] * g.mask_scale : 0.f;
+              f[8 + 2 * j] = __low2float(mb1[j]) > 0.f ? f[8 + 2 * j] * g.mask_scale : 0.f;
+              f[8 + 2 * j + 1] = __high2float(mb1[j]) > 0.f ? f[8 + 2 * j + 1] * g.mask_scale : 0.f;
+            }
           }
           uint4 o0, o1;
           o0.x = pack_bf16(f[0], f[1]); o0.y = pack_bf16(f[2], f[3]); o0.z = pack_bf16(f[4], f[5]); o0.w = pack_bf16(f[6], f[7]);
@@ -476,15 +504,17 @@ int omr_conv3x3_fwd_tc(const void* x, const void* w, const float* bias, void* y,
 // dx[N,H,W,Ci] from dy[N,Ho,Wo,Co] and the transposed pack wT[Ci, 9*Co]:
 //   dx[h,w,ci] = sum_{kh,kw,co} dy[(h+1-kh)/sh, (w+1-kw)/sw, co] * w[co,ci,kh,kw]   (only exact divisions)
 int omr_conv3x3_dgrad_tc(const void* dy, const void* wT, void* dx, int N, int H, int W, int Ci, int Co, int sh, int sw,
-                         cudaStream_t st) {
+                         const void* mask, float mask_scale, cudaStream_t st) {
   if (!shape_ok(Ci, Co) || N < 1 || sh > 2 || sw > 2) return OMR_TC_NOT_ELIGIBLE;
-  if ((reinterpret_cast<uintptr_t>(dy) & 15) || (reinterpret_cast<uintptr_t>(wT) & 15) || (reinterpret_cast<uintptr_t>(dx) & 15))
+  if ((reinterpret_cast<uintptr_t>(dy) & 15) || (reinterpret_cast<uintptr_t>(wT) & 15) || (reinterpret_cast<uintptr_t>(dx) & 15) ||
+      (reinterpret_cast<uintptr_t>(mask) & 15))
     return OMR_TC_NOT_ELIGIBLE;
   const int Ho = (H + sh - 1) / sh, Wo = (W + sw - 1) / sw;
   for (int ph = 0; ph < sh; ++ph)
     for (int pw = 0; pw < sw; ++pw) {
       ConvTcArgs a{};
       a.y = (bf16*)dx; a.bias = nullptr; a.relu = 0; a.N = N;
+      a.mask = (const bf16*)mask; a.mask_scale = mask_scale;
       a.GH = (H - ph + sh - 1) / sh; a.GW = (W - pw + sw - 1) / sw;  // pixels of this parity class
       if (a.GH <= 0 || a.GW <= 0) continue;
       a.ish = 1; a.isw = 1;

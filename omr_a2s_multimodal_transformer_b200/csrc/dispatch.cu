@@ -52,13 +52,15 @@ extern "C" int omr_conv3x3_fwd(int dt, const void* x, const void* w, const float
 }
 
 extern "C" int omr_conv3x3_dgrad(int dt, const void* dy, const void* wT, void* dx, int N, int H, int W, int Ci, int Co,
-                                 int sh, int sw, omr_stream_t stream) {
+                                 int sh, int sw, const void* mask, float mask_scale, omr_stream_t stream) {
   OMR_REQUIRE(N >= 0 && H > 0 && W > 0 && Ci > 0 && Co > 0 && sh > 0 && sw > 0, "omr_conv3x3_dgrad: bad shape");
   cudaStream_t st = as_stream(stream);
   if (tc_enabled() && dt == OMR_BF16) {
-    TC_TRY(omr_conv3x3_dgrad_tc(dy, wT, dx, N, H, W, Ci, Co, sh, sw, st));
+    TC_TRY(omr_conv3x3_dgrad_tc(dy, wT, dx, N, H, W, Ci, Co, sh, sw, mask, mask_scale, st));
   }
-  return omr_conv3x3_dgrad_simt(dt, dy, wT, dx, N, H, W, Ci, Co, sh, sw, st);
+  int rc = omr_conv3x3_dgrad_simt(dt, dy, wT, dx, N, H, W, Ci, Co, sh, sw, st);
+  if (rc || !mask) return rc;
+  return omr_relu_mask_scale(dt, dx, mask, mask_scale, (long long)N * H * W * Ci, st);  // CUDA-core path: separate pass
 }
 
 extern "C" int omr_conv3x3_wgrad(int dt, const void* x, const void* dy, float* dw, float* db, int N, int H, int W,

@@ -84,7 +84,7 @@ __global__ void in_apply_fwd_kernel(const T* __restrict__ x, const float* __rest
 template <typename T>
 __global__ void in_apply_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const float* __restrict__ stats,
                                     const double* __restrict__ sums, T* __restrict__ dx, int N, int HW, int C,
-                                    double inv_hw) {
+                                    double inv_hw, int relu_mask, float mask_scale) {
   const int c4n = C / 4;
   long long total = (long long)N * HW * c4n;
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -102,7 +102,9 @@ __global__ void in_apply_bwd_kernel(const T* __restrict__ dy, const T* __restric
     for (int k = 0; k < 4; ++k) {
       float rstd = s[2 * k + 1];
       float xh = (v[k] - s[2 * k]) * rstd;
+      const float xin = v[k];
       v[k] = rstd * (g[k] - (float)(q[2 * k] * inv_hw) - xh * (float)(q[2 * k + 1] * inv_hw));
+      if (relu_mask) v[k] = xin > 0.f ? v[k] * mask_scale : 0.f;
     }
     store4(dx + p * C + c4 * 4, v);
   }
@@ -241,7 +243,7 @@ extern "C" int omr_instnorm_fwd(int dt, const void* x, void* y, float* stats, do
 }
 
 extern "C" int omr_instnorm_bwd(int dt, const void* dy, const void* x, const float* stats, void* dx, double* ws, int N,
-                                int HW, int C, omr_stream_t stream) {
+                                int HW, int C, int relu_mask, float mask_scale, omr_stream_t stream) {
   int CT = pick_ct(C);
   OMR_REQUIRE(CT > 0 && C % 4 == 0, "omr_instnorm_bwd: unsupported channel count %d", C);
   if ((long long)N * HW * C <= 0) return OMR_OK;
@@ -256,7 +258,7 @@ extern "C" int omr_instnorm_bwd(int dt, const void* dy, const void* x, const flo
   OMR_LAUNCHED();
   long long total = (long long)N * HW * (C / 4);
   OMR_DISPATCH_DT(dt, T, (in_apply_bwd_kernel<T><<<grid_cap(total), 256, 0, st>>>((const T*)dy, (const T*)x, stats, ws,
-                                                                                 (T*)dx, N, HW, C, 1.0 / HW)));
+                                                                                 (T*)dx, N, HW, C, 1.0 / HW, relu_mask, mask_scale)));
   OMR_LAUNCHED();
   return OMR_OK;
 }

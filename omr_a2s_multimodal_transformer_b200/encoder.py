@@ -52,40 +52,80 @@ class DropoutPlan:
         return random.random() < 0.5
 
 
-def _maybe_dropout(x: torch.Tensor, c: _Ctx, here: bool) -> torch.Tensor:
+FUSE_RELU_BWD = True  # tests flip this to compare against the unfused relu_bwd / dropout-backward kernels
+
+
+class _Act:
+    """Book-keeping for a ReLU output y (possibly followed by dropout) whose ONLY consumer can fuse the backward of that
+    ReLU/dropout into its own gradient kernel (conv data-gradient epilogue, InstanceNorm backward): the consumer multiplies
+    its dx by (x > 0 ? scale : 0), where x = the tensor it consumed -- zeros of x cover both inactive and dropped elements,
+    scale is the dropout's 1/(1-p).  ``premasked`` is set by such a consumer at forward time; the producer's backward
+    closures read it at backward time and skip their relu_bwd / dropout-backward kernels."""
+
+    __slots__ = ("premasked", "scale")
+
+    def __init__(self) -> None:
+        self.premasked = False
+        self.scale = 1.0
+
+
+def _maybe_dropout(x: torch.Tensor, c: _Ctx, here: bool, act: Optional[_Act] = None) -> torch.Tensor:
     if not (here and c.training and c.dropout.p > 0.0):
         return x
     elementwise = c.dropout.kind()
     p = c.dropout.p if elementwise else c.dropout.p / 2
     seed = c.dropout.seed_fn()
     y = ops.dropout(x, p, seed, channelwise=not elementwise)
+    if act is not None:
+        act.scale = 1.0 / (1.0 - p)
     if c.tape is not None:
-        c.tape.append(lambda dy: ops.dropout(dy, p, seed, channelwise=not elementwise, inplace=True))
-    return y
 
-
-def _conv_step(x: torch.Tensor, cp: ConvParams, stride: Tuple[int, int], relu: bool, c: _Ctx, need_dx: bool) -> torch.Tensor:
-    wp = c.cache.get(cp.weight, "conv", c.dtype)
-    y = ops.conv3x3_fwd(x, wp, cp.bias, stride, relu)
-    if c.tape is not None:
-        in_hw = (x.shape[1], x.shape[2])
-
-        def bwd(dy: torch.Tensor) -> Optional[torch.Tensor]:
-            dz = ops.relu_bwd(y, dy, inplace=True) if relu else dy
-            if cp.weight.requires_grad:
-                ops.conv3x3_wgrad(x, dz, grad_buf(cp.weight), grad_buf(cp.bias), stride, accumulate=True)
-            if not need_dx:
-                return None
-            return ops.conv3x3_dgrad(dz, c.cache.get(cp.weight, "convT", c.dtype), in_hw, stride)
+        def bwd(dy: torch.Tensor) -> torch.Tensor:
+            if act is not None and act.premasked:
+                return dy  # the consumer of y already applied (y > 0 ? 1/(1-p) : 0)
+            return ops.dropout(dy, p, seed, channelwise=not elementwise, inplace=True)
 
         c.tape.append(bwd)
     return y
 
 
-def _instnorm_step(x: torch.Tensor, c: _Ctx) -> torch.Tensor:
+def _conv_step(x: torch.Tensor, cp: ConvParams, stride: Tuple[int, int], relu: bool, c: _Ctx, need_dx: bool,
+               x_act: Optional[_Act] = None, y_act: Optional[_Act] = None) -> torch.Tensor:
+    """x_act: x is a ReLU(+dropout) output whose backward this conv's data gradient fuses; y_act: record for this conv's
+    own ReLU output, filled in by whoever consumes it."""
+    wp = c.cache.get(cp.weight, "conv", c.dtype)
+    y = ops.conv3x3_fwd(x, wp, cp.bias, stride, relu)
+    if c.tape is not None:
+        in_hw = (x.shape[1], x.shape[2])
+        fuse = FUSE_RELU_BWD and x_act is not None and need_dx
+        if fuse:
+            x_act.premasked = True
+
+        def bwd(dy: torch.Tensor) -> Optional[torch.Tensor]:
+            dz = dy
+            if relu and not (y_act is not None and y_act.premasked):
+                dz = ops.relu_bwd(y, dy, inplace=True)
+            if cp.weight.requires_grad:
+                ops.conv3x3_wgrad(x, dz, grad_buf(cp.weight), grad_buf(cp.bias), stride, accumulate=True)
+            if not need_dx:
+                return None
+            wt = c.cache.get(cp.weight, "convT", c.dtype)
+            if fuse:
+                return ops.conv3x3_dgrad(dz, wt, in_hw, stride, mask=x, mask_scale=x_act.scale)
+            return ops.conv3x3_dgrad(dz, wt, in_hw, stride)
+
+        c.tape.append(bwd)
+    return y
+
+
+def _instnorm_step(x: torch.Tensor, c: _Ctx, x_act: Optional[_Act] = None) -> torch.Tensor:
     y, stats = ops.instnorm_fwd(x, IN_EPS)
     if c.tape is not None:
-        c.tape.append(lambda dy: ops.instnorm_bwd(dy, x, stats))
+        if FUSE_RELU_BWD and x_act is not None:
+            x_act.premasked = True
+            c.tape.append(lambda dy: ops.instnorm_bwd(dy, x, stats, relu_mask=True, mask_scale=x_act.scale))
+        else:
+            c.tape.append(lambda dy: ops.instnorm_bwd(dy, x, stats))
     return y
 
 
@@ -166,15 +206,19 @@ class ConvBlock(nn.Module):
         self.conv3 = ConvParams(out_c, out_c, (3, 3))
         self.dropout = MixDropout(dropout_prob=dropout, dropout_2d_prob=dropout / 2)
 
-    def _run(self, x: torch.Tensor, c: _Ctx, need_dx: bool) -> torch.Tensor:
+    def _run(self, x: torch.Tensor, c: _Ctx, need_dx: bool, x_act: Optional[_Act] = None,
+             out_act: Optional[_Act] = None) -> torch.Tensor:
+        """x_act: record of the ReLU output x comes from (previous block), out_act: record for this block's output, to
+        be completed by the next block's first convolution."""
         pos = c.dropout.draw()
-        x = _conv_step(x, self.conv1, (1, 1), True, c, need_dx)
-        x = _maybe_dropout(x, c, pos == 1)
-        x = _conv_step(x, self.conv2, (1, 1), True, c, True)
-        x = _maybe_dropout(x, c, pos == 2)
-        x = _instnorm_step(x, c)
-        x = _conv_step(x, self.conv3, self.stride, True, c, True)
-        x = _maybe_dropout(x, c, pos == 3)
+        a1, a2 = _Act(), _Act()
+        x = _conv_step(x, self.conv1, (1, 1), True, c, need_dx, x_act=x_act, y_act=a1)
+        x = _maybe_dropout(x, c, pos == 1, a1)
+        x = _conv_step(x, self.conv2, (1, 1), True, c, True, x_act=a1, y_act=a2)
+        x = _maybe_dropout(x, c, pos == 2, a2)
+        x = _instnorm_step(x, c, x_act=a2)
+        x = _conv_step(x, self.conv3, self.stride, True, c, True, y_act=out_act)
+        x = _maybe_dropout(x, c, pos == 3, out_act)
         return x
 
 
@@ -266,8 +310,14 @@ class Encoder(nn.Module):
 
     def _run(self, x: torch.Tensor, dtype: torch.dtype, tape: Tape, training: bool) -> torch.Tensor:
         c = _Ctx(dtype, self._wcache, tape, training, DropoutPlan(self.dropout_p, self._next_seed))
+        prev_act: Optional[_Act] = None
+        nblk = len(self.conv_blocks)
         for i, blk in enumerate(self.conv_blocks):
-            x = blk._run(x, c, need_dx=(i > 0))
+            # the output of the last block feeds the DSC stack (depthwise conv + residual add: several consumers), so
+            # only blocks 0..n-2 hand their output record to the next block's first convolution
+            out_act = _Act() if i + 1 < nblk else None
+            x = blk._run(x, c, need_dx=(i > 0), x_act=prev_act, out_act=out_act)
+            prev_act = out_act
         for blk in self.dscblocks:
             if tape is None:
                 xt = blk._run(x, c)

@@ -101,15 +101,18 @@ def conv3x3_fwd(x, wp, bias, stride=(1, 1), relu=False):
     return y
 
 
-def conv3x3_dgrad(dy, wpt, in_hw, stride=(1, 1)):
-    """dy [N,Ho,Wo,Co], wpt [Ci,3,3,Co] -> dx [N,H,W,Ci]"""
+def conv3x3_dgrad(dy, wpt, in_hw, stride=(1, 1), mask=None, mask_scale: float = 1.0):
+    """dy [N,Ho,Wo,Co], wpt [Ci,3,3,Co] -> dx [N,H,W,Ci]; with ``mask`` (the conv's forward input, a ReLU/dropout output)
+    the backward of that ReLU/dropout is fused: dx = mask > 0 ? dx * mask_scale : 0"""
     _chk(dy, "conv3x3_dgrad.dy"), _chk(wpt, "conv3x3_dgrad.w")
+    if mask is not None:
+        _chk(mask, "conv3x3_dgrad.mask")
     n, _, _, co = dy.shape
     ci = wpt.shape[0]
     h, w = in_hw
     dx = torch.empty((n, h, w, ci), dtype=dy.dtype, device=dy.device)
     call("omr_conv3x3_dgrad", dt_code(dy.dtype), ptr(dy), ptr(wpt), ptr(dx), n, h, w, ci, co, stride[0], stride[1],
-         stream_ptr())
+         ptr(mask), float(mask_scale), stream_ptr())
     return dx
 
 
@@ -156,12 +159,14 @@ def instnorm_fwd(x, eps: float):
     return y, stats
 
 
-def instnorm_bwd(dy, x, stats):
+def instnorm_bwd(dy, x, stats, relu_mask: bool = False, mask_scale: float = 1.0):
+    """relu_mask: x is a ReLU (+dropout) output and the backward of that ReLU/dropout is fused into the result"""
     _chk(dy, "instnorm_bwd.dy"), _chk(x, "instnorm_bwd.x")
     n, h, w, c = x.shape
     dx = torch.empty_like(x)
     ws = torch.empty((n, c, 2), dtype=torch.float64, device=x.device)
-    call("omr_instnorm_bwd", dt_code(x.dtype), ptr(dy), ptr(x), ptr(stats), ptr(dx), ptr(ws), n, h * w, c, stream_ptr())
+    call("omr_instnorm_bwd", dt_code(x.dtype), ptr(dy), ptr(x), ptr(stats), ptr(dx), ptr(ws), n, h * w, c, int(relu_mask),
+         float(mask_scale), stream_ptr())
     return dx
 
 

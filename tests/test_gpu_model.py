@@ -211,3 +211,78 @@ def test_cpu_tensor_raises():
     m, _, w2i = build_unimodal()
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         m.encoder(torch.zeros(1, 1, 32, 32))
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-5), (torch.bfloat16, 3e-2)])
+def test_fused_relu_dropout_backward_matches_unfused_in_train_mode(dtype, tol):
+    """train mode (MixDropout active): the ReLU / dropout backward fused into the consumer's gradient kernel (conv dgrad
+    epilogue, InstanceNorm backward) against the separate relu_bwd / dropout kernels, same host RNG and seeds"""
+    import random
+
+    from omr_a2s_multimodal_transformer_b200 import encoder as enc_mod
+
+    enc = __import__("omr_a2s_multimodal_transformer_b200").Encoder(1)
+    sd = synth.synth_state_dict(enc.state_dict(), seed=5)
+    enc.load_state_dict(sd)
+    enc = enc.to(DEV).train()
+    enc.compute_dtype = dtype
+    x = torch.rand(2, 1, 64, 128, generator=torch.Generator().manual_seed(1)).to(DEV)
+    gy = None
+    grads = []
+    for fuse in (True, False):
+        enc_mod.FUSE_RELU_BWD = fuse
+        try:
+            random.seed(123)
+            enc._seed_state = 0x1234567
+            enc.zero_grad(set_to_none=True)
+            y = enc(x)
+            if gy is None:
+                gy = torch.randn(y.shape, generator=torch.Generator().manual_seed(2)).to(DEV).to(y.dtype)
+            y.backward(gy)
+            grads.append({k: p.grad.detach().clone() for k, p in enc.named_parameters()})
+        finally:
+            enc_mod.FUSE_RELU_BWD = True
+    num = den = 0.0
+    for k in grads[0]:
+        num += float((grads[0][k].double() - grads[1][k].double()).pow(2).sum())
+        den += float(grads[1][k].double().pow(2).sum())
+    assert den > 0 and (num / den) ** 0.5 < tol, (num / den) ** 0.5
+
+
+def test_graphed_train_step_matches_eager():
+    """whole-step CUDA-graph replay == the same steps driven eagerly (eval mode: no dropout, so both are deterministic
+    up to atomic-add ordering)"""
+    import omr_a2s_multimodal_transformer_b200 as pkg
+
+    batch = None
+    finals = []
+    for graphed in (False, True):
+        m, sd, w2i = build_multimodal(dtype=torch.bfloat16)
+        if batch is None:
+            batch = [t.to(DEV) for t in synth.synth_multimodal_batch(2, (64, 128), (48, 96), [12, 9], w2i)]
+        dp = pkg.DataParallel(m, broadcast=False)
+        opt = m.configure_optimizers()
+
+        def step(b):
+            xi, xli, xa, xla, y_in, y_out = b
+            dp.zero_grad()
+            mem, xl = m._memory(xi, xa, xli, xla, "both")
+            loss = m.decoder.loss(tgt=y_in, memory=mem, memory_len=xl, targets=y_out)
+            loss.backward()
+            dp.sync_gradients()
+            opt.step()
+            return loss
+
+        losses = []
+        if graphed:
+            st = pkg.GraphedTrainStep(step, batch, opt, variants=2, warmup=1)  # the warm-up is step 1
+            for _ in range(3):
+                losses.append(float(st()))
+        else:
+            for _ in range(4):
+                losses.append(float(step(batch)))
+            losses = losses[1:]
+        finals.append((losses, {k: p.detach().clone() for k, p in m.named_parameters()}))
+    (l0, p0), (l1, p1) = finals
+    assert max(abs(a - b) for a, b in zip(l0, l1)) < 2e-2 * max(l0), (l0, l1)
+    assert l1[-1] < l1[0]  # it trains
