@@ -226,6 +226,7 @@ template <int RB>
 __global__ void __launch_bounds__(192, 1) conv_halo_kernel(const __grid_constant__ CUtensorMap tmX,
                                                            const __grid_constant__ CUtensorMap tmW, ConvTcArgs g, int wsub,
                                                            int hsub, int stages) {
+  // one tile = TH output rows x TW pixels of one image: ONE (TH+2) x (TW+2) TMA box, TH accumulators of [128 x Cout]
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sW = smem;                // 9 taps x wsub
@@ -239,7 +240,10 @@ __global__ void __launch_bounds__(192, 1) conv_halo_kernel(const __grid_constant
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t tmem_cols = g.Cout * 2 <= 32 ? 32 : (g.Cout * 2 <= 64 ? 64 : (g.Cout * 2 <= 128 ? 128 : 256));
+  const int TH = g.TH;
+  const uint32_t acc_cols = (uint32_t)(TH * g.Cout);  // per accumulator buffer
+  const uint32_t need = 2 * acc_cols;
+  const uint32_t tmem_cols = need <= 32 ? 32 : (need <= 64 ? 64 : (need <= 128 ? 128 : (need <= 256 ? 256 : 512)));
   const int pitch = g.TW + 2;  // pixel rows per input image row inside the halo box
 
   if (warp == 4 && lane == 0) {
@@ -273,14 +277,25 @@ __global__ void __launch_bounds__(192, 1) conv_halo_kernel(const __grid_constant
         const int n = tile / (g.tiles_w * g.tiles_h);
         const int s = it % stages;
         mbar_wait(&empty_bar[s], ((it / stages) & 1) ^ 1);
-        mbar_expect_tx(&full_bar[s], 3u * (uint32_t)pitch * RB);
-        tma_load_4d(sH + s * hsub, &tmX, &full_bar[s], 0, tw * g.TW - 1, th - 1, n);
+        mbar_expect_tx(&full_bar[s], (uint32_t)(TH + 2) * (uint32_t)pitch * RB);
+        tma_load_4d(sH + s * hsub, &tmX, &full_bar[s], 0, tw * g.TW - 1, th * TH - 1, n);
       }
     }
   } else if (warp == 5) {
     if (lane == 0) {
       const uint32_t idesc = make_idesc_bf16(128, g.Cout, 0, 0);
+      const uint64_t d_hi = make_smem_desc(0, 16, 8 * RB, RB);
+      // per-tap start offsets inside the halo (A) and the weight bank (B), in 16-byte units, held in registers
+      uint32_t ta[9], tb[9];
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        const int tt = t < g.ntaps ? t : 0;
+        ta[t] = (uint32_t)(((g.dh[tt] + 1) * pitch + (g.dw[tt] + 1)) * RB) >> 4;
+        tb[t] = (uint32_t)(g.widx[tt] * wsub) >> 4;
+      }
+      const uint32_t row_step = (uint32_t)(pitch * RB) >> 4;
       mbar_wait(w_full, 0);
+      const uint32_t w_lo = smem_u32(sW) >> 4;
       uint32_t it = 0;
       for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++it) {
         const uint32_t a = it & 1, aph = (it >> 1) & 1;
@@ -288,17 +303,18 @@ __global__ void __launch_bounds__(192, 1) conv_halo_kernel(const __grid_constant
         const int s = it % stages;
         mbar_wait(&full_bar[s], (it / stages) & 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + a * (uint32_t)g.Cout;
-        const uint32_t h_addr = smem_u32(sH + s * hsub), w_addr = smem_u32(sW);
-        uint32_t first = 1;
-        for (int t = 0; t < g.ntaps; ++t) {
-          const uint32_t a_addr = h_addr + (uint32_t)((g.dh[t] + 1) * pitch + (g.dw[t] + 1)) * RB;
-          const uint32_t b_addr = w_addr + (uint32_t)g.widx[t] * wsub;
+        const uint32_t h_lo = smem_u32(sH + s * hsub) >> 4;
+        for (int r = 0; r < TH; ++r) {
+          const uint32_t d_tmem = tmem_base + a * acc_cols + (uint32_t)(r * g.Cout);
+          const uint32_t hr = h_lo + (uint32_t)r * row_step;
 #pragma unroll
-          for (int j = 0; j < RB / 32; ++j) {
-            umma_bf16(d_tmem, make_smem_desc(a_addr + j * 32, 16, 8 * RB, RB), make_smem_desc(b_addr + j * 32, 16, 8 * RB, RB), idesc,
-                      first ? 0u : 1u);
-            first = 0;
+          for (int t = 0; t < 9; ++t) {
+            if (t < g.ntaps) {
+#pragma unroll
+              for (int j = 0; j < RB / 32; ++j)
+                umma_bf16(d_tmem, d_hi | (uint64_t)(hr + ta[t] + 2 * j), d_hi | (uint64_t)(w_lo + tb[t] + 2 * j), idesc,
+                          (t > 0 || j > 0) ? 1u : 0u);
+            }
           }
         }
         umma_commit(&empty_bar[s]);
@@ -307,49 +323,52 @@ __global__ void __launch_bounds__(192, 1) conv_halo_kernel(const __grid_constant
     }
   } else {
     uint32_t it = 0;
-    const int r = warp * 32 + lane;  // pixel inside the row tile (TH == 1)
+    const int px = warp * 32 + lane;  // pixel inside an output row of the tile
     for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++it) {
       const uint32_t a = it & 1, aph = (it >> 1) & 1;
       const int tw = tile % g.tiles_w;
       const int th = (tile / g.tiles_w) % g.tiles_h;
       const int n = tile / (g.tiles_w * g.tiles_h);
-      const int gw = tw * g.TW + r;
-      const bool ok = r < g.TW && gw < g.GW;
-      bf16* dst = g.y + (((long long)n * g.OH + th) * g.OW + gw) * g.Cout;
+      const int gw = tw * g.TW + px;
       mbar_wait(&tfull_bar[a], aph);
       tc_fence_after();
-      const uint32_t t_addr = tmem_base + a * (uint32_t)g.Cout + ((uint32_t)(warp * 32) << 16);
-      for (int c0 = 0; c0 < g.Cout; c0 += 16) {
-        uint32_t v[16];
-        tmem_ld16(t_addr + c0, v);
-        tmem_ld_wait();
-        if (ok) {
-          float f[16];
+      for (int r = 0; r < TH; ++r) {
+        const int gh = th * TH + r;
+        const bool ok = px < g.TW && gw < g.GW && gh < g.GH;
+        bf16* dst = g.y + (((long long)n * g.OH + gh) * g.OW + gw) * g.Cout;
+        const uint32_t t_addr = tmem_base + a * acc_cols + (uint32_t)(r * g.Cout) + ((uint32_t)(warp * 32) << 16);
+        for (int c0 = 0; c0 < g.Cout; c0 += 16) {
+          uint32_t v[16];
+          tmem_ld16(t_addr + c0, v);
+          tmem_ld_wait();
+          if (ok) {
+            float f[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            f[j] = __uint_as_float(v[j]);
-            if (g.bias) f[j] += __ldg(g.bias + c0 + j);
-            if (g.relu) f[j] = fmaxf(f[j], 0.f);
-          }
-          if (g.mask) {  // fused ReLU / dropout backward of the layer that produced this conv's forward input
-            const uint4 m0 = reinterpret_cast<const uint4*>(g.mask + (dst - g.y) + c0)[0];
-            const uint4 m1 = reinterpret_cast<const uint4*>(g.mask + (dst - g.y) + c0)[1];
-            const __nv_bfloat162* mb0 = reinterpret_cast<const __nv_bfloat162*>(&m0);
-            const __nv_bfloat162* mb1 = reinterpret_cast<const __nv_bfloat162*>(&m1);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              f[2 * j] = __low2float(mb0[j]) > 0.f ? f[2 * j] * g.mask_scale : 0.f;
-              f[2 * j + 1] = __high2float(mb0[j]) > 0.f ? f[2 * j + 1] * g.mask_scale : 0.f;
-              f[8 + 2 * j] = __low2float(mb1[j]) > 0.f ? f[8 + 2 * j] * g.mask_scale : 0.f;
-              f[8 + 2 * j + 1] = __high2float(mb1[j]) > 0.f ? f[8 + 2 * j + 1] * g.mask_scale : 0.f;
+            for (int j = 0; j < 16; ++j) {
+              f[j] = __uint_as_float(v[j]);
+              if (g.bias) f[j] += __ldg(g.bias + c0 + j);
+              if (g.relu) f[j] = fmaxf(f[j], 0.f);
             }
+            if (g.mask) {  // fused ReLU / dropout backward of the layer that produced this conv's forward input
+              const uint4 m0 = reinterpret_cast<const uint4*>(g.mask + (dst - g.y) + c0)[0];
+              const uint4 m1 = reinterpret_cast<const uint4*>(g.mask + (dst - g.y) + c0)[1];
+              const __nv_bfloat162* mb0 = reinterpret_cast<const __nv_bfloat162*>(&m0);
+              const __nv_bfloat162* mb1 = reinterpret_cast<const __nv_bfloat162*>(&m1);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                f[2 * j] = __low2float(mb0[j]) > 0.f ? f[2 * j] * g.mask_scale : 0.f;
+                f[2 * j + 1] = __high2float(mb0[j]) > 0.f ? f[2 * j + 1] * g.mask_scale : 0.f;
+                f[8 + 2 * j] = __low2float(mb1[j]) > 0.f ? f[8 + 2 * j] * g.mask_scale : 0.f;
+                f[8 + 2 * j + 1] = __high2float(mb1[j]) > 0.f ? f[8 + 2 * j + 1] * g.mask_scale : 0.f;
+              }
+            }
+            uint4 o0, o1;
+            o0.x = pack_bf16(f[0], f[1]); o0.y = pack_bf16(f[2], f[3]); o0.z = pack_bf16(f[4], f[5]); o0.w = pack_bf16(f[6], f[7]);
+            o1.x = pack_bf16(f[8], f[9]); o1.y = pack_bf16(f[10], f[11]); o1.z = pack_bf16(f[12], f[13]); o1.w = pack_bf16(f[14], f[15]);
+            uint4* d4 = reinterpret_cast<uint4*>(dst + c0);
+            d4[0] = o0;
+            d4[1] = o1;
           }
-          uint4 o0, o1;
-          o0.x = pack_bf16(f[0], f[1]); o0.y = pack_bf16(f[2], f[3]); o0.z = pack_bf16(f[4], f[5]); o0.w = pack_bf16(f[6], f[7]);
-          o1.x = pack_bf16(f[8], f[9]); o1.y = pack_bf16(f[10], f[11]); o1.z = pack_bf16(f[12], f[13]); o1.w = pack_bf16(f[14], f[15]);
-          uint4* d4 = reinterpret_cast<uint4*>(dst + c0);
-          d4[0] = o0;
-          d4[1] = o1;
         }
       }
       tc_fence_before();
@@ -405,23 +424,30 @@ int run_taps(const void* x, int N, int XH, int XW, int Cin, const void* wpack, i
   if (halo_enabled() && a.ish == 1 && a.isw == 1 && a.ntaps == 9 && Cin <= 64 && a.osh == 1 && a.osw == 1) {
     const int TW = a.GW >= 128 ? 128 : a.GW;
     const int pitch = TW + 2;
-    int rows = 3 * pitch;
-    if (rows < 2 * pitch + 2 + 128) rows = 2 * pitch + 2 + 128;
-    const int hsub = (rows * rb + 1023) / 1024 * 1024;
     const int wsub = (Cout * rb + 1023) / 1024 * 1024;
-    int stages = (225 * 1024 - 1024 - 512 - 9 * wsub) / hsub;
-    if (stages > 4) stages = 4;
-    if (stages >= 2) {
+    // TH output rows per tile: fewer TMA rows per output pixel ((TH+2)/TH instead of 3) and fewer barrier round trips;
+    // bounded by TMEM (2 buffers x TH x Cout columns <= 512) and by shared memory (>= 2 halo stages next to the weights)
+    int TH = 4, hsub = 0, stages = 0;
+    for (; TH >= 1; TH >>= 1) {
+      if (2 * TH * Cout > 512 || (TH > 1 && a.GH < TH)) continue;
+      int rows = (TH + 2) * pitch;
+      if (rows < (TH + 1) * pitch + 2 + 128) rows = (TH + 1) * pitch + 2 + 128;
+      hsub = (rows * rb + 1023) / 1024 * 1024;
+      stages = (225 * 1024 - 1024 - 512 - 9 * wsub) / hsub;
+      if (stages > 4) stages = 4;
+      if (stages >= 2) break;
+    }
+    if (TH >= 1 && stages >= 2) {
       ConvTcArgs h = a;
-      h.TH = 1; h.TW = TW;
+      h.TH = TH; h.TW = TW;
       h.tiles_w = (a.GW + TW - 1) / TW;
-      h.tiles_h = a.GH;
+      h.tiles_h = (a.GH + TH - 1) / TH;
       h.num_tiles = a.N * h.tiles_h * h.tiles_w;
       h.Cin = Cin; h.Cout = Cout;
       CUtensorMap tmX, tmW;
       unsigned long long dims[4] = {(unsigned long long)Cin, (unsigned long long)XW, (unsigned long long)XH, (unsigned long long)N};
       unsigned long long strides[3] = {(unsigned long long)Cin * 2, (unsigned long long)XW * Cin * 2, (unsigned long long)XH * XW * Cin * 2};
-      unsigned int box[4] = {(unsigned)Cin, (unsigned)pitch, 3u, 1u};
+      unsigned int box[4] = {(unsigned)Cin, (unsigned)pitch, (unsigned)(TH + 2), 1u};
       int rc = omr_make_tensor_map(&tmX, 2, x, 4, dims, strides, box, nullptr, rb);
       if (rc) return rc;
       unsigned long long wd[2] = {(unsigned long long)9 * Cin, (unsigned long long)Cout};

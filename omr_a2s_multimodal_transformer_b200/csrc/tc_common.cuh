@@ -90,8 +90,9 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate));  // no "memory" clobber: operands live in shared memory
+                                                              // written by the async proxy; ordering vs. the barriers is
+                                                              // kept by their own volatile asm + clobbers
 }
 // mbarrier arrives when all previously issued tcgen05.mma of this thread have completed
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {

@@ -115,24 +115,7 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant_
     // leading byte offset = one row), otherwise one tap (N = Ci).
     const bool merge = g.halo && g.chunks_b == 1;
     const int ngroup = merge ? ntap / 3 : ntap;
-    const int nj = g.KP / 16;
-    for (int idx = lane; idx < ngroup * nj + nj; idx += 32) {
-      if (idx < nj) {
-        s_aoff[idx] = (uint32_t)(idx * 16 * g.rba) >> 4;
-      } else {
-        const int e = idx - nj, m = e / nj, j = e - m * nj;
-        const int tap = tap0 + (merge ? 3 * m : m), kh = tap / 3, kw = tap - kh * 3;
-        uint32_t off;
-        if (g.halo) {
-          const int pr = (j * 16) / g.TW, pc = (j * 16) - pr * g.TW;
-          off = (uint32_t)((pr + kh) * g.pitch + pc + kw) * g.rbb;
-        } else {
-          off = (uint32_t)(m * g.chunks_b * b_sub + j * 16 * g.rbb);
-        }
-        s_boff[e] = off >> 4;
-      }
-    }
-    __syncwarp();
+    const int nj = g.KP / 16;  // <= 8
     if (lane == 0) {
       const uint32_t nB = merge ? 3 * g.Ci : g.Ci;
       const uint32_t idesc = make_idesc_bf16(128, nB, 1, 1);
@@ -140,6 +123,24 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant_
       const uint32_t lbo_b = merge ? (uint32_t)g.rbb : (g.chunks_b > 1 ? (uint32_t)b_sub : 0u);
       const uint64_t a_hi = make_smem_desc(0, lbo_a, 8 * g.rba, g.rba);  // everything but the start address
       const uint64_t b_hi = make_smem_desc(0, lbo_b, 8 * g.rbb, g.rbb);
+      // start-address offsets (16-byte units) kept in registers: A per k16 step, B = per-step part + per-group part
+      const uint32_t a_step = (uint32_t)(16 * g.rba) >> 4;
+      uint32_t jb[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (g.halo) {
+          const int pr = (j * 16) / g.TW, pc = (j * 16) - pr * g.TW;
+          jb[j] = (uint32_t)((pr * g.pitch + pc) * g.rbb) >> 4;
+        } else {
+          jb[j] = (uint32_t)(j * 16 * g.rbb) >> 4;
+        }
+      }
+      uint32_t gb[9];
+#pragma unroll
+      for (int m = 0; m < 9; ++m) {
+        const int tap = tap0 + (merge ? 3 * m : m), kh = tap / 3, kw = tap - kh * 3;
+        gb[m] = g.halo ? (uint32_t)((kh * g.pitch + kw) * g.rbb) >> 4 : (uint32_t)(m * g.chunks_b * b_sub) >> 4;
+      }
       for (int i = 0; i < ntiles; ++i) {
         const int s = i % g.stages;
         const uint32_t ph = (i / g.stages) & 1;
@@ -148,11 +149,15 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant_
         const uint32_t a_lo = smem_u32(smem + s * g.stage_bytes) >> 4;
         const uint32_t b_lo = a_lo + ((uint32_t)a_bytes >> 4);
         const uint32_t acc0 = i > 0 ? 1u : 0u;
-        for (int m = 0; m < ngroup; ++m) {
-          const uint32_t d = tmem_base + (uint32_t)m * nB;
-          const uint32_t* bo = s_boff + m * nj;
-          for (int j = 0; j < nj; ++j)
-            umma_bf16(d, a_hi | (uint64_t)(a_lo + s_aoff[j]), b_hi | (uint64_t)(b_lo + bo[j]), idesc, j > 0 ? 1u : acc0);
+#pragma unroll
+        for (int m = 0; m < 9; ++m) {
+          if (m < ngroup) {
+            const uint32_t d = tmem_base + (uint32_t)m * nB;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              if (j < nj)
+                umma_bf16(d, a_hi | (uint64_t)(a_lo + j * a_step), b_hi | (uint64_t)(b_lo + gb[m] + jb[j]), idesc, j > 0 ? 1u : acc0);
+          }
         }
         umma_commit(&empty_bar[s]);
       }
