@@ -190,6 +190,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline sample")
     ap.add_argument("--decode-steps", type=int, default=MAX_LEN)
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--no-library", action="store_true", help="skip the stock-PyTorch (cuDNN/cuBLAS/SDPA) GPU baseline leg")
     ap.add_argument("--no-graph", action="store_true", help="drive the step eagerly from Python instead of replaying CUDA graphs")
     args = ap.parse_args()
     from oracle import synth  # vocabulary loader + synthetic weights only (test infrastructure, not on the timed path)
@@ -339,6 +340,41 @@ def main():
                   "hbm_roofline_tokens_per_s_per_gpu": pk["hbm"] * 1e9 / 24.7e6}
         model.train()
 
+    library = None
+    graphed = stepper is not None
+    if rank == 0 and world == 1 and not args.no_library:
+        # "library kernels to beat": the same architecture from stock torch.nn modules (oracle/torch_twin.py), bf16
+        # autocast, same batch, forward + backward + fused torch Adam, on this GPU
+        try:
+            from oracle.torch_twin import TwinMultimodal
+
+            graphed = stepper is not None
+            stepper = None  # release the captured graphs' memory pool
+            torch.cuda.empty_cache()
+            twin = TwinMultimodal(len(w2i), MAX_LEN, IMG_HW, AUD_HW).to(dev).train()
+            topt = torch.optim.Adam(twin.parameters(), lr=1e-4, fused=True)
+            xi, xli, xa, xla, y_in, y_out = resident
+
+            def tstep():
+                topt.zero_grad(set_to_none=True)
+                with torch.autocast("cuda", dtype=torch.bfloat16):
+                    logits = twin(xi, xli, xa, xla, y_in)
+                loss = torch.nn.functional.cross_entropy(logits.float(), y_out, ignore_index=0)
+                loss.backward()
+                topt.step()
+
+            for _ in range(3):
+                tstep()
+            ms_lib = timed(tstep, args.steps)
+            library = {"value": b * args.steps / (ms_lib / 1e3), "unit": UNIT, "ms_per_step": ms_lib / args.steps,
+                       "what": "stock torch.nn twin of the reference (cuDNN conv / InstanceNorm, nn.TransformerDecoder SDPA, cuBLAS, "
+                               "CrossEntropyLoss, fused Adam), bf16 autocast, same batch on this GPU, eager",
+                       "torch": torch.__version__}
+            del twin, topt
+            torch.cuda.empty_cache()
+        except Exception as e:  # a reported baseline must never take the benchmark down
+            library = {"unavailable": f"{type(e).__name__}: {e}"[:300]}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cstep = cpu_reference_step_fn(w2i, args.cpu_batch)
@@ -363,7 +399,7 @@ def main():
                        "l2": "per-step working set (activations, several GB) is far larger than the 126 MB L2; no flush needed"},
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches),
-            "step_driver": "cuda-graph replay (2 captured variants, device-side dropout seeds)" if stepper is not None else "eager python",
+            "step_driver": "cuda-graph replay (2 captured variants, device-side dropout seeds)" if graphed else "eager python",
             "host_issue_ms_per_step": host_issue_ms,
             "clocks": clocks,
             "model_tflops_per_gpu": flops_step / (ms / args.steps * 1e-3) / 1e12,
@@ -371,6 +407,7 @@ def main():
             "roofline": roof,
             "breakdown_ms": breakdown,
             "decode": decode,
+            "library_baseline": library,
             "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)
