@@ -58,6 +58,7 @@ __device__ __forceinline__ void kv_tile_range(const AttnTcArgs& a, int q0, int& 
 }
 
 __device__ __forceinline__ void softmax_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void softmax_bar2() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 __global__ void __launch_bounds__(192, 2) attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
                                                              const __grid_constant__ CUtensorMap tmK,
@@ -359,7 +360,7 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-__global__ void __launch_bounds__(192, 1) attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
+__global__ void __launch_bounds__(320, 1) attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
                                                              const __grid_constant__ CUtensorMap tmK,
                                                              const __grid_constant__ CUtensorMap tmV,
                                                              const __grid_constant__ CUtensorMap tmDO, AttnBwdArgs g) {
@@ -389,7 +390,7 @@ __global__ void __launch_bounds__(192, 1) attn_bwd_tc_kernel(const __grid_consta
   q_tile_range(a, j0, qt0, qt1);
   const int ntiles = qt1 - qt0;
 
-  if (warp == 4 && lane == 0) {
+  if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
@@ -400,11 +401,11 @@ __global__ void __launch_bounds__(192, 1) attn_bwd_tc_kernel(const __grid_consta
       mbar_init(&qd_empty[s], 1);
     }
     mbar_init(sdp_full, 1);
-    mbar_init(pds_full, 4);
+    mbar_init(pds_full, 8);
     mbar_init(mma2_done, 1);
     fence_barrier_init();
   }
-  if (warp == 5) tmem_alloc(tmem_slot, 512);
+  if (warp == 9) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -412,7 +413,7 @@ __global__ void __launch_bounds__(192, 1) attn_bwd_tc_kernel(const __grid_consta
   const uint32_t tmem_ST = tmem_base, tmem_DPT = tmem_base + 128, tmem_DV = tmem_base + 256, tmem_DK = tmem_base + 320,
                  tmem_DQ = tmem_base + 384;
 
-  if (warp == 4) {
+  if (warp == 8) {
     if (lane == 0 && ntiles > 0) {
       mbar_expect_tx(kv_full, 2 * TILE);
       tma_load_3d(sK, &tmK, kv_full, h * HD, j0, b);
@@ -425,7 +426,7 @@ __global__ void __launch_bounds__(192, 1) attn_bwd_tc_kernel(const __grid_consta
         tma_load_3d(sDO + s * TILE, &tmDO, &qd_full[s], h * HD, (qt0 + i) * BQ, b);
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     if (lane == 0 && ntiles > 0) {
       constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
       constexpr uint32_t idesc_kn = make_idesc_bf16(128, 64, 0, 1);  // A K-major (P^T / dS^T), B MN-major
@@ -465,11 +466,14 @@ __global__ void __launch_bounds__(192, 1) attn_bwd_tc_kernel(const __grid_consta
       }
     }
   } else {
-    // ---- thread = key row (S^T, dP^T, dV, dK accumulators) and = query row for the dQ accumulator ----
-    const int r = warp * 32 + lane;
+    // ---- 8 warps: thread = (key row r, column half hf) of the S^T / dP^T / dV / dK accumulators, and (query row r,
+    // column half) of the dQ accumulator.  Warps w and w+4 share TMEM lanes 32(w&3)..+31 and split the columns, so the
+    // exp/convert/store work of a tile is spread over twice the issue slots of a 4-warp epilogue. ----
+    const int r = (warp & 3) * 32 + lane;
+    const int hf = warp >> 2;
     const int j = j0 + r;
     const int off = a.Tk - a.Tq;
-    const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
+    const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
     const float bias = (a.key_bias && j < a.Tk) ? a.key_bias[(long long)b * a.Tk + j] * LOG2E : 0.f;
     // queries that can see key j: t in [t_lo, t_hi]
     int t_lo = 0, t_hi = a.Tq - 1;
@@ -483,8 +487,8 @@ __global__ void __launch_bounds__(192, 1) attn_bwd_tc_kernel(const __grid_consta
     auto dq_epilogue = [&](int q_tile) {
       const int t = q_tile * BQ + r;
       float* dst = g.dq_acc + (stat_base + t) * HD;
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
+      {
+        const int c = hf;
         uint32_t v[32];
         tmem_ld32(tmem_DQ + lane_addr + c * 32, v);
         tmem_ld_wait();
@@ -499,13 +503,13 @@ __global__ void __launch_bounds__(192, 1) attn_bwd_tc_kernel(const __grid_consta
 
     for (int i = 0; i < ntiles; ++i) {
       const int q0 = (qt0 + i) * BQ;
-      softmax_bar();  // readers of the previous tile's statistics are done
-      {
+      softmax_bar2();  // readers of the previous tile's statistics are done
+      if (hf == 0) {
         const int t = q0 + r;
         sLse[r] = t < a.Tq ? a.lse[stat_base + t] * LOG2E : 0.f;
         sDelta[r] = t < a.Tq ? g.delta[stat_base + t] : 0.f;
       }
-      softmax_bar();
+      softmax_bar2();
       mbar_wait(sdp_full, i & 1);
       tc_fence_after();
       if (i > 0) {
@@ -514,7 +518,7 @@ __global__ void __launch_bounds__(192, 1) attn_bwd_tc_kernel(const __grid_consta
         dq_epilogue(qt0 + i - 1);
       }
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 2 * hf; c < 2 * hf + 2; ++c) {
         uint32_t sv[32], dv[32];
         tmem_ld32(tmem_ST + lane_addr + c * 32, sv);
         tmem_ld32(tmem_DPT + lane_addr + c * 32, dv);
@@ -557,7 +561,7 @@ __global__ void __launch_bounds__(192, 1) attn_bwd_tc_kernel(const __grid_consta
       bf16* dvp = g.dv + (long long)b * g.dv_bs + (long long)j * g.dv_rs + h * HD;
       if (ntiles == 0) {
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
+        for (int u = 4 * hf; u < 4 * hf + 4; ++u) {
           reinterpret_cast<uint4*>(dkp)[u] = make_uint4(0, 0, 0, 0);
           reinterpret_cast<uint4*>(dvp)[u] = make_uint4(0, 0, 0, 0);
         }
@@ -569,8 +573,8 @@ __global__ void __launch_bounds__(192, 1) attn_bwd_tc_kernel(const __grid_consta
         const float mul = which == 0 ? g.scale : 1.f;
         bf16* dst = which == 0 ? g.dk + (long long)b * g.dk_bs + (long long)j * g.dk_rs + h * HD
                                : g.dv + (long long)b * g.dv_bs + (long long)j * g.dv_rs + h * HD;
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
+        {
+          const int c = hf;
           uint32_t v[32];
           tmem_ld32((which == 0 ? tmem_DK : tmem_DV) + lane_addr + c * 32, v);
           tmem_ld_wait();
@@ -591,7 +595,7 @@ __global__ void __launch_bounds__(192, 1) attn_bwd_tc_kernel(const __grid_consta
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) {
+  if (warp == 9) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
@@ -675,7 +679,7 @@ int omr_attn_bwd_tc(const void* q, long long q_bs, long long q_rs, const void* k
     configured = true;
   }
   dim3 grid((unsigned)((Tk + BKV - 1) / BKV), (unsigned)H, (unsigned)B);
-  attn_bwd_tc_kernel<<<grid, 192, BWD_SMEM, st>>>(tmQ, tmK, tmV, tmDO, g);
+  attn_bwd_tc_kernel<<<grid, 320, BWD_SMEM, st>>>(tmQ, tmK, tmV, tmDO, g);
   OMR_LAUNCHED();
   attn_dq_finalize_kernel<<<(unsigned)((rows * 8 + 255) / 256), 256, 0, st>>>(dq_acc, (bf16*)dq, dq_bs, dq_rs, B, H, Tq, scale);
   OMR_LAUNCHED();

@@ -40,7 +40,7 @@ template <int BN>
 constexpr int epilogue_bytes(int out_esz) { return 128 * BN * out_esz; }  // the staging rows alias the ring
 
 template <int BN, int A_MN, int B_MN, typename TO>
-__global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+__global__ void __launch_bounds__(320) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                      const __grid_constant__ CUtensorMap tmB, GemmTcArgs g) {
   const int STAGES = g.stages;
   constexpr int B_TILE_BYTES = BN * BK * 2;
@@ -61,7 +61,7 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
   if (kb_end > kb_total) kb_end = kb_total;
   const int nkb = kb_end - kb_begin;  // >= 1 by construction of the grid
 
-  if (warp == 4 && lane == 0) {
+  if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < STAGES; ++s) {
@@ -71,13 +71,13 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
     mbar_init(accum_bar, 1);
     fence_barrier_init();
   }
-  if (warp == 5) tmem_alloc(tmem_slot, TMEM_COLS);
+  if (warp == 9) tmem_alloc(tmem_slot, TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 4) {
+  if (warp == 8) {
     if (lane == 0) {
       for (int i = 0; i < nkb; ++i) {
         const int s = i % STAGES;
@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
         }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_bf16(BM, BN, A_MN, B_MN);
       for (int i = 0; i < nkb; ++i) {
@@ -124,31 +124,35 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
       umma_commit(accum_bar);  // accumulator complete
     }
   } else {
-    // ---- epilogue: warp w owns TMEM lanes / tile rows 32w .. 32w+31 ----
+    // ---- epilogue: 8 warps; warp w owns TMEM lanes / tile rows 32(w&3) .. +31 and column half w>>2 (BN >= 64) ----
     // phase 1: thread = row: TMEM -> registers -> bias/ReLU -> output type -> this warp's staging rows in the
     // (now idle) pipeline buffers, 16-byte units XOR-swizzled by the row so that neither phase bank-conflicts;
     // phase 2: consecutive lanes write consecutive 16-byte units of a row -> fully coalesced global stores.
     mbar_wait(accum_bar, 0);
     tc_fence_after();
-    const int row = m0 + warp * 32 + lane;
+    constexpr int HALVES = BN >= 64 ? 2 : 1;
+    constexpr int HC = BN / HALVES;  // columns per warp
+    const int quarter = warp & 3, half = warp >> 2;
+    const int row = m0 + quarter * 32 + lane;
     const bool row_ok = row < g.M;
     const float brow = (g.bias_mode == 2 && row_ok) ? g.bias[row] : 0.f;
     const bool vec_ok = ((g.ldc * sizeof(TO)) % 16 == 0) && ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0);
     constexpr int EPU = 16 / (int)sizeof(TO);      // elements per 16-byte unit
-    constexpr int U = BN / EPU;                    // units per staged row
+    constexpr int U = HC / EPU;                    // units per staged row (this warp's column half)
     constexpr int UMASK = U >= 8 ? 7 : (U - 1);
-    uint4* stage = reinterpret_cast<uint4*>(smem) + warp * 32 * U;
+    uint4* stage = reinterpret_cast<uint4*>(smem) + (half * 4 + quarter) * 32 * U;
+    const int nh0 = n0 + half * HC;  // first global column of this warp's half
     const bool staged = vec_ok && g.acc_mode != 2;
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      if (n0 + c0 >= g.N) break;  // warp-uniform
+    for (int c0 = 0; c0 < HC; c0 += 32) {
+      if (half >= HALVES || nh0 + c0 >= g.N) break;  // warp-uniform
       uint32_t r[32];
-      tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, r);
+      tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(half * HC + c0), r);
       tmem_ld_wait();
       float v[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + brow;
-      const int ncol = n0 + c0;
+      const int ncol = nh0 + c0;
       const bool full = ncol + 32 <= g.N;
       if (g.bias_mode == 1) {
 #pragma unroll
@@ -207,18 +211,19 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
         }
       }
     }
-    if (staged) {
+    if (staged && half < HALVES) {
       __syncwarp();
-      int ncols = g.N - n0;
-      if (ncols > BN) ncols = BN;
+      int ncols = g.N - nh0;
+      if (ncols > HC) ncols = HC;
+      if (ncols < 0) ncols = 0;
       const int nunits = (ncols + EPU - 1) / EPU;  // units that hold at least one valid column
 #pragma unroll 1
       for (int idx = lane; idx < 32 * U; idx += 32) {
         const int rr = idx / U, u = idx - rr * U;
-        const int grow = m0 + warp * 32 + rr;
+        const int grow = m0 + quarter * 32 + rr;
         if (grow >= g.M || u >= nunits) continue;
         uint4 val = stage[rr * U + (u ^ (rr & UMASK))];
-        TO* dst = reinterpret_cast<TO*>(g.C) + (long long)grow * g.ldc + n0 + u * EPU;
+        TO* dst = reinterpret_cast<TO*>(g.C) + (long long)grow * g.ldc + nh0 + u * EPU;
         if ((u + 1) * EPU <= ncols) {
           if (g.acc_mode == 1) {
             const uint4 old = *reinterpret_cast<const uint4*>(dst);
@@ -249,7 +254,7 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) {
+  if (warp == 9) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
   }
@@ -266,7 +271,7 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmTcArgs& g, 
   int smem = smem_bytes<BN>(g.stages);
   const int need = epilogue_bytes<BN>((int)sizeof(TO)) + 1024 + 256;
   if (smem < need) smem = need;
-  kern<<<grid, 192, smem, st>>>(tmA, tmB, g);
+  kern<<<grid, 320, smem, st>>>(tmA, tmB, g);
   OMR_LAUNCHED();
   return OMR_OK;
 }
