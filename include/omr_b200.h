@@ -247,7 +247,7 @@ int omr_kv_append(int dt, const void* src, long long src_rs, void* cache, int B,
  * with j_lo = max(0, Tk-1-window) when window > 0 (decoder.py:191-217), else 0.
  * q element (b,h,d) at q[b*q_bs + h*hd + d]; K element (b,j,h,d) at k[b*k_bs + j*k_rs + h*hd + d].
  * pos_dev != NULL: the live key count is *pos_dev + 1 and Tk only bounds it (graph replay).
- * ws: fp32 scratch, at least B*H*nsplit*(hd+2) floats with nsplit <= max(1, ceil(592/(B*H))). */
+ * ws: fp32 scratch, at least B*H*nsplit*(hd+2) floats with nsplit <= max(1, ceil(1184/(B*H))). */
 int omr_attn_decode(int dt, const void* q, long long q_bs, const void* k, long long k_bs, long long k_rs,
                     const void* v, long long v_bs, long long v_rs, void* o, long long o_bs, const float* key_bias,
                     long long kb_bs, float* ws, long long ws_floats, int B, int H, int Tk, int hd, float scale,

@@ -232,7 +232,7 @@ extern "C" int omr_attn_decode(int dt, const void* q, long long q_bs, const void
   OMR_REQUIRE(((q_bs | k_bs | k_rs | v_bs | v_rs | o_bs) & 3) == 0, "omr_attn_decode: strides must be multiples of 4");
   if (B <= 0 || H <= 0 || Tk <= 0) return OMR_OK;
   long long bh = (long long)B * H;
-  int nsplit = (int)cdiv(148LL * 4, bh);
+  int nsplit = (int)cdiv(148LL * 8, bh);  // ~8 resident CTAs per SM: the KV stream is latency-bound, not compute-bound
   int max_split = (int)cdiv(Tk, 128);
   if (nsplit > max_split) nsplit = max_split;
   if (nsplit < 1) nsplit = 1;

@@ -398,7 +398,7 @@ def kv_append(src_ptr, src_rs, cache, pos, dtype, pos_dev=None):
 
 
 def attn_decode_ws_floats(b, h, hd=64):
-    nsplit = max(1, -(-592 // (b * h)))
+    nsplit = max(1, -(-1184 // (b * h)))
     return b * h * nsplit * (hd + 2)
 
 
