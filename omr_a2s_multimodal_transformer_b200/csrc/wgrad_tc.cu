@@ -118,7 +118,9 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant_
     const int nj = g.KP / 16;  // <= 8
     if (lane == 0) {
       const uint32_t nB = merge ? 3 * g.Ci : g.Ci;
-      const uint32_t idesc = make_idesc_bf16(128, nB, 1, 1);
+      // Co <= 64 -> M = 64: the MN-major A fetch costs one shared-memory wavefront per (k row, M chunk), and with 16/32
+      // channel rows most chunks of an M = 128 tile would be aliases of the real one; M = 64 halves that traffic
+      const uint32_t idesc = make_idesc_bf16(g.Co > 64 ? 128 : 64, nB, 1, 1);
       const uint32_t lbo_a = g.chunks_a > 1 ? (uint32_t)a_sub : 0u;  // Co <= 64: every 64-wide M chunk aliases the real one
       const uint32_t lbo_b = merge ? (uint32_t)g.rbb : (g.chunks_b > 1 ? (uint32_t)b_sub : 0u);
       const uint64_t a_hi = make_smem_desc(0, lbo_a, 8 * g.rba, g.rba);  // everything but the start address
@@ -167,8 +169,10 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant_
     // ---- epilogue: thread = output channel co; add this CTA's partial sums into dW[co, ci, kh, kw] ----
     mbar_wait(accum_bar, 0);
     tc_fence_after();
-    const int co = warp * 32 + lane;
-    const bool ok = co < g.Co;
+    // accumulator rows: M = 128 -> lane = row; M = 64 -> row r lives in lane (r % 16) + 32 * (r / 16) (16 per warp)
+    const bool m64 = g.Co <= 64;
+    const int co = m64 ? warp * 16 + lane : warp * 32 + lane;
+    const bool ok = co < g.Co && (!m64 || lane < 16);
     for (int t = 0; t < ntap; ++t) {
       const int tap = tap0 + t;
       for (int c0 = 0; c0 < g.Ci; c0 += 16) {
