@@ -51,6 +51,7 @@ _SIGS = {
     "omr_argmax_step": "ipqiipppqqppiipp",
     "omr_kv_append": "ipqpiiiipp",
     "omr_attn_decode": "ipqpqqpqqpqpqpqiiiifipp",
+    "omr_decode_persistent": "ipippppiiiiiiiipppppipqqpqfpqpp",
 }
 _CT = {"i": c_int, "q": c_longlong, "p": c_void_p, "f": c_float, "d": c_double}
 
@@ -72,6 +73,8 @@ def load() -> ctypes.CDLL:
     lib.omr_abi_version.restype = c_int
     lib.omr_launch_count.restype = c_longlong
     lib.omr_tc_call_count.restype = c_longlong
+    lib.omr_decode_persistent_scratch_floats.restype = c_longlong
+    lib.omr_decode_persistent_scratch_floats.argtypes = [c_int, c_int, c_int, c_int]
     lib.omr_tensor_core_path_enabled.restype = c_int
     lib.omr_set_tensor_core_path.argtypes = [c_int]
     for name, sig in _SIGS.items():
@@ -84,7 +87,7 @@ def load() -> ctypes.CDLL:
 
 def exported_symbols():
     return ["omr_abi_version", "omr_last_error", "omr_launch_count", "omr_tc_call_count", "omr_tensor_core_path_enabled",
-            "omr_set_tensor_core_path"] + list(_SIGS)
+            "omr_set_tensor_core_path", "omr_decode_persistent_scratch_floats"] + list(_SIGS)
 
 
 def check(rc: int, what: str) -> None:

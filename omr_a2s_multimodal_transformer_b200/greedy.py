@@ -15,13 +15,24 @@ and synchronises with the host at every token.  Here:
 """
 from __future__ import annotations
 
+import ctypes
+import os
 from typing import List, Optional, Tuple
 
 import torch
 
-from . import ops
+from . import _lib, ops
+from ._lib import ptr, stream_ptr
 from .decoder import Decoder
 from .params import resolve_dtype
+
+
+class _DecodeLayer(ctypes.Structure):
+    """mirror of omr_decode_layer (include/omr_b200.h)"""
+
+    _fields_ = [(n, ctypes.c_void_p) for n in (
+        "w_in", "b_in", "w_o", "b_o", "wc_q", "bc_q", "wc_o", "bc_o", "w1", "b1", "w2", "b2",
+        "g1", "be1", "g2", "be2", "g3", "be3", "self_kv", "cross_kv")]
 
 
 class BatchedGreedyDecoder:
@@ -76,6 +87,65 @@ class BatchedGreedyDecoder:
                         st["out_vals"], 0, step_dev=pos)
         ops.tick(pos)
 
+    def _persistent_ok(self, b: int) -> bool:
+        dec = self.dec
+        return (os.environ.get("OMR_DECODE_MODE", "persistent") != "graph" and b <= 64 and dec.d_model == 256
+                and dec.nhead == 4 and dec.ff_dim == 256)
+
+    def _decode_persistent(self, st, cross_kv, steps: int, stop_at_eos: bool, poll_every: int) -> int:
+        """the whole step loop as launches of ONE persistent cooperative kernel (csrc/decode_persistent.cu); the host
+        only polls the device-side ``finished`` flags every ``poll_every`` steps.  Returns the number of steps run."""
+        dec, dtype = self.dec, self.dtype
+        c = dec._wcache
+        b, d = st["B"], dec.d_model
+        dev = st["tok"].device
+        keep = []  # keeps sliced weight views alive until the launches are enqueued
+        recs = (_DecodeLayer * len(cross_kv))()
+        for li, L in enumerate(dec.transformer_decoder.layers):
+            sa, ca = L.self_attn, L.multihead_attn
+            wc_in = c.get(ca.in_proj_weight, "mat", dtype)
+            vals = dict(
+                w_in=c.get(sa.in_proj_weight, "mat", dtype), b_in=sa.in_proj_bias,
+                w_o=c.get(sa.out_proj.weight, "mat", dtype), b_o=sa.out_proj.bias,
+                wc_q=wc_in[:d], bc_q=ca.in_proj_bias[:d],
+                wc_o=c.get(ca.out_proj.weight, "mat", dtype), bc_o=ca.out_proj.bias,
+                w1=c.get(L.linear1.weight, "mat", dtype), b1=L.linear1.bias,
+                w2=c.get(L.linear2.weight, "mat", dtype), b2=L.linear2.bias,
+                g1=L.norm1.weight, be1=L.norm1.bias, g2=L.norm2.weight, be2=L.norm2.bias, g3=L.norm3.weight, be3=L.norm3.bias,
+                self_kv=st["self_kv"][li], cross_kv=cross_kv[li])
+            for k, t in vals.items():
+                setattr(recs[li], k, t.data_ptr())
+                keep.append(t)
+        table = torch.frombuffer(bytearray(bytes(recs)), dtype=torch.uint8).to(dev)
+        nfl = int(_lib.load().omr_decode_persistent_scratch_floats(b, dec.nhead, d, dec.output_size))
+        scratch = torch.empty(nfl, dtype=torch.float32, device=dev)
+        wout = c.get(dec.out_layer.weight, "mat", dtype)
+        table_emb = c.get(dec.embedding.weight, "mat", dtype)
+        mem_bias = st["mem_bias"]
+        s_len = cross_kv[0].shape[1]
+        tmax = st["self_kv"][0].shape[1]
+        timing = torch.zeros(16, dtype=torch.int64, device=dev) if os.environ.get("OMR_DECODE_TIMING") else None
+        done = 0
+        while done < steps:
+            n = min(poll_every if (stop_at_eos and poll_every > 0) else steps, steps - done)
+            _lib.call("omr_decode_persistent", _lib.dt_code(dtype), ptr(table), len(cross_kv), ptr(table_emb),
+                      ptr(dec.pos_1d.pe), ptr(wout), ptr(dec.out_layer.bias), b, dec.nhead, d, dec.output_size, s_len, tmax, n,
+                      dec.attn_window if dec.attn_window and dec.attn_window > 0 else 0, ptr(st["tok"]), ptr(st["val"]),
+                      ptr(st["finished"]), ptr(st["out_tokens"]), ptr(st["out_vals"]), st["out_tokens"].shape[1], ptr(st["pos"]),
+                      st["eos"], st["pad"], ptr(mem_bias), mem_bias.stride(0) if mem_bias is not None else 0,
+                      float(dec.transformer_decoder.layers[0].norm1.eps), ptr(scratch), nfl, ptr(timing), stream_ptr())
+            done += n
+            if stop_at_eos and done < steps and bool(st["finished"].all().item()):
+                break
+        del keep
+        if timing is not None:
+            names = ["embed", "qkv", "self_attn", "out_proj", "cross_q", "cross_attn", "cross_out", "ffn1", "ffn2", "classifier", "argmax"]
+            cyc = timing.cpu().tolist()
+            tot = sum(cyc) or 1
+            print("[decode timing, SM cycles per step on CTA 0] " + ", ".join(
+                f"{n} {c / max(done, 1):.0f} ({100 * c / tot:.0f}%)" for n, c in zip(names, cyc)) + f" | total {tot / max(done, 1):.0f}")
+        return done
+
     @torch.no_grad()
     def decode(self, memory: torch.Tensor, sos: int, eos: int, pad: int = 0, max_steps: Optional[int] = None,
                stop_at_eos: bool = True, use_graph: bool = True, poll_every: int = 64,
@@ -118,6 +188,13 @@ class BatchedGreedyDecoder:
             st["out_tokens"].fill_(int(pad))
             st["out_vals"].zero_()
 
+        if use_graph and self._persistent_ok(b):
+            done_steps = self._decode_persistent(st, cross_kv, steps, stop_at_eos, poll_every)
+            toks = st["out_tokens"][:, :done_steps]
+            vals = st["out_vals"][:, :done_steps]
+            is_eos = toks == int(eos) if stop_at_eos else torch.zeros_like(toks, dtype=torch.bool)
+            first = torch.where(is_eos.any(dim=1), is_eos.float().argmax(dim=1) + 1, torch.full((b,), done_steps, device=dev))
+            return toks, vals, first.to(torch.int64)
         graph = None
         if use_graph and steps > 2:
             # warm-up on a side stream (sets kernel attributes, fills the weight cache), then capture one step
