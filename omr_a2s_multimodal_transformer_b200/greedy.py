@@ -89,12 +89,12 @@ class BatchedGreedyDecoder:
 
     def _persistent_ok(self, b: int) -> bool:
         dec = self.dec
-        return (os.environ.get("OMR_DECODE_MODE", "persistent") != "graph" and b <= 64 and dec.d_model == 256
-                and dec.nhead == 4 and dec.ff_dim == 256)
+        return (os.environ.get("OMR_DECODE_MODE", "persistent") != "graph" and dec.d_model == 256 and dec.nhead == 4
+                and dec.ff_dim == 256)
 
     def _decode_persistent(self, st, cross_kv, steps: int, stop_at_eos: bool, poll_every: int) -> int:
-        """the whole step loop as launches of ONE persistent cooperative kernel (csrc/decode_persistent.cu); the host
-        only polls the device-side ``finished`` flags every ``poll_every`` steps.  Returns the number of steps run."""
+        """the whole step loop as ONE launch of the persistent kernel (csrc/decode_persistent.cu): a 4-CTA cluster per
+        sample runs all steps of that sample and stops at its own EOS -- no host polling.  Returns the step budget."""
         dec, dtype = self.dec, self.dtype
         c = dec._wcache
         b, d = st["B"], dec.d_model
@@ -125,18 +125,16 @@ class BatchedGreedyDecoder:
         s_len = cross_kv[0].shape[1]
         tmax = st["self_kv"][0].shape[1]
         timing = torch.zeros(16, dtype=torch.int64, device=dev) if os.environ.get("OMR_DECODE_TIMING") else None
-        done = 0
-        while done < steps:
-            n = min(poll_every if (stop_at_eos and poll_every > 0) else steps, steps - done)
-            _lib.call("omr_decode_persistent", _lib.dt_code(dtype), ptr(table), len(cross_kv), ptr(table_emb),
-                      ptr(dec.pos_1d.pe), ptr(wout), ptr(dec.out_layer.bias), b, dec.nhead, d, dec.output_size, s_len, tmax, n,
-                      dec.attn_window if dec.attn_window and dec.attn_window > 0 else 0, ptr(st["tok"]), ptr(st["val"]),
-                      ptr(st["finished"]), ptr(st["out_tokens"]), ptr(st["out_vals"]), st["out_tokens"].shape[1], ptr(st["pos"]),
-                      st["eos"], st["pad"], ptr(mem_bias), mem_bias.stride(0) if mem_bias is not None else 0,
-                      float(dec.transformer_decoder.layers[0].norm1.eps), ptr(scratch), nfl, ptr(timing), stream_ptr())
-            done += n
-            if stop_at_eos and done < steps and bool(st["finished"].all().item()):
-                break
+        _lib.call("omr_decode_persistent", _lib.dt_code(dtype), ptr(table), len(cross_kv), ptr(table_emb),
+                  ptr(dec.pos_1d.pe), ptr(wout), ptr(dec.out_layer.bias), b, dec.nhead, d, dec.output_size, s_len, tmax, steps,
+                  dec.attn_window if dec.attn_window and dec.attn_window > 0 else 0, ptr(st["tok"]), ptr(st["val"]),
+                  ptr(st["finished"]), ptr(st["out_tokens"]), ptr(st["out_vals"]), st["out_tokens"].shape[1], ptr(st["pos"]),
+                  st["eos"], st["pad"], ptr(mem_bias), mem_bias.stride(0) if mem_bias is not None else 0,
+                  float(dec.transformer_decoder.layers[0].norm1.eps), ptr(scratch), nfl, ptr(timing), stream_ptr())
+        done = steps
+        if stop_at_eos:  # trim the all-PAD tail (every sample stopped at its own EOS inside the kernel)
+            nz = (st["out_tokens"] != st["pad"]).any(dim=0).nonzero()
+            done = int(nz.max().item()) + 1 if nz.numel() else 1
         del keep
         if timing is not None:
             names = ["embed", "qkv", "self_attn", "out_proj", "cross_q", "cross_attn", "cross_out", "ffn1", "ffn2", "classifier", "argmax"]
