@@ -6,25 +6,43 @@
 // of 4 CTAs (4 x 512 threads on 4 neighbouring SMs; batch 32 -> 128 of the 148 SMs) that runs ALL decode steps of that
 // sample inside a single launch -- embedding + 1-D PE, 8 x (KV-cached self-attention, cross-attention over the
 // pre-projected encoder memory, FFN, three post-norm LayerNorms), vocabulary classifier, first-max argmax, EOS -- and
-// synchronises only with the hardware cluster barrier (barrier.cluster, ~0.2 us) between dependent phases: no grid-wide
-// barrier, no host round trip, no kernel launch per token.  A decode step is a weight / KV stream:
-//   * attention phases: CTA r of the cluster owns head r (4 heads): it streams that head's K/V rows (16-byte loads, 8
-//     keys in flight per thread, 64 key lanes x 8 dim chunks), softmax in shared memory, no split-K combine needed;
-//   * projection phases (GEMV: 256-vector x [N,256] weight): the N output columns are dealt to the 64 warps of the
-//     cluster, every lane holds 8 elements of the input vector, one 16-byte weight load per lane and column, shuffle
-//     reduction; LayerNorm of the previous block is recomputed by every warp on the fly (256 values);
-//   * vectors travel between the CTAs of a cluster through a small fp32 scratch in L2; barrier.cluster (release /
-//     acquire) orders them; the new K/V rows go straight into the in-HBM cache.
+// synchronises only with the hardware cluster barrier between dependent phases: no grid-wide barrier, no host round
+// trip, no kernel launch per token.  A decode step is a weight / KV stream:
+//   * WEIGHTS never wait on a dependency, so they are streamed ahead of the computation: thread 0 of every CTA keeps a
+//     145 KB shared-memory ring full with cp.async.bulk copies (8 slots of 32 weight rows = 16 KB bf16, plus their
+//     biases and the LayerNorm scale / shift the projection needs; completion on an mbarrier per slot; L2 evict-last)
+//     in the fixed order the phases consume them; CTA r owns a contiguous quarter of the output
+//     columns of every projection, warp w of it two columns of every slot (one 16-byte LDS per lane and column, shuffle
+//     reduction).  Slots are recycled at the barriers that already separate the phases.
+//   * VECTORS (residual stream, q, attention output, FFN hidden: 256 fp32 each) live replicated in the shared memory
+//     of all four CTAs; a producer lane writes its element into the four copies through distributed shared memory
+//     (st.shared::cluster), barrier.cluster (release / acquire) publishes them.  LayerNorm is recomputed by every warp
+//     from its local copy.  A projection phase touches no global memory on its critical path (the barrier's acquire
+//     invalidates L1, so every global read after it would be an L2 round trip): the layer table is copied to shared
+//     memory once, parameters arrive through the ring.
+//   * ATTENTION: CTA r owns head r; it streams that head's K then V rows straight from the in-HBM cache with 16-byte
+//     loads, double buffered in registers (8 keys in flight + 8 being consumed per thread, 64 key lanes x 8 dim
+//     chunks); the first V batch is already in flight while the softmax statistics are reduced.  New K/V rows go
+//     straight into the cache.
 // Numerics are those of the per-kernel path (fp32 accumulation; logits rounded to the storage type before the argmax).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "kernels.h"
+#include "tc_common.cuh"
 
 namespace {
 
+using tc::mbar_expect_tx;
+using tc::mbar_init;
+using tc::mbar_wait;
+using tc::smem_u32;
+
 constexpr int DP_D = 256, DP_HD = 64, DP_H = 4, DP_THREADS = 512, DP_WARPS = 16, DP_KL = DP_THREADS / 8;
 constexpr int DP_CL = 4;                      // CTAs per cluster = heads
-constexpr int DP_CW = DP_CL * DP_WARPS;       // warps per cluster
-constexpr int DP_SCR = 6 * DP_D + 16;         // fp32 scratch per sample: x, s, q, a, h (256 each), argmax candidates
+constexpr int DP_CH = 32;                     // weight rows (= output columns) per ring slot: two per warp
+constexpr int DP_LCH = 16;                    // ring slots per layer and CTA: 6 (q|k|v) + 5 x 2
+constexpr int DP_VEC = 5 * DP_D + 2 * DP_HD + 16;  // fp32 vectors x, s, q, a, h, the new k / v row of the head, argmax candidates
 
 template <typename T>
 struct LayerW {
@@ -48,8 +66,9 @@ struct DPArgs {
   long long eos, pad;
   const float* mem_bias; long long mem_bias_bs;
   float ln_eps, scale;
-  float* scratch;      // [B][DP_SCR]
   long long* timing;   // optional [16] cycle counters per phase kind (cluster 0, rank 0), NULL = off
+  int sc_floats;       // floats reserved for the attention scores
+  int pf_cross, pf_self;  // rows of the next attention's K/V stream that are prefetched into L2 one phase ahead
 };
 
 // 8 consecutive elements as raw registers (so that many independent 16-byte loads can be in flight per thread)
@@ -57,7 +76,15 @@ template <typename T> struct Raw8;
 template <> struct Raw8<bf16> {
   uint4 v;
   __device__ __forceinline__ void load(const bf16* p) { v = *reinterpret_cast<const uint4*>(p); }
+  // streaming global load: K/V rows are read once per step, keep them out of L1
+  __device__ __forceinline__ void load_stream(const bf16* p, uint64_t pol) {
+    asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(pol));
+  }
   __device__ __forceinline__ void zero() { v = make_uint4(0, 0, 0, 0); }
+  __device__ __forceinline__ void set(const float* p) {  // 8 fp32 values that are exactly representable
+    v = make_uint4(tc::pack_bf16(p[0], p[1]), tc::pack_bf16(p[2], p[3]), tc::pack_bf16(p[4], p[5]), tc::pack_bf16(p[6], p[7]));
+  }
   __device__ __forceinline__ void get(float (&f)[8]) const {
     const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
 #pragma unroll
@@ -67,15 +94,21 @@ template <> struct Raw8<bf16> {
 template <> struct Raw8<float> {
   float4 a, b;
   __device__ __forceinline__ void load(const float* p) { a = *reinterpret_cast<const float4*>(p); b = *reinterpret_cast<const float4*>(p + 4); }
+  __device__ __forceinline__ void load_stream(const float* p, uint64_t pol) {
+    asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+                 : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w) : "l"(p), "l"(pol));
+    asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+                 : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p + 4), "l"(pol));
+  }
   __device__ __forceinline__ void zero() { a = make_float4(0, 0, 0, 0); b = a; }
+  __device__ __forceinline__ void set(const float* p) { a = *reinterpret_cast<const float4*>(p); b = *reinterpret_cast<const float4*>(p + 4); }
   __device__ __forceinline__ void get(float (&f)[8]) const {
     f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
   }
 };
 
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 __device__ __forceinline__ unsigned cluster_rank() {
   unsigned r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -86,100 +119,278 @@ __device__ __forceinline__ unsigned cluster_id_x() {
   asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r));
   return r;
 }
+// store into the same shared-memory location of CTA `cta` of the cluster
+__device__ __forceinline__ void st_cluster(const float* local, float v, unsigned cta) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(local)), "r"(cta));
+  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(remote), "f"(v) : "memory");
+}
 
-// lane-distributed 256-vector: lane holds elements lane*8 .. lane*8+7.  Optional LayerNorm (every warp redundantly).
-__device__ __forceinline__ void load_vec(const float* __restrict__ src, float (&v)[8], const float* gamma, const float* beta, float eps) {
-  const int lane = threadIdx.x & 31;
-  const float4 a = __ldcg(reinterpret_cast<const float4*>(src + lane * 8));
-  const float4 b = __ldcg(reinterpret_cast<const float4*>(src + lane * 8 + 4));
-  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-  if (gamma) {
-    float sum = 0.f;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) sum += v[k];
-    const float mean = warp_sum(sum) * (1.f / DP_D);
-    float var = 0.f;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) { const float d = v[k] - mean; var = fmaf(d, d, var); }
-    const float rstd = rsqrtf(warp_sum(var) * (1.f / DP_D) + eps);
-#pragma unroll
-    for (int k = 0; k < 8; ++k) v[k] = (v[k] - mean) * rstd * gamma[lane * 8 + k] + beta[lane * 8 + k];
+// asynchronous store into CTA `cta`'s copy of a shared-memory word; the 4 bytes are accounted on that CTA's copy of
+// the mbarrier `bar` (complete_tx), whose phase completion makes them visible to the waiter: no fence, no cluster barrier
+__device__ __forceinline__ void st_async(const float* local, float v, unsigned cta, const uint64_t* bar) {
+  uint32_t ra, rb;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(local)), "r"(cta));
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rb) : "r"(smem_u32(bar)), "r"(cta));
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(ra), "r"(__float_as_uint(v)), "r"(rb)
+               : "memory");
+}
+
+// L2 prefetch of rows [r0, r1) of a [rows, 2D] K/V matrix, one phase ahead of the attention that streams them: 16 KB
+// pieces dealt round-robin to the CTAs of the cluster and to their threads (fire and forget: no registers, no barrier).
+// The projection phases in between use no HBM bandwidth, so the stream overlaps them.
+template <typename T>
+__device__ __forceinline__ void prefetch_rows(const T* base, int r0, int r1, int rank) {
+  constexpr int ROWS = 16384 / (2 * DP_D * (int)sizeof(T));  // rows per piece
+  const int i = r0 / ROWS + rank + DP_CL * (int)threadIdx.x;  // piece index
+  const int a = i * ROWS < r0 ? r0 : i * ROWS, b = (i + 1) * ROWS < r1 ? (i + 1) * ROWS : r1;
+  if (a < b)
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(base + (long long)a * (2 * DP_D)),
+                 "r"((uint32_t)(b - a) * (uint32_t)(2 * DP_D * sizeof(T)))
+                 : "memory");
+}
+
+// ---- the weight ring -------------------------------------------------------------------------------------------
+// Slot g % NSLOT holds the g-th chunk of the fixed consumption order (per step: L layers x 16 chunks, then the CTA's
+// share of the classifier): 32 weight rows, their 32 biases and -- with the first chunk of a projection that reads a
+// LayerNorm output -- that LayerNorm's scale and shift.  `consumed` / `issued` are tracked identically by every thread;
+// only thread 0 copies.  Nothing a projection phase needs is fetched from global memory on its critical path.
+constexpr int DP_PAR = 128 + 2 * DP_D * 4;  // bytes of the parameter tail of a slot: bias[32] | gamma[256] | beta[256]
+template <typename T>
+struct Ring {
+  static constexpr int W_BYTES = DP_CH * DP_D * (int)sizeof(T);
+  static constexpr int SLOT_BYTES = W_BYTES + DP_PAR;
+  static constexpr int NSLOT = sizeof(T) == 2 ? 8 : 4;
+  static constexpr int BYTES = NSLOT * SLOT_BYTES;
+  uint8_t* base;
+  uint64_t* full;
+  const LayerW<T>* layers;  // shared-memory copy of the layer table
+  const T* w_out;
+  const float* b_out;
+  uint64_t pol;             // L2 evict-last: the weights are re-read by every cluster, every step
+  long long* t_wait;        // optional cycle counter of the time spent waiting for a slot
+  int L, rank, cps, vbeg, vend;
+  int consumed, issued, limit;  // chunk counters (nsteps x cps fits 31 bits: checked by the launcher)
+
+  __device__ __forceinline__ void copy(uint8_t* dst, const void* src, uint32_t bytes, uint64_t* bar) const {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
+                 : "memory");
   }
+  // call only right after a barrier every warp of the CTA has passed: all chunks < consumed are then free.
+  // Issuing a bulk copy costs its thread a few hundred cycles, so the work is spread: the chunk for slot s is issued by
+  // warp s, its (up to four) copies by four lanes side by side (complete_tx may precede expect_tx on an mbarrier).
+  __device__ __forceinline__ void top_up() {
+    int target = consumed + NSLOT;
+    if (target > limit) target = limit;
+    if (target <= issued) return;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp < NSLOT && lane < 4) {
+      // the one chunk in [issued, target) that lands in slot `warp`
+      const int g = issued + ((warp - issued % NSLOT) + NSLOT) % NSLOT;
+      if (g < target) {
+        const int k = g % cps;
+        const T* src;
+        const float *bias, *gamma = nullptr, *beta = nullptr;
+        int rows = DP_CH, brows = DP_CH;
+        if (k < DP_LCH * L) {
+          const int l = k / DP_LCH, c = k % DP_LCH;
+          const LayerW<T>& W = layers[l];
+          if (c < 6) {
+            src = W.w_in + (long long)(rank * 192 + c * DP_CH) * DP_D;
+            bias = W.b_in + rank * 192 + c * DP_CH;
+            if (c == 0 && l > 0) { gamma = layers[l - 1].g3; beta = layers[l - 1].be3; }
+          } else {
+            const int ph = (c - 6) >> 1, hf = (c - 6) & 1;
+            const T* w = ph == 0 ? W.w_o : ph == 1 ? W.wc_q : ph == 2 ? W.wc_o : ph == 3 ? W.w1 : W.w2;
+            const float* bb = ph == 0 ? W.b_o : ph == 1 ? W.bc_q : ph == 2 ? W.bc_o : ph == 3 ? W.b1 : W.b2;
+            src = w + (long long)(rank * 64 + hf * DP_CH) * DP_D;
+            bias = bb + rank * 64 + hf * DP_CH;
+            if (hf == 0 && ph == 1) { gamma = W.g1; beta = W.be1; }
+            if (hf == 0 && ph == 3) { gamma = W.g2; beta = W.be2; }
+          }
+        } else {
+          const int c = k - DP_LCH * L, r0 = vbeg + c * DP_CH;
+          rows = vend - r0 < DP_CH ? vend - r0 : DP_CH;
+          brows = rows & ~3;  // bulk copies move multiples of 16 bytes; a ragged tail is read directly by its warp
+          src = w_out + (long long)r0 * DP_D;
+          bias = b_out + r0;
+          if (c == 0) { gamma = layers[L - 1].g3; beta = layers[L - 1].be3; }
+        }
+        const uint32_t wbytes = (uint32_t)rows * DP_D * (uint32_t)sizeof(T);
+        uint8_t* dst = base + (size_t)warp * SLOT_BYTES;
+        uint64_t* bar = &full[warp];
+        if (lane == 0) {
+          mbar_expect_tx(bar, wbytes + (uint32_t)brows * 4u + (gamma ? 2u * DP_D * 4u : 0u));
+          copy(dst, src, wbytes, bar);
+        } else if (lane == 1) {
+          if (brows) copy(dst + W_BYTES, bias, (uint32_t)brows * 4u, bar);
+        } else if (gamma) {
+          if (lane == 2) copy(dst + W_BYTES + 128, gamma, DP_D * 4, bar);
+          else copy(dst + W_BYTES + 128 + DP_D * 4, beta, DP_D * 4, bar);
+        }
+      }
+      __syncwarp(0xfu);
+    }
+    issued = target;
+  }
+  // wait for the next chunk; returns its slot
+  __device__ __forceinline__ const uint8_t* acquire() {
+    if (consumed >= issued) {  // ring smaller than the phase: recycle inside it (uniform branch)
+      __syncthreads();
+      top_up();
+    }
+    const int slot = consumed % NSLOT;
+    if (t_wait) {
+      const long long t0 = clock64();
+      mbar_wait(&full[slot], (uint32_t)((consumed / NSLOT) & 1));
+      *t_wait += clock64() - t0;
+    } else {
+      mbar_wait(&full[slot], (uint32_t)((consumed / NSLOT) & 1));
+    }
+    return base + (size_t)slot * SLOT_BYTES;
+  }
+};
+
+// lane-distributed 256-vector from shared memory: lane holds elements lane*8 .. lane*8+7
+__device__ __forceinline__ void load_vec(const float* src, float (&v)[8]) {
+  const int lane = threadIdx.x & 31;
+  const float4 a = *reinterpret_cast<const float4*>(src + lane * 8);
+  const float4 b = *reinterpret_cast<const float4*>(src + lane * 8 + 4);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
 }
 __device__ __forceinline__ void store_vec(float* dst, const float (&v)[8]) {
   const int lane = threadIdx.x & 31;
   *reinterpret_cast<float4*>(dst + lane * 8) = make_float4(v[0], v[1], v[2], v[3]);
   *reinterpret_cast<float4*>(dst + lane * 8 + 4) = make_float4(v[4], v[5], v[6], v[7]);
 }
+// LayerNorm of the lane-distributed vector with the scale / shift rows of a ring slot
+__device__ __forceinline__ void layer_norm(float (&v)[8], const float* gamma, const float* beta, float eps) {
+  float sum = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) sum += v[k];
+  const float mean = warp_sum(sum) * (1.f / DP_D);
+  float var = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { const float d = v[k] - mean; var = fmaf(d, d, var); }
+  const float rstd = rsqrtf(warp_sum(var) * (1.f / DP_D) + eps);
+  float g[8], b[8];
+  load_vec(gamma, g);
+  load_vec(beta, b);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) v[k] = (v[k] - mean) * rstd * g[k] + b[k];
+}
 
-// out(n) = <x, W[n, :]> + bias[n] for the columns of this warp (cluster-wide warp id wg of DP_CW), 4 columns in flight
-template <typename T, typename Epi>
-__device__ __forceinline__ void gemv_cols(const float (&x)[8], const T* __restrict__ W, const float* __restrict__ bias, int N, int wg,
-                                          Epi epi) {
-  const int lane = threadIdx.x & 31;
-  for (int n0 = wg; n0 < N; n0 += 4 * DP_CW) {
-    Raw8<T> raw[4];
+// the two columns (2 warp, 2 warp + 1 of the slot's 32) of this warp and their biases; every lane gets both sums
+template <typename T>
+__device__ __forceinline__ void gemv_slot(const uint8_t* slot, const float (&x)[8], float& d0, float& d1, float2& bias) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const T* w = reinterpret_cast<const T*>(slot) + (2 * warp) * DP_D + lane * 8;
+  Raw8<T> r0, r1;
+  r0.load(w);
+  r1.load(w + DP_D);
+  bias = *reinterpret_cast<const float2*>(slot + Ring<T>::W_BYTES + 8 * warp);
+  float w0[8], w1[8];
+  r0.get(w0);
+  r1.get(w1);
+  d0 = 0.f; d1 = 0.f;
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int n = n0 + u * DP_CW;
-      if (n < N) raw[u].load(W + (long long)n * DP_D + lane * 8);
-      else raw[u].zero();
-    }
+  for (int e = 0; e < 8; ++e) { d0 = fmaf(x[e], w0[e], d0); d1 = fmaf(x[e], w1[e], d1); }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int n = n0 + u * DP_CW;
-      float w[8];
-      raw[u].get(w);
-      float d = 0.f;
+  for (int o = 16; o > 0; o >>= 1) {
+    d0 += __shfl_xor_sync(0xffffffffu, d0, o);
+    d1 += __shfl_xor_sync(0xffffffffu, d1, o);
+  }
+}
+// A projection of NCH ring slots per CTA: x = xs (shared memory), optionally LayerNorm'ed with the parameters that
+// travel in the first slot (the normalised vector is then also kept in x_keep for a later residual);
+// epi(ch, j, value) runs on all 32 lanes for column ch*32 + 2*warp + j of the CTA's share.
+template <typename T, int NCH, typename Epi>
+__device__ __forceinline__ void gemv_phase(Ring<T>& R, const float* xs, bool LN, float* x_keep, float eps, Epi epi, long long* dbg = nullptr) {
+  long long t0 = dbg ? clock64() : 0;
+  const uint8_t* slot = R.acquire();
+  if (dbg) { long long t = clock64(); dbg[0] += t - t0; t0 = t; }
+  float x[8];
+  load_vec(xs, x);
+  if (LN) {
+    const float* gamma = reinterpret_cast<const float*>(slot + Ring<T>::W_BYTES + 128);
+    layer_norm(x, gamma, gamma + DP_D, eps);
+    if (x_keep && threadIdx.x < 32) store_vec(x_keep, x);
+  }
+  if (dbg) { long long t = clock64(); dbg[1] += t - t0; t0 = t; }
 #pragma unroll
-      for (int e = 0; e < 8; ++e) d = fmaf(x[e], w[e], d);
-      d = warp_sum(d);
-      if (n < N && lane == 0) epi(n, d + (bias ? bias[n] : 0.f));
-    }
+  for (int ch = 0; ch < NCH; ++ch) {
+    if (ch > 0) slot = R.acquire();
+    if (dbg) { long long t = clock64(); dbg[2] += t - t0; t0 = t; }
+    float d0, d1;
+    float2 bias;
+    gemv_slot<T>(slot, x, d0, d1, bias);
+    ++R.consumed;
+    if (dbg) { long long t = clock64(); dbg[3] += t - t0; t0 = t; }
+    epi(ch, 0, d0 + bias.x);
+    epi(ch, 1, d1 + bias.y);
+    if (dbg) { long long t = clock64(); dbg[4] += t - t0; t0 = t; }
   }
 }
 
-// single-query attention of ONE (sample, head) by the whole CTA: keys [j_lo, tk); result out[0..63] (global, fp32)
+// single-query attention of ONE (sample, head) by the whole CTA: keys [j_lo, tk); q in shared memory; the 64 outputs
+// are written into `out` of all four CTAs.  K / V rows: 16-byte streaming loads, register double buffer.
 template <typename T>
-__device__ void attn_head(float* sm, const float* __restrict__ q, const T* __restrict__ kp, int tk, int j_lo,
-                          const float* __restrict__ kb, float scale, float* __restrict__ out) {
+__device__ void attn_head(float* sc, float* red, float* s_red, const float* q, const T* __restrict__ kp, int tk, int j_lo,
+                          const float* __restrict__ kb, float scale, float* out, const uint64_t* out_bar, uint64_t pol,
+                          const float* knew, const float* vnew) {
+  constexpr int U = sizeof(T) == 2 ? 8 : 4;  // rows per buffer and thread
+  constexpr int PER = U * DP_KL;             // keys per iteration of the CTA
   const int tid = threadIdx.x, c = tid & 7, g = tid >> 3;  // DP_KL key lanes x 8 dim chunks
-  __shared__ float s_red[33];
-  float* sc = sm;                                // [n]
-  const int n = tk - j_lo;
-  float* red = sm + ((n + 3) & ~3);              // [DP_KL][64]
-  const T* vp = kp + DP_D;
-  float qv[8];
-#pragma unroll
-  for (int e = 0; e < 8; ++e) qv[e] = __ldcg(q + c * 8 + e) * scale;
-  constexpr int U = sizeof(T) == 2 ? 8 : 4;  // keys in flight per thread
-  float mx = -INFINITY;
-  for (int jb = 0; jb < n; jb += U * DP_KL) {
-    Raw8<T> raw[U];
+  const int n = tk - j_lo;                  // keys, the last of which may still be in shared memory (knew / vnew):
+  const int n_glob = knew ? n - 1 : n;      // the token being decoded; its cache row is written for the steps to come
+  const int niter = (n + PER - 1) / PER;
+  const T* kbase = kp + (long long)j_lo * (2 * DP_D) + c * 8;
+  const T* vbase = kbase + DP_D;
+  Raw8<T> ba[U], bb[U];
+  auto fetch = [&](Raw8<T>(&r)[U], const T* base, const float* extra, int it) {
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const int j = jb + u * DP_KL + g;
-      if (j < n) raw[u].load(kp + (long long)(j_lo + j) * (2 * DP_D) + c * 8);
-      else raw[u].zero();
+      const int j = it * PER + u * DP_KL + g;
+      if (j < n_glob) r[u].load_stream(base + (long long)j * (2 * DP_D), pol);
+      else if (j < n) r[u].set(extra + c * 8);
+      else r[u].zero();
     }
+  };
+  fetch(ba, kbase, knew, 0);
+  float qv[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) qv[e] = q[c * 8 + e] * scale;
+  float mx = -INFINITY;
+  auto scores = [&](const Raw8<T>(&r)[U], int it) {
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       float kvv[8];
-      raw[u].get(kvv);
+      r[u].get(kvv);
       float d = 0.f;
 #pragma unroll
       for (int e = 0; e < 8; ++e) d = fmaf(qv[e], kvv[e], d);
       d += __shfl_xor_sync(0xffffffffu, d, 1);
       d += __shfl_xor_sync(0xffffffffu, d, 2);
       d += __shfl_xor_sync(0xffffffffu, d, 4);
-      const int j = jb + u * DP_KL + g;
+      const int j = it * PER + u * DP_KL + g;
       if (j < n) {
         if (kb) d += kb[j_lo + j];
         if (c == 0) sc[j] = d;
         mx = fmaxf(mx, d);
       }
     }
+  };
+  for (int it = 0; it < niter; it += 2) {
+    if (it + 1 < niter) fetch(bb, kbase, knew, it + 1);
+    scores(ba, it);
+    if (it + 1 < niter) {
+      if (it + 2 < niter) fetch(ba, kbase, knew, it + 2);
+      scores(bb, it + 1);
+    }
   }
+  fetch(ba, vbase, vnew, 0);  // in flight while the softmax statistics are reduced
   mx = block_max(mx, s_red);
   const float msafe = (mx == -INFINITY) ? 0.f : mx;
   float sum = 0.f;
@@ -192,159 +403,437 @@ __device__ void attn_head(float* sm, const float* __restrict__ q, const T* __res
   float acc[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) acc[e] = 0.f;
-  for (int jb = 0; jb < n; jb += U * DP_KL) {
-    Raw8<T> raw[U];
+  auto weigh = [&](const Raw8<T>(&r)[U], int it) {
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const int j = jb + u * DP_KL + g;
-      if (j < n) raw[u].load(vp + (long long)(j_lo + j) * (2 * DP_D) + c * 8);
-      else raw[u].zero();
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int j = jb + u * DP_KL + g;
+      const int j = it * PER + u * DP_KL + g;
       const float pj = j < n ? sc[j] : 0.f;
       float vv[8];
-      raw[u].get(vv);
+      r[u].get(vv);
 #pragma unroll
       for (int e = 0; e < 8; ++e) acc[e] = fmaf(pj, vv[e], acc[e]);
+    }
+  };
+  for (int it = 0; it < niter; it += 2) {
+    if (it + 1 < niter) fetch(bb, vbase, vnew, it + 1);
+    weigh(ba, it);
+    if (it + 1 < niter) {
+      if (it + 2 < niter) fetch(ba, vbase, vnew, it + 2);
+      weigh(bb, it + 1);
     }
   }
 #pragma unroll
   for (int e = 0; e < 8; ++e) red[g * DP_HD + c * 8 + e] = acc[e];
   __syncthreads();
-  if (tid < DP_HD) {
-    float o = 0.f;
-#pragma unroll 8
-    for (int l = 0; l < DP_KL; ++l) o += red[l * DP_HD + tid];
-    out[tid] = sum > 0.f ? o / sum : 0.f;
+  if (tid < 4 * DP_HD) {  // 4 threads per output: 16 key lanes each
+    const int o = tid >> 2, part = tid & 3;
+    float s = 0.f;
+#pragma unroll 4
+    for (int l = part * (DP_KL / 4); l < (part + 1) * (DP_KL / 4); ++l) s += red[l * DP_HD + o];
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    st_async(out + o, sum > 0.f ? s / sum : 0.f, (unsigned)part, out_bar);
   }
-  __syncthreads();  // sc / red may be reused by the next call
+  // sc / red are next written two phases on, which the whole cluster enters only after these sends
 }
 
-enum { PH_EMBED = 0, PH_QKV, PH_SELF, PH_OUT, PH_CQ, PH_CROSS, PH_COUT, PH_FFN1, PH_FFN2, PH_VOCAB, PH_ARGMAX };
-#define DP_SYNC(kind)                                   \
-  do {                                                  \
-    cluster_sync_all();                                 \
-    if (timed) {                                        \
-      const long long now = clock64();                  \
-      p.timing[kind] += now - t_prev;                   \
-      t_prev = now;                                     \
-    }                                                   \
+// ---- bf16 attention on the (legacy, warp-level) tensor-core path ------------------------------------------------------
+// A decode step has ONE query per head, so the attention is a matrix-vector product -- but issued as FMAs it costs ~30
+// instructions per 16-byte load and the phase becomes issue bound long before it is HBM bound.  mma.sync.m16n8k16 does a
+// [16 keys x 16 dims] tile per instruction with the K / V rows used exactly as they come out of a 16-byte load:
+//   scores: A = K tile (rows = keys, k = dims), B = q broadcast to the 8 columns.  The k index is a free permutation as
+//           long as A and B agree, so thread (g, t) simply feeds the registers of its load of row g, dims 16t..16t+15.
+//   P V   : A = p (bf16, broadcast to the rows), B = V tile (k = keys, n = dims): movmatrix.trans turns the loaded
+//           registers (key g, dim pair t) into the B fragment (key pair t, dim g); again the n index is a permutation we
+//           only have to undo when the result is written.
+// tcgen05 would need the operands in shared memory and a 128-row accumulator for a 1-row product; this path keeps the
+// stream in registers.  The fp32 parity mode keeps the exact FMA path above.
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t movm_trans(uint32_t a) {
+  uint32_t d;
+  asm volatile("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;" : "=r"(d) : "r"(a));
+  return d;
+}
+struct Row32 {  // 32 bytes of one K or V row
+  uint4 lo, hi;
+};
+__device__ __forceinline__ uint4 ldg_stream(const bf16* p, uint64_t pol) {
+  uint4 v;
+  asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ uint4 pack8(const float* p) {
+  return make_uint4(tc::pack_bf16(p[0], p[1]), tc::pack_bf16(p[2], p[3]), tc::pack_bf16(p[4], p[5]), tc::pack_bf16(p[6], p[7]));
+}
+
+// Same contract as attn_head.  Warp w owns the 16-key tiles w, w+16, ...; two tiles (128 B per thread) are in flight
+// while two are consumed.
+__device__ void attn_head_mma(float* sc, float* red, float* s_red, const float* q, const bf16* __restrict__ kp, int tk, int j_lo,
+                              const float* __restrict__ kb, float scale, float* out, const uint64_t* out_bar, uint64_t pol,
+                              const float* knew, const float* vnew) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int n = tk - j_lo;
+  const int n_glob = knew ? n - 1 : n;
+  const int ntile = (n + 15) >> 4;
+  const bf16* kbase = kp + (long long)j_lo * (2 * DP_D);
+  // a pair of rows (g, g + 8) of tile `tile`: `o0`, `o1` = element offsets of the two 16-byte pieces inside the head
+  auto fetch = [&](Row32(&r)[2], const bf16* base, const float* extra, int tile, int o0, int o1) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int j = tile * 16 + g + 8 * h;
+      if (j < n_glob) {
+        const bf16* rp = base + (long long)j * (2 * DP_D);
+        r[h].lo = ldg_stream(rp + o0, pol);
+        r[h].hi = ldg_stream(rp + o1, pol);
+      } else if (j < n) {
+        r[h].lo = pack8(extra + o0);
+        r[h].hi = pack8(extra + o1);
+      } else {
+        r[h].lo = make_uint4(0, 0, 0, 0);
+        r[h].hi = r[h].lo;
+      }
+    }
+  };
+  // ---- scores ----
+  Row32 ka[2], kc[2];
+  if (warp < ntile) fetch(ka, kbase, knew, warp, 16 * t, 16 * t + 8);
+  uint32_t qb[8];
+  {
+    const float* qp = q + 16 * t;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) qb[i] = tc::pack_bf16(qp[2 * i] * scale, qp[2 * i + 1] * scale);
+  }
+  float mx = -INFINITY;
+  auto scores = [&](const Row32(&r)[2], int tile) {
+    float c[4] = {0.f, 0.f, 0.f, 0.f};
+    mma_bf16_16816(c, r[0].lo.x, r[1].lo.x, r[0].lo.y, r[1].lo.y, qb[0], qb[1]);
+    mma_bf16_16816(c, r[0].lo.z, r[1].lo.z, r[0].lo.w, r[1].lo.w, qb[2], qb[3]);
+    mma_bf16_16816(c, r[0].hi.x, r[1].hi.x, r[0].hi.y, r[1].hi.y, qb[4], qb[5]);
+    mma_bf16_16816(c, r[0].hi.z, r[1].hi.z, r[0].hi.w, r[1].hi.w, qb[6], qb[7]);
+    const int j0 = tile * 16 + g, j1 = j0 + 8;
+    float s0 = c[0], s1 = c[2];
+    if (kb) {
+      if (j0 < n) s0 += kb[j_lo + j0];
+      if (j1 < n) s1 += kb[j_lo + j1];
+    }
+    if (j0 < n) { mx = fmaxf(mx, s0); if (t == 0) sc[j0] = s0; }
+    if (j1 < n) { mx = fmaxf(mx, s1); if (t == 0) sc[j1] = s1; }
+  };
+  for (int tile = warp; tile < ntile; tile += 2 * DP_WARPS) {
+    if (tile + DP_WARPS < ntile) fetch(kc, kbase, knew, tile + DP_WARPS, 16 * t, 16 * t + 8);
+    scores(ka, tile);
+    if (tile + DP_WARPS < ntile) {
+      if (tile + 2 * DP_WARPS < ntile) fetch(ka, kbase, knew, tile + 2 * DP_WARPS, 16 * t, 16 * t + 8);
+      scores(kc, tile + DP_WARPS);
+    }
+  }
+  // ---- first V tile in flight while the softmax statistics are reduced ----
+  const bf16* vbase = kbase + DP_D;
+  if (warp < ntile) fetch(ka, vbase, vnew, warp, 8 * t, 32 + 8 * t);
+  mx = block_max(mx, s_red);
+  const float msafe = (mx == -INFINITY) ? 0.f : mx;
+  float sum = 0.f;
+  for (int j = tid; j < ntile * 16; j += DP_THREADS) {
+    const float pr = j < n ? to_f(__float2bfloat16_rn(expf(sc[j] - msafe))) : 0.f;  // the value the P V product will see
+    sc[j] = pr;
+    sum += pr;
+  }
+  sum = block_sum(sum, s_red);  // contains the __syncthreads that publishes sc[]
+  // ---- P V ----
+  float acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { acc[i][0] = 0.f; acc[i][1] = 0.f; acc[i][2] = 0.f; acc[i][3] = 0.f; }
+  auto weigh = [&](const Row32(&r)[2], int tile) {
+    const float2 p0 = *reinterpret_cast<const float2*>(sc + tile * 16 + 2 * t);
+    const float2 p1 = *reinterpret_cast<const float2*>(sc + tile * 16 + 8 + 2 * t);
+    const uint32_t a0 = tc::pack_bf16(p0.x, p0.y), a2 = tc::pack_bf16(p1.x, p1.y);
+    const uint32_t v0[8] = {r[0].lo.x, r[0].lo.y, r[0].lo.z, r[0].lo.w, r[0].hi.x, r[0].hi.y, r[0].hi.z, r[0].hi.w};
+    const uint32_t v1[8] = {r[1].lo.x, r[1].lo.y, r[1].lo.z, r[1].lo.w, r[1].hi.x, r[1].hi.y, r[1].hi.z, r[1].hi.w};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) mma_bf16_16816(acc[i], a0, 0u, a2, 0u, movm_trans(v0[i]), movm_trans(v1[i]));
+  };
+  for (int tile = warp; tile < ntile; tile += 2 * DP_WARPS) {
+    if (tile + DP_WARPS < ntile) fetch(kc, vbase, vnew, tile + DP_WARPS, 8 * t, 32 + 8 * t);
+    weigh(ka, tile);
+    if (tile + DP_WARPS < ntile) {
+      if (tile + 2 * DP_WARPS < ntile) fetch(ka, vbase, vnew, tile + 2 * DP_WARPS, 8 * t, 32 + 8 * t);
+      weigh(kc, tile + DP_WARPS);
+    }
+  }
+  // rows of the accumulator are identical; lanes g == 0 hold, for i = 0..7, dims (i<4 ? 0 : 32) + 8t + 2(i%4) + {0,1}
+  if (g == 0) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      *reinterpret_cast<float2*>(red + warp * DP_HD + (i < 4 ? 0 : 32) + 8 * t + 2 * (i & 3)) = make_float2(acc[i][0], acc[i][1]);
+  }
+  __syncthreads();
+  if (tid < 4 * DP_HD) {  // 4 threads per output: 4 warps' partials each
+    const int o = tid >> 2, part = tid & 3;
+    float s = 0.f;
+#pragma unroll
+    for (int l = part * (DP_WARPS / 4); l < (part + 1) * (DP_WARPS / 4); ++l) s += red[l * DP_HD + o];
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    st_async(out + o, sum > 0.f ? s / sum : 0.f, (unsigned)part, out_bar);
+  }
+}
+template <typename T>
+__device__ __forceinline__ void attention(float* sc, float* red, float* s_red, const float* q, const T* kp, int tk, int j_lo,
+                                          const float* kb, float scale, float* out, const uint64_t* out_bar, uint64_t pol,
+                                          const float* knew, const float* vnew) {
+  if constexpr (sizeof(T) == 2) attn_head_mma(sc, red, s_red, q, kp, tk, j_lo, kb, scale, out, out_bar, pol, knew, vnew);
+  else attn_head<T>(sc, red, s_red, q, kp, tk, j_lo, kb, scale, out, out_bar, pol, knew, vnew);
+}
+
+enum { PH_EMBED = 0, PH_QKV, PH_SELF, PH_OUT, PH_CQ, PH_CROSS, PH_COUT, PH_FFN1, PH_FFN2, PH_VOCAB, PH_ARGMAX, PH_BARRIER, PH_RING };
+enum { VB_Q = 0, VB_A, VB_S, VB_H };  // the exchanged vectors and their mbarriers
+// A phase boundary: wait until all `bytes` of the exchanged vector X have landed in this CTA (sent by the 64 warps of
+// the cluster with st.async) -- which also means that every warp of the cluster is done with the phase's ring slots --
+// account the time, recycle the slots.
+#define VEC_WAIT(X, bytes, kind)                                   \
+  do {                                                             \
+    const long long tb = timed ? clock64() : 0;                    \
+    if (threadIdx.x == 0) mbar_expect_tx(&vb[X], bytes);           \
+    mbar_wait(&vb[X], (vpar >> (X)) & 1u);                         \
+    vpar ^= 1u << (X);                                             \
+    if (timed) {                                                   \
+      const long long now = clock64();                             \
+      tacc[kind] += now - t_prev;                                  \
+      tacc[PH_BARRIER] += now - tb;                                \
+      t_prev = now;                                                \
+    }                                                              \
+    R.top_up();                                                    \
+    if (timed) tacc[13] += clock64() - t_prev;                     \
   } while (0)
 
 template <typename T>
 __global__ void __launch_bounds__(DP_THREADS, 1) decode_persistent_kernel(DPArgs p) {
-  extern __shared__ __align__(16) float smem[];  // attention scores + key-lane partials
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  float* vecs = reinterpret_cast<float*>(smem_raw + Ring<T>::BYTES);
+  float *xv = vecs, *sv = vecs + DP_D, *qv = vecs + 2 * DP_D, *av = vecs + 3 * DP_D, *hv = vecs + 4 * DP_D;
+  float *kn = vecs + 5 * DP_D, *vn = kn + DP_HD;  // this head's K / V row of the token being decoded
+  float* cand = vn + DP_HD;                      // [4][2] per-CTA argmax candidates
+  uint64_t* full = reinterpret_cast<uint64_t*>(vecs + DP_VEC);  // [8] ring slots
+  uint64_t* vb = full + 8;                       // [4] exchanged vectors
+  float* s_red = reinterpret_cast<float*>(vb + 4);   // [40]
+  float* sc = s_red + 40;                        // [sc_floats] attention scores
+  float* red = sc + p.sc_floats;                 // [DP_KL][64] key-lane partials
+  LayerW<T>* layers = reinterpret_cast<LayerW<T>*>(red + DP_KL * DP_HD);  // [L] copy of the layer table
   __shared__ float cand_v[DP_WARPS];
   __shared__ int cand_i[DP_WARPS];
-  const LayerW<T>* layers = reinterpret_cast<const LayerW<T>*>(p.layers);
+  __shared__ long long dbgc[8];
+  if (threadIdx.x < 8) dbgc[threadIdx.x] = 0;
+  __shared__ long long tacc[16];  // per-phase cycle counters of thread 0 (flushed to p.timing at the end)
+  if (threadIdx.x < 16) tacc[threadIdx.x] = 0;
   const T* emb = reinterpret_cast<const T*>(p.emb);
-  const T* w_out = reinterpret_cast<const T*>(p.w_out);
   const int rank = (int)cluster_rank();          // = head owned by this CTA
   const int b = (int)cluster_id_x();             // = sample owned by this cluster
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int wg = rank * DP_WARPS + warp;         // cluster-wide warp id
   const bool timed = p.timing && b == 0 && rank == 0 && threadIdx.x == 0;
-  long long t_prev = clock64();
-  float* scr = p.scratch + (long long)b * DP_SCR;
-  float *xv = scr, *sv = scr + DP_D, *qv = scr + 2 * DP_D, *av = scr + 3 * DP_D, *hv = scr + 4 * DP_D;
-  float* cand = scr + 5 * DP_D;                  // [4][2] per-CTA argmax candidates
   const int pos0 = *p.pos;
+  int nsteps = p.nsteps;
+  if (pos0 + nsteps > p.Tmax) nsteps = p.Tmax - pos0;
   const float* kbias = p.mem_bias ? p.mem_bias + (long long)b * p.mem_bias_bs : nullptr;
   long long tok = p.tok[b];
   bool fin = p.finished[b] != 0;
+  unsigned vpar = 0;    // phase parities of vb[]
+  uint64_t pol_stream;  // K / V rows are read once per step: first out of L2
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
 
-  for (int step = 0; step < p.nsteps && !fin; ++step) {
+  {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(p.layers);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(layers);
+    for (int i = threadIdx.x; i < p.L * (int)(sizeof(LayerW<T>) / 4); i += DP_THREADS) dst[i] = src[i];
+  }
+  Ring<T> R;
+  R.base = smem_raw; R.full = full; R.layers = layers; R.w_out = reinterpret_cast<const T*>(p.w_out); R.b_out = p.b_out;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(R.pol));
+  R.t_wait = timed ? tacc + PH_RING : nullptr;
+  R.L = p.L; R.rank = rank;
+  {
+    const int vq = (((p.V + DP_CL - 1) / DP_CL) + DP_CH - 1) / DP_CH * DP_CH;  // classifier columns per CTA
+    R.vbeg = rank * vq < p.V ? rank * vq : p.V;
+    R.vend = R.vbeg + vq < p.V ? R.vbeg + vq : p.V;
+  }
+  const int ncols_v = R.vend - R.vbeg;
+  const int nvch = (ncols_v + DP_CH - 1) / DP_CH;
+  R.cps = DP_LCH * p.L + nvch;
+  R.consumed = 0; R.issued = 0;
+  R.limit = (fin || nsteps <= 0) ? 0 : nsteps * R.cps;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < Ring<T>::NSLOT; ++s) mbar_init(&full[s], 1);
+    for (int s = 0; s < 4; ++s) mbar_init(&vb[s], 1);
+    tc::fence_barrier_init();
+  }
+  __syncthreads();
+  R.top_up();
+  cluster_arrive();  // every CTA of the cluster is resident, its barriers initialised, before the first remote store
+  cluster_wait();
+  long long t_prev = clock64();
+
+  for (int step = 0; step < nsteps && !fin; ++step) {
     const int pos = pos0 + step;  // position of the token being consumed; keys 0..pos are visible
-    if (pos >= p.Tmax) break;
-    // ---- x = emb[tok] + pe[pos] : written once (rank 0, warp 0), fp32 residual stream ----
-    if (rank == 0 && warp == 0) {
+    // ---- x = emb[tok] + pe[pos]: every CTA builds its own copy (fp32 residual stream) ----
+    if (warp == 0) {
       float v[8];
 #pragma unroll
       for (int k = 0; k < 8; ++k) v[k] = to_f(emb[tok * DP_D + lane * 8 + k]) + p.pe[(long long)pos * DP_D + lane * 8 + k];
       store_vec(xv, v);
     }
-    DP_SYNC(PH_EMBED);
+    __syncthreads();
+    if (timed) { const long long now = clock64(); tacc[PH_EMBED] += now - t_prev; t_prev = now; }
     for (int l = 0; l < p.L; ++l) {
       const LayerW<T>& W = layers[l];
-      float x[8];
-      // P1: q | k | v of x (= the embedding, or LN3 of the previous layer's sum); k, v go straight into the cache
-      if (l == 0) load_vec(xv, x, nullptr, nullptr, 0.f);
-      else load_vec(sv, x, layers[l - 1].g3, layers[l - 1].be3, p.ln_eps);
+      // P1: q | k | v of x (= the embedding, or LN3 of the previous layer's sum -> kept in xv for P3's residual).
+      //     q goes to all four CTAs, the k / v values (rounded to the cache type) to the CTA of their head and, for
+      //     the steps to come, into the cache
       {
         T* crow = W.self_kv + ((long long)b * p.Tmax + pos) * (2 * DP_D);
-        gemv_cols<T>(x, W.w_in, W.b_in, 3 * DP_D, wg, [&](int n, float v) {
-          if (n < DP_D) qv[n] = v;
-          else crow[n - DP_D] = from_f<T>(v);
+        gemv_phase<T, 6>(R, l == 0 ? xv : sv, l > 0, xv, p.ln_eps, [&](int ch, int j, float v) {
+          const int n = rank * 192 + ch * DP_CH + 2 * warp + j;
+          if (n < DP_D) {
+            if (lane < DP_CL) st_async(qv + n, v, lane, &vb[VB_Q]);
+          } else {
+            const T r = from_f<T>(v);
+            const int m = n - DP_D;  // 0..255 key, 256..511 value; 64 per head
+            if (lane == 0) st_async((m < DP_D ? kn : vn) + (m & (DP_HD - 1)), to_f(r), (unsigned)((m >> 6) & 3), &vb[VB_Q]);
+            if (lane == 1) crow[m] = r;
+          }
         });
       }
-      if (l > 0 && wg == 0) store_vec(xv, x);  // publish x = LN3(s): nobody reads xv in P1, P3 reads it two barriers later
-      DP_SYNC(PH_QKV);
-      // P2: causal / windowed self-attention of head `rank` over the cache
+      VEC_WAIT(VB_Q, 4 * DP_D + 8 * DP_HD, PH_QKV);
+      // P2: causal / windowed self-attention of head `rank` over the cache (+ the new row from shared memory)
       {
         int j_lo = 0;
         if (p.window > 0 && pos - p.window > 0) j_lo = pos - p.window;
-        attn_head<T>(smem, qv + rank * DP_HD, W.self_kv + (long long)b * p.Tmax * 2 * DP_D + rank * DP_HD, pos + 1, j_lo, nullptr,
-                     p.scale, av + rank * DP_HD);
+        attention<T>(sc, red, s_red, qv + rank * DP_HD, W.self_kv + (long long)b * p.Tmax * 2 * DP_D + rank * DP_HD, pos + 1, j_lo,
+                     nullptr, p.scale, av + rank * DP_HD, &vb[VB_A], pol_stream, kn, vn);
       }
-      DP_SYNC(PH_SELF);
+      VEC_WAIT(VB_A, 4 * DP_D, PH_SELF);
+      prefetch_rows<T>(W.cross_kv + (long long)b * p.S * 2 * DP_D, 0, p.S < p.pf_cross ? p.S : p.pf_cross, rank);
       // P3: s = x + out_proj(a)
-      load_vec(av, x, nullptr, nullptr, 0.f);
-      gemv_cols<T>(x, W.w_o, W.b_o, DP_D, wg, [&](int n, float v) { sv[n] = v + __ldcg(xv + n); });
-      DP_SYNC(PH_OUT);
-      // P4: x1 = LN1(s) -> cross query
-      load_vec(sv, x, W.g1, W.be1, p.ln_eps);
-      gemv_cols<T>(x, W.wc_q, W.bc_q, DP_D, wg, [&](int n, float v) { qv[n] = v; });
-      if (wg == 0) store_vec(xv, x);  // x1: read again in P6 (two barriers later); P4 reads only sv
-      DP_SYNC(PH_CQ);
+      gemv_phase<T, 2>(R, av, false, nullptr, 0.f, [&](int ch, int j, float v) {
+        const int n = rank * 64 + ch * DP_CH + 2 * warp + j;
+        if (lane < DP_CL) st_async(sv + n, v + xv[n], lane, &vb[VB_S]);
+      }, timed ? dbgc : nullptr);
+      VEC_WAIT(VB_S, 4 * DP_D, PH_OUT);
+      // P4: x1 = LN1(s) (kept in xv for P6's residual) -> cross query
+      gemv_phase<T, 2>(R, sv, true, xv, p.ln_eps, [&](int ch, int j, float v) {
+        const int n = rank * 64 + ch * DP_CH + 2 * warp + j;
+        if (lane < DP_CL) st_async(qv + n, v, lane, &vb[VB_Q]);
+      });
+      VEC_WAIT(VB_Q, 4 * DP_D, PH_CQ);
       // P5: cross-attention of head `rank` over the projected encoder memory
-      attn_head<T>(smem, qv + rank * DP_HD, W.cross_kv + (long long)b * p.S * 2 * DP_D + rank * DP_HD, p.S, 0, kbias, p.scale,
-                   av + rank * DP_HD);
-      DP_SYNC(PH_CROSS);
+      attention<T>(sc, red, s_red, qv + rank * DP_HD, W.cross_kv + (long long)b * p.S * 2 * DP_D + rank * DP_HD, p.S, 0, kbias,
+                   p.scale, av + rank * DP_HD, &vb[VB_A], pol_stream, nullptr, nullptr);
+      VEC_WAIT(VB_A, 4 * DP_D, PH_CROSS);
+      {  // the self-attention that comes next: layer l + 1 of this token, or layer 0 of the next one
+        const int nl = l + 1 < p.L ? l + 1 : 0, npos = l + 1 < p.L ? pos : pos + 1;
+        int lo = 0;
+        if (p.window > 0 && npos - p.window > 0) lo = npos - p.window;
+        if (npos - lo > p.pf_self) lo = npos - p.pf_self;  // the newest rows are the ones least likely to be cached
+        prefetch_rows<T>(layers[nl].self_kv + (long long)b * p.Tmax * 2 * DP_D, lo, npos, rank);
+      }
       // P6: s = x1 + cross out_proj(a)
-      load_vec(av, x, nullptr, nullptr, 0.f);
-      gemv_cols<T>(x, W.wc_o, W.bc_o, DP_D, wg, [&](int n, float v) { sv[n] = v + __ldcg(xv + n); });
-      DP_SYNC(PH_COUT);
-      // P7: x2 = LN2(s) -> h = relu(W1 x2 + b1)
-      load_vec(sv, x, W.g2, W.be2, p.ln_eps);
-      gemv_cols<T>(x, W.w1, W.b1, DP_D, wg, [&](int n, float v) { hv[n] = fmaxf(v, 0.f); });
-      if (wg == 0) store_vec(xv, x);  // x2
-      DP_SYNC(PH_FFN1);
+      gemv_phase<T, 2>(R, av, false, nullptr, 0.f, [&](int ch, int j, float v) {
+        const int n = rank * 64 + ch * DP_CH + 2 * warp + j;
+        if (lane < DP_CL) st_async(sv + n, v + xv[n], lane, &vb[VB_S]);
+      });
+      VEC_WAIT(VB_S, 4 * DP_D, PH_COUT);
+      // P7: x2 = LN2(s) (kept in xv for P8's residual) -> h = relu(W1 x2 + b1)
+      gemv_phase<T, 2>(R, sv, true, xv, p.ln_eps, [&](int ch, int j, float v) {
+        const int n = rank * 64 + ch * DP_CH + 2 * warp + j;
+        if (lane < DP_CL) st_async(hv + n, fmaxf(v, 0.f), lane, &vb[VB_H]);
+      });
+      VEC_WAIT(VB_H, 4 * DP_D, PH_FFN1);
       // P8: s = x2 + W2 h + b2
-      load_vec(hv, x, nullptr, nullptr, 0.f);
-      gemv_cols<T>(x, W.w2, W.b2, DP_D, wg, [&](int n, float v) { sv[n] = v + __ldcg(xv + n); });
-      DP_SYNC(PH_FFN2);
+      gemv_phase<T, 2>(R, hv, false, nullptr, 0.f, [&](int ch, int j, float v) {
+        const int n = rank * 64 + ch * DP_CH + 2 * warp + j;
+        if (lane < DP_CL) st_async(sv + n, v + xv[n], lane, &vb[VB_S]);
+      });
+      VEC_WAIT(VB_S, 4 * DP_D, PH_FFN2);
     }
     // ---- classifier on LN3(s) of the last layer, fused with the first-max argmax ----
     {
-      float x[8];
-      load_vec(sv, x, layers[p.L - 1].g3, layers[p.L - 1].be3, p.ln_eps);
       float best = -INFINITY;
       int bi = 0x7fffffff;
-      gemv_cols<T>(x, w_out, p.b_out, p.V, wg, [&](int n, float v) {
+      // a ragged classifier tail (V % 4 columns) cannot travel by bulk copy: its owner warp reads those biases here
+      float tb0 = 0.f, tb1 = 0.f;
+      {
+        const int c0 = (nvch - 1) * DP_CH + 2 * warp, lim = (ncols_v - (nvch - 1) * DP_CH) & ~3;
+        if (nvch > 0 && c0 < ncols_v && 2 * warp >= lim) tb0 = p.b_out[R.vbeg + c0];
+        if (nvch > 0 && c0 + 1 < ncols_v && 2 * warp + 1 >= lim) tb1 = p.b_out[R.vbeg + c0 + 1];
+      }
+      float x[8];
+      if (nvch > 0) {
+        const uint8_t* slot = R.acquire();
+        load_vec(sv, x);
+        const float* gamma = reinterpret_cast<const float*>(slot + Ring<T>::W_BYTES + 128);
+        layer_norm(x, gamma, gamma + DP_D, p.ln_eps);
+      }
+      for (int ch = 0; ch < nvch; ++ch) {
+        const uint8_t* slot = R.acquire();
+        float d0, d1;
+        float2 bias;
+        gemv_slot<T>(slot, x, d0, d1, bias);
+        ++R.consumed;
+        __syncthreads();  // long phase: hand the slot back at once so that the weight stream never drains
+        R.top_up();
+        const int c0 = ch * DP_CH + 2 * warp;
+        if (ch == nvch - 1) {  // columns past the bulk-copied biases: the slot holds stale values there
+          const int lim = (ncols_v - ch * DP_CH) & ~3;
+          if (2 * warp >= lim) bias.x = tb0;
+          if (2 * warp + 1 >= lim) bias.y = tb1;
+        }
+        d0 += bias.x;
+        d1 += bias.y;
         // the per-kernel path rounds logits to the storage type before the argmax; do the same so that ties resolve alike
-        const float r = to_f(from_f<T>(v));
-        if (r > best || (r == best && n < bi)) { best = r; bi = n; }
-      });
+        if (c0 < ncols_v) {
+          const float r = to_f(from_f<T>(d0));
+          if (r > best) { best = r; bi = R.vbeg + c0; }  // columns ascend within a warp: strict > keeps the first max
+        }
+        if (c0 + 1 < ncols_v) {
+          const float r = to_f(from_f<T>(d1));
+          if (r > best) { best = r; bi = R.vbeg + c0 + 1; }
+        }
+      }
       if (lane == 0) { cand_v[warp] = best; cand_i[warp] = bi; }
       __syncthreads();
-      if (threadIdx.x == 0) {
+      if (threadIdx.x < DP_CL) {
+        best = cand_v[0]; bi = cand_i[0];
         for (int w = 1; w < DP_WARPS; ++w)
           if (cand_v[w] > best || (cand_v[w] == best && cand_i[w] < bi)) { best = cand_v[w]; bi = cand_i[w]; }
-        cand[rank * 2] = best;
-        cand[rank * 2 + 1] = __int_as_float(bi);
+        st_cluster(cand + rank * 2, best, threadIdx.x);
+        st_cluster(cand + rank * 2 + 1, __int_as_float(bi), threadIdx.x);
       }
     }
-    DP_SYNC(PH_VOCAB);
+    // the one full cluster barrier of a step (release / acquire at GPU scope): publishes the candidates and orders
+    // this step's cache rows before the reads of the steps to come
+    {
+      cluster_arrive();
+      const long long tb = timed ? clock64() : 0;
+      cluster_wait();
+      if (timed) {
+        const long long now = clock64();
+        tacc[PH_VOCAB] += now - t_prev;
+        tacc[PH_BARRIER] += now - tb;
+        t_prev = now;
+      }
+      R.top_up();
+    }
     // ---- every thread resolves the 4 CTA candidates identically; rank 0 publishes ----
     {
-      float best = __ldcg(cand);
-      int bi = __float_as_int(__ldcg(cand + 1));
+      float best = cand[0];
+      int bi = __float_as_int(cand[1]);
 #pragma unroll
       for (int r = 1; r < DP_CL; ++r) {
-        const float v = __ldcg(cand + 2 * r);
-        const int i = __float_as_int(__ldcg(cand + 2 * r + 1));
+        const float v = cand[2 * r];
+        const int i = __float_as_int(cand[2 * r + 1]);
         if (v > best || (v == best && i < bi)) { best = v; bi = i; }
       }
       tok = bi;
@@ -359,12 +848,20 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_persistent_kernel(DPArgs
         if (fin) p.finished[b] = 1;
       }
     }
-    DP_SYNC(PH_ARGMAX);  // candidates are consumed before the next step overwrites them
+    // the candidates are next written a whole step from here: no barrier needed before the next step
   }
-  if (b == 0 && rank == 0 && threadIdx.x == 0) {
-    int done = p.nsteps;
-    if (pos0 + done > p.Tmax) done = p.Tmax - pos0;
-    *p.pos = pos0 + (done > 0 ? done : 0);
+  // drain the copies issued ahead for a step that an EOS cancelled, then leave together (no CTA may exit while a
+  // peer could still address its shared memory)
+  while (R.consumed < R.issued) {
+    mbar_wait(&full[R.consumed % Ring<T>::NSLOT], (uint32_t)((R.consumed / Ring<T>::NSLOT) & 1));
+    ++R.consumed;
+  }
+  cluster_arrive();
+  cluster_wait();
+  if (b == 0 && rank == 0 && threadIdx.x == 0) *p.pos = pos0 + (nsteps > 0 ? nsteps : 0);
+  if (timed) {
+    for (int i = 0; i < 16; ++i) p.timing[i] += tacc[i];
+    for (int i = 0; i < 8; ++i) p.timing[16 + i] += dbgc[i];
   }
 }
 
@@ -372,7 +869,7 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_persistent_kernel(DPArgs
 
 extern "C" long long omr_decode_persistent_scratch_floats(int B, int H, int D, int V) {
   (void)H; (void)D; (void)V;
-  return (long long)B * DP_SCR + 64;
+  return 64;  // the vectors live in (distributed) shared memory now; kept for ABI stability
 }
 
 extern "C" int omr_decode_persistent(int dt, const void* layers_dev, int L, const void* emb, const float* pe, const void* w_out,
@@ -384,8 +881,9 @@ extern "C" int omr_decode_persistent(int dt, const void* layers_dev, int L, cons
   OMR_REQUIRE(D == DP_D && H == DP_H, "omr_decode_persistent: d_model must be 256 with 4 heads of 64");
   OMR_REQUIRE(B >= 1, "omr_decode_persistent: empty batch");
   OMR_REQUIRE(L >= 1 && V >= 1 && S >= 1 && Tmax >= 1 && nsteps >= 0, "omr_decode_persistent: bad sizes");
+  OMR_REQUIRE((long long)nsteps * (16LL * L + V / 32 + 2) < (1LL << 30), "omr_decode_persistent: step budget too large");
   OMR_REQUIRE(dt == OMR_BF16 || dt == OMR_F32, "omr_decode_persistent: bad dtype");
-  OMR_REQUIRE(scratch_floats >= (long long)B * DP_SCR, "omr_decode_persistent: scratch too small");
+  (void)scratch_floats;
   if (nsteps == 0) return OMR_OK;
   cudaStream_t st = as_stream(stream);
   DPArgs p{};
@@ -393,10 +891,24 @@ extern "C" int omr_decode_persistent(int dt, const void* layers_dev, int L, cons
   p.B = B; p.V = V; p.S = S; p.Tmax = Tmax; p.nsteps = nsteps; p.window = window;
   p.tok = tok; p.val = val; p.finished = finished; p.out_tokens = out_tokens; p.out_vals = out_vals; p.out_ld = out_ld; p.pos = pos;
   p.eos = eos; p.pad = pad; p.mem_bias = mem_bias; p.mem_bias_bs = mem_bias_bs; p.ln_eps = ln_eps; p.scale = 0.125f;
-  p.scratch = scratch; p.timing = timing;
+  p.timing = timing;
+  (void)scratch;
+  {
+    static int pf[2] = {-1, -1};
+    if (pf[0] < 0) {
+      const char* a = getenv("OMR_DECODE_PF_CROSS");
+      const char* c = getenv("OMR_DECODE_PF_SELF");
+      pf[0] = a ? atoi(a) : 1024;
+      pf[1] = c ? atoi(c) : 4096;
+    }
+    p.pf_cross = pf[0]; p.pf_self = pf[1];
+  }
   const int max_keys = S > Tmax ? S : Tmax;
-  const size_t smem = sizeof(float) * ((size_t)((max_keys + 3) & ~3) + DP_KL * DP_HD + 16);
-  OMR_REQUIRE(smem <= 200 * 1024, "omr_decode_persistent: memory / sequence too long for the score buffer (%zu B)", smem);
+  p.sc_floats = (max_keys + 15) & ~15;
+  // weight ring | vectors + candidates | 8 slot barriers | reduction scratch | scores | key-lane partials
+  const size_t ring = dt == OMR_BF16 ? Ring<bf16>::BYTES : Ring<float>::BYTES;
+  const size_t smem = ring + sizeof(float) * ((size_t)DP_VEC + 24 + 40 + (size_t)p.sc_floats + DP_KL * DP_HD) + (size_t)L * sizeof(LayerW<bf16>);
+  OMR_REQUIRE(smem <= 226 * 1024, "omr_decode_persistent: memory / sequence too long for the score buffer (%zu B)", smem);
   static bool cfg[2] = {false, false};
   cudaLaunchConfig_t lc{};
   lc.gridDim = dim3((unsigned)(B * DP_CL));
@@ -408,10 +920,10 @@ extern "C" int omr_decode_persistent(int dt, const void* layers_dev, int L, cons
   attr[0].val.clusterDim.x = DP_CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   lc.attrs = attr; lc.numAttrs = 1;
   if (dt == OMR_BF16) {
-    if (!cfg[1]) { OMR_CUDA(cudaFuncSetAttribute(decode_persistent_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); cfg[1] = true; }
+    if (!cfg[1]) { OMR_CUDA(cudaFuncSetAttribute(decode_persistent_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024)); cfg[1] = true; }
     OMR_CUDA(cudaLaunchKernelEx(&lc, decode_persistent_kernel<bf16>, p));
   } else {
-    if (!cfg[0]) { OMR_CUDA(cudaFuncSetAttribute(decode_persistent_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); cfg[0] = true; }
+    if (!cfg[0]) { OMR_CUDA(cudaFuncSetAttribute(decode_persistent_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024)); cfg[0] = true; }
     OMR_CUDA(cudaLaunchKernelEx(&lc, decode_persistent_kernel<float>, p));
   }
   omr_count_launch();

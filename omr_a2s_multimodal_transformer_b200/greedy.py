@@ -124,7 +124,7 @@ class BatchedGreedyDecoder:
         mem_bias = st["mem_bias"]
         s_len = cross_kv[0].shape[1]
         tmax = st["self_kv"][0].shape[1]
-        timing = torch.zeros(16, dtype=torch.int64, device=dev) if os.environ.get("OMR_DECODE_TIMING") else None
+        timing = torch.zeros(32, dtype=torch.int64, device=dev) if os.environ.get("OMR_DECODE_TIMING") else None
         _lib.call("omr_decode_persistent", _lib.dt_code(dtype), ptr(table), len(cross_kv), ptr(table_emb),
                   ptr(dec.pos_1d.pe), ptr(wout), ptr(dec.out_layer.bias), b, dec.nhead, d, dec.output_size, s_len, tmax, steps,
                   dec.attn_window if dec.attn_window and dec.attn_window > 0 else 0, ptr(st["tok"]), ptr(st["val"]),
@@ -139,6 +139,9 @@ class BatchedGreedyDecoder:
         if timing is not None:
             names = ["embed", "qkv", "self_attn", "out_proj", "cross_q", "cross_attn", "cross_out", "ffn1", "ffn2", "classifier", "argmax"]
             cyc = timing.cpu().tolist()
+            print(f"[decode timing] of which cluster-barrier wait {cyc[11] / max(done, 1):.0f}, weight-ring wait {cyc[12] / max(done, 1):.0f}, ring top-up at barriers {cyc[13] / max(done, 1):.0f}, barrier arrive (release) {cyc[14] / max(done, 1):.0f} cycles per step")
+            print("[decode timing] out_proj phase detail (acquire, load/LN, acquire2, gemv, epilogue):", [round(c / max(done, 1)) for c in cyc[16:21]])
+            cyc = cyc[:11]
             tot = sum(cyc) or 1
             print("[decode timing, SM cycles per step on CTA 0] " + ", ".join(
                 f"{n} {c / max(done, 1):.0f} ({100 * c / tot:.0f}%)" for n, c in zip(names, cyc)) + f" | total {tot / max(done, 1):.0f}")

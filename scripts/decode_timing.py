@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Per-phase cycle counters of the persistent decode kernel (OMR_DECODE_TIMING=1) at BASELINE config 4 per-GPU size."""
 import os, sys
-os.environ["OMR_DECODE_TIMING"] = "1"
+if "--no-timing" not in sys.argv:
+    os.environ["OMR_DECODE_TIMING"] = "1"
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import bench
@@ -13,7 +14,7 @@ dev = torch.device("cuda", 0)
 m = pkg.MultimodalTransformer(128, 1024, 195, 808, 1268, w2i, i2w).to(dev).eval()
 m.set_compute_dtype(torch.bfloat16)
 xi, _, xa, _, _, _ = bench.make_batch(32, w2i, seed=500)
-steps = int(sys.argv[1]) if len(sys.argv) > 1 else 1268
+steps = int(sys.argv[1]) if len(sys.argv) > 1 and sys.argv[1].isdigit() else 1268
 with torch.no_grad():
     mem, _ = m._memory(xi.to(dev), xa.to(dev), None, None, "both")
     r = m._decoder_runner()
