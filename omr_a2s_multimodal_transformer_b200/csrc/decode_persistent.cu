@@ -153,24 +153,30 @@ __device__ __forceinline__ void prefetch_rows(const T* base, int r0, int r1, int
 // ---- the weight ring -------------------------------------------------------------------------------------------
 // Slot g % NSLOT holds the g-th chunk of the fixed consumption order (per step: L layers x 16 chunks, then the CTA's
 // share of the classifier): 32 weight rows, their 32 biases and -- with the first chunk of a projection that reads a
-// LayerNorm output -- that LayerNorm's scale and shift.  `consumed` / `issued` are tracked identically by every thread;
-// only thread 0 copies.  Nothing a projection phase needs is fetched from global memory on its critical path.
+// LayerNorm output -- that LayerNorm's scale and shift.  Nothing a projection phase needs is fetched from global memory
+// on its critical path.  Producer / consumer protocol: full[s] (tx-count mbarrier) says the slot's copies have landed;
+// every warp arrives on empty[s] once it has read the slot; warp s owns slot s and refills it -- DEFER chunks later, so
+// that the wait on empty[s] is over before it starts -- from a descriptor table built once in shared memory.
 constexpr int DP_PAR = 128 + 2 * DP_D * 4;  // bytes of the parameter tail of a slot: bias[32] | gamma[256] | beta[256]
+struct ChunkDesc {  // one entry per chunk of a step
+  const void* w; const float* bias; const float* gamma; const float* beta;
+  uint32_t wbytes, bbytes;
+};
 template <typename T>
 struct Ring {
   static constexpr int W_BYTES = DP_CH * DP_D * (int)sizeof(T);
   static constexpr int SLOT_BYTES = W_BYTES + DP_PAR;
   static constexpr int NSLOT = sizeof(T) == 2 ? 8 : 4;
+  static constexpr int DEFER = sizeof(T) == 2 ? 2 : 1;
   static constexpr int BYTES = NSLOT * SLOT_BYTES;
   uint8_t* base;
-  uint64_t* full;
-  const LayerW<T>* layers;  // shared-memory copy of the layer table
-  const T* w_out;
-  const float* b_out;
+  uint64_t *full, *empty;
+  const ChunkDesc* desc;    // [cps]
   uint64_t pol;             // L2 evict-last: the weights are re-read by every cluster, every step
   long long* t_wait;        // optional cycle counter of the time spent waiting for a slot
-  int L, rank, cps, vbeg, vend;
-  int consumed, issued, limit;  // chunk counters (nsteps x cps fits 31 bits: checked by the launcher)
+  int cps;                  // chunks per step
+  int consumed, limit;      // chunk counters (nsteps x cps fits 31 bits: checked by the launcher)
+  int next_k;               // this warp's slot: index (mod cps) of the chunk it issues next
 
   __device__ __forceinline__ void copy(uint8_t* dst, const void* src, uint32_t bytes, uint64_t* bar) const {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
@@ -178,69 +184,39 @@ struct Ring {
                  "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
                  : "memory");
   }
-  // call only right after a barrier every warp of the CTA has passed: all chunks < consumed are then free.
-  // Issuing a bulk copy costs its thread a few hundred cycles, so the work is spread: the chunk for slot s is issued by
-  // warp s, its (up to four) copies by four lanes side by side (complete_tx may precede expect_tx on an mbarrier).
-  __device__ __forceinline__ void top_up() {
-    int target = consumed + NSLOT;
-    if (target > limit) target = limit;
-    if (target <= issued) return;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (warp < NSLOT && lane < 4) {
-      // the one chunk in [issued, target) that lands in slot `warp`
-      const int g = issued + ((warp - issued % NSLOT) + NSLOT) % NSLOT;
-      if (g < target) {
-        const int k = g % cps;
-        const T* src;
-        const float *bias, *gamma = nullptr, *beta = nullptr;
-        int rows = DP_CH, brows = DP_CH;
-        if (k < DP_LCH * L) {
-          const int l = k / DP_LCH, c = k % DP_LCH;
-          const LayerW<T>& W = layers[l];
-          if (c < 6) {
-            src = W.w_in + (long long)(rank * 192 + c * DP_CH) * DP_D;
-            bias = W.b_in + rank * 192 + c * DP_CH;
-            if (c == 0 && l > 0) { gamma = layers[l - 1].g3; beta = layers[l - 1].be3; }
-          } else {
-            const int ph = (c - 6) >> 1, hf = (c - 6) & 1;
-            const T* w = ph == 0 ? W.w_o : ph == 1 ? W.wc_q : ph == 2 ? W.wc_o : ph == 3 ? W.w1 : W.w2;
-            const float* bb = ph == 0 ? W.b_o : ph == 1 ? W.bc_q : ph == 2 ? W.bc_o : ph == 3 ? W.b1 : W.b2;
-            src = w + (long long)(rank * 64 + hf * DP_CH) * DP_D;
-            bias = bb + rank * 64 + hf * DP_CH;
-            if (hf == 0 && ph == 1) { gamma = W.g1; beta = W.be1; }
-            if (hf == 0 && ph == 3) { gamma = W.g2; beta = W.be2; }
-          }
-        } else {
-          const int c = k - DP_LCH * L, r0 = vbeg + c * DP_CH;
-          rows = vend - r0 < DP_CH ? vend - r0 : DP_CH;
-          brows = rows & ~3;  // bulk copies move multiples of 16 bytes; a ragged tail is read directly by its warp
-          src = w_out + (long long)r0 * DP_D;
-          bias = b_out + r0;
-          if (c == 0) { gamma = layers[L - 1].g3; beta = layers[L - 1].be3; }
-        }
-        const uint32_t wbytes = (uint32_t)rows * DP_D * (uint32_t)sizeof(T);
-        uint8_t* dst = base + (size_t)warp * SLOT_BYTES;
-        uint64_t* bar = &full[warp];
-        if (lane == 0) {
-          mbar_expect_tx(bar, wbytes + (uint32_t)brows * 4u + (gamma ? 2u * DP_D * 4u : 0u));
-          copy(dst, src, wbytes, bar);
-        } else if (lane == 1) {
-          if (brows) copy(dst + W_BYTES, bias, (uint32_t)brows * 4u, bar);
-        } else if (gamma) {
-          if (lane == 2) copy(dst + W_BYTES + 128, gamma, DP_D * 4, bar);
-          else copy(dst + W_BYTES + 128 + DP_D * 4, beta, DP_D * 4, bar);
-        }
+  // chunks issued once `consumed` chunks have been read (identical in every thread)
+  __device__ __forceinline__ int issued() const {
+    const int i = NSLOT + (consumed > DEFER ? consumed - DEFER : 0);
+    return i < limit ? i : limit;
+  }
+  // warp `slot` (lanes 0..3 side by side; complete_tx may precede expect_tx on an mbarrier) copies its next chunk
+  __device__ __forceinline__ void issue(int slot) {
+    const int lane = threadIdx.x & 31;
+    if (lane < 4) {
+      const ChunkDesc d = desc[next_k];
+      uint8_t* dst = base + (size_t)slot * SLOT_BYTES;
+      uint64_t* bar = &full[slot];
+      if (lane == 0) {
+        mbar_expect_tx(bar, d.wbytes + d.bbytes + (d.gamma ? 2u * DP_D * 4u : 0u));
+        copy(dst, d.w, d.wbytes, bar);
+      } else if (lane == 1) {
+        if (d.bbytes) copy(dst + W_BYTES, d.bias, d.bbytes, bar);
+      } else if (d.gamma) {
+        if (lane == 2) copy(dst + W_BYTES + 128, d.gamma, DP_D * 4, bar);
+        else copy(dst + W_BYTES + 128 + DP_D * 4, d.beta, DP_D * 4, bar);
       }
-      __syncwarp(0xfu);
     }
-    issued = target;
+    next_k += NSLOT;
+    while (next_k >= cps) next_k -= cps;
+  }
+  __device__ __forceinline__ void prime() {  // the first NSLOT chunks
+    const int warp = threadIdx.x >> 5;
+    next_k = warp;
+    while (next_k >= cps) next_k -= cps;
+    if (warp < NSLOT && warp < limit) issue(warp);
   }
   // wait for the next chunk; returns its slot
   __device__ __forceinline__ const uint8_t* acquire() {
-    if (consumed >= issued) {  // ring smaller than the phase: recycle inside it (uniform branch)
-      __syncthreads();
-      top_up();
-    }
     const int slot = consumed % NSLOT;
     if (t_wait) {
       const long long t0 = clock64();
@@ -250,6 +226,18 @@ struct Ring {
       mbar_wait(&full[slot], (uint32_t)((consumed / NSLOT) & 1));
     }
     return base + (size_t)slot * SLOT_BYTES;
+  }
+  // this warp has the slot's values in registers: hand the slot back; its owner refills the slot freed DEFER chunks ago
+  __device__ __forceinline__ void release() {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __syncwarp();
+    if (lane == 0) tc::mbar_arrive(&empty[consumed % NSLOT]);
+    ++consumed;
+    const int r = consumed - 1 - DEFER;  // chunk whose slot is refilled now, with chunk r + NSLOT
+    if (r >= 0 && r + NSLOT < limit && warp == r % NSLOT) {
+      mbar_wait(&empty[warp], (uint32_t)((r / NSLOT) & 1));
+      issue(warp);
+    }
   }
 };
 
@@ -326,7 +314,7 @@ __device__ __forceinline__ void gemv_phase(Ring<T>& R, const float* xs, bool LN,
     float d0, d1;
     float2 bias;
     gemv_slot<T>(slot, x, d0, d1, bias);
-    ++R.consumed;
+    R.release();
     if (dbg) { long long t = clock64(); dbg[3] += t - t0; t0 = t; }
     epi(ch, 0, d0 + bias.x);
     epi(ch, 1, d1 + bias.y);
@@ -607,8 +595,6 @@ enum { VB_Q = 0, VB_A, VB_S, VB_H };  // the exchanged vectors and their mbarrie
       tacc[PH_BARRIER] += now - tb;                                \
       t_prev = now;                                                \
     }                                                              \
-    R.top_up();                                                    \
-    if (timed) tacc[13] += clock64() - t_prev;                     \
   } while (0)
 
 template <typename T>
@@ -618,12 +604,13 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_persistent_kernel(DPArgs
   float *xv = vecs, *sv = vecs + DP_D, *qv = vecs + 2 * DP_D, *av = vecs + 3 * DP_D, *hv = vecs + 4 * DP_D;
   float *kn = vecs + 5 * DP_D, *vn = kn + DP_HD;  // this head's K / V row of the token being decoded
   float* cand = vn + DP_HD;                      // [4][2] per-CTA argmax candidates
-  uint64_t* full = reinterpret_cast<uint64_t*>(vecs + DP_VEC);  // [8] ring slots
-  uint64_t* vb = full + 8;                       // [4] exchanged vectors
+  uint64_t* full = reinterpret_cast<uint64_t*>(vecs + DP_VEC);  // [8] ring slots: data landed; [8] more: slot read by all warps
+  uint64_t* vb = full + 16;                      // [4] exchanged vectors
   float* s_red = reinterpret_cast<float*>(vb + 4);   // [40]
   float* sc = s_red + 40;                        // [sc_floats] attention scores
   float* red = sc + p.sc_floats;                 // [DP_KL][64] key-lane partials
   LayerW<T>* layers = reinterpret_cast<LayerW<T>*>(red + DP_KL * DP_HD);  // [L] copy of the layer table
+  ChunkDesc* desc = reinterpret_cast<ChunkDesc*>(layers + p.L);            // [16 L + classifier chunks]
   __shared__ float cand_v[DP_WARPS];
   __shared__ int cand_i[DP_WARPS];
   __shared__ long long dbgc[8];
@@ -650,28 +637,63 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_persistent_kernel(DPArgs
     uint32_t* dst = reinterpret_cast<uint32_t*>(layers);
     for (int i = threadIdx.x; i < p.L * (int)(sizeof(LayerW<T>) / 4); i += DP_THREADS) dst[i] = src[i];
   }
-  Ring<T> R;
-  R.base = smem_raw; R.full = full; R.layers = layers; R.w_out = reinterpret_cast<const T*>(p.w_out); R.b_out = p.b_out;
-  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(R.pol));
-  R.t_wait = timed ? tacc + PH_RING : nullptr;
-  R.L = p.L; R.rank = rank;
+  const T* w_out = reinterpret_cast<const T*>(p.w_out);
+  int vbeg, vend;
   {
     const int vq = (((p.V + DP_CL - 1) / DP_CL) + DP_CH - 1) / DP_CH * DP_CH;  // classifier columns per CTA
-    R.vbeg = rank * vq < p.V ? rank * vq : p.V;
-    R.vend = R.vbeg + vq < p.V ? R.vbeg + vq : p.V;
+    vbeg = rank * vq < p.V ? rank * vq : p.V;
+    vend = vbeg + vq < p.V ? vbeg + vq : p.V;
   }
-  const int ncols_v = R.vend - R.vbeg;
+  const int ncols_v = vend - vbeg;
   const int nvch = (ncols_v + DP_CH - 1) / DP_CH;
+  Ring<T> R;
+  R.base = smem_raw; R.full = full; R.empty = full + 8; R.desc = desc;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(R.pol));
+  R.t_wait = timed ? tacc + PH_RING : nullptr;
   R.cps = DP_LCH * p.L + nvch;
-  R.consumed = 0; R.issued = 0;
+  R.consumed = 0;
   R.limit = (fin || nsteps <= 0) ? 0 : nsteps * R.cps;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < Ring<T>::NSLOT; ++s) mbar_init(&full[s], 1);
+    for (int s = 0; s < Ring<T>::NSLOT; ++s) { mbar_init(&full[s], 1); mbar_init(&full[8 + s], DP_WARPS); }
     for (int s = 0; s < 4; ++s) mbar_init(&vb[s], 1);
     tc::fence_barrier_init();
   }
+  __syncthreads();  // the layer table is complete
+  // descriptor of every chunk of a step, in consumption order
+  for (int k = threadIdx.x; k < R.cps; k += DP_THREADS) {
+    ChunkDesc d;
+    d.gamma = nullptr; d.beta = nullptr;
+    int rows = DP_CH, brows = DP_CH;
+    if (k < DP_LCH * p.L) {
+      const int l = k / DP_LCH, c = k % DP_LCH;
+      const LayerW<T>& W = layers[l];
+      if (c < 6) {
+        d.w = W.w_in + (long long)(rank * 192 + c * DP_CH) * DP_D;
+        d.bias = W.b_in + rank * 192 + c * DP_CH;
+        if (c == 0 && l > 0) { d.gamma = layers[l - 1].g3; d.beta = layers[l - 1].be3; }
+      } else {
+        const int ph = (c - 6) >> 1, hf = (c - 6) & 1;
+        const T* w = ph == 0 ? W.w_o : ph == 1 ? W.wc_q : ph == 2 ? W.wc_o : ph == 3 ? W.w1 : W.w2;
+        const float* bb = ph == 0 ? W.b_o : ph == 1 ? W.bc_q : ph == 2 ? W.bc_o : ph == 3 ? W.b1 : W.b2;
+        d.w = w + (long long)(rank * 64 + hf * DP_CH) * DP_D;
+        d.bias = bb + rank * 64 + hf * DP_CH;
+        if (hf == 0 && ph == 1) { d.gamma = W.g1; d.beta = W.be1; }
+        if (hf == 0 && ph == 3) { d.gamma = W.g2; d.beta = W.be2; }
+      }
+    } else {
+      const int c = k - DP_LCH * p.L, r0 = vbeg + c * DP_CH;
+      rows = vend - r0 < DP_CH ? vend - r0 : DP_CH;
+      brows = rows & ~3;  // bulk copies move multiples of 16 bytes; a ragged tail is read directly by its warp
+      d.w = w_out + (long long)r0 * DP_D;
+      d.bias = p.b_out + r0;
+      if (c == 0) { d.gamma = layers[p.L - 1].g3; d.beta = layers[p.L - 1].be3; }
+    }
+    d.wbytes = (uint32_t)rows * DP_D * (uint32_t)sizeof(T);
+    d.bbytes = (uint32_t)brows * 4u;
+    desc[k] = d;
+  }
   __syncthreads();
-  R.top_up();
+  R.prime();
   cluster_arrive();  // every CTA of the cluster is resident, its barriers initialised, before the first remote store
   cluster_wait();
   long long t_prev = clock64();
@@ -766,8 +788,8 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_persistent_kernel(DPArgs
       float tb0 = 0.f, tb1 = 0.f;
       {
         const int c0 = (nvch - 1) * DP_CH + 2 * warp, lim = (ncols_v - (nvch - 1) * DP_CH) & ~3;
-        if (nvch > 0 && c0 < ncols_v && 2 * warp >= lim) tb0 = p.b_out[R.vbeg + c0];
-        if (nvch > 0 && c0 + 1 < ncols_v && 2 * warp + 1 >= lim) tb1 = p.b_out[R.vbeg + c0 + 1];
+        if (nvch > 0 && c0 < ncols_v && 2 * warp >= lim) tb0 = p.b_out[vbeg + c0];
+        if (nvch > 0 && c0 + 1 < ncols_v && 2 * warp + 1 >= lim) tb1 = p.b_out[vbeg + c0 + 1];
       }
       float x[8];
       if (nvch > 0) {
@@ -781,9 +803,7 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_persistent_kernel(DPArgs
         float d0, d1;
         float2 bias;
         gemv_slot<T>(slot, x, d0, d1, bias);
-        ++R.consumed;
-        __syncthreads();  // long phase: hand the slot back at once so that the weight stream never drains
-        R.top_up();
+        R.release();
         const int c0 = ch * DP_CH + 2 * warp;
         if (ch == nvch - 1) {  // columns past the bulk-copied biases: the slot holds stale values there
           const int lim = (ncols_v - ch * DP_CH) & ~3;
@@ -795,11 +815,11 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_persistent_kernel(DPArgs
         // the per-kernel path rounds logits to the storage type before the argmax; do the same so that ties resolve alike
         if (c0 < ncols_v) {
           const float r = to_f(from_f<T>(d0));
-          if (r > best) { best = r; bi = R.vbeg + c0; }  // columns ascend within a warp: strict > keeps the first max
+          if (r > best) { best = r; bi = vbeg + c0; }  // columns ascend within a warp: strict > keeps the first max
         }
         if (c0 + 1 < ncols_v) {
           const float r = to_f(from_f<T>(d1));
-          if (r > best) { best = r; bi = R.vbeg + c0 + 1; }
+          if (r > best) { best = r; bi = vbeg + c0 + 1; }
         }
       }
       if (lane == 0) { cand_v[warp] = best; cand_i[warp] = bi; }
@@ -824,7 +844,6 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_persistent_kernel(DPArgs
         tacc[PH_BARRIER] += now - tb;
         t_prev = now;
       }
-      R.top_up();
     }
     // ---- every thread resolves the 4 CTA candidates identically; rank 0 publishes ----
     {
@@ -852,10 +871,8 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_persistent_kernel(DPArgs
   }
   // drain the copies issued ahead for a step that an EOS cancelled, then leave together (no CTA may exit while a
   // peer could still address its shared memory)
-  while (R.consumed < R.issued) {
-    mbar_wait(&full[R.consumed % Ring<T>::NSLOT], (uint32_t)((R.consumed / Ring<T>::NSLOT) & 1));
-    ++R.consumed;
-  }
+  for (int g = R.consumed, e = R.issued(); g < e; ++g)
+    mbar_wait(&full[g % Ring<T>::NSLOT], (uint32_t)((g / Ring<T>::NSLOT) & 1));
   cluster_arrive();
   cluster_wait();
   if (b == 0 && rank == 0 && threadIdx.x == 0) *p.pos = pos0 + (nsteps > 0 ? nsteps : 0);
@@ -907,7 +924,8 @@ extern "C" int omr_decode_persistent(int dt, const void* layers_dev, int L, cons
   p.sc_floats = (max_keys + 15) & ~15;
   // weight ring | vectors + candidates | 8 slot barriers | reduction scratch | scores | key-lane partials
   const size_t ring = dt == OMR_BF16 ? Ring<bf16>::BYTES : Ring<float>::BYTES;
-  const size_t smem = ring + sizeof(float) * ((size_t)DP_VEC + 24 + 40 + (size_t)p.sc_floats + DP_KL * DP_HD) + (size_t)L * sizeof(LayerW<bf16>);
+  const size_t smem = ring + sizeof(float) * ((size_t)DP_VEC + 40 + 40 + (size_t)p.sc_floats + DP_KL * DP_HD) + (size_t)L * sizeof(LayerW<bf16>) +
+                      (size_t)(DP_LCH * L + (V / DP_CL + 2 * DP_CH) / DP_CH + 1) * sizeof(ChunkDesc);
   OMR_REQUIRE(smem <= 226 * 1024, "omr_decode_persistent: memory / sequence too long for the score buffer (%zu B)", smem);
   static bool cfg[2] = {false, false};
   cudaLaunchConfig_t lc{};
