@@ -69,6 +69,7 @@ struct DPArgs {
   long long* timing;   // optional [16] cycle counters per phase kind (cluster 0, rank 0), NULL = off
   int sc_floats;       // floats reserved for the attention scores
   int pf_cross, pf_self;  // rows of the next attention's K/V stream that are prefetched into L2 one phase ahead
+  int stagger_ns;         // start delay per cluster (x cluster index mod 8): de-phases the clusters' HBM bursts
 };
 
 // 8 consecutive elements as raw registers (so that many independent 16-byte loads can be in flight per thread)
@@ -696,6 +697,12 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_persistent_kernel(DPArgs
   R.prime();
   cluster_arrive();  // every CTA of the cluster is resident, its barriers initialised, before the first remote store
   cluster_wait();
+  // All clusters do identical work and would stay in lockstep: every attention phase a chip-wide HBM burst, every
+  // projection phase an idle bus.  A one-off start offset spreads the phases of different samples over time.
+  if (p.stagger_ns > 0) {
+    const long long until = clock64() + (long long)(b & 7) * p.stagger_ns * 2;  // ~2 cycles per ns
+    while (clock64() < until) __nanosleep(200);
+  }
   long long t_prev = clock64();
 
   for (int step = 0; step < nsteps && !fin; ++step) {
@@ -911,14 +918,16 @@ extern "C" int omr_decode_persistent(int dt, const void* layers_dev, int L, cons
   p.timing = timing;
   (void)scratch;
   {
-    static int pf[2] = {-1, -1};
+    static int pf[3] = {-1, -1, -1};
     if (pf[0] < 0) {
       const char* a = getenv("OMR_DECODE_PF_CROSS");
       const char* c = getenv("OMR_DECODE_PF_SELF");
-      pf[0] = a ? atoi(a) : 1024;
+      const char* d = getenv("OMR_DECODE_STAGGER_NS");
+      pf[0] = a ? atoi(a) : 2400;
       pf[1] = c ? atoi(c) : 4096;
+      pf[2] = d ? atoi(d) : 0;
     }
-    p.pf_cross = pf[0]; p.pf_self = pf[1];
+    p.pf_cross = pf[0]; p.pf_self = pf[1]; p.stagger_ns = pf[2];
   }
   const int max_keys = S > Tmax ? S : Tmax;
   p.sc_floats = (max_keys + 15) & ~15;
