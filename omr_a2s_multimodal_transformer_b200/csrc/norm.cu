@@ -7,43 +7,95 @@ namespace {
 // ---------------------------------------------------------------------------------------------
 // InstanceNorm: per-(n,c) statistics over HW.  Phase 1 accumulates two sums per (n,c) with one
 // atomicAdd pair per block; phase 2 turns them into (mean, rstd) / applies them.
+// Both phases see a sample as a flat array of HW*C elements walked with 16-byte accesses; the grid
+// stride is a multiple of C, so a thread keeps ONE group of 16/sizeof(T) channels for its whole life
+// (statistics in registers, no index arithmetic in the loop) and several loads are in flight per thread.
 // ---------------------------------------------------------------------------------------------
+template <typename T> struct V16;
+template <> struct V16<bf16> {
+  static constexpr int N = 8;
+  static __device__ __forceinline__ void load(const bf16* p, float (&v)[8]) {
+    const uint4 t = *reinterpret_cast<const uint4*>(p);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { v[2 * i] = __low2float(h[i]); v[2 * i + 1] = __high2float(h[i]); }
+  }
+  static __device__ __forceinline__ void store(bf16* p, const float (&v)[8]) {
+    uint4 t;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&t);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    *reinterpret_cast<uint4*>(p) = t;
+  }
+};
+template <> struct V16<float> {
+  static constexpr int N = 4;
+  static __device__ __forceinline__ void load(const float* p, float (&v)[4]) {
+    const float4 t = *reinterpret_cast<const float4*>(p);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  }
+  static __device__ __forceinline__ void store(float* p, const float (&v)[4]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+};
+
+constexpr int IN_UNROLL = 4;
+
 // MODE 0: (sum x, sum x^2).  MODE 1: (sum dy, sum dy * xhat) with xhat from saved stats.
+// grid (blocks per sample, N); requires (256 * VEC) % C == 0.
 template <typename T, int MODE>
 __global__ void __launch_bounds__(256) in_partial_kernel(const T* __restrict__ a, const T* __restrict__ xin,
                                                          const float* __restrict__ stats, double* __restrict__ out,
-                                                         int HW, int C, int CT, int rows_per_block) {
-  __shared__ float sm0[256], sm1[256];
+                                                         long long per_sample, int C) {
+  constexpr int VEC = V16<T>::N;
+  __shared__ float sm0[256 * VEC], sm1[256 * VEC];
   const int n = blockIdx.y;
-  const int RS = 256 / CT;
-  const int cl = threadIdx.x % CT, rl = threadIdx.x / CT;
-  const int c = blockIdx.z * CT + cl;
-  long long r0 = (long long)blockIdx.x * rows_per_block;
-  long long r1 = r0 + rows_per_block;
-  if (r1 > HW) r1 = HW;
-  float mean = 0.f, rstd = 0.f;
-  if (MODE == 1) {
-    mean = stats[((long long)n * C + c) * 2];
-    rstd = stats[((long long)n * C + c) * 2 + 1];
-  }
-  float s0 = 0.f, s1 = 0.f;
-  const long long base = (long long)n * HW;
-  for (long long r = r0 + rl; r < r1; r += RS) {
-    float v = to_f(a[(base + r) * C + c]);
-    if (MODE == 0) {
-      s0 += v; s1 = fmaf(v, v, s1);
-    } else {
-      float xh = (to_f(xin[(base + r) * C + c]) - mean) * rstd;
-      s0 += v; s1 = fmaf(v, xh, s1);
+  const long long step = (long long)gridDim.x * 256 * VEC;
+  long long e = ((long long)blockIdx.x * 256 + threadIdx.x) * VEC;
+  const int c0 = (int)(e % C);
+  const T* ap = a + (long long)n * per_sample;
+  const T* xp = MODE == 1 ? xin + (long long)n * per_sample : nullptr;
+  float mean[VEC], rstd[VEC], s0[VEC], s1[VEC];
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) {
+    s0[k] = 0.f; s1[k] = 0.f;
+    if (MODE == 1) {
+      mean[k] = stats[((long long)n * C + c0 + k) * 2];
+      rstd[k] = stats[((long long)n * C + c0 + k) * 2 + 1];
     }
   }
-  sm0[threadIdx.x] = s0; sm1[threadIdx.x] = s1;
+  for (; e < per_sample; e += step * IN_UNROLL) {
+    float v[IN_UNROLL][VEC], x[IN_UNROLL][VEC];
+#pragma unroll
+    for (int u = 0; u < IN_UNROLL; ++u) {
+      const long long eu = e + u * step;
+      if (eu < per_sample) {
+        V16<T>::load(ap + eu, v[u]);
+        if (MODE == 1) V16<T>::load(xp + eu, x[u]);
+      } else {
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) { v[u][k] = 0.f; if (MODE == 1) x[u][k] = mean[k]; }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < IN_UNROLL; ++u)
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) {
+        s0[k] += v[u][k];
+        if (MODE == 0) s1[k] = fmaf(v[u][k], v[u][k], s1[k]);
+        else s1[k] = fmaf(v[u][k], (x[u][k] - mean[k]) * rstd[k], s1[k]);
+      }
+  }
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) { sm0[threadIdx.x * VEC + k] = s0[k]; sm1[threadIdx.x * VEC + k] = s1[k]; }
   __syncthreads();
-  if (rl == 0) {
-    // block partials are combined in double: the variance E[x^2] - E[x]^2 and the backward's mean
-    // subtractions are cancellation-prone, and fp32 parity (1e-4 on gradients) needs them clean
-    double d0 = s0, d1 = s1;
-    for (int k = 1; k < RS; ++k) { d0 += (double)sm0[k * CT + cl]; d1 += (double)sm1[k * CT + cl]; }
+  // thread t's channel group starts at (t * VEC) % C: channel c lives in the slots c, c + C, c + 2C, ... of the block's
+  // 256 * VEC values.  Block partials are combined in double: the variance E[x^2] - E[x]^2 and the backward's mean
+  // subtractions are cancellation-prone, and fp32 parity (1e-4 on gradients) needs them clean.
+  // (blockIdx.x * 256 * VEC is a multiple of C, so the block offset does not shift the mapping.)
+  for (int c = threadIdx.x; c < C; c += 256) {
+    double d0 = 0.0, d1 = 0.0;
+    for (int i = c; i < 256 * VEC; i += C) { d0 += (double)sm0[i]; d1 += (double)sm1[i]; }
     atomicAdd(out + ((long long)n * C + c) * 2, d0);
     atomicAdd(out + ((long long)n * C + c) * 2 + 1, d1);
   }
@@ -61,52 +113,81 @@ __global__ void in_finalize_kernel(const double* __restrict__ sums, float* __res
   }
 }
 
+// grid (blocks per sample, N); requires (256 * VEC) % C == 0
 template <typename T>
-__global__ void in_apply_fwd_kernel(const T* __restrict__ x, const float* __restrict__ stats, T* __restrict__ y, int N,
-                                    int HW, int C) {
-  const int c4n = C / 4;
-  long long total = (long long)N * HW * c4n;
-  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  long long stride = (long long)gridDim.x * blockDim.x;
-  for (; i < total; i += stride) {
-    int c4 = (int)(i % c4n);
-    long long p = i / c4n;
-    int n = (int)(p / HW);
-    float v[4];
-    load4(x + p * C + c4 * 4, v);
-    const float* s = stats + ((long long)n * C + c4 * 4) * 2;
+__global__ void __launch_bounds__(256) in_apply_fwd_kernel(const T* __restrict__ x, const float* __restrict__ stats,
+                                                           T* __restrict__ y, long long per_sample, int C) {
+  constexpr int VEC = V16<T>::N;
+  const int n = blockIdx.y;
+  const long long step = (long long)gridDim.x * 256 * VEC;
+  long long e = ((long long)blockIdx.x * 256 + threadIdx.x) * VEC;
+  const int c0 = (int)(e % C);
+  const T* xp = x + (long long)n * per_sample;
+  T* yp = y + (long long)n * per_sample;
+  float mean[VEC], rstd[VEC];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) v[k] = (v[k] - s[2 * k]) * s[2 * k + 1];
-    store4(y + p * C + c4 * 4, v);
+  for (int k = 0; k < VEC; ++k) {
+    mean[k] = stats[((long long)n * C + c0 + k) * 2];
+    rstd[k] = stats[((long long)n * C + c0 + k) * 2 + 1];
+  }
+  for (; e < per_sample; e += step * IN_UNROLL) {
+    float v[IN_UNROLL][VEC];
+#pragma unroll
+    for (int u = 0; u < IN_UNROLL; ++u)
+      if (e + u * step < per_sample) V16<T>::load(xp + e + u * step, v[u]);
+#pragma unroll
+    for (int u = 0; u < IN_UNROLL; ++u)
+      if (e + u * step < per_sample) {
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) v[u][k] = (v[u][k] - mean[k]) * rstd[k];
+        V16<T>::store(yp + e + u * step, v[u]);
+      }
   }
 }
 
 template <typename T>
-__global__ void in_apply_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const float* __restrict__ stats,
-                                    const double* __restrict__ sums, T* __restrict__ dx, int N, int HW, int C,
-                                    double inv_hw, int relu_mask, float mask_scale) {
-  const int c4n = C / 4;
-  long long total = (long long)N * HW * c4n;
-  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  long long stride = (long long)gridDim.x * blockDim.x;
-  for (; i < total; i += stride) {
-    int c4 = (int)(i % c4n);
-    long long p = i / c4n;
-    int n = (int)(p / HW);
-    float g[4], v[4];
-    load4(dy + p * C + c4 * 4, g);
-    load4(x + p * C + c4 * 4, v);
-    const float* s = stats + ((long long)n * C + c4 * 4) * 2;
-    const double* q = sums + ((long long)n * C + c4 * 4) * 2;
+__global__ void __launch_bounds__(256) in_apply_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x,
+                                                           const float* __restrict__ stats, const double* __restrict__ sums,
+                                                           T* __restrict__ dx, long long per_sample, int C, double inv_hw,
+                                                           int relu_mask, float mask_scale) {
+  constexpr int VEC = V16<T>::N;
+  const int n = blockIdx.y;
+  const long long step = (long long)gridDim.x * 256 * VEC;
+  long long e = ((long long)blockIdx.x * 256 + threadIdx.x) * VEC;
+  const int c0 = (int)(e % C);
+  const T* gp = dy + (long long)n * per_sample;
+  const T* xp = x + (long long)n * per_sample;
+  T* op = dx + (long long)n * per_sample;
+  float mean[VEC], rstd[VEC], m1[VEC], m2[VEC];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      float rstd = s[2 * k + 1];
-      float xh = (v[k] - s[2 * k]) * rstd;
-      const float xin = v[k];
-      v[k] = rstd * (g[k] - (float)(q[2 * k] * inv_hw) - xh * (float)(q[2 * k + 1] * inv_hw));
-      if (relu_mask) v[k] = xin > 0.f ? v[k] * mask_scale : 0.f;
-    }
-    store4(dx + p * C + c4 * 4, v);
+  for (int k = 0; k < VEC; ++k) {
+    const long long i = (long long)n * C + c0 + k;
+    mean[k] = stats[i * 2];
+    rstd[k] = stats[i * 2 + 1];
+    m1[k] = (float)(sums[i * 2] * inv_hw);
+    m2[k] = (float)(sums[i * 2 + 1] * inv_hw);
+  }
+  for (; e < per_sample; e += step * IN_UNROLL) {
+    float g[IN_UNROLL][VEC], v[IN_UNROLL][VEC];
+#pragma unroll
+    for (int u = 0; u < IN_UNROLL; ++u)
+      if (e + u * step < per_sample) {
+        V16<T>::load(gp + e + u * step, g[u]);
+        V16<T>::load(xp + e + u * step, v[u]);
+      }
+#pragma unroll
+    for (int u = 0; u < IN_UNROLL; ++u)
+      if (e + u * step < per_sample) {
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) {
+          const float xin = v[u][k];
+          const float xh = (xin - mean[k]) * rstd[k];
+          float r = rstd[k] * (g[u][k] - m1[k] - xh * m2[k]);
+          if (relu_mask) r = xin > 0.f ? r * mask_scale : 0.f;
+          v[u][k] = r;
+        }
+        V16<T>::store(op + e + u * step, v[u]);
+      }
   }
 }
 
@@ -219,46 +300,51 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const T* __restrict__ dy, c
 
 }  // namespace
 
+// blocks per sample for the flat InstanceNorm kernels: ~8 CTAs per SM over the batch, at least IN_UNROLL loads per thread
+static int in_blocks(long long per_sample, int vec, int N) {
+  long long want = cdiv(148LL * 8, N);
+  long long most = cdiv(per_sample, 256LL * vec * IN_UNROLL);
+  if (want > most) want = most;
+  return (int)(want < 1 ? 1 : want);
+}
+
 extern "C" int omr_instnorm_fwd(int dt, const void* x, void* y, float* stats, double* ws, int N, int HW, int C,
                                 float eps, omr_stream_t stream) {
-  int CT = pick_ct(C);
-  OMR_REQUIRE(CT > 0 && C % 4 == 0, "omr_instnorm_fwd: unsupported channel count %d", C);
+  const int vec = dt == OMR_BF16 ? 8 : 4;
+  OMR_REQUIRE(C >= vec && C % vec == 0 && (256 * vec) % C == 0, "omr_instnorm_fwd: unsupported channel count %d", C);
+  OMR_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0,
+              "omr_instnorm_fwd: x and y must be 16-byte aligned");
   if ((long long)N * HW * C <= 0) return OMR_OK;
   cudaStream_t st = as_stream(stream);
   OMR_CUDA(cudaMemsetAsync(ws, 0, sizeof(double) * (size_t)N * C * 2, st));
-  int RS = 256 / CT;
-  int rpb = (int)cdiv(HW, cdiv(148LL * 8, (long long)N * (C / CT)));
-  if (rpb < RS * 8) rpb = RS * 8;
-  dim3 grid((unsigned)cdiv(HW, rpb), (unsigned)N, (unsigned)(C / CT));
-  OMR_DISPATCH_DT(dt, T, (in_partial_kernel<T, 0><<<grid, 256, 0, st>>>((const T*)x, nullptr, nullptr, ws, HW, C, CT,
-                                                                        rpb)));
+  const long long per = (long long)HW * C;
+  dim3 grid((unsigned)in_blocks(per, vec, N), (unsigned)N);
+  OMR_DISPATCH_DT(dt, T, (in_partial_kernel<T, 0><<<grid, 256, 0, st>>>((const T*)x, nullptr, nullptr, ws, per, C)));
   OMR_LAUNCHED();
   in_finalize_kernel<<<(int)cdiv((long long)N * C, 256), 256, 0, st>>>(ws, stats, (long long)N * C, 1.0 / HW,
                                                                                 (double)eps);
   OMR_LAUNCHED();
-  long long total = (long long)N * HW * (C / 4);
-  OMR_DISPATCH_DT(dt, T, (in_apply_fwd_kernel<T><<<grid_cap(total), 256, 0, st>>>((const T*)x, stats, (T*)y, N, HW, C)));
+  OMR_DISPATCH_DT(dt, T, (in_apply_fwd_kernel<T><<<grid, 256, 0, st>>>((const T*)x, stats, (T*)y, per, C)));
   OMR_LAUNCHED();
   return OMR_OK;
 }
 
 extern "C" int omr_instnorm_bwd(int dt, const void* dy, const void* x, const float* stats, void* dx, double* ws, int N,
                                 int HW, int C, int relu_mask, float mask_scale, omr_stream_t stream) {
-  int CT = pick_ct(C);
-  OMR_REQUIRE(CT > 0 && C % 4 == 0, "omr_instnorm_bwd: unsupported channel count %d", C);
+  const int vec = dt == OMR_BF16 ? 8 : 4;
+  OMR_REQUIRE(C >= vec && C % vec == 0 && (256 * vec) % C == 0, "omr_instnorm_bwd: unsupported channel count %d", C);
+  OMR_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(dy) & 15) == 0 &&
+                  (reinterpret_cast<uintptr_t>(dx) & 15) == 0,
+              "omr_instnorm_bwd: dy, x and dx must be 16-byte aligned");
   if ((long long)N * HW * C <= 0) return OMR_OK;
   cudaStream_t st = as_stream(stream);
   OMR_CUDA(cudaMemsetAsync(ws, 0, sizeof(double) * (size_t)N * C * 2, st));
-  int RS = 256 / CT;
-  int rpb = (int)cdiv(HW, cdiv(148LL * 8, (long long)N * (C / CT)));
-  if (rpb < RS * 8) rpb = RS * 8;
-  dim3 grid((unsigned)cdiv(HW, rpb), (unsigned)N, (unsigned)(C / CT));
-  OMR_DISPATCH_DT(dt, T, (in_partial_kernel<T, 1><<<grid, 256, 0, st>>>((const T*)dy, (const T*)x, stats, ws, HW, C, CT,
-                                                                        rpb)));
+  const long long per = (long long)HW * C;
+  dim3 grid((unsigned)in_blocks(per, vec, N), (unsigned)N);
+  OMR_DISPATCH_DT(dt, T, (in_partial_kernel<T, 1><<<grid, 256, 0, st>>>((const T*)dy, (const T*)x, stats, ws, per, C)));
   OMR_LAUNCHED();
-  long long total = (long long)N * HW * (C / 4);
-  OMR_DISPATCH_DT(dt, T, (in_apply_bwd_kernel<T><<<grid_cap(total), 256, 0, st>>>((const T*)dy, (const T*)x, stats, ws,
-                                                                                 (T*)dx, N, HW, C, 1.0 / HW, relu_mask, mask_scale)));
+  OMR_DISPATCH_DT(dt, T, (in_apply_bwd_kernel<T><<<grid, 256, 0, st>>>((const T*)dy, (const T*)x, stats, ws, (T*)dx, per, C,
+                                                                      1.0 / HW, relu_mask, mask_scale)));
   OMR_LAUNCHED();
   return OMR_OK;
 }

@@ -253,12 +253,21 @@ int omr_conv3x3_wgrad_tc(const void* x, const void* dy, float* dw, int N, int H,
   if (g.halo) g.halo_rows = ((g.halo_rows * g.rbb + 1023) / 1024 * 1024) / g.rbb;  // chunk tiles stay 1 KB aligned
   g.stage_bytes = (raw + 1023) / 1024 * 1024;
   g.stages = (200 * 1024) / g.stage_bytes;
-  if (g.stages > 4) g.stages = 4;
+  // narrow channel rows make every TMA box hundreds of 32/64-byte requests: the pipeline is bound by their latency,
+  // so it runs as deep as shared memory allows
+  static int max_stages = 0;
+  if (!max_stages) {
+    const char* e = getenv("OMR_WGRAD_STAGES");
+    max_stages = e ? atoi(e) : 12;
+    if (max_stages < 2) max_stages = 2;
+    if (max_stages > 16) max_stages = 16;
+  }
+  if (g.stages > max_stages) g.stages = max_stages;
   if (g.stages < 2) return OMR_TC_NOT_ELIGIBLE;
   // every sub-tile must start on a swizzle-atom boundary (8 rows): KP is a multiple of 16 rows, so a_sub/b_sub are
   // multiples of 16 * rb >= 512 B; the 128 B swizzle needs 1024 B: 16 rows * 128 B = 2048 ok, 64 B: 16*64 = 1024 ok,
   // 32 B: atom is 256 B, 16*32 = 512 ok.
-  const int smem_bytes = g.stages * g.stage_bytes + 1024 + 512;
+  const int smem_bytes = g.stages * g.stage_bytes + 1024 + 1024;
 
   CUtensorMap tmDY, tmX;
   {

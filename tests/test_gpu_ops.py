@@ -89,7 +89,7 @@ def test_conv3x3_fwd_dgrad_wgrad(ops, dtype, case):
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
-@pytest.mark.parametrize("shape", [(2, 8, 16, 128), (1, 13, 11, 256), (3, 5, 7, 32)])
+@pytest.mark.parametrize("shape", [(2, 8, 16, 128), (1, 13, 11, 256), (3, 5, 7, 32), (8, 13, 101, 256), (16, 8, 128, 128)])
 def test_dwconv3x3(ops, dtype, shape):
     n, h, w, c = shape
     x = rnd(n, c, h, w, seed=5)
