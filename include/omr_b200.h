@@ -167,6 +167,11 @@ int omr_colsum(int dt, const void* x, long long rows, int N, long long ld, float
  * Layout: element (b, t, h, d) of Q lives at q[b*q_bs + t*q_rs + h*hd + d] (same for k, v, o with
  * their strides), so packed in-proj outputs are consumed in place.
  * lse [B,H,Tq] fp32 receives log-sum-exp (natural log) for the backward. */
+/* Attention-probability dropout (the `dropout` of nn.MultiheadAttention as built at decoder.py:86-95, and of the
+ * mixers' nn.MultiheadAttention, model.py:292-297; train mode only): arms the NEXT omr_attn_fwd or omr_attn_bwd call
+ * (one-shot), which then computes O = (P o M / (1-p)) V with a keep mask M that is a pure function of (seed [+ the
+ * device int32 *seed_off], batch*head, query, key) -- the backward regenerates it from the same arguments.  p in [0,1). */
+int omr_attn_next_dropout(float p, unsigned int seed, const int* seed_off);
 int omr_attn_fwd(int dt, const void* q, long long q_bs, long long q_rs, const void* k, long long k_bs, long long k_rs,
                  const void* v, long long v_bs, long long v_rs, void* o, long long o_bs, long long o_rs, float* lse,
                  const float* key_bias, int B, int H, int Tq, int Tk, int hd, float scale, int causal, int window,

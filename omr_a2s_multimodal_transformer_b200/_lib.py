@@ -39,6 +39,7 @@ _SIGS = {
     "omr_embed_bwd": "ipppqiqp",
     "omr_gemm": "iiiiiiipqqpqqpqqipiiip",
     "omr_colsum": "ipqiqpip",
+    "omr_attn_next_dropout": "fip",
     "omr_attn_fwd": "ipqqpqqpqqpqqppiiiiifiippip",
     "omr_attn_bwd": "ipqqpqqpqqpqqpqqppqqpqqpqqppiiiiifiippip",
     "omr_add_layernorm_fwd": "ipppppppqifp",

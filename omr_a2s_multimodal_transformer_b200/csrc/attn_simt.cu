@@ -7,6 +7,7 @@
 // (SURVEY.md appendix B): additive fp32 key bias per (b, key) (0 / +1.0 / -inf), causal or
 // sliding-window structure, and the mixer's (rows >= lq) x (cols >= lkv) block mask with its
 // head-major repeat quirk (quirk_mod).
+#include "attn_drop.cuh"
 #include "simt_tile.cuh"
 
 namespace {
@@ -24,7 +25,15 @@ struct AttnArgs {
   float scale;
   int causal, window;
   const int* q_len; const int* kv_len; int quirk_mod;
+  AttnDrop drop;  // attention-probability dropout (thr == 0: off)
 };
+
+// mask-and-scale factor of pair (t, j): 0 if dropped, 1/(1-p) if kept, 1 when dropout is off
+__device__ __forceinline__ float drop_factor(const AttnArgs& a, uint32_t stream, int t, int j) {
+  if (a.drop.thr == 0) return 1.f;
+  const uint32_t bits = attn_drop_bits(stream, (uint32_t)t, (uint32_t)(j >> 1), (uint32_t)((a.Tk + 1) >> 1));
+  return attn_keep(bits, j, a.drop.thr) ? a.drop.inv_keep : 0.f;
+}
 
 template <typename T>
 __device__ __forceinline__ float fexp(float x) {
@@ -133,6 +142,7 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(AttnArgs a) {
   const T* k = (const T*)a.k + (long long)b * a.k_bs + h * HD;
   const T* v = (const T*)a.v + (long long)b * a.v_bs + h * HD;
   const MaskCtx mc = make_mask_ctx(a, b, h);
+  const uint32_t dstream = a.drop.thr ? attn_drop_stream(a.drop, b * a.H + h) : 0u;
 
   load_tile<T, false, true>(q, a.q_rs, t0, a.Tq, nullptr, Qt, a.scale);
 
@@ -187,7 +197,7 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(AttnArgs a) {
 #pragma unroll
       for (int c = 0; c < 4; ++c) oacc[r][c] *= alpha;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) Pt[(tx * 4 + c) * LDT + ty * 4 + r] = s[r][c];
+      for (int c = 0; c < 4; ++c) Pt[(tx * 4 + c) * LDT + ty * 4 + r] = s[r][c] * drop_factor(a, dstream, t, j0 + tx * 4 + c);
     }
     __syncthreads();
     simt_mma_4x4<LDT, LDT, BT>(Pt, Vs, ty * 4, tx * 4, oacc);
@@ -246,6 +256,7 @@ __global__ void __launch_bounds__(256) attn_bwd_dkdv_kernel(AttnArgs a) {
   const T* v = (const T*)a.v + (long long)b * a.v_bs + h * HD;
   const T* dO = (const T*)a.dout + (long long)b * a.do_bs + h * HD;
   const MaskCtx mc = make_mask_ctx(a, b, h);
+  const uint32_t dstream = a.drop.thr ? attn_drop_stream(a.drop, b * a.H + h) : 0u;
 
   load_tile<T, false, true>(k, a.k_rs, j0, a.Tk, nullptr, Kt, 1.f);
   load_tile<T, false, true>(v, a.v_rs, j0, a.Tk, nullptr, Vt, 1.f);
@@ -288,9 +299,10 @@ __global__ void __launch_bounds__(256) attn_bwd_dkdv_kernel(AttnArgs a) {
       for (int c = 0; c < 4; ++c) {
         float mt = mask_term(a, mc, t0 + i, j0 + tx * 4 + c);
         float p = (mt == -INFINITY) ? 0.f : fexp<T>(s[r][c] * a.scale + mt - l);
+        const float df = drop_factor(a, dstream, t0 + i, j0 + tx * 4 + c);
         s[r][c] = p;
-        dp[r][c] = p * (dp[r][c] - dl);
-        Ps[i * LDT + tx * 4 + c] = p;
+        dp[r][c] = p * (dp[r][c] * df - dl);
+        Ps[i * LDT + tx * 4 + c] = p * df;
       }
     }
     __syncthreads();
@@ -335,6 +347,7 @@ __global__ void __launch_bounds__(256) attn_bwd_dq_kernel(AttnArgs a) {
   const T* v = (const T*)a.v + (long long)b * a.v_bs + h * HD;
   const T* dO = (const T*)a.dout + (long long)b * a.do_bs + h * HD;
   const MaskCtx mc = make_mask_ctx(a, b, h);
+  const uint32_t dstream = a.drop.thr ? attn_drop_stream(a.drop, b * a.H + h) : 0u;
   const long long stat_base = ((long long)b * a.H + h) * a.Tq;
 
   load_tile<T, false, true>(q, a.q_rs, t0, a.Tq, nullptr, Qt, 1.f);
@@ -376,7 +389,7 @@ __global__ void __launch_bounds__(256) attn_bwd_dq_kernel(AttnArgs a) {
       for (int c = 0; c < 4; ++c) {
         float mt = mask_term(a, mc, t0 + i, j0 + tx * 4 + c);
         float p = (mt == -INFINITY) ? 0.f : fexp<T>(s[r][c] * a.scale + mt - lse_r[r]);
-        dSt[(tx * 4 + c) * LDT + i] = p * (dp[r][c] - delta_r[r]);
+        dSt[(tx * 4 + c) * LDT + i] = p * (dp[r][c] * drop_factor(a, dstream, t0 + i, j0 + tx * 4 + c) - delta_r[r]);
       }
     }
     __syncthreads();
@@ -423,6 +436,7 @@ int omr_attn_fwd_simt(int dt, const void* q, long long q_bs, long long q_rs, con
   a.q_bs = q_bs; a.q_rs = q_rs; a.k_bs = k_bs; a.k_rs = k_rs; a.v_bs = v_bs; a.v_rs = v_rs; a.o_bs = o_bs; a.o_rs = o_rs;
   a.B = B; a.H = H; a.Tq = Tq; a.Tk = Tk; a.scale = scale; a.causal = causal; a.window = window;
   a.q_len = q_len; a.kv_len = kv_len; a.quirk_mod = quirk_mod;
+  a.drop = omr_attn_cur_dropout();
   dim3 grid((unsigned)cdiv(Tq, BT), (unsigned)H, (unsigned)B);
   size_t smem = sizeof(float) * 4 * TILE_F;
   OMR_DISPATCH_DT(dt, T, {
@@ -459,6 +473,7 @@ int omr_attn_bwd_simt(int dt, const void* q, long long q_bs, long long q_rs, con
   a.dv_bs = dv_bs; a.dv_rs = dv_rs;
   a.B = B; a.H = H; a.Tq = Tq; a.Tk = Tk; a.scale = scale; a.causal = causal; a.window = window;
   a.q_len = q_len; a.kv_len = kv_len; a.quirk_mod = quirk_mod;
+  a.drop = omr_attn_cur_dropout();
   long long nw = (long long)B * H * Tq;
   size_t smem_kv = sizeof(float) * (7 * TILE_F + 2 * BT);
   size_t smem_q = sizeof(float) * 6 * TILE_F;

@@ -13,6 +13,7 @@
 // key bias per (b, key) (0, +1.0 or -inf), keys visible to query t iff k <= t + Tk - Tq (causal) and
 // k >= t + Tk - Tq - window.  lse (natural log) is saved for the backward.
 // Warp roles: 0-3 softmax + epilogue (TMEM lanes 32w..32w+31), 4 TMA producer, 5 MMA issuer + TMEM allocator.
+#include "attn_drop.cuh"
 #include "kernels.h"
 #include "tc_common.cuh"
 
@@ -33,6 +34,7 @@ struct AttnTcArgs {
   int B, H, Tq, Tk;
   float scale_log2;  // scale * log2(e)
   int causal, window;
+  AttnDrop drop;     // attention-probability dropout (thr == 0: off)
 };
 
 // Q, K[2], V[2], P (2 tiles) + bias tile + barriers: 115,456 B, so that two CTAs (+1 KB system reserve each) fit
@@ -155,6 +157,8 @@ __global__ void __launch_bounds__(192, 2) attn_fwd_tc_kernel(const __grid_consta
 #pragma unroll
     for (int d = 0; d < HD; ++d) o_acc[d] = 0.f;
     const float* kb = a.key_bias ? a.key_bias + (long long)b * a.Tk : nullptr;
+    const uint32_t dstream = a.drop.thr ? attn_drop_stream(a.drop, b * a.H + h) : 0u;
+    const uint32_t dkp = (uint32_t)((a.Tk + 1) >> 1);
     // visible key interval of this row
     int k_hi = a.Tk - 1, k_lo = 0;
     if (a.causal) {
@@ -220,6 +224,12 @@ __global__ void __launch_bounds__(192, 2) attn_fwd_tc_kernel(const __grid_consta
           // the row sum uses the bf16-rounded probabilities that the P V product will see
           __nv_bfloat162 pb = __floats2bfloat162_rn(p0, p1);
           rs += __low2float(pb) + __high2float(pb);
+          if (a.drop.thr) {  // dropout acts on the normalised probabilities: the row sum stays that of the full row
+            const uint32_t bits = attn_drop_bits(dstream, (uint32_t)t, (uint32_t)(j >> 1), dkp);
+            p0 = (bits & 0xFFFFu) >= a.drop.thr ? p0 * a.drop.inv_keep : 0.f;
+            p1 = (bits >> 16) >= a.drop.thr ? p1 * a.drop.inv_keep : 0.f;
+            pb = __floats2bfloat162_rn(p0, p1);
+          }
           pk[e >> 1] = *reinterpret_cast<uint32_t*>(&pb);
         }
         // keys c*32 .. c*32+31 = 64 bytes = 4 sixteen-byte units of row r in chunk c/2
@@ -298,7 +308,7 @@ int omr_attn_fwd_tc(const void* q, long long q_bs, long long q_rs, const void* k
   if (rc) return rc;
   rc = make_head_map(&tmV, v, v_bs, v_rs, B, Tk, H, BKV);
   if (rc) return rc;
-  AttnTcArgs a{(bf16*)o, o_bs, o_rs, lse, key_bias, B, H, Tq, Tk, scale * LOG2E, causal, window};
+  AttnTcArgs a{(bf16*)o, o_bs, o_rs, lse, key_bias, B, H, Tq, Tk, scale * LOG2E, causal, window, omr_attn_cur_dropout()};
   static bool configured = false;
   if (!configured) {
     OMR_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM));
@@ -483,6 +493,8 @@ __global__ void __launch_bounds__(320, 1) attn_bwd_tc_kernel(const __grid_consta
     }
     if (j >= a.Tk) t_hi = -1;
     const long long stat_base = ((long long)b * a.H + h) * a.Tq;
+    const uint32_t dstream = a.drop.thr ? attn_drop_stream(a.drop, b * a.H + h) : 0u;
+    const uint32_t dkp = (uint32_t)((a.Tk + 1) >> 1), dsh = (uint32_t)(j & 1) * 16u;
 
     auto dq_epilogue = [&](int q_tile) {
       const int t = q_tile * BQ + r;
@@ -531,9 +543,16 @@ __global__ void __launch_bounds__(320, 1) attn_bwd_tc_kernel(const __grid_consta
           const float x1 = fmaf(__uint_as_float(sv[e + 1]), a.scale_log2, bias) - sLse[c * 32 + e + 1];
           const float p0 = (t >= t_lo && t <= t_hi) ? exp2f(x0) : 0.f;
           const float p1 = (t + 1 >= t_lo && t + 1 <= t_hi) ? exp2f(x1) : 0.f;
-          const float d0 = p0 * (__uint_as_float(dv[e]) - sDelta[c * 32 + e]);
-          const float d1 = p1 * (__uint_as_float(dv[e + 1]) - sDelta[c * 32 + e + 1]);
-          pk[e >> 1] = pack_bf16(p0, p1);
+          float f0 = 1.f, f1 = 1.f;  // mask / (1-p) of the pairs (t, j), (t+1, j)
+          if (a.drop.thr) {
+            const uint32_t b0 = attn_drop_bits(dstream, (uint32_t)t, (uint32_t)(j >> 1), dkp);
+            const uint32_t b1 = attn_drop_bits(dstream, (uint32_t)(t + 1), (uint32_t)(j >> 1), dkp);
+            f0 = ((b0 >> dsh) & 0xFFFFu) >= a.drop.thr ? a.drop.inv_keep : 0.f;
+            f1 = ((b1 >> dsh) & 0xFFFFu) >= a.drop.thr ? a.drop.inv_keep : 0.f;
+          }
+          const float d0 = p0 * (__uint_as_float(dv[e]) * f0 - sDelta[c * 32 + e]);
+          const float d1 = p1 * (__uint_as_float(dv[e + 1]) * f1 - sDelta[c * 32 + e + 1]);
+          pk[e >> 1] = pack_bf16(p0 * f0, p1 * f1);
           dk[e >> 1] = pack_bf16(d0, d1);
         }
         uint8_t* prow = sPT + (c >> 1) * TILE + r * 128;
@@ -668,7 +687,8 @@ int omr_attn_bwd_tc(const void* q, long long q_bs, long long q_rs, const void* k
                                                                             delta, B, H, Tq);
   OMR_LAUNCHED();
   AttnBwdArgs g{};
-  g.f = AttnTcArgs{nullptr, 0, 0, const_cast<float*>(lse), key_bias, B, H, Tq, Tk, scale * LOG2E, causal, window};
+  g.f = AttnTcArgs{nullptr, 0, 0, const_cast<float*>(lse), key_bias, B, H, Tq, Tk, scale * LOG2E, causal, window,
+                   omr_attn_cur_dropout()};
   g.delta = delta; g.dq_acc = dq_acc;
   g.dk = (bf16*)dk; g.dk_bs = dk_bs; g.dk_rs = dk_rs;
   g.dv = (bf16*)dv; g.dv_bs = dv_bs; g.dv_rs = dv_rs;

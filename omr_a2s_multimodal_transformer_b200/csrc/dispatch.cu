@@ -3,6 +3,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "attn_drop.cuh"
 #include "kernels.h"
 
 static int g_tc_enabled = -1;
@@ -82,12 +83,30 @@ extern "C" int omr_conv3x3_wgrad(int dt, const void* x, const void* dy, float* d
   return omr_conv3x3_wgrad_simt(dt, x, dy, dw, N, H, W, Ci, Co, sh, sw, accumulate, st);
 }
 
+// ---- attention-probability dropout: one-shot state consumed by the next omr_attn_fwd / omr_attn_bwd ----
+namespace {
+AttnDrop g_drop_next = {0, nullptr, 0, 1.f};
+AttnDrop g_drop_cur = {0, nullptr, 0, 1.f};
+void take_dropout() {
+  g_drop_cur = g_drop_next;
+  g_drop_next = AttnDrop{0, nullptr, 0, 1.f};
+}
+}  // namespace
+const AttnDrop& omr_attn_cur_dropout() { return g_drop_cur; }
+extern "C" int omr_attn_next_dropout(float p, unsigned int seed, const int* seed_off) {
+  OMR_REQUIRE(p >= 0.f && p < 1.f, "omr_attn_next_dropout: p must be in [0, 1) (got %f)", (double)p);
+  const unsigned int thr = (unsigned int)(p * 65536.f + 0.5f);
+  g_drop_next = AttnDrop{seed, seed_off, thr, thr ? 65536.f / (float)(65536u - thr) : 1.f};
+  return OMR_OK;
+}
+
 extern "C" int omr_attn_fwd(int dt, const void* q, long long q_bs, long long q_rs, const void* k, long long k_bs,
                             long long k_rs, const void* v, long long v_bs, long long v_rs, void* o, long long o_bs,
                             long long o_rs, float* lse, const float* key_bias, int B, int H, int Tq, int Tk, int hd,
                             float scale, int causal, int window, const int* q_len, const int* kv_len, int quirk_mod,
                             omr_stream_t stream) {
   cudaStream_t st = as_stream(stream);
+  take_dropout();
   if (tc_enabled() && dt == OMR_BF16) {
     TC_TRY(omr_attn_fwd_tc(q, q_bs, q_rs, k, k_bs, k_rs, v, v_bs, v_rs, o, o_bs, o_rs, lse, key_bias, B, H, Tq, Tk, hd,
                              scale, causal, window, q_len, kv_len, quirk_mod, st));
@@ -104,6 +123,7 @@ extern "C" int omr_attn_bwd(int dt, const void* q, long long q_bs, long long q_r
                             const float* key_bias, int B, int H, int Tq, int Tk, int hd, float scale, int causal,
                             int window, const int* q_len, const int* kv_len, int quirk_mod, omr_stream_t stream) {
   cudaStream_t st = as_stream(stream);
+  take_dropout();
   if (tc_enabled() && dt == OMR_BF16) {
     TC_TRY(omr_attn_bwd_tc(q, q_bs, q_rs, k, k_bs, k_rs, v, v_bs, v_rs, o, o_bs, o_rs, dout, do_bs, do_rs, lse, dq, dq_bs, dq_rs,
                            dk, dk_bs, dk_rs, dv, dv_bs, dv_rs, delta_ws, key_bias, B, H, Tq, Tk, hd, scale, causal, window,

@@ -288,6 +288,10 @@ class Decoder(nn.Module):
         w1 = c.get(L.linear1.weight, "mat", dtype)
         w2 = c.get(L.linear2.weight, "mat", dtype)
         save = tape is not None
+        if training and self.dropout_p > 0:
+            # nn.MultiheadAttention(dropout=dropout_p) of both attention blocks: dropout on the softmax probabilities
+            spec_self = ops.attn_spec_with_dropout(spec_self, self.dropout_p, self._next_seed())
+            spec_cross = ops.attn_spec_with_dropout(spec_cross, self.dropout_p, self._next_seed())
         x2d = x.view(b * t, d)
         # --- self-attention block: x1 = LN(x + out_proj(attn(in_proj(x)))) -------------------------
         qkv = ops.linear_fwd(x2d, w_in, sa.in_proj_bias).view(b, t, 3 * d)

@@ -323,6 +323,9 @@ class _CrossAttnFn(torch.autograd.Function):
         q = ops.linear_fwd(q2, w_in[:d], att.in_proj_bias[:d]).view(b, tq, d)
         kv = ops.linear_fwd(kv2, w_in[d:], att.in_proj_bias[d:]).view(b, tk, 2 * d)
         spec = AttnSpec(att.num_heads, att.head_dim, q_len=q_len, kv_len=kv_len, quirk_mod=b if q_len is not None else 0)
+        if mod.training and mod.dropout_p > 0:  # nn.MultiheadAttention(dropout=0.1) of the mixer (reference model.py:292-297)
+            mod._drop_seed = (mod._drop_seed * 6364136223846793005 + 1442695040888963407) & 0xFFFFFFFFFFFFFFFF
+            spec = ops.attn_spec_with_dropout(spec, mod.dropout_p, (mod._drop_seed >> 17) & 0x7FFFFFFF)
         o, lse = ops.attn_fwd(q, 0, kv, 0, kv, d, spec)
         out = ops.linear_fwd(o.view(b * tq, d), w_o, att.out_proj.bias).view(b, tq, d)
         ctx.mod, ctx.dtype, ctx.spec = mod, dtype, spec
@@ -369,6 +372,7 @@ class CrossAttention(nn.Module):
         self.attention = MHAParams(feature_dim, num_heads)
         self.compute_dtype: Optional[torch.dtype] = None
         self._wcache = WeightCache()
+        self._drop_seed = 0x1357911
 
     def forward(self, query, len_query, key_value, len_key_value):
         dtype = resolve_dtype(self.compute_dtype)

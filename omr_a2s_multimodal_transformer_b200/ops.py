@@ -290,13 +290,27 @@ def colsum(x2d, out, accumulate=True):
 class AttnSpec:
     """Mask description shared by attention forward and backward."""
 
-    __slots__ = ("H", "hd", "scale", "causal", "window", "key_bias", "q_len", "kv_len", "quirk_mod")
+    __slots__ = ("H", "hd", "scale", "causal", "window", "key_bias", "q_len", "kv_len", "quirk_mod", "dropout_p", "seed")
 
-    def __init__(self, H, hd, causal=False, window=-1, key_bias=None, q_len=None, kv_len=None, quirk_mod=0):
+    def __init__(self, H, hd, causal=False, window=-1, key_bias=None, q_len=None, kv_len=None, quirk_mod=0, dropout_p=0.0,
+                 seed=0):
         self.H, self.hd = H, hd
+        # attention-probability dropout (train mode): the forward and the backward call must carry the same (p, seed)
+        self.dropout_p, self.seed = float(dropout_p), int(seed)
         self.scale = 1.0 / math.sqrt(hd)
         self.causal, self.window = bool(causal), int(window) if window and window > 0 else 0
         self.key_bias, self.q_len, self.kv_len, self.quirk_mod = key_bias, q_len, kv_len, quirk_mod
+
+
+def attn_spec_with_dropout(spec: "AttnSpec", p: float, seed: int) -> "AttnSpec":
+    """copy of ``spec`` that applies attention-probability dropout (p, seed) in forward and backward"""
+    return AttnSpec(spec.H, spec.hd, causal=spec.causal, window=spec.window, key_bias=spec.key_bias, q_len=spec.q_len,
+                    kv_len=spec.kv_len, quirk_mod=spec.quirk_mod, dropout_p=p, seed=seed)
+
+
+def _arm_attn_dropout(spec: "AttnSpec") -> None:
+    if spec.dropout_p > 0.0:
+        call("omr_attn_next_dropout", float(spec.dropout_p), int(spec.seed) & 0x7FFFFFFF, ptr(SEED_OFFSET_DEV))
 
 
 def _view3(t, off, width):
@@ -315,6 +329,7 @@ def attn_fwd(qbuf, q_off, kbuf, k_off, vbuf, v_off, spec: AttnSpec):
     qp, qbs, qrs = _view3(qbuf, q_off, d)
     kp, kbs, krs = _view3(kbuf, k_off, d)
     vp, vbs, vrs = _view3(vbuf, v_off, d)
+    _arm_attn_dropout(spec)
     call("omr_attn_fwd", dt_code(qbuf.dtype), qp, qbs, qrs, kp, kbs, krs, vp, vbs, vrs, ptr(o), o.stride(0), o.stride(1),
          ptr(lse), ptr(spec.key_bias), b, spec.H, tq, tk, spec.hd, spec.scale, int(spec.causal), spec.window,
          ptr(spec.q_len), ptr(spec.kv_len), spec.quirk_mod, stream_ptr())
@@ -334,6 +349,7 @@ def attn_bwd(qbuf, q_off, kbuf, k_off, vbuf, v_off, o, do, lse, dqbuf, dq_off, d
     dkp, dkbs, dkrs = _view3(dkbuf, dk_off, d)
     dvp, dvbs, dvrs = _view3(dvbuf, dv_off, d)
     delta = torch.empty(b * spec.H * tq * 65 + 4, dtype=torch.float32, device=qbuf.device)  # delta + fp32 dQ accumulators
+    _arm_attn_dropout(spec)
     call("omr_attn_bwd", dt_code(qbuf.dtype), qp, qbs, qrs, kp, kbs, krs, vp, vbs, vrs, ptr(o), o.stride(0), o.stride(1),
          ptr(do), do.stride(0), do.stride(1), ptr(lse), dqp, dqbs, dqrs, dkp, dkbs, dkrs, dvp, dvbs, dvrs, ptr(delta),
          ptr(spec.key_bias), b, spec.H, tq, tk, spec.hd, spec.scale, int(spec.causal), spec.window, ptr(spec.q_len),

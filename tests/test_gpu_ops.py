@@ -279,6 +279,88 @@ def test_attention_fwd_bwd(ops, dtype, case):
     assert rel_err(dv, unheads(vr.grad)) < tol(dtype, 1e-4, 3e-2)
 
 
+def _extract_attn_dropout_mask(ops, dtype, B, H, Tq, Tk, causal, p, seed):
+    """keep mask [B,H,Tq,Tk] of the attention-probability dropout, read back through the kernel itself: with Q = K = 0 the
+    probabilities are uniform over the visible keys, and one-hot V blocks turn O into rows of P o M / (1-p)."""
+    hd, D = 64, H * 64
+    q = torch.zeros(B, Tq, D, device=dev(), dtype=dtype)
+    mask = torch.zeros(B, H, Tq, Tk, dtype=torch.bool)
+    for blk in range(0, Tk, hd):
+        kv = torch.zeros(B, Tk, 2 * D, device=dev(), dtype=dtype)
+        for h in range(H):
+            for dcol in range(min(hd, Tk - blk)):
+                kv[:, blk + dcol, D + h * hd + dcol] = 1.0
+        spec = ops.AttnSpec(H, hd, causal=causal, dropout_p=p, seed=seed)
+        o, _ = ops.attn_fwd(q, 0, kv, 0, kv, D, spec)
+        o = o.float().view(B, Tq, H, hd).transpose(1, 2).cpu()  # [B,H,Tq,hd]
+        n = min(hd, Tk - blk)
+        mask[:, :, :, blk:blk + n] = o[:, :, :, :n] > 0
+    return mask
+
+
+@pytest.mark.parametrize("case", [dict(Tq=130, Tk=200, causal=False), dict(Tq=160, Tk=160, causal=True)])
+def test_attention_dropout_fwd_bwd(ops, case):
+    """attention-probability dropout: the fp32 CUDA-core kernels and the bf16 tcgen05 kernels draw the SAME keep mask (a pure
+    function of seed, head, query, key), the forward and both backward kernels agree with a torch reference that applies
+    that mask to softmax(S) (nn.MultiheadAttention's dropout), and the drop rate is the requested one."""
+    B, H, Tq, Tk, hd, p, seed = 2, 4, case["Tq"], case["Tk"], 64, 0.25, 1234
+    causal = case["causal"]
+    D = H * hd
+    m32 = _extract_attn_dropout_mask(ops, torch.float32, B, H, Tq, Tk, causal, p, seed)
+    m16 = _extract_attn_dropout_mask(ops, torch.bfloat16, B, H, Tq, Tk, causal, p, seed)
+    vis = torch.ones(Tq, Tk, dtype=torch.bool).tril(Tk - Tq) if causal else torch.ones(Tq, Tk, dtype=torch.bool)
+    assert torch.equal(m32 & vis, m16 & vis)
+    rate = 1.0 - float(m32[:, :, vis].float().mean())
+    assert abs(rate - p) < 0.01, rate
+    assert not torch.equal(m32[0, 0], m32[0, 1]) and not torch.equal(m32[0, 0], m32[1, 0])  # per (batch, head) streams
+    other = _extract_attn_dropout_mask(ops, torch.float32, B, H, Tq, Tk, causal, p, seed + 1)
+    assert not torch.equal(other & vis, m32 & vis)
+    keep = m32.to(dev()).float() / (1.0 - round(p * 65536) / 65536.0)
+    for dtype in DTYPES:
+        g = torch.Generator().manual_seed(5)
+        if causal:
+            qkv = torch.randn(B, Tq, 3 * D, generator=g).to(dev()).to(dtype).contiguous()
+            qb, kb, vb, qo, ko, vo = qkv, qkv, qkv, 0, D, 2 * D
+        else:
+            qb = torch.randn(B, Tq, D, generator=g).to(dev()).to(dtype).contiguous()
+            kvb = torch.randn(B, Tk, 2 * D, generator=g).to(dev()).to(dtype).contiguous()
+            kb, vb, qo, ko, vo = kvb, kvb, 0, 0, D
+        spec = ops.AttnSpec(H, hd, causal=causal, dropout_p=p, seed=seed)
+        o, lse = ops.attn_fwd(qb, qo, kb, ko, vb, vo, spec)
+
+        def heads(buf, off):
+            return buf[:, :, off:off + D].float().view(B, -1, H, hd).transpose(1, 2).contiguous().requires_grad_(True)
+
+        qr, kr, vr = heads(qb, qo), heads(kb, ko), heads(vb, vo)
+        sc = qr @ kr.transpose(-1, -2) / math.sqrt(hd)
+        if causal:
+            sc = sc.masked_fill(~vis.to(dev()), float("-inf"))
+        oref = (torch.softmax(sc, dim=-1) * keep) @ vr
+        assert rel_err(o.float().view(B, Tq, H, hd).transpose(1, 2), oref) < tol(dtype, 2e-5, 2e-2)
+        go = torch.randn(B, Tq, D, generator=g).to(dev()).to(dtype).contiguous()
+        oref.backward(go.float().view(B, Tq, H, hd).transpose(1, 2))
+        if causal:
+            dqkv = torch.zeros_like(qkv)
+            ops.attn_bwd(qb, qo, kb, ko, vb, vo, o, go, lse, dqkv, 0, dqkv, D, dqkv, 2 * D, spec)
+            dq, dk, dv = dqkv[:, :, :D], dqkv[:, :, D:2 * D], dqkv[:, :, 2 * D:]
+        else:
+            dqb, dkvb = torch.zeros_like(qb), torch.zeros_like(kvb)
+            ops.attn_bwd(qb, qo, kb, ko, vb, vo, o, go, lse, dqb, 0, dkvb, 0, dkvb, D, spec)
+            dq, dk, dv = dqb, dkvb[:, :, :D], dkvb[:, :, D:]
+
+        def unheads(t):
+            return t.transpose(1, 2).reshape(B, -1, D)
+
+        assert rel_err(dq, unheads(qr.grad)) < tol(dtype, 1e-4, 4e-2)
+        assert rel_err(dk, unheads(kr.grad)) < tol(dtype, 1e-4, 4e-2)
+        assert rel_err(dv, unheads(vr.grad)) < tol(dtype, 1e-4, 4e-2)
+    # the state is one-shot: a following call without dropout is unaffected
+    spec0 = ops.AttnSpec(H, hd, causal=causal)
+    o0, _ = ops.attn_fwd(qb, qo, kb, ko, vb, vo, spec0)
+    o1, _ = ops.attn_fwd(qb, qo, kb, ko, vb, vo, spec0)
+    assert torch.equal(o0, o1)
+
+
 @pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("cfg", [(4, 4, 300, 0), (32, 4, 2337, 0), (2, 4, 77, 20), (1, 4, 1, 0)])
 def test_attn_decode(ops, dtype, cfg):
