@@ -13,6 +13,8 @@
 // key bias per (b, key) (0, +1.0 or -inf), keys visible to query t iff k <= t + Tk - Tq (causal) and
 // k >= t + Tk - Tq - window.  lse (natural log) is saved for the backward.
 // Warp roles: 0-3 softmax + epilogue (TMEM lanes 32w..32w+31), 4 TMA producer, 5 MMA issuer + TMEM allocator.
+#include <type_traits>
+
 #include "attn_drop.cuh"
 #include "kernels.h"
 #include "tc_common.cuh"
@@ -61,6 +63,104 @@ __device__ __forceinline__ void kv_tile_range(const AttnTcArgs& a, int q0, int& 
 
 __device__ __forceinline__ void softmax_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 __device__ __forceinline__ void softmax_bar2() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// ---- the per-tile work of a softmax thread (one query row, 128 keys of S in TMEM), specialised so that the common
+// tile -- every key visible to every row -- pays for no interval tests, and a call without key bias for no bias loads.
+// x = scale_log2 * S + bias (log2 units).  MASKED tiles (causal diagonal, window edge, ragged key tail) test the row's
+// visible interval [k_lo, k_hi] per key.
+struct SmRow {
+  uint32_t tmem_s;      // TMEM address of this row's S values
+  const float* bias;    // shared-memory bias tile of the 128 keys (pre-multiplied by log2 e)
+  float scale_log2;
+  int j0, k_lo, k_hi;   // first key of the tile, visible interval of the row
+};
+
+template <bool MASKED, bool BIAS>
+__device__ __forceinline__ float softmax_row_max(const SmRow& w) {
+  float mx = -INFINITY;
+#pragma unroll 1
+  for (int c = 0; c < 4; ++c) {
+    uint32_t v[32];
+    tmem_ld32(w.tmem_s + c * 32, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int e = 0; e < 32; e += 4) {
+      float bq[4] = {0.f, 0.f, 0.f, 0.f};
+      if (BIAS || MASKED) {
+        const float4 b4 = *reinterpret_cast<const float4*>(w.bias + c * 32 + e);
+        bq[0] = b4.x; bq[1] = b4.y; bq[2] = b4.z; bq[3] = b4.w;
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int j = w.j0 + c * 32 + e + k;
+        float x = __uint_as_float(v[e + k]);
+        if (BIAS || MASKED) x = fmaf(x, w.scale_log2, bq[k]);  // otherwise the (positive) scale is applied to the max
+        if (MASKED) x = (j >= w.k_lo && j <= w.k_hi) ? x : -INFINITY;
+        mx = fmaxf(mx, x);
+      }
+    }
+  }
+  return (BIAS || MASKED) ? mx : mx * w.scale_log2;
+}
+
+// P = exp2(x - m) -> row sum (returned) and the bf16 tile in the 128B-swizzled K-major operand layout; with DROP the
+// stored probabilities carry the keep mask / (1-p) while the sum stays that of the full row
+template <bool MASKED, bool BIAS, bool DROP>
+__device__ __forceinline__ float softmax_row_exp(const SmRow& w, float m_safe, uint8_t* sP, int r, int t, uint32_t dstream,
+                                                 uint32_t dkp, uint32_t thr, float inv_keep) {
+  float rs = 0.f;
+  const float nm = -m_safe;
+#pragma unroll 1
+  for (int c = 0; c < 4; ++c) {
+    uint32_t v[32];
+    tmem_ld32(w.tmem_s + c * 32, v);
+    tmem_ld_wait();
+    uint32_t pk[16];
+#pragma unroll
+    for (int e = 0; e < 32; e += 4) {
+      float bq[4] = {nm, nm, nm, nm};
+      if (BIAS || MASKED) {
+        const float4 b4 = *reinterpret_cast<const float4*>(w.bias + c * 32 + e);
+        bq[0] += b4.x; bq[1] += b4.y; bq[2] += b4.z; bq[3] += b4.w;
+      }
+      float pr[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int j = w.j0 + c * 32 + e + k;
+        pr[k] = ex2_approx(fmaf(__uint_as_float(v[e + k]), w.scale_log2, bq[k]));
+        if (MASKED) pr[k] = (j >= w.k_lo && j <= w.k_hi) ? pr[k] : 0.f;
+        rs += pr[k];
+      }
+      if (DROP) {
+#pragma unroll
+        for (int k = 0; k < 4; k += 2) {
+          const int j = w.j0 + c * 32 + e + k;
+          const uint2 blk = attn_drop_block(dstream, (uint32_t)(t >> 1), (uint32_t)(j >> 1), dkp);
+          const uint32_t word = (t & 1) ? blk.y : blk.x;
+          pr[k] = (word & 0xFFFFu) >= thr ? pr[k] * inv_keep : 0.f;
+          pr[k + 1] = (word >> 16) >= thr ? pr[k + 1] * inv_keep : 0.f;
+        }
+      }
+      pk[e >> 1] = pack_bf16(pr[0], pr[1]);
+      pk[(e >> 1) + 1] = pack_bf16(pr[2], pr[3]);
+    }
+    // keys c*32 .. c*32+31 = 64 bytes = 4 sixteen-byte units of row r in chunk c/2
+    uint8_t* rowp = sP + (c >> 1) * TILE + r * 128;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int unit = (c & 1) * 4 + u;
+      *reinterpret_cast<uint4*>(rowp + ((unit ^ (r & 7)) << 4)) = make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
+    }
+  }
+  return rs;
+}
 
 __global__ void __launch_bounds__(192, 2) attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
                                                              const __grid_constant__ CUtensorMap tmK,
@@ -177,23 +277,20 @@ __global__ void __launch_bounds__(192, 2) attn_fwd_tc_kernel(const __grid_consta
       softmax_bar();
       mbar_wait(s_full, i & 1);
       tc_fence_after();
-      // pass 1: row max
-      float mx = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld32(tmem_S + lane_addr + c * 32, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int e = 0; e < 32; ++e) {
-          const int j = j0 + c * 32 + e;
-          const float x = fmaf(__uint_as_float(v[e]), a.scale_log2, sBias[c * 32 + e]);
-          mx = fmaxf(mx, (j >= k_lo && j <= k_hi) ? x : -INFINITY);
-        }
+      // does every row of this CTA see every key of the tile?  (rows past Tq are never stored: they may see anything)
+      bool full = j0 + BKV <= a.Tk;
+      if (a.causal) {
+        full = full && (j0 + BKV - 1 <= q0 + off) && (a.window <= 0 || j0 >= q0 + BQ - 1 + off - a.window);
       }
+      const SmRow w{tmem_S + lane_addr, sBias, a.scale_log2, j0, k_lo, k_hi};
+      // pass 1: row max
+      float mx;
+      if (!full) mx = softmax_row_max<true, true>(w);
+      else if (kb) mx = softmax_row_max<false, true>(w);
+      else mx = softmax_row_max<false, false>(w);
       const float m_new = fmaxf(m_run, mx);
       const float m_safe = (m_new == -INFINITY) ? 0.f : m_new;
-      const float alpha = (m_run == -INFINITY) ? 0.f : exp2f(m_run - m_safe);
+      const float alpha = (m_run == -INFINITY) ? 0.f : ex2_approx(m_run - m_safe);
       if (i > 0) {
         mbar_wait(pv_full, (i - 1) & 1);
         tc_fence_after();
@@ -207,38 +304,17 @@ __global__ void __launch_bounds__(192, 2) attn_fwd_tc_kernel(const __grid_consta
         }
       }
       // pass 2: P = exp2(x - m), row sum, bf16 into the swizzled A-operand tile
-      float rs = 0.f;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld32(tmem_S + lane_addr + c * 32, v);
-        tmem_ld_wait();
-        uint32_t pk[16];
-#pragma unroll
-        for (int e = 0; e < 32; e += 2) {
-          const int j = j0 + c * 32 + e;
-          float x0 = fmaf(__uint_as_float(v[e]), a.scale_log2, sBias[c * 32 + e]);
-          float x1 = fmaf(__uint_as_float(v[e + 1]), a.scale_log2, sBias[c * 32 + e + 1]);
-          float p0 = (j >= k_lo && j <= k_hi) ? exp2f(x0 - m_safe) : 0.f;
-          float p1 = (j + 1 >= k_lo && j + 1 <= k_hi) ? exp2f(x1 - m_safe) : 0.f;
-          // the row sum uses the bf16-rounded probabilities that the P V product will see
-          __nv_bfloat162 pb = __floats2bfloat162_rn(p0, p1);
-          rs += __low2float(pb) + __high2float(pb);
-          if (a.drop.thr) {  // dropout acts on the normalised probabilities: the row sum stays that of the full row
-            const uint32_t bits = attn_drop_bits(dstream, (uint32_t)t, (uint32_t)(j >> 1), dkp);
-            p0 = (bits & 0xFFFFu) >= a.drop.thr ? p0 * a.drop.inv_keep : 0.f;
-            p1 = (bits >> 16) >= a.drop.thr ? p1 * a.drop.inv_keep : 0.f;
-            pb = __floats2bfloat162_rn(p0, p1);
-          }
-          pk[e >> 1] = *reinterpret_cast<uint32_t*>(&pb);
-        }
-        // keys c*32 .. c*32+31 = 64 bytes = 4 sixteen-byte units of row r in chunk c/2
-        uint8_t* rowp = sP + (c >> 1) * TILE + r * 128;
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int unit = (c & 1) * 4 + u;
-          *reinterpret_cast<uint4*>(rowp + ((unit ^ (r & 7)) << 4)) = make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
-        }
+      float rs;
+      const uint32_t thr = a.drop.thr;
+      const float ik = a.drop.inv_keep;
+      if (thr) {
+        if (!full) rs = softmax_row_exp<true, true, true>(w, m_safe, sP, r, t, dstream, dkp, thr, ik);
+        else if (kb) rs = softmax_row_exp<false, true, true>(w, m_safe, sP, r, t, dstream, dkp, thr, ik);
+        else rs = softmax_row_exp<false, false, true>(w, m_safe, sP, r, t, dstream, dkp, thr, ik);
+      } else {
+        if (!full) rs = softmax_row_exp<true, true, false>(w, m_safe, sP, r, t, dstream, dkp, thr, ik);
+        else if (kb) rs = softmax_row_exp<false, true, false>(w, m_safe, sP, r, t, dstream, dkp, thr, ik);
+        else rs = softmax_row_exp<false, false, false>(w, m_safe, sP, r, t, dstream, dkp, thr, ik);
       }
       l_run = l_run * alpha + rs;
       m_run = m_new;
@@ -484,7 +560,7 @@ __global__ void __launch_bounds__(320, 1) attn_bwd_tc_kernel(const __grid_consta
     const int j = j0 + r;
     const int off = a.Tk - a.Tq;
     const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
-    const float bias = (a.key_bias && j < a.Tk) ? a.key_bias[(long long)b * a.Tk + j] * LOG2E : 0.f;
+    const float bias = j < a.Tk ? (a.key_bias ? a.key_bias[(long long)b * a.Tk + j] * LOG2E : 0.f) : -INFINITY;
     // queries that can see key j: t in [t_lo, t_hi]
     int t_lo = 0, t_hi = a.Tq - 1;
     if (a.causal) {
@@ -529,40 +605,67 @@ __global__ void __launch_bounds__(320, 1) attn_bwd_tc_kernel(const __grid_consta
         tc_fence_after();
         dq_epilogue(qt0 + i - 1);
       }
+      // every (query, key) pair of this tile visible?  (then no interval tests; rows past Tk carry bias = -inf)
+      bool full = q0 + BQ <= a.Tq && j0 + BKV <= a.Tk;
+      if (a.causal) full = full && q0 >= j0 + BKV - 1 - off && (a.window <= 0 || q0 + BQ - 1 <= j0 - off + a.window);
+      auto tile_half = [&](auto masked_tag, auto drop_tag) {
+        constexpr bool MASKED = decltype(masked_tag)::value, DROP = decltype(drop_tag)::value;
 #pragma unroll 1
-      for (int c = 2 * hf; c < 2 * hf + 2; ++c) {
-        uint32_t sv[32], dv[32];
-        tmem_ld32(tmem_ST + lane_addr + c * 32, sv);
-        tmem_ld32(tmem_DPT + lane_addr + c * 32, dv);
-        tmem_ld_wait();
-        uint32_t pk[16], dk[16];
+        for (int c = 2 * hf; c < 2 * hf + 2; ++c) {
+          uint32_t sv[32], dv[32];
+          tmem_ld32(tmem_ST + lane_addr + c * 32, sv);
+          tmem_ld32(tmem_DPT + lane_addr + c * 32, dv);
+          tmem_ld_wait();
+          uint32_t pk[16], dk[16];
 #pragma unroll
-        for (int e = 0; e < 32; e += 2) {
-          const int t = q0 + c * 32 + e;
-          const float x0 = fmaf(__uint_as_float(sv[e]), a.scale_log2, bias) - sLse[c * 32 + e];
-          const float x1 = fmaf(__uint_as_float(sv[e + 1]), a.scale_log2, bias) - sLse[c * 32 + e + 1];
-          const float p0 = (t >= t_lo && t <= t_hi) ? exp2f(x0) : 0.f;
-          const float p1 = (t + 1 >= t_lo && t + 1 <= t_hi) ? exp2f(x1) : 0.f;
-          float f0 = 1.f, f1 = 1.f;  // mask / (1-p) of the pairs (t, j), (t+1, j)
-          if (a.drop.thr) {
-            const uint32_t b0 = attn_drop_bits(dstream, (uint32_t)t, (uint32_t)(j >> 1), dkp);
-            const uint32_t b1 = attn_drop_bits(dstream, (uint32_t)(t + 1), (uint32_t)(j >> 1), dkp);
-            f0 = ((b0 >> dsh) & 0xFFFFu) >= a.drop.thr ? a.drop.inv_keep : 0.f;
-            f1 = ((b1 >> dsh) & 0xFFFFu) >= a.drop.thr ? a.drop.inv_keep : 0.f;
+          for (int e = 0; e < 32; e += 4) {
+            const float4 l4 = *reinterpret_cast<const float4*>(sLse + c * 32 + e);
+            const float4 d4 = *reinterpret_cast<const float4*>(sDelta + c * 32 + e);
+            const float ls[4] = {bias - l4.x, bias - l4.y, bias - l4.z, bias - l4.w};
+            const float dl[4] = {d4.x, d4.y, d4.z, d4.w};
+            float pr[4], fk[4] = {1.f, 1.f, 1.f, 1.f};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int t = q0 + c * 32 + e + k;
+              pr[k] = ex2_approx(fmaf(__uint_as_float(sv[e + k]), a.scale_log2, ls[k]));
+              if (MASKED) pr[k] = (t >= t_lo && t <= t_hi) ? pr[k] : 0.f;
+            }
+            if (DROP) {  // mask / (1-p) of the pairs (t, j): one block serves the query pair (t, t+1)
+#pragma unroll
+              for (int k = 0; k < 4; k += 2) {
+                const int t = q0 + c * 32 + e + k;
+                const uint2 blk = attn_drop_block(dstream, (uint32_t)(t >> 1), (uint32_t)(j >> 1), dkp);
+                fk[k] = ((blk.x >> dsh) & 0xFFFFu) >= a.drop.thr ? a.drop.inv_keep : 0.f;
+                fk[k + 1] = ((blk.y >> dsh) & 0xFFFFu) >= a.drop.thr ? a.drop.inv_keep : 0.f;
+              }
+            }
+            float ds[4], pd[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              ds[k] = pr[k] * (DROP ? fmaf(__uint_as_float(dv[e + k]), fk[k], -dl[k]) : __uint_as_float(dv[e + k]) - dl[k]);
+              pd[k] = DROP ? pr[k] * fk[k] : pr[k];
+            }
+            pk[e >> 1] = pack_bf16(pd[0], pd[1]);
+            pk[(e >> 1) + 1] = pack_bf16(pd[2], pd[3]);
+            dk[e >> 1] = pack_bf16(ds[0], ds[1]);
+            dk[(e >> 1) + 1] = pack_bf16(ds[2], ds[3]);
           }
-          const float d0 = p0 * (__uint_as_float(dv[e]) * f0 - sDelta[c * 32 + e]);
-          const float d1 = p1 * (__uint_as_float(dv[e + 1]) * f1 - sDelta[c * 32 + e + 1]);
-          pk[e >> 1] = pack_bf16(p0 * f0, p1 * f1);
-          dk[e >> 1] = pack_bf16(d0, d1);
-        }
-        uint8_t* prow = sPT + (c >> 1) * TILE + r * 128;
-        uint8_t* drow = sDS + (c >> 1) * TILE + r * 128;
+          uint8_t* prow = sPT + (c >> 1) * TILE + r * 128;
+          uint8_t* drow = sDS + (c >> 1) * TILE + r * 128;
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int sw = (((c & 1) * 4 + u) ^ (r & 7)) << 4;
-          *reinterpret_cast<uint4*>(prow + sw) = make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
-          *reinterpret_cast<uint4*>(drow + sw) = make_uint4(dk[4 * u], dk[4 * u + 1], dk[4 * u + 2], dk[4 * u + 3]);
+          for (int u = 0; u < 4; ++u) {
+            const int sw = (((c & 1) * 4 + u) ^ (r & 7)) << 4;
+            *reinterpret_cast<uint4*>(prow + sw) = make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
+            *reinterpret_cast<uint4*>(drow + sw) = make_uint4(dk[4 * u], dk[4 * u + 1], dk[4 * u + 2], dk[4 * u + 3]);
+          }
         }
+      };
+      if (a.drop.thr) {
+        if (full) tile_half(std::false_type{}, std::true_type{});
+        else tile_half(std::true_type{}, std::true_type{});
+      } else {
+        if (full) tile_half(std::false_type{}, std::false_type{});
+        else tile_half(std::true_type{}, std::false_type{});
       }
       fence_proxy_async();
       tc_fence_before();
