@@ -371,24 +371,27 @@ __device__ __forceinline__ uint32_t mix32(uint32_t a, uint32_t b) {
   h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
   return h;
 }
+// keep decision of element `key`: one hash serves the two 16-bit uniforms of keys (2m, 2m+1); dropped iff uniform < thr
+__device__ __forceinline__ uint32_t drop_pair_bits(uint32_t seed, long long key) {
+  return mix32(seed ^ (uint32_t)(key >> 33) * 0x632BE5ABu, (uint32_t)(key >> 1));
+}
 template <typename T>
 __global__ void dropout_kernel(const T* __restrict__ x, T* __restrict__ y, long long n, int C, long long per_sample,
-                               float p, float scale, uint32_t seed, int channelwise, const int* __restrict__ seed_off) {
+                               uint32_t thr, float scale, uint32_t seed, int channelwise, const int* __restrict__ seed_off) {
   if (seed_off) seed += (uint32_t)(*seed_off) * 0x9E3779B9u;
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long stride = (long long)gridDim.x * blockDim.x;
   for (; i < n; i += stride) {
     long long key = channelwise ? (i / per_sample) * C + (i % C) : i;
-    uint32_t h = mix32(seed ^ (uint32_t)(key >> 32) * 0x632BE5ABu, (uint32_t)key);
-    float u = (h >> 8) * (1.0f / 16777216.0f);
-    y[i] = u < p ? from_f<T>(0.f) : from_f<T>(to_f(x[i]) * scale);
+    const uint32_t u = (drop_pair_bits(seed, key) >> ((uint32_t)(key & 1) * 16)) & 0xFFFFu;
+    y[i] = u < thr ? from_f<T>(0.f) : from_f<T>(to_f(x[i]) * scale);
   }
 }
-// same mask function, 4 elements per thread (8/16-byte accesses); needs n % 4 == 0 and, for the channel-wise form,
-// C % 4 == 0 so that a quad never straddles a sample/channel-row boundary
+// same mask function, 4 elements per thread (8/16-byte accesses, two hashes); needs n % 4 == 0 and, for the
+// channel-wise form, C % 4 == 0 so that a quad never straddles a sample/channel-row boundary (its first key is even)
 template <typename T>
 __global__ void dropout_vec_kernel(const T* __restrict__ x, T* __restrict__ y, long long n4, int C, long long per_sample,
-                                   float p, float scale, uint32_t seed, int channelwise, const int* __restrict__ seed_off) {
+                                   uint32_t thr, float scale, uint32_t seed, int channelwise, const int* __restrict__ seed_off) {
   if (seed_off) seed += (uint32_t)(*seed_off) * 0x9E3779B9u;
   long long i4 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long stride = (long long)gridDim.x * blockDim.x;
@@ -398,11 +401,10 @@ __global__ void dropout_vec_kernel(const T* __restrict__ x, T* __restrict__ y, l
     load4(x + i, v);
     const long long key0 = channelwise ? (i / per_sample) * C + (i % C) : i;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const long long key = key0 + k;
-      const uint32_t h = mix32(seed ^ (uint32_t)(key >> 32) * 0x632BE5ABu, (uint32_t)key);
-      const float u = (h >> 8) * (1.0f / 16777216.0f);
-      v[k] = u < p ? 0.f : v[k] * scale;
+    for (int k = 0; k < 4; k += 2) {
+      const uint32_t h = drop_pair_bits(seed, key0 + k);
+      v[k] = (h & 0xFFFFu) < thr ? 0.f : v[k] * scale;
+      v[k + 1] = (h >> 16) < thr ? 0.f : v[k + 1] * scale;
     }
     store4(y + i, v);
   }
@@ -412,18 +414,19 @@ extern "C" int omr_dropout(int dt, const void* x, void* y, long long n, int C, l
   OMR_REQUIRE(p >= 0.f && p < 1.f, "omr_dropout: p must be in [0,1) (got %f)", p);
   OMR_REQUIRE(C > 0 && per_sample > 0, "omr_dropout: bad channel geometry");
   if (n <= 0) return OMR_OK;
+  const uint32_t thr = (uint32_t)(p * 65536.f + 0.5f);  // 16-bit uniforms: p = 0.1 -> 0.100006, 0.25 and 0.5 exact
   {
     const int esz = dt == OMR_F32 ? 4 : 2;
     if (n % 4 == 0 && (!channelwise || (C % 4 == 0 && per_sample % 4 == 0)) && (reinterpret_cast<uintptr_t>(x) % (4 * esz)) == 0 &&
         (reinterpret_cast<uintptr_t>(y) % (4 * esz)) == 0) {
       OMR_DISPATCH_DT(dt, T, (dropout_vec_kernel<T><<<grid_for(n / 4, 256, 2), 256, 0, as_stream(stream)>>>(
-                                 (const T*)x, (T*)y, n / 4, C, per_sample, p, 1.f / (1.f - p), (uint32_t)seed, channelwise, seed_offset)));
+                                 (const T*)x, (T*)y, n / 4, C, per_sample, thr, 1.f / (1.f - p), (uint32_t)seed, channelwise, seed_offset)));
       OMR_LAUNCHED();
       return OMR_OK;
     }
   }
   OMR_DISPATCH_DT(dt, T, (dropout_kernel<T><<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(
-                             (const T*)x, (T*)y, n, C, per_sample, p, 1.f / (1.f - p), (uint32_t)seed, channelwise, seed_offset)));
+                             (const T*)x, (T*)y, n, C, per_sample, thr, 1.f / (1.f - p), (uint32_t)seed, channelwise, seed_offset)));
   OMR_LAUNCHED();
   return OMR_OK;
 }
