@@ -413,7 +413,14 @@ def main():
         }
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # Leave without tearing NCCL down: the captured training-step graphs hold the communicator's kernels, and
+        # ncclCommDestroy behind destroy_process_group() was seen to wait forever on them after the line was printed
+        # (round 1, N = 2).  Everything is measured and flushed; a barrier keeps the ranks together, then a hard exit.
+        torch.cuda.synchronize(dev)
+        dist.barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":

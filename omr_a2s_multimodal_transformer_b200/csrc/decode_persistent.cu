@@ -228,6 +228,12 @@ struct Ring {
     }
     return base + (size_t)slot * SLOT_BYTES;
   }
+  // chunk consumed + ahead (ahead < NSLOT - DEFER: it has been issued)
+  __device__ __forceinline__ const uint8_t* acquire_at(int ahead) {
+    const int g = consumed + ahead, slot = g % NSLOT;
+    mbar_wait(&full[slot], (uint32_t)((g / NSLOT) & 1));
+    return base + (size_t)slot * SLOT_BYTES;
+  }
   // this warp has the slot's values in registers: hand the slot back; its owner refills the slot freed DEFER chunks ago
   __device__ __forceinline__ void release() {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -271,54 +277,75 @@ __device__ __forceinline__ void layer_norm(float (&v)[8], const float* gamma, co
   for (int k = 0; k < 8; ++k) v[k] = (v[k] - mean) * rstd * g[k] + b[k];
 }
 
-// the two columns (2 warp, 2 warp + 1 of the slot's 32) of this warp and their biases; every lane gets both sums
+// Two ring slots at a time: this warp's four columns (2 warp, 2 warp + 1 of each slot's 32).  The four dot products are
+// reduced with a reduce-scatter (6 shuffles instead of 20): lane l ends up with the sum -- bias included -- of column
+// q = l >> 3 (slot q >> 1, column 2 warp + (q & 1)), replicated over the 8 lanes of its group; sub-lanes 0..3 of a group
+// are the four senders (one per CTA of the cluster).  `second` = false: only the first slot is valid (odd tail).
 template <typename T>
-__device__ __forceinline__ void gemv_slot(const uint8_t* slot, const float (&x)[8], float& d0, float& d1, float2& bias) {
+__device__ __forceinline__ float gemv_pair(const uint8_t* s0, const uint8_t* s1, bool second, const float (&x)[8], bool use_bias = true) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const T* w = reinterpret_cast<const T*>(slot) + (2 * warp) * DP_D + lane * 8;
-  Raw8<T> r0, r1;
-  r0.load(w);
-  r1.load(w + DP_D);
-  bias = *reinterpret_cast<const float2*>(slot + Ring<T>::W_BYTES + 8 * warp);
-  float w0[8], w1[8];
-  r0.get(w0);
-  r1.get(w1);
-  d0 = 0.f; d1 = 0.f;
-#pragma unroll
-  for (int e = 0; e < 8; ++e) { d0 = fmaf(x[e], w0[e], d0); d1 = fmaf(x[e], w1[e], d1); }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    d0 += __shfl_xor_sync(0xffffffffu, d0, o);
-    d1 += __shfl_xor_sync(0xffffffffu, d1, o);
+  const int q = lane >> 3;
+  Raw8<T> r[4];
+  const T* w0 = reinterpret_cast<const T*>(s0) + (2 * warp) * DP_D + lane * 8;
+  r[0].load(w0);
+  r[1].load(w0 + DP_D);
+  if (second) {
+    const T* w1 = reinterpret_cast<const T*>(s1) + (2 * warp) * DP_D + lane * 8;
+    r[2].load(w1);
+    r[3].load(w1 + DP_D);
+  } else {
+    r[2].zero();
+    r[3].zero();
   }
+  const float bias = (use_bias && (second || q < 2)) ? *reinterpret_cast<const float*>(((q & 2) ? s1 : s0) + Ring<T>::W_BYTES + 8 * warp + 4 * (q & 1)) : 0.f;
+  float d[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    float w[8];
+    r[c].get(w);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) d[c] = fmaf(x[e], w[e], d[c]);
+  }
+  const bool hi = lane & 16, mid = lane & 8;
+  // step 1 (xor 16): lanes with bit 4 clear keep columns 0, 1 and send 2, 3 (and vice versa)
+  const float k0 = (hi ? d[2] : d[0]) + __shfl_xor_sync(0xffffffffu, hi ? d[0] : d[2], 16);
+  const float k1 = (hi ? d[3] : d[1]) + __shfl_xor_sync(0xffffffffu, hi ? d[1] : d[3], 16);
+  // step 2 (xor 8): bit 3 clear keeps the even column
+  float v = (mid ? k1 : k0) + __shfl_xor_sync(0xffffffffu, mid ? k0 : k1, 8);
+  v += __shfl_xor_sync(0xffffffffu, v, 4);
+  v += __shfl_xor_sync(0xffffffffu, v, 2);
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  return v + bias;
 }
-// A projection of NCH ring slots per CTA: x = xs (shared memory), optionally LayerNorm'ed with the parameters that
-// travel in the first slot (the normalised vector is then also kept in x_keep for a later residual);
-// epi(ch, j, value) runs on all 32 lanes for column ch*32 + 2*warp + j of the CTA's share.
+// A projection of NCH (even) ring slots per CTA: x = xs (shared memory), optionally LayerNorm'ed with the parameters
+// that travel in the first slot (the normalised vector is then also kept in x_keep for a later residual);
+// epi(c, value, sub) runs once per lane: c = column of the CTA's share that this lane's group holds, sub = lane & 7.
 template <typename T, int NCH, typename Epi>
 __device__ __forceinline__ void gemv_phase(Ring<T>& R, const float* xs, bool LN, float* x_keep, float eps, Epi epi, long long* dbg = nullptr) {
+  static_assert(NCH % 2 == 0, "slots are consumed in pairs");
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   long long t0 = dbg ? clock64() : 0;
-  const uint8_t* slot = R.acquire();
+  const uint8_t* s0 = R.acquire_at(0);
   if (dbg) { long long t = clock64(); dbg[0] += t - t0; t0 = t; }
   float x[8];
   load_vec(xs, x);
   if (LN) {
-    const float* gamma = reinterpret_cast<const float*>(slot + Ring<T>::W_BYTES + 128);
+    const float* gamma = reinterpret_cast<const float*>(s0 + Ring<T>::W_BYTES + 128);
     layer_norm(x, gamma, gamma + DP_D, eps);
     if (x_keep && threadIdx.x < 32) store_vec(x_keep, x);
   }
   if (dbg) { long long t = clock64(); dbg[1] += t - t0; t0 = t; }
 #pragma unroll
-  for (int ch = 0; ch < NCH; ++ch) {
-    if (ch > 0) slot = R.acquire();
+  for (int ch = 0; ch < NCH; ch += 2) {
+    if (ch > 0) s0 = R.acquire_at(0);
+    const uint8_t* s1 = R.acquire_at(1);
     if (dbg) { long long t = clock64(); dbg[2] += t - t0; t0 = t; }
-    float d0, d1;
-    float2 bias;
-    gemv_slot<T>(slot, x, d0, d1, bias);
+    const float v = gemv_pair<T>(s0, s1, true, x);
+    R.release();
     R.release();
     if (dbg) { long long t = clock64(); dbg[3] += t - t0; t0 = t; }
-    epi(ch, 0, d0 + bias.x);
-    epi(ch, 1, d1 + bias.y);
+    const int q = lane >> 3;
+    epi((ch + (q >> 1)) * DP_CH + 2 * warp + (q & 1), v, lane & 7);
     if (dbg) { long long t = clock64(); dbg[4] += t - t0; t0 = t; }
   }
 }
@@ -723,15 +750,15 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_persistent_kernel(DPArgs
       //     the steps to come, into the cache
       {
         T* crow = W.self_kv + ((long long)b * p.Tmax + pos) * (2 * DP_D);
-        gemv_phase<T, 6>(R, l == 0 ? xv : sv, l > 0, xv, p.ln_eps, [&](int ch, int j, float v) {
-          const int n = rank * 192 + ch * DP_CH + 2 * warp + j;
+        gemv_phase<T, 6>(R, l == 0 ? xv : sv, l > 0, xv, p.ln_eps, [&](int c, float v, int sub) {
+          const int n = rank * 192 + c;
           if (n < DP_D) {
-            if (lane < DP_CL) st_async(qv + n, v, lane, &vb[VB_Q]);
+            if (sub < DP_CL) st_async(qv + n, v, sub, &vb[VB_Q]);
           } else {
             const T r = from_f<T>(v);
             const int m = n - DP_D;  // 0..255 key, 256..511 value; 64 per head
-            if (lane == 0) st_async((m < DP_D ? kn : vn) + (m & (DP_HD - 1)), to_f(r), (unsigned)((m >> 6) & 3), &vb[VB_Q]);
-            if (lane == 1) crow[m] = r;
+            if (sub == 0) st_async((m < DP_D ? kn : vn) + (m & (DP_HD - 1)), to_f(r), (unsigned)((m >> 6) & 3), &vb[VB_Q]);
+            if (sub == 1) crow[m] = r;
           }
         });
       }
@@ -746,15 +773,14 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_persistent_kernel(DPArgs
       VEC_WAIT(VB_A, 4 * DP_D, PH_SELF);
       prefetch_rows<T>(W.cross_kv + (long long)b * p.S * 2 * DP_D, 0, p.S < p.pf_cross ? p.S : p.pf_cross, rank);
       // P3: s = x + out_proj(a)
-      gemv_phase<T, 2>(R, av, false, nullptr, 0.f, [&](int ch, int j, float v) {
-        const int n = rank * 64 + ch * DP_CH + 2 * warp + j;
-        if (lane < DP_CL) st_async(sv + n, v + xv[n], lane, &vb[VB_S]);
+      gemv_phase<T, 2>(R, av, false, nullptr, 0.f, [&](int c, float v, int sub) {
+        const int n = rank * 64 + c;
+        if (sub < DP_CL) st_async(sv + n, v + xv[n], sub, &vb[VB_S]);
       }, timed ? dbgc : nullptr);
       VEC_WAIT(VB_S, 4 * DP_D, PH_OUT);
       // P4: x1 = LN1(s) (kept in xv for P6's residual) -> cross query
-      gemv_phase<T, 2>(R, sv, true, xv, p.ln_eps, [&](int ch, int j, float v) {
-        const int n = rank * 64 + ch * DP_CH + 2 * warp + j;
-        if (lane < DP_CL) st_async(qv + n, v, lane, &vb[VB_Q]);
+      gemv_phase<T, 2>(R, sv, true, xv, p.ln_eps, [&](int c, float v, int sub) {
+        if (sub < DP_CL) st_async(qv + rank * 64 + c, v, sub, &vb[VB_Q]);
       });
       VEC_WAIT(VB_Q, 4 * DP_D, PH_CQ);
       // P5: cross-attention of head `rank` over the projected encoder memory
@@ -769,21 +795,20 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_persistent_kernel(DPArgs
         prefetch_rows<T>(layers[nl].self_kv + (long long)b * p.Tmax * 2 * DP_D, lo, npos, rank);
       }
       // P6: s = x1 + cross out_proj(a)
-      gemv_phase<T, 2>(R, av, false, nullptr, 0.f, [&](int ch, int j, float v) {
-        const int n = rank * 64 + ch * DP_CH + 2 * warp + j;
-        if (lane < DP_CL) st_async(sv + n, v + xv[n], lane, &vb[VB_S]);
+      gemv_phase<T, 2>(R, av, false, nullptr, 0.f, [&](int c, float v, int sub) {
+        const int n = rank * 64 + c;
+        if (sub < DP_CL) st_async(sv + n, v + xv[n], sub, &vb[VB_S]);
       });
       VEC_WAIT(VB_S, 4 * DP_D, PH_COUT);
       // P7: x2 = LN2(s) (kept in xv for P8's residual) -> h = relu(W1 x2 + b1)
-      gemv_phase<T, 2>(R, sv, true, xv, p.ln_eps, [&](int ch, int j, float v) {
-        const int n = rank * 64 + ch * DP_CH + 2 * warp + j;
-        if (lane < DP_CL) st_async(hv + n, fmaxf(v, 0.f), lane, &vb[VB_H]);
+      gemv_phase<T, 2>(R, sv, true, xv, p.ln_eps, [&](int c, float v, int sub) {
+        if (sub < DP_CL) st_async(hv + rank * 64 + c, fmaxf(v, 0.f), sub, &vb[VB_H]);
       });
       VEC_WAIT(VB_H, 4 * DP_D, PH_FFN1);
       // P8: s = x2 + W2 h + b2
-      gemv_phase<T, 2>(R, hv, false, nullptr, 0.f, [&](int ch, int j, float v) {
-        const int n = rank * 64 + ch * DP_CH + 2 * warp + j;
-        if (lane < DP_CL) st_async(sv + n, v + xv[n], lane, &vb[VB_S]);
+      gemv_phase<T, 2>(R, hv, false, nullptr, 0.f, [&](int c, float v, int sub) {
+        const int n = rank * 64 + c;
+        if (sub < DP_CL) st_async(sv + n, v + xv[n], sub, &vb[VB_S]);
       });
       VEC_WAIT(VB_S, 4 * DP_D, PH_FFN2);
     }
@@ -791,43 +816,43 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_persistent_kernel(DPArgs
     {
       float best = -INFINITY;
       int bi = 0x7fffffff;
-      // a ragged classifier tail (V % 4 columns) cannot travel by bulk copy: its owner warp reads those biases here
-      float tb0 = 0.f, tb1 = 0.f;
-      {
-        const int c0 = (nvch - 1) * DP_CH + 2 * warp, lim = (ncols_v - (nvch - 1) * DP_CH) & ~3;
-        if (nvch > 0 && c0 < ncols_v && 2 * warp >= lim) tb0 = p.b_out[vbeg + c0];
-        if (nvch > 0 && c0 + 1 < ncols_v && 2 * warp + 1 >= lim) tb1 = p.b_out[vbeg + c0 + 1];
-      }
+      // a ragged classifier tail (V % 4 columns) cannot travel by bulk copy: the lanes that own those columns read their
+      // bias here (one L2 round trip per token, hidden behind the whole phase)
+      const int q = lane >> 3;
+      const int lastc = (nvch - 1) * DP_CH + 2 * warp + (q & 1);     // this lane's column if it sits in the last slot
+      const int lim = (ncols_v - (nvch - 1) * DP_CH) & ~3;
+      const bool tail_bias = nvch > 0 && lastc < ncols_v && 2 * warp + (q & 1) >= lim;
+      const float tb = tail_bias ? p.b_out[vbeg + lastc] : 0.f;
       float x[8];
       if (nvch > 0) {
-        const uint8_t* slot = R.acquire();
+        const uint8_t* slot = R.acquire_at(0);
         load_vec(sv, x);
         const float* gamma = reinterpret_cast<const float*>(slot + Ring<T>::W_BYTES + 128);
         layer_norm(x, gamma, gamma + DP_D, p.ln_eps);
       }
-      for (int ch = 0; ch < nvch; ++ch) {
-        const uint8_t* slot = R.acquire();
-        float d0, d1;
-        float2 bias;
-        gemv_slot<T>(slot, x, d0, d1, bias);
+      for (int ch = 0; ch < nvch; ch += 2) {
+        const bool second = ch + 1 < nvch;
+        const uint8_t* s0 = R.acquire_at(0);
+        const uint8_t* s1 = second ? R.acquire_at(1) : s0;
+        const int myslot = ch + (q >> 1);
+        const int c = myslot * DP_CH + 2 * warp + (q & 1);
+        const bool own_bias = myslot == nvch - 1 && tail_bias;  // the slot holds a stale value past the bulk-copied biases
+        float v = gemv_pair<T>(s0, s1, second, x, !own_bias);
         R.release();
-        const int c0 = ch * DP_CH + 2 * warp;
-        if (ch == nvch - 1) {  // columns past the bulk-copied biases: the slot holds stale values there
-          const int lim = (ncols_v - ch * DP_CH) & ~3;
-          if (2 * warp >= lim) bias.x = tb0;
-          if (2 * warp + 1 >= lim) bias.y = tb1;
-        }
-        d0 += bias.x;
-        d1 += bias.y;
+        if (second) R.release();
+        if (own_bias) v += tb;
         // the per-kernel path rounds logits to the storage type before the argmax; do the same so that ties resolve alike
-        if (c0 < ncols_v) {
-          const float r = to_f(from_f<T>(d0));
-          if (r > best) { best = r; bi = vbeg + c0; }  // columns ascend within a warp: strict > keeps the first max
+        if (myslot < nvch && c < ncols_v) {
+          const float r = to_f(from_f<T>(v));
+          if (r > best) { best = r; bi = vbeg + c; }  // a lane's columns ascend: strict > keeps the first max
         }
-        if (c0 + 1 < ncols_v) {
-          const float r = to_f(from_f<T>(d1));
-          if (r > best) { best = r; bi = vbeg + c0 + 1; }
-        }
+      }
+      // the four column groups of the warp (lanes 0, 8, 16, 24): first-max merge
+#pragma unroll
+      for (int o = 8; o <= 16; o <<= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
       }
       if (lane == 0) { cand_v[warp] = best; cand_i[warp] = bi; }
       __syncthreads();

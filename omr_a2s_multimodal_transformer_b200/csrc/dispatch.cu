@@ -78,6 +78,12 @@ extern "C" int omr_conv3x3_wgrad(int dt, const void* x, const void* dy, float* d
     if (rc1 != OMR_TC_NOT_ELIGIBLE) return rc1;
   }
   if (tc_enabled() && dt == OMR_BF16) {
+    static int small_path = -1;  // narrow stride-1 layers: ldmatrix + mma.sync kernel (OMR_WGRAD_SMALL=0 disables)
+    if (small_path < 0) {
+      const char* e = getenv("OMR_WGRAD_SMALL");
+      small_path = (e && e[0] == '0') ? 0 : 1;
+    }
+    if (small_path) TC_TRY(omr_conv3x3_wgrad_small(x, dy, dw, N, H, W, Ci, Co, sh, sw, accumulate, st));
     TC_TRY(omr_conv3x3_wgrad_tc(x, dy, dw, N, H, W, Ci, Co, sh, sw, accumulate, st));
   }
   return omr_conv3x3_wgrad_simt(dt, x, dy, dw, N, H, W, Ci, Co, sh, sw, accumulate, st);

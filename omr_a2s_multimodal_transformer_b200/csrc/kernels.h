@@ -49,5 +49,7 @@ int omr_attn_bwd_tc(const void* q, long long q_bs, long long q_rs, const void* k
                     long long dq_rs, void* dk, long long dk_bs, long long dk_rs, void* dv, long long dv_bs, long long dv_rs,
                     float* ws, const float* key_bias, int B, int H, int Tq, int Tk, int hd, float scale, int causal,
                     int window, const int* q_len, const int* kv_len, cudaStream_t st);
+int omr_conv3x3_wgrad_small(const void* x, const void* dy, float* dw, int N, int H, int W, int Ci, int Co, int sh, int sw,
+                            int accumulate, cudaStream_t st);
 int omr_conv3x3_wgrad_c1(int dt, const void* x, const void* dy, float* dw, int N, int H, int W, int Co, int sh, int sw,
                          int accumulate, cudaStream_t st);

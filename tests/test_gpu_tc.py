@@ -144,7 +144,8 @@ def test_conv3x3_tc_fwd_dgrad(ops, case):
     assert rel_err(dx.permute(0, 3, 1, 2).float(), gx_ref) < 6e-3
 
 
-@pytest.mark.parametrize("case", CONV_TC_CASES + [(4, 64, 512, 16, 16, (1, 1)), (2, 32, 256, 64, 128, (2, 2))])
+@pytest.mark.parametrize("case", CONV_TC_CASES + [(4, 64, 512, 16, 16, (1, 1)), (2, 32, 256, 64, 128, (2, 2)), (2, 20, 70, 32, 16, (1, 1)),
+                                                  (3, 17, 99, 32, 32, (1, 1))])
 def test_conv3x3_tc_wgrad(ops, case):
     import torch.nn.functional as F
 
