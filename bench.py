@@ -151,6 +151,13 @@ def run_reference(args, w2i):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # torchrun exports OMP_NUM_THREADS=1 to its workers: the reference arm takes all the host threads it may use
+    try:
+        avail = len(os.sched_getaffinity(0))
+    except AttributeError:
+        avail = os.cpu_count() or 1
+    if torch.get_num_threads() < avail:
+        torch.set_num_threads(avail)
     cores = torch.get_num_threads()
     b = args.cpu_batch
     step = cpu_reference_step_fn(w2i, b)
