@@ -10,6 +10,8 @@
 // warp 4 TMA producer, warp 5 MMA issuer + TMEM allocator.  The decoder's GEMMs have K = 256, i.e. they are
 // HBM-bound (AI ~ 50 flop/B): BN covers the whole N when N <= 256 so that A is read from HBM exactly once,
 // and 2-3 CTAs are resident per SM so that one tile's stores overlap the next tile's loads.
+#include <stdlib.h>
+
 #include "kernels.h"
 #include "tc_common.cuh"
 
@@ -306,6 +308,17 @@ int omr_gemm_tc(int out_dt, int transA, int transB, int M, int N, int K, const v
   if ((long long)M * N * K < (1LL << 18)) return OMR_TC_NOT_ELIGIBLE;
   if (M <= 64 && !a_mn && !b_mn && !accumulate) return OMR_TC_NOT_ELIGIBLE;
   int BN = N <= 32 ? 32 : (N <= 64 ? 64 : (N <= 128 ? 128 : 256));
+  static int bn_cap = -1, split_div = -1;
+  if (bn_cap < 0) {
+    const char* e = getenv("OMR_GEMM_BN_CAP");
+    bn_cap = e ? atoi(e) : 128;
+    const char* f = getenv("OMR_GEMM_SPLIT_DIV");
+    split_div = f ? atoi(f) : 8;
+    if (split_div < 1) split_div = 8;
+  }
+  // short-K problems with few tiles (the decoder's 256-wide projections): narrower tiles double the CTA count so that
+  // two CTAs share an SM and one's loads overlap the other's epilogue
+  if (bn_cap > 0 && BN > bn_cap && (long long)((M + BM - 1) / BM) * ((N + BN - 1) / BN) < 2 * 148) BN = bn_cap;
   if (b_mn && BN < 64) BN = 64;
   if (a_mn && BN < 64) BN = 64;
 
@@ -332,7 +345,7 @@ int omr_gemm_tc(int out_dt, int transA, int transB, int M, int N, int K, const v
     // gradient accumulation: split the long reduction across CTAs until the machine is full
     long long tiles = (long long)tiles_m * tiles_n;
     long long want = (148 + tiles - 1) / tiles;
-    long long cap = kb_total / 8;
+    long long cap = kb_total / split_div;
     if (want > cap) want = cap;
     if (want > 1) { splits = (int)want; acc_mode = 2; }
   }

@@ -15,6 +15,8 @@
 // A warp keeps one 16 x 16 (co x ci) block of all nine taps in registers (72 fp32) across its whole pixel range; wider
 // layers split the blocks over the warps.  Partial sums are combined in shared memory and added to the fp32 gradient
 // with one atomic per element and CTA.  Warp roles: 0-7 MMA, 8 TMA producer.
+#include <stdlib.h>
+
 #include "kernels.h"
 #include "tc_common.cuh"
 
@@ -192,7 +194,19 @@ int omr_conv3x3_wgrad_small(const void* x, const void* dy, float* dw, int N, int
   const int rba = Co * 2, rbb = Ci * 2;
   g.a_bytes = (WS_TH * WS_TW * rba + 1023) / 1024 * 1024;
   g.stage_bytes = g.a_bytes + ((WS_TH + 2) * WS_PITCH * rbb + 1023) / 1024 * 1024;
+  // two CTAs per SM hide the ldmatrix / mma.sync latencies better than a deeper pipeline: 3 stages where 4 would
+  // leave room for only one CTA
   g.stages = 4;
+  {
+    static int forced = -1;
+    if (forced < 0) {
+      const char* e = getenv("OMR_WGRAD_SMALL_STAGES");
+      forced = e ? atoi(e) : 0;
+    }
+    if (forced >= 2 && forced <= 8) g.stages = forced;
+    else if (2 * (4 * g.stage_bytes + 3 * 1024) > 220 * 1024 && 2 * (3 * g.stage_bytes + 3 * 1024) <= 220 * 1024) g.stages = 3;
+    else if (2 * (3 * g.stage_bytes + 3 * 1024) > 220 * 1024 && 2 * (2 * g.stage_bytes + 3 * 1024) <= 220 * 1024) g.stages = 2;
+  }
   int smem_bytes = g.stages * g.stage_bytes + 1024 + 256;
   const int red_bytes = Co * Ci * 9 * 4 + 1024 + 256;
   if (smem_bytes < red_bytes) smem_bytes = red_bytes;
