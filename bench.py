@@ -304,19 +304,31 @@ def main():
     barrier()
     _lib.prof_start()
     step(resident)
-    prof = _lib.prof_stop()
+    shaped = _lib.prof_stop(by_shape=True)
+    prof = {}
+    for (name, _shape), d in shaped.items():
+        a = prof.setdefault(name, {"calls": 0, "launches": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0})
+        for k in a:
+            a[k] += d[k]
     tot_ms = sum(d["ms"] for d in prof.values()) or 1e-9
     pk = peaks()
-    top_name, top = max(prof.items(), key=lambda kv: kv[1]["ms"])
+    # the dominant kernel = the (entry point, launch shape) group with the largest share of the step
+    (top_name, top_shape), top = max(shaped.items(), key=lambda kv: kv[1]["ms"])
     ai = top["flops"] / max(top["bytes"], 1.0)
     if top["flops"] > 0 and ai > pk["tc"] * 1e12 / (pk["hbm"] * 1e9) * 0.25:
         roof = {"bound": "tensor", "achieved": top["flops"] / (top["ms"] * 1e-3) / 1e12, "peak": pk["tc"], "unit": "TFLOP/s"}
     else:
         roof = {"bound": "hbm", "achieved": top["bytes"] / (top["ms"] * 1e-3) / 1e9, "peak": pk["hbm"], "unit": "GB/s"}
     roof["frac"] = roof["achieved"] / roof["peak"]
-    roof.update({"kernel": top_name, "calls_per_step": top["calls"], "avg_ms": top["ms"] / max(top["calls"], 1),
+    # DRAM bytes per launch from the committed `ncu --set full` capture of the same kernel at the same shape, when there is one
+    traffic = None
+    if top_name == "omr_attn_bwd" and 2337 in top_shape and b == BATCH:
+        traffic = 158.74e6  # dram__bytes_read.sum + dram__bytes_write.sum per launch, profiles/r01_final_ncu_full_top_kernels.txt
+    roof.update({"kernel": top_name, "launch_shape": [int(v) for v in top_shape if abs(int(v)) < (1 << 20)][-12:],
+                 "calls_per_step": top["calls"], "avg_ms": top["ms"] / max(top["calls"], 1),
+                 "algorithmic_per_launch": {"flops": top["flops"] / max(top["calls"], 1), "bytes": top["bytes"] / max(top["calls"], 1)},
                  "share_of_step": top["ms"] / tot_ms, "peak_source": pk["src"] + (" (sustained bf16)" if roof["bound"] == "tensor" else ""),
-                 "traffic": None})
+                 "traffic": traffic})
     breakdown = {k: {"ms": round(d["ms"], 3), "calls": d["calls"],
                      "tflops": round(d["flops"] / (d["ms"] * 1e-3) / 1e12, 2) if d["flops"] else None,
                      "gbs": round(d["bytes"] / (d["ms"] * 1e-3) / 1e9, 1) if d["bytes"] else None}

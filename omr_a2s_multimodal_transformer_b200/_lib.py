@@ -179,8 +179,9 @@ def prof_start() -> None:
     _prof = []
 
 
-def prof_stop() -> dict:
-    """-> {entry point: {calls, launches, ms, flops, bytes}} summed over the calls since prof_start()"""
+def prof_stop(by_shape: bool = False) -> dict:
+    """-> {entry point: {calls, launches, ms, flops, bytes}} summed over the calls since prof_start(); with ``by_shape``
+    the key is (entry point, tuple of the call's small integer arguments), i.e. one kernel at one launch shape"""
     global _prof
     recs, _prof = _prof or [], None
     torch.cuda.synchronize()
@@ -192,7 +193,8 @@ def prof_stop() -> dict:
                 ms = e0.elapsed_time(e1)
                 f.write(f"{name}\t{ms:.4f}\t{fl / (ms * 1e-3) / 1e12 if ms > 0 else 0:.1f}\t{by / (ms * 1e-3) / 1e9 if ms > 0 else 0:.0f}\t{ints}\n")
     for name, (fl, by), nl, e0, e1, _ints in recs:
-        d = out.setdefault(name, {"calls": 0, "launches": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0})
+        key = (name, tuple(_ints)) if by_shape else name
+        d = out.setdefault(key, {"calls": 0, "launches": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0})
         d["calls"] += 1
         d["launches"] += nl
         d["ms"] += e0.elapsed_time(e1)

@@ -139,14 +139,17 @@ __device__ __forceinline__ float softmax_row_exp(const SmRow& w, float m_safe, u
         rs += pr[k];
       }
       if (DROP) {
-#pragma unroll
-        for (int k = 0; k < 4; k += 2) {
-          const int j = w.j0 + c * 32 + e + k;
-          const uint2 blk = attn_drop_block(dstream, (uint32_t)(t >> 1), (uint32_t)(j >> 1), dkp);
-          const uint32_t word = (t & 1) ? blk.y : blk.x;
-          pr[k] = (word & 0xFFFFu) >= thr ? pr[k] * inv_keep : 0.f;
-          pr[k + 1] = (word >> 16) >= thr ? pr[k + 1] * inv_keep : 0.f;
-        }
+        // rows t and t^1 (neighbouring lanes) share their 2 x 2 blocks: the even lane hashes the block of keys
+        // (j, j+1), the odd lane that of (j+2, j+3), and each hands the other the word of its row parity
+        const int j = w.j0 + c * 32 + e;
+        const uint2 mine = attn_drop_block(dstream, (uint32_t)(t >> 1), (uint32_t)((j >> 1) + (t & 1)), dkp);
+        const uint32_t ox = __shfl_xor_sync(0xffffffffu, mine.x, 1), oy = __shfl_xor_sync(0xffffffffu, mine.y, 1);
+        const uint32_t w0 = (t & 1) ? oy : mine.x;  // keys (j, j+1) for this row
+        const uint32_t w1 = (t & 1) ? mine.y : ox;  // keys (j+2, j+3)
+        pr[0] = (w0 & 0xFFFFu) >= thr ? pr[0] * inv_keep : 0.f;
+        pr[1] = (w0 >> 16) >= thr ? pr[1] * inv_keep : 0.f;
+        pr[2] = (w1 & 0xFFFFu) >= thr ? pr[2] * inv_keep : 0.f;
+        pr[3] = (w1 >> 16) >= thr ? pr[3] * inv_keep : 0.f;
       }
       pk[e >> 1] = pack_bf16(pr[0], pr[1]);
       pk[(e >> 1) + 1] = pack_bf16(pr[2], pr[3]);
@@ -630,14 +633,17 @@ __global__ void __launch_bounds__(320, 1) attn_bwd_tc_kernel(const __grid_consta
               pr[k] = ex2_approx(fmaf(__uint_as_float(sv[e + k]), a.scale_log2, ls[k]));
               if (MASKED) pr[k] = (t >= t_lo && t <= t_hi) ? pr[k] : 0.f;
             }
-            if (DROP) {  // mask / (1-p) of the pairs (t, j): one block serves the query pair (t, t+1)
-#pragma unroll
-              for (int k = 0; k < 4; k += 2) {
-                const int t = q0 + c * 32 + e + k;
-                const uint2 blk = attn_drop_block(dstream, (uint32_t)(t >> 1), (uint32_t)(j >> 1), dkp);
-                fk[k] = ((blk.x >> dsh) & 0xFFFFu) >= a.drop.thr ? a.drop.inv_keep : 0.f;
-                fk[k + 1] = ((blk.y >> dsh) & 0xFFFFu) >= a.drop.thr ? a.drop.inv_keep : 0.f;
-              }
+            if (DROP) {  // mask / (1-p) of the pairs (t, j).  Keys j and j^1 (neighbouring lanes) share their 2 x 2 blocks:
+              // the even lane hashes the block of queries (t, t+1), the odd lane that of (t+2, t+3); both words travel
+              const int t = q0 + c * 32 + e;
+              const uint2 mine = attn_drop_block(dstream, (uint32_t)((t >> 1) + (j & 1)), (uint32_t)(j >> 1), dkp);
+              const uint32_t ox = __shfl_xor_sync(0xffffffffu, mine.x, 1), oy = __shfl_xor_sync(0xffffffffu, mine.y, 1);
+              const uint2 b0 = (j & 1) ? make_uint2(ox, oy) : mine;  // queries (t, t+1)
+              const uint2 b1 = (j & 1) ? mine : make_uint2(ox, oy);  // queries (t+2, t+3)
+              fk[0] = ((b0.x >> dsh) & 0xFFFFu) >= a.drop.thr ? a.drop.inv_keep : 0.f;
+              fk[1] = ((b0.y >> dsh) & 0xFFFFu) >= a.drop.thr ? a.drop.inv_keep : 0.f;
+              fk[2] = ((b1.x >> dsh) & 0xFFFFu) >= a.drop.thr ? a.drop.inv_keep : 0.f;
+              fk[3] = ((b1.y >> dsh) & 0xFFFFu) >= a.drop.thr ? a.drop.inv_keep : 0.f;
             }
             float ds[4], pd[4];
 #pragma unroll
