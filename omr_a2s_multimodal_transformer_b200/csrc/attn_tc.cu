@@ -183,12 +183,25 @@ __global__ void __launch_bounds__(192, 2) attn_fwd_tc_kernel(const __grid_consta
   uint64_t* p_full = bars + 6;
   uint64_t* pv_full = bars + 7;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  uint32_t* live = reinterpret_cast<uint32_t*>(bars + 9);  // [32] bit i: key tile kt0 + i holds a key that is not masked out
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * BQ, h = blockIdx.y, b = blockIdx.z;
   int kt0, kt1;
   kv_tile_range(a, q0, kt0, kt1);
   const int ntiles = kt1 - kt0;
+  // Key tiles whose every key carries bias = -inf (the padded tail of the memory, reference decoder.py:150-189 with
+  // the concat mixer's bool mask) contribute exactly zero: they are skipped by all three roles.
+  const bool use_live = a.key_bias != nullptr && ntiles <= 1024;
+  if (use_live) {
+    for (int i = threadIdx.x; i < 32; i += blockDim.x) live[i] = 0u;
+    __syncthreads();
+    const float* kbp = a.key_bias + (long long)b * a.Tk;
+    const int jend = kt1 * BKV < a.Tk ? kt1 * BKV : a.Tk;
+    for (int j = kt0 * BKV + (int)threadIdx.x; j < jend; j += blockDim.x)
+      if (kbp[j] > -INFINITY) atomicOr(&live[(j / BKV - kt0) >> 5], 1u << ((j / BKV - kt0) & 31));
+  }
+  auto tile_live = [&](int i) { return !use_live || ((live[i >> 5] >> (i & 31)) & 1u); };
 
   if (warp == 4 && lane == 0) {
     tma_prefetch_desc(&tmQ);
@@ -215,12 +228,14 @@ __global__ void __launch_bounds__(192, 2) attn_fwd_tc_kernel(const __grid_consta
     if (lane == 0 && ntiles > 0) {
       mbar_expect_tx(q_full, TILE);
       tma_load_3d(sQ, &tmQ, q_full, h * HD, q0, b);
-      for (int i = 0; i < ntiles; ++i) {
-        const int s = i & 1;
-        mbar_wait(&kv_empty[s], ((i >> 1) & 1) ^ 1);
+      for (int i = 0, n = 0; i < ntiles; ++i) {
+        if (!tile_live(i)) continue;
+        const int s = n & 1;
+        mbar_wait(&kv_empty[s], ((n >> 1) & 1) ^ 1);
         mbar_expect_tx(&kv_full[s], 2 * TILE);
         tma_load_3d(sK + s * TILE, &tmK, &kv_full[s], h * HD, (kt0 + i) * BKV, b);
         tma_load_3d(sV + s * TILE, &tmV, &kv_full[s], h * HD, (kt0 + i) * BKV, b);
+        ++n;
       }
     }
   } else if (warp == 5) {
@@ -229,9 +244,10 @@ __global__ void __launch_bounds__(192, 2) attn_fwd_tc_kernel(const __grid_consta
       constexpr uint32_t idesc_pv = make_idesc_bf16(128, 64, 0, 1);
       mbar_wait(q_full, 0);
       const uint32_t q_addr = smem_u32(sQ), p_addr = smem_u32(sP);
-      for (int i = 0; i < ntiles; ++i) {
-        const int s = i & 1;
-        mbar_wait(&kv_full[s], (i >> 1) & 1);
+      for (int i = 0, n = 0; i < ntiles; ++i) {
+        if (!tile_live(i)) continue;
+        const int s = n & 1;
+        mbar_wait(&kv_full[s], (n >> 1) & 1);
         tc_fence_after();
         const uint32_t k_addr = smem_u32(sK + s * TILE), v_addr = smem_u32(sV + s * TILE);
 #pragma unroll
@@ -239,7 +255,8 @@ __global__ void __launch_bounds__(192, 2) attn_fwd_tc_kernel(const __grid_consta
           umma_bf16(tmem_S, make_smem_desc(q_addr + j * 32, 16, 1024, 128), make_smem_desc(k_addr + j * 32, 16, 1024, 128), idesc_s,
                     j > 0 ? 1u : 0u);
         umma_commit(s_full);
-        mbar_wait(p_full, i & 1);
+        mbar_wait(p_full, n & 1);
+        ++n;
         tc_fence_after();
 #pragma unroll
         for (int j = 0; j < 8; ++j)
@@ -269,7 +286,9 @@ __global__ void __launch_bounds__(192, 2) attn_fwd_tc_kernel(const __grid_consta
       if (a.window > 0) k_lo = max(0, t + off - a.window);
     }
     if (t >= a.Tq) k_hi = -1;
+    int n = 0;  // live tiles processed so far (the barrier phases count these)
     for (int i = 0; i < ntiles; ++i) {
+      if (!tile_live(i)) continue;
       const int j0 = (kt0 + i) * BKV;
       // key-bias tile (pre-multiplied by log2 e) -> smem, shared by the 128 rows
       softmax_bar();  // previous tile's readers are done with sBias
@@ -278,7 +297,7 @@ __global__ void __launch_bounds__(192, 2) attn_fwd_tc_kernel(const __grid_consta
         sBias[r] = (kb && j < a.Tk) ? kb[j] * LOG2E : 0.f;
       }
       softmax_bar();
-      mbar_wait(s_full, i & 1);
+      mbar_wait(s_full, n & 1);
       tc_fence_after();
       // does every row of this CTA see every key of the tile?  (rows past Tq are never stored: they may see anything)
       bool full = j0 + BKV <= a.Tk;
@@ -294,8 +313,8 @@ __global__ void __launch_bounds__(192, 2) attn_fwd_tc_kernel(const __grid_consta
       const float m_new = fmaxf(m_run, mx);
       const float m_safe = (m_new == -INFINITY) ? 0.f : m_new;
       const float alpha = (m_run == -INFINITY) ? 0.f : ex2_approx(m_run - m_safe);
-      if (i > 0) {
-        mbar_wait(pv_full, (i - 1) & 1);
+      if (n > 0) {
+        mbar_wait(pv_full, (n - 1) & 1);
         tc_fence_after();
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
@@ -325,9 +344,10 @@ __global__ void __launch_bounds__(192, 2) attn_fwd_tc_kernel(const __grid_consta
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full);
+      ++n;
     }
-    if (ntiles > 0) {
-      mbar_wait(pv_full, (ntiles - 1) & 1);
+    if (n > 0) {
+      mbar_wait(pv_full, (n - 1) & 1);
       tc_fence_after();
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
@@ -415,7 +435,8 @@ int omr_attn_fwd_tc(const void* q, long long q_bs, long long q_rs, const void* k
 // =================================================================================================================
 namespace {
 
-constexpr int BWD_SMEM = TILE * 10 + 1024 + 256;
+constexpr int DQ_LD = 68;  // floats per staged dQ row: 272 B, so that 16-byte stores of 8 lanes hit 8 different bank groups
+constexpr int BWD_SMEM = TILE * 10 + 1024 + 256 + 128 * DQ_LD * 4;
 
 __device__ __forceinline__ void q_tile_range(const AttnTcArgs& a, int j0, int& qt0, int& qt1) {
   const int nqt = (a.Tq + BQ - 1) / BQ;
@@ -465,6 +486,7 @@ __global__ void __launch_bounds__(320, 1) attn_bwd_tc_kernel(const __grid_consta
   float* sLse = reinterpret_cast<float*>(smem + 10 * TILE);  // [128] (already * log2e)
   float* sDelta = sLse + 128;                               // [128]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 10 * TILE + 1024);
+  float* sDQ = reinterpret_cast<float*>(smem + 10 * TILE + 1024 + 256);  // [128][DQ_LD] staging of a dQ tile
   uint64_t* kv_full = bars;
   uint64_t* qd_full = bars + 1;   // [2]
   uint64_t* qd_empty = bars + 3;  // [2]
@@ -477,7 +499,14 @@ __global__ void __launch_bounds__(320, 1) attn_bwd_tc_kernel(const __grid_consta
   const int j0 = blockIdx.x * BKV, h = blockIdx.y, b = blockIdx.z;
   int qt0, qt1;
   q_tile_range(a, j0, qt0, qt1);
-  const int ntiles = qt1 - qt0;
+  // a key tile whose every key is masked out (bias = -inf: the padded tail of the memory) has P = 0 throughout:
+  // dK = dV = 0 and no contribution to dQ -- the CTA only writes the zeros
+  bool row_dead = true;
+  if (warp < 8) {
+    const int jr = j0 + (warp & 3) * 32 + lane;
+    row_dead = jr >= a.Tk || (a.key_bias && !(a.key_bias[(long long)b * a.Tk + jr] > -INFINITY));
+  }
+  const int ntiles = __syncthreads_and(row_dead) ? 0 : qt1 - qt0;
 
   if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&tmQ);
@@ -575,20 +604,29 @@ __global__ void __launch_bounds__(320, 1) attn_bwd_tc_kernel(const __grid_consta
     const uint32_t dstream = a.drop.thr ? attn_drop_stream(a.drop, b * a.H + h) : 0u;
     const uint32_t dkp = (uint32_t)((a.Tk + 1) >> 1), dsh = (uint32_t)(j & 1) * 16u;
 
+    // dQ tile -> fp32 accumulation buffer.  The accumulator row of a thread is 128 contiguous bytes, but a warp-wide
+    // red of one register group would touch 32 different lines; the tile is therefore transposed through shared memory
+    // (padded rows: conflict-free both ways) and added with reds that cover 512 contiguous bytes per warp instruction.
     auto dq_epilogue = [&](int q_tile) {
-      const int t = q_tile * BQ + r;
-      float* dst = g.dq_acc + (stat_base + t) * HD;
+      softmax_bar2();  // the previous tile's readers are done with sDQ
       {
-        const int c = hf;
         uint32_t v[32];
-        tmem_ld32(tmem_DQ + lane_addr + c * 32, v);
+        tmem_ld32(tmem_DQ + lane_addr + hf * 32, v);
         tmem_ld_wait();
-        if (t < a.Tq) {
+        float* rowp = sDQ + r * DQ_LD + hf * 32;
 #pragma unroll
-          for (int e = 0; e < 32; e += 4)
-            red_add_v4(dst + c * 32 + e, __uint_as_float(v[e]), __uint_as_float(v[e + 1]), __uint_as_float(v[e + 2]),
-                       __uint_as_float(v[e + 3]));
-        }
+        for (int u = 0; u < 8; ++u)
+          *reinterpret_cast<float4*>(rowp + 4 * u) = make_float4(__uint_as_float(v[4 * u]), __uint_as_float(v[4 * u + 1]),
+                                                                  __uint_as_float(v[4 * u + 2]), __uint_as_float(v[4 * u + 3]));
+      }
+      softmax_bar2();
+      const int tid8 = threadIdx.x;  // 0..255: the eight epilogue warps
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int L = it * 256 + tid8, row = L >> 4, c4 = L & 15;
+        const int t = q_tile * BQ + row;
+        const float4 x = *reinterpret_cast<const float4*>(sDQ + row * DQ_LD + c4 * 4);
+        if (t < a.Tq) red_add_v4(g.dq_acc + (stat_base + t) * HD + c4 * 4, x.x, x.y, x.z, x.w);
       }
     };
 
