@@ -27,6 +27,63 @@ __global__ void __launch_bounds__(256) ce_fwd_kernel(const T* __restrict__ logit
   }
 }
 
+// Vector variant (rows 16-byte aligned, V <= 4 * 256 * 16/sizeof(T)): a row is read ONCE with 16-byte loads and kept in
+// registers for both the max and the sum; rows whose target is ignore_index (the padded tail of a batch, ~1/3 of the
+// rows) are not read at all -- their loss is 0 and the backward writes zeros without the log-sum-exp.
+template <typename T>
+__global__ void __launch_bounds__(256) ce_fwd_vec_kernel(const T* __restrict__ logits, long long ld,
+                                                         const long long* __restrict__ targets, int V,
+                                                         long long ignore_index, float* __restrict__ row_loss,
+                                                         float* __restrict__ row_lse) {
+  constexpr int VEC = 16 / (int)sizeof(T);
+  __shared__ float sm[33];
+  const long long r = blockIdx.x;
+  const long long t = targets[r];
+  if (t == ignore_index || t < 0 || t >= V) {  // uniform per block
+    if (threadIdx.x == 0) { row_loss[r] = 0.f; row_lse[r] = 0.f; }
+    return;
+  }
+  const T* x = logits + r * ld;
+  const int nv = (V + VEC - 1) / VEC;  // the padded row stride covers the last partial vector
+  float v[4][VEC];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int i = threadIdx.x + u * 256;
+    if (i < nv) {
+      if constexpr (sizeof(T) == 2) {
+        const uint4 raw = *reinterpret_cast<const uint4*>(x + (long long)i * VEC);
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { v[u][2 * k] = __low2float(h[k]); v[u][2 * k + 1] = __high2float(h[k]); }
+      } else {
+        const float4 raw = *reinterpret_cast<const float4*>(x + (long long)i * VEC);
+        v[u][0] = raw.x; v[u][1] = raw.y; v[u][2] = raw.z; v[u][3] = raw.w;
+      }
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) {
+        if (i * VEC + k >= V) v[u][k] = -INFINITY;  // padding columns of the row stride
+        mx = fmaxf(mx, v[u][k]);
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) v[u][k] = -INFINITY;
+    }
+  }
+  mx = block_max(mx, sm);
+  float sum = 0.f;
+#pragma unroll
+  for (int u = 0; u < 4; ++u)
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) sum += expf(v[u][k] - mx);
+  sum = block_sum(sum, sm);
+  if (threadIdx.x == 0) {
+    const float lse = mx + logf(sum);
+    row_lse[r] = lse;
+    row_loss[r] = lse - to_f(x[t]);
+  }
+}
+
 // single block: deterministic tree reduction of the per-row losses
 __global__ void __launch_bounds__(1024) ce_reduce_kernel(const float* __restrict__ row_loss,
                                                          const long long* __restrict__ targets, long long rows,
@@ -65,6 +122,55 @@ __global__ void __launch_bounds__(256) ce_bwd_kernel(const T* __restrict__ logit
   for (int i = threadIdx.x; i < V; i += blockDim.x) {
     float p = expf(to_f(x[i]) - lse);
     d[i] = from_f<T>((p - (i == t ? 1.f : 0.f)) * g);
+  }
+}
+
+// Vector variant of the backward (16-byte loads / stores; the padded columns of the row stride are written as zeros)
+template <typename T>
+__global__ void __launch_bounds__(256) ce_bwd_vec_kernel(const T* __restrict__ logits, long long ld,
+                                                         const long long* __restrict__ targets,
+                                                         const float* __restrict__ row_lse,
+                                                         const float* __restrict__ loss_out,
+                                                         const float* __restrict__ gscale, T* __restrict__ dlogits, int V,
+                                                         long long ignore_index) {
+  constexpr int VEC = 16 / (int)sizeof(T);
+  const long long r = blockIdx.x;
+  const long long t = targets[r];
+  const T* x = logits + r * ld;
+  T* d = dlogits + r * ld;
+  const int nv = (V + VEC - 1) / VEC;
+  if (t == ignore_index) {
+    for (int i = threadIdx.x; i < nv; i += 256) *reinterpret_cast<uint4*>(d + (long long)i * VEC) = make_uint4(0, 0, 0, 0);
+    return;
+  }
+  const float n = loss_out[1];
+  const float g = (gscale ? gscale[0] : 1.f) / (n > 0.f ? n : 1.f);
+  const float lse = row_lse[r];
+  for (int i = threadIdx.x; i < nv; i += 256) {
+    float v[VEC];
+    if constexpr (sizeof(T) == 2) {
+      const uint4 raw = *reinterpret_cast<const uint4*>(x + (long long)i * VEC);
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { v[2 * k] = __low2float(h[k]); v[2 * k + 1] = __high2float(h[k]); }
+    } else {
+      const float4 raw = *reinterpret_cast<const float4*>(x + (long long)i * VEC);
+      v[0] = raw.x; v[1] = raw.y; v[2] = raw.z; v[3] = raw.w;
+    }
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      const int c = i * VEC + k;
+      v[k] = c < V ? (expf(v[k] - lse) - (c == t ? 1.f : 0.f)) * g : 0.f;
+    }
+    if constexpr (sizeof(T) == 2) {
+      uint4 o;
+      __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) h[k] = __floats2bfloat162_rn(v[2 * k], v[2 * k + 1]);
+      *reinterpret_cast<uint4*>(d + (long long)i * VEC) = o;
+    } else {
+      *reinterpret_cast<float4*>(d + (long long)i * VEC) = make_float4(v[0], v[1], v[2], v[3]);
+    }
   }
 }
 
@@ -128,6 +234,16 @@ extern "C" int omr_ce_fwd(int dt, const void* logits, long long ld, const long l
                           long long ignore_index, float* row_loss, float* row_lse, omr_stream_t stream) {
   if (rows <= 0) return OMR_OK;
   OMR_REQUIRE(V > 0, "omr_ce_fwd: empty vocabulary");
+  {
+    const int esz = dt == OMR_F32 ? 4 : 2, vec = 16 / esz;
+    const long long nv = (V + vec - 1) / vec;
+    if (nv * vec <= ld && nv <= 4 * 256 && (ld * esz) % 16 == 0 && (reinterpret_cast<uintptr_t>(logits) & 15) == 0) {
+      OMR_DISPATCH_DT(dt, T, (ce_fwd_vec_kernel<T><<<(unsigned)rows, 256, 0, as_stream(stream)>>>(
+                                 (const T*)logits, ld, targets, V, ignore_index, row_loss, row_lse)));
+      OMR_LAUNCHED();
+      return OMR_OK;
+    }
+  }
   OMR_DISPATCH_DT(dt, T, (ce_fwd_kernel<T><<<(unsigned)rows, 256, 0, as_stream(stream)>>>(
                              (const T*)logits, ld, targets, V, ignore_index, row_loss, row_lse)));
   OMR_LAUNCHED();
@@ -145,6 +261,17 @@ extern "C" int omr_ce_bwd(int dt, const void* logits, long long ld, const long l
                           const float* loss_out, const float* gscale, void* dlogits, long long rows, int V,
                           long long ignore_index, omr_stream_t stream) {
   if (rows <= 0) return OMR_OK;
+  {
+    const int esz = dt == OMR_F32 ? 4 : 2, vec = 16 / esz;
+    const long long nv = (V + vec - 1) / vec;
+    if (nv * vec <= ld && (ld * esz) % 16 == 0 && (reinterpret_cast<uintptr_t>(logits) & 15) == 0 &&
+        (reinterpret_cast<uintptr_t>(dlogits) & 15) == 0) {
+      OMR_DISPATCH_DT(dt, T, (ce_bwd_vec_kernel<T><<<(unsigned)rows, 256, 0, as_stream(stream)>>>(
+                                 (const T*)logits, ld, targets, row_lse, loss_out, gscale, (T*)dlogits, V, ignore_index)));
+      OMR_LAUNCHED();
+      return OMR_OK;
+    }
+  }
   OMR_DISPATCH_DT(dt, T, (ce_bwd_kernel<T><<<(unsigned)rows, 256, 0, as_stream(stream)>>>(
                              (const T*)logits, ld, targets, row_lse, loss_out, gscale, (T*)dlogits, V, ignore_index)));
   OMR_LAUNCHED();

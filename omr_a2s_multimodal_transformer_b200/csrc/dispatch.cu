@@ -46,6 +46,10 @@ extern "C" int omr_conv3x3_fwd(int dt, const void* x, const void* w, const float
                                int Ci, int Co, int sh, int sw, int relu, omr_stream_t stream) {
   OMR_REQUIRE(N >= 0 && H > 0 && W > 0 && Ci > 0 && Co > 0 && sh > 0 && sw > 0, "omr_conv3x3_fwd: bad shape");
   cudaStream_t st = as_stream(stream);
+  if (Ci == 1) {  // first layer: K = 9, output-write bound streaming kernel (both dtypes)
+    int rc1 = omr_conv3x3_fwd_c1(dt, x, w, bias, y, N, H, W, Co, sh, sw, relu, st);
+    if (rc1 != OMR_TC_NOT_ELIGIBLE) return rc1;
+  }
   if (tc_enabled() && dt == OMR_BF16) {
     TC_TRY(omr_conv3x3_fwd_tc(x, w, bias, y, N, H, W, Ci, Co, sh, sw, relu, st));
   }

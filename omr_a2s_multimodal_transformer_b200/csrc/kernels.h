@@ -51,5 +51,7 @@ int omr_attn_bwd_tc(const void* q, long long q_bs, long long q_rs, const void* k
                     int window, const int* q_len, const int* kv_len, cudaStream_t st);
 int omr_conv3x3_wgrad_small(const void* x, const void* dy, float* dw, int N, int H, int W, int Ci, int Co, int sh, int sw,
                             int accumulate, cudaStream_t st);
+int omr_conv3x3_fwd_c1(int dt, const void* x, const void* w, const float* bias, void* y, int N, int H, int W, int Co, int sh,
+                       int sw, int relu, cudaStream_t st);
 int omr_conv3x3_wgrad_c1(int dt, const void* x, const void* dy, float* dw, int N, int H, int W, int Co, int sh, int sw,
                          int accumulate, cudaStream_t st);
