@@ -328,7 +328,8 @@ def main():
                  "calls_per_step": top["calls"], "avg_ms": top["ms"] / max(top["calls"], 1),
                  "algorithmic_per_launch": {"flops": top["flops"] / max(top["calls"], 1), "bytes": top["bytes"] / max(top["calls"], 1)},
                  "share_of_step": top["ms"] / tot_ms, "peak_source": pk["src"] + (" (sustained bf16)" if roof["bound"] == "tensor" else ""),
-                 "traffic": traffic})
+                 "traffic": traffic,
+                 "traffic_source": "profiles/r01_final_ncu_full_top_kernels.txt (ncu --set full, before masked-tile skipping)" if traffic else None})
     breakdown = {k: {"ms": round(d["ms"], 3), "calls": d["calls"],
                      "tflops": round(d["flops"] / (d["ms"] * 1e-3) / 1e12, 2) if d["flops"] else None,
                      "gbs": round(d["bytes"] / (d["ms"] * 1e-3) / 1e9, 1) if d["bytes"] else None}

@@ -349,7 +349,13 @@ extern "C" int omr_colsum(int dt, const void* x, long long rows, int N, long lon
     const int esz = dt == OMR_F32 ? 4 : 2;
     if (N % 4 == 0 && N <= 1024 && 256 % (N / 4) == 0 && (ld * esz) % (4 * esz) == 0 &&
         (reinterpret_cast<uintptr_t>(x) % (4 * esz)) == 0) {
-      long long per = cdiv(rows, 148LL * 4);
+      static int colsum_ctas = 0;  // CTAs per launch: every CTA ends with N atomics onto the same N addresses
+      if (!colsum_ctas) {
+        const char* e = getenv("OMR_COLSUM_CTAS");
+        colsum_ctas = e ? atoi(e) : 148 * 4;
+        if (colsum_ctas < 1) colsum_ctas = 148 * 4;
+      }
+      long long per = cdiv(rows, (long long)colsum_ctas);
       const long long min_per = 256 / (N / 4) * 8;
       if (per < min_per) per = min_per;
       const unsigned blocks = (unsigned)cdiv(rows, per);
