@@ -40,18 +40,28 @@ class BucketReducer:
         self.buckets = list(buckets)
         self.group = group
         self._ready = [False] * len(self.buckets)
+        self._events: List = [None] * len(self.buckets)
         self._issued = 0
         self._works: List = []
 
     def _issue_ready_prefix(self, force: bool = False) -> None:
         while self._issued < len(self.buckets) and (force or self._ready[self._issued]):
             b = self.buckets[self._issued]
+            ev = self._events[self._issued]
+            if ev is not None:
+                # the bucket may have been completed on ANOTHER stream than the one issuing it now (the two encoders
+                # run their backward passes on two streams): order the reduction after the completing kernels
+                torch.cuda.current_stream(b.device).wait_event(ev)
             self._works.append(dist.all_reduce(b, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
             self._issued += 1
 
     def mark_ready(self, index: int) -> None:
         """bucket ``index`` has received its last gradient on the current stream"""
         self._ready[index] = True
+        if self.buckets[index].is_cuda:
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(self.buckets[index].device))
+            self._events[index] = ev
         self._issue_ready_prefix()
 
     def finish(self) -> None:
@@ -61,6 +71,7 @@ class BucketReducer:
             w.wait()
         self._works.clear()
         self._ready = [False] * len(self.buckets)
+        self._events = [None] * len(self.buckets)
         self._issued = 0
 
 

@@ -17,6 +17,8 @@ import math
 import random
 from typing import Dict, List, Optional, Tuple
 
+import os
+
 import torch
 import torch.nn as nn
 
@@ -439,8 +441,7 @@ class MultimodalTransformer(_ModelBase):
     def _memory(self, xi, xa, xli, xla, modality: str):
         """-> (memory [B,S,256], memory_len for the decoder).  For the concat mixer the fused memory is
         written in one pass and the mask is a kernel-built fp32 key bias (-inf on padded frames)."""
-        fi = self.image_encoder.forward_nhwc(xi)
-        fa = self.audio_encoder.forward_nhwc(xa)
+        fi, fa = self._encode_both(xi, xa)
         if modality == "image":  # model.py:510-512
             return _MemoryFn.apply(fi, None, self.image_pos_2d, None, self.training), xli
         if modality == "audio":  # model.py:513-515
@@ -455,6 +456,26 @@ class MultimodalTransformer(_ModelBase):
         mi = _MemoryFn.apply(fi, None, self.image_pos_2d, None, self.training)
         ma = _MemoryFn.apply(fa, None, self.audio_pos_2d, None, self.training)
         return self.mixer(xi=mi, xa=ma, xli=xli, xla=xla)
+
+    def _encode_both(self, xi, xa):
+        """Both encoders always run (reference model.py:485-506) and are independent: the audio encoder is issued on a
+        side stream so that its (many small, latency-bound) kernels fill the gaps of the image encoder's.  Each encoder
+        is one autograd node, and autograd replays a node's backward on the stream of its forward, so the two backward
+        passes overlap the same way.  ``OMR_OVERLAP_ENCODERS=0`` keeps everything on one stream."""
+        if os.environ.get("OMR_OVERLAP_ENCODERS", "1") == "0" or not xi.is_cuda:
+            return self.image_encoder.forward_nhwc(xi), self.audio_encoder.forward_nhwc(xa)
+        cur = torch.cuda.current_stream(xi.device)
+        side = getattr(self, "_enc_side_stream", None)
+        if side is None or side.device != xi.device:
+            side = torch.cuda.Stream(device=xi.device)
+            self._enc_side_stream = side
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            fa = self.audio_encoder.forward_nhwc(xa)
+        fi = self.image_encoder.forward_nhwc(xi)
+        cur.wait_stream(side)
+        fa.record_stream(cur)
+        return fi, fa
 
     def encoder_forward(self, xi, xa, xli=None, xla=None, apply_teacher_forcing_modality: bool = False):
         """reference model.py:485-522: returns (memory, xl) with xl a bool [B,S] mask (concat), the
