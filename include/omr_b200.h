@@ -286,6 +286,35 @@ int omr_decode_persistent(int dt, const void* layers, int L, const void* emb, co
 /* timing (device int64 [16], may be NULL): SM-clock cycles spent by CTA 0 per phase kind, accumulated over the steps
  * (0 embed, 1 qkv, 2 self-attn, 3 out-proj, 4 cross-q, 5 cross-attn, 6 cross-out, 7 ffn1, 8 ffn2, 9 classifier, 10 argmax). */
 
+/* ---- the steps either side of the model ------------------------------------------ */
+
+/* Batch collation on the device (reference pad_batch_inputs, src/data/preprocessing.py:55-74, and get_number_of_frames,
+ * src/data/ar_dataset.py:439-442).  The B ragged single-channel fp32 samples lie back to back in `flat`
+ * (sample b = heights[b] x widths[b] row-major at flat + offsets[b]); dst [B,1,Hmax,Wmax] fp32 receives the sample
+ * in its top-left corner and pad_value elsewhere (1.0 for score images, 0.0 for spectrograms,
+ * preprocessing.py:118-136).  n_frames (may be NULL): n_frames[b] = ceil(h/height_reduction) * ceil(w/width_reduction). */
+int omr_pad_collate(const float* flat, const long long* offsets, const int* heights, const int* widths, float* dst, int B,
+                    int Hmax, int Wmax, float pad_value, int* n_frames, int height_reduction, int width_reduction,
+                    omr_stream_t stream);
+/* pad_batch_transcripts of transcript[:-1] / transcript[1:] (preprocessing.py:77-100): transcript b =
+ * flat[offsets[b] .. offsets[b+1]) (offsets has B+1 entries); y_in, y_out int64 [B,T] with T = max length - 1. */
+int omr_pad_transcripts(const long long* flat, const long long* offsets, int B, int T, long long* y_in, long long* y_out,
+                        long long pad_id, omr_stream_t stream);
+/* One step of token-level late fusion (weighted_prediction, src/multimodal/weighted_multimodal/test.py:47-70):
+ * p = alpha * softmax(logits_a[b]) + (1 - alpha) * softmax(logits_b[b]) (fp32), tok[b] = first-max argmax of p,
+ * val[b] = that probability; finished / eos / pad / out_* / step_dev exactly as omr_argmax_step. */
+int omr_mix_argmax_step(int dt, const void* logits_a, long long lda, const void* logits_b, long long ldb, int B, int V,
+                        float alpha, long long* tok, float* val, int* finished, long long eos_id, long long pad_id,
+                        long long* out_tokens, float* out_vals, int out_ld, int step, const int* step_dev,
+                        omr_stream_t stream);
+/* Levenshtein distance (unit costs) of `pairs` (truth, hypothesis) token-id sequences, sequence p =
+ * tokens[offsets[p] .. offsets[p+1]) (compute_ed_metrics, src/utils/metrics.py:52-88).  ed_out int32 [pairs];
+ * sums (may be NULL; must be zeroed by the caller) accumulates {sum of distances, sum of truth lengths, number of pairs
+ * with distance > 0}: Sym-ER = 100*sums[0]/sums[1], Seq-ER = 100*sums[2]/pairs.  max_len >= every truth length. */
+int omr_levenshtein(const long long* truth, const long long* truth_offsets, const long long* hyp,
+                    const long long* hyp_offsets, int pairs, int max_len, int* ed_out, unsigned long long* sums,
+                    omr_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

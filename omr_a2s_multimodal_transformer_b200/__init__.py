@@ -9,7 +9,8 @@ from .ddp import BucketReducer, DataParallel
 from .decoder import Decoder, PositionalEncoding1D
 from .encoder import HEIGHT_REDUCTION, WIDTH_REDUCTION, ConvBlock, DepthSepConv2D, DSCBlock, Encoder, MixDropout
 from .graph import GraphedTrainStep
-from .greedy import BatchedGreedyDecoder
+from .greedy import BatchedGreedyDecoder, WeightedGreedyDecoder
+from .late_fusion import weighted_prediction, weighted_prediction_batch
 from .model import (EOS_TOKEN, NUM_CHANNELS, SOS_TOKEN, CrossAttention, MultimodalTransformer, PositionalEncoding2D,
                     Transformer)
 from .optim import FusedAdam
@@ -18,5 +19,5 @@ from .params import GradArena
 __all__ = [
     "Decoder", "PositionalEncoding1D", "Encoder", "ConvBlock", "DSCBlock", "DepthSepConv2D", "MixDropout",
     "PositionalEncoding2D", "CrossAttention", "Transformer", "MultimodalTransformer", "BatchedGreedyDecoder",
-    "FusedAdam", "GradArena", "GraphedTrainStep", "DataParallel", "BucketReducer", "HEIGHT_REDUCTION", "WIDTH_REDUCTION", "SOS_TOKEN", "EOS_TOKEN", "NUM_CHANNELS",
+    "WeightedGreedyDecoder", "weighted_prediction", "weighted_prediction_batch", "FusedAdam", "GradArena", "GraphedTrainStep", "DataParallel", "BucketReducer", "HEIGHT_REDUCTION", "WIDTH_REDUCTION", "SOS_TOKEN", "EOS_TOKEN", "NUM_CHANNELS",
 ]

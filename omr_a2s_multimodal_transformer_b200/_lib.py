@@ -52,6 +52,10 @@ _SIGS = {
     "omr_argmax_step": "ipqiipppqqppiipp",
     "omr_kv_append": "ipqpiiiipp",
     "omr_attn_decode": "ipqpqqpqqpqpqpqiiiifipp",
+    "omr_pad_collate": "pppppiiifpiip",
+    "omr_pad_transcripts": "ppiippqp",
+    "omr_mix_argmax_step": "ipqpqiifpppqqppiipp",
+    "omr_levenshtein": "ppppiippp",
     "omr_decode_persistent": "ipippppiiiiiiiipppppipqqpqfpqpp",
 }
 _CT = {"i": c_int, "q": c_longlong, "p": c_void_p, "f": c_float, "d": c_double}

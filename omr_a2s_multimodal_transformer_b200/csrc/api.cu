@@ -17,6 +17,14 @@ void omr_set_error(const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
+bool omr_pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("OMR_PDL");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
 void omr_count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 extern "C" int omr_abi_version(void) { return 1; }
@@ -26,6 +34,7 @@ extern "C" long long omr_launch_count(void) { return g_launches.load(); }
 // ---- cast -----------------------------------------------------------------------------------
 template <typename TS, typename TD>
 __global__ void cast_kernel(const TS* __restrict__ s, TD* __restrict__ d, long long n) {
+  omr_pdl_enter();
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long stride = (long long)gridDim.x * blockDim.x;
   for (; i < n; i += stride) d[i] = from_f<TD>(to_f(s[i]));
@@ -43,13 +52,13 @@ extern "C" int omr_cast(int src_dt, int dst_dt, const void* src, void* dst, long
   cudaStream_t st = as_stream(stream);
   int g = grid_for(n, 256);
   if (src_dt == OMR_F32 && dst_dt == OMR_BF16)
-    cast_kernel<float, bf16><<<g, 256, 0, st>>>((const float*)src, (bf16*)dst, n);
+    OmrLaunch(g, 256, 0, st)(cast_kernel<float, bf16>, (const float*)src, (bf16*)dst, n);
   else if (src_dt == OMR_BF16 && dst_dt == OMR_F32)
-    cast_kernel<bf16, float><<<g, 256, 0, st>>>((const bf16*)src, (float*)dst, n);
+    OmrLaunch(g, 256, 0, st)(cast_kernel<bf16, float>, (const bf16*)src, (float*)dst, n);
   else if (src_dt == OMR_F32 && dst_dt == OMR_F32)
-    cast_kernel<float, float><<<g, 256, 0, st>>>((const float*)src, (float*)dst, n);
+    OmrLaunch(g, 256, 0, st)(cast_kernel<float, float>, (const float*)src, (float*)dst, n);
   else if (src_dt == OMR_BF16 && dst_dt == OMR_BF16)
-    cast_kernel<bf16, bf16><<<g, 256, 0, st>>>((const bf16*)src, (bf16*)dst, n);
+    OmrLaunch(g, 256, 0, st)(cast_kernel<bf16, bf16>, (const bf16*)src, (bf16*)dst, n);
   else
     OMR_REQUIRE(false, "omr_cast: bad dtypes %d -> %d", src_dt, dst_dt);
   OMR_LAUNCHED();
@@ -59,13 +68,14 @@ extern "C" int omr_cast(int src_dt, int dst_dt, const void* src, void* dst, long
 // ---- relu backward / add ------------------------------------------------------------------------
 template <typename T>
 __global__ void relu_bwd_kernel(const T* __restrict__ y, const T* __restrict__ dy, T* __restrict__ dx, long long n) {
+  omr_pdl_enter();
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long stride = (long long)gridDim.x * blockDim.x;
   for (; i < n; i += stride) dx[i] = to_f(y[i]) > 0.f ? dy[i] : from_f<T>(0.f);
 }
 extern "C" int omr_relu_bwd(int dt, const void* y, const void* dy, void* dx, long long n, omr_stream_t stream) {
   if (n <= 0) return OMR_OK;
-  OMR_DISPATCH_DT(dt, T, (relu_bwd_kernel<T><<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(
+  OMR_DISPATCH_DT(dt, T, (OmrLaunch(grid_for(n, 256), 256, 0, as_stream(stream))(relu_bwd_kernel<T>, 
                              (const T*)y, (const T*)dy, (T*)dx, n)));
   OMR_LAUNCHED();
   return OMR_OK;
@@ -73,26 +83,28 @@ extern "C" int omr_relu_bwd(int dt, const void* y, const void* dy, void* dx, lon
 
 template <typename T>
 __global__ void relu_mask_scale_kernel(T* __restrict__ dx, const T* __restrict__ m, float scale, long long n) {
+  omr_pdl_enter();
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long stride = (long long)gridDim.x * blockDim.x;
   for (; i < n; i += stride) dx[i] = to_f(m[i]) > 0.f ? from_f<T>(to_f(dx[i]) * scale) : from_f<T>(0.f);
 }
 int omr_relu_mask_scale(int dt, void* dx, const void* mask, float scale, long long n, cudaStream_t st) {
   if (n <= 0) return OMR_OK;
-  OMR_DISPATCH_DT(dt, T, (relu_mask_scale_kernel<T><<<grid_for(n, 256), 256, 0, st>>>((T*)dx, (const T*)mask, scale, n)));
+  OMR_DISPATCH_DT(dt, T, (OmrLaunch(grid_for(n, 256), 256, 0, st)(relu_mask_scale_kernel<T>, (T*)dx, (const T*)mask, scale, n)));
   OMR_LAUNCHED();
   return OMR_OK;
 }
 
 template <typename T>
 __global__ void add_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ o, long long n) {
+  omr_pdl_enter();
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long stride = (long long)gridDim.x * blockDim.x;
   for (; i < n; i += stride) o[i] = from_f<T>(to_f(a[i]) + to_f(b[i]));
 }
 extern "C" int omr_add(int dt, const void* a, const void* b, void* out, long long n, omr_stream_t stream) {
   if (n <= 0) return OMR_OK;
-  OMR_DISPATCH_DT(dt, T, (add_kernel<T><<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(
+  OMR_DISPATCH_DT(dt, T, (OmrLaunch(grid_for(n, 256), 256, 0, as_stream(stream))(add_kernel<T>, 
                              (const T*)a, (const T*)b, (T*)out, n)));
   OMR_LAUNCHED();
   return OMR_OK;
@@ -102,6 +114,7 @@ extern "C" int omr_add(int dt, const void* a, const void* b, void* out, long lon
 // w [Co,Ci,3,3] -> transpose==0: out[co][tap][ci] ; transpose==1: out[ci][tap][co]
 template <typename T>
 __global__ void pack_conv_w_kernel(const float* __restrict__ w, T* __restrict__ out, int Co, int Ci, int transpose) {
+  omr_pdl_enter();
   long long n = (long long)Co * Ci * 9;
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long stride = (long long)gridDim.x * blockDim.x;
@@ -116,7 +129,7 @@ __global__ void pack_conv_w_kernel(const float* __restrict__ w, T* __restrict__ 
 extern "C" int omr_pack_conv_weight(int dt, const float* w, void* out, int Co, int Ci, int transpose,
                                     omr_stream_t stream) {
   long long n = (long long)Co * Ci * 9;
-  OMR_DISPATCH_DT(dt, T, (pack_conv_w_kernel<T><<<grid_for(n, 256, 1), 256, 0, as_stream(stream)>>>(
+  OMR_DISPATCH_DT(dt, T, (OmrLaunch(grid_for(n, 256, 1), 256, 0, as_stream(stream))(pack_conv_w_kernel<T>, 
                              w, (T*)out, Co, Ci, transpose)));
   OMR_LAUNCHED();
   return OMR_OK;
@@ -125,6 +138,7 @@ extern "C" int omr_pack_conv_weight(int dt, const float* w, void* out, int Co, i
 // w [C,1,3,3] -> out [tap][c]
 template <typename T>
 __global__ void pack_dw_w_kernel(const float* __restrict__ w, T* __restrict__ out, int C) {
+  omr_pdl_enter();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < C * 9) {
     int tap = i % 9, c = i / 9;
@@ -132,7 +146,7 @@ __global__ void pack_dw_w_kernel(const float* __restrict__ w, T* __restrict__ ou
   }
 }
 extern "C" int omr_pack_dw_weight(int dt, const float* w, void* out, int C, omr_stream_t stream) {
-  OMR_DISPATCH_DT(dt, T, (pack_dw_w_kernel<T><<<(int)cdiv(C * 9, 256), 256, 0, as_stream(stream)>>>(w, (T*)out, C)));
+  OMR_DISPATCH_DT(dt, T, (OmrLaunch((int)cdiv(C * 9, 256), 256, 0, as_stream(stream))(pack_dw_w_kernel<T>, w, (T*)out, C)));
   OMR_LAUNCHED();
   return OMR_OK;
 }
@@ -141,6 +155,7 @@ extern "C" int omr_pack_dw_weight(int dt, const float* w, void* out, int C, omr_
 template <typename T>
 __global__ void pe2d_add_kernel(const T* __restrict__ x, const float* __restrict__ pe, T* __restrict__ out, int B,
                                 int h, int w, int C, int pe_w, int out_rows, int row_off) {
+  omr_pdl_enter();
   // one thread per 4 channels
   long long n4 = (long long)B * h * w * (C / 4);
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -166,7 +181,7 @@ extern "C" int omr_pe2d_add(int dt, const void* x, const float* pe, void* out, i
   OMR_REQUIRE(w <= pe_w, "omr_pe2d_add: feature map wider than the PE table (%d > %d)", w, pe_w);
   long long n4 = (long long)B * h * w * (C / 4);
   if (n4 <= 0) return OMR_OK;
-  OMR_DISPATCH_DT(dt, T, (pe2d_add_kernel<T><<<grid_for(n4, 256, 1), 256, 0, as_stream(stream)>>>(
+  OMR_DISPATCH_DT(dt, T, (OmrLaunch(grid_for(n4, 256, 1), 256, 0, as_stream(stream))(pe2d_add_kernel<T>, 
                              (const T*)x, pe, (T*)out, B, h, w, C, pe_w, out_rows, row_off)));
   OMR_LAUNCHED();
   return OMR_OK;
@@ -175,6 +190,7 @@ extern "C" int omr_pe2d_add(int dt, const void* x, const float* pe, void* out, i
 template <typename T>
 __global__ void copy_rows_kernel(const T* __restrict__ src, T* __restrict__ dst, int B, int rows, int C, int src_rows,
                                  int src_off) {
+  omr_pdl_enter();
   long long n4 = (long long)B * rows * (C / 4);
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long stride = (long long)gridDim.x * blockDim.x;
@@ -194,7 +210,7 @@ extern "C" int omr_copy_rows(int dt, const void* src, void* dst, int B, int rows
   OMR_REQUIRE(C % 4 == 0, "omr_copy_rows: C must be a multiple of 4 (got %d)", C);
   long long n4 = (long long)B * rows * (C / 4);
   if (n4 <= 0) return OMR_OK;
-  OMR_DISPATCH_DT(dt, T, (copy_rows_kernel<T><<<grid_for(n4, 256, 1), 256, 0, as_stream(stream)>>>(
+  OMR_DISPATCH_DT(dt, T, (OmrLaunch(grid_for(n4, 256, 1), 256, 0, as_stream(stream))(copy_rows_kernel<T>, 
                              (const T*)src, (T*)dst, B, rows, C, src_rows, src_off)));
   OMR_LAUNCHED();
   return OMR_OK;
@@ -203,6 +219,7 @@ extern "C" int omr_copy_rows(int dt, const void* src, void* dst, int B, int rows
 // ---- masks -------------------------------------------------------------------------------------
 __global__ void key_bias_len_kernel(float* __restrict__ bias, const int* __restrict__ lens, int B, int S, int seg_off,
                                     int seg_len, float value) {
+  omr_pdl_enter();
   long long n = (long long)B * seg_len;
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) {
@@ -215,20 +232,21 @@ extern "C" int omr_key_bias_from_lengths(float* bias, const int* lens, int B, in
   OMR_REQUIRE(seg_off >= 0 && seg_off + seg_len <= S, "omr_key_bias_from_lengths: segment out of range");
   long long n = (long long)B * seg_len;
   if (n <= 0) return OMR_OK;
-  key_bias_len_kernel<<<(int)cdiv(n, 256), 256, 0, as_stream(stream)>>>(bias, lens, B, S, seg_off, seg_len, value);
+  OmrLaunch((int)cdiv(n, 256), 256, 0, as_stream(stream))(key_bias_len_kernel, bias, lens, B, S, seg_off, seg_len, value);
   OMR_LAUNCHED();
   return OMR_OK;
 }
 
 __global__ void key_bias_tok_kernel(float* __restrict__ bias, const long long* __restrict__ tok, long long n,
                                     long long pad_id, float value) {
+  omr_pdl_enter();
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) bias[i] = (tok[i] == pad_id) ? value : 0.f;
 }
 extern "C" int omr_key_bias_from_tokens(float* bias, const long long* tokens, long long n, long long pad_id,
                                         float value, omr_stream_t stream) {
   if (n <= 0) return OMR_OK;
-  key_bias_tok_kernel<<<(int)cdiv(n, 256), 256, 0, as_stream(stream)>>>(bias, tokens, n, pad_id, value);
+  OmrLaunch((int)cdiv(n, 256), 256, 0, as_stream(stream))(key_bias_tok_kernel, bias, tokens, n, pad_id, value);
   OMR_LAUNCHED();
   return OMR_OK;
 }
@@ -238,6 +256,7 @@ template <typename T>
 __global__ void embed_pe_kernel(const long long* __restrict__ tok, const T* __restrict__ table,
                                 const float* __restrict__ pe, T* __restrict__ out, int B, int Tn, int D, int pos0,
                                 const int* __restrict__ pos_dev) {
+  omr_pdl_enter();
   if (pos_dev) pos0 = *pos_dev;
   long long n4 = (long long)B * Tn * (D / 4);
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -261,7 +280,7 @@ extern "C" int omr_embed_pe_fwd(int dt, const long long* tokens, const void* tab
   OMR_REQUIRE(D % 4 == 0, "omr_embed_pe_fwd: D must be a multiple of 4");
   long long n4 = (long long)B * T_ * (D / 4);
   if (n4 <= 0) return OMR_OK;
-  OMR_DISPATCH_DT(dt, T, (embed_pe_kernel<T><<<grid_for(n4, 256, 1), 256, 0, as_stream(stream)>>>(
+  OMR_DISPATCH_DT(dt, T, (OmrLaunch(grid_for(n4, 256, 1), 256, 0, as_stream(stream))(embed_pe_kernel<T>, 
                              tokens, (const T*)table, pe, (T*)out, B, T_, D, pos0, pos_dev)));
   OMR_LAUNCHED();
   return OMR_OK;
@@ -270,6 +289,7 @@ extern "C" int omr_embed_pe_fwd(int dt, const long long* tokens, const void* tab
 template <typename T>
 __global__ void embed_bwd_kernel(const long long* __restrict__ tok, const T* __restrict__ dout,
                                  float* __restrict__ dtable, long long rows, int D, long long padding_idx) {
+  omr_pdl_enter();
   long long n = rows * D;
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long stride = (long long)gridDim.x * blockDim.x;
@@ -284,7 +304,7 @@ extern "C" int omr_embed_bwd(int dt, const long long* tokens, const void* dout, 
                              long long padding_idx, omr_stream_t stream) {
   long long n = rows * D;
   if (n <= 0) return OMR_OK;
-  OMR_DISPATCH_DT(dt, T, (embed_bwd_kernel<T><<<grid_for(n, 256, 1), 256, 0, as_stream(stream)>>>(
+  OMR_DISPATCH_DT(dt, T, (OmrLaunch(grid_for(n, 256, 1), 256, 0, as_stream(stream))(embed_bwd_kernel<T>, 
                              tokens, (const T*)dout, dtable, rows, D, padding_idx)));
   OMR_LAUNCHED();
   return OMR_OK;
@@ -294,6 +314,7 @@ extern "C" int omr_embed_bwd(int dt, const long long* tokens, const void* dout, 
 // grid.x tiles columns by 32, grid.y splits rows; block (32, 8)
 template <typename T>
 __global__ void colsum_kernel(const T* __restrict__ x, long long rows, int N, long long ld, float* __restrict__ out) {
+  omr_pdl_enter();
   __shared__ float sm[8][33];
   int c = blockIdx.x * 32 + threadIdx.x;
   float acc = 0.f;
@@ -315,6 +336,7 @@ __global__ void colsum_kernel(const T* __restrict__ x, long long rows, int N, lo
 template <typename T>
 __global__ void __launch_bounds__(256) colsum_vec_kernel(const T* __restrict__ x, long long rows, int N, long long ld,
                                                          float* __restrict__ out, int rows_per_block) {
+  omr_pdl_enter();
   __shared__ float sm[256 * 4];
   const int quads = N / 4;  // <= 256 and a divisor of 256
   const int lanes = 256 / quads;
@@ -359,14 +381,14 @@ extern "C" int omr_colsum(int dt, const void* x, long long rows, int N, long lon
       const long long min_per = 256 / (N / 4) * 8;
       if (per < min_per) per = min_per;
       const unsigned blocks = (unsigned)cdiv(rows, per);
-      OMR_DISPATCH_DT(dt, T, (colsum_vec_kernel<T><<<blocks, 256, 0, st>>>((const T*)x, rows, N, ld, out, (int)per)));
+      OMR_DISPATCH_DT(dt, T, (OmrLaunch(blocks, 256, 0, st)(colsum_vec_kernel<T>, (const T*)x, rows, N, ld, out, (int)per)));
       OMR_LAUNCHED();
       return OMR_OK;
     }
   }
   dim3 grid((unsigned)cdiv(N, 32), (unsigned)(rows >= 8 * 64 ? (cdiv(rows, 8 * 16) > 512 ? 512 : cdiv(rows, 8 * 16)) : 1));
   dim3 block(32, 8);
-  OMR_DISPATCH_DT(dt, T, (colsum_kernel<T><<<grid, block, 0, st>>>((const T*)x, rows, N, ld, out)));
+  OMR_DISPATCH_DT(dt, T, (OmrLaunch(grid, block, 0, st)(colsum_kernel<T>, (const T*)x, rows, N, ld, out)));
   OMR_LAUNCHED();
   return OMR_OK;
 }
@@ -384,6 +406,7 @@ __device__ __forceinline__ uint32_t drop_pair_bits(uint32_t seed, long long key)
 template <typename T>
 __global__ void dropout_kernel(const T* __restrict__ x, T* __restrict__ y, long long n, int C, long long per_sample,
                                uint32_t thr, float scale, uint32_t seed, int channelwise, const int* __restrict__ seed_off) {
+  omr_pdl_enter();
   if (seed_off) seed += (uint32_t)(*seed_off) * 0x9E3779B9u;
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long stride = (long long)gridDim.x * blockDim.x;
@@ -398,6 +421,7 @@ __global__ void dropout_kernel(const T* __restrict__ x, T* __restrict__ y, long 
 template <typename T>
 __global__ void dropout_vec_kernel(const T* __restrict__ x, T* __restrict__ y, long long n4, int C, long long per_sample,
                                    uint32_t thr, float scale, uint32_t seed, int channelwise, const int* __restrict__ seed_off) {
+  omr_pdl_enter();
   if (seed_off) seed += (uint32_t)(*seed_off) * 0x9E3779B9u;
   long long i4 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long stride = (long long)gridDim.x * blockDim.x;
@@ -425,13 +449,13 @@ extern "C" int omr_dropout(int dt, const void* x, void* y, long long n, int C, l
     const int esz = dt == OMR_F32 ? 4 : 2;
     if (n % 4 == 0 && (!channelwise || (C % 4 == 0 && per_sample % 4 == 0)) && (reinterpret_cast<uintptr_t>(x) % (4 * esz)) == 0 &&
         (reinterpret_cast<uintptr_t>(y) % (4 * esz)) == 0) {
-      OMR_DISPATCH_DT(dt, T, (dropout_vec_kernel<T><<<grid_for(n / 4, 256, 2), 256, 0, as_stream(stream)>>>(
+      OMR_DISPATCH_DT(dt, T, (OmrLaunch(grid_for(n / 4, 256, 2), 256, 0, as_stream(stream))(dropout_vec_kernel<T>, 
                                  (const T*)x, (T*)y, n / 4, C, per_sample, thr, 1.f / (1.f - p), (uint32_t)seed, channelwise, seed_offset)));
       OMR_LAUNCHED();
       return OMR_OK;
     }
   }
-  OMR_DISPATCH_DT(dt, T, (dropout_kernel<T><<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(
+  OMR_DISPATCH_DT(dt, T, (OmrLaunch(grid_for(n, 256), 256, 0, as_stream(stream))(dropout_kernel<T>, 
                              (const T*)x, (T*)y, n, C, per_sample, thr, 1.f / (1.f - p), (uint32_t)seed, channelwise, seed_offset)));
   OMR_LAUNCHED();
   return OMR_OK;

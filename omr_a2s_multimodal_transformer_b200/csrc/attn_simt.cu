@@ -131,6 +131,7 @@ __device__ __forceinline__ void query_tile_range(const AttnArgs& a, int j0, int 
 // ---------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(256) attn_fwd_kernel(AttnArgs a) {
+  omr_pdl_enter();
   extern __shared__ __align__(16) float smem[];
   float* Qt = smem;               // [d][i], pre-scaled
   float* Kt = smem + TILE_F;      // [d][j]
@@ -221,6 +222,7 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(AttnArgs a) {
 // delta[b,h,t] = sum_d dO * O ; one warp per (b,h,t)
 template <typename T>
 __global__ void attn_delta_kernel(AttnArgs a) {
+  omr_pdl_enter();
   long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   int lane = threadIdx.x & 31;
   long long total = (long long)a.B * a.H * a.Tq;
@@ -239,6 +241,7 @@ __global__ void attn_delta_kernel(AttnArgs a) {
 // dK, dV: one block per (key tile, h, b), loops over the query tiles that can see it.
 template <typename T>
 __global__ void __launch_bounds__(256) attn_bwd_dkdv_kernel(AttnArgs a) {
+  omr_pdl_enter();
   extern __shared__ __align__(16) float smem[];
   float* Kt = smem;                // [d][j]
   float* Vt = smem + TILE_F;       // [d][j]
@@ -333,6 +336,7 @@ __global__ void __launch_bounds__(256) attn_bwd_dkdv_kernel(AttnArgs a) {
 // dQ: one block per (query tile, h, b), loops over key tiles.
 template <typename T>
 __global__ void __launch_bounds__(256) attn_bwd_dq_kernel(AttnArgs a) {
+  omr_pdl_enter();
   extern __shared__ __align__(16) float smem[];
   float* Qt = smem;                // [d][i]
   float* dOt = smem + TILE_F;      // [d][i]
@@ -446,7 +450,7 @@ int omr_attn_fwd_simt(int dt, const void* q, long long q_bs, long long q_rs, con
       if (rc) return rc;
       done = true;
     }
-    attn_fwd_kernel<T><<<grid, 256, smem, st>>>(a);
+    OmrLaunch(grid, 256, smem, st)(attn_fwd_kernel<T>, a);
   });
   OMR_LAUNCHED();
   return OMR_OK;
@@ -480,7 +484,7 @@ int omr_attn_bwd_simt(int dt, const void* q, long long q_bs, long long q_rs, con
   dim3 grid_kv((unsigned)cdiv(Tk, BT), (unsigned)H, (unsigned)B);
   dim3 grid_q((unsigned)cdiv(Tq, BT), (unsigned)H, (unsigned)B);
   OMR_DISPATCH_DT(dt, T, {
-    attn_delta_kernel<T><<<(unsigned)cdiv(nw * 32, 256), 256, 0, st>>>(a);
+    OmrLaunch((unsigned)cdiv(nw * 32, 256), 256, 0, st)(attn_delta_kernel<T>, a);
     omr_count_launch();
     static bool done = false;
     if (!done) {
@@ -490,9 +494,9 @@ int omr_attn_bwd_simt(int dt, const void* q, long long q_bs, long long q_rs, con
       if (rc) return rc;
       done = true;
     }
-    attn_bwd_dkdv_kernel<T><<<grid_kv, 256, smem_kv, st>>>(a);
+    OmrLaunch(grid_kv, 256, smem_kv, st)(attn_bwd_dkdv_kernel<T>, a);
     omr_count_launch();
-    attn_bwd_dq_kernel<T><<<grid_q, 256, smem_q, st>>>(a);
+    OmrLaunch(grid_q, 256, smem_q, st)(attn_bwd_dq_kernel<T>, a);
   });
   OMR_LAUNCHED();
   return OMR_OK;

@@ -168,6 +168,7 @@ __device__ __forceinline__ float softmax_row_exp(const SmRow& w, float m_safe, u
 __global__ void __launch_bounds__(192, 2) attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
                                                              const __grid_constant__ CUtensorMap tmK,
                                                              const __grid_constant__ CUtensorMap tmV, AttnTcArgs a) {
+  omr_pdl_enter();
   extern __shared__ __align__(1024) uint8_t smem[];
   if (smem_u32(smem) & 1023u) __trap();  // the swizzled tiles need 1 KB alignment
   uint8_t* sQ = smem;
@@ -414,7 +415,7 @@ int omr_attn_fwd_tc(const void* q, long long q_bs, long long q_rs, const void* k
     configured = true;
   }
   dim3 grid((unsigned)((Tq + BQ - 1) / BQ), (unsigned)H, (unsigned)B);
-  attn_fwd_tc_kernel<<<grid, 192, FWD_SMEM, st>>>(tmQ, tmK, tmV, a);
+  OmrLaunch(grid, 192, FWD_SMEM, st)(attn_fwd_tc_kernel, tmQ, tmK, tmV, a);
   OMR_LAUNCHED();
   return OMR_OK;
 }
@@ -474,6 +475,7 @@ __global__ void __launch_bounds__(320, 1) attn_bwd_tc_kernel(const __grid_consta
                                                              const __grid_constant__ CUtensorMap tmK,
                                                              const __grid_constant__ CUtensorMap tmV,
                                                              const __grid_constant__ CUtensorMap tmDO, AttnBwdArgs g) {
+  omr_pdl_enter();
   extern __shared__ __align__(1024) uint8_t smem[];
   if (smem_u32(smem) & 1023u) __trap();
   const AttnTcArgs& a = g.f;
@@ -770,6 +772,7 @@ __global__ void __launch_bounds__(320, 1) attn_bwd_tc_kernel(const __grid_consta
 // delta[b,h,t] = sum_d dO * O ; one warp per (b,h,t)
 __global__ void attn_delta_tc_kernel(const bf16* __restrict__ o, long long o_bs, long long o_rs, const bf16* __restrict__ dO,
                                      long long do_bs, long long do_rs, float* __restrict__ delta, int B, int H, int Tq) {
+  omr_pdl_enter();
   const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (w >= (long long)B * H * Tq) return;
@@ -786,6 +789,7 @@ __global__ void attn_delta_tc_kernel(const bf16* __restrict__ o, long long o_bs,
 // dq[b,t,h,:] = bf16(scale * dq_acc[b,h,t,:])
 __global__ void attn_dq_finalize_kernel(const float* __restrict__ acc, bf16* __restrict__ dq, long long dq_bs, long long dq_rs,
                                         int B, int H, int Tq, float scale) {
+  omr_pdl_enter();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // one thread = 8 channels
   if (i >= (long long)B * H * Tq * 8) return;
   const int u = (int)(i & 7);
@@ -830,7 +834,7 @@ int omr_attn_bwd_tc(const void* q, long long q_bs, long long q_rs, const void* k
   float* delta = ws;
   float* dq_acc = ws + ((rows + 3) / 4) * 4;  // keep the accumulators 16-byte aligned
   OMR_CUDA(cudaMemsetAsync(dq_acc, 0, sizeof(float) * (size_t)rows * HD, st));
-  attn_delta_tc_kernel<<<(unsigned)((rows * 32 + 255) / 256), 256, 0, st>>>((const bf16*)o, o_bs, o_rs, (const bf16*)dout, do_bs, do_rs,
+  OmrLaunch((unsigned)((rows * 32 + 255) / 256), 256, 0, st)(attn_delta_tc_kernel, (const bf16*)o, o_bs, o_rs, (const bf16*)dout, do_bs, do_rs,
                                                                             delta, B, H, Tq);
   OMR_LAUNCHED();
   AttnBwdArgs g{};
@@ -846,9 +850,9 @@ int omr_attn_bwd_tc(const void* q, long long q_bs, long long q_rs, const void* k
     configured = true;
   }
   dim3 grid((unsigned)((Tk + BKV - 1) / BKV), (unsigned)H, (unsigned)B);
-  attn_bwd_tc_kernel<<<grid, 320, BWD_SMEM, st>>>(tmQ, tmK, tmV, tmDO, g);
+  OmrLaunch(grid, 320, BWD_SMEM, st)(attn_bwd_tc_kernel, tmQ, tmK, tmV, tmDO, g);
   OMR_LAUNCHED();
-  attn_dq_finalize_kernel<<<(unsigned)((rows * 8 + 255) / 256), 256, 0, st>>>(dq_acc, (bf16*)dq, dq_bs, dq_rs, B, H, Tq, scale);
+  OmrLaunch((unsigned)((rows * 8 + 255) / 256), 256, 0, st)(attn_dq_finalize_kernel, dq_acc, (bf16*)dq, dq_bs, dq_rs, B, H, Tq, scale);
   OMR_LAUNCHED();
   return OMR_OK;
 }

@@ -10,6 +10,7 @@ __global__ void __launch_bounds__(256) ce_fwd_kernel(const T* __restrict__ logit
                                                      const long long* __restrict__ targets, int V,
                                                      long long ignore_index, float* __restrict__ row_loss,
                                                      float* __restrict__ row_lse) {
+  omr_pdl_enter();
   __shared__ float sm[33];
   const long long r = blockIdx.x;
   const T* x = logits + r * ld;
@@ -35,6 +36,7 @@ __global__ void __launch_bounds__(256) ce_fwd_vec_kernel(const T* __restrict__ l
                                                          const long long* __restrict__ targets, int V,
                                                          long long ignore_index, float* __restrict__ row_loss,
                                                          float* __restrict__ row_lse) {
+  omr_pdl_enter();
   constexpr int VEC = 16 / (int)sizeof(T);
   __shared__ float sm[33];
   const long long r = blockIdx.x;
@@ -88,6 +90,7 @@ __global__ void __launch_bounds__(256) ce_fwd_vec_kernel(const T* __restrict__ l
 __global__ void __launch_bounds__(1024) ce_reduce_kernel(const float* __restrict__ row_loss,
                                                          const long long* __restrict__ targets, long long rows,
                                                          long long ignore_index, float* __restrict__ out) {
+  omr_pdl_enter();
   __shared__ float sm[33];
   float s = 0.f, n = 0.f;
   for (long long i = threadIdx.x; i < rows; i += blockDim.x) {
@@ -108,6 +111,7 @@ __global__ void __launch_bounds__(256) ce_bwd_kernel(const T* __restrict__ logit
                                                      const float* __restrict__ loss_out,
                                                      const float* __restrict__ gscale, T* __restrict__ dlogits, int V,
                                                      long long ignore_index) {
+  omr_pdl_enter();
   const long long r = blockIdx.x;
   const long long t = targets[r];
   const T* x = logits + r * ld;
@@ -133,6 +137,7 @@ __global__ void __launch_bounds__(256) ce_bwd_vec_kernel(const T* __restrict__ l
                                                          const float* __restrict__ loss_out,
                                                          const float* __restrict__ gscale, T* __restrict__ dlogits, int V,
                                                          long long ignore_index) {
+  omr_pdl_enter();
   constexpr int VEC = 16 / (int)sizeof(T);
   const long long r = blockIdx.x;
   const long long t = targets[r];
@@ -175,7 +180,8 @@ __global__ void __launch_bounds__(256) ce_bwd_vec_kernel(const T* __restrict__ l
 }
 
 // ---- Adam ------------------------------------------------------------------------------------
-__global__ void adam_tick_kernel(int* step) { *step += 1; }
+__global__ void adam_tick_kernel(int* step) {
+  omr_pdl_enter(); *step += 1; }
 
 __device__ __forceinline__ long long adam_shadow_index(long long i, int layout, int d0, int d1) {
   if (layout == 1) {  // [Co,Ci,3,3] -> [Co,3,3,Ci]   (d0 = Co, d1 = Ci)
@@ -207,6 +213,7 @@ __device__ __forceinline__ long long adam_shadow_index(long long i, int layout, 
 
 __global__ void __launch_bounds__(256) adam_kernel(const omr_adam_entry* __restrict__ table, const int* __restrict__ step,
                                                    double lr, double b1d, double b2d, double epsd, double gsd) {
+  omr_pdl_enter();
   const omr_adam_entry e = table[blockIdx.y];
   if (e.grad == nullptr) return;
   const int t = *step;
@@ -238,13 +245,13 @@ extern "C" int omr_ce_fwd(int dt, const void* logits, long long ld, const long l
     const int esz = dt == OMR_F32 ? 4 : 2, vec = 16 / esz;
     const long long nv = (V + vec - 1) / vec;
     if (nv * vec <= ld && nv <= 4 * 256 && (ld * esz) % 16 == 0 && (reinterpret_cast<uintptr_t>(logits) & 15) == 0) {
-      OMR_DISPATCH_DT(dt, T, (ce_fwd_vec_kernel<T><<<(unsigned)rows, 256, 0, as_stream(stream)>>>(
+      OMR_DISPATCH_DT(dt, T, (OmrLaunch((unsigned)rows, 256, 0, as_stream(stream))(ce_fwd_vec_kernel<T>, 
                                  (const T*)logits, ld, targets, V, ignore_index, row_loss, row_lse)));
       OMR_LAUNCHED();
       return OMR_OK;
     }
   }
-  OMR_DISPATCH_DT(dt, T, (ce_fwd_kernel<T><<<(unsigned)rows, 256, 0, as_stream(stream)>>>(
+  OMR_DISPATCH_DT(dt, T, (OmrLaunch((unsigned)rows, 256, 0, as_stream(stream))(ce_fwd_kernel<T>, 
                              (const T*)logits, ld, targets, V, ignore_index, row_loss, row_lse)));
   OMR_LAUNCHED();
   return OMR_OK;
@@ -252,7 +259,7 @@ extern "C" int omr_ce_fwd(int dt, const void* logits, long long ld, const long l
 
 extern "C" int omr_ce_reduce(const float* row_loss, const long long* targets, long long rows, long long ignore_index,
                              float* loss_out, omr_stream_t stream) {
-  ce_reduce_kernel<<<1, 1024, 0, as_stream(stream)>>>(row_loss, targets, rows, ignore_index, loss_out);
+  OmrLaunch(1, 1024, 0, as_stream(stream))(ce_reduce_kernel, row_loss, targets, rows, ignore_index, loss_out);
   OMR_LAUNCHED();
   return OMR_OK;
 }
@@ -266,20 +273,20 @@ extern "C" int omr_ce_bwd(int dt, const void* logits, long long ld, const long l
     const long long nv = (V + vec - 1) / vec;
     if (nv * vec <= ld && (ld * esz) % 16 == 0 && (reinterpret_cast<uintptr_t>(logits) & 15) == 0 &&
         (reinterpret_cast<uintptr_t>(dlogits) & 15) == 0) {
-      OMR_DISPATCH_DT(dt, T, (ce_bwd_vec_kernel<T><<<(unsigned)rows, 256, 0, as_stream(stream)>>>(
+      OMR_DISPATCH_DT(dt, T, (OmrLaunch((unsigned)rows, 256, 0, as_stream(stream))(ce_bwd_vec_kernel<T>, 
                                  (const T*)logits, ld, targets, row_lse, loss_out, gscale, (T*)dlogits, V, ignore_index)));
       OMR_LAUNCHED();
       return OMR_OK;
     }
   }
-  OMR_DISPATCH_DT(dt, T, (ce_bwd_kernel<T><<<(unsigned)rows, 256, 0, as_stream(stream)>>>(
+  OMR_DISPATCH_DT(dt, T, (OmrLaunch((unsigned)rows, 256, 0, as_stream(stream))(ce_bwd_kernel<T>, 
                              (const T*)logits, ld, targets, row_lse, loss_out, gscale, (T*)dlogits, V, ignore_index)));
   OMR_LAUNCHED();
   return OMR_OK;
 }
 
 extern "C" int omr_adam_tick(int* step, omr_stream_t stream) {
-  adam_tick_kernel<<<1, 1, 0, as_stream(stream)>>>(step);
+  OmrLaunch(1, 1, 0, as_stream(stream))(adam_tick_kernel, step);
   OMR_LAUNCHED();
   return OMR_OK;
 }
@@ -291,7 +298,7 @@ extern "C" int omr_adam_step(const omr_adam_entry* table, int n_tensors, long lo
   if (bx < 1) bx = 1;
   if (bx > 64) bx = 64;
   dim3 grid((unsigned)bx, (unsigned)n_tensors);
-  adam_kernel<<<grid, 256, 0, as_stream(stream)>>>(table, step, lr, beta1, beta2, eps, grad_scale);
+  OmrLaunch(grid, 256, 0, as_stream(stream))(adam_kernel, table, step, lr, beta1, beta2, eps, grad_scale);
   OMR_LAUNCHED();
   return OMR_OK;
 }

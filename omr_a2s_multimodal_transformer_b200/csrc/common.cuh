@@ -41,6 +41,37 @@ void omr_count_launch(int n = 1);
     }                                                                                    \
   } while (0)
 
+// ---- programmatic dependent launch ------------------------------------------------------------
+// Every kernel opens with omr_pdl_enter(): it lets the NEXT kernel of the stream start scheduling its CTAs while this
+// grid drains (launch_dependents), then blocks until the PREVIOUS grid has completed and its writes are visible
+// (wait) -- the data dependency is exactly that of ordinary stream order; only launch latency and the CTA ramp overlap.
+// Both instructions are no-ops for a grid launched without the attribute (OMR_PDL=0, or a predecessor that is not a
+// kernel).
+__device__ __forceinline__ void omr_pdl_enter() {
+  asm volatile("griddepcontrol.launch_dependents;\n\tgriddepcontrol.wait;" ::: "memory");
+}
+bool omr_pdl_enabled();  // api.cu: OMR_PDL=1 (default off)
+
+struct OmrLaunch {
+  cudaLaunchConfig_t lc;
+  cudaLaunchAttribute at[1];
+  OmrLaunch(dim3 grid, dim3 block, size_t smem, cudaStream_t st) {
+    lc = cudaLaunchConfig_t{};
+    lc.gridDim = grid;
+    lc.blockDim = block;
+    lc.dynamicSmemBytes = smem;
+    lc.stream = st;
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    lc.attrs = at;
+    lc.numAttrs = omr_pdl_enabled() ? 1 : 0;
+  }
+  template <typename... KArgs, typename... Args>
+  void operator()(void (*kernel)(KArgs...), Args&&... args) {
+    (void)cudaLaunchKernelEx(&lc, kernel, static_cast<KArgs>(args)...);  // the error is picked up by OMR_LAUNCHED()
+  }
+};
+
 #define OMR_DISPATCH_DT(dt, T, ...)                 \
   do {                                              \
     if ((dt) == OMR_F32) {                          \

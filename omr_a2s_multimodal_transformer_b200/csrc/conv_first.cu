@@ -28,6 +28,7 @@ __device__ __forceinline__ void load8<bf16>(const bf16* p, float (&v)[8]) {
 template <typename T>
 __global__ void __launch_bounds__(256) conv1_wgrad_kernel(const T* __restrict__ x, const T* __restrict__ dy, float* __restrict__ dw,
                                                           int N, int H, int W, int Co, int Ho, int Wo, int sh, int sw) {
+  omr_pdl_enter();
   extern __shared__ float red[];  // [8 warps][groups * 72]
   const int groups = Co / 8;
   const long long npix = (long long)N * Ho * Wo;
@@ -95,6 +96,7 @@ __global__ void __launch_bounds__(256) conv1_wgrad_kernel(const T* __restrict__ 
 template <typename T>
 __global__ void __launch_bounds__(256, 3) conv1_fwd_kernel(const T* __restrict__ x, const T* __restrict__ w, const float* __restrict__ bias,
                                                         T* __restrict__ y, int N, int H, int W, int relu) {
+  omr_pdl_enter();
   __shared__ __align__(16) float sw[9][16];
   __shared__ float sb[16];
   if (threadIdx.x < 144) sw[threadIdx.x % 9][threadIdx.x / 9] = to_f(w[threadIdx.x]);  // w: [16][3][3][1]
@@ -150,7 +152,7 @@ int omr_conv3x3_fwd_c1(int dt, const void* x, const void* w, const float* bias, 
   if (total <= 0 || total >= (1LL << 31) - (1LL << 22)) return OMR_TC_NOT_ELIGIBLE;
   long long blocks = cdiv(total, 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
-  OMR_DISPATCH_DT(dt, T, (conv1_fwd_kernel<T><<<(unsigned)blocks, 256, 0, st>>>((const T*)x, (const T*)w, bias, (T*)y, N, H, W, relu)));
+  OMR_DISPATCH_DT(dt, T, (OmrLaunch((unsigned)blocks, 256, 0, st)(conv1_fwd_kernel<T>, (const T*)x, (const T*)w, bias, (T*)y, N, H, W, relu)));
   OMR_LAUNCHED();
   return OMR_OK;
 }
@@ -170,7 +172,7 @@ int omr_conv3x3_wgrad_c1(int dt, const void* x, const void* dy, float* dw, int N
   if (blocks > 148 * 8) blocks = 148 * 8;
   if (blocks < 1) blocks = 1;
   const size_t smem = sizeof(float) * 8 * groups * 72;
-  OMR_DISPATCH_DT(dt, T, (conv1_wgrad_kernel<T><<<(unsigned)blocks, 256, smem, st>>>((const T*)x, (const T*)dy, dw, N, H, W, Co, Ho,
+  OMR_DISPATCH_DT(dt, T, (OmrLaunch((unsigned)blocks, 256, smem, st)(conv1_wgrad_kernel<T>, (const T*)x, (const T*)dy, dw, N, H, W, Co, Ho,
                                                                                     Wo, sh, sw)));
   OMR_LAUNCHED();
   return OMR_OK;

@@ -18,6 +18,7 @@ struct ConvArgs {
 // MODE 0: forward (src = x, dst = y).  MODE 1: data gradient (src = dy, dst = dx, w = [Ci,3,3,Co]).
 template <typename T, int TX, int MODE>
 __global__ void __launch_bounds__(256) conv3x3_igemm_kernel(ConvArgs a) {
+  omr_pdl_enter();
   constexpr int BN_ = 4 * TX, BM_ = 4 * (256 / TX);
   constexpr int LDA = BM_ + 4, LDB = BN_ + 4;
   constexpr int A_PER = BM_ / 16, B_PER = (BN_ * 16 + 255) / 256;
@@ -150,13 +151,13 @@ int launch_conv(const ConvArgs& a, cudaStream_t st) {
   if (Mtot <= 0) return OMR_OK;
   if (a.Cd <= 16) {
     dim3 grid((unsigned)cdiv(Mtot, 256), (unsigned)cdiv(a.Cd, 16));
-    conv3x3_igemm_kernel<T, 4, MODE><<<grid, 256, 0, st>>>(a);
+    OmrLaunch(grid, 256, 0, st)(conv3x3_igemm_kernel<T, 4, MODE>, a);
   } else if (a.Cd <= 32) {
     dim3 grid((unsigned)cdiv(Mtot, 128), (unsigned)cdiv(a.Cd, 32));
-    conv3x3_igemm_kernel<T, 8, MODE><<<grid, 256, 0, st>>>(a);
+    OmrLaunch(grid, 256, 0, st)(conv3x3_igemm_kernel<T, 8, MODE>, a);
   } else {
     dim3 grid((unsigned)cdiv(Mtot, 64), (unsigned)cdiv(a.Cd, 64));
-    conv3x3_igemm_kernel<T, 16, MODE><<<grid, 256, 0, st>>>(a);
+    OmrLaunch(grid, 256, 0, st)(conv3x3_igemm_kernel<T, 16, MODE>, a);
   }
   OMR_LAUNCHED();
   return OMR_OK;
@@ -171,6 +172,7 @@ struct WgradArgs {
 
 template <typename T>
 __global__ void __launch_bounds__(256) conv3x3_wgrad_kernel(WgradArgs a) {
+  omr_pdl_enter();
   constexpr int LDS = 68;
   __shared__ __align__(16) float As[SIMT_BK * LDS];  // [k=pix][m=co]
   __shared__ __align__(16) float Bs[SIMT_BK * LDS];  // [k=pix][n=(tap,ci)]
@@ -290,7 +292,7 @@ int omr_conv3x3_wgrad_simt(int dt, const void* x, const void* dy, float* dw, int
   split = cdiv(nk, per);
   WgradArgs a{x, dy, dw, N, H, W, Ci, Ho, Wo, Co, sh, sw, (int)per};
   dim3 grid((unsigned)cdiv(9 * Ci, 64), (unsigned)cdiv(Co, 64), (unsigned)split);
-  OMR_DISPATCH_DT(dt, T, (conv3x3_wgrad_kernel<T><<<grid, 256, 0, st>>>(a)));
+  OMR_DISPATCH_DT(dt, T, (OmrLaunch(grid, 256, 0, st)(conv3x3_wgrad_kernel<T>, a)));
   OMR_LAUNCHED();
   return OMR_OK;
 }

@@ -54,6 +54,7 @@ struct Cfg {
 template <int RB, int G>
 __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap tmX,
                                                          const __grid_constant__ CUtensorMap tmW, ConvTcArgs g) {
+  omr_pdl_enter();
   using C = Cfg<RB, G>;
   constexpr int STAGES = C::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -226,6 +227,7 @@ template <int RB>
 __global__ void __launch_bounds__(192, 1) conv_halo_kernel(const __grid_constant__ CUtensorMap tmX,
                                                            const __grid_constant__ CUtensorMap tmW, ConvTcArgs g, int wsub,
                                                            int hsub, int stages) {
+  omr_pdl_enter();
   // one tile = TH output rows x TW pixels of one image: ONE (TH+2) x (TW+2) TMA box, TH accumulators of [128 x Cout]
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -413,7 +415,7 @@ int launch_cfg(const CUtensorMap& tmX, const CUtensorMap& tmW, const ConvTcArgs&
     configured = true;
   }
   int grid = a.num_tiles < num_sms() ? a.num_tiles : num_sms();
-  kern<<<grid, 192, Cfg<RB, G>::SMEM, st>>>(tmX, tmW, a);
+  OmrLaunch(grid, 192, Cfg<RB, G>::SMEM, st)(kern, tmX, tmW, a);
   OMR_LAUNCHED();
   return OMR_OK;
 }
@@ -465,9 +467,9 @@ int run_taps(const void* x, int N, int XH, int XW, int Cin, const void* wpack, i
         if (rb == 128) OMR_CUDA(cudaFuncSetAttribute(conv_halo_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         cfgd[ci] = true;
       }
-      if (rb == 32) conv_halo_kernel<32><<<grid, 192, smem_bytes, st>>>(tmX, tmW, h, wsub, hsub, stages);
-      else if (rb == 64) conv_halo_kernel<64><<<grid, 192, smem_bytes, st>>>(tmX, tmW, h, wsub, hsub, stages);
-      else conv_halo_kernel<128><<<grid, 192, smem_bytes, st>>>(tmX, tmW, h, wsub, hsub, stages);
+      if (rb == 32) OmrLaunch(grid, 192, smem_bytes, st)(conv_halo_kernel<32>, tmX, tmW, h, wsub, hsub, stages);
+      else if (rb == 64) OmrLaunch(grid, 192, smem_bytes, st)(conv_halo_kernel<64>, tmX, tmW, h, wsub, hsub, stages);
+      else OmrLaunch(grid, 192, smem_bytes, st)(conv_halo_kernel<128>, tmX, tmW, h, wsub, hsub, stages);
       OMR_LAUNCHED();
       return OMR_OK;
     }

@@ -33,6 +33,7 @@ __device__ __forceinline__ float dot64(const T* __restrict__ row, const float (&
 // grid (B*H, nsplit), block 128
 template <typename T>
 __global__ void __launch_bounds__(128) attn_decode_partial_kernel(DecArgs a) {
+  omr_pdl_enter();
   extern __shared__ float sc[];  // chunk scores, then 2*64 floats for the group reduction
   __shared__ float red[33];
   const int bh = blockIdx.x, b = bh / a.H, h = bh % a.H, sp = blockIdx.y;
@@ -150,6 +151,7 @@ __global__ void __launch_bounds__(128) attn_decode_partial_kernel(DecArgs a) {
 // grid B*H, block 64
 template <typename T>
 __global__ void attn_decode_combine_kernel(DecArgs a) {
+  omr_pdl_enter();
   const int bh = blockIdx.x, b = bh / a.H, h = bh % a.H, d = threadIdx.x;
   float M = -INFINITY;
   for (int s = 0; s < a.nsplit; ++s) M = fmaxf(M, a.ws_ml[((long long)bh * a.nsplit + s) * 2]);
@@ -168,6 +170,7 @@ __global__ void attn_decode_combine_kernel(DecArgs a) {
 template <typename T>
 __global__ void kv_append_kernel(const T* __restrict__ src, long long src_rs, T* __restrict__ cache, int B, int Tmax,
                                  int width, int pos, const int* __restrict__ pos_dev) {
+  omr_pdl_enter();
   if (pos_dev) pos = *pos_dev;
   if (pos < 0 || pos >= Tmax) return;
   long long n = (long long)B * width;
@@ -185,6 +188,7 @@ __global__ void __launch_bounds__(256) argmax_step_kernel(const T* __restrict__ 
                                                           long long pad_id, long long* __restrict__ out_tokens,
                                                           float* __restrict__ out_vals, int out_ld, int step,
                                                           const int* __restrict__ step_dev) {
+  omr_pdl_enter();
   if (step_dev) step = *step_dev;
   __shared__ float sv[256];
   __shared__ int si[256];
@@ -258,9 +262,9 @@ extern "C" int omr_attn_decode(int dt, const void* q, long long q_bs, const void
         done = true;
       }
     }
-    attn_decode_partial_kernel<T><<<grid, 128, smem, st>>>(a);
+    OmrLaunch(grid, 128, smem, st)(attn_decode_partial_kernel<T>, a);
     omr_count_launch();
-    attn_decode_combine_kernel<T><<<(unsigned)bh, HD, 0, st>>>(a);
+    OmrLaunch((unsigned)bh, HD, 0, st)(attn_decode_combine_kernel<T>, a);
   });
   OMR_LAUNCHED();
   return OMR_OK;
@@ -271,7 +275,7 @@ extern "C" int omr_kv_append(int dt, const void* src, long long src_rs, void* ca
   OMR_REQUIRE(pos_dev || (pos >= 0 && pos < Tmax), "omr_kv_append: position %d outside the cache (Tmax %d)", pos, Tmax);
   long long n = (long long)B * width;
   if (n <= 0) return OMR_OK;
-  OMR_DISPATCH_DT(dt, T, (kv_append_kernel<T><<<(unsigned)cdiv(n, 256), 256, 0, as_stream(stream)>>>(
+  OMR_DISPATCH_DT(dt, T, (OmrLaunch((unsigned)cdiv(n, 256), 256, 0, as_stream(stream))(kv_append_kernel<T>, 
                              (const T*)src, src_rs, (T*)cache, B, Tmax, width, pos, pos_dev)));
   OMR_LAUNCHED();
   return OMR_OK;
@@ -282,7 +286,7 @@ extern "C" int omr_argmax_step(int dt, const void* logits, long long ld, int B, 
                                float* out_vals, int out_ld, int step, const int* step_dev, omr_stream_t stream) {
   if (B <= 0) return OMR_OK;
   OMR_REQUIRE(V > 0, "omr_argmax_step: empty vocabulary");
-  OMR_DISPATCH_DT(dt, T, (argmax_step_kernel<T><<<(unsigned)B, 256, 0, as_stream(stream)>>>(
+  OMR_DISPATCH_DT(dt, T, (OmrLaunch((unsigned)B, 256, 0, as_stream(stream))(argmax_step_kernel<T>, 
                              (const T*)logits, ld, V, tok, val, finished, eos_id, pad_id, out_tokens, out_vals, out_ld,
                              step, step_dev)));
   OMR_LAUNCHED();

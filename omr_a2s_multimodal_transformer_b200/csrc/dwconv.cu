@@ -8,6 +8,7 @@ namespace {
 template <typename T, int FLIP>
 __global__ void dwconv3x3_kernel(const T* __restrict__ x, const T* __restrict__ w, const float* __restrict__ bias,
                                  T* __restrict__ y, int N, int H, int W, int C) {
+  omr_pdl_enter();
   const int c4n = C / 4;
   long long total = (long long)N * H * W * c4n;
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -49,6 +50,7 @@ __global__ void dwconv3x3_kernel(const T* __restrict__ x, const T* __restrict__ 
 template <typename T>
 __global__ void dwconv3x3_wgrad_kernel(const T* __restrict__ x, const T* __restrict__ dy, float* __restrict__ dw,
                                        float* __restrict__ db, int N, int H, int W, int C, int pix_per_block) {
+  omr_pdl_enter();
   const int c = threadIdx.x;
   long long P = (long long)N * H * W;
   long long p0 = (long long)blockIdx.x * pix_per_block;
@@ -89,6 +91,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) dwconv3x3_wgrad_wide_kernel(const T* __restrict__ x, const T* __restrict__ dy,
                                                                    float* __restrict__ dw, float* __restrict__ db, int N, int H,
                                                                    int W, int C, int pix_per_block) {
+  omr_pdl_enter();
   extern __shared__ float red[];  // [lanes][C/4][40]
   const int quads = C / 4, lanes = 256 / quads;
   const int cq = threadIdx.x % quads, lane = threadIdx.x / quads;
@@ -183,6 +186,7 @@ template <typename T, int FLIP>
 __global__ void __launch_bounds__(256) dwconv3x3_col_kernel(const T* __restrict__ x, const T* __restrict__ w,
                                                             const float* __restrict__ bias, T* __restrict__ y, int N, int H,
                                                             int W, int C) {
+  omr_pdl_enter();
   constexpr int VEC = R16<T>::N;
   const int cg = C / VEC;
   const int idx = blockIdx.x * 256 + threadIdx.x;
@@ -243,6 +247,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) dwconv3x3_wgrad_col_kernel(const T* __restrict__ x, const T* __restrict__ dy,
                                                                   float* __restrict__ dw, float* __restrict__ db, int N, int H,
                                                                   int W, int C) {
+  omr_pdl_enter();
   extern __shared__ float red[];  // [256][41]
   const int cg = C / 4;
   const int idx = blockIdx.x * 256 + threadIdx.x;
@@ -339,12 +344,12 @@ extern "C" int omr_dwconv3x3_fwd(int dt, const void* x, const void* w, const flo
   if (col_ok(dt, x, w, y, N, H, W, C)) {
     const int vec = dt == OMR_BF16 ? 8 : 4;
     const int blocks = (int)cdiv((long long)N * W * (C / vec), 256);
-    OMR_DISPATCH_DT(dt, T, (dwconv3x3_col_kernel<T, 0><<<blocks, 256, 0, as_stream(stream)>>>((const T*)x, (const T*)w, bias, (T*)y,
+    OMR_DISPATCH_DT(dt, T, (OmrLaunch(blocks, 256, 0, as_stream(stream))(dwconv3x3_col_kernel<T, 0>, (const T*)x, (const T*)w, bias, (T*)y,
                                                                                             N, H, W, C)));
     OMR_LAUNCHED();
     return OMR_OK;
   }
-  OMR_DISPATCH_DT(dt, T, (dwconv3x3_kernel<T, 0><<<grid_cap(total), 256, 0, as_stream(stream)>>>(
+  OMR_DISPATCH_DT(dt, T, (OmrLaunch(grid_cap(total), 256, 0, as_stream(stream))(dwconv3x3_kernel<T, 0>, 
                              (const T*)x, (const T*)w, bias, (T*)y, N, H, W, C)));
   OMR_LAUNCHED();
   return OMR_OK;
@@ -358,12 +363,12 @@ extern "C" int omr_dwconv3x3_dgrad(int dt, const void* dy, const void* w, void* 
   if (col_ok(dt, dy, w, dx, N, H, W, C)) {
     const int vec = dt == OMR_BF16 ? 8 : 4;
     const int blocks = (int)cdiv((long long)N * W * (C / vec), 256);
-    OMR_DISPATCH_DT(dt, T, (dwconv3x3_col_kernel<T, 1><<<blocks, 256, 0, as_stream(stream)>>>((const T*)dy, (const T*)w, nullptr,
+    OMR_DISPATCH_DT(dt, T, (OmrLaunch(blocks, 256, 0, as_stream(stream))(dwconv3x3_col_kernel<T, 1>, (const T*)dy, (const T*)w, nullptr,
                                                                                             (T*)dx, N, H, W, C)));
     OMR_LAUNCHED();
     return OMR_OK;
   }
-  OMR_DISPATCH_DT(dt, T, (dwconv3x3_kernel<T, 1><<<grid_cap(total), 256, 0, as_stream(stream)>>>(
+  OMR_DISPATCH_DT(dt, T, (OmrLaunch(grid_cap(total), 256, 0, as_stream(stream))(dwconv3x3_kernel<T, 1>, 
                              (const T*)dy, (const T*)w, nullptr, (T*)dx, N, H, W, C)));
   OMR_LAUNCHED();
   return OMR_OK;
@@ -384,7 +389,7 @@ extern "C" int omr_dwconv3x3_wgrad(int dt, const void* x, const void* dy, float*
       (long long)N * W * (C / 4) < (1LL << 31) && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
       (reinterpret_cast<uintptr_t>(dy) & 15) == 0) {
     const int blocks = (int)cdiv((long long)N * W * (C / 4), 256);
-    OMR_DISPATCH_DT(dt, T, (dwconv3x3_wgrad_col_kernel<T><<<blocks, 256, sizeof(float) * 256 * 41, st>>>((const T*)x, (const T*)dy, dw,
+    OMR_DISPATCH_DT(dt, T, (OmrLaunch(blocks, 256, sizeof(float) * 256 * 41, st)(dwconv3x3_wgrad_col_kernel<T>, (const T*)x, (const T*)dy, dw,
                                                                                                        db, N, H, W, C)));
     OMR_LAUNCHED();
     return OMR_OK;
@@ -395,7 +400,7 @@ extern "C" int omr_dwconv3x3_wgrad(int dt, const void* x, const void* dy, float*
     if (per < 64) per = 64;
     const int blocks = (int)cdiv(P, per);
     const size_t smem = sizeof(float) * 256 * 40;
-    OMR_DISPATCH_DT(dt, T, (dwconv3x3_wgrad_wide_kernel<T><<<blocks, 256, smem, st>>>((const T*)x, (const T*)dy, dw, db, N, H, W, C,
+    OMR_DISPATCH_DT(dt, T, (OmrLaunch(blocks, 256, smem, st)(dwconv3x3_wgrad_wide_kernel<T>, (const T*)x, (const T*)dy, dw, db, N, H, W, C,
                                                                                      per)));
     OMR_LAUNCHED();
     return OMR_OK;
@@ -403,7 +408,7 @@ extern "C" int omr_dwconv3x3_wgrad(int dt, const void* x, const void* dy, float*
   int per = (int)cdiv(P, 148LL * 8);
   if (per < 16) per = 16;
   int blocks = (int)cdiv(P, per);
-  OMR_DISPATCH_DT(dt, T, (dwconv3x3_wgrad_kernel<T><<<blocks, C, 0, st>>>((const T*)x, (const T*)dy, dw, db, N, H, W,
+  OMR_DISPATCH_DT(dt, T, (OmrLaunch(blocks, C, 0, st)(dwconv3x3_wgrad_kernel<T>, (const T*)x, (const T*)dy, dw, db, N, H, W,
                                                                           C, per)));
   OMR_LAUNCHED();
   return OMR_OK;

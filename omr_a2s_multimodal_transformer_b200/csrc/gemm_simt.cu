@@ -15,6 +15,7 @@ struct GemmArgs {
 
 template <typename TI, typename TO, int TA, int TB>
 __global__ void __launch_bounds__(256) gemm_simt_kernel(GemmArgs g) {
+  omr_pdl_enter();
   __shared__ __align__(16) float As[SIMT_BK * LDS];
   __shared__ __align__(16) float Bs[SIMT_BK * LDS];
   const int tid = threadIdx.x;
@@ -106,6 +107,7 @@ constexpr int SK_KS = 256;          // K slab
 constexpr int SK_LDX = SK_KS + 8;   // padded row (elements) -> 16-byte units of consecutive rows land in distinct banks
 template <typename TI, typename TO>
 __global__ void __launch_bounds__(128) gemm_skinny_kernel(GemmArgs g) {
+  omr_pdl_enter();
   __shared__ __align__(16) TI sx[32 * SK_LDX];
   __shared__ __align__(16) TI sw[8 * SK_LDX];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -173,15 +175,15 @@ template <typename TI, typename TO>
 int launch_gemm(const GemmArgs& g, int transA, int transB, int batch, cudaStream_t st) {
   if (batch == 1 && g.M <= 64 && transA == 0 && transB == 1 && g.K % 8 == 0 && g.lda % 8 == 0 && g.ldb % 8 == 0 &&
       (reinterpret_cast<uintptr_t>(g.A) & 15) == 0 && (reinterpret_cast<uintptr_t>(g.B) & 15) == 0) {
-    gemm_skinny_kernel<TI, TO><<<(unsigned)cdiv(g.N, 8), 128, 0, st>>>(g);
+    OmrLaunch((unsigned)cdiv(g.N, 8), 128, 0, st)(gemm_skinny_kernel<TI, TO>, g);
     OMR_LAUNCHED();
     return OMR_OK;
   }
   dim3 grid((unsigned)cdiv(g.N, BN), (unsigned)cdiv(g.M, BM), (unsigned)batch);
-  if (transA == 0 && transB == 0) gemm_simt_kernel<TI, TO, 0, 0><<<grid, 256, 0, st>>>(g);
-  else if (transA == 0 && transB == 1) gemm_simt_kernel<TI, TO, 0, 1><<<grid, 256, 0, st>>>(g);
-  else if (transA == 1 && transB == 0) gemm_simt_kernel<TI, TO, 1, 0><<<grid, 256, 0, st>>>(g);
-  else gemm_simt_kernel<TI, TO, 1, 1><<<grid, 256, 0, st>>>(g);
+  if (transA == 0 && transB == 0) OmrLaunch(grid, 256, 0, st)(gemm_simt_kernel<TI, TO, 0, 0>, g);
+  else if (transA == 0 && transB == 1) OmrLaunch(grid, 256, 0, st)(gemm_simt_kernel<TI, TO, 0, 1>, g);
+  else if (transA == 1 && transB == 0) OmrLaunch(grid, 256, 0, st)(gemm_simt_kernel<TI, TO, 1, 0>, g);
+  else OmrLaunch(grid, 256, 0, st)(gemm_simt_kernel<TI, TO, 1, 1>, g);
   OMR_LAUNCHED();
   return OMR_OK;
 }

@@ -44,6 +44,7 @@ constexpr int epilogue_bytes(int out_esz) { return 128 * BN * out_esz; }  // the
 template <int BN, int A_MN, int B_MN, typename TO>
 __global__ void __launch_bounds__(320) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                      const __grid_constant__ CUtensorMap tmB, GemmTcArgs g) {
+  omr_pdl_enter();
   const int STAGES = g.stages;
   constexpr int B_TILE_BYTES = BN * BK * 2;
   constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
@@ -273,7 +274,7 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmTcArgs& g, 
   int smem = smem_bytes<BN>(g.stages);
   const int need = epilogue_bytes<BN>((int)sizeof(TO)) + 1024 + 256;
   if (smem < need) smem = need;
-  kern<<<grid, 320, smem, st>>>(tmA, tmB, g);
+  OmrLaunch(grid, 320, smem, st)(kern, tmA, tmB, g);
   OMR_LAUNCHED();
   return OMR_OK;
 }

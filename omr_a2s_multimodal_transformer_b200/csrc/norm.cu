@@ -47,6 +47,7 @@ template <typename T, int MODE>
 __global__ void __launch_bounds__(256) in_partial_kernel(const T* __restrict__ a, const T* __restrict__ xin,
                                                          const float* __restrict__ stats, double* __restrict__ out,
                                                          long long per_sample, int C) {
+  omr_pdl_enter();
   constexpr int VEC = V16<T>::N;
   __shared__ float sm0[256 * VEC], sm1[256 * VEC];
   const int n = blockIdx.y;
@@ -103,6 +104,7 @@ __global__ void __launch_bounds__(256) in_partial_kernel(const T* __restrict__ a
 
 __global__ void in_finalize_kernel(const double* __restrict__ sums, float* __restrict__ stats, long long NC,
                                    double inv_hw, double eps) {
+  omr_pdl_enter();
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < NC) {
     double mean = sums[i * 2] * inv_hw;
@@ -117,6 +119,7 @@ __global__ void in_finalize_kernel(const double* __restrict__ sums, float* __res
 template <typename T>
 __global__ void __launch_bounds__(256) in_apply_fwd_kernel(const T* __restrict__ x, const float* __restrict__ stats,
                                                            T* __restrict__ y, long long per_sample, int C) {
+  omr_pdl_enter();
   constexpr int VEC = V16<T>::N;
   const int n = blockIdx.y;
   const long long step = (long long)gridDim.x * 256 * VEC;
@@ -150,6 +153,7 @@ __global__ void __launch_bounds__(256) in_apply_bwd_kernel(const T* __restrict__
                                                            const float* __restrict__ stats, const double* __restrict__ sums,
                                                            T* __restrict__ dx, long long per_sample, int C, double inv_hw,
                                                            int relu_mask, float mask_scale) {
+  omr_pdl_enter();
   constexpr int VEC = V16<T>::N;
   const int n = blockIdx.y;
   const long long step = (long long)gridDim.x * 256 * VEC;
@@ -211,6 +215,7 @@ __global__ void __launch_bounds__(256) add_ln_fwd_kernel(const T* __restrict__ x
                                                          const float* __restrict__ beta, T* __restrict__ s_out,
                                                          T* __restrict__ y, float* __restrict__ stats, long long rows,
                                                          float eps) {
+  omr_pdl_enter();
   constexpr int D = VPL * 32;
   const int lane = threadIdx.x & 31;
   long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -252,6 +257,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const T* __restrict__ dy, c
                                                      const float* __restrict__ stats, const float* __restrict__ gamma,
                                                      T* __restrict__ ds, float* __restrict__ dgamma,
                                                      float* __restrict__ dbeta, long long rows) {
+  omr_pdl_enter();
   constexpr int D = VPL * 32;
   __shared__ float sg[8][D + 1];
   __shared__ float sb[8][D + 1];
@@ -319,12 +325,12 @@ extern "C" int omr_instnorm_fwd(int dt, const void* x, void* y, float* stats, do
   OMR_CUDA(cudaMemsetAsync(ws, 0, sizeof(double) * (size_t)N * C * 2, st));
   const long long per = (long long)HW * C;
   dim3 grid((unsigned)in_blocks(per, vec, N), (unsigned)N);
-  OMR_DISPATCH_DT(dt, T, (in_partial_kernel<T, 0><<<grid, 256, 0, st>>>((const T*)x, nullptr, nullptr, ws, per, C)));
+  OMR_DISPATCH_DT(dt, T, (OmrLaunch(grid, 256, 0, st)(in_partial_kernel<T, 0>, (const T*)x, nullptr, nullptr, ws, per, C)));
   OMR_LAUNCHED();
-  in_finalize_kernel<<<(int)cdiv((long long)N * C, 256), 256, 0, st>>>(ws, stats, (long long)N * C, 1.0 / HW,
+  OmrLaunch((int)cdiv((long long)N * C, 256), 256, 0, st)(in_finalize_kernel, ws, stats, (long long)N * C, 1.0 / HW,
                                                                                 (double)eps);
   OMR_LAUNCHED();
-  OMR_DISPATCH_DT(dt, T, (in_apply_fwd_kernel<T><<<grid, 256, 0, st>>>((const T*)x, stats, (T*)y, per, C)));
+  OMR_DISPATCH_DT(dt, T, (OmrLaunch(grid, 256, 0, st)(in_apply_fwd_kernel<T>, (const T*)x, stats, (T*)y, per, C)));
   OMR_LAUNCHED();
   return OMR_OK;
 }
@@ -341,9 +347,9 @@ extern "C" int omr_instnorm_bwd(int dt, const void* dy, const void* x, const flo
   OMR_CUDA(cudaMemsetAsync(ws, 0, sizeof(double) * (size_t)N * C * 2, st));
   const long long per = (long long)HW * C;
   dim3 grid((unsigned)in_blocks(per, vec, N), (unsigned)N);
-  OMR_DISPATCH_DT(dt, T, (in_partial_kernel<T, 1><<<grid, 256, 0, st>>>((const T*)dy, (const T*)x, stats, ws, per, C)));
+  OMR_DISPATCH_DT(dt, T, (OmrLaunch(grid, 256, 0, st)(in_partial_kernel<T, 1>, (const T*)dy, (const T*)x, stats, ws, per, C)));
   OMR_LAUNCHED();
-  OMR_DISPATCH_DT(dt, T, (in_apply_bwd_kernel<T><<<grid, 256, 0, st>>>((const T*)dy, (const T*)x, stats, ws, (T*)dx, per, C,
+  OMR_DISPATCH_DT(dt, T, (OmrLaunch(grid, 256, 0, st)(in_apply_bwd_kernel<T>, (const T*)dy, (const T*)x, stats, ws, (T*)dx, per, C,
                                                                       1.0 / HW, relu_mask, mask_scale)));
   OMR_LAUNCHED();
   return OMR_OK;
@@ -368,7 +374,7 @@ extern "C" int omr_add_layernorm_fwd(int dt, const void* x, const void* res, con
   if (rows <= 0) return OMR_OK;
   cudaStream_t st = as_stream(stream);
   int blocks = (int)cdiv(rows, 8);
-  OMR_DISPATCH_DT(dt, T, LN_SWITCH(D, (add_ln_fwd_kernel<T, VPL><<<blocks, 256, 0, st>>>(
+  OMR_DISPATCH_DT(dt, T, LN_SWITCH(D, (OmrLaunch(blocks, 256, 0, st)(add_ln_fwd_kernel<T, VPL>, 
                                           (const T*)x, (const T*)res, gamma, beta, (T*)s_out, (T*)y, stats, rows, eps))));
   OMR_LAUNCHED();
   return OMR_OK;
@@ -382,7 +388,7 @@ extern "C" int omr_layernorm_bwd(int dt, const void* dy, const void* s, const fl
   long long blocks = cdiv(rows, 8 * 4);
   if (blocks > 148 * 4) blocks = 148 * 4;
   if (blocks < 1) blocks = 1;
-  OMR_DISPATCH_DT(dt, T, LN_SWITCH(D, (ln_bwd_kernel<T, VPL><<<(int)blocks, 256, 0, st>>>(
+  OMR_DISPATCH_DT(dt, T, LN_SWITCH(D, (OmrLaunch((int)blocks, 256, 0, st)(ln_bwd_kernel<T, VPL>, 
                                           (const T*)dy, (const T*)s, stats, gamma, (T*)ds, dgamma, dbeta, rows))));
   OMR_LAUNCHED();
   return OMR_OK;

@@ -56,6 +56,7 @@ __device__ __forceinline__ uint32_t swz(uint32_t R, uint32_t c16) {
 template <int RBA, int RBB>  // row bytes of dY (2 Co) and X (2 Ci)
 __global__ void __launch_bounds__((WS_WARPS + 1) * 32) wgrad_small_kernel(const __grid_constant__ CUtensorMap tmDY,
                                                                           const __grid_constant__ CUtensorMap tmX, WsArgs g) {
+  omr_pdl_enter();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + g.stages * g.stage_bytes);
@@ -175,7 +176,7 @@ int launch_ws(const CUtensorMap& tmDY, const CUtensorMap& tmX, const WsArgs& g, 
     OMR_CUDA(cudaFuncSetAttribute(wgrad_small_kernel<RBA, RBB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     configured = true;
   }
-  wgrad_small_kernel<RBA, RBB><<<grid, (WS_WARPS + 1) * 32, smem_bytes, st>>>(tmDY, tmX, g);
+  OmrLaunch(grid, (WS_WARPS + 1) * 32, smem_bytes, st)(wgrad_small_kernel<RBA, RBB>, tmDY, tmX, g);
   OMR_LAUNCHED();
   return OMR_OK;
 }

@@ -36,6 +36,7 @@ struct WgradArgs {
 
 __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY,
                                                           const __grid_constant__ CUtensorMap tmX, WgradArgs g) {
+  omr_pdl_enter();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + g.stages * g.stage_bytes);
@@ -289,7 +290,7 @@ int omr_conv3x3_wgrad_tc(const void* x, const void* dy, float* dw, int N, int H,
     OMR_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured = true;
   }
-  wgrad_tc_kernel<<<g.ctas_per_group * g.tap_groups, 192, smem_bytes, st>>>(tmDY, tmX, g);
+  OmrLaunch(g.ctas_per_group * g.tap_groups, 192, smem_bytes, st)(wgrad_tc_kernel, tmDY, tmX, g);
   OMR_LAUNCHED();
   return OMR_OK;
 }

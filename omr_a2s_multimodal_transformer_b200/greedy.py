@@ -44,6 +44,13 @@ class BatchedGreedyDecoder:
 
     # -- one decode step (all kernels read the position from the device counter ``pos``) ---------------
     def _step(self, st) -> None:
+        logits = self._logits_step(st)
+        ops.argmax_step(logits, st["tok"], st["val"], st["finished"], st["eos"], st["pad"], st["out_tokens"],
+                        st["out_vals"], 0, step_dev=st["pos"])
+        ops.tick(st["pos"])
+
+    def _logits_step(self, st) -> torch.Tensor:
+        """the decoder on the current token ``st["tok"]`` at position ``st["pos"]`` -> logits [B,V] (in ``st["logits"]``)"""
         dec, dtype = self.dec, self.dtype
         c = dec._wcache
         b, d, h = st["B"], dec.d_model, dec.nhead
@@ -82,10 +89,7 @@ class BatchedGreedyDecoder:
             f = ops.linear_fwd(hmid, w2, L.linear2.bias)
             x2, _, _ = ops.add_layernorm_fwd(f, x2n, L.norm3.weight, L.norm3.bias, L.norm3.eps, False)
         wout = c.get(dec.out_layer.weight, "mat", dtype)
-        logits = ops.linear_fwd(x2, wout, dec.out_layer.bias, out=st["logits"])
-        ops.argmax_step(logits, st["tok"], st["val"], st["finished"], st["eos"], st["pad"], st["out_tokens"],
-                        st["out_vals"], 0, step_dev=pos)
-        ops.tick(pos)
+        return ops.linear_fwd(x2, wout, dec.out_layer.bias, out=st["logits"])
 
     def _persistent_ok(self, b: int) -> bool:
         dec = self.dec
@@ -147,17 +151,18 @@ class BatchedGreedyDecoder:
                 f"{n} {c / max(done, 1):.0f} ({100 * c / tot:.0f}%)" for n, c in zip(names, cyc)) + f" | total {tot / max(done, 1):.0f}")
         return done
 
-    @torch.no_grad()
-    def decode(self, memory: torch.Tensor, sos: int, eos: int, pad: int = 0, max_steps: Optional[int] = None,
-               stop_at_eos: bool = True, use_graph: bool = True, poll_every: int = 64,
-               mem_bias: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
-        """memory [B,S,D] -> (tokens int64 [B,steps] (PAD after EOS), top logits fp32 [B,steps], lengths int64 [B])."""
+    def _new_state(self, memory: torch.Tensor, sos: int, eos: int, pad: int, max_steps: Optional[int], stop_at_eos: bool,
+                   mem_bias: Optional[torch.Tensor], shared: Optional[dict] = None) -> dict:
+        """cross K/V of ``memory`` (projected once per layer), the self K/V cache and the device-side bookkeeping of one
+        decode; ``shared`` = a state whose token / position / output buffers this one reuses (lock-step late fusion)"""
         dec, dtype = self.dec, self.dtype
         ops._lib.require_cuda(memory, "greedy decode")
         dev = memory.device
         mem = ops.cast(memory.contiguous(), dtype)
         b, s, d = mem.shape
         steps = dec.max_seq_len if max_steps is None else min(int(max_steps), dec.max_seq_len)
+        if shared is not None:
+            steps = shared["steps"]
         c = dec._wcache
         mem2 = mem.view(b * s, d)
         cross_kv = []
@@ -167,20 +172,36 @@ class BatchedGreedyDecoder:
             cross_kv.append(ops.linear_fwd(mem2, wc_in[d:], ca.in_proj_bias[d:]).view(b, s, 2 * d))
         nl = len(cross_kv)
         st = {
-            "B": b, "eos": int(eos), "pad": int(pad), "cross_kv": cross_kv, "mem_bias": mem_bias,
+            "B": b, "steps": steps, "eos": int(eos), "pad": int(pad), "cross_kv": cross_kv, "mem_bias": mem_bias,
             "self_kv": [torch.zeros((b, steps, 2 * d), dtype=dtype, device=dev) for _ in range(nl)],
             "x": torch.empty((b, 1, d), dtype=dtype, device=dev),
             "logits": torch.empty((b, dec.output_size), dtype=dtype, device=dev),
-            "tok": torch.full((b,), int(sos), dtype=torch.int64, device=dev),
-            "val": torch.zeros((b,), dtype=torch.float32, device=dev),
-            "finished": torch.zeros((b,), dtype=torch.int32, device=dev),
-            "out_tokens": torch.full((b, steps), int(pad), dtype=torch.int64, device=dev),
-            "out_vals": torch.zeros((b, steps), dtype=torch.float32, device=dev),
-            "pos": torch.zeros((1,), dtype=torch.int32, device=dev),
             "ws": torch.empty(ops.attn_decode_ws_floats(b, dec.nhead), dtype=torch.float32, device=dev),
         }
+        if shared is not None:
+            for k in ("tok", "val", "finished", "out_tokens", "out_vals", "pos"):
+                st[k] = shared[k]
+        else:
+            st.update({
+                "tok": torch.full((b,), int(sos), dtype=torch.int64, device=dev),
+                "val": torch.zeros((b,), dtype=torch.float32, device=dev),
+                "finished": torch.zeros((b,), dtype=torch.int32, device=dev),
+                "out_tokens": torch.full((b, steps), int(pad), dtype=torch.int64, device=dev),
+                "out_vals": torch.zeros((b, steps), dtype=torch.float32, device=dev),
+                "pos": torch.zeros((1,), dtype=torch.int32, device=dev),
+            })
         if not stop_at_eos:
             st["eos"] = -1  # never matches: forced full-length decoding
+        return st
+
+    @torch.no_grad()
+    def decode(self, memory: torch.Tensor, sos: int, eos: int, pad: int = 0, max_steps: Optional[int] = None,
+               stop_at_eos: bool = True, use_graph: bool = True, poll_every: int = 64,
+               mem_bias: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        """memory [B,S,D] -> (tokens int64 [B,steps] (PAD after EOS), top logits fp32 [B,steps], lengths int64 [B])."""
+        dec = self.dec
+        st = self._new_state(memory, sos, eos, pad, max_steps, stop_at_eos, mem_bias)
+        b, steps, dev, cross_kv = st["B"], st["steps"], memory.device, st["cross_kv"]
 
         def reset() -> None:
             st["tok"].fill_(int(sos))
@@ -196,36 +217,87 @@ class BatchedGreedyDecoder:
             is_eos = toks == int(eos) if stop_at_eos else torch.zeros_like(toks, dtype=torch.bool)
             first = torch.where(is_eos.any(dim=1), is_eos.float().argmax(dim=1) + 1, torch.full((b,), done_steps, device=dev))
             return toks, vals, first.to(torch.int64)
-        graph = None
-        if use_graph and steps > 2:
-            # warm-up on a side stream (sets kernel attributes, fills the weight cache), then capture one step
-            side = torch.cuda.Stream(device=dev)
-            side.wait_stream(torch.cuda.current_stream(dev))
-            with torch.cuda.stream(side):
-                self._step(st)
-            torch.cuda.current_stream(dev).wait_stream(side)
-            reset()
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                self._step(st)
-            reset()
-        done_steps = 0
-        for t in range(steps):
-            if graph is not None:
-                graph.replay()
-            else:
-                self._step(st)
-            done_steps = t + 1
-            if stop_at_eos and poll_every > 0 and done_steps % poll_every == 0 and done_steps < steps:
-                if bool(st["finished"].all().item()):
-                    break
-        toks = st["out_tokens"][:, :done_steps]
-        vals = st["out_vals"][:, :done_steps]
-        is_eos = toks == int(eos) if stop_at_eos else torch.zeros_like(toks, dtype=torch.bool)
-        first = torch.where(is_eos.any(dim=1), is_eos.float().argmax(dim=1) + 1, torch.full((b,), done_steps, device=dev))
-        return toks, vals, first.to(torch.int64)
+        return _drive(lambda: self._step(st), st, reset, steps, int(eos), stop_at_eos, use_graph, poll_every, dev)
 
     @staticmethod
     def to_lists(tokens: torch.Tensor, vals: torch.Tensor, lengths: torch.Tensor) -> Tuple[List[List[int]], List[List[float]]]:
         tk, vl, ln = tokens.cpu().tolist(), vals.cpu().tolist(), lengths.cpu().tolist()
         return [r[:n] for r, n in zip(tk, ln)], [r[:n] for r, n in zip(vl, ln)]
+
+
+def _drive(step_fn, st, reset, steps: int, eos: int, stop_at_eos: bool, use_graph: bool, poll_every: int, dev):
+    """run ``step_fn`` (one decode step reading the device-side position) ``steps`` times -- replayed from a CUDA graph
+    captured once -- polling the ``finished`` flags every ``poll_every`` steps; -> (tokens, values, lengths)"""
+    b = st["B"]
+    graph = None
+    if use_graph and steps > 2:
+        # warm-up on a side stream (sets kernel attributes, fills the weight cache), then capture one step
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            step_fn()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        reset()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            step_fn()
+        reset()
+    done_steps = 0
+    for t in range(steps):
+        if graph is not None:
+            graph.replay()
+        else:
+            step_fn()
+        done_steps = t + 1
+        if stop_at_eos and poll_every > 0 and done_steps % poll_every == 0 and done_steps < steps:
+            if bool(st["finished"].all().item()):
+                break
+    toks = st["out_tokens"][:, :done_steps]
+    vals = st["out_vals"][:, :done_steps]
+    is_eos = toks == int(eos) if stop_at_eos else torch.zeros_like(toks, dtype=torch.bool)
+    first = torch.where(is_eos.any(dim=1), is_eos.float().argmax(dim=1) + 1, torch.full((b,), done_steps, device=dev))
+    return toks, vals, first.to(torch.int64)
+
+
+class WeightedGreedyDecoder:
+    """Token-level late fusion of two unimodal decoders (reference ``weighted_prediction``,
+    src/multimodal/weighted_multimodal/test.py:21-70): both KV-cached decoders are stepped in lock-step on the SAME
+    token; each step mixes their vocabulary distributions ``alpha * softmax(img) + (1 - alpha) * softmax(audio)`` and
+    takes the first-max argmax (``omr_mix_argmax_step``).  Batched; the reference handles one sample at a time."""
+
+    def __init__(self, img_decoder: Decoder, audio_decoder: Decoder, dtype: Optional[torch.dtype] = None):
+        if img_decoder.output_size != audio_decoder.output_size:
+            raise ValueError("Vocabularies do not match")  # the reference asserts w2i equality (test.py:140)
+        self.a = BatchedGreedyDecoder(img_decoder, dtype)
+        self.b = BatchedGreedyDecoder(audio_decoder, dtype)
+        self.dtype = self.a.dtype
+
+    @torch.no_grad()
+    def decode(self, memory_img: torch.Tensor, memory_audio: torch.Tensor, sos: int, eos: int, pad: int = 0,
+               alpha: float = 0.5, max_steps: Optional[int] = None, stop_at_eos: bool = True, use_graph: bool = True,
+               poll_every: int = 64) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        """memories [B,S_i,D], [B,S_a,D] -> (tokens int64 [B,steps], mixed probabilities fp32 [B,steps], lengths [B])"""
+        if memory_img.shape[0] != memory_audio.shape[0]:
+            raise ValueError("image and audio batches differ")
+        # the reference loops max(img.max_seq_len, audio.max_seq_len) times; both PE tables must cover the prefix
+        limit = min(self.a.dec.max_seq_len, self.b.dec.max_seq_len)
+        steps = limit if max_steps is None else min(int(max_steps), limit)
+        sa = self.a._new_state(memory_img, sos, eos, pad, steps, stop_at_eos, None)
+        sb = self.b._new_state(memory_audio, sos, eos, pad, steps, stop_at_eos, None, shared=sa)
+        dev = memory_img.device
+
+        def step() -> None:
+            la = self.a._logits_step(sa)
+            lb = self.b._logits_step(sb)
+            ops.mix_argmax_step(la, lb, alpha, sa["tok"], sa["val"], sa["finished"], sa["eos"], sa["pad"], sa["out_tokens"],
+                                sa["out_vals"], 0, step_dev=sa["pos"])
+            ops.tick(sa["pos"])
+
+        def reset() -> None:
+            sa["tok"].fill_(int(sos))
+            sa["finished"].zero_()
+            sa["pos"].zero_()
+            sa["out_tokens"].fill_(int(pad))
+            sa["out_vals"].zero_()
+
+        return _drive(step, sa, reset, sa["steps"], int(eos), stop_at_eos, use_graph, poll_every, dev)

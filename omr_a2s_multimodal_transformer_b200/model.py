@@ -27,7 +27,6 @@ from .decoder import Decoder, _CastFn
 from .encoder import HEIGHT_REDUCTION, WIDTH_REDUCTION, Encoder
 from .greedy import BatchedGreedyDecoder
 from .lightning_compat import LightningModule
-from .metrics import compute_metrics
 from .ops import AttnSpec
 from .optim import FusedAdam
 from .params import MHAParams, WeightCache, grad_buf, resolve_dtype
@@ -189,8 +188,12 @@ class _ModelBase(LightningModule):
 
     @torch.no_grad()
     def on_validation_epoch_end(self, name: str = "val", print_random_samples: bool = False) -> Dict[str, float]:
-        """reference model.py:205-220 / 623-636"""
-        metrics = compute_metrics(y_true=self.Y, y_pred=self.YHat)
+        """reference model.py:205-220 / 623-636; the Levenshtein distances of all (truth, prediction) pairs of the epoch
+        are computed by one launch of ``omr_levenshtein`` (``staging.compute_ed_metrics``; same rational numbers as the
+        reference's ``compute_ed_metrics``, src/utils/metrics.py:52-88)"""
+        from .staging import compute_ed_metrics
+
+        metrics = compute_ed_metrics(self.Y, self.YHat, device=self.device)
         for k, v in metrics.items():
             self.log(f"{name}_{k}", v, prog_bar=True, logger=True, on_epoch=True)
         if print_random_samples:

@@ -429,3 +429,44 @@ def attn_decode(q_ptr, q_bs, k_ptr, k_bs, k_rs, v_ptr, v_bs, v_rs, o, key_bias, 
 def tick(counter_i32):
     """*counter += 1 on the stream (device-side step/position counter)"""
     call("omr_adam_tick", ptr(counter_i32), stream_ptr())
+
+
+# ---- staging: collate, late fusion step, Levenshtein (csrc/staging.cu) ---------------------------------------
+def pad_collate(flat, offsets, heights, widths, hmax, wmax, pad_value, height_reduction=16, width_reduction=8):
+    """ragged fp32 samples (flat + offsets/heights/widths on the device) -> (x [B,1,Hmax,Wmax] fp32, n_frames int32 [B])"""
+    _lib.require_cuda(flat, "pad_collate")
+    b = heights.numel()
+    x = torch.empty((b, 1, hmax, wmax), dtype=torch.float32, device=flat.device)
+    nf = torch.empty((b,), dtype=torch.int32, device=flat.device)
+    call("omr_pad_collate", ptr(flat), ptr(offsets), ptr(heights), ptr(widths), ptr(x), b, hmax, wmax, float(pad_value),
+         ptr(nf), height_reduction, width_reduction, stream_ptr())
+    return x, nf
+
+
+def pad_transcripts(flat, offsets, t, pad_id=0):
+    """ragged int64 transcripts -> (y_in, y_out) int64 [B,t] (transcript[:-1] / transcript[1:], zero padded)"""
+    _lib.require_cuda(flat, "pad_transcripts")
+    b = offsets.numel() - 1
+    y_in = torch.empty((b, t), dtype=torch.int64, device=flat.device)
+    y_out = torch.empty((b, t), dtype=torch.int64, device=flat.device)
+    call("omr_pad_transcripts", ptr(flat), ptr(offsets), b, t, ptr(y_in), ptr(y_out), pad_id, stream_ptr())
+    return y_in, y_out
+
+
+def mix_argmax_step(logits_a, logits_b, alpha, tok, val, finished, eos_id, pad_id, out_tokens, out_vals, step, step_dev=None):
+    b, v = logits_a.shape
+    assert logits_b.shape == logits_a.shape and logits_b.dtype == logits_a.dtype
+    call("omr_mix_argmax_step", dt_code(logits_a.dtype), ptr(logits_a), logits_a.stride(0), ptr(logits_b), logits_b.stride(0),
+         b, v, float(alpha), ptr(tok), ptr(val), ptr(finished), eos_id, pad_id, ptr(out_tokens), ptr(out_vals),
+         out_tokens.shape[1] if out_tokens is not None else 0, step, ptr(step_dev), stream_ptr())
+
+
+def levenshtein(truth, truth_offsets, hyp, hyp_offsets, max_len):
+    """-> (ed int32 [P], sums int64 [3] = {sum ed, sum truth length, #pairs with ed > 0}), all on the device"""
+    _lib.require_cuda(truth_offsets, "levenshtein")
+    p = truth_offsets.numel() - 1
+    ed = torch.empty((p,), dtype=torch.int32, device=truth_offsets.device)
+    sums = torch.zeros((3,), dtype=torch.int64, device=truth_offsets.device)
+    call("omr_levenshtein", ptr(truth), ptr(truth_offsets), ptr(hyp), ptr(hyp_offsets), p, int(max_len), ptr(ed), ptr(sums),
+         stream_ptr())
+    return ed, sums

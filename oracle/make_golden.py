@@ -141,6 +141,8 @@ def builder(kind, seed, **kw):
 def main():
     from oracle import restate
 
+    if len(sys.argv) > 1 and sys.argv[1] == "full-size":
+        return main_full_size()
     lens = [20, 12, 7]
     for window in (-1, 5):
         run_case(
@@ -169,6 +171,30 @@ def main():
         lambda sd, b, dt: restate.unimodal_forward(sd, b[0], b[1], b[2], dtype=dt),
         greedy_inputs=lambda w2i, b: [(b[0][:1], torch.tensor([[w2i["<sos>"], 3, 4, w2i["<eos>"]]]))],
         logits_stride=(97, 8), greedy_steps=48,
+    )
+
+
+def main_full_size():
+    """BASELINE configs 2 and 3 at their real per-sample shapes (195x808 spectrograms, 128x1024 images, the grandstaff
+    vocabulary and max length), batch 2 so that the fp64 run fits the build container; logits strided."""
+    from oracle import restate
+
+    run_case(
+        "c2_audio_only", builder("uni", 5, hw=(195, 808), max_len=1268, vocab="real"),
+        lambda w2i: synth.synth_unimodal_batch(2, 195, 808, [300, 129], w2i, pad_value=0.0, frame_lens=[1313, 900]),
+        lambda m, b: m(b[0], b[1], b[2]),
+        lambda sd, b, dt: restate.unimodal_forward(sd, b[0], b[1], b[2], dtype=dt),
+        greedy_inputs=lambda w2i, b: [(b[0][:1], torch.tensor([[w2i["<sos>"], 3, 4, w2i["<eos>"]]]))],
+        logits_stride=(97, 8), greedy_steps=32,
+    )
+    run_case(
+        "c3_multimodal", builder("mm", 6, img=(128, 1024), aud=(195, 808), max_len=1268, mixer="concat", vocab="real"),
+        lambda w2i: synth.synth_multimodal_batch(2, (128, 1024), (195, 808), [300, 129], w2i, img_frame_lens=[1024, 700],
+                                                 aud_frame_lens=[800, 1313]),
+        lambda m, b: m(b[0], b[1], b[2], b[3], b[4]),
+        lambda sd, b, dt: restate.multimodal_forward(sd, b[0], b[1], b[2], b[3], b[4], mixer_type="concat", dtype=dt),
+        greedy_inputs=lambda w2i, b: [(b[0][:1], b[2][:1], torch.tensor([[w2i["<sos>"], 3, 4, w2i["<eos>"]]]))],
+        logits_stride=(97, 8), greedy_steps=32,
     )
 
 

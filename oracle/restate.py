@@ -332,7 +332,8 @@ def multimodal_forward(sd: SD, xi, xli, xa, xla, y_in, mixer_type="concat", attn
 
 @torch.no_grad()
 def greedy_decode(
-    sd: SD, memory: torch.Tensor, sos: int, eos: int, max_seq_len: int, attn_window: int = -1, max_steps: Optional[int] = None
+    sd: SD, memory: torch.Tensor, sos: int, eos: int, max_seq_len: int, attn_window: int = -1, max_steps: Optional[int] = None,
+    nhead: int = 4, num_layers: int = 8,
 ) -> Tuple[List[int], List[float]]:
     """Reference batch-1 loop: re-run the whole decoder on the growing prefix, first-max argmax of
     the last position, append (EOS included) and stop at EOS or after max_seq_len steps.  Returns
@@ -343,7 +344,7 @@ def greedy_decode(
     vals: List[float] = []
     steps = max_seq_len if max_steps is None else min(max_steps, max_seq_len)
     for _ in range(steps):
-        logits = decoder_forward(sd, "decoder.", y_in, memory, None, attn_window)[0, :, -1]
+        logits = decoder_forward(sd, "decoder.", y_in, memory, None, attn_window, nhead, num_layers)[0, :, -1]
         val, tok = logits.max(dim=-1)  # first max index, like argmax / topk(k=1)
         toks.append(int(tok))
         vals.append(float(val))

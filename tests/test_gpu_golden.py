@@ -63,3 +63,88 @@ def test_multimodal_fp32_and_bf16_match_reference_vectors(mixer):
         seqs, _ = m._decoder_runner().to_lists(toks, vals, lens)
         for i, ref_tokens in enumerate(fix["greedy"]):
             assert seqs[i] == ref_tokens, (i, seqs[i], ref_tokens)
+
+
+# ---- BASELINE configs at their real per-sample shapes (grandstaff vocabulary, max_len 1268) ---------------------------
+def _full_size_model(kind, seed):
+    import omr_a2s_multimodal_transformer_b200 as pkg
+
+    w2i, i2w = synth.load_vocab()
+    if kind == "c1":
+        m = pkg.Transformer(128, 1024, 1268, w2i, i2w)
+    elif kind == "c2":
+        m = pkg.Transformer(195, 808, 1268, w2i, i2w)
+    else:
+        m = pkg.MultimodalTransformer(128, 1024, 195, 808, 1268, w2i, i2w, mixer_type="concat")
+    m.load_state_dict(synth.synth_state_dict(m.state_dict(), seed=seed))
+    m = m.to(DEV).eval()
+    m.set_compute_dtype(torch.float32)
+    return m, w2i
+
+
+def _check_full_size(fix, m, fwd, loss_fn, greedy_fn):
+    sv, st = fix["logits_stride"]
+    with torch.no_grad():
+        logits = fwd()
+    assert tuple(logits.shape) == fix["logits_shape"]
+    assert rel_err(logits[:, ::sv, ::st], fix["logits_fp64"]) < 1e-4
+    assert rel_err(logits[:, ::sv, ::st], fix["logits_ref_fp32"]) < 1e-4
+    m.zero_grad(set_to_none=True)
+    loss = loss_fn()
+    loss.backward()
+    assert abs(float(loss) - fix["loss_ref_fp32"]) < 1e-4 * max(1.0, abs(fix["loss_ref_fp32"]))
+    grads = dict(m.named_parameters())
+    num = den = 0.0
+    for k, (nrm, _prj) in fix["grad_summary_fp64"].items():
+        got = float(grads[k].grad.double().norm())
+        num += (got - nrm) ** 2
+        den += nrm ** 2
+    # per-tensor gradient norms against the fp64 truth; the reference's own fp32 run is this far from it
+    ref_floor = fix["noise"]["fp32_grad"][0]
+    assert (num / den) ** 0.5 < max(1e-3, 4 * ref_floor)
+    seqs = greedy_fn()
+    for i, ref_tokens in enumerate(fix["greedy"]):
+        assert seqs[i] == ref_tokens, (i, seqs[i], ref_tokens)
+    m.set_compute_dtype(torch.bfloat16)
+    with torch.no_grad():
+        lb = fwd()
+    assert rel_err(lb.float()[:, ::sv, ::st], fix["logits_fp64"]) < max(1e-2, 1.5 * fix["noise"]["bf16_logits"])
+
+
+@pytest.mark.parametrize("name,seed,hw,lens,frames,pad", [
+    ("c1_image_only", 0, (128, 1024), [257, 200, 128, 64], [1024, 1024, 896, 768], 1.0),
+    ("c2_audio_only", 5, (195, 808), [300, 129], [1313, 900], 0.0),
+])
+def test_full_size_unimodal_matches_reference_vectors(name, seed, hw, lens, frames, pad):
+    """BASELINE config 1 (image-only, batch 4) and config 2's shapes (audio-only 195x808 spectrograms)"""
+    fix = load(name)
+    m, w2i = _full_size_model(name[:2], seed)
+    x, xl, y_in, y_out = synth.synth_unimodal_batch(len(lens), hw[0], hw[1], lens, w2i, pad_value=pad, frame_lens=frames)
+    x, xl, y_in, y_out = x.to(DEV), xl.to(DEV), y_in.to(DEV), y_out.to(DEV)
+    steps = 48 if name.startswith("c1") else 32
+
+    def greedy():
+        toks, vals, ln = m.greedy_decode_batch(x[:1], max_steps=steps)
+        return m._decoder_runner().to_lists(toks, vals, ln)[0]
+
+    _check_full_size(fix, m, lambda: m(x, xl, y_in),
+                     lambda: m.decoder.loss(tgt=y_in, memory=m.encode(x), memory_len=xl, targets=y_out), greedy)
+
+
+def test_full_size_multimodal_matches_reference_vectors():
+    """BASELINE config 3's shapes: image 1x128x1024 + audio 1x195x808 -> fused memory of 2337 positions"""
+    fix = load("c3_multimodal")
+    m, w2i = _full_size_model("c3", 6)
+    batch = synth.synth_multimodal_batch(2, (128, 1024), (195, 808), [300, 129], w2i, img_frame_lens=[1024, 700],
+                                         aud_frame_lens=[800, 1313])
+    xi, xli, xa, xla, y_in, y_out = (t.to(DEV) for t in batch)
+
+    def loss_fn():
+        mem, xl = m._memory(xi, xa, xli, xla, "both")
+        return m.decoder.loss(tgt=y_in, memory=mem, memory_len=xl, targets=y_out)
+
+    def greedy():
+        toks, vals, ln = m.greedy_decode_batch(xi[:1], xa[:1], max_steps=32)
+        return m._decoder_runner().to_lists(toks, vals, ln)[0]
+
+    _check_full_size(fix, m, lambda: m(xi, xli, xa, xla, y_in), loss_fn, greedy)
