@@ -13,6 +13,7 @@ and accumulates parameter gradients straight into ``param.grad``.
 """
 from __future__ import annotations
 
+import os
 from typing import List, Optional, Tuple
 
 import torch
@@ -97,9 +98,17 @@ class _DecoderStackFn(torch.autograd.Function):
         if tape is None:
             raise RuntimeError("decoder backward called twice (activations are released after the first pass)")
         need_dmem = ctx.needs_input_grad[0]
-        state = {"g": dy.contiguous().clone(), "dmem": None, "need_dmem": need_dmem}
+        side = ctx.dec._side_stream(dy.device)
+        # "keep": tensors read by work queued on the side stream; they must outlive it (the allocator only orders reuse
+        # against the stream a block was allocated on), so they are released after the join below
+        state = {"g": dy.contiguous().clone(), "dmem": None, "need_dmem": need_dmem, "side": side, "keep": []}
+        if side is not None:
+            side.wait_stream(torch.cuda.current_stream(dy.device))
         while tape:
             tape.pop()(state)
+        if side is not None:
+            torch.cuda.current_stream(dy.device).wait_stream(side)
+        state["keep"].clear()
         cb = getattr(ctx.dec, "_bwd_done_cb", None)
         if cb is not None:  # data-parallel: the decoder's gradient bucket is complete (ddp.py)
             cb()
@@ -220,6 +229,19 @@ class Decoder(nn.Module):
         return self.create_variable_window_mask(t, w, device=tgt.device), (tgt == 0).to(torch.float32)
 
     # ---- kernels ---------------------------------------------------------------------------------------
+    def _side_stream(self, device) -> Optional["torch.cuda.Stream"]:
+        """The decoder is one dependent chain of small kernels (most of them less than one wave of CTAs); the work that
+        is NOT on that chain -- the 8 cross-K/V projections of the memory in the forward, every weight/bias gradient and
+        the memory gradient in the backward -- is issued on this side stream and fills the idle SMs.
+        ``OMR_OVERLAP_DECODER=0`` keeps everything on one stream."""
+        if os.environ.get("OMR_OVERLAP_DECODER", "1") == "0" or torch.device(device).type != "cuda":
+            return None
+        side = getattr(self, "_side", None)
+        if side is None or side.device != torch.device(device):
+            side = torch.cuda.Stream(device=device)
+            self._side = side
+        return side
+
     def _next_seed(self) -> int:
         self._seed_state = (self._seed_state * 6364136223846793005 + 1442695040888963407) & 0xFFFFFFFFFFFFFFFF
         return (self._seed_state >> 17) & 0x7FFFFFFF
@@ -273,11 +295,28 @@ class Decoder(nn.Module):
         x = self._drop(x, tape, training)
         spec_self = AttnSpec(h, hd, causal=True, window=self.attn_window, key_bias=tgt_bias)
         spec_cross = AttnSpec(h, hd, key_bias=mem_bias)
-        for layer in self.transformer_decoder.layers:
-            x = self._run_layer(layer, x, mem2, b, t, s, spec_self, spec_cross, dtype, tape, training)
+        side = self._side_stream(mem2.device)
+        kvs: List = [None] * len(self.transformer_decoder.layers)
+        if side is not None:
+            # kv_l = memory @ Wkv_l^T depends on the memory only: all layers' projections run beside the chain.  The
+            # outputs are allocated on the current stream (they are consumed and freed there).
+            cur = torch.cuda.current_stream(mem2.device)
+            outs = [torch.empty((b * s, 2 * d), dtype=mem2.dtype, device=mem2.device) for _ in kvs]
+            # working copies of the weights are (re)built on the current stream, which also reads them
+            wkv = [c.get(layer.multihead_attn.in_proj_weight, "mat", dtype) for layer in self.transformer_decoder.layers]
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                for i, layer in enumerate(self.transformer_decoder.layers):
+                    ca = layer.multihead_attn
+                    ops.linear_fwd(mem2, wkv[i][d:], ca.in_proj_bias[d:], out=outs[i])
+                    kvs[i] = (outs[i], side.record_event())
+        for i, layer in enumerate(self.transformer_decoder.layers):
+            x = self._run_layer(layer, x, mem2, b, t, s, spec_self, spec_cross, dtype, tape, training, kvs[i])
+        if side is not None:
+            torch.cuda.current_stream(mem2.device).wait_stream(side)
         return x
 
-    def _run_layer(self, L: _DecoderLayer, x, mem2, b, t, s, spec_self, spec_cross, dtype, tape, training):
+    def _run_layer(self, L: _DecoderLayer, x, mem2, b, t, s, spec_self, spec_cross, dtype, tape, training, kv_ready=None):
         c = self._wcache
         d = self.d_model
         sa, ca = L.self_attn, L.multihead_attn
@@ -304,7 +343,11 @@ class Decoder(nn.Module):
         # --- cross-attention block: x2 = LN(x1 + out_proj(attn(q(x1), kv(memory)))) ----------------
         x1_2d = x1.view(b * t, d)
         q = ops.linear_fwd(x1_2d, wc_in[:d], ca.in_proj_bias[:d]).view(b, t, d)
-        kv = ops.linear_fwd(mem2, wc_in[d:], ca.in_proj_bias[d:]).view(b, s, 2 * d)
+        if kv_ready is None:
+            kv = ops.linear_fwd(mem2, wc_in[d:], ca.in_proj_bias[d:]).view(b, s, 2 * d)
+        else:  # projected on the side stream (see _run_stack)
+            kv = kv_ready[0].view(b, s, 2 * d)
+            torch.cuda.current_stream(mem2.device).wait_event(kv_ready[1])
         o2, lse2 = ops.attn_fwd(q, 0, kv, 0, kv, d, spec_cross)
         cc = ops.linear_fwd(o2.view(b * t, d), wc_o, ca.out_proj.bias).view(b, t, d)
         seed2 = self._next_seed() if training and self.dropout_p > 0 else None
@@ -330,25 +373,46 @@ class Decoder(nn.Module):
 
         def bwd(st) -> None:
             g = st["g"]  # dL/dx3 [B,T,D]
+            side = st.get("side")
+            cur = torch.cuda.current_stream(mem2.device) if side is not None else None
+
+            def off_chain(fn, *tensors) -> None:
+                """run fn() -- work nothing later in this chain reads -- on the side stream, after everything queued
+                so far; ``tensors`` are its inputs (kept alive until the side stream is joined)"""
+                if side is None:
+                    fn()
+                    return
+                st["keep"].extend(tensors)
+                side.wait_event(cur.record_event())
+                with torch.cuda.stream(side):
+                    fn()
+
+            def join_if(aliased: bool) -> None:
+                # without dropout d(sublayer output) IS the residual-gradient buffer, which the chain accumulates into
+                if aliased and side is not None:
+                    cur.wait_stream(side)
+
             # feed-forward block
             ds3 = ops.layernorm_bwd(g, s3, st3, L.norm3.weight, grad_buf(L.norm3.weight), grad_buf(L.norm3.bias))
             ds3_2d = ds3.view(b * t, d)
             df = ops.dropout(ds3_2d, p, seed4) if seed4 is not None else ds3_2d
             if train_w:
-                ops.linear_wgrad(hdrop, df, grad_buf(L.linear2.weight), grad_buf(L.linear2.bias))
+                off_chain(lambda: ops.linear_wgrad(hdrop, df, grad_buf(L.linear2.weight), grad_buf(L.linear2.bias)), hdrop, df)
             dh = ops.linear_dgrad(df, w2)
             if seed3 is not None:
                 ops.dropout(dh, p, seed3, inplace=True)
             ops.relu_bwd(hmid, dh, inplace=True)
             if train_w:
-                ops.linear_wgrad(x2_2d, dh, grad_buf(L.linear1.weight), grad_buf(L.linear1.bias))
+                off_chain(lambda: ops.linear_wgrad(x2_2d, dh, grad_buf(L.linear1.weight), grad_buf(L.linear1.bias)), x2_2d, dh)
+            join_if(seed4 is None)
             ops.gemm(dh, w1, ds3_2d, b * t, d, ff, lda=ff, ldb=d, ldc=d, accumulate=True)  # dx2 = ds3 + dh W1
             # cross-attention block
             ds2 = ops.layernorm_bwd(ds3, s2, st2, L.norm2.weight, grad_buf(L.norm2.weight), grad_buf(L.norm2.bias))
             ds2_2d = ds2.view(b * t, d)
             dcc = ops.dropout(ds2_2d, p, seed2) if seed2 is not None else ds2_2d
             if train_w:
-                ops.linear_wgrad(o2.view(b * t, d), dcc, grad_buf(ca.out_proj.weight), grad_buf(ca.out_proj.bias))
+                off_chain(lambda: ops.linear_wgrad(o2.view(b * t, d), dcc, grad_buf(ca.out_proj.weight),
+                                                   grad_buf(ca.out_proj.bias)), o2, dcc)
             do2 = ops.linear_dgrad(dcc, wc_o).view(b, t, d)
             dq = torch.empty_like(q)
             dkv = torch.empty_like(kv)
@@ -357,27 +421,37 @@ class Decoder(nn.Module):
             dq2 = dq.view(b * t, d)
             if train_w:
                 gw, gb = grad_buf(ca.in_proj_weight), grad_buf(ca.in_proj_bias)
-                ops.linear_wgrad(mem2, dkv2, gw[d:], gb[d:])
-                ops.linear_wgrad(x1_2d, dq2, gw[:d], gb[:d])
+
+                def cross_wgrads() -> None:
+                    ops.linear_wgrad(mem2, dkv2, gw[d:], gb[d:])
+                    ops.linear_wgrad(x1_2d, dq2, gw[:d], gb[:d])
+
+                off_chain(cross_wgrads, mem2, dkv2, x1_2d, dq2)
             if st["need_dmem"]:
                 first = st["dmem"] is None
                 if first:
                     st["dmem"] = torch.empty((b, s, d), dtype=dtype, device=mem2.device)
-                ops.gemm(dkv2, wc_in[d:], st["dmem"].view(b * s, d), b * s, d, 2 * d, lda=2 * d, ldb=d, ldc=d,
-                         accumulate=not first)
+                dmem2 = st["dmem"].view(b * s, d)
+                # the memory gradient is only read after the whole stack: its 8 accumulating GEMMs stay off the chain
+                off_chain(lambda: ops.gemm(dkv2, wc_in[d:], dmem2, b * s, d, 2 * d, lda=2 * d, ldb=d, ldc=d,
+                                           accumulate=not first), dkv2)
+            join_if(seed2 is None)
             ops.gemm(dq2, wc_in[:d], ds2_2d, b * t, d, d, lda=d, ldb=d, ldc=d, accumulate=True)  # dx1 = ds2 + dq Wq
             # self-attention block
             ds1 = ops.layernorm_bwd(ds2, s1, st1, L.norm1.weight, grad_buf(L.norm1.weight), grad_buf(L.norm1.bias))
             ds1_2d = ds1.view(b * t, d)
             da = ops.dropout(ds1_2d, p, seed1) if seed1 is not None else ds1_2d
             if train_w:
-                ops.linear_wgrad(o.view(b * t, d), da, grad_buf(sa.out_proj.weight), grad_buf(sa.out_proj.bias))
+                off_chain(lambda: ops.linear_wgrad(o.view(b * t, d), da, grad_buf(sa.out_proj.weight),
+                                                   grad_buf(sa.out_proj.bias)), o, da)
             do = ops.linear_dgrad(da, w_o).view(b, t, d)
             dqkv = torch.empty_like(qkv)
             ops.attn_bwd(qkv, 0, qkv, d, qkv, 2 * d, o, do, lse, dqkv, 0, dqkv, d, dqkv, 2 * d, spec_self)
             dqkv2 = dqkv.view(b * t, 3 * d)
             if train_w:
-                ops.linear_wgrad(x2d, dqkv2, grad_buf(sa.in_proj_weight), grad_buf(sa.in_proj_bias))
+                off_chain(lambda: ops.linear_wgrad(x2d, dqkv2, grad_buf(sa.in_proj_weight), grad_buf(sa.in_proj_bias)),
+                          x2d, dqkv2)
+            join_if(seed1 is None)
             ops.gemm(dqkv2, w_in, ds1_2d, b * t, d, 3 * d, lda=3 * d, ldb=d, ldc=d, accumulate=True)  # dx = ds1 + dqkv Win
             st["g"] = ds1
 

@@ -326,3 +326,37 @@ def test_graphed_train_step_matches_eager():
     (l0, p0), (l1, p1) = finals
     assert max(abs(a - b) for a, b in zip(l0, l1)) < 2e-2 * max(l0), (l0, l1)
     assert l1[-1] < l1[0]  # it trains
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-5), (torch.bfloat16, 2e-3)])
+@pytest.mark.parametrize("train", [True, False])
+def test_decoder_side_stream_overlap_matches_single_stream(monkeypatch, dtype, tol, train):
+    """The decoder issues the work that is off its dependent chain (cross-K/V projections, weight / bias / memory
+    gradients) on a side stream; loss and every gradient must equal the single-stream run (same dropout seeds; the
+    split-K atomics make the sums order-dependent, hence a tolerance instead of bit equality).  Eval mode exercises the
+    aliasing joins (without dropout the sublayer gradient IS the residual-gradient buffer)."""
+    import random
+
+    results = []
+    for overlap in ("0", "1"):
+        monkeypatch.setenv("OMR_OVERLAP_DECODER", overlap)
+        m, sd, w2i = build_multimodal(dtype=dtype)
+        if train:
+            m.train()
+        random.seed(0)
+        xi, xli, xa, xla, y_in, y_out = synth.synth_multimodal_batch(3, (64, 128), (48, 96), [33, 12, 7], w2i)
+        losses = []
+        for _ in range(2):  # twice: the second pass reuses freed blocks of the first (allocator / stream ordering)
+            m.zero_grad(set_to_none=True)
+            mem, xl = m._memory(xi.to(DEV), xa.to(DEV), xli.to(DEV), xla.to(DEV), "both")
+            loss = m.decoder.loss(tgt=y_in.to(DEV), memory=mem, memory_len=xl, targets=y_out.to(DEV))
+            loss.backward()
+            losses.append(float(loss))
+        torch.cuda.synchronize()
+        results.append((losses, {k: p.grad.detach().double().cpu() for k, p in m.named_parameters() if p.grad is not None}))
+    (l0, g0), (l1, g1) = results
+    assert max(abs(a - b) for a, b in zip(l0, l1)) < tol * max(1.0, abs(l0[0]))
+    assert set(g0) == set(g1)
+    num = sum(float((g1[k] - g0[k]).pow(2).sum()) for k in g0)
+    den = sum(float(g0[k].pow(2).sum()) for k in g0)
+    assert (num / den) ** 0.5 < tol, (num / den) ** 0.5
