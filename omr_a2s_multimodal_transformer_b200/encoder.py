@@ -69,7 +69,9 @@ class _Act:
         self.scale = 1.0
 
 
-def _maybe_dropout(x: torch.Tensor, c: _Ctx, here: bool, act: Optional[_Act] = None) -> torch.Tensor:
+def _maybe_dropout(x: torch.Tensor, c: _Ctx, here: bool, act: Optional[_Act] = None, inplace_bwd: bool = True) -> torch.Tensor:
+    """inplace_bwd=False: the incoming gradient has a second reader (the residual branch of a DSC block) and must not
+    be overwritten by the dropout backward."""
     if not (here and c.training and c.dropout.p > 0.0):
         return x
     elementwise = c.dropout.kind()
@@ -83,7 +85,7 @@ def _maybe_dropout(x: torch.Tensor, c: _Ctx, here: bool, act: Optional[_Act] = N
         def bwd(dy: torch.Tensor) -> torch.Tensor:
             if act is not None and act.premasked:
                 return dy  # the consumer of y already applied (y > 0 ? 1/(1-p) : 0)
-            return ops.dropout(dy, p, seed, channelwise=not elementwise, inplace=True)
+            return ops.dropout(dy, p, seed, channelwise=not elementwise, inplace=inplace_bwd)
 
         c.tape.append(bwd)
     return y
@@ -243,7 +245,8 @@ class DSCBlock(nn.Module):
         x = _maybe_dropout(x, c, pos == 2)
         x = _instnorm_step(x, c)
         x = self.conv3._run(x, False, c)
-        x = _maybe_dropout(x, c, pos == 3)
+        # the block's output gradient is also the gradient of the residual branch (Encoder._run): keep it intact
+        x = _maybe_dropout(x, c, pos == 3, inplace_bwd=False)
         return x
 
 

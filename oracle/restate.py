@@ -39,13 +39,15 @@ def instance_norm(x: torch.Tensor, eps: float = IN_EPS) -> torch.Tensor:
     return (x - mean) / torch.sqrt(var + eps)
 
 
-def conv_block(sd: SD, pre: str, x: torch.Tensor, stride: Tuple[int, int]) -> torch.Tensor:
-    """ConvBlock.forward in eval mode: encoder.py:159-181."""
+def conv_block(sd: SD, pre: str, x: torch.Tensor, stride: Tuple[int, int], drop=None) -> torch.Tensor:
+    """ConvBlock.forward: encoder.py:159-181.  ``drop`` (train mode only): callable(slot, x) -> x applied at the three
+    MixDropout slots (after the ReLUs of conv1, conv2, conv3); None = eval mode."""
     dt = x.dtype
-    x = F.relu(F.conv2d(x, _p(sd, pre + "conv1.weight", dt), _p(sd, pre + "conv1.bias", dt), padding=1))
-    x = F.relu(F.conv2d(x, _p(sd, pre + "conv2.weight", dt), _p(sd, pre + "conv2.bias", dt), padding=1))
+    drop = drop or (lambda slot, t: t)
+    x = drop(1, F.relu(F.conv2d(x, _p(sd, pre + "conv1.weight", dt), _p(sd, pre + "conv1.bias", dt), padding=1)))
+    x = drop(2, F.relu(F.conv2d(x, _p(sd, pre + "conv2.weight", dt), _p(sd, pre + "conv2.bias", dt), padding=1)))
     x = instance_norm(x)
-    x = F.relu(F.conv2d(x, _p(sd, pre + "conv3.weight", dt), _p(sd, pre + "conv3.bias", dt), padding=1, stride=stride))
+    x = drop(3, F.relu(F.conv2d(x, _p(sd, pre + "conv3.weight", dt), _p(sd, pre + "conv3.bias", dt), padding=1, stride=stride)))
     return x
 
 
@@ -58,21 +60,24 @@ def depth_sep_conv(sd: SD, pre: str, x: torch.Tensor) -> torch.Tensor:
     return x
 
 
-def dsc_block(sd: SD, pre: str, x: torch.Tensor) -> torch.Tensor:
-    """DSCBlock.forward in eval mode (ReLU after conv1/conv2 only): encoder.py:218-238."""
-    x = F.relu(depth_sep_conv(sd, pre + "conv1.", x))
-    x = F.relu(depth_sep_conv(sd, pre + "conv2.", x))
+def dsc_block(sd: SD, pre: str, x: torch.Tensor, drop=None) -> torch.Tensor:
+    """DSCBlock.forward (ReLU after conv1/conv2 only): encoder.py:218-238; ``drop`` as in conv_block."""
+    drop = drop or (lambda slot, t: t)
+    x = drop(1, F.relu(depth_sep_conv(sd, pre + "conv1.", x)))
+    x = drop(2, F.relu(depth_sep_conv(sd, pre + "conv2.", x)))
     x = instance_norm(x)
-    x = depth_sep_conv(sd, pre + "conv3.", x)
+    x = drop(3, depth_sep_conv(sd, pre + "conv3.", x))
     return x
 
 
-def encoder_forward(sd: SD, pre: str, x: torch.Tensor) -> torch.Tensor:
-    """Encoder.forward: encoder.py:271-291.  x [B,1,H,W] -> [B,256,ceil(H/16),ceil(W/8)]."""
+def encoder_forward(sd: SD, pre: str, x: torch.Tensor, drop=None) -> torch.Tensor:
+    """Encoder.forward: encoder.py:271-291.  x [B,1,H,W] -> [B,256,ceil(H/16),ceil(W/8)].
+    ``drop``: callable(block_index 0..8, slot 1..3, x) -> x for a train-mode pass with given dropout masks."""
+    bd = (lambda b: None) if drop is None else (lambda b: (lambda slot, t: drop(b, slot, t)))
     for i, s in enumerate(CONV_BLOCK_STRIDES):
-        x = conv_block(sd, f"{pre}conv_blocks.{i}.", x, s)
+        x = conv_block(sd, f"{pre}conv_blocks.{i}.", x, s, bd(i))
     for i in range(4):
-        xt = dsc_block(sd, f"{pre}dscblocks.{i}.", x)
+        xt = dsc_block(sd, f"{pre}dscblocks.{i}.", x, bd(len(CONV_BLOCK_STRIDES) + i))
         x = x + xt if x.shape == xt.shape else xt  # encoder.py:287-289
     return x
 

@@ -360,3 +360,57 @@ def test_decoder_side_stream_overlap_matches_single_stream(monkeypatch, dtype, t
     num = sum(float((g1[k] - g0[k]).pow(2).sum()) for k in g0)
     den = sum(float(g0[k].pow(2).sum()) for k in g0)
     assert (num / den) ** 0.5 < tol, (num / den) ** 0.5
+
+
+@pytest.mark.parametrize("pos", [1, 2, 3])
+@pytest.mark.parametrize("elementwise", [True, False])
+def test_encoder_train_mode_gradients_with_the_kernels_own_dropout_masks(monkeypatch, pos, elementwise):
+    """Train mode: every block's MixDropout forced to one slot / kind; the keep masks the kernels drew are read back
+    (dropout of a tensor of ones with the same seed) and replayed in the oracle encoder, whose autograd gradients are the
+    reference for the hand-written backward (fused ReLU/dropout epilogues, the residual branch of the DSC blocks)."""
+    from omr_a2s_multimodal_transformer_b200 import encoder as enc_mod
+    from omr_a2s_multimodal_transformer_b200 import ops
+
+    monkeypatch.setattr(enc_mod.DropoutPlan, "draw", lambda self: pos)
+    monkeypatch.setattr(enc_mod.DropoutPlan, "kind", lambda self: elementwise)
+    calls = []
+    real = ops.dropout
+
+    def spy(x, p, seed, channelwise=False, inplace=False):
+        if len(calls) < 9:  # the nine forward calls come first (one per block)
+            calls.append((p, seed, channelwise, tuple(x.shape)))
+        return real(x, p, seed, channelwise=channelwise, inplace=inplace)
+
+    monkeypatch.setattr(ops, "dropout", spy)
+    enc = __import__("omr_a2s_multimodal_transformer_b200").Encoder(1)
+    sd = synth.synth_state_dict(enc.state_dict(), seed=5)
+    enc.load_state_dict(sd)
+    enc = enc.to(DEV).train()
+    enc.compute_dtype = torch.float32
+    x = torch.rand(2, 1, 64, 128, generator=torch.Generator().manual_seed(1))
+    y = enc(x.to(DEV))
+    assert len(calls) == 9
+    gy = torch.randn(y.shape, generator=torch.Generator().manual_seed(2))
+    y.backward(gy.to(DEV))
+    # keep masks (already scaled by 1/(1-p)) in NCHW for the oracle
+    masks = []
+    for p, seed, cw, shape in calls:
+        assert abs(p - (0.5 if elementwise else 0.25)) < 1e-9 and cw == (not elementwise)
+        m = real(torch.ones(shape, device=DEV), p, seed, channelwise=cw)
+        keep = float((m > 0).float().mean())
+        assert abs(keep - (1 - p)) < (0.02 if elementwise else 0.2)
+        masks.append(m.permute(0, 3, 1, 2).double().cpu())
+
+    def drop(block, slot, t):
+        return t * masks[block].to(t.dtype) if slot == pos else t
+
+    ref_loss, ref_g = oracle_grads(lambda s: (restate.encoder_forward(s, "", x.double(), drop=drop) * gy.double()).sum(),
+                                   {k: v.double() for k, v in sd.items()})
+    with torch.no_grad():
+        ref_y = restate.encoder_forward({k: v.double() for k, v in sd.items()}, "", x.double(), drop=drop)
+    assert rel_err(y, ref_y) < 1e-4
+    rep = grad_report(enc, ref_g)
+    assert not rep["missing"], rep
+    # fp32 kernels against the fp64 oracle; a ReLU pre-activation within rounding of zero may flip one mask entry (see
+    # test_multimodal_logits_loss_grads), hence 1e-2 rather than 1e-4 -- a wrongly masked branch shows up as O(1)
+    assert rep["global_rel"] < 1e-2 and rep["cos"] > 1 - 1e-3, rep
