@@ -200,19 +200,22 @@ def memory_key_padding_mask(memory: torch.Tensor, memory_len: Optional[torch.Ten
     return m
 
 
-def decoder_layer(sd: SD, pre: str, x, memory, tmask, tkpm, mkpm, nhead: int) -> torch.Tensor:
-    """torch nn.TransformerDecoderLayer, post-norm, ReLU FFN (built at decoder.py:86-95)."""
+def decoder_layer(sd: SD, pre: str, x, memory, tmask, tkpm, mkpm, nhead: int, drop=None) -> torch.Tensor:
+    """torch nn.TransformerDecoderLayer, post-norm, ReLU FFN (built at decoder.py:86-95).  ``drop`` (train mode with given
+    masks): callable(slot, x) -> x at dropout1 (1), dropout2 (2), the FFN's inner dropout (3) and dropout3 (4); the
+    attention-probability dropout is not replayed here (tests/test_gpu_ops.py covers it at kernel level)."""
     dt = x.dtype
     D = x.shape[-1]
+    drop = drop or (lambda slot, t: t)
 
     def ln(t, name):
         return F.layer_norm(t, (D,), _p(sd, pre + name + ".weight", dt), _p(sd, pre + name + ".bias", dt), LN_EPS)
 
-    x = ln(x + mha(sd, pre + "self_attn.", x, x, x, nhead, attn_mask=tmask, key_padding_mask=tkpm), "norm1")
-    x = ln(x + mha(sd, pre + "multihead_attn.", x, memory, memory, nhead, key_padding_mask=mkpm), "norm2")
-    h = F.relu(F.linear(x, _p(sd, pre + "linear1.weight", dt), _p(sd, pre + "linear1.bias", dt)))
+    x = ln(x + drop(1, mha(sd, pre + "self_attn.", x, x, x, nhead, attn_mask=tmask, key_padding_mask=tkpm)), "norm1")
+    x = ln(x + drop(2, mha(sd, pre + "multihead_attn.", x, memory, memory, nhead, key_padding_mask=mkpm)), "norm2")
+    h = drop(3, F.relu(F.linear(x, _p(sd, pre + "linear1.weight", dt), _p(sd, pre + "linear1.bias", dt))))
     h = F.linear(h, _p(sd, pre + "linear2.weight", dt), _p(sd, pre + "linear2.bias", dt))
-    return ln(x + h, "norm3")
+    return ln(x + drop(4, h), "norm3")
 
 
 def decoder_hidden(
@@ -224,23 +227,29 @@ def decoder_hidden(
     attn_window: int = -1,
     nhead: int = 4,
     num_layers: int = 8,
+    drop=None,
 ) -> torch.Tensor:
-    """Decoder.forward up to (not including) the classifier: decoder.py:104-143."""
+    """Decoder.forward up to (not including) the classifier: decoder.py:104-143.
+    ``drop``: callable(layer index or -1 for the embedding dropout, slot, x) -> x (train mode with given masks)."""
     dt = memory.dtype
     emb = _p(sd, pre + "embedding.weight", dt)[tgt]  # row padding_idx is zero (decoder.py:73-77)
     x = emb + sd[pre + "pos_1d.pe"].to(dt)[:, : tgt.shape[1], :]  # decoder.py:29-32
+    if drop is not None:
+        x = drop(-1, 0, x)
     mkpm = memory_key_padding_mask(memory, memory_len)
     tmask, tkpm = tgt_masks(tgt, attn_window, dt)
     tkpm = None if mkpm is None else tkpm  # decoder.py:132
     for i in range(num_layers):
-        x = decoder_layer(sd, f"{pre}transformer_decoder.layers.{i}.", x, memory, tmask, tkpm, mkpm, nhead)
+        ld = None if drop is None else (lambda slot, t, i=i: drop(i, slot, t))
+        x = decoder_layer(sd, f"{pre}transformer_decoder.layers.{i}.", x, memory, tmask, tkpm, mkpm, nhead, ld)
     return x
 
 
-def decoder_forward(sd: SD, pre: str, tgt, memory, memory_len, attn_window: int = -1, nhead: int = 4, num_layers: int = 8):
+def decoder_forward(sd: SD, pre: str, tgt, memory, memory_len, attn_window: int = -1, nhead: int = 4, num_layers: int = 8,
+                    drop=None):
     """Decoder.forward: decoder.py:104-148 -> logits [B,V,T] (Conv1d k=1 on the permuted hidden)."""
     dt = memory.dtype
-    h = decoder_hidden(sd, pre, tgt, memory, memory_len, attn_window, nhead, num_layers)
+    h = decoder_hidden(sd, pre, tgt, memory, memory_len, attn_window, nhead, num_layers, drop)
     w = _p(sd, pre + "out_layer.weight", dt)  # [V,D,1]
     return F.conv1d(h.permute(0, 2, 1).contiguous(), w, _p(sd, pre + "out_layer.bias", dt))
 

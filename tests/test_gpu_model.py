@@ -414,3 +414,49 @@ def test_encoder_train_mode_gradients_with_the_kernels_own_dropout_masks(monkeyp
     # fp32 kernels against the fp64 oracle; a ReLU pre-activation within rounding of zero may flip one mask entry (see
     # test_multimodal_logits_loss_grads), hence 1e-2 rather than 1e-4 -- a wrongly masked branch shows up as O(1)
     assert rep["global_rel"] < 1e-2 and rep["cos"] > 1 - 1e-3, rep
+
+
+def test_decoder_train_mode_gradients_with_the_kernels_own_dropout_masks(monkeypatch):
+    """Train mode of the decoder stack: the keep masks of the embedding dropout and of the four dropouts of every layer
+    are read back from the kernels and replayed in the oracle decoder (attention-probability dropout switched off here;
+    its own mask test is test_attention_dropout_fwd_bwd); loss and all decoder gradients against autograd."""
+    from omr_a2s_multimodal_transformer_b200 import ops
+
+    monkeypatch.setattr(ops, "attn_spec_with_dropout", lambda spec, p, seed: spec)
+    m, sd, w2i = build_unimodal(dtype=torch.float32)
+    layers = len(m.decoder.transformer_decoder.layers)
+    x, xl, y_in, y_out = synth.synth_unimodal_batch(3, 64, 128, [20, 12, 7], w2i)
+    with torch.no_grad():
+        mem = m.encode(x.to(DEV))  # eval-mode memory: only the decoder is under test
+    m.decoder.train()
+    calls = []
+    real = ops.dropout
+
+    def spy(t, p, seed, channelwise=False, inplace=False):
+        if len(calls) < 1 + 4 * layers:  # forward calls come first: embedding, then (a, cc, hmid, f) per layer
+            calls.append((p, seed, tuple(t.shape)))
+        return real(t, p, seed, channelwise=channelwise, inplace=inplace)
+
+    monkeypatch.setattr(ops, "dropout", spy)
+    m.zero_grad(set_to_none=True)
+    loss = m.decoder.loss(tgt=y_in.to(DEV), memory=mem, memory_len=xl.to(DEV), targets=y_out.to(DEV))
+    loss.backward()
+    assert len(calls) == 1 + 4 * layers
+    masks = [real(torch.ones(shape, device=DEV), p, seed).double().cpu() for p, seed, shape in calls]
+    assert all(abs(float((k > 0).double().mean()) - 0.9) < 0.03 for k in masks)
+
+    def drop(layer, slot, t):
+        k = masks[0] if layer < 0 else masks[1 + 4 * layer + (slot - 1)]
+        return t * k.reshape(t.shape).to(t.dtype)
+
+    mem64 = mem.double().cpu()
+
+    def oracle_loss(s):
+        return restate.ce_loss(restate.decoder_forward(s, "decoder.", y_in, mem64, xl, drop=drop), y_out)
+
+    ref_loss, ref_g = oracle_grads(oracle_loss, {k: v.double() for k, v in sd.items()})
+    assert abs(float(loss) - ref_loss) < 1e-4 * max(1.0, abs(ref_loss))
+    dec_g = {k: v for k, v in ref_g.items() if k.startswith("decoder.")}
+    rep = grad_report(m, dec_g)
+    assert not rep["missing"], rep
+    assert rep["global_rel"] < 2e-4 and rep["cos"] > 1 - 1e-6, rep
