@@ -14,6 +14,7 @@ state-dict keys and output semantics):
 """
 from __future__ import annotations
 
+import os
 import random
 from typing import Callable, List, Optional, Tuple, Union
 
@@ -33,7 +34,11 @@ Tape = Optional[List[Callable[[torch.Tensor], Optional[torch.Tensor]]]]
 class _Ctx:
     """Per-call execution context: compute dtype, weight cache, backward tape, training flags."""
 
-    def __init__(self, dtype: torch.dtype, cache: WeightCache, tape: Tape, training: bool, dropout: "DropoutPlan"):
+    # backward-time state shared by the closures of one encoder pass (set by _EncoderFn.backward): ``side`` = stream for
+    # the work nothing later in the chain reads (weight / bias gradients), ``keep`` = tensors that work reads
+    def __init__(self, dtype: torch.dtype, cache: WeightCache, tape: Tape, training: bool, dropout: "DropoutPlan",
+                 bw: Optional[dict] = None):
+        self.bw = bw if bw is not None else {"side": None, "keep": []}
         self.dtype, self.cache, self.tape, self.training, self.dropout = dtype, cache, tape, training, dropout
 
 
@@ -53,6 +58,20 @@ class DropoutPlan:
 
 
 FUSE_RELU_BWD = True  # tests flip this to compare against the unfused relu_bwd / dropout-backward kernels
+
+
+def _off_chain(c: "_Ctx", fn, *tensors) -> None:
+    """backward only: run fn() -- a weight / bias gradient, which nothing later in the chain reads -- on the side stream
+    of this encoder pass, ordered after everything queued so far; ``tensors`` (its inputs) stay alive until the join in
+    ``_EncoderFn.backward``.  Without a side stream fn() simply runs in place."""
+    side = c.bw["side"]
+    if side is None:
+        fn()
+        return
+    c.bw["keep"].extend(tensors)
+    side.wait_event(torch.cuda.current_stream(side.device).record_event())
+    with torch.cuda.stream(side):
+        fn()
 
 
 class _Act:
@@ -108,7 +127,8 @@ def _conv_step(x: torch.Tensor, cp: ConvParams, stride: Tuple[int, int], relu: b
             if relu and not (y_act is not None and y_act.premasked):
                 dz = ops.relu_bwd(y, dy, inplace=True)
             if cp.weight.requires_grad:
-                ops.conv3x3_wgrad(x, dz, grad_buf(cp.weight), grad_buf(cp.bias), stride, accumulate=True)
+                gw, gb = grad_buf(cp.weight), grad_buf(cp.bias)
+                _off_chain(c, lambda: ops.conv3x3_wgrad(x, dz, gw, gb, stride, accumulate=True), x, dz)
             if not need_dx:
                 return None
             wt = c.cache.get(cp.weight, "convT", c.dtype)
@@ -138,7 +158,8 @@ def _dw_step(x: torch.Tensor, cp: ConvParams, c: _Ctx) -> torch.Tensor:
 
         def bwd(dy: torch.Tensor) -> torch.Tensor:
             if cp.weight.requires_grad:
-                ops.dwconv3x3_wgrad(x, dy, grad_buf(cp.weight), grad_buf(cp.bias), accumulate=True)
+                gw, gb = grad_buf(cp.weight), grad_buf(cp.bias)
+                _off_chain(c, lambda: ops.dwconv3x3_wgrad(x, dy, gw, gb, accumulate=True), x, dy)
             return ops.dwconv3x3_dgrad(dy, wp)
 
         c.tape.append(bwd)
@@ -158,7 +179,8 @@ def _pw_step(x: torch.Tensor, cp: ConvParams, relu: bool, c: _Ctx) -> torch.Tens
             if relu:
                 dz = ops.relu_bwd(y2, dz, inplace=True)
             if cp.weight.requires_grad:
-                ops.linear_wgrad(x2, dz, grad_buf(cp.weight).view(co, ci), grad_buf(cp.bias), accumulate=True)
+                gw, gb = grad_buf(cp.weight).view(co, ci), grad_buf(cp.bias)
+                _off_chain(c, lambda: ops.linear_wgrad(x2, dz, gw, gb, accumulate=True), x2, dz)
             return ops.linear_dgrad(dz, wm).view(n, h, w, ci)
 
         c.tape.append(bwd)
@@ -258,8 +280,10 @@ class _EncoderFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x_nhwc: torch.Tensor, enc: "Encoder", dtype: torch.dtype, training: bool, *params):
         tape: List = []
-        y = enc._run(x_nhwc, dtype, tape, training)
+        bw = {"side": None, "keep": []}
+        y = enc._run(x_nhwc, dtype, tape, training, bw)
         ctx.tape = tape
+        ctx.bw = bw
         ctx.enc = enc
         return y
 
@@ -269,9 +293,20 @@ class _EncoderFn(torch.autograd.Function):
         if tape is None:
             raise RuntimeError("encoder backward called twice (activations are released after the first pass)")
         g: Optional[torch.Tensor] = dy.contiguous().clone()
+        # the data-gradient chain stays on this stream; the weight gradients (about as much kernel time again) go to a
+        # side stream and fill the SMs the chain leaves idle (OMR_OVERLAP_ENCODER_WGRAD=0: one stream)
+        side = ctx.enc._wgrad_stream(dy.device)
+        cur = torch.cuda.current_stream(dy.device) if side is not None else None
+        ctx.bw["side"] = side
+        if side is not None:
+            side.wait_stream(cur)
         while tape:
             step = tape.pop()
             g = step(g)
+        if side is not None:
+            cur.wait_stream(side)
+        ctx.bw["side"] = None
+        ctx.bw["keep"].clear()
         cb = getattr(ctx.enc, "_bwd_done_cb", None)
         if cb is not None:  # data-parallel: this encoder's gradient bucket is complete (ddp.py)
             cb()
@@ -311,8 +346,17 @@ class Encoder(nn.Module):
         self._seed_state = (self._seed_state * 6364136223846793005 + 1442695040888963407) & 0xFFFFFFFFFFFFFFFF
         return (self._seed_state >> 17) & 0x7FFFFFFF
 
-    def _run(self, x: torch.Tensor, dtype: torch.dtype, tape: Tape, training: bool) -> torch.Tensor:
-        c = _Ctx(dtype, self._wcache, tape, training, DropoutPlan(self.dropout_p, self._next_seed))
+    def _wgrad_stream(self, device) -> Optional["torch.cuda.Stream"]:
+        if os.environ.get("OMR_OVERLAP_ENCODER_WGRAD", "1") == "0" or torch.device(device).type != "cuda":
+            return None
+        side = getattr(self, "_wg_side", None)
+        if side is None or side.device != torch.device(device):
+            side = torch.cuda.Stream(device=device)
+            self._wg_side = side
+        return side
+
+    def _run(self, x: torch.Tensor, dtype: torch.dtype, tape: Tape, training: bool, bw: Optional[dict] = None) -> torch.Tensor:
+        c = _Ctx(dtype, self._wcache, tape, training, DropoutPlan(self.dropout_p, self._next_seed), bw)
         prev_act: Optional[_Act] = None
         nblk = len(self.conv_blocks)
         for i, blk in enumerate(self.conv_blocks):
@@ -327,7 +371,7 @@ class Encoder(nn.Module):
                 x = ops.add(x, xt) if x.shape == xt.shape else xt
             else:
                 inner: List = []
-                ci = _Ctx(dtype, self._wcache, inner, training, c.dropout)
+                ci = _Ctx(dtype, self._wcache, inner, training, c.dropout, c.bw)
                 xt = blk._run(x, ci)
                 residual = x.shape == xt.shape
 

@@ -340,6 +340,7 @@ def test_decoder_side_stream_overlap_matches_single_stream(monkeypatch, dtype, t
     results = []
     for overlap in ("0", "1"):
         monkeypatch.setenv("OMR_OVERLAP_DECODER", overlap)
+        monkeypatch.setenv("OMR_OVERLAP_ENCODER_WGRAD", overlap)  # the encoders' weight gradients likewise
         m, sd, w2i = build_multimodal(dtype=dtype)
         if train:
             m.train()
