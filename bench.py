@@ -323,13 +323,13 @@ def main():
     # DRAM bytes per launch from the committed `ncu --set full` capture of the same kernel at the same shape, when there is one
     traffic = None
     if top_name == "omr_attn_bwd" and 2337 in top_shape and b == BATCH:
-        traffic = 158.74e6  # dram__bytes_read.sum + dram__bytes_write.sum per launch, profiles/r01_final_ncu_full_top_kernels.txt
+        traffic = 142.2e6  # dram__bytes_read.sum (96.7 MB) + dram__bytes_write.sum (45.5 MB) per launch, profiles/r01_final3_ncu_full_attn_bwd.txt
     roof.update({"kernel": top_name, "launch_shape": [int(v) for v in top_shape if abs(int(v)) < (1 << 20)][-12:],
                  "calls_per_step": top["calls"], "avg_ms": top["ms"] / max(top["calls"], 1),
                  "algorithmic_per_launch": {"flops": top["flops"] / max(top["calls"], 1), "bytes": top["bytes"] / max(top["calls"], 1)},
                  "share_of_step": top["ms"] / tot_ms, "peak_source": pk["src"] + (" (sustained bf16)" if roof["bound"] == "tensor" else ""),
                  "traffic": traffic,
-                 "traffic_source": "profiles/r01_final_ncu_full_top_kernels.txt (ncu --set full, before masked-tile skipping)" if traffic else None})
+                 "traffic_source": "profiles/r01_final3_ncu_full_attn_bwd.txt (ncu --set full of this kernel at this shape, end of round 1)" if traffic else None})
     breakdown = {k: {"ms": round(d["ms"], 3), "calls": d["calls"],
                      "tflops": round(d["flops"] / (d["ms"] * 1e-3) / 1e12, 2) if d["flops"] else None,
                      "gbs": round(d["bytes"] / (d["ms"] * 1e-3) / 1e9, 1) if d["bytes"] else None}
