@@ -75,6 +75,27 @@ class BucketReducer:
         self._issued = 0
 
 
+def token_weight(targets: torch.Tensor, ignore_index: int = 0, group: Optional[dist.ProcessGroup] = None) -> torch.Tensor:
+    """Scale that makes data-parallel training match ONE process on the concatenated batch.
+
+    The reference's loss is the mean over the LOCAL non-pad targets (``CrossEntropyLoss(ignore_index=pad)``, reference
+    model.py:444,588), so averaging gradients over ranks (stock DDP, and this module's default) weights every rank
+    equally even when their token counts differ.  The global-batch mean is ``sum_r n_r * loss_r / sum_r n_r``; with the
+    gradient MEAN over ranks that is ``loss_r * s_r`` with ``s_r = n_r * world / sum_r n_r``, which this returns as a
+    0-dim tensor on the targets' device (one scalar all-reduce, no host synchronisation):
+
+        loss = model.decoder.loss(...)                        # local mean, as the reference computes it
+        (loss * ddp.token_weight(y_out, pad)).backward()      # global-batch semantics
+
+    Without an initialised process group (or world size 1) the scale is exactly 1."""
+    n = (targets != ignore_index).sum().to(torch.float32)
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return torch.ones_like(n)
+    total = n.clone()
+    dist.all_reduce(total, op=dist.ReduceOp.SUM, group=group)
+    return n * dist.get_world_size(group) / total.clamp_min(1.0)
+
+
 class DataParallel:
     """Wraps a ``Transformer`` / ``MultimodalTransformer`` for data-parallel training.
 
@@ -134,6 +155,10 @@ class DataParallel:
         if not self.arena.attached():
             self.arena.reattach()
         self.arena.zero_()
+
+    def token_weight(self, targets: torch.Tensor, ignore_index: int = 0) -> torch.Tensor:
+        """see :func:`token_weight` (global-batch loss semantics; bench.py times the stock-DDP mean of local means)"""
+        return token_weight(targets, ignore_index, self.group)
 
     def sync_gradients(self) -> None:
         if self.reducer is not None:

@@ -81,3 +81,51 @@ def test_grad_arena_layout_and_buckets():
     dp.arena.flat.fill_(1.0)
     dp.zero_grad()
     assert float(dp.arena.flat.abs().sum()) == 0.0
+
+
+def _tw_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from omr_a2s_multimodal_transformer_b200.ddp import token_weight
+
+        # rank 0 holds 5 real targets, rank 1 holds 2 (0 = PAD); per-token losses are known numbers
+        y = torch.tensor([[3, 4, 5, 0], [6, 7, 0, 0]]) if rank == 0 else torch.tensor([[9, 0, 0, 0], [8, 0, 0, 0]])
+        tok_loss = torch.arange(8, dtype=torch.float32).reshape(2, 4) + 10 * rank
+        w = torch.ones(1, requires_grad=True)
+        local = (tok_loss * w)[y != 0].mean()  # what CrossEntropyLoss(ignore_index=0) returns on this rank
+        (local * token_weight(y, 0)).backward()
+        g = w.grad.clone()
+        dist.all_reduce(g)
+        g /= world  # gradient mean over ranks (DataParallel folds 1/world into Adam)
+        q.put((rank, float(g), float(token_weight(y, 0))))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_token_weight_reproduces_the_global_batch_mean():
+    """loss_r * n_r * world / sum(n) averaged over ranks == the mean over ALL non-pad targets of the concatenated batch"""
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_tw_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0, "worker crashed or timed out"
+    res = sorted(q.get(timeout=5) for _ in range(world))
+    vals0 = [0.0, 1.0, 2.0, 4.0, 5.0]  # rank 0: positions with y != 0
+    vals1 = [10.0, 14.0]               # rank 1
+    want = sum(vals0 + vals1) / 7
+    for rank, g, s in res:
+        assert abs(g - want) < 1e-5, (rank, g, want)
+    assert abs(res[0][2] - 5 * 2 / 7) < 1e-6 and abs(res[1][2] - 2 * 2 / 7) < 1e-6
+
+
+def test_token_weight_is_one_without_a_process_group():
+    from omr_a2s_multimodal_transformer_b200.ddp import token_weight
+
+    assert float(token_weight(torch.tensor([[1, 2, 0]]), 0)) == 1.0
