@@ -109,6 +109,7 @@ class _DecoderStackFn(torch.autograd.Function):
         if side is not None:
             torch.cuda.current_stream(dy.device).wait_stream(side)
         state["keep"].clear()
+        ctx.dec._side_keep = []
         cb = getattr(ctx.dec, "_bwd_done_cb", None)
         if cb is not None:  # data-parallel: the decoder's gradient bucket is complete (ddp.py)
             cb()
@@ -172,7 +173,17 @@ class _ProjCEFn(torch.autograd.Function):
         dh = ops.linear_dgrad(dl, wm)
         if dec.out_layer.weight.requires_grad:
             v, d = wm.shape
-            ops.linear_wgrad(h2, dl, grad_buf(dec.out_layer.weight).view(v, d), grad_buf(dec.out_layer.bias))
+            gw, gb = grad_buf(dec.out_layer.weight).view(v, d), grad_buf(dec.out_layer.bias)
+            # the classifier's weight gradient is off the chain too; the decoder stack's backward, which follows whenever
+            # the hidden state needs a gradient, joins the side stream and releases the tensors kept here
+            side = dec._side_stream(dl.device) if ctx.needs_input_grad[0] else None
+            if side is None:
+                ops.linear_wgrad(h2, dl, gw, gb)
+            else:
+                dec._side_keep = [h2, dl]
+                side.wait_event(torch.cuda.current_stream(dl.device).record_event())
+                with torch.cuda.stream(side):
+                    ops.linear_wgrad(h2, dl, gw, gb)
         return dh.view(ctx.shape), None, None, None, None, None, None
 
 

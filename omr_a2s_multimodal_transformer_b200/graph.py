@@ -17,6 +17,7 @@ The eager path (``model.training_step`` under Lightning) is unchanged; this is t
 """
 from __future__ import annotations
 
+import os
 from typing import Callable, List, Optional, Sequence
 
 import torch
@@ -51,11 +52,17 @@ class GraphedTrainStep:
             raise RuntimeError("GraphedTrainStep needs the FusedAdam device step counter (run at least one optimizer step)")
         prev = ops.SEED_OFFSET_DEV
         ops.SEED_OFFSET_DEV = step_dev
+        # The dependent chains (encoders' data path, decoder chain) are captured on a HIGH-priority stream; the off-chain
+        # work forked from them (weight gradients, cross-K/V projections: decoder._side_stream, encoder._wgrad_stream)
+        # runs on default-priority streams, so whenever both have CTAs pending the chain goes first
+        # (OMR_STREAM_PRIORITY=0: capture on a default-priority stream).
+        prio = os.environ.get("OMR_STREAM_PRIORITY", "1") != "0"
+        cap_stream = torch.cuda.Stream(device=dev, priority=-1) if prio else torch.cuda.Stream(device=dev)
         try:
             pool = None
             for _ in range(max(1, variants)):
                 g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g, pool=pool):
+                with torch.cuda.graph(g, pool=pool, stream=cap_stream):
                     loss = self.step_fn(self.static_in)
                 pool = g.pool()
                 self.graphs.append(g)

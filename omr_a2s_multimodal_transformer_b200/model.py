@@ -470,7 +470,9 @@ class MultimodalTransformer(_ModelBase):
         cur = torch.cuda.current_stream(xi.device)
         side = getattr(self, "_enc_side_stream", None)
         if side is None or side.device != xi.device:
-            side = torch.cuda.Stream(device=xi.device)
+            # as important as the stream it forks from (see graph.GraphedTrainStep): high priority
+            prio = os.environ.get("OMR_STREAM_PRIORITY", "1") != "0"
+            side = torch.cuda.Stream(device=xi.device, priority=-1) if prio else torch.cuda.Stream(device=xi.device)
             self._enc_side_stream = side
         side.wait_stream(cur)
         with torch.cuda.stream(side):
