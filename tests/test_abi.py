@@ -49,6 +49,16 @@ def test_no_cpu_fallback_and_clear_errors(lib_built):
         pkg.MultimodalTransformer(32, 64, 32, 64, 12, w2i, i2w, mixer_type="nope")
     with pytest.raises(NotImplementedError):
         pkg.Decoder(31, 12, 31, embedding_dim=256, nhead=8)
+    # the steps either side of the model (staging.py) are device-only as well
+    from omr_a2s_multimodal_transformer_b200 import staging
+
+    sample = (torch.rand(1, 5, 7), 1, torch.tensor([1, 2, 3]))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        staging.ar_batch_preparation_image([sample], device="cpu")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        staging.compute_ed_metrics([["a"]], [["b"]], device="cpu")
+    with pytest.raises(ValueError, match="Vocabularies do not match"):
+        pkg.WeightedGreedyDecoder(pkg.Decoder(31, 12, 31), pkg.Decoder(30, 12, 30))
 
 
 def test_product_never_imports_oracle():
