@@ -275,16 +275,14 @@ class Transformer(_ModelBase):
         return self.decoder(tgt=y_in, memory=self.encode(x), memory_len=xl)
 
     def apply_teacher_forcing(self, y: torch.Tensor) -> torch.Tensor:
-        """reference model.py:152-160 (a per-token host loop there): each non-pad token is replaced with
-        probability p by randint(0, V-1); drawn here with the same Python RNG, vectorised per row."""
-        y_cpu = y.detach().cpu()
-        out = y_cpu.clone()
-        v = len(self.w2i)
-        for i in range(out.size(0)):
-            for j in range(out.size(1)):
-                if random.random() < self.teacher_forcing_prob and int(y_cpu[i, j]) != self.padding_idx:
-                    out[i, j] = random.randint(0, v - 1)
-        return out.to(y.device)
+        """reference model.py:152-160: each non-pad token is replaced with probability ``teacher_forcing_prob`` by
+        ``randint(0, V-1)``.  The reference draws token by token in a B x T Python loop that synchronises with the device
+        at every element; the same distribution is drawn here on the device in one pass (as the reference's own
+        multimodal variant does, model.py:545-559), which also keeps the step capturable in a CUDA graph."""
+        random_mask = torch.rand_like(y, dtype=torch.float) < self.teacher_forcing_prob
+        combined = random_mask & (y != self.padding_idx)
+        random_indices = torch.randint(0, len(self.w2i), y.shape, device=y.device)
+        return torch.where(combined, random_indices, y)
 
     def training_step(self, batch, batch_idx) -> torch.Tensor:
         x, xl, y_in, y_out = batch
