@@ -2,7 +2,7 @@
 """Training throughput of the other BASELINE.json training configurations on one GPU (bench.py times config 3):
   C2  audio-only A2S model, 1x195x808 spectrograms, batch 16, T = 512, bf16
   C5  scaled-up multimodal model: d_model 512, 8 heads, ff 512, 8 layers, max_len 2536, encoders ending in 512
-      channels, image 1x128x1024 + audio 1x195x808 (S = 2337), batch 32, T = 1024, bf16
+      channels, image 1x128x1024 + audio 1x195x808 (S = 2337), batch 32, T = 1024 (c5) or 2535 (c5long), bf16
 Same protocol as bench.py: full step (zero grads, forward, fused projection + cross-entropy, backward, fused Adam) in
 train mode, replayed as a CUDA graph, CUDA-event timing after warm-up.  One JSON line per configuration."""
 import json
@@ -86,7 +86,7 @@ def c2():
     run("C2 audio-only train step (195x808 spectrograms, batch 16, T=512, bf16)", m, batch, build, 3.0 * (19.551e9 + dec), b)
 
 
-def c5():
+def c5(t=1024):
     import omr_a2s_multimodal_transformer_b200 as pkg
     from omr_a2s_multimodal_transformer_b200.decoder import Decoder
     from omr_a2s_multimodal_transformer_b200.encoder import Encoder
@@ -102,7 +102,7 @@ def c5():
     m.decoder = Decoder(len(w2i), MAXLEN, len(w2i), embedding_dim=D, ff_dim=D, nhead=H, num_transformer_layers=L,
                         padding_idx=m.padding_idx)
     m.load_state_dict(synth.synth_state_dict(m.state_dict(), seed=0))
-    b, t = 32, 1024
+    b = 32
 
     def batch():
         return list(bench.make_batch(b, w2i, seed=300, t_len=t))
@@ -124,7 +124,7 @@ def c5():
     d, s, ff, v = D, 2337, D, 6997
     dec = L * (8 * t * d * d + 4 * t * t * d + 4 * t * d * d + 4 * s * d * d + 4 * t * s * d + 4 * t * d * ff) + 2 * t * d * v
     enc = 16.110e9 + 19.551e9  # + the wider last pointwise convolutions (128 -> 512), < 1 % of the encoders
-    run("C5 scaled-up multimodal train step (d_model 512, 8 heads, 8 layers, max_len 2536; batch 32, T=1024, S=2337, bf16)",
+    run(f"C5 scaled-up multimodal train step (d_model 512, 8 heads, 8 layers, max_len 2536; batch 32, T={t}, S=2337, bf16)",
         m, batch, build, 3.0 * (enc + dec), b)
 
 
@@ -133,7 +133,7 @@ if __name__ == "__main__":
     for w in which:
         t0 = time.time()
         try:
-            {"c2": c2, "c5": c5}[w]()
+            {"c2": c2, "c5": c5, "c5long": lambda: c5(2535)}[w]()
         except Exception as e:  # report and go on to the next configuration
             import traceback
 
