@@ -17,9 +17,12 @@ import torch.nn as nn
 try:  # pragma: no cover - depends on the environment
     from lightning.pytorch import LightningModule  # type: ignore
 
-    HAVE_LIGHTNING = True
+    # a partial stand-in registered under that name (e.g. a test stub) does not count as Lightning
+    HAVE_LIGHTNING = all(hasattr(LightningModule, a) for a in ("load_from_checkpoint", "save_hyperparameters", "freeze"))
 except Exception:  # pragma: no cover
     HAVE_LIGHTNING = False
+
+if not HAVE_LIGHTNING:
 
     class LightningModule(nn.Module):  # type: ignore
         def __init__(self) -> None:

@@ -91,3 +91,32 @@ def test_state_dict_surface_matches(ref):
     a = ref.Transformer(128, 1024, 1268, w2i, i2w).state_dict()
     b = pkg.Transformer(128, 1024, 1268, w2i, i2w).state_dict()
     assert list(a.keys()) == list(b.keys()) and sum(v.numel() for k, v in b.items() if not k.endswith(".pe")) == 10128309
+
+
+def test_reference_checkpoint_loads_unchanged(ref, tmp_path):
+    """a Lightning-style checkpoint of the REAL reference model ({state_dict, hyper_parameters = ctor args}) loads into
+    the replacement through load_from_checkpoint, with overrides, exactly as src/test.py:61-62 does"""
+    import inspect
+
+    import omr_a2s_multimodal_transformer_b200 as pkg
+
+    w2i, i2w = synth.tiny_vocab(53)
+    torch.manual_seed(0)
+    for ref_cls, cls, args in [
+        (ref.Transformer, pkg.Transformer, dict(max_input_height=64, max_input_width=128, max_seq_len=20, w2i=w2i, i2w=i2w,
+                                                attn_window=7, teacher_forcing_prob=0.3)),
+        (ref.MultimodalTransformer, pkg.MultimodalTransformer,
+         dict(max_img_height=64, max_img_width=128, max_audio_height=48, max_audio_width=96, max_seq_len=20, w2i=w2i, i2w=i2w,
+              mixer_type="attn_both", attn_window=-1)),
+    ]:
+        # same constructor signature, so the reference's hyper_parameters are valid constructor arguments here
+        assert list(inspect.signature(ref_cls.__init__).parameters) == list(inspect.signature(cls.__init__).parameters)
+        m_ref = ref_cls(**args)
+        path = tmp_path / f"{cls.__name__}.ckpt"
+        torch.save({"state_dict": m_ref.state_dict(), "hyper_parameters": args}, path)
+        m = cls.load_from_checkpoint(str(path), ytest_i2w=i2w)
+        sd_ref, sd = m_ref.state_dict(), m.state_dict()
+        assert list(sd) == list(sd_ref) and all(torch.equal(sd[k], sd_ref[k]) for k in sd)
+        assert m.max_seq_len == 20 and m.attn_window == args["attn_window"] and m.ytest_i2w == i2w
+        m.freeze()
+        assert not m.training and not any(p.requires_grad for p in m.parameters())
