@@ -129,3 +129,65 @@ def test_token_weight_is_one_without_a_process_group():
     from omr_a2s_multimodal_transformer_b200.ddp import token_weight
 
     assert float(token_weight(torch.tensor([[1, 2, 0]]), 0)) == 1.0
+
+
+def _dp_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import omr_a2s_multimodal_transformer_b200 as pkg
+        from oracle import synth
+
+        w2i, i2w = synth.tiny_vocab(31)
+        torch.manual_seed(100 + rank)  # ranks start from DIFFERENT weights: the wrapper must broadcast rank 0's
+        m = pkg.MultimodalTransformer(32, 64, 32, 64, 12, w2i, i2w)
+        dp = pkg.DataParallel(m, broadcast=True)
+        flat = torch.cat([p.detach().reshape(-1) for p in m.parameters()])
+        gathered = [torch.empty_like(flat) for _ in range(world)]
+        dist.all_gather(gathered, flat)
+        same_weights = all(torch.equal(gathered[0], g) for g in gathered)
+        ok = True
+        for step in range(2):
+            dp.zero_grad()
+            # what the backward kernels do: write gradients straight into the arena views
+            for i, p in enumerate(m.parameters()):
+                p.grad.fill_(float(rank + 1) * (1 + (i % 3)) + step)
+            skip_audio = rank == 1 and step == 1  # modality dropped on this rank: that encoder never reports
+            if skip_audio:
+                for p in m.audio_encoder.parameters():
+                    p.grad.zero_()
+            # completion order of the real backward: decoder first, then the encoders (either order)
+            m.decoder._bwd_done_cb()
+            order = [m.image_encoder, m.audio_encoder] if rank == 0 else [m.audio_encoder, m.image_encoder]
+            for enc in order:
+                if skip_audio and enc is m.audio_encoder:
+                    continue
+                enc._bwd_done_cb()
+            dp.sync_gradients()
+            audio = {id(p) for p in m.audio_encoder.parameters()}
+            for i, p in enumerate(m.parameters()):
+                want = sum(float(r + 1) * (1 + (i % 3)) + step for r in range(world))
+                if step == 1 and id(p) in audio:
+                    want -= float(1 + 1) * (1 + (i % 3)) + step
+                ok = ok and bool(torch.all(p.grad == want))
+        q.put((rank, same_weights, ok, dp.grad_scale))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_data_parallel_wrapper_broadcasts_and_reduces_arena_buckets():
+    """DataParallel end to end on the host side: parameter broadcast, gradient arena, bucket callbacks in rank-dependent
+    order, a rank whose audio encoder got no gradient, SUM all-reduce with the mean left to the optimizer (grad_scale)"""
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_dp_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+        assert p.exitcode == 0, "worker crashed or timed out"
+    res = sorted(q.get(timeout=5) for _ in range(world))
+    assert res == [(0, True, True, 0.5), (1, True, True, 0.5)]
