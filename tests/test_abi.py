@@ -83,3 +83,37 @@ def test_grad_arena_and_weight_cache_host_logic():
     assert not arena.attached()
     arena.reattach()
     assert arena.attached()
+
+
+def test_drop_in_module_aliases_accept_the_callers_keyword_arguments(monkeypatch):
+    """alias the reference's module names, then construct the models exactly as
+    src/train.py:80-104 does (keyword arguments) -- no edit to the callers"""
+    import sys
+
+    import omr_a2s_multimodal_transformer_b200 as b200
+    from oracle import synth
+
+    for name, mod in (("src.transformer.model", b200.model), ("src.transformer.encoder", b200.encoder),
+                      ("src.transformer.decoder", b200.decoder)):
+        monkeypatch.setitem(sys.modules, name, mod)
+    for parent in ("src", "src.transformer"):
+        if parent not in sys.modules:
+            import types
+
+            monkeypatch.setitem(sys.modules, parent, types.ModuleType(parent))
+    from src.transformer.model import MultimodalTransformer, Transformer  # noqa: E402  (the callers' import line)
+
+    w2i, i2w = synth.tiny_vocab(31)
+    m = MultimodalTransformer(max_img_height=32, max_img_width=64, max_audio_height=32, max_audio_width=64, max_seq_len=12,
+                              w2i=w2i, i2w=i2w, mixer_type="concat", attn_window=100, teacher_forcing_prob=0.2,
+                              teacher_forcing_modality_prob=0.2)
+    u = Transformer(max_input_height=32, max_input_width=64, max_seq_len=12, w2i=w2i, i2w=i2w, attn_window=100,
+                    teacher_forcing_prob=0.2)
+    assert m.teacher_forcing_modality_prob == 0.2 and u.teacher_forcing_prob == 0.2 and m.decoder.attn_window == 100
+    # the sub-module names the late-fusion scripts and the checkpoint splitter reach into
+    for attr in ("image_encoder", "audio_encoder", "image_pos_2d", "audio_pos_2d", "decoder"):
+        assert hasattr(m, attr)
+    for attr in ("encoder", "pos_2d", "decoder", "w2i", "i2w", "ytest_i2w", "padding_idx", "max_seq_len", "Y", "YHat"):
+        assert hasattr(u, attr)
+    opt = u.configure_optimizers()
+    assert isinstance(opt, torch.optim.Optimizer) and opt.param_groups[0]["lr"] == 1e-4
