@@ -44,6 +44,9 @@ _SIGS = {
     "omr_attn_bwd": "ipqqpqqpqqpqqpqqppqqpqqpqqppiiiiifiippip",
     "omr_add_layernorm_fwd": "ipppppppqifp",
     "omr_layernorm_bwd": "ippppppp" + "qip",
+    "omr_dropout_add_layernorm_fwd": "ipppppppqiffqpp",
+    "omr_layernorm_bwd_dropout": "ippppppppqifqpp",
+    "omr_mask_scale": "ippfqp",
     "omr_ce_fwd": "ipqpqiqppp",
     "omr_ce_reduce": "ppqqpp",
     "omr_ce_bwd": "ipqpppppqiqp",

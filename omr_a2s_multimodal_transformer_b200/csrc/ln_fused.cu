@@ -1,0 +1,214 @@
+// ln_fused.cu -- shorter decoder chain (first item): the element-wise neighbours of the residual
+// LayerNorm folded into it.  OPT-IN (OMR_FUSE_DECODER_LINKS=1, decoder.py); the default path keeps the separate kernels.
+//   forward :  y = LN(dropout(x) + res)            replaces  omr_dropout (in place) + omr_add_layernorm_fwd
+//   backward:  ds = dLN(dy) ; da = dropout'(ds)    replaces  omr_layernorm_bwd + omr_dropout on the gradient
+//   FFN     :  dh = (hdrop > 0 ? scale : 0) * dh   replaces  omr_dropout (in place) + omr_relu_bwd (hdrop = dropout(relu(h)):
+//              its zeros cover the inactive AND the dropped elements, the same trick as the encoders' fused backward)
+// The keep decision is the one of omr_dropout (api.cu: drop_pair_bits on the flat element index, 16-bit uniform,
+// threshold round(p * 65536)), so fused and unfused passes of one step may be mixed freely.
+#include "common.cuh"
+
+namespace {
+
+// ---- the mask function of omr_dropout (api.cu), element-wise form: key = flat index ------------------------------
+__device__ __forceinline__ uint32_t lf_mix32(uint32_t a, uint32_t b) {
+  uint32_t h = a * 0x9E3779B1u ^ (b + 0x7F4A7C15u + (a << 6) + (a >> 2));
+  h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
+  return h;
+}
+__device__ __forceinline__ uint32_t lf_pair_bits(uint32_t seed, long long key) {
+  return lf_mix32(seed ^ (uint32_t)(key >> 33) * 0x632BE5ABu, (uint32_t)(key >> 1));
+}
+// 0 for a dropped element, 1/(1-p) for a kept one
+__device__ __forceinline__ float lf_keep(uint32_t seed, long long key, uint32_t thr, float scale) {
+  const uint32_t u = (lf_pair_bits(seed, key) >> ((uint32_t)(key & 1) * 16)) & 0xFFFFu;
+  return u < thr ? 0.f : scale;
+}
+
+// one warp per row, VPL = D / 32 values per lane (the layout of norm.cu)
+template <typename T, int VPL>
+__global__ void __launch_bounds__(256) drop_add_ln_fwd_kernel(const T* __restrict__ x, const T* __restrict__ res,
+                                                              const float* __restrict__ gamma,
+                                                              const float* __restrict__ beta, T* __restrict__ s_out,
+                                                              T* __restrict__ y, float* __restrict__ stats, long long rows,
+                                                              float eps, uint32_t thr, float scale, uint32_t seed,
+                                                              const int* __restrict__ seed_off) {
+  omr_pdl_enter();
+  if (seed_off) seed += (uint32_t)(*seed_off) * 0x9E3779B9u;
+  constexpr int D = VPL * 32;
+  const int lane = threadIdx.x & 31;
+  long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  float v[VPL];
+  float sum = 0.f;
+#pragma unroll
+  for (int k = 0; k < VPL; ++k) {
+    const long long i = row * D + k * 32 + lane;
+    float a = to_f(x[i]) * lf_keep(seed, i, thr, scale);
+    if (res) a += to_f(res[i]);
+    v[k] = a;
+    sum += a;
+  }
+  const float mean = warp_sum(sum) * (1.f / D);
+  float var = 0.f;
+#pragma unroll
+  for (int k = 0; k < VPL; ++k) {
+    const float d = v[k] - mean;
+    var = fmaf(d, d, var);
+  }
+  const float rstd = rsqrtf(warp_sum(var) * (1.f / D) + eps);
+#pragma unroll
+  for (int k = 0; k < VPL; ++k) {
+    const int d = k * 32 + lane;
+    if (s_out) s_out[row * D + d] = from_f<T>(v[k]);
+    y[row * D + d] = from_f<T>((v[k] - mean) * rstd * gamma[d] + beta[d]);
+  }
+  if (stats && lane == 0) {
+    stats[row * 2] = mean;
+    stats[row * 2 + 1] = rstd;
+  }
+}
+
+template <typename T, int VPL>
+__global__ void __launch_bounds__(256) ln_bwd_drop_kernel(const T* __restrict__ dy, const T* __restrict__ s,
+                                                          const float* __restrict__ stats, const float* __restrict__ gamma,
+                                                          T* __restrict__ ds, T* __restrict__ da, float* __restrict__ dgamma,
+                                                          float* __restrict__ dbeta, long long rows, uint32_t thr,
+                                                          float scale, uint32_t seed, const int* __restrict__ seed_off) {
+  omr_pdl_enter();
+  if (seed_off) seed += (uint32_t)(*seed_off) * 0x9E3779B9u;
+  constexpr int D = VPL * 32;
+  __shared__ float sg[8][D + 1];
+  __shared__ float sb[8][D + 1];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  float gsum[VPL], bsum[VPL], gam[VPL];
+#pragma unroll
+  for (int k = 0; k < VPL; ++k) {
+    gsum[k] = 0.f; bsum[k] = 0.f; gam[k] = gamma[k * 32 + lane];
+  }
+  for (long long row = (long long)blockIdx.x * nw + wid; row < rows; row += (long long)gridDim.x * nw) {
+    const float mean = stats[row * 2], rstd = stats[row * 2 + 1];
+    float xh[VPL], g[VPL];
+    float m1 = 0.f, m2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+      const long long i = row * D + k * 32 + lane;
+      const float gy = to_f(dy[i]);
+      xh[k] = (to_f(s[i]) - mean) * rstd;
+      gsum[k] = fmaf(gy, xh[k], gsum[k]);
+      bsum[k] += gy;
+      g[k] = gy * gam[k];
+      m1 += g[k];
+      m2 = fmaf(g[k], xh[k], m2);
+    }
+    m1 = warp_sum(m1) * (1.f / D);
+    m2 = warp_sum(m2) * (1.f / D);
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+      const long long i = row * D + k * 32 + lane;
+      const float r = rstd * (g[k] - m1 - xh[k] * m2);
+      ds[i] = from_f<T>(r);
+      // the separate kernels round ds to the storage type first and scale that; keep the same value chain
+      da[i] = from_f<T>(round_to<T>(r) * lf_keep(seed, i, thr, scale));
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < VPL; ++k) {
+    sg[wid][k * 32 + lane] = gsum[k];
+    sb[wid][k * 32 + lane] = bsum[k];
+  }
+  __syncthreads();
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    float a = 0.f, b = 0.f;
+    for (int w = 0; w < nw; ++w) { a += sg[w][d]; b += sb[w][d]; }
+    atomicAdd(dgamma + d, a);
+    atomicAdd(dbeta + d, b);
+  }
+}
+
+// dx = (m > 0 ? scale : 0) * dx, four elements per thread
+template <typename T>
+__global__ void __launch_bounds__(256) mask_scale_vec_kernel(T* __restrict__ dx, const T* __restrict__ m, float scale,
+                                                             long long n4) {
+  omr_pdl_enter();
+  for (long long i4 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i4 < n4; i4 += (long long)gridDim.x * blockDim.x) {
+    float g[4], v[4];
+    load4(dx + i4 * 4, g);
+    load4(m + i4 * 4, v);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) g[k] = v[k] > 0.f ? g[k] * scale : 0.f;
+    store4(dx + i4 * 4, g);
+  }
+}
+template <typename T>
+__global__ void mask_scale_kernel(T* __restrict__ dx, const T* __restrict__ m, float scale, long long n) {
+  omr_pdl_enter();
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    dx[i] = to_f(m[i]) > 0.f ? from_f<T>(to_f(dx[i]) * scale) : from_f<T>(0.f);
+}
+
+}  // namespace
+
+#define LF_SWITCH(D, CALL)                                     \
+  switch ((D) / 32) {                                          \
+    case 1: { constexpr int VPL = 1; CALL; } break;            \
+    case 2: { constexpr int VPL = 2; CALL; } break;            \
+    case 4: { constexpr int VPL = 4; CALL; } break;            \
+    case 8: { constexpr int VPL = 8; CALL; } break;            \
+    case 16: { constexpr int VPL = 16; CALL; } break;          \
+    default:                                                   \
+      omr_set_error("layernorm: unsupported width %d (32,64,128,256,512)", (int)(D)); \
+      return OMR_ERR_INVALID;                                  \
+  }
+
+static inline uint32_t lf_thr(float p) { return (uint32_t)(p * 65536.f + 0.5f); }  // as omr_dropout
+
+extern "C" int omr_dropout_add_layernorm_fwd(int dt, const void* x, const void* res, const float* gamma, const float* beta,
+                                             void* s_out, void* y, float* stats, long long rows, int D, float eps, float p,
+                                             long long seed, const int* seed_offset, omr_stream_t stream) {
+  OMR_REQUIRE(D % 32 == 0, "omr_dropout_add_layernorm_fwd: D must be a multiple of 32");
+  OMR_REQUIRE(p >= 0.f && p < 1.f, "omr_dropout_add_layernorm_fwd: p must be in [0,1) (got %f)", p);
+  if (rows <= 0) return OMR_OK;
+  cudaStream_t st = as_stream(stream);
+  const int blocks = (int)cdiv(rows, 8);
+  OMR_DISPATCH_DT(dt, T, LF_SWITCH(D, (OmrLaunch(blocks, 256, 0, st)(drop_add_ln_fwd_kernel<T, VPL>, (const T*)x, (const T*)res,
+                                          gamma, beta, (T*)s_out, (T*)y, stats, rows, eps, lf_thr(p), 1.f / (1.f - p),
+                                          (uint32_t)seed, seed_offset))));
+  OMR_LAUNCHED();
+  return OMR_OK;
+}
+
+extern "C" int omr_layernorm_bwd_dropout(int dt, const void* dy, const void* s, const float* stats, const float* gamma,
+                                         void* ds, void* da, float* dgamma, float* dbeta, long long rows, int D, float p,
+                                         long long seed, const int* seed_offset, omr_stream_t stream) {
+  OMR_REQUIRE(D % 32 == 0, "omr_layernorm_bwd_dropout: D must be a multiple of 32");
+  OMR_REQUIRE(p >= 0.f && p < 1.f, "omr_layernorm_bwd_dropout: p must be in [0,1) (got %f)", p);
+  if (rows <= 0) return OMR_OK;
+  cudaStream_t st = as_stream(stream);
+  long long blocks = cdiv(rows, 8 * 4);
+  if (blocks > 148 * 4) blocks = 148 * 4;
+  if (blocks < 1) blocks = 1;
+  OMR_DISPATCH_DT(dt, T, LF_SWITCH(D, (OmrLaunch((int)blocks, 256, 0, st)(ln_bwd_drop_kernel<T, VPL>, (const T*)dy, (const T*)s,
+                                          stats, gamma, (T*)ds, (T*)da, dgamma, dbeta, rows, lf_thr(p), 1.f / (1.f - p),
+                                          (uint32_t)seed, seed_offset))));
+  OMR_LAUNCHED();
+  return OMR_OK;
+}
+
+extern "C" int omr_mask_scale(int dt, void* dx, const void* mask, float scale, long long n, omr_stream_t stream) {
+  if (n <= 0) return OMR_OK;
+  cudaStream_t st = as_stream(stream);
+  const int esz = dt == OMR_F32 ? 4 : 2;
+  if (n % 4 == 0 && (reinterpret_cast<uintptr_t>(dx) % (4 * esz)) == 0 && (reinterpret_cast<uintptr_t>(mask) % (4 * esz)) == 0) {
+    long long blocks = cdiv(n / 4, 256);
+    if (blocks > 148LL * 16) blocks = 148LL * 16;
+    OMR_DISPATCH_DT(dt, T, (OmrLaunch((unsigned)blocks, 256, 0, st)(mask_scale_vec_kernel<T>, (T*)dx, (const T*)mask, scale, n / 4)));
+    OMR_LAUNCHED();
+    return OMR_OK;
+  }
+  long long blocks = cdiv(n, 256);
+  if (blocks > 148LL * 16) blocks = 148LL * 16;
+  OMR_DISPATCH_DT(dt, T, (OmrLaunch((unsigned)blocks, 256, 0, st)(mask_scale_kernel<T>, (T*)dx, (const T*)mask, scale, n)));
+  OMR_LAUNCHED();
+  return OMR_OK;
+}

@@ -379,6 +379,38 @@ def layernorm_bwd(dy, s, stats, gamma, dgamma, dbeta):
     return ds
 
 
+def dropout_add_layernorm_fwd(x, res, gamma, beta, eps: float, save: bool, p: float, seed: int):
+    """y = LN(dropout(x; p, seed) + res) in one kernel (x is NOT modified); same returns as add_layernorm_fwd"""
+    _chk(x, "dropout_add_layernorm_fwd.x")
+    d = x.shape[-1]
+    rows = x.numel() // d
+    y = torch.empty_like(x)
+    s = torch.empty_like(x) if save else None
+    stats = torch.empty((rows, 2), dtype=torch.float32, device=x.device) if save else None
+    call("omr_dropout_add_layernorm_fwd", dt_code(x.dtype), ptr(x), ptr(res), ptr(gamma), ptr(beta), ptr(s), ptr(y), ptr(stats),
+         rows, d, float(eps), float(p), int(seed), ptr(SEED_OFFSET_DEV), stream_ptr())
+    return y, s, stats
+
+
+def layernorm_bwd_dropout(dy, s, stats, gamma, dgamma, dbeta, p: float, seed: int):
+    """-> (ds, da): ds as layernorm_bwd, da = dropout'(ds; p, seed) = the gradient of the dropped sublayer output"""
+    _chk(dy, "layernorm_bwd_dropout.dy")
+    d = dy.shape[-1]
+    rows = dy.numel() // d
+    ds = torch.empty_like(dy)
+    da = torch.empty_like(dy)
+    call("omr_layernorm_bwd_dropout", dt_code(dy.dtype), ptr(dy), ptr(s), ptr(stats), ptr(gamma), ptr(ds), ptr(da), ptr(dgamma),
+         ptr(dbeta), rows, d, float(p), int(seed), ptr(SEED_OFFSET_DEV), stream_ptr())
+    return ds, da
+
+
+def mask_scale(dx, mask, scale: float):
+    """dx *= (mask > 0 ? scale : 0) in place: backward of ReLU followed by dropout, mask = the dropped ReLU output"""
+    _chk(dx, "mask_scale.dx"), _chk(mask, "mask_scale.mask")
+    call("omr_mask_scale", dt_code(dx.dtype), ptr(dx), ptr(mask), float(scale), dx.numel(), stream_ptr())
+    return dx
+
+
 def ce_fwd(logits2d, targets, ignore_index: int):
     """logits [rows, V] (row stride may exceed V), targets int64 [rows] -> (loss_out fp32 [2] = (mean loss, n_valid), row_lse)"""
     rows, v = logits2d.shape

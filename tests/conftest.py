@@ -10,6 +10,8 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    config.addinivalue_line("markers", "gpu_next: opt-in code paths written without GPU time left in the round; not part of "
+                            "-m gpu until they have run green on a B200 once (python -m pytest tests -m gpu_next)")
     try:  # the torch ops used as fp32 references in the kernel tests must not run in TF32
         import torch
 
@@ -30,7 +32,7 @@ def pytest_collection_modifyitems(config, items):
         return
     skip = pytest.mark.skip(reason="no CUDA device")
     for item in items:
-        if "gpu" in item.keywords:
+        if "gpu" in item.keywords or "gpu_next" in item.keywords:
             item.add_marker(skip)
 
 

@@ -1,0 +1,95 @@
+"""-m gpu_next (NOT part of -m gpu yet): the opt-in fused decoder links of csrc/ln_fused.cu (OMR_FUSE_DECODER_LINKS=1),
+written at the end of round 1 after the GPU budget was spent.  First thing to run in round 2:
+    python -m pytest tests -m gpu_next -q
+Each fused kernel against the pair of kernels it replaces (same seeds -> the same dropout mask), then the whole decoder
+in train mode, fused against unfused."""
+import pytest
+import torch
+
+from oracle import synth
+from tests.helpers import build_unimodal
+
+pytestmark = pytest.mark.gpu_next
+DEV = "cuda:0"
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-6), (torch.bfloat16, 1e-2)])
+@pytest.mark.parametrize("d", [256, 512])
+def test_dropout_add_layernorm_fwd_matches_the_two_kernels(dtype, tol, d):
+    from omr_a2s_multimodal_transformer_b200 import ops
+
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(37, 5, d, generator=g).to(DEV).to(dtype)
+    res = torch.randn(37, 5, d, generator=g).to(DEV).to(dtype)
+    gamma, beta = torch.rand(d, generator=g).to(DEV) + 0.5, torch.randn(d, generator=g).to(DEV)
+    p, seed = 0.1, 12345
+    y1, s1, st1 = ops.dropout_add_layernorm_fwd(x, res, gamma, beta, 1e-5, True, p, seed)
+    xd = ops.dropout(x, p, seed)
+    y0, s0, st0 = ops.add_layernorm_fwd(xd, res, gamma, beta, 1e-5, True)
+    # identical mask: the dropped positions of s - res coincide
+    assert torch.equal((s1.float() - res.float()) == 0, (s0.float() - res.float()) == 0) or dtype == torch.bfloat16
+    assert float((y1.float() - y0.float()).norm() / y0.float().norm()) < tol
+    assert float((s1.float() - s0.float()).norm() / s0.float().norm()) < tol
+    assert torch.allclose(st1, st0, rtol=1e-3, atol=1e-3)
+    keep = float((ops.dropout(torch.ones_like(x), p, seed) > 0).float().mean())
+    assert abs(keep - 0.9) < 0.01
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-6), (torch.bfloat16, 1e-2)])
+def test_layernorm_bwd_dropout_matches_the_two_kernels(dtype, tol):
+    from omr_a2s_multimodal_transformer_b200 import ops
+
+    g = torch.Generator().manual_seed(1)
+    d = 256
+    x = torch.randn(64, 9, d, generator=g).to(DEV).to(dtype)
+    res = torch.randn(64, 9, d, generator=g).to(DEV).to(dtype)
+    gamma, beta = torch.rand(d, generator=g).to(DEV) + 0.5, torch.randn(d, generator=g).to(DEV)
+    dy = torch.randn(64, 9, d, generator=g).to(DEV).to(dtype)
+    p, seed = 0.1, 777
+    _, s, st = ops.add_layernorm_fwd(x, res, gamma, beta, 1e-5, True)
+    dg0, db0, dg1, db1 = (torch.zeros(d, device=DEV) for _ in range(4))
+    ds0 = ops.layernorm_bwd(dy, s, st, gamma, dg0, db0)
+    da0 = ops.dropout(ds0, p, seed)
+    ds1, da1 = ops.layernorm_bwd_dropout(dy, s, st, gamma, dg1, db1, p, seed)
+    assert torch.equal(ds1, ds0)
+    assert torch.equal(da1 == 0, da0 == 0)
+    assert float((da1.float() - da0.float()).norm() / da0.float().norm()) < tol
+    assert torch.allclose(dg1, dg0, rtol=1e-4, atol=1e-4) and torch.allclose(db1, db0, rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("n", [4096, 4097])
+def test_mask_scale_is_relu_and_dropout_backward(dtype, n):
+    from omr_a2s_multimodal_transformer_b200 import ops
+
+    g = torch.Generator().manual_seed(2)
+    h = torch.randn(n, generator=g).to(DEV).to(dtype)
+    hmid = torch.relu(h)
+    p, seed = 0.1, 99
+    hdrop = ops.dropout(hmid.view(1, -1), p, seed).view(-1)
+    dh = torch.randn(n, generator=g).to(DEV).to(dtype)
+    ref = ops.relu_bwd(hmid, ops.dropout(dh.clone().view(1, -1), p, seed).view(-1))
+    got = ops.mask_scale(dh.clone(), hdrop, 1.0 / (1.0 - p))
+    assert torch.equal(got, ref)
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-5), (torch.bfloat16, 2e-2)])
+def test_decoder_train_step_fused_links_match_unfused(monkeypatch, dtype, tol):
+    results = []
+    for fuse in ("0", "1"):
+        monkeypatch.setenv("OMR_FUSE_DECODER_LINKS", fuse)
+        m, sd, w2i = build_unimodal(dtype=dtype)
+        x, xl, y_in, y_out = synth.synth_unimodal_batch(3, 64, 128, [20, 12, 7], w2i)
+        with torch.no_grad():
+            mem = m.encode(x.to(DEV))
+        m.decoder.train()
+        m.zero_grad(set_to_none=True)
+        loss = m.decoder.loss(tgt=y_in.to(DEV), memory=mem, memory_len=xl.to(DEV), targets=y_out.to(DEV))
+        loss.backward()
+        torch.cuda.synchronize()
+        results.append((float(loss), {k: p.grad.detach().double().cpu() for k, p in m.decoder.named_parameters() if p.grad is not None}))
+    (l0, g0), (l1, g1) = results
+    assert abs(l0 - l1) < tol * max(1.0, abs(l0))
+    num = sum(float((g1[k] - g0[k]).pow(2).sum()) for k in g0)
+    den = sum(float(g0[k].pow(2).sum()) for k in g0)
+    assert set(g0) == set(g1) and (num / den) ** 0.5 < tol
