@@ -1,31 +1,16 @@
-"""Symbol / sequence error rates used by ``on_validation_epoch_end`` (reference
-``src/utils/metrics.py:52-88``): token-level Levenshtein distance summed over the set divided by the
-total reference length (Sym-ER, %), and the share of sequences with at least one error (Seq-ER, %).
-Host-side bookkeeping on short token lists; MV2H (music21 / pyMV2H) is outside the hot path."""
+"""Symbol / sequence error rates (reference ``src/utils/metrics.py``): ``compute_metrics(y_true, y_pred)`` with the
+reference's signature, served by the Levenshtein kernel (``staging.compute_ed_metrics`` -> ``omr_levenshtein``, one CTA
+per (truth, prediction) pair).  Like every other entry point of this package it needs a CUDA device; there is no CPU
+implementation here (the tests keep their own CPU restatement).  MV2H (music21 /
+pyMV2H, ``src/utils/metrics.py:91-175``) is outside the accelerated path."""
 from __future__ import annotations
 
-from typing import Dict, List, Sequence
+from typing import Dict, List
 
 
-def edit_distance(a: Sequence, b: Sequence) -> int:
-    if len(a) < len(b):
-        a, b = b, a
-    prev = list(range(len(b) + 1))
-    for i, x in enumerate(a, 1):
-        cur = [i]
-        for j, y in enumerate(b, 1):
-            cur.append(min(prev[j] + 1, cur[j - 1] + 1, prev[j - 1] + (x != y)))
-        prev = cur
-    return prev[-1]
-
-
-def compute_metrics(y_true: List[List[str]], y_pred: List[List[str]], compute_mv2h: bool = False) -> Dict[str, float]:
+def compute_metrics(y_true: List[List[str]], y_pred: List[List[str]], compute_mv2h: bool = False, device=None) -> Dict[str, float]:
     if compute_mv2h:
         raise NotImplementedError("MV2H needs music21/pyMV2H and is not part of the accelerated path")
-    ed_total = length_total = wrong = 0
-    for t, h in zip(y_true, y_pred):
-        ed = edit_distance(t, h)
-        ed_total += ed
-        length_total += len(t)
-        wrong += ed > 0
-    return {"sym-er": 100.0 * ed_total / length_total, "seq-er": 100.0 * wrong / len(y_pred)}
+    from .staging import compute_ed_metrics
+
+    return compute_ed_metrics(y_true, y_pred, device=device)
