@@ -93,3 +93,43 @@ def test_decoder_train_step_fused_links_match_unfused(monkeypatch, dtype, tol):
     num = sum(float((g1[k] - g0[k]).pow(2).sum()) for k in g0)
     den = sum(float(g0[k].pow(2).sum()) for k in g0)
     assert set(g0) == set(g1) and (num / den) ** 0.5 < tol
+
+
+def test_graphed_step_prefetch_matches_plain_loading():
+    """GraphedTrainStep(double_buffer=True): a step replayed on a batch prefetched through the copy stream equals the same
+    step with the batch loaded on the compute stream (eval mode: deterministic up to atomic ordering)"""
+    import omr_a2s_multimodal_transformer_b200 as pkg
+    from tests.helpers import build_multimodal
+
+    finals = []
+    for double in (False, True):
+        m, sd, w2i = build_multimodal(dtype=torch.bfloat16)
+        dp = pkg.DataParallel(m, broadcast=False)
+        opt = m.configure_optimizers()
+        batches = [[t.pin_memory() for t in synth.synth_multimodal_batch(3, (64, 128), (48, 96), [20, 12, 7], w2i, seed=s)]
+                   for s in (1, 2, 3)]
+        dev0 = [t.to(DEV) for t in batches[0]]
+
+        def step(bt):
+            xi, xli, xa, xla, y_in, y_out = bt
+            dp.zero_grad()
+            mem, xl = m._memory(xi, xa, xli, xla, "both")
+            loss = m.decoder.loss(tgt=y_in, memory=mem, memory_len=xl, targets=y_out)
+            loss.backward()
+            dp.sync_gradients()
+            opt.step()
+            return loss
+
+        stepper = pkg.GraphedTrainStep(step, dev0, opt, variants=2, warmup=1, double_buffer=double)
+        losses = []
+        if double:
+            stepper.prefetch(batches[0])
+            for k in range(6):
+                loss = stepper()
+                stepper.prefetch(batches[(k + 1) % 3])
+                losses.append(float(loss))
+        else:
+            for k in range(6):
+                losses.append(float(stepper(batches[k % 3])))
+        finals.append(losses)
+    assert max(abs(a - b) for a, b in zip(*finals)) < 2e-2 * max(finals[0]), finals
