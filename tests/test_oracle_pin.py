@@ -120,3 +120,45 @@ def test_reference_checkpoint_loads_unchanged(ref, tmp_path):
         assert m.max_seq_len == 20 and m.attn_window == args["attn_window"] and m.ytest_i2w == i2w
         m.freeze()
         assert not m.training and not any(p.requires_grad for p in m.parameters())
+
+
+def test_mask_builders_match_reference_over_random_sizes(ref):
+    """window / causal / target-padding / memory-padding / concat masks of the restatement against the reference's own
+    builders (decoder.py:150-254, model.py:644-675) for random sizes, windows and lengths -- and the product's host-side
+    mask builders (kept for API compatibility) against the same"""
+    import random
+
+    import omr_a2s_multimodal_transformer_b200 as pkg
+
+    rnd = random.Random(11)
+    w2i, i2w = synth.tiny_vocab(31)
+    for _ in range(25):
+        t, s, b = rnd.randint(1, 40), rnd.randint(1, 30), rnd.randint(1, 4)
+        window = rnd.choice([-1, 1, 2, 5, 39, 40, 100])
+        rdec = ref.Decoder(31, 64, 31, attn_window=window)
+        pdec = pkg.Decoder(31, 64, 31, attn_window=window)
+        tgt = torch.randint(0, 31, (b, t), generator=torch.Generator().manual_seed(rnd.randint(0, 10 ** 6)))
+        rm, rk = rdec.get_tgt_masks(tgt)
+        om, ok = restate.tgt_masks(tgt, window, torch.float32)
+        pm, pk = pdec.get_tgt_masks(tgt)
+        assert torch.equal(rm, om) and torch.equal(rk, ok) and torch.equal(rm, pm) and torch.equal(rk, pk)
+        if window > 0:
+            wm = ref.Decoder.create_variable_window_mask(t, window)
+            assert torch.equal(wm, restate.window_mask(t, window, torch.float32))
+            assert torch.equal(wm, pkg.Decoder.create_variable_window_mask(t, window))
+        mem = torch.zeros(b, s, 256)
+        lens = torch.tensor([rnd.randint(1, s) for _ in range(b)], dtype=torch.int32)
+        for ml in (None, lens, torch.rand(b, s) < 0.3):
+            r = rdec.get_memory_key_padding_mask(mem, ml)
+            o = restate.memory_key_padding_mask(mem, ml)
+            p = pdec.get_memory_key_padding_mask(mem, ml)
+            assert (r is None and o is None and p is None) or (r.dtype == o.dtype == p.dtype and torch.equal(r, o) and torch.equal(r, p))
+    rmm = ref.MultimodalTransformer(64, 128, 48, 96, 20, w2i, i2w)
+    for _ in range(10):
+        b, li, la = rnd.randint(1, 4), rnd.randint(1, 20), rnd.randint(1, 20)
+        xi, xa = torch.rand(b, li, 256), torch.rand(b, la, 256)
+        xli = torch.tensor([rnd.randint(1, li) for _ in range(b)], dtype=torch.int32)
+        xla = torch.tensor([rnd.randint(1, la) for _ in range(b)], dtype=torch.int32)
+        rx, rl = rmm.mixer_concat(xi, xa, xli, xla)
+        ox, ol = restate.mixer_concat(xi, xa, xli, xla)
+        assert torch.equal(rx, ox) and rl.dtype == ol.dtype and torch.equal(rl, ol)
