@@ -170,7 +170,8 @@ int omr_colsum(int dt, const void* x, long long rows, int N, long long ld, float
 /* Attention-probability dropout (the `dropout` of nn.MultiheadAttention as built at decoder.py:86-95, and of the
  * mixers' nn.MultiheadAttention, model.py:292-297; train mode only): arms the NEXT omr_attn_fwd or omr_attn_bwd call
  * (one-shot), which then computes O = (P o M / (1-p)) V with a keep mask M that is a pure function of (seed [+ the
- * device int32 *seed_off], batch*head, query, key) -- the backward regenerates it from the same arguments.  p in [0,1). */
+ * device int32 *seed_off], batch*head, query, key) -- the backward regenerates it from the same arguments.  p in [0,1).
+ * Threading contract: the armed state is PER CALLING THREAD (thread_local); arm and consume on the same thread.  */
 int omr_attn_next_dropout(float p, unsigned int seed, const int* seed_off);
 int omr_attn_fwd(int dt, const void* q, long long q_bs, long long q_rs, const void* k, long long k_bs, long long k_rs,
                  const void* v, long long v_bs, long long v_rs, void* o, long long o_bs, long long o_rs, float* lse,

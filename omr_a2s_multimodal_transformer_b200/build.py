@@ -71,7 +71,7 @@ def build(verbose: bool = False, force: bool = False) -> str:
         objs = list(ex.map(lambda s: _compile(s, hd, verbose), srcs))
     newest = max(os.path.getmtime(o) for o in objs)
     if (not os.path.exists(LIB)) or os.path.getmtime(LIB) < newest:
-        cmd = [NVCC, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcuda"]
+        cmd = [NVCC, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")

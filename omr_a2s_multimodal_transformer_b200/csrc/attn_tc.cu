@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(192, 2) attn_fwd_tc_kernel(const __grid_consta
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
   uint32_t* live = reinterpret_cast<uint32_t*>(bars + 9);  // [32] bit i: key tile kt0 + i holds a key that is not masked out
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = (int)warp_idx_sync(), lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * BQ, h = blockIdx.y, b = blockIdx.z;
   int kt0, kt1;
   kv_tile_range(a, q0, kt0, kt1);
@@ -222,49 +222,69 @@ __global__ void __launch_bounds__(192, 2) attn_fwd_tc_kernel(const __grid_consta
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = bcast0(*tmem_slot);
   const uint32_t tmem_S = tmem_base, tmem_PV = tmem_base + 128;
 
+  // Producer and MMA issuer run their loops WARP-wide on uniform values and issue under elect_one() (tc_common.cuh): a
+  // lone lane under `if (lane == 0)` made the compiler wrap every tcgen05.mma / TMA in an ELECT / R2UR / BRA.U.ANY waterfall.
   if (warp == 4) {
-    if (lane == 0 && ntiles > 0) {
-      mbar_expect_tx(q_full, TILE);
-      tma_load_3d(sQ, &tmQ, q_full, h * HD, q0, b);
+    if (ntiles > 0) {
+      if (elect_one()) {
+        mbar_expect_tx(q_full, TILE);
+        tma_load_3d(sQ, &tmQ, q_full, h * HD, q0, b);
+      }
       for (int i = 0, n = 0; i < ntiles; ++i) {
-        if (!tile_live(i)) continue;
+        if (!bcast0(tile_live(i) ? 1u : 0u)) continue;
         const int s = n & 1;
         mbar_wait(&kv_empty[s], ((n >> 1) & 1) ^ 1);
-        mbar_expect_tx(&kv_full[s], 2 * TILE);
-        tma_load_3d(sK + s * TILE, &tmK, &kv_full[s], h * HD, (kt0 + i) * BKV, b);
-        tma_load_3d(sV + s * TILE, &tmV, &kv_full[s], h * HD, (kt0 + i) * BKV, b);
+        if (elect_one()) {
+          mbar_expect_tx(&kv_full[s], 2 * TILE);
+          tma_load_3d(sK + s * TILE, &tmK, &kv_full[s], h * HD, (kt0 + i) * BKV, b);
+          tma_load_3d(sV + s * TILE, &tmV, &kv_full[s], h * HD, (kt0 + i) * BKV, b);
+        }
+        __syncwarp();
         ++n;
       }
     }
   } else if (warp == 5) {
-    if (lane == 0 && ntiles > 0) {
+    if (ntiles > 0) {
       constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
       constexpr uint32_t idesc_pv = make_idesc_bf16(128, 64, 0, 1);
       mbar_wait(q_full, 0);
-      const uint32_t q_addr = smem_u32(sQ), p_addr = smem_u32(sP);
+      const uint32_t q_addr = smem_u32(sQ), p_addr = smem_u32(sP), k_base = smem_u32(sK), v_base = smem_u32(sV);
       for (int i = 0, n = 0; i < ntiles; ++i) {
-        if (!tile_live(i)) continue;
+        if (!bcast0(tile_live(i) ? 1u : 0u)) continue;
         const int s = n & 1;
         mbar_wait(&kv_full[s], (n >> 1) & 1);
         tc_fence_after();
-        const uint32_t k_addr = smem_u32(sK + s * TILE), v_addr = smem_u32(sV + s * TILE);
+        const uint32_t k_addr = k_base + (uint32_t)s * TILE, v_addr = v_base + (uint32_t)s * TILE;
+        if (elect_one()) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-          umma_bf16(tmem_S, make_smem_desc(q_addr + j * 32, 16, 1024, 128), make_smem_desc(k_addr + j * 32, 16, 1024, 128), idesc_s,
-                    j > 0 ? 1u : 0u);
-        umma_commit(s_full);
+          for (int j = 0; j < 4; ++j) {
+            if (j > 0)
+              umma_bf16_acc(tmem_S, make_smem_desc(q_addr + j * 32, 16, 1024, 128), make_smem_desc(k_addr + j * 32, 16, 1024, 128), idesc_s);
+            else
+              umma_bf16_new(tmem_S, make_smem_desc(q_addr, 16, 1024, 128), make_smem_desc(k_addr, 16, 1024, 128), idesc_s);
+          }
+          umma_commit(s_full);
+        }
+        __syncwarp();
         mbar_wait(p_full, n & 1);
         ++n;
         tc_fence_after();
+        if (elect_one()) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          umma_bf16(tmem_PV, make_smem_desc(p_addr + (j >> 2) * TILE + (j & 3) * 32, 16, 1024, 128),
-                    make_smem_desc(v_addr + j * 2048, 0, 1024, 128), idesc_pv, j > 0 ? 1u : 0u);
-        umma_commit(pv_full);
-        umma_commit(&kv_empty[s]);
+          for (int j = 0; j < 8; ++j) {
+            if (j > 0)
+              umma_bf16_acc(tmem_PV, make_smem_desc(p_addr + (j >> 2) * TILE + (j & 3) * 32, 16, 1024, 128),
+                            make_smem_desc(v_addr + j * 2048, 0, 1024, 128), idesc_pv);
+            else
+              umma_bf16_new(tmem_PV, make_smem_desc(p_addr, 16, 1024, 128), make_smem_desc(v_addr, 0, 1024, 128), idesc_pv);
+          }
+          umma_commit(pv_full);
+          umma_commit(&kv_empty[s]);
+        }
+        __syncwarp();
       }
     }
   } else {
@@ -497,7 +517,7 @@ __global__ void __launch_bounds__(320, 1) attn_bwd_tc_kernel(const __grid_consta
   uint64_t* mma2_done = bars + 7; // dV, dK, dQ MMAs of this q tile complete
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = (int)warp_idx_sync(), lane = threadIdx.x & 31;
   const int j0 = blockIdx.x * BKV, h = blockIdx.y, b = blockIdx.z;
   int qt0, qt1;
   q_tile_range(a, j0, qt0, qt1);
@@ -529,60 +549,90 @@ __global__ void __launch_bounds__(320, 1) attn_bwd_tc_kernel(const __grid_consta
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = bcast0(*tmem_slot);
   const uint32_t tmem_ST = tmem_base, tmem_DPT = tmem_base + 128, tmem_DV = tmem_base + 256, tmem_DK = tmem_base + 320,
                  tmem_DQ = tmem_base + 384;
 
+  // warp-uniform producer / issuer loops, instructions under elect_one() (see tc_common.cuh)
   if (warp == 8) {
-    if (lane == 0 && ntiles > 0) {
-      mbar_expect_tx(kv_full, 2 * TILE);
-      tma_load_3d(sK, &tmK, kv_full, h * HD, j0, b);
-      tma_load_3d(sV, &tmV, kv_full, h * HD, j0, b);
+    if (ntiles > 0) {
+      if (elect_one()) {
+        mbar_expect_tx(kv_full, 2 * TILE);
+        tma_load_3d(sK, &tmK, kv_full, h * HD, j0, b);
+        tma_load_3d(sV, &tmV, kv_full, h * HD, j0, b);
+      }
       for (int i = 0; i < ntiles; ++i) {
         const int s = i & 1;
         mbar_wait(&qd_empty[s], ((i >> 1) & 1) ^ 1);
-        mbar_expect_tx(&qd_full[s], 2 * TILE);
-        tma_load_3d(sQ + s * TILE, &tmQ, &qd_full[s], h * HD, (qt0 + i) * BQ, b);
-        tma_load_3d(sDO + s * TILE, &tmDO, &qd_full[s], h * HD, (qt0 + i) * BQ, b);
+        if (elect_one()) {
+          mbar_expect_tx(&qd_full[s], 2 * TILE);
+          tma_load_3d(sQ + s * TILE, &tmQ, &qd_full[s], h * HD, (qt0 + i) * BQ, b);
+          tma_load_3d(sDO + s * TILE, &tmDO, &qd_full[s], h * HD, (qt0 + i) * BQ, b);
+        }
+        __syncwarp();
       }
     }
   } else if (warp == 9) {
-    if (lane == 0 && ntiles > 0) {
+    if (ntiles > 0) {
       constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
       constexpr uint32_t idesc_kn = make_idesc_bf16(128, 64, 0, 1);  // A K-major (P^T / dS^T), B MN-major
       constexpr uint32_t idesc_mn = make_idesc_bf16(128, 64, 1, 1);  // A MN-major (dS), B MN-major
       mbar_wait(kv_full, 0);
       const uint32_t k_addr = smem_u32(sK), v_addr = smem_u32(sV), pt_addr = smem_u32(sPT), ds_addr = smem_u32(sDS);
+      const uint32_t q_base = smem_u32(sQ), do_base = smem_u32(sDO);
       for (int i = 0; i < ntiles; ++i) {
         const int s = i & 1;
         mbar_wait(&qd_full[s], (i >> 1) & 1);
         tc_fence_after();
-        const uint32_t q_addr = smem_u32(sQ + s * TILE), do_addr = smem_u32(sDO + s * TILE);
+        const uint32_t q_addr = q_base + (uint32_t)s * TILE, do_addr = do_base + (uint32_t)s * TILE;
+        if (elect_one()) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-          umma_bf16(tmem_ST, make_smem_desc(k_addr + j * 32, 16, 1024, 128), make_smem_desc(q_addr + j * 32, 16, 1024, 128), idesc_s,
-                    j > 0 ? 1u : 0u);
+          for (int j = 0; j < 4; ++j) {
+            if (j > 0)
+              umma_bf16_acc(tmem_ST, make_smem_desc(k_addr + j * 32, 16, 1024, 128), make_smem_desc(q_addr + j * 32, 16, 1024, 128), idesc_s);
+            else
+              umma_bf16_new(tmem_ST, make_smem_desc(k_addr, 16, 1024, 128), make_smem_desc(q_addr, 16, 1024, 128), idesc_s);
+          }
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-          umma_bf16(tmem_DPT, make_smem_desc(v_addr + j * 32, 16, 1024, 128), make_smem_desc(do_addr + j * 32, 16, 1024, 128), idesc_s,
-                    j > 0 ? 1u : 0u);
-        umma_commit(sdp_full);
+          for (int j = 0; j < 4; ++j) {
+            if (j > 0)
+              umma_bf16_acc(tmem_DPT, make_smem_desc(v_addr + j * 32, 16, 1024, 128), make_smem_desc(do_addr + j * 32, 16, 1024, 128), idesc_s);
+            else
+              umma_bf16_new(tmem_DPT, make_smem_desc(v_addr, 16, 1024, 128), make_smem_desc(do_addr, 16, 1024, 128), idesc_s);
+          }
+          umma_commit(sdp_full);
+        }
+        __syncwarp();
         mbar_wait(pds_full, i & 1);
         tc_fence_after();
+        if (elect_one()) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j)  // dV += P^T dO
-          umma_bf16(tmem_DV, make_smem_desc(pt_addr + (j >> 2) * TILE + (j & 3) * 32, 16, 1024, 128),
-                    make_smem_desc(do_addr + j * 2048, 0, 1024, 128), idesc_kn, (i > 0 || j > 0) ? 1u : 0u);
+          for (int j = 0; j < 8; ++j) {  // dV += P^T dO
+            if (j > 0)
+              umma_bf16_acc(tmem_DV, make_smem_desc(pt_addr + (j >> 2) * TILE + (j & 3) * 32, 16, 1024, 128),
+                            make_smem_desc(do_addr + j * 2048, 0, 1024, 128), idesc_kn);
+            else
+              umma_bf16(tmem_DV, make_smem_desc(pt_addr, 16, 1024, 128), make_smem_desc(do_addr, 0, 1024, 128), idesc_kn, i > 0 ? 1u : 0u);
+          }
 #pragma unroll
-        for (int j = 0; j < 8; ++j)  // dK += dS^T Q
-          umma_bf16(tmem_DK, make_smem_desc(ds_addr + (j >> 2) * TILE + (j & 3) * 32, 16, 1024, 128),
-                    make_smem_desc(q_addr + j * 2048, 0, 1024, 128), idesc_kn, (i > 0 || j > 0) ? 1u : 0u);
+          for (int j = 0; j < 8; ++j) {  // dK += dS^T Q
+            if (j > 0)
+              umma_bf16_acc(tmem_DK, make_smem_desc(ds_addr + (j >> 2) * TILE + (j & 3) * 32, 16, 1024, 128),
+                            make_smem_desc(q_addr + j * 2048, 0, 1024, 128), idesc_kn);
+            else
+              umma_bf16(tmem_DK, make_smem_desc(ds_addr, 16, 1024, 128), make_smem_desc(q_addr, 0, 1024, 128), idesc_kn, i > 0 ? 1u : 0u);
+          }
 #pragma unroll
-        for (int j = 0; j < 8; ++j)  // dQ_tile = dS K : A = dS^T tile read MN-major (M = queries: 2 chunks, K = key rows)
-          umma_bf16(tmem_DQ, make_smem_desc(ds_addr + j * 2048, TILE, 1024, 128), make_smem_desc(k_addr + j * 2048, 0, 1024, 128),
-                    idesc_mn, j > 0 ? 1u : 0u);
-        umma_commit(mma2_done);
-        umma_commit(&qd_empty[s]);
+          for (int j = 0; j < 8; ++j) {  // dQ_tile = dS K : A = dS^T tile read MN-major (M = queries: 2 chunks, K = key rows)
+            if (j > 0)
+              umma_bf16_acc(tmem_DQ, make_smem_desc(ds_addr + j * 2048, TILE, 1024, 128), make_smem_desc(k_addr + j * 2048, 0, 1024, 128), idesc_mn);
+            else
+              umma_bf16_new(tmem_DQ, make_smem_desc(ds_addr, TILE, 1024, 128), make_smem_desc(k_addr, 0, 1024, 128), idesc_mn);
+          }
+          umma_commit(mma2_done);
+          umma_commit(&qd_empty[s]);
+        }
+        __syncwarp();
       }
     }
   } else {

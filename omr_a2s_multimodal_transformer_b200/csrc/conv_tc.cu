@@ -15,6 +15,7 @@
 //   stride 2 -> one launch per output parity class (1, 2, 2 or 4 taps each), written with a strided epilogue.
 // Warp roles: 0-3 epilogue (TMEM lanes 32w..32w+31), 4 TMA producer, 5 MMA issuer + TMEM allocator.
 #define OMR_HAVE_TC_CONV 1
+#include <stdio.h>
 #include <stdlib.h>
 
 #include "kernels.h"
@@ -39,7 +40,13 @@ struct ConvTcArgs {
   int OH, OW, osh, osw, oph, opw;  // output tensor extent and the affine map grid -> output pixel
   const bf16* mask;                // optional: out = mask > 0 ? out * mask_scale : 0 (same layout as y)
   float mask_scale;
+  int debug;  // OMR_CONV_DEBUG (diagnostics, results are WRONG when set): 1 = no MMAs, 2 = no TMA loads, 4 = no global stores
+  long long* dbg;  // OMR_CONV_DEBUG & 8: per-tile clock64() stamps of CTA 0 (halo kernel), [role][tile][4]
 };
+#define DBG_STAMP(role, it, k)                                                     \
+  do {                                                                             \
+    if (g.dbg && blockIdx.x == 0 && (it) < 64) g.dbg[((role) * 64 + (it)) * 4 + (k)] = clock64(); \
+  } while (0)
 
 // RB: row bytes (= 2 * min(Cin, 64)); G: (tap, chunk) sub-tiles per pipeline stage
 template <int RB, int G>
@@ -65,7 +72,7 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
   uint64_t* tempty_bar = tfull_bar + 2;      // [2] accumulator drained
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = (int)warp_idx_sync(), lane = threadIdx.x & 31;
   const int chunks = (g.Cin * 2 + RB - 1) / RB;  // 64-channel chunks per tap (1 or 2)
   const int nsub = g.ntaps * chunks;
   const int ngroups = (nsub + G - 1) / G;
@@ -88,24 +95,24 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = bcast0(*tmem_slot);
   const uint32_t a_box_bytes = (uint32_t)(g.TH * g.TW) * RB;
   const uint32_t b_box_bytes = (uint32_t)g.Cout * RB;
 
   if (warp == 4) {
-    if (lane == 0) {
-      uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
-        const int tw = tile % g.tiles_w;
-        const int th = (tile / g.tiles_w) % g.tiles_h;
-        const int n = tile / (g.tiles_w * g.tiles_h);
-        const int oh0 = th * g.TH, ow0 = tw * g.TW;
-        for (int grp = 0; grp < ngroups; ++grp, ++it) {
-          const int s = it % STAGES;
-          const uint32_t ph = (it / STAGES) & 1;
-          mbar_wait(&empty_bar[s], ph ^ 1);
-          const int sub0 = grp * G;
-          const int cnt = (nsub - sub0) < G ? (nsub - sub0) : G;
+    // ---- TMA producer: warp-uniform loop (see tc_common.cuh), one elected lane issues ----
+    int s = 0;
+    uint32_t ph = 1;
+    for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
+      const int tw = tile % g.tiles_w;
+      const int th = (tile / g.tiles_w) % g.tiles_h;
+      const int n = tile / (g.tiles_w * g.tiles_h);
+      const int oh0 = th * g.TH, ow0 = tw * g.TW;
+      for (int grp = 0; grp < ngroups; ++grp) {
+        mbar_wait(&empty_bar[s], ph);
+        const int sub0 = grp * G;
+        const int cnt = (nsub - sub0) < G ? (nsub - sub0) : G;
+        if (elect_one()) {
           mbar_expect_tx(&full_bar[s], (uint32_t)cnt * (a_box_bytes + b_box_bytes));
           uint8_t* stage = smem + s * C::STAGE;
           for (int q = 0; q < cnt; ++q) {
@@ -116,39 +123,55 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
             tma_load_2d(stage + G * C::A_SUB + q * C::B_SUB, &tmW, &full_bar[s], g.widx[tap] * g.Cin + c0, 0);
           }
         }
+        __syncwarp();
+        if (++s == STAGES) {
+          s = 0;
+          ph ^= 1;
+        }
       }
     }
   } else if (warp == 5) {
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(128, g.Cout, 0, 0);
-      uint32_t it = 0, tcount = 0;
-      for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++tcount) {
-        const uint32_t a = tcount & 1, aph = (tcount >> 1) & 1;
-        mbar_wait(&tempty_bar[a], aph ^ 1);
+    // ---- MMA issuer: warp-uniform loop, tcgen05.mma / commit under elect_one() ----
+    const uint32_t idesc = make_idesc_bf16(128, g.Cout, 0, 0);
+    const uint64_t d_hi = make_smem_desc(0, 16, 8 * RB, RB);
+    const uint32_t smem_lo = smem_u32(smem) >> 4;
+    uint32_t tcount = 0;
+    int s = 0;
+    uint32_t ph = 0;
+    for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++tcount) {
+      const uint32_t a = tcount & 1, aph = (tcount >> 1) & 1;
+      mbar_wait(&tempty_bar[a], aph ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + a * (uint32_t)g.Cout;
+      for (int grp = 0; grp < ngroups; ++grp) {
+        mbar_wait(&full_bar[s], ph);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + a * (uint32_t)g.Cout;
-        uint32_t first = 1;
-        for (int grp = 0; grp < ngroups; ++grp, ++it) {
-          const int s = it % STAGES;
-          const uint32_t ph = (it / STAGES) & 1;
-          mbar_wait(&full_bar[s], ph);
-          tc_fence_after();
-          const int sub0 = grp * G;
-          const int cnt = (nsub - sub0) < G ? (nsub - sub0) : G;
-          const uint32_t stage = smem_u32(smem + s * C::STAGE);
-          for (int q = 0; q < cnt; ++q) {
-            const uint32_t a_addr = stage + q * C::A_SUB;
-            const uint32_t b_addr = stage + G * C::A_SUB + q * C::B_SUB;
+        const int sub0 = grp * G;
+        const int cnt = (nsub - sub0) < G ? (nsub - sub0) : G;
+        const uint32_t stage = smem_lo + (uint32_t)s * (C::STAGE >> 4);
+        if (elect_one()) {
 #pragma unroll
-            for (int j = 0; j < RB / 32; ++j) {
-              umma_bf16(d_tmem, make_smem_desc(a_addr + j * 32, 16, 8 * RB, RB), make_smem_desc(b_addr + j * 32, 16, 8 * RB, RB),
-                        idesc, first ? 0u : 1u);
-              first = 0;
+          for (int q = 0; q < G; ++q) {
+            if (q < cnt) {
+              const uint32_t a_addr = stage + q * (C::A_SUB >> 4);
+              const uint32_t b_addr = stage + (G * C::A_SUB + q * C::B_SUB) / 16;
+#pragma unroll
+              for (int j = 0; j < RB / 32; ++j) {
+                if (grp == 0 && q == 0 && j == 0)
+                  umma_bf16_new(d_tmem, d_hi | (uint64_t)(a_addr + 2 * j), d_hi | (uint64_t)(b_addr + 2 * j), idesc);
+                else
+                  umma_bf16_acc(d_tmem, d_hi | (uint64_t)(a_addr + 2 * j), d_hi | (uint64_t)(b_addr + 2 * j), idesc);
+              }
             }
           }
           umma_commit(&empty_bar[s]);
+          if (grp == ngroups - 1) umma_commit(&tfull_bar[a]);
         }
-        umma_commit(&tfull_bar[a]);
+        __syncwarp();
+        if (++s == STAGES) {
+          s = 0;
+          ph ^= 1;
+        }
       }
     }
   } else {
@@ -241,7 +264,7 @@ __global__ void __launch_bounds__(192, 1) conv_halo_kernel(const __grid_constant
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = (int)warp_idx_sync(), lane = threadIdx.x & 31;
   const int TH = g.TH;
   const uint32_t acc_cols = (uint32_t)(TH * g.Cout);  // per accumulator buffer
   const uint32_t need = 2 * acc_cols;
@@ -266,61 +289,97 @@ __global__ void __launch_bounds__(192, 1) conv_halo_kernel(const __grid_constant
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = bcast0(*tmem_slot);
 
   if (warp == 4) {
-    if (lane == 0) {
+    // ---- TMA producer: the whole warp walks the tiles (uniform state), one elected lane issues ----
+    if (elect_one()) {
       mbar_expect_tx(w_full, 9u * (uint32_t)g.Cout * RB);
       for (int t = 0; t < 9; ++t) tma_load_2d(sW + t * wsub, &tmW, w_full, t * g.Cin, 0);
-      uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++it) {
-        const int tw = tile % g.tiles_w;
-        const int th = (tile / g.tiles_w) % g.tiles_h;
-        const int n = tile / (g.tiles_w * g.tiles_h);
-        const int s = it % stages;
-        mbar_wait(&empty_bar[s], ((it / stages) & 1) ^ 1);
-        mbar_expect_tx(&full_bar[s], (uint32_t)(TH + 2) * (uint32_t)pitch * RB);
-        tma_load_4d(sH + s * hsub, &tmX, &full_bar[s], 0, tw * g.TW - 1, th * TH - 1, n);
+    }
+    uint32_t it = 0;
+    int s = 0;
+    uint32_t ph = 1;  // parity to wait for on empty_bar[s]
+    for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++it) {
+      const int tw = tile % g.tiles_w;
+      const int th = (tile / g.tiles_w) % g.tiles_h;
+      const int n = tile / (g.tiles_w * g.tiles_h);
+      DBG_STAMP(0, it, 0);
+      mbar_wait(&empty_bar[s], ph);
+      DBG_STAMP(0, it, 1);
+      if (elect_one()) {
+        if (g.debug & 2) {
+          mbar_arrive(&full_bar[s]);
+        } else {
+          mbar_expect_tx(&full_bar[s], (uint32_t)(TH + 2) * (uint32_t)pitch * RB);
+          tma_load_4d(sH + s * hsub, &tmX, &full_bar[s], 0, tw * g.TW - 1, th * TH - 1, n);
+        }
+      }
+      DBG_STAMP(0, it, 2);
+      if (++s == stages) {
+        s = 0;
+        ph ^= 1;
       }
     }
   } else if (warp == 5) {
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(128, g.Cout, 0, 0);
-      const uint64_t d_hi = make_smem_desc(0, 16, 8 * RB, RB);
-      // per-tap start offsets inside the halo (A) and the weight bank (B), in 16-byte units, held in registers
-      uint32_t ta[9], tb[9];
+    // ---- MMA issuer: warp-uniform loop, tcgen05.mma / commit under elect_one() ----
+    const uint32_t idesc = make_idesc_bf16(128, g.Cout, 0, 0);
+    const uint64_t d_hi = make_smem_desc(0, 16, 8 * RB, RB);
+    // per-tap start offsets inside the halo (A) and the weight bank (B), in 16-byte units
+    uint32_t ta[9], tb[9];
 #pragma unroll
-      for (int t = 0; t < 9; ++t) {
-        const int tt = t < g.ntaps ? t : 0;
-        ta[t] = (uint32_t)(((g.dh[tt] + 1) * pitch + (g.dw[tt] + 1)) * RB) >> 4;
-        tb[t] = (uint32_t)(g.widx[tt] * wsub) >> 4;
-      }
-      const uint32_t row_step = (uint32_t)(pitch * RB) >> 4;
-      mbar_wait(w_full, 0);
-      const uint32_t w_lo = smem_u32(sW) >> 4;
-      uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++it) {
-        const uint32_t a = it & 1, aph = (it >> 1) & 1;
-        mbar_wait(&tempty_bar[a], aph ^ 1);
-        const int s = it % stages;
-        mbar_wait(&full_bar[s], (it / stages) & 1);
-        tc_fence_after();
-        const uint32_t h_lo = smem_u32(sH + s * hsub) >> 4;
-        for (int r = 0; r < TH; ++r) {
-          const uint32_t d_tmem = tmem_base + a * acc_cols + (uint32_t)(r * g.Cout);
-          const uint32_t hr = h_lo + (uint32_t)r * row_step;
+    for (int t = 0; t < 9; ++t) {
+      const int tt = t < g.ntaps ? t : 0;
+      ta[t] = (uint32_t)(((g.dh[tt] + 1) * pitch + (g.dw[tt] + 1)) * RB) >> 4;
+      tb[t] = (uint32_t)(g.widx[tt] * wsub) >> 4;
+    }
+    const uint32_t row_step = (uint32_t)(pitch * RB) >> 4;
+    const uint32_t cout = (uint32_t)g.Cout;
+    const int ntaps = g.ntaps;
+    const bool no_mma = (g.debug & 1) != 0;
+    mbar_wait(w_full, 0);
+    const uint32_t w_lo = smem_u32(sW) >> 4;
+    const uint32_t h_base = smem_u32(sH) >> 4, h_step = (uint32_t)hsub >> 4;
+    uint32_t it = 0;
+    int s = 0;
+    uint32_t ph = 0;  // parity to wait for on full_bar[s]
+    for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++it) {
+      const uint32_t a = it & 1, aph = (it >> 1) & 1;
+      DBG_STAMP(1, it, 0);
+      mbar_wait(&tempty_bar[a], aph ^ 1);
+      DBG_STAMP(1, it, 1);
+      mbar_wait(&full_bar[s], ph);
+      DBG_STAMP(1, it, 2);
+      tc_fence_after();
+      const uint32_t h_lo = h_base + (uint32_t)s * h_step;
+      const uint32_t d0 = tmem_base + a * acc_cols;
+      if (elect_one()) {
+        if (!no_mma) {
+          for (int r = 0; r < TH; ++r) {
+            const uint32_t d_tmem = d0 + (uint32_t)r * cout;
+            const uint32_t hr = h_lo + (uint32_t)r * row_step;
 #pragma unroll
-          for (int t = 0; t < 9; ++t) {
-            if (t < g.ntaps) {
+            for (int t = 0; t < 9; ++t) {
+              if (t < ntaps) {
 #pragma unroll
-              for (int j = 0; j < RB / 32; ++j)
-                umma_bf16(d_tmem, d_hi | (uint64_t)(hr + ta[t] + 2 * j), d_hi | (uint64_t)(w_lo + tb[t] + 2 * j), idesc,
-                          (t > 0 || j > 0) ? 1u : 0u);
+                for (int j = 0; j < RB / 32; ++j) {
+                  if (t > 0 || j > 0)
+                    umma_bf16_acc(d_tmem, d_hi | (uint64_t)(hr + ta[t] + 2 * j), d_hi | (uint64_t)(w_lo + tb[t] + 2 * j), idesc);
+                  else
+                    umma_bf16_new(d_tmem, d_hi | (uint64_t)(hr + ta[t] + 2 * j), d_hi | (uint64_t)(w_lo + tb[t] + 2 * j), idesc);
+                }
+              }
             }
           }
         }
         umma_commit(&empty_bar[s]);
         umma_commit(&tfull_bar[a]);
+      }
+      __syncwarp();
+      DBG_STAMP(1, it, 3);
+      if (++s == stages) {
+        s = 0;
+        ph ^= 1;
       }
     }
   } else {
@@ -332,7 +391,9 @@ __global__ void __launch_bounds__(192, 1) conv_halo_kernel(const __grid_constant
       const int th = (tile / g.tiles_w) % g.tiles_h;
       const int n = tile / (g.tiles_w * g.tiles_h);
       const int gw = tw * g.TW + px;
+      if (threadIdx.x == 0) DBG_STAMP(2, it, 0);
       mbar_wait(&tfull_bar[a], aph);
+      if (threadIdx.x == 0) DBG_STAMP(2, it, 1);
       tc_fence_after();
       for (int r = 0; r < TH; ++r) {
         const int gh = th * TH + r;
@@ -368,14 +429,18 @@ __global__ void __launch_bounds__(192, 1) conv_halo_kernel(const __grid_constant
             o0.x = pack_bf16(f[0], f[1]); o0.y = pack_bf16(f[2], f[3]); o0.z = pack_bf16(f[4], f[5]); o0.w = pack_bf16(f[6], f[7]);
             o1.x = pack_bf16(f[8], f[9]); o1.y = pack_bf16(f[10], f[11]); o1.z = pack_bf16(f[12], f[13]); o1.w = pack_bf16(f[14], f[15]);
             uint4* d4 = reinterpret_cast<uint4*>(dst + c0);
-            d4[0] = o0;
-            d4[1] = o1;
+            if (!(g.debug & 4)) {
+              d4[0] = o0;
+              d4[1] = o1;
+            }
           }
         }
       }
+      if (threadIdx.x == 0) DBG_STAMP(2, it, 2);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[a]);
+      if (threadIdx.x == 0) DBG_STAMP(2, it, 3);
     }
   }
   tc_fence_before();
@@ -384,6 +449,15 @@ __global__ void __launch_bounds__(192, 1) conv_halo_kernel(const __grid_constant
     tc_fence_after();
     tmem_dealloc(tmem_base, tmem_cols);
   }
+}
+
+int g_conv_debug = -1;
+int conv_debug() {
+  if (g_conv_debug < 0) {
+    const char* e = getenv("OMR_CONV_DEBUG");
+    g_conv_debug = e ? atoi(e) : 0;
+  }
+  return g_conv_debug;
 }
 
 int g_halo_mode = -1;
@@ -441,6 +515,13 @@ int run_taps(const void* x, int N, int XH, int XW, int Cin, const void* wpack, i
     }
     if (TH >= 1 && stages >= 2) {
       ConvTcArgs h = a;
+      h.debug = conv_debug();
+      static long long* dbg_dev = nullptr;
+      if (h.debug & 8) {
+        if (!dbg_dev) cudaMalloc(&dbg_dev, 3 * 64 * 4 * sizeof(long long));
+        cudaMemsetAsync(dbg_dev, 0, 3 * 64 * 4 * sizeof(long long), st);
+        h.dbg = dbg_dev;
+      }
       h.TH = TH; h.TW = TW;
       h.tiles_w = (a.GW + TW - 1) / TW;
       h.tiles_h = (a.GH + TH - 1) / TH;
@@ -471,6 +552,23 @@ int run_taps(const void* x, int N, int XH, int XW, int Cin, const void* wpack, i
       else if (rb == 64) OmrLaunch(grid, 192, smem_bytes, st)(conv_halo_kernel<64>, tmX, tmW, h, wsub, hsub, stages);
       else OmrLaunch(grid, 192, smem_bytes, st)(conv_halo_kernel<128>, tmX, tmW, h, wsub, hsub, stages);
       OMR_LAUNCHED();
+      if (h.dbg) {  // diagnostics only: synchronises
+        static int dumps = 0;
+        cudaStreamSynchronize(st);
+        static long long hb[3 * 64 * 4];
+        cudaMemcpy(hb, dbg_dev, sizeof(hb), cudaMemcpyDeviceToHost);
+        if (dumps++ < 3) {
+          const long long t0 = hb[(0 * 64 + 0) * 4 + 0];
+          fprintf(stderr, "[conv_halo dbg] Cin %d Cout %d TH %d TW %d tiles %d grid %d stages %d (clk rel. to producer start)\n", Cin, Cout, TH, TW,
+                  h.num_tiles, grid, stages);
+          for (int it = 0; it < 24; ++it) {
+            fprintf(stderr, " it%2d  TMA wait %6lld got %6lld issued %6lld | MMA wait_te %6lld got %6lld full %6lld commit %6lld | EPI wait %6lld got %6lld done %6lld arr %6lld\n",
+                    it, hb[(0 * 64 + it) * 4 + 0] - t0, hb[(0 * 64 + it) * 4 + 1] - t0, hb[(0 * 64 + it) * 4 + 2] - t0,
+                    hb[(1 * 64 + it) * 4 + 0] - t0, hb[(1 * 64 + it) * 4 + 1] - t0, hb[(1 * 64 + it) * 4 + 2] - t0, hb[(1 * 64 + it) * 4 + 3] - t0,
+                    hb[(2 * 64 + it) * 4 + 0] - t0, hb[(2 * 64 + it) * 4 + 1] - t0, hb[(2 * 64 + it) * 4 + 2] - t0, hb[(2 * 64 + it) * 4 + 3] - t0);
+          }
+        }
+      }
       return OMR_OK;
     }
   }

@@ -93,10 +93,12 @@ extern "C" int omr_conv3x3_wgrad(int dt, const void* x, const void* dy, float* d
   return omr_conv3x3_wgrad_simt(dt, x, dy, dw, N, H, W, Ci, Co, sh, sw, accumulate, st);
 }
 
-// ---- attention-probability dropout: one-shot state consumed by the next omr_attn_fwd / omr_attn_bwd ----
+// ---- attention-probability dropout: one-shot state consumed by the next omr_attn_fwd / omr_attn_bwd OF THE CALLING
+// THREAD (thread_local: autograd runs backward on another thread than forward, and a second model / a validation
+// loop in another thread must not steal or mis-arm the (p, seed) pair; contract stated in include/omr_b200.h) ----
 namespace {
-AttnDrop g_drop_next = {0, nullptr, 0, 1.f};
-AttnDrop g_drop_cur = {0, nullptr, 0, 1.f};
+thread_local AttnDrop g_drop_next = {0, nullptr, 0, 1.f};
+thread_local AttnDrop g_drop_cur = {0, nullptr, 0, 1.f};
 void take_dropout() {
   g_drop_cur = g_drop_next;
   g_drop_next = AttnDrop{0, nullptr, 0, 1.f};

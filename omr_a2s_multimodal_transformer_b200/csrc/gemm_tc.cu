@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(320) gemm_tc_kernel(const __grid_constant__ CU
   uint64_t* accum_bar = empty_bar + STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = (int)warp_idx_sync(), lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
   const int kb_total = (g.K + BK - 1) / BK;
   const int kb_begin = blockIdx.z * g.kb_per_split;
@@ -78,18 +78,19 @@ __global__ void __launch_bounds__(320) gemm_tc_kernel(const __grid_constant__ CU
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = bcast0(*tmem_slot);
 
   if (warp == 8) {
-    if (lane == 0) {
+    {  // TMA producer: warp-uniform loop (see tc_common.cuh), one elected lane issues
       for (int i = 0; i < nkb; ++i) {
         const int s = i % STAGES;
         const uint32_t ph = (i / STAGES) & 1;
         mbar_wait(&empty_bar[s], ph ^ 1);
         uint8_t* a_dst = smem + s * STAGE_BYTES;
         uint8_t* b_dst = a_dst + A_TILE_BYTES;
-        mbar_expect_tx(&full_bar[s], STAGE_BYTES);
         const int k0 = (kb_begin + i) * BK;
+        if (elect_one()) {
+        mbar_expect_tx(&full_bar[s], STAGE_BYTES);
         if (A_MN == 0) {
           tma_load_2d(a_dst, &tmA, &full_bar[s], k0, m0);
         } else {
@@ -102,29 +103,38 @@ __global__ void __launch_bounds__(320) gemm_tc_kernel(const __grid_constant__ CU
 #pragma unroll
           for (int c = 0; c < BN / 64; ++c) tma_load_2d(b_dst + c * 8192, &tmB, &full_bar[s], n0 + c * 64, k0);
         }
+        }
+        __syncwarp();
       }
     }
   } else if (warp == 9) {
-    if (lane == 0) {
+    {  // MMA issuer: warp-uniform loop, tcgen05.mma / commit under elect_one()
       constexpr uint32_t idesc = make_idesc_bf16(BM, BN, A_MN, B_MN);
+      const uint32_t smem0 = smem_u32(smem);
       for (int i = 0; i < nkb; ++i) {
         const int s = i % STAGES;
         const uint32_t ph = (i / STAGES) & 1;
         mbar_wait(&full_bar[s], ph);
         tc_fence_after();
-        const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES);
+        const uint32_t a_addr = smem0 + (uint32_t)s * STAGE_BYTES;
         const uint32_t b_addr = a_addr + A_TILE_BYTES;
+        if (elect_one()) {
 #pragma unroll
         for (int j = 0; j < BK / UMMA_K; ++j) {
           const uint64_t ad = A_MN == 0 ? make_smem_desc(a_addr + j * 32, 16, 1024, 128)
                                         : make_smem_desc(a_addr + j * 2048, 8192, 1024, 128);
           const uint64_t bd = B_MN == 0 ? make_smem_desc(b_addr + j * 32, 16, 1024, 128)
                                         : make_smem_desc(b_addr + j * 2048, 8192, 1024, 128);
-          umma_bf16(tmem_base, ad, bd, idesc, (i > 0 || j > 0) ? 1u : 0u);
+          if (j > 0)
+            umma_bf16_acc(tmem_base, ad, bd, idesc);
+          else
+            umma_bf16(tmem_base, ad, bd, idesc, i > 0 ? 1u : 0u);
         }
         umma_commit(&empty_bar[s]);  // frees the stage once these MMAs have read it
+        if (i == nkb - 1) umma_commit(accum_bar);  // accumulator complete
+        }
+        __syncwarp();
       }
-      umma_commit(accum_bar);  // accumulator complete
     }
   } else {
     // ---- epilogue: 8 warps; warp w owns TMEM lanes / tile rows 32(w&3) .. +31 and column half w>>2 (BN >= 64) ----

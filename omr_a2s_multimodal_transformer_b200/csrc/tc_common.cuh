@@ -17,6 +17,26 @@ namespace tc {
 // ---- addresses ------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// ---- warp-uniform role dispatch ----------------------------------------------------------------------
+// tcgen05.mma / cp.async.bulk.tensor take their operands (descriptors, TMEM addresses, coordinates) from UNIFORM registers.
+// When a single lane runs the issue loop under `if (lane == 0)`, the compiler cannot prove the operands warp-uniform and
+// wraps EVERY instruction in a waterfall (ELECT / R2UR x3 / VOTEU / BRA.U.ANY: ~16 instructions, measured ~65 clk per
+// tcgen05.mma on B200 -- twice the tensor-core time of an M128 x N64 x K16 MMA).  So the producer / issuer loops are run
+// by the WHOLE warp on values that are uniform by construction (kernel parameters, blockIdx, loop counters, shuffled
+// broadcasts), and only the instruction itself sits under elect_one(): the loop state then lives in uniform registers.
+__device__ __forceinline__ uint32_t warp_idx_sync() { return __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0); }
+__device__ __forceinline__ uint32_t bcast0(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
+// one lane of the (fully active) warp; the same lane every time, so tcgen05.commit tracks the MMAs it issued
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---- mbarrier ---------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
@@ -93,6 +113,21 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate));  // no "memory" clobber: operands live in shared memory
                                                               // written by the async proxy; ordering vs. the barriers is
                                                               // kept by their own volatile asm + clobbers
+}
+// the same with the accumulate flag fixed at compile time (no predicate register to set up per instruction)
+__device__ __forceinline__ void umma_bf16_acc(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.eq.b32 p, 0, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc));
+}
+__device__ __forceinline__ void umma_bf16_new(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, 0, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc));
 }
 // mbarrier arrives when all previously issued tcgen05.mma of this thread have completed
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {

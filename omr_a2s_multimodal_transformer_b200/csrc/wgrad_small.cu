@@ -61,7 +61,7 @@ __global__ void __launch_bounds__((WS_WARPS + 1) * 32) wgrad_small_kernel(const 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + g.stages * g.stage_bytes);
   uint64_t* empty_bar = full_bar + g.stages;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = (int)tc::warp_idx_sync(), lane = threadIdx.x & 31;
   constexpr int MT = RBA / 32, NH = RBB / 32;  // 16-channel blocks of dY / X
   constexpr int NCOMBO = MT * NH;              // (co block, ci block) pairs, dealt to the warps
   constexpr int ROWS = NCOMBO;                 // tile rows per warp (8 warps cover NCOMBO blocks x 8 / NCOMBO row groups)
@@ -80,19 +80,27 @@ __global__ void __launch_bounds__((WS_WARPS + 1) * 32) wgrad_small_kernel(const 
   const int my_tiles = g.num_tiles > (int)blockIdx.x ? (g.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
   if (warp == WS_WARPS) {
-    if (lane == 0) {
+    {  // TMA producer: warp-uniform loop, one elected lane issues (see tc_common.cuh)
       const uint32_t tx = (uint32_t)(WS_TH * WS_TW * RBA + (WS_TH + 2) * WS_PITCH * RBB);
+      int s = 0;
+      uint32_t ph = 1;
       for (int i = 0; i < my_tiles; ++i) {
         const int tile = blockIdx.x + i * gridDim.x;
         const int tw = tile % g.tiles_w;
         const int th = (tile / g.tiles_w) % g.tiles_h;
         const int n = tile / (g.tiles_w * g.tiles_h);
-        const int s = i % g.stages;
-        mbar_wait(&empty_bar[s], ((i / g.stages) & 1) ^ 1);
-        mbar_expect_tx(&full_bar[s], tx);
-        uint8_t* stage = smem + s * g.stage_bytes;
-        tma_load_4d(stage, &tmDY, &full_bar[s], 0, tw * WS_TW, th * WS_TH, n);
-        tma_load_4d(stage + g.a_bytes, &tmX, &full_bar[s], 0, tw * WS_TW - 1, th * WS_TH - 1, n);
+        mbar_wait(&empty_bar[s], ph);
+        if (tc::elect_one()) {
+          mbar_expect_tx(&full_bar[s], tx);
+          uint8_t* stage = smem + s * g.stage_bytes;
+          tma_load_4d(stage, &tmDY, &full_bar[s], 0, tw * WS_TW, th * WS_TH, n);
+          tma_load_4d(stage + g.a_bytes, &tmX, &full_bar[s], 0, tw * WS_TW - 1, th * WS_TH - 1, n);
+        }
+        __syncwarp();
+        if (++s == g.stages) {
+          s = 0;
+          ph ^= 1;
+        }
       }
     }
   } else {

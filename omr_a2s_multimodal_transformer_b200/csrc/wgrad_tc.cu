@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant_
   uint32_t* s_aoff = tmem_slot + 2;  // [8]   A start-address offsets per k16 step (16-byte units)
   uint32_t* s_boff = s_aoff + 8;     // [72]  B start-address offsets per (MMA group, k16 step)
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = (int)warp_idx_sync(), lane = threadIdx.x & 31;
   const int group = blockIdx.x / g.ctas_per_group;        // tap group
   const int member = blockIdx.x - group * g.ctas_per_group;
   const int tap0 = group * g.taps_per_cta;
@@ -77,33 +77,40 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant_
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = bcast0(*tmem_slot);
 
   if (warp == 4) {
-    if (lane == 0) {
+    {  // TMA producer: warp-uniform loop (see tc_common.cuh), one elected lane issues
       const uint32_t tx = g.halo ? (uint32_t)(a_bytes + g.chunks_b * (g.TH + 2) * g.pitch * g.rbb)
                                  : (uint32_t)(a_bytes + ntap * g.chunks_b * b_sub);
+      int s = 0;
+      uint32_t ph = 1;
       for (int i = 0; i < ntiles; ++i) {
         const int tile = t_begin + i;
         const int tw = tile % g.tiles_w;
         const int th = (tile / g.tiles_w) % g.tiles_h;
         const int n = tile / (g.tiles_w * g.tiles_h);
         const int oh0 = th * g.TH, ow0 = tw * g.TW;
-        const int s = i % g.stages;
-        const uint32_t ph = (i / g.stages) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1);
-        mbar_expect_tx(&full_bar[s], tx);
-        uint8_t* stage = smem + s * g.stage_bytes;
-        for (int c = 0; c < g.chunks_a; ++c) tma_load_4d(stage + c * a_sub, &tmDY, &full_bar[s], c * 64, ow0, oh0, n);
-        if (g.halo) {
-          for (int c = 0; c < g.chunks_b; ++c) tma_load_4d(stage + a_bytes + c * b_sub, &tmX, &full_bar[s], c * 64, ow0 - 1, oh0 - 1, n);
-        } else {
-          for (int t = 0; t < ntap; ++t) {
-            const int tap = tap0 + t, kh = tap / 3, kw = tap - kh * 3;
-            for (int c = 0; c < g.chunks_b; ++c)
-              tma_load_4d(stage + a_bytes + (t * g.chunks_b + c) * b_sub, &tmX, &full_bar[s], c * 64, ow0 * g.sw + kw - 1,
-                          oh0 * g.sh + kh - 1, n);
+        mbar_wait(&empty_bar[s], ph);
+        if (elect_one()) {
+          mbar_expect_tx(&full_bar[s], tx);
+          uint8_t* stage = smem + s * g.stage_bytes;
+          for (int c = 0; c < g.chunks_a; ++c) tma_load_4d(stage + c * a_sub, &tmDY, &full_bar[s], c * 64, ow0, oh0, n);
+          if (g.halo) {
+            for (int c = 0; c < g.chunks_b; ++c) tma_load_4d(stage + a_bytes + c * b_sub, &tmX, &full_bar[s], c * 64, ow0 - 1, oh0 - 1, n);
+          } else {
+            for (int t = 0; t < ntap; ++t) {
+              const int tap = tap0 + t, kh = tap / 3, kw = tap - kh * 3;
+              for (int c = 0; c < g.chunks_b; ++c)
+                tma_load_4d(stage + a_bytes + (t * g.chunks_b + c) * b_sub, &tmX, &full_bar[s], c * 64, ow0 * g.sw + kw - 1,
+                            oh0 * g.sh + kh - 1, n);
+            }
           }
+        }
+        __syncwarp();
+        if (++s == g.stages) {
+          s = 0;
+          ph ^= 1;
         }
       }
     }
@@ -117,7 +124,7 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant_
     const bool merge = g.halo && g.chunks_b == 1;
     const int ngroup = merge ? ntap / 3 : ntap;
     const int nj = g.KP / 16;  // <= 8
-    if (lane == 0) {
+    {
       const uint32_t nB = merge ? 3 * g.Ci : g.Ci;
       // Co <= 64 -> M = 64: the MN-major A fetch costs one shared-memory wavefront per (k row, M chunk), and with 16/32
       // channel rows most chunks of an M = 128 tile would be aliases of the real one; M = 64 halves that traffic
@@ -126,7 +133,7 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant_
       const uint32_t lbo_b = merge ? (uint32_t)g.rbb : (g.chunks_b > 1 ? (uint32_t)b_sub : 0u);
       const uint64_t a_hi = make_smem_desc(0, lbo_a, 8 * g.rba, g.rba);  // everything but the start address
       const uint64_t b_hi = make_smem_desc(0, lbo_b, 8 * g.rbb, g.rbb);
-      // start-address offsets (16-byte units) kept in registers: A per k16 step, B = per-step part + per-group part
+      // start-address offsets (16-byte units) kept in (uniform) registers: A per k16 step, B = per-step part + per-group part
       const uint32_t a_step = (uint32_t)(16 * g.rba) >> 4;
       uint32_t jb[8];
 #pragma unroll
@@ -144,27 +151,39 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant_
         const int tap = tap0 + (merge ? 3 * m : m), kh = tap / 3, kw = tap - kh * 3;
         gb[m] = g.halo ? (uint32_t)((kh * g.pitch + kw) * g.rbb) >> 4 : (uint32_t)(m * g.chunks_b * b_sub) >> 4;
       }
+      const uint32_t smem_lo = smem_u32(smem) >> 4, stage_step = (uint32_t)g.stage_bytes >> 4;
+      int s = 0;
+      uint32_t ph = 0;
       for (int i = 0; i < ntiles; ++i) {
-        const int s = i % g.stages;
-        const uint32_t ph = (i / g.stages) & 1;
         mbar_wait(&full_bar[s], ph);
         tc_fence_after();
-        const uint32_t a_lo = smem_u32(smem + s * g.stage_bytes) >> 4;
+        const uint32_t a_lo = smem_lo + (uint32_t)s * stage_step;
         const uint32_t b_lo = a_lo + ((uint32_t)a_bytes >> 4);
-        const uint32_t acc0 = i > 0 ? 1u : 0u;
+        if (elect_one()) {
 #pragma unroll
-        for (int m = 0; m < 9; ++m) {
-          if (m < ngroup) {
-            const uint32_t d = tmem_base + (uint32_t)m * nB;
+          for (int m = 0; m < 9; ++m) {
+            if (m < ngroup) {
+              const uint32_t d = tmem_base + (uint32_t)m * nB;
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-              if (j < nj)
-                umma_bf16(d, a_hi | (uint64_t)(a_lo + j * a_step), b_hi | (uint64_t)(b_lo + gb[m] + jb[j]), idesc, j > 0 ? 1u : acc0);
+              for (int j = 0; j < 8; ++j)
+                if (j < nj) {
+                  if (j > 0)
+                    umma_bf16_acc(d, a_hi | (uint64_t)(a_lo + j * a_step), b_hi | (uint64_t)(b_lo + gb[m] + jb[j]), idesc);
+                  else
+                    umma_bf16(d, a_hi | (uint64_t)(a_lo), b_hi | (uint64_t)(b_lo + gb[m] + jb[0]), idesc, i > 0 ? 1u : 0u);
+                }
+            }
           }
+          umma_commit(&empty_bar[s]);
+          if (i == ntiles - 1) umma_commit(accum_bar);
         }
-        umma_commit(&empty_bar[s]);
+        __syncwarp();
+        if (++s == g.stages) {
+          s = 0;
+          ph ^= 1;
+        }
       }
-      umma_commit(accum_bar);
+      if (ntiles == 0 && elect_one()) umma_commit(accum_bar);
     }
   } else if (ntiles > 0) {
     // ---- epilogue: thread = output channel co; add this CTA's partial sums into dW[co, ci, kh, kw] ----

@@ -344,7 +344,7 @@ class Decoder(nn.Module):
             spec_cross = ops.attn_spec_with_dropout(spec_cross, self.dropout_p, self._next_seed())
         # opt-in (round-2 work): the dropouts next to the residual LayerNorms and the FFN's
         # ReLU/dropout backward folded into their neighbours (csrc/ln_fused.cu) -- 7 fewer links per layer in the chain
-        fuse = training and self.dropout_p > 0 and os.environ.get("OMR_FUSE_DECODER_LINKS", "0") == "1"
+        fuse = training and self.dropout_p > 0 and os.environ.get("OMR_FUSE_DECODER_LINKS", "1") != "0"
 
         def add_ln(sub, resid, norm, seed):
             """resid + dropout(sub) -> LayerNorm; returns (y, s, stats)"""
@@ -376,6 +376,7 @@ class Decoder(nn.Module):
         # --- feed-forward block: x3 = LN(x2 + W2 relu(W1 x2)) -------------------------------------------
         x2_2d = x2.view(b * t, d)
         hmid = ops.linear_fwd(x2_2d, w1, L.linear1.bias, relu=True)
+        ops._probe_relu(hmid)
         seed3 = self._next_seed() if training and self.dropout_p > 0 else None
         hdrop = ops.dropout(hmid, self.dropout_p, seed3) if seed3 is not None else hmid
         f = ops.linear_fwd(hdrop, w2, L.linear2.bias).view(b, t, d)

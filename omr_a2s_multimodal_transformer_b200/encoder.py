@@ -116,6 +116,8 @@ def _conv_step(x: torch.Tensor, cp: ConvParams, stride: Tuple[int, int], relu: b
     own ReLU output, filled in by whoever consumes it."""
     wp = c.cache.get(cp.weight, "conv", c.dtype)
     y = ops.conv3x3_fwd(x, wp, cp.bias, stride, relu)
+    if relu:
+        ops._probe_relu(y)
     if c.tape is not None:
         in_hw = (x.shape[1], x.shape[2])
         fuse = FUSE_RELU_BWD and x_act is not None and need_dx
@@ -172,6 +174,8 @@ def _pw_step(x: torch.Tensor, cp: ConvParams, relu: bool, c: _Ctx) -> torch.Tens
     wm = c.cache.get(cp.weight, "mat", c.dtype)
     x2 = x.view(-1, ci)
     y2 = ops.linear_fwd(x2, wm, cp.bias, relu=relu)
+    if relu:
+        ops._probe_relu(y2.view(n, h, w, co))
     if c.tape is not None:
 
         def bwd(dy: torch.Tensor) -> torch.Tensor:

@@ -53,6 +53,16 @@ def add(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None) ->
     return out
 
 
+# Debug probe for the parity tests: when set to a list, every ReLU output of the encoders and of the decoder's feed-forward
+# blocks is appended to it in call order (tests/helpers.py compares these ReLU decisions with the CPU checker's).
+RELU_PROBE: Optional[list] = None
+
+
+def _probe_relu(y: torch.Tensor) -> None:
+    if RELU_PROBE is not None:
+        RELU_PROBE.append(y)
+
+
 # device int32 scalar mixed into every dropout seed on the GPU (None: host seeds only).  A graph-captured training
 # step points this at its step counter so that replays draw fresh masks (graph.GraphedTrainStep).
 SEED_OFFSET_DEV: Optional[torch.Tensor] = None

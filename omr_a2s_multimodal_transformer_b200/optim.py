@@ -74,7 +74,7 @@ class FusedAdam(torch.optim.Optimizer):
                 e.d1 = p.shape[1] if p.dim() > 1 else 1
                 if p.dim() == 2 or (p.dim() == 3 and p.shape[2] == 1):
                     e.d1 = p.shape[1]
-            key.append((e.param, e.grad, tuple(t.data_ptr() for t, _ in sh)))
+            key.append((e.param, e.grad, tuple(t.data_ptr() for t, _ in sh), e.exp_avg, e.exp_avg_sq))
             self._has_shadow.append(bool(sh))
         raw = bytes(entries)
         host = torch.frombuffer(bytearray(raw), dtype=torch.uint8)
@@ -102,7 +102,44 @@ class FusedAdam(torch.optim.Optimizer):
                 sh = []
             if tuple(t.data_ptr() for t, _ in sh) != k[2]:
                 return True
+            st = self.state.get(p)
+            if st is None or "exp_avg" not in st or st["exp_avg"].data_ptr() != k[3] or st["exp_avg_sq"].data_ptr() != k[4]:
+                return True  # load_state_dict() replaced the moment tensors: the kernel must not keep the old pointers
         return False
+
+    # ---- checkpointing: same layout as torch.optim.Adam (per-parameter ``step``, ``exp_avg``, ``exp_avg_sq``) -------------
+    def state_dict(self):
+        """The Adam step lives on the device (``_step_dev``, shared by all parameters); it is written into every
+        parameter's ``state["step"]`` here so that a checkpoint carries it exactly like torch.optim.Adam's (one host
+        read at checkpoint time)."""
+        if self._step_dev is not None:
+            t = float(self._step_dev.item())
+            for p in self._params():
+                st = self.state.get(p)
+                if st is not None and "exp_avg" in st:
+                    st["step"] = torch.tensor(t, dtype=torch.float32)
+        return super().state_dict()
+
+    def load_state_dict(self, state_dict) -> None:
+        """Restores the moments AND the bias-correction step (from this class or from a torch.optim.Adam checkpoint), and
+        drops the pointer table so that the next step() binds the loaded moment tensors."""
+        super().load_state_dict(state_dict)
+        steps = [float(st["step"]) for st in self.state.values() if "step" in st]
+        ps = [p for p in self._params() if p.requires_grad]
+        if steps and ps:
+            if max(steps) != min(steps):
+                raise RuntimeError("FusedAdam keeps ONE step counter for all parameters; the checkpoint holds several "
+                                   f"({min(steps)} .. {max(steps)})")
+            dev = ps[0].device
+            if self._step_dev is None or self._step_dev.device != dev:
+                self._step_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+            self._step_dev.fill_(int(steps[0]))
+        for p in ps:  # moments must be contiguous fp32 on the parameter's device (the kernel reads raw pointers)
+            st = self.state.get(p)
+            if st is not None and "exp_avg" in st:
+                for k in ("exp_avg", "exp_avg_sq"):
+                    st[k] = st[k].to(device=p.device, dtype=p.dtype).contiguous()
+        self._table = None
 
     @torch.no_grad()
     def step(self, closure=None):

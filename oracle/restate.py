@@ -23,6 +23,15 @@ IN_EPS = 1e-3  # src/transformer/encoder.py:153
 LN_EPS = 1e-5  # torch nn.TransformerDecoderLayer default (src/transformer/decoder.py:86-95)
 
 
+# Test hook: when set, every ReLU of the path goes through RELU_HOOK(x) instead of F.relu(x) -- the parity tests use it to
+# record pre-activations and to replay another implementation's ReLU decisions (tests/helpers.relu_decisions).
+RELU_HOOK = None
+
+
+def _relu(x: torch.Tensor) -> torch.Tensor:
+    return F.relu(x) if RELU_HOOK is None else RELU_HOOK(x)
+
+
 def _p(sd: SD, key: str, dtype: torch.dtype) -> torch.Tensor:
     return sd[key].to(dtype)
 
@@ -44,10 +53,10 @@ def conv_block(sd: SD, pre: str, x: torch.Tensor, stride: Tuple[int, int], drop=
     MixDropout slots (after the ReLUs of conv1, conv2, conv3); None = eval mode."""
     dt = x.dtype
     drop = drop or (lambda slot, t: t)
-    x = drop(1, F.relu(F.conv2d(x, _p(sd, pre + "conv1.weight", dt), _p(sd, pre + "conv1.bias", dt), padding=1)))
-    x = drop(2, F.relu(F.conv2d(x, _p(sd, pre + "conv2.weight", dt), _p(sd, pre + "conv2.bias", dt), padding=1)))
+    x = drop(1, _relu(F.conv2d(x, _p(sd, pre + "conv1.weight", dt), _p(sd, pre + "conv1.bias", dt), padding=1)))
+    x = drop(2, _relu(F.conv2d(x, _p(sd, pre + "conv2.weight", dt), _p(sd, pre + "conv2.bias", dt), padding=1)))
     x = instance_norm(x)
-    x = drop(3, F.relu(F.conv2d(x, _p(sd, pre + "conv3.weight", dt), _p(sd, pre + "conv3.bias", dt), padding=1, stride=stride)))
+    x = drop(3, _relu(F.conv2d(x, _p(sd, pre + "conv3.weight", dt), _p(sd, pre + "conv3.bias", dt), padding=1, stride=stride)))
     return x
 
 
@@ -63,8 +72,8 @@ def depth_sep_conv(sd: SD, pre: str, x: torch.Tensor) -> torch.Tensor:
 def dsc_block(sd: SD, pre: str, x: torch.Tensor, drop=None) -> torch.Tensor:
     """DSCBlock.forward (ReLU after conv1/conv2 only): encoder.py:218-238; ``drop`` as in conv_block."""
     drop = drop or (lambda slot, t: t)
-    x = drop(1, F.relu(depth_sep_conv(sd, pre + "conv1.", x)))
-    x = drop(2, F.relu(depth_sep_conv(sd, pre + "conv2.", x)))
+    x = drop(1, _relu(depth_sep_conv(sd, pre + "conv1.", x)))
+    x = drop(2, _relu(depth_sep_conv(sd, pre + "conv2.", x)))
     x = instance_norm(x)
     x = drop(3, depth_sep_conv(sd, pre + "conv3.", x))
     return x
@@ -213,7 +222,7 @@ def decoder_layer(sd: SD, pre: str, x, memory, tmask, tkpm, mkpm, nhead: int, dr
 
     x = ln(x + drop(1, mha(sd, pre + "self_attn.", x, x, x, nhead, attn_mask=tmask, key_padding_mask=tkpm)), "norm1")
     x = ln(x + drop(2, mha(sd, pre + "multihead_attn.", x, memory, memory, nhead, key_padding_mask=mkpm)), "norm2")
-    h = drop(3, F.relu(F.linear(x, _p(sd, pre + "linear1.weight", dt), _p(sd, pre + "linear1.bias", dt))))
+    h = drop(3, _relu(F.linear(x, _p(sd, pre + "linear1.weight", dt), _p(sd, pre + "linear1.bias", dt))))
     h = F.linear(h, _p(sd, pre + "linear2.weight", dt), _p(sd, pre + "linear2.bias", dt))
     return ln(x + drop(4, h), "norm3")
 

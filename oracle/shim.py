@@ -20,7 +20,18 @@ from types import SimpleNamespace
 import torch
 import torch.nn as nn
 
-REFERENCE_ROOT = os.environ.get("OMR_REFERENCE_ROOT", "/root/reference")
+def _find_reference_root() -> str:
+    """the read-only reference checkout in the build container, else the git-ignored verbatim copy that
+    oracle/build_ref.py makes under oracle/_ref (the only form in which the reference reaches the GPU box)"""
+    cands = [os.environ.get("OMR_REFERENCE_ROOT"), "/root/reference",
+             os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")]
+    for c in cands:
+        if c and os.path.isfile(os.path.join(c, "src", "transformer", "model.py")):
+            return c
+    return cands[1]
+
+
+REFERENCE_ROOT = _find_reference_root()
 
 
 def reference_available() -> bool:

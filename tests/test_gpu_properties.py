@@ -1,4 +1,4 @@
-"""-m gpu_next (NOT part of -m gpu yet; written after the round's GPU budget was spent): size-independent properties of
+"""-m gpu: size-independent properties of
 the CUDA path at BASELINE.json's real per-sample shapes (image 1x128x1024, audio 1x195x808, grandstaff vocabulary), where
 the CPU oracle is too slow to serve as the checker:
   * batch independence  -- a sample's logits do not depend on its batch mates (InstanceNorm per sample, LayerNorm per
@@ -12,7 +12,7 @@ import torch
 
 from oracle import synth
 
-pytestmark = pytest.mark.gpu_next
+pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
 
