@@ -75,16 +75,26 @@ int omr_pack_dw_weight(int dt, const float* w, void* out, int C, omr_stream_t st
 
 /* ---- convolutional encoders (nn.Conv2d call sites encoder.py:132-150, 56-70) ---------- */
 /* y[N,Ho,Wo,Co] = act(conv3x3(x[N,H,W,Ci], w[Co,3,3,Ci], pad 1, stride (sh,sw)) + bias)
- * Ho = ceil(H/sh), Wo = ceil(W/sw); relu != 0 fuses the activation. */
+ * Ho = ceil(H/sh), Wo = ceil(W/sw); relu != 0 fuses the activation.
+ * in_sums (may be NULL): fp64 [N][Co][2] RECEIVES (sum y, sum y^2) over the pixels of every (sample, channel) of the STORED
+ * output -- the statistics of the nn.InstanceNorm2d that follows conv2 (encoder.py:151-156,174); pass them to
+ * omr_instnorm_fwd(..., sums_ready = 1).  Accumulated in the convolution's epilogue (bf16, Co <= 64), else by one
+ * extra pass over y. */
 int omr_conv3x3_fwd(int dt, const void* x, const void* w, const float* bias, void* y, int N, int H, int W, int Ci,
-                    int Co, int sh, int sw, int relu, omr_stream_t stream);
+                    int Co, int sh, int sw, int relu, double* in_sums, omr_stream_t stream);
 /* dx[N,H,W,Ci] = conv3x3 data gradient of dy[N,Ho,Wo,Co].
  * mask (same shape/type as dx, may be NULL): fused backward of the ReLU (and dropout) that PRODUCED this conv's
  * input: dx = mask > 0 ? dx * mask_scale : 0, with mask = the conv's own forward input (a ReLU output, possibly
  * passed through dropout, whose zeros cover both the inactive and the dropped elements) and mask_scale the
- * dropout's 1/(1-p) (1 without dropout).  Saves the separate relu_bwd / dropout-backward passes. */
+ * dropout's 1/(1-p) (1 without dropout).  Saves the separate relu_bwd / dropout-backward passes.
+ * colsum (may be NULL): fp32 [Ci] += column sums of the stored dx = the BIAS gradient of the convolution whose ReLU
+ * output this conv consumed (its omr_conv3x3_wgrad is then called with db = NULL).
+ * in_x + in_bsums (may be NULL; not together with colsum): dx is the gradient of an InstanceNorm OUTPUT, in_x that
+ * norm's input (laid out like dx); fp64 in_bsums [N][Ci][2] RECEIVES the raw backward sums (sum dx, sum dx * in_x) for
+ * omr_instnorm_bwd(..., sums_ready = 1).  Both are accumulated in the epilogue (bf16, Ci <= 64), else by an extra pass. */
 int omr_conv3x3_dgrad(int dt, const void* dy, const void* w, void* dx, int N, int H, int W, int Ci, int Co, int sh,
-                      int sw, const void* mask, float mask_scale, omr_stream_t stream);
+                      int sw, const void* mask, float mask_scale, float* colsum, const void* in_x, double* in_bsums,
+                      omr_stream_t stream);
 /* dw[Co,Ci,3,3] (fp32, torch layout) and db[Co] (fp32) ; accumulate != 0 adds to dw/db */
 int omr_conv3x3_wgrad(int dt, const void* x, const void* dy, float* dw, float* db, int N, int H, int W, int Ci, int Co,
                       int sh, int sw, int accumulate, omr_stream_t stream);
@@ -99,14 +109,18 @@ int omr_dwconv3x3_wgrad(int dt, const void* x, const void* dy, float* dw, float*
 
 /* nn.InstanceNorm2d(eps, affine=False) (encoder.py:151-156, 210-215) on NHWC.
  * stats[N,C,2] fp32 receives (mean, rstd); ws: fp64 scratch of N*C*2 doubles (the plane sums are
- * combined in double so that E[x^2]-E[x]^2 and the backward's mean subtractions do not cancel). */
+ * combined in double so that E[x^2]-E[x]^2 and the backward's mean subtractions do not cancel).
+ * sums_ready != 0: ws already holds (sum x, sum x^2) per (n, c) (omr_conv3x3_fwd's in_sums): the statistics pass over x is skipped. */
 int omr_instnorm_fwd(int dt, const void* x, void* y, float* stats, double* ws, int N, int HW, int C, float eps,
-                     omr_stream_t stream);
+                     int sums_ready, omr_stream_t stream);
 /* dx from dy, the saved INPUT x and stats; ws: fp64 scratch of N*C*2 doubles.
  * relu_mask != 0: x is a ReLU output (possibly after dropout); the result is additionally multiplied by
- * (x > 0 ? mask_scale : 0), i.e. the backward of that ReLU/dropout is fused (see omr_conv3x3_dgrad). */
+ * (x > 0 ? mask_scale : 0), i.e. the backward of that ReLU/dropout is fused (see omr_conv3x3_dgrad).
+ * sums_ready != 0: ws already holds the RAW sums (sum dy, sum dy * x) per (n, c) (omr_conv3x3_dgrad's in_bsums): the
+ * reduction pass over dy and x is skipped.  colsum (may be NULL): fp32 [C] += column sums of the stored dx (the bias
+ * gradient of the convolution in front of the norm's ReLU). */
 int omr_instnorm_bwd(int dt, const void* dy, const void* x, const float* stats, void* dx, double* ws, int N, int HW,
-                     int C, int relu_mask, float mask_scale, omr_stream_t stream);
+                     int C, int relu_mask, float mask_scale, int sums_ready, float* colsum, omr_stream_t stream);
 
 /* PositionalEncoding2D + flatten/permute + concat (model.py:45-48, 498, 506, 654):
  * out[b, row_off + p, c] = x[b, p, c] + pe[(p / w) * pe_w + (p % w), c]   for p < h*w

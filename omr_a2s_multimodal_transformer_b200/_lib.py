@@ -23,14 +23,14 @@ _SIGS = {
     "omr_dropout": "ippqiqfqipp",
     "omr_pack_conv_weight": "ippiiip",
     "omr_pack_dw_weight": "ippip",
-    "omr_conv3x3_fwd": "ippppiiiiiiiip",
-    "omr_conv3x3_dgrad": "ipppiiiiiiipfp",
+    "omr_conv3x3_fwd": "ippppiiiiiiiipp",
+    "omr_conv3x3_dgrad": "ipppiiiiiiipfpppp",
     "omr_conv3x3_wgrad": "ippppiiiiiiiip",
     "omr_dwconv3x3_fwd": "ippppiiiip",
     "omr_dwconv3x3_dgrad": "ipppiiiip",
     "omr_dwconv3x3_wgrad": "ippppiiiiip",
-    "omr_instnorm_fwd": "ippppiiifp",
-    "omr_instnorm_bwd": "ipppppiiiifp",
+    "omr_instnorm_fwd": "ippppiiifip",
+    "omr_instnorm_bwd": "ipppppiiiifipp",
     "omr_pe2d_add": "ipppiiiiiiip",
     "omr_copy_rows": "ippiiiiip",
     "omr_key_bias_from_lengths": "ppiiiifp",
@@ -152,10 +152,10 @@ def _work(name: str, a) -> tuple:
             return 18.0 * nb * h * w * c, 2.0 * _ESZ[a[0]] * nb * h * w * c
         if name == "omr_instnorm_fwd":
             nb, hw, c = a[5:8]
-            return 0.0, 3.0 * _ESZ[a[0]] * nb * hw * c  # read (stats), read + write (apply)
+            return 0.0, (2.0 if a[9] else 3.0) * _ESZ[a[0]] * nb * hw * c  # read (stats, unless they came with the conv), read + write (apply)
         if name == "omr_instnorm_bwd":
             nb, hw, c = a[6:9]
-            return 0.0, 5.0 * _ESZ[a[0]] * nb * hw * c
+            return 0.0, (3.0 if a[11] else 5.0) * _ESZ[a[0]] * nb * hw * c
         if name in ("omr_relu_bwd", "omr_add"):
             return 0.0, 3.0 * _ESZ[a[0]] * a[4]
         if name == "omr_dropout":

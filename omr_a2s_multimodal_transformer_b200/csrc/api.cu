@@ -27,7 +27,7 @@ bool omr_pdl_enabled() {
 }
 void omr_count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
-extern "C" int omr_abi_version(void) { return 1; }
+extern "C" int omr_abi_version(void) { return 2; }
 extern "C" const char* omr_last_error(void) { return g_err; }
 extern "C" long long omr_launch_count(void) { return g_launches.load(); }
 

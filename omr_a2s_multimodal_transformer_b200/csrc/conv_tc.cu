@@ -2,18 +2,28 @@
 //
 //   D[pixel, co] = sum over taps t, channels c of  X[n, oh*ish + dh_t, ow*isw + dw_t, c] * Wt[co, widx_t, c]
 //
-// * activations are NHWC bf16; the A operand of tap t is fetched by ONE 4-D TMA box per (tap, 64-channel chunk)
-//   whose start coordinate carries the tap shift -- out-of-range coordinates (the zero padding) are filled with
-//   zeros by the TMA unit and strided convolutions use the tensor map's element strides, so no thread ever
-//   computes an im2col address;
+// * activations are NHWC bf16; the A operand of tap t is fetched by 4-D TMA boxes whose start coordinate carries the
+//   tap shift -- out-of-range coordinates (the zero padding) are filled with zeros by the TMA unit and strided
+//   convolutions use the tensor map's element strides, so no thread ever computes an im2col address;
 // * one smem row = one pixel = min(C,64) channels (32/64/128 bytes) in the TMA swizzle of that width, which is
 //   exactly the K-major UMMA operand layout; the weight slice [Cout x chunk] of the tap is the B operand;
-// * persistent CTAs (one per SM) walk the output tiles (128 pixels = TH x TW patch of one image); the fp32
-//   accumulator lives in TMEM and is double buffered, so the epilogue of tile i (bias + ReLU + bf16 NHWC store)
-//   overlaps the TMA/MMA main loop of tile i+1;
-// * the same kernel computes the data gradient: stride 1 -> taps mirrored, weights from the [Ci,3,3,Co] pack;
+// * persistent CTAs (one per SM), each owning a CONTIGUOUS range of output tiles; the fp32 accumulator lives in TMEM and
+//   is double buffered, so the epilogue of tile i overlaps the TMA/MMA main loop of tile i+1;
+// * the same kernels compute the data gradient: stride 1 -> taps mirrored, weights from the [Ci,3,3,Co] pack;
 //   stride 2 -> one launch per output parity class (1, 2, 2 or 4 taps each), written with a strided epilogue.
-// Warp roles: 0-3 epilogue (TMEM lanes 32w..32w+31), 4 TMA producer, 5 MMA issuer + TMEM allocator.
+//
+// Warp roles (320 threads): 0-7 epilogue, 8 TMA producer, 9 MMA issuer + TMEM allocator.  Producer and issuer run their
+// loops warp-wide on uniform values with the instruction under elect_one() (tc_common.cuh).  The epilogue was the
+// bottleneck of the narrow (C = 16 / 32) layers when it had ONE warp per SM sub-partition (measured: ~2100 clk per 512-pixel
+// tile, instruction-latency bound): it now has two warps per sub-partition -- warps w and w + 4 share the TMEM lanes
+// 32 (w & 3) .. + 31 and split a tile's (row, 16-channel chunk) units between them -- batches its TMEM loads, takes the
+// bias from shared memory and does ReLU / masking on packed bf16 pairs.
+//
+// Fused per-channel reductions in the epilogue (MODE, output channels <= 64), accumulated per thread over the CTA's tile
+// range and flushed with one atomic per (warp, channel) when the sample changes:
+//   MODE 1  InstanceNorm statistics of the stored output: (sum y, sum y^2) per (n, c)     [conv2 of a block, forward]
+//   MODE 2  column sums of the stored output per c = bias gradient of the producing layer  [data gradient with fused mask]
+//   MODE 3  InstanceNorm backward sums (sum dy, sum dy * x) per (n, c), x = the norm's input [data gradient of conv3]
 #define OMR_HAVE_TC_CONV 1
 #include <stdio.h>
 #include <stdlib.h>
@@ -26,6 +36,8 @@ namespace {
 using namespace tc;
 
 constexpr int MAX_TAPS = 9;
+constexpr int NTHREADS = 320;
+constexpr int EPI_WARPS = 8, W_TMA = 8, W_MMA = 9;
 
 struct ConvTcArgs {
   bf16* y;
@@ -40,13 +52,174 @@ struct ConvTcArgs {
   int OH, OW, osh, osw, oph, opw;  // output tensor extent and the affine map grid -> output pixel
   const bf16* mask;                // optional: out = mask > 0 ? out * mask_scale : 0 (same layout as y)
   float mask_scale;
-  int debug;  // OMR_CONV_DEBUG (diagnostics, results are WRONG when set): 1 = no MMAs, 2 = no TMA loads, 4 = no global stores
-  long long* dbg;  // OMR_CONV_DEBUG & 8: per-tile clock64() stamps of CTA 0 (halo kernel), [role][tile][4]
+  // fused reductions (see the header): exactly one of them is non-null in MODE 1 / 2 / 3
+  double* in_sums;     // MODE 1: [N][Cout][2] += (sum y, sum y^2)
+  float* colsum;       // MODE 2: [Cout] += sum y
+  const bf16* in_x;    // MODE 3: the InstanceNorm input (same layout as y) ...
+  double* in_bsums;    //         ... and [N][Cout][2] += (sum y, sum y * x)
+  int debug;           // OMR_CONV_DEBUG (diagnostics, results are WRONG when set): 1 = no MMAs, 2 = no TMA loads, 4 = no global stores
 };
-#define DBG_STAMP(role, it, k)                                                     \
-  do {                                                                             \
-    if (g.dbg && blockIdx.x == 0 && (it) < 64) g.dbg[((role) * 64 + (it)) * 4 + (k)] = clock64(); \
-  } while (0)
+
+// ---- epilogue building blocks ---------------------------------------------------------------------------------------
+// contiguous, balanced tile range of this CTA
+__device__ __forceinline__ void tile_range(int num_tiles, int& t0, int& cnt) {
+  const int base = num_tiles / (int)gridDim.x, rem = num_tiles % (int)gridDim.x;
+  const int b = (int)blockIdx.x;
+  t0 = b * base + (b < rem ? b : rem);
+  cnt = base + (b < rem ? 1 : 0);
+}
+
+// One (pixel, 16-channel chunk) unit: fp32 accumulators -> (+bias, ReLU | mask) -> bf16 -> global, plus the fused sums.
+// a0 / a1: this chunk's 16 per-thread accumulators (MODE != 0).
+template <int MODE>
+__device__ __forceinline__ void epi_unit(const ConvTcArgs& g, const uint32_t (&v)[16], long long off, const float* sbias, bool ok,
+                                         float* a0, float* a1) {
+  if (!ok) return;
+  float f[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+  if (g.bias) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float4 b4 = reinterpret_cast<const float4*>(sbias)[q];
+      f[4 * q] += b4.x; f[4 * q + 1] += b4.y; f[4 * q + 2] += b4.z; f[4 * q + 3] += b4.w;
+    }
+  }
+  __nv_bfloat162 h[8];
+  if (g.mask) {  // fused ReLU / dropout backward of the layer that produced this conv's forward input
+    const uint4 m0 = reinterpret_cast<const uint4*>(g.mask + off)[0];
+    const uint4 m1 = reinterpret_cast<const uint4*>(g.mask + off)[1];
+    const __nv_bfloat162* mb0 = reinterpret_cast<const __nv_bfloat162*>(&m0);
+    const __nv_bfloat162* mb1 = reinterpret_cast<const __nv_bfloat162*>(&m1);
+    const __nv_bfloat162 zero = __float2bfloat162_rn(0.f);
+    const float sc = g.mask_scale;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      h[j] = __hmul2(__floats2bfloat162_rn(f[2 * j] * sc, f[2 * j + 1] * sc), __hgt2(mb0[j], zero));
+      h[4 + j] = __hmul2(__floats2bfloat162_rn(f[8 + 2 * j] * sc, f[8 + 2 * j + 1] * sc), __hgt2(mb1[j], zero));
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) h[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+    if (g.relu) {
+      const __nv_bfloat162 zero = __float2bfloat162_rn(0.f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) h[j] = __hmax2(h[j], zero);
+    }
+  }
+  if (MODE == 1) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float lo = __low2float(h[j]), hi = __high2float(h[j]);
+      a0[2 * j] += lo; a0[2 * j + 1] += hi;
+      a1[2 * j] = fmaf(lo, lo, a1[2 * j]); a1[2 * j + 1] = fmaf(hi, hi, a1[2 * j + 1]);
+    }
+  } else if (MODE == 2) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      a0[2 * j] += __low2float(h[j]);
+      a0[2 * j + 1] += __high2float(h[j]);
+    }
+  } else if (MODE == 3) {
+    const uint4 x0 = reinterpret_cast<const uint4*>(g.in_x + off)[0];
+    const uint4 x1 = reinterpret_cast<const uint4*>(g.in_x + off)[1];
+    const __nv_bfloat162* xb0 = reinterpret_cast<const __nv_bfloat162*>(&x0);
+    const __nv_bfloat162* xb1 = reinterpret_cast<const __nv_bfloat162*>(&x1);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const __nv_bfloat162 xv = j < 4 ? xb0[j] : xb1[j - 4];
+      const float lo = __low2float(h[j]), hi = __high2float(h[j]);
+      a0[2 * j] += lo; a0[2 * j + 1] += hi;
+      a1[2 * j] = fmaf(lo, __low2float(xv), a1[2 * j]); a1[2 * j + 1] = fmaf(hi, __high2float(xv), a1[2 * j + 1]);
+    }
+  }
+  if (!(g.debug & 4)) {
+    uint4* d4 = reinterpret_cast<uint4*>(g.y + off);
+    d4[0] = *reinterpret_cast<const uint4*>(&h[0]);
+    d4[1] = *reinterpret_cast<const uint4*>(&h[4]);
+  }
+}
+
+// add this warp's per-thread partial sums of sample n to the global accumulators and clear them
+template <int MODE>
+__device__ __forceinline__ void epi_flush(const ConvTcArgs& g, int n, int hf, int nchunk, int lane, float (&a0)[32], float (&a1)[32]) {
+  if (MODE == 0) return;
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const int chunk = nchunk == 1 ? 0 : hf + 2 * k;
+    if (chunk < nchunk && (nchunk > 1 || k == 0)) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float s0 = warp_sum(a0[k * 16 + j]);
+        const float s1 = (MODE == 2) ? 0.f : warp_sum(a1[k * 16 + j]);
+        if (lane == j) {
+          const int c = chunk * 16 + j;
+          if (MODE == 1) {
+            atomicAdd(g.in_sums + ((long long)n * g.Cout + c) * 2, (double)s0);
+            atomicAdd(g.in_sums + ((long long)n * g.Cout + c) * 2 + 1, (double)s1);
+          } else if (MODE == 2) {
+            atomicAdd(g.colsum + c, s0);
+          } else {
+            atomicAdd(g.in_bsums + ((long long)n * g.Cout + c) * 2, (double)s0);
+            atomicAdd(g.in_bsums + ((long long)n * g.Cout + c) * 2 + 1, (double)s1);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      a0[k * 16 + j] = 0.f;
+      a1[k * 16 + j] = 0.f;
+    }
+  }
+}
+
+// The epilogue of one tile: `rows` accumulator rows of 128 pixels x Cout channels in TMEM at t_base (+ r * Cout).
+// Warp (q = warp & 3, hf = warp >> 2), lane -> pixel column px = 32 q + lane of every row; the (row, chunk) units are dealt
+// to the two halves: Cout = 16 -> rows alternate, Cout >= 32 -> chunk parity = hf (so a thread's accumulators belong to fixed
+// channels).  pix(r, ok) gives the element offset of (row r, this thread's pixel, channel 0) in y and whether it exists.
+template <int MODE, typename PixFn>
+__device__ __forceinline__ void epi_tile(const ConvTcArgs& g, uint32_t t_base, int rows, int q, int hf, const float* sbias, PixFn pix,
+                                         float (&a0)[32], float (&a1)[32]) {
+  const int nchunk = g.Cout >> 4;
+  const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+  if (nchunk == 1) {
+    for (int r = hf; r < rows; r += 4) {  // two rows in flight (r, r + 2)
+      uint32_t v0[16], v1[16];
+      const bool two = r + 2 < rows;
+      tmem_ld16(t_base + lane_addr + (uint32_t)(r * 16), v0);
+      if (two) tmem_ld16(t_base + lane_addr + (uint32_t)((r + 2) * 16), v1);
+      tmem_ld_wait();
+      bool ok;
+      long long off = pix(r, ok);
+      epi_unit<MODE>(g, v0, off, sbias, ok, a0, a1);
+      if (two) {
+        off = pix(r + 2, ok);
+        epi_unit<MODE>(g, v1, off, sbias, ok, a0, a1);
+      }
+    }
+  } else {
+    for (int r = 0; r < rows; ++r) {
+      bool ok;
+      const long long off = pix(r, ok);
+      const uint32_t t_row = t_base + lane_addr + (uint32_t)(r * g.Cout);
+#pragma unroll
+      for (int k = 0; k < 4; k += 2) {  // chunks hf + 2k and hf + 2k + 2 in flight
+        const int c0 = (hf + 2 * k) * 16;
+        if (hf + 2 * k < nchunk) {
+          const bool two = hf + 2 * k + 2 < nchunk;
+          uint32_t v0[16], v1[16];
+          tmem_ld16(t_row + (uint32_t)c0, v0);
+          if (two) tmem_ld16(t_row + (uint32_t)(c0 + 32), v1);
+          tmem_ld_wait();
+          // per-thread accumulators exist for a warp's first two chunks only (MODE != 0 requires Cout <= 64: k = 0)
+          epi_unit<MODE>(g, v0, off + c0, sbias + c0, ok, &a0[0], &a1[0]);
+          if (two) epi_unit<MODE>(g, v1, off + c0 + 32, sbias + c0 + 32, ok, &a0[16], &a1[16]);
+        }
+      }
+    }
+  }
+}
 
 // RB: row bytes (= 2 * min(Cin, 64)); G: (tap, chunk) sub-tiles per pipeline stage
 template <int RB, int G>
@@ -55,12 +228,12 @@ struct Cfg {
   static constexpr int B_SUB = ((128 * RB) + 1023) / 1024 * 1024;  // room for Cout <= 128 rows, 1 KB aligned
   static constexpr int STAGE = G * (A_SUB + B_SUB);
   static constexpr int STAGES = (STAGE * 4 <= 160 * 1024) ? 4 : (STAGE * 3 <= 160 * 1024 ? 3 : 2);
-  static constexpr int SMEM = STAGES * STAGE + 1024 + 256;
+  static constexpr int SMEM = STAGES * STAGE + 1024 + 1024;
 };
 
-template <int RB, int G>
-__global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap tmX,
-                                                         const __grid_constant__ CUtensorMap tmW, ConvTcArgs g) {
+template <int RB, int G, int MODE>
+__global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap tmX,
+                                                              const __grid_constant__ CUtensorMap tmW, ConvTcArgs g) {
   omr_pdl_enter();
   using C = Cfg<RB, G>;
   constexpr int STAGES = C::STAGES;
@@ -71,14 +244,17 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
   uint64_t* tfull_bar = empty_bar + STAGES;  // [2] accumulator ready
   uint64_t* tempty_bar = tfull_bar + 2;      // [2] accumulator drained
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  float* sbias = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~uintptr_t(15));  // [128], 16-byte aligned
 
   const int warp = (int)warp_idx_sync(), lane = threadIdx.x & 31;
   const int chunks = (g.Cin * 2 + RB - 1) / RB;  // 64-channel chunks per tap (1 or 2)
   const int nsub = g.ntaps * chunks;
   const int ngroups = (nsub + G - 1) / G;
   const uint32_t tmem_cols = g.Cout * 2 <= 32 ? 32 : (g.Cout * 2 <= 64 ? 64 : (g.Cout * 2 <= 128 ? 128 : 256));
+  int t0, tcnt;
+  tile_range(g.num_tiles, t0, tcnt);
 
-  if (warp == 4 && lane == 0) {
+  if (warp == W_TMA && lane == 0) {
     tma_prefetch_desc(&tmX);
     tma_prefetch_desc(&tmW);
     for (int s = 0; s < STAGES; ++s) {
@@ -87,11 +263,12 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
-      mbar_init(&tempty_bar[a], 4);
+      mbar_init(&tempty_bar[a], EPI_WARPS);
     }
     fence_barrier_init();
   }
-  if (warp == 5) tmem_alloc(tmem_slot, tmem_cols);
+  if (warp == W_MMA) tmem_alloc(tmem_slot, tmem_cols);
+  if (threadIdx.x < 128) sbias[threadIdx.x] = (g.bias && (int)threadIdx.x < g.Cout) ? g.bias[threadIdx.x] : 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -99,11 +276,12 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
   const uint32_t a_box_bytes = (uint32_t)(g.TH * g.TW) * RB;
   const uint32_t b_box_bytes = (uint32_t)g.Cout * RB;
 
-  if (warp == 4) {
-    // ---- TMA producer: warp-uniform loop (see tc_common.cuh), one elected lane issues ----
+  if (warp == W_TMA) {
+    // ---- TMA producer: warp-uniform loop, one elected lane issues ----
     int s = 0;
     uint32_t ph = 1;
-    for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
+    for (int i = 0; i < tcnt; ++i) {
+      const int tile = t0 + i;
       const int tw = tile % g.tiles_w;
       const int th = (tile / g.tiles_w) % g.tiles_h;
       const int n = tile / (g.tiles_w * g.tiles_h);
@@ -130,16 +308,15 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
         }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == W_MMA) {
     // ---- MMA issuer: warp-uniform loop, tcgen05.mma / commit under elect_one() ----
     const uint32_t idesc = make_idesc_bf16(128, g.Cout, 0, 0);
     const uint64_t d_hi = make_smem_desc(0, 16, 8 * RB, RB);
     const uint32_t smem_lo = smem_u32(smem) >> 4;
-    uint32_t tcount = 0;
     int s = 0;
     uint32_t ph = 0;
-    for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++tcount) {
-      const uint32_t a = tcount & 1, aph = (tcount >> 1) & 1;
+    for (int i = 0; i < tcnt; ++i) {
+      const uint32_t a = i & 1, aph = (i >> 1) & 1;
       mbar_wait(&tempty_bar[a], aph ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + a * (uint32_t)g.Cout;
@@ -175,83 +352,62 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
       }
     }
   } else {
-    // ---- epilogue: thread = one output pixel; Cout channels from TMEM -> bias/ReLU -> bf16 NHWC ----
-    uint32_t tcount = 0;
-    const int r = warp * 32 + lane;  // tile row = pixel index inside the TH x TW patch
+    // ---- epilogue: thread = one output pixel of the TH x TW patch, its Cout channels split between warps w and w + 4 ----
+    const int q = warp & 3, hf = warp >> 2;
+    const int r = q * 32 + lane;  // tile row = pixel index inside the patch
     const int pr = r / g.TW, pc = r - pr * g.TW;
-    for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++tcount) {
-      const uint32_t a = tcount & 1, aph = (tcount >> 1) & 1;
+    float a0[32], a1[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      a0[j] = 0.f;
+      a1[j] = 0.f;
+    }
+    int cur_n = -1;
+    for (int i = 0; i < tcnt; ++i) {
+      const uint32_t a = i & 1, aph = (i >> 1) & 1;
+      const int tile = t0 + i;
       const int tw = tile % g.tiles_w;
       const int th = (tile / g.tiles_w) % g.tiles_h;
       const int n = tile / (g.tiles_w * g.tiles_h);
+      if (MODE != 0 && MODE != 2 && n != cur_n) {
+        if (cur_n >= 0) epi_flush<MODE>(g, cur_n, hf, g.Cout >> 4, lane, a0, a1);
+        cur_n = n;
+      }
       const int gh = th * g.TH + pr, gw = tw * g.TW + pc;
       const int oh = gh * g.osh + g.oph, ow = gw * g.osw + g.opw;
-      const bool ok = pr < g.TH && gh < g.GH && gw < g.GW && oh < g.OH && ow < g.OW;
-      bf16* dst = g.y + (((long long)n * g.OH + oh) * g.OW + ow) * g.Cout;
+      const bool okp = pr < g.TH && gh < g.GH && gw < g.GW && oh < g.OH && ow < g.OW;
+      const long long offp = (((long long)n * g.OH + oh) * g.OW + ow) * g.Cout;
       mbar_wait(&tfull_bar[a], aph);
       tc_fence_after();
-      const uint32_t t_addr = tmem_base + a * (uint32_t)g.Cout + ((uint32_t)(warp * 32) << 16);
-      for (int c0 = 0; c0 < g.Cout; c0 += 16) {
-        uint32_t v[16];
-        tmem_ld16(t_addr + c0, v);
-        tmem_ld_wait();
-        if (ok) {
-          float f[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            f[j] = __uint_as_float(v[j]);
-            if (g.bias) f[j] += __ldg(g.bias + c0 + j);
-            if (g.relu) f[j] = fmaxf(f[j], 0.f);
-          }
-          if (g.mask) {  // fused ReLU / dropout backward of the layer that produced this conv's forward input
-            const uint4 m0 = reinterpret_cast<const uint4*>(g.mask + (dst - g.y) + c0)[0];
-            const uint4 m1 = reinterpret_cast<const uint4*>(g.mask + (dst - g.y) + c0)[1];
-            const __nv_bfloat162* mb0 = reinterpret_cast<const __nv_bfloat162*>(&m0);
-            const __nv_bfloat162* mb1 = reinterpret_cast<const __nv_bfloat162*>(&m1);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              f[2 * j] = __low2float(mb0[j]) > 0.f ? f[2 * j] * g.mask_scale : 0.f;
-              f[2 * j + 1] = __high2float(mb0[j]) > 0.f ? f[2 * j + 1] * g.mask_scale : 0.f;
-              f[8 + 2 * j] = __low2float(mb1[j]) > 0.f ? f[8 + 2 * j] * g.mask_scale : 0.f;
-              f[8 + 2 * j + 1] = __high2float(mb1[j]) > 0.f ? f[8 + 2 * j + 1] * g.mask_scale : 0.f;
-            }
-          }
-          uint4 o0, o1;
-          o0.x = pack_bf16(f[0], f[1]); o0.y = pack_bf16(f[2], f[3]); o0.z = pack_bf16(f[4], f[5]); o0.w = pack_bf16(f[6], f[7]);
-          o1.x = pack_bf16(f[8], f[9]); o1.y = pack_bf16(f[10], f[11]); o1.z = pack_bf16(f[12], f[13]); o1.w = pack_bf16(f[14], f[15]);
-          uint4* d4 = reinterpret_cast<uint4*>(dst + c0);
-          d4[0] = o0;
-          d4[1] = o1;
-        }
-      }
+      // the patch is ONE accumulator row block: with Cout = 16 only the hf = 0 warps have a unit (rows = 1)
+      epi_tile<MODE>(g, tmem_base + a * (uint32_t)g.Cout, 1, q, hf, sbias, [&](int, bool& ok) { ok = okp; return offp; }, a0, a1);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[a]);
     }
+    if (MODE != 0 && (MODE == 2 || cur_n >= 0)) epi_flush<MODE>(g, cur_n, hf, g.Cout >> 4, lane, a0, a1);
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) {
+  if (warp == W_MMA) {
     tc_fence_after();
     tmem_dealloc(tmem_base, tmem_cols);
   }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Halo variant for stride-1 convolutions with C_in <= 64 (the high-resolution layers, which are bound by L2->SM
-// traffic and TMA box rate, not by the tensor cores): per 128-pixel row tile ONE TMA box brings the 3 x (TW+2)
+// Halo variant for stride-1 convolutions with C_in <= 64 (the high-resolution layers, which are bound by HBM / L2->SM
+// traffic, not by the tensor cores): per tile of TH output rows x TW pixels ONE TMA box brings the (TH+2) x (TW+2)
 // input pixels, and the nine taps are nine UMMA descriptors whose start address is shifted by whole pixel rows
 // ((dh+1)*(TW+2) + (dw+1) rows of RB bytes) inside that box -- the swizzle is a function of the shared-memory
 // address, so a row-shifted window of a TMA-written tile is still a valid K-major operand.  All nine weight taps
-// stay resident in shared memory for the life of the persistent CTA.  Input traffic per tile drops from 9 boxes
-// to 1 (3.05x the output pixels instead of 9x) and the per-tile TMA operations from 18 to 1.
+// stay resident in shared memory for the life of the persistent CTA.
 // ---------------------------------------------------------------------------------------------------------------
-template <int RB>
-__global__ void __launch_bounds__(192, 1) conv_halo_kernel(const __grid_constant__ CUtensorMap tmX,
-                                                           const __grid_constant__ CUtensorMap tmW, ConvTcArgs g, int wsub,
-                                                           int hsub, int stages) {
+template <int RB, int MODE>
+__global__ void __launch_bounds__(NTHREADS, 1) conv_halo_kernel(const __grid_constant__ CUtensorMap tmX,
+                                                                const __grid_constant__ CUtensorMap tmW, ConvTcArgs g, int wsub,
+                                                                int hsub, int stages) {
   omr_pdl_enter();
-  // one tile = TH output rows x TW pixels of one image: ONE (TH+2) x (TW+2) TMA box, TH accumulators of [128 x Cout]
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sW = smem;                // 9 taps x wsub
@@ -263,6 +419,7 @@ __global__ void __launch_bounds__(192, 1) conv_halo_kernel(const __grid_constant
   uint64_t* tfull_bar = empty_bar + stages;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  float* sbias = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~uintptr_t(15));  // [128], 16-byte aligned
 
   const int warp = (int)warp_idx_sync(), lane = threadIdx.x & 31;
   const int TH = g.TH;
@@ -270,8 +427,10 @@ __global__ void __launch_bounds__(192, 1) conv_halo_kernel(const __grid_constant
   const uint32_t need = 2 * acc_cols;
   const uint32_t tmem_cols = need <= 32 ? 32 : (need <= 64 ? 64 : (need <= 128 ? 128 : (need <= 256 ? 256 : 512)));
   const int pitch = g.TW + 2;  // pixel rows per input image row inside the halo box
+  int t0, tcnt;
+  tile_range(g.num_tiles, t0, tcnt);
 
-  if (warp == 4 && lane == 0) {
+  if (warp == W_TMA && lane == 0) {
     tma_prefetch_desc(&tmX);
     tma_prefetch_desc(&tmW);
     mbar_init(w_full, 1);
@@ -281,32 +440,31 @@ __global__ void __launch_bounds__(192, 1) conv_halo_kernel(const __grid_constant
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
-      mbar_init(&tempty_bar[a], 4);
+      mbar_init(&tempty_bar[a], EPI_WARPS);
     }
     fence_barrier_init();
   }
-  if (warp == 5) tmem_alloc(tmem_slot, tmem_cols);
+  if (warp == W_MMA) tmem_alloc(tmem_slot, tmem_cols);
+  if (threadIdx.x < 128) sbias[threadIdx.x] = (g.bias && (int)threadIdx.x < g.Cout) ? g.bias[threadIdx.x] : 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = bcast0(*tmem_slot);
 
-  if (warp == 4) {
+  if (warp == W_TMA) {
     // ---- TMA producer: the whole warp walks the tiles (uniform state), one elected lane issues ----
     if (elect_one()) {
       mbar_expect_tx(w_full, 9u * (uint32_t)g.Cout * RB);
       for (int t = 0; t < 9; ++t) tma_load_2d(sW + t * wsub, &tmW, w_full, t * g.Cin, 0);
     }
-    uint32_t it = 0;
     int s = 0;
     uint32_t ph = 1;  // parity to wait for on empty_bar[s]
-    for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++it) {
+    for (int i = 0; i < tcnt; ++i) {
+      const int tile = t0 + i;
       const int tw = tile % g.tiles_w;
       const int th = (tile / g.tiles_w) % g.tiles_h;
       const int n = tile / (g.tiles_w * g.tiles_h);
-      DBG_STAMP(0, it, 0);
       mbar_wait(&empty_bar[s], ph);
-      DBG_STAMP(0, it, 1);
       if (elect_one()) {
         if (g.debug & 2) {
           mbar_arrive(&full_bar[s]);
@@ -315,13 +473,13 @@ __global__ void __launch_bounds__(192, 1) conv_halo_kernel(const __grid_constant
           tma_load_4d(sH + s * hsub, &tmX, &full_bar[s], 0, tw * g.TW - 1, th * TH - 1, n);
         }
       }
-      DBG_STAMP(0, it, 2);
+      __syncwarp();
       if (++s == stages) {
         s = 0;
         ph ^= 1;
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == W_MMA) {
     // ---- MMA issuer: warp-uniform loop, tcgen05.mma / commit under elect_one() ----
     const uint32_t idesc = make_idesc_bf16(128, g.Cout, 0, 0);
     const uint64_t d_hi = make_smem_desc(0, 16, 8 * RB, RB);
@@ -340,16 +498,12 @@ __global__ void __launch_bounds__(192, 1) conv_halo_kernel(const __grid_constant
     mbar_wait(w_full, 0);
     const uint32_t w_lo = smem_u32(sW) >> 4;
     const uint32_t h_base = smem_u32(sH) >> 4, h_step = (uint32_t)hsub >> 4;
-    uint32_t it = 0;
     int s = 0;
     uint32_t ph = 0;  // parity to wait for on full_bar[s]
-    for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++it) {
-      const uint32_t a = it & 1, aph = (it >> 1) & 1;
-      DBG_STAMP(1, it, 0);
+    for (int i = 0; i < tcnt; ++i) {
+      const uint32_t a = i & 1, aph = (i >> 1) & 1;
       mbar_wait(&tempty_bar[a], aph ^ 1);
-      DBG_STAMP(1, it, 1);
       mbar_wait(&full_bar[s], ph);
-      DBG_STAMP(1, it, 2);
       tc_fence_after();
       const uint32_t h_lo = h_base + (uint32_t)s * h_step;
       const uint32_t d0 = tmem_base + a * acc_cols;
@@ -376,76 +530,54 @@ __global__ void __launch_bounds__(192, 1) conv_halo_kernel(const __grid_constant
         umma_commit(&tfull_bar[a]);
       }
       __syncwarp();
-      DBG_STAMP(1, it, 3);
       if (++s == stages) {
         s = 0;
         ph ^= 1;
       }
     }
   } else {
-    uint32_t it = 0;
-    const int px = warp * 32 + lane;  // pixel inside an output row of the tile
-    for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++it) {
-      const uint32_t a = it & 1, aph = (it >> 1) & 1;
+    // ---- epilogue: thread = pixel column px of every output row of the tile ----
+    const int q = warp & 3, hf = warp >> 2;
+    const int px = q * 32 + lane;
+    float a0[32], a1[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      a0[j] = 0.f;
+      a1[j] = 0.f;
+    }
+    int cur_n = -1;
+    for (int i = 0; i < tcnt; ++i) {
+      const uint32_t a = i & 1, aph = (i >> 1) & 1;
+      const int tile = t0 + i;
       const int tw = tile % g.tiles_w;
       const int th = (tile / g.tiles_w) % g.tiles_h;
       const int n = tile / (g.tiles_w * g.tiles_h);
-      const int gw = tw * g.TW + px;
-      if (threadIdx.x == 0) DBG_STAMP(2, it, 0);
-      mbar_wait(&tfull_bar[a], aph);
-      if (threadIdx.x == 0) DBG_STAMP(2, it, 1);
-      tc_fence_after();
-      for (int r = 0; r < TH; ++r) {
-        const int gh = th * TH + r;
-        const bool ok = px < g.TW && gw < g.GW && gh < g.GH;
-        bf16* dst = g.y + (((long long)n * g.OH + gh) * g.OW + gw) * g.Cout;
-        const uint32_t t_addr = tmem_base + a * acc_cols + (uint32_t)(r * g.Cout) + ((uint32_t)(warp * 32) << 16);
-        for (int c0 = 0; c0 < g.Cout; c0 += 16) {
-          uint32_t v[16];
-          tmem_ld16(t_addr + c0, v);
-          tmem_ld_wait();
-          if (ok) {
-            float f[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              f[j] = __uint_as_float(v[j]);
-              if (g.bias) f[j] += __ldg(g.bias + c0 + j);
-              if (g.relu) f[j] = fmaxf(f[j], 0.f);
-            }
-            if (g.mask) {  // fused ReLU / dropout backward of the layer that produced this conv's forward input
-              const uint4 m0 = reinterpret_cast<const uint4*>(g.mask + (dst - g.y) + c0)[0];
-              const uint4 m1 = reinterpret_cast<const uint4*>(g.mask + (dst - g.y) + c0)[1];
-              const __nv_bfloat162* mb0 = reinterpret_cast<const __nv_bfloat162*>(&m0);
-              const __nv_bfloat162* mb1 = reinterpret_cast<const __nv_bfloat162*>(&m1);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                f[2 * j] = __low2float(mb0[j]) > 0.f ? f[2 * j] * g.mask_scale : 0.f;
-                f[2 * j + 1] = __high2float(mb0[j]) > 0.f ? f[2 * j + 1] * g.mask_scale : 0.f;
-                f[8 + 2 * j] = __low2float(mb1[j]) > 0.f ? f[8 + 2 * j] * g.mask_scale : 0.f;
-                f[8 + 2 * j + 1] = __high2float(mb1[j]) > 0.f ? f[8 + 2 * j + 1] * g.mask_scale : 0.f;
-              }
-            }
-            uint4 o0, o1;
-            o0.x = pack_bf16(f[0], f[1]); o0.y = pack_bf16(f[2], f[3]); o0.z = pack_bf16(f[4], f[5]); o0.w = pack_bf16(f[6], f[7]);
-            o1.x = pack_bf16(f[8], f[9]); o1.y = pack_bf16(f[10], f[11]); o1.z = pack_bf16(f[12], f[13]); o1.w = pack_bf16(f[14], f[15]);
-            uint4* d4 = reinterpret_cast<uint4*>(dst + c0);
-            if (!(g.debug & 4)) {
-              d4[0] = o0;
-              d4[1] = o1;
-            }
-          }
-        }
+      if (MODE != 0 && MODE != 2 && n != cur_n) {
+        if (cur_n >= 0) epi_flush<MODE>(g, cur_n, hf, g.Cout >> 4, lane, a0, a1);
+        cur_n = n;
       }
-      if (threadIdx.x == 0) DBG_STAMP(2, it, 2);
+      const int gw = tw * g.TW + px;
+      const bool okw = px < g.TW && gw < g.GW;
+      const long long off0 = (((long long)n * g.OH + th * TH) * g.OW + gw) * g.Cout;
+      const long long row_elems = (long long)g.OW * g.Cout;
+      const int gh0 = th * TH;
+      mbar_wait(&tfull_bar[a], aph);
+      tc_fence_after();
+      epi_tile<MODE>(g, tmem_base + a * acc_cols, TH, q, hf, sbias,
+                     [&](int r, bool& ok) {
+                       ok = okw && gh0 + r < g.GH;
+                       return off0 + r * row_elems;
+                     },
+                     a0, a1);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[a]);
-      if (threadIdx.x == 0) DBG_STAMP(2, it, 3);
     }
+    if (MODE != 0 && (MODE == 2 || cur_n >= 0)) epi_flush<MODE>(g, cur_n, hf, g.Cout >> 4, lane, a0, a1);
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) {
+  if (warp == W_MMA) {
     tc_fence_after();
     tmem_dealloc(tmem_base, tmem_cols);
   }
@@ -480,23 +612,61 @@ int num_sms() {
   return g_num_sms;
 }
 
-template <int RB, int G>
-int launch_cfg(const CUtensorMap& tmX, const CUtensorMap& tmW, const ConvTcArgs& a, cudaStream_t st) {
-  auto kern = conv_tc_kernel<RB, G>;
+int mode_of(const ConvTcArgs& a) { return a.in_sums ? 1 : (a.colsum ? 2 : (a.in_bsums ? 3 : 0)); }
+
+template <int RB, int G, int MODE>
+int launch_generic(const CUtensorMap& tmX, const CUtensorMap& tmW, const ConvTcArgs& a, cudaStream_t st) {
+  auto kern = conv_tc_kernel<RB, G, MODE>;
   static bool configured = false;
   if (!configured) {
     OMR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<RB, G>::SMEM));
     configured = true;
   }
   int grid = a.num_tiles < num_sms() ? a.num_tiles : num_sms();
-  OmrLaunch(grid, 192, Cfg<RB, G>::SMEM, st)(kern, tmX, tmW, a);
+  OmrLaunch(grid, NTHREADS, Cfg<RB, G>::SMEM, st)(kern, tmX, tmW, a);
   OMR_LAUNCHED();
   return OMR_OK;
+}
+template <int RB, int G>
+int launch_generic_mode(const CUtensorMap& tmX, const CUtensorMap& tmW, const ConvTcArgs& a, cudaStream_t st) {
+  switch (mode_of(a)) {
+    case 0: return launch_generic<RB, G, 0>(tmX, tmW, a, st);
+    case 1: return launch_generic<RB, G, 1>(tmX, tmW, a, st);
+    case 2: return launch_generic<RB, G, 2>(tmX, tmW, a, st);
+    default: return launch_generic<RB, G, 3>(tmX, tmW, a, st);
+  }
+}
+
+template <int RB, int MODE>
+int launch_halo(const CUtensorMap& tmX, const CUtensorMap& tmW, const ConvTcArgs& h, int wsub, int hsub, int stages, int smem_bytes,
+                cudaStream_t st) {
+  auto kern = conv_halo_kernel<RB, MODE>;
+  static bool configured = false;
+  if (!configured) {
+    OMR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    configured = true;
+  }
+  const int grid = h.num_tiles < num_sms() ? h.num_tiles : num_sms();
+  OmrLaunch(grid, NTHREADS, smem_bytes, st)(kern, tmX, tmW, h, wsub, hsub, stages);
+  OMR_LAUNCHED();
+  return OMR_OK;
+}
+template <int RB>
+int launch_halo_mode(const CUtensorMap& tmX, const CUtensorMap& tmW, const ConvTcArgs& h, int wsub, int hsub, int stages, int smem_bytes,
+                     cudaStream_t st) {
+  switch (mode_of(h)) {
+    case 0: return launch_halo<RB, 0>(tmX, tmW, h, wsub, hsub, stages, smem_bytes, st);
+    case 1: return launch_halo<RB, 1>(tmX, tmW, h, wsub, hsub, stages, smem_bytes, st);
+    case 2: return launch_halo<RB, 2>(tmX, tmW, h, wsub, hsub, stages, smem_bytes, st);
+    default: return launch_halo<RB, 3>(tmX, tmW, h, wsub, hsub, stages, smem_bytes, st);
+  }
 }
 
 // One launch of the tap-GEMM.  x: [N, XH, XW, Cin] bf16; wpack: [Cout, 9*Cin] bf16 (tap-major, channels innermost).
 int run_taps(const void* x, int N, int XH, int XW, int Cin, const void* wpack, int Cout, ConvTcArgs a, cudaStream_t st) {
   const int rb = (Cin >= 64 ? 64 : Cin) * 2;
+  a.debug = conv_debug();
+  if (mode_of(a) != 0 && Cout > 64) return OMR_TC_NOT_ELIGIBLE;  // the caller must not ask (fused sums need Cout <= 64)
   if (halo_enabled() && a.ish == 1 && a.isw == 1 && a.ntaps == 9 && Cin <= 64 && a.osh == 1 && a.osw == 1) {
     const int TW = a.GW >= 128 ? 128 : a.GW;
     const int pitch = TW + 2;
@@ -509,19 +679,12 @@ int run_taps(const void* x, int N, int XH, int XW, int Cin, const void* wpack, i
       int rows = (TH + 2) * pitch;
       if (rows < (TH + 1) * pitch + 2 + 128) rows = (TH + 1) * pitch + 2 + 128;
       hsub = (rows * rb + 1023) / 1024 * 1024;
-      stages = (225 * 1024 - 1024 - 512 - 9 * wsub) / hsub;
+      stages = (225 * 1024 - 1024 - 1024 - 9 * wsub) / hsub;
       if (stages > 4) stages = 4;
       if (stages >= 2) break;
     }
     if (TH >= 1 && stages >= 2) {
       ConvTcArgs h = a;
-      h.debug = conv_debug();
-      static long long* dbg_dev = nullptr;
-      if (h.debug & 8) {
-        if (!dbg_dev) cudaMalloc(&dbg_dev, 3 * 64 * 4 * sizeof(long long));
-        cudaMemsetAsync(dbg_dev, 0, 3 * 64 * 4 * sizeof(long long), st);
-        h.dbg = dbg_dev;
-      }
       h.TH = TH; h.TW = TW;
       h.tiles_w = (a.GW + TW - 1) / TW;
       h.tiles_h = (a.GH + TH - 1) / TH;
@@ -538,38 +701,10 @@ int run_taps(const void* x, int N, int XH, int XW, int Cin, const void* wpack, i
       unsigned int wb[2] = {(unsigned)Cin, (unsigned)Cout};
       rc = omr_make_tensor_map(&tmW, 2, wpack, 2, wd, ws, wb, nullptr, rb);
       if (rc) return rc;
-      const int smem_bytes = 9 * wsub + stages * hsub + 1024 + 512;
-      const int grid = h.num_tiles < num_sms() ? h.num_tiles : num_sms();
-      static bool cfgd[3] = {false, false, false};
-      const int ci = rb == 32 ? 0 : (rb == 64 ? 1 : 2);
-      if (!cfgd[ci]) {
-        if (rb == 32) OMR_CUDA(cudaFuncSetAttribute(conv_halo_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        if (rb == 64) OMR_CUDA(cudaFuncSetAttribute(conv_halo_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        if (rb == 128) OMR_CUDA(cudaFuncSetAttribute(conv_halo_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        cfgd[ci] = true;
-      }
-      if (rb == 32) OmrLaunch(grid, 192, smem_bytes, st)(conv_halo_kernel<32>, tmX, tmW, h, wsub, hsub, stages);
-      else if (rb == 64) OmrLaunch(grid, 192, smem_bytes, st)(conv_halo_kernel<64>, tmX, tmW, h, wsub, hsub, stages);
-      else OmrLaunch(grid, 192, smem_bytes, st)(conv_halo_kernel<128>, tmX, tmW, h, wsub, hsub, stages);
-      OMR_LAUNCHED();
-      if (h.dbg) {  // diagnostics only: synchronises
-        static int dumps = 0;
-        cudaStreamSynchronize(st);
-        static long long hb[3 * 64 * 4];
-        cudaMemcpy(hb, dbg_dev, sizeof(hb), cudaMemcpyDeviceToHost);
-        if (dumps++ < 3) {
-          const long long t0 = hb[(0 * 64 + 0) * 4 + 0];
-          fprintf(stderr, "[conv_halo dbg] Cin %d Cout %d TH %d TW %d tiles %d grid %d stages %d (clk rel. to producer start)\n", Cin, Cout, TH, TW,
-                  h.num_tiles, grid, stages);
-          for (int it = 0; it < 24; ++it) {
-            fprintf(stderr, " it%2d  TMA wait %6lld got %6lld issued %6lld | MMA wait_te %6lld got %6lld full %6lld commit %6lld | EPI wait %6lld got %6lld done %6lld arr %6lld\n",
-                    it, hb[(0 * 64 + it) * 4 + 0] - t0, hb[(0 * 64 + it) * 4 + 1] - t0, hb[(0 * 64 + it) * 4 + 2] - t0,
-                    hb[(1 * 64 + it) * 4 + 0] - t0, hb[(1 * 64 + it) * 4 + 1] - t0, hb[(1 * 64 + it) * 4 + 2] - t0, hb[(1 * 64 + it) * 4 + 3] - t0,
-                    hb[(2 * 64 + it) * 4 + 0] - t0, hb[(2 * 64 + it) * 4 + 1] - t0, hb[(2 * 64 + it) * 4 + 2] - t0, hb[(2 * 64 + it) * 4 + 3] - t0);
-          }
-        }
-      }
-      return OMR_OK;
+      const int smem_bytes = 9 * wsub + stages * hsub + 1024 + 1024;
+      if (rb == 32) return launch_halo_mode<32>(tmX, tmW, h, wsub, hsub, stages, smem_bytes, st);
+      if (rb == 64) return launch_halo_mode<64>(tmX, tmW, h, wsub, hsub, stages, smem_bytes, st);
+      return launch_halo_mode<128>(tmX, tmW, h, wsub, hsub, stages, smem_bytes, st);
     }
   }
   // tile geometry: a TH x TW patch of the logical output grid, TH*TW <= 128
@@ -596,9 +731,9 @@ int run_taps(const void* x, int N, int XH, int XW, int Cin, const void* wpack, i
     rc = omr_make_tensor_map(&tmW, 2, wpack, 2, wd, ws, wb, nullptr, rb);
     if (rc) return rc;
   }
-  if (rb == 32) return launch_cfg<32, 3>(tmX, tmW, a, st);
-  if (rb == 64) return launch_cfg<64, 3>(tmX, tmW, a, st);
-  return launch_cfg<128, 1>(tmX, tmW, a, st);
+  if (rb == 32) return launch_generic_mode<32, 3>(tmX, tmW, a, st);
+  if (rb == 64) return launch_generic_mode<64, 3>(tmX, tmW, a, st);
+  return launch_generic_mode<128, 1>(tmX, tmW, a, st);
 }
 
 bool shape_ok(int Ci, int Co) {
@@ -608,13 +743,16 @@ bool shape_ok(int Ci, int Co) {
 
 }  // namespace
 
+// in_sums (nullable, Co <= 64): [N][Co][2] += (sum y, sum y^2) of the stored output (InstanceNorm statistics)
 int omr_conv3x3_fwd_tc(const void* x, const void* w, const float* bias, void* y, int N, int H, int W, int Ci, int Co,
-                       int sh, int sw, int relu, cudaStream_t st) {
+                       int sh, int sw, int relu, double* in_sums, cudaStream_t st) {
   if (!shape_ok(Ci, Co) || N < 1) return OMR_TC_NOT_ELIGIBLE;
   if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(w) & 15) || (reinterpret_cast<uintptr_t>(y) & 15))
     return OMR_TC_NOT_ELIGIBLE;
+  if (in_sums && Co > 64) return OMR_TC_NOT_ELIGIBLE;
   ConvTcArgs a{};
   a.y = (bf16*)y; a.bias = bias; a.relu = relu; a.N = N;
+  a.in_sums = in_sums;
   a.GH = (H + sh - 1) / sh; a.GW = (W + sw - 1) / sw;
   a.ish = sh; a.isw = sw;
   a.ntaps = 9;
@@ -629,18 +767,23 @@ int omr_conv3x3_fwd_tc(const void* x, const void* w, const float* bias, void* y,
 
 // dx[N,H,W,Ci] from dy[N,Ho,Wo,Co] and the transposed pack wT[Ci, 9*Co]:
 //   dx[h,w,ci] = sum_{kh,kw,co} dy[(h+1-kh)/sh, (w+1-kw)/sw, co] * w[co,ci,kh,kw]   (only exact divisions)
+// colsum (nullable, Ci <= 64): [Ci] += column sums of the stored dx; in_x / in_bsums (nullable, Ci <= 64): InstanceNorm
+// backward sums [N][Ci][2] += (sum dx, sum dx * in_x) with in_x laid out like dx.
 int omr_conv3x3_dgrad_tc(const void* dy, const void* wT, void* dx, int N, int H, int W, int Ci, int Co, int sh, int sw,
-                         const void* mask, float mask_scale, cudaStream_t st) {
+                         const void* mask, float mask_scale, float* colsum, const void* in_x, double* in_bsums, cudaStream_t st) {
   if (!shape_ok(Ci, Co) || N < 1 || sh > 2 || sw > 2) return OMR_TC_NOT_ELIGIBLE;
   if ((reinterpret_cast<uintptr_t>(dy) & 15) || (reinterpret_cast<uintptr_t>(wT) & 15) || (reinterpret_cast<uintptr_t>(dx) & 15) ||
-      (reinterpret_cast<uintptr_t>(mask) & 15))
+      (reinterpret_cast<uintptr_t>(mask) & 15) || (reinterpret_cast<uintptr_t>(in_x) & 15))
     return OMR_TC_NOT_ELIGIBLE;
+  if ((colsum || in_bsums) && Ci > 64) return OMR_TC_NOT_ELIGIBLE;
+  if (colsum && in_bsums) return OMR_TC_NOT_ELIGIBLE;
   const int Ho = (H + sh - 1) / sh, Wo = (W + sw - 1) / sw;
   for (int ph = 0; ph < sh; ++ph)
     for (int pw = 0; pw < sw; ++pw) {
       ConvTcArgs a{};
       a.y = (bf16*)dx; a.bias = nullptr; a.relu = 0; a.N = N;
       a.mask = (const bf16*)mask; a.mask_scale = mask_scale;
+      a.colsum = colsum; a.in_x = (const bf16*)in_x; a.in_bsums = in_bsums;
       a.GH = (H - ph + sh - 1) / sh; a.GW = (W - pw + sw - 1) / sw;  // pixels of this parity class
       if (a.GH <= 0 || a.GW <= 0) continue;
       a.ish = 1; a.isw = 1;

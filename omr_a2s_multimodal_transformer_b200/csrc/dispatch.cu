@@ -42,30 +42,66 @@ extern "C" int omr_gemm(int in_dt, int out_dt, int transA, int transB, int M, in
                        bias, bias_mode, relu, accumulate, st);
 }
 
-extern "C" int omr_conv3x3_fwd(int dt, const void* x, const void* w, const float* bias, void* y, int N, int H, int W,
-                               int Ci, int Co, int sh, int sw, int relu, omr_stream_t stream) {
-  OMR_REQUIRE(N >= 0 && H > 0 && W > 0 && Ci > 0 && Co > 0 && sh > 0 && sw > 0, "omr_conv3x3_fwd: bad shape");
-  cudaStream_t st = as_stream(stream);
+// Fused outputs (in_sums / colsum / in_bsums) are produced in the tcgen05 epilogue when the kernel takes them (bf16, <= 64
+// output channels) and by a separate pass over the stored result otherwise -- same contents either way.
+static int conv_fwd_plain(int dt, const void* x, const void* w, const float* bias, void* y, int N, int H, int W, int Ci, int Co,
+                          int sh, int sw, int relu, cudaStream_t st) {
   if (Ci == 1) {  // first layer: K = 9, output-write bound streaming kernel (both dtypes)
     int rc1 = omr_conv3x3_fwd_c1(dt, x, w, bias, y, N, H, W, Co, sh, sw, relu, st);
     if (rc1 != OMR_TC_NOT_ELIGIBLE) return rc1;
   }
   if (tc_enabled() && dt == OMR_BF16) {
-    TC_TRY(omr_conv3x3_fwd_tc(x, w, bias, y, N, H, W, Ci, Co, sh, sw, relu, st));
+    TC_TRY(omr_conv3x3_fwd_tc(x, w, bias, y, N, H, W, Ci, Co, sh, sw, relu, nullptr, st));
   }
   return omr_conv3x3_fwd_simt(dt, x, w, bias, y, N, H, W, Ci, Co, sh, sw, relu, st);
 }
 
-extern "C" int omr_conv3x3_dgrad(int dt, const void* dy, const void* wT, void* dx, int N, int H, int W, int Ci, int Co,
-                                 int sh, int sw, const void* mask, float mask_scale, omr_stream_t stream) {
-  OMR_REQUIRE(N >= 0 && H > 0 && W > 0 && Ci > 0 && Co > 0 && sh > 0 && sw > 0, "omr_conv3x3_dgrad: bad shape");
+extern "C" int omr_conv3x3_fwd(int dt, const void* x, const void* w, const float* bias, void* y, int N, int H, int W,
+                               int Ci, int Co, int sh, int sw, int relu, double* in_sums, omr_stream_t stream) {
+  OMR_REQUIRE(N >= 0 && H > 0 && W > 0 && Ci > 0 && Co > 0 && sh > 0 && sw > 0, "omr_conv3x3_fwd: bad shape");
   cudaStream_t st = as_stream(stream);
+  if (!in_sums) return conv_fwd_plain(dt, x, w, bias, y, N, H, W, Ci, Co, sh, sw, relu, st);
+  const int Ho = (H + sh - 1) / sh, Wo = (W + sw - 1) / sw;
+  if (tc_enabled() && dt == OMR_BF16 && Ci > 1 && Co <= 64) {
+    OMR_CUDA(cudaMemsetAsync(in_sums, 0, sizeof(double) * (size_t)N * Co * 2, st));
+    TC_TRY(omr_conv3x3_fwd_tc(x, w, bias, y, N, H, W, Ci, Co, sh, sw, relu, in_sums, st));
+  }
+  int rc = conv_fwd_plain(dt, x, w, bias, y, N, H, W, Ci, Co, sh, sw, relu, st);
+  if (rc) return rc;
+  return omr_in_partial_sums(dt, 0, y, nullptr, in_sums, N, Ho * Wo, Co, st);
+}
+
+extern "C" int omr_conv3x3_dgrad(int dt, const void* dy, const void* wT, void* dx, int N, int H, int W, int Ci, int Co,
+                                 int sh, int sw, const void* mask, float mask_scale, float* colsum, const void* in_x,
+                                 double* in_bsums, omr_stream_t stream) {
+  OMR_REQUIRE(N >= 0 && H > 0 && W > 0 && Ci > 0 && Co > 0 && sh > 0 && sw > 0, "omr_conv3x3_dgrad: bad shape");
+  OMR_REQUIRE(!(colsum && in_bsums), "omr_conv3x3_dgrad: colsum and in_bsums are mutually exclusive");
+  OMR_REQUIRE(!in_bsums || in_x, "omr_conv3x3_dgrad: in_bsums needs in_x");
+  cudaStream_t st = as_stream(stream);
+  const bool fused = (colsum || in_bsums);
   if (tc_enabled() && dt == OMR_BF16) {
-    TC_TRY(omr_conv3x3_dgrad_tc(dy, wT, dx, N, H, W, Ci, Co, sh, sw, mask, mask_scale, st));
+    if (!fused || Ci <= 64) {
+      if (in_bsums) OMR_CUDA(cudaMemsetAsync(in_bsums, 0, sizeof(double) * (size_t)N * Ci * 2, st));
+      TC_TRY(omr_conv3x3_dgrad_tc(dy, wT, dx, N, H, W, Ci, Co, sh, sw, mask, mask_scale, colsum, in_x, in_bsums, st));
+    } else {
+      int rc = omr_conv3x3_dgrad_tc(dy, wT, dx, N, H, W, Ci, Co, sh, sw, mask, mask_scale, nullptr, nullptr, nullptr, st);
+      if (rc != OMR_TC_NOT_ELIGIBLE) {
+        if (rc) return rc;
+        ++g_tc_calls;
+        if (colsum) return omr_colsum(dt, dx, (long long)N * H * W, Ci, Ci, colsum, 1, stream);
+        return omr_in_partial_sums(dt, 2, dx, in_x, in_bsums, N, H * W, Ci, st);
+      }
+    }
   }
   int rc = omr_conv3x3_dgrad_simt(dt, dy, wT, dx, N, H, W, Ci, Co, sh, sw, st);
-  if (rc || !mask) return rc;
-  return omr_relu_mask_scale(dt, dx, mask, mask_scale, (long long)N * H * W * Ci, st);  // CUDA-core path: separate pass
+  if (rc) return rc;
+  if (mask) {
+    rc = omr_relu_mask_scale(dt, dx, mask, mask_scale, (long long)N * H * W * Ci, st);  // CUDA-core path: separate pass
+    if (rc) return rc;
+  }
+  if (colsum) return omr_colsum(dt, dx, (long long)N * H * W, Ci, Ci, colsum, 1, stream);
+  if (in_bsums) return omr_in_partial_sums(dt, 2, dx, in_x, in_bsums, N, H * W, Ci, st);
+  return OMR_OK;
 }
 
 extern "C" int omr_conv3x3_wgrad(int dt, const void* x, const void* dy, float* dw, float* db, int N, int H, int W,

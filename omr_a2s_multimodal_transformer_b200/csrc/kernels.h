@@ -20,9 +20,11 @@ int omr_conv3x3_dgrad_simt(int dt, const void* dy, const void* wT, void* dx, int
 int omr_conv3x3_wgrad_simt(int dt, const void* x, const void* dy, float* dw, int N, int H, int W, int Ci, int Co, int sh,
                            int sw, int accumulate, cudaStream_t st);
 int omr_conv3x3_fwd_tc(const void* x, const void* w, const float* bias, void* y, int N, int H, int W, int Ci, int Co,
-                       int sh, int sw, int relu, cudaStream_t st);
+                       int sh, int sw, int relu, double* in_sums, cudaStream_t st);
 int omr_conv3x3_dgrad_tc(const void* dy, const void* wT, void* dx, int N, int H, int W, int Ci, int Co, int sh, int sw,
-                         const void* mask, float mask_scale, cudaStream_t st);
+                         const void* mask, float mask_scale, float* colsum, const void* in_x, double* in_bsums,
+                         cudaStream_t st);
+int omr_in_partial_sums(int dt, int mode, const void* a, const void* xin, double* out, int N, int HW, int C, cudaStream_t st);
 int omr_relu_mask_scale(int dt, void* dx, const void* mask, float scale, long long n, cudaStream_t st);
 int omr_conv3x3_wgrad_tc(const void* x, const void* dy, float* dw, int N, int H, int W, int Ci, int Co, int sh, int sw,
                          int accumulate, cudaStream_t st);

@@ -41,7 +41,8 @@ template <> struct V16<float> {
 
 constexpr int IN_UNROLL = 4;
 
-// MODE 0: (sum x, sum x^2).  MODE 1: (sum dy, sum dy * xhat) with xhat from saved stats.
+// MODE 0: (sum x, sum x^2).  MODE 1: (sum dy, sum dy * xhat) with xhat from saved stats.  MODE 2: (sum dy, sum dy * x)
+// -- the "raw" backward sums that the convolution data-gradient epilogue also produces (conv_tc.cu MODE 3).
 // grid (blocks per sample, N); requires (256 * VEC) % C == 0.
 template <typename T, int MODE>
 __global__ void __launch_bounds__(256) in_partial_kernel(const T* __restrict__ a, const T* __restrict__ xin,
@@ -55,7 +56,7 @@ __global__ void __launch_bounds__(256) in_partial_kernel(const T* __restrict__ a
   long long e = ((long long)blockIdx.x * 256 + threadIdx.x) * VEC;
   const int c0 = (int)(e % C);
   const T* ap = a + (long long)n * per_sample;
-  const T* xp = MODE == 1 ? xin + (long long)n * per_sample : nullptr;
+  const T* xp = MODE >= 1 ? xin + (long long)n * per_sample : nullptr;
   float mean[VEC], rstd[VEC], s0[VEC], s1[VEC];
 #pragma unroll
   for (int k = 0; k < VEC; ++k) {
@@ -72,10 +73,10 @@ __global__ void __launch_bounds__(256) in_partial_kernel(const T* __restrict__ a
       const long long eu = e + u * step;
       if (eu < per_sample) {
         V16<T>::load(ap + eu, v[u]);
-        if (MODE == 1) V16<T>::load(xp + eu, x[u]);
+        if (MODE >= 1) V16<T>::load(xp + eu, x[u]);
       } else {
 #pragma unroll
-        for (int k = 0; k < VEC; ++k) { v[u][k] = 0.f; if (MODE == 1) x[u][k] = mean[k]; }
+        for (int k = 0; k < VEC; ++k) { v[u][k] = 0.f; if (MODE == 1) x[u][k] = mean[k]; if (MODE == 2) x[u][k] = 0.f; }
       }
     }
 #pragma unroll
@@ -84,7 +85,8 @@ __global__ void __launch_bounds__(256) in_partial_kernel(const T* __restrict__ a
       for (int k = 0; k < VEC; ++k) {
         s0[k] += v[u][k];
         if (MODE == 0) s1[k] = fmaf(v[u][k], v[u][k], s1[k]);
-        else s1[k] = fmaf(v[u][k], (x[u][k] - mean[k]) * rstd[k], s1[k]);
+        else if (MODE == 1) s1[k] = fmaf(v[u][k], (x[u][k] - mean[k]) * rstd[k], s1[k]);
+        else s1[k] = fmaf(v[u][k], x[u][k], s1[k]);
       }
   }
 #pragma unroll
@@ -152,9 +154,10 @@ template <typename T>
 __global__ void __launch_bounds__(256) in_apply_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x,
                                                            const float* __restrict__ stats, const double* __restrict__ sums,
                                                            T* __restrict__ dx, long long per_sample, int C, double inv_hw,
-                                                           int relu_mask, float mask_scale) {
+                                                           int relu_mask, float mask_scale, int raw_sums, float* __restrict__ colsum) {
   omr_pdl_enter();
   constexpr int VEC = V16<T>::N;
+  __shared__ float smc[256 * VEC];
   const int n = blockIdx.y;
   const long long step = (long long)gridDim.x * 256 * VEC;
   long long e = ((long long)blockIdx.x * 256 + threadIdx.x) * VEC;
@@ -169,8 +172,13 @@ __global__ void __launch_bounds__(256) in_apply_bwd_kernel(const T* __restrict__
     mean[k] = stats[i * 2];
     rstd[k] = stats[i * 2 + 1];
     m1[k] = (float)(sums[i * 2] * inv_hw);
-    m2[k] = (float)(sums[i * 2 + 1] * inv_hw);
+    // raw_sums: sums = (sum dy, sum dy * x) -> sum dy * xhat = rstd * (sum dy * x - mean * sum dy), combined in double
+    m2[k] = raw_sums ? (float)((double)rstd[k] * (sums[i * 2 + 1] - (double)mean[k] * sums[i * 2]) * inv_hw)
+                     : (float)(sums[i * 2 + 1] * inv_hw);
   }
+  float cs[VEC];
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) cs[k] = 0.f;
   for (; e < per_sample; e += step * IN_UNROLL) {
     float g[IN_UNROLL][VEC], v[IN_UNROLL][VEC];
 #pragma unroll
@@ -189,9 +197,20 @@ __global__ void __launch_bounds__(256) in_apply_bwd_kernel(const T* __restrict__
           float r = rstd[k] * (g[u][k] - m1[k] - xh * m2[k]);
           if (relu_mask) r = xin > 0.f ? r * mask_scale : 0.f;
           v[u][k] = r;
+          cs[k] += round_to<T>(r);
         }
         V16<T>::store(op + e + u * step, v[u]);
       }
+  }
+  if (colsum) {  // column sums of the stored dx = bias gradient of the convolution in front of the ReLU / norm
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) smc[threadIdx.x * VEC + k] = cs[k];
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += 256) {
+      float d0 = 0.f;
+      for (int i = c; i < 256 * VEC; i += C) d0 += smc[i];
+      atomicAdd(colsum + c, d0);
+    }
   }
 }
 
@@ -314,19 +333,38 @@ static int in_blocks(long long per_sample, int vec, int N) {
   return (int)(want < 1 ? 1 : want);
 }
 
+// (sum a, sum a * b-ish) per (n, c) into `out` (zeroed here): mode 0 / 2 of in_partial_kernel, for the callers in dispatch.cu
+int omr_in_partial_sums(int dt, int mode, const void* a, const void* xin, double* out, int N, int HW, int C, cudaStream_t st) {
+  const int vec = dt == OMR_BF16 ? 8 : 4;
+  OMR_REQUIRE(C >= vec && C % vec == 0 && (256 * vec) % C == 0, "instnorm sums: unsupported channel count %d", C);
+  OMR_CUDA(cudaMemsetAsync(out, 0, sizeof(double) * (size_t)N * C * 2, st));
+  if ((long long)N * HW * C <= 0) return OMR_OK;
+  const long long per = (long long)HW * C;
+  dim3 grid((unsigned)in_blocks(per, vec, N), (unsigned)N);
+  if (mode == 0) {
+    OMR_DISPATCH_DT(dt, T, (OmrLaunch(grid, 256, 0, st)(in_partial_kernel<T, 0>, (const T*)a, nullptr, nullptr, out, per, C)));
+  } else {
+    OMR_DISPATCH_DT(dt, T, (OmrLaunch(grid, 256, 0, st)(in_partial_kernel<T, 2>, (const T*)a, (const T*)xin, nullptr, out, per, C)));
+  }
+  OMR_LAUNCHED();
+  return OMR_OK;
+}
+
 extern "C" int omr_instnorm_fwd(int dt, const void* x, void* y, float* stats, double* ws, int N, int HW, int C,
-                                float eps, omr_stream_t stream) {
+                                float eps, int sums_ready, omr_stream_t stream) {
   const int vec = dt == OMR_BF16 ? 8 : 4;
   OMR_REQUIRE(C >= vec && C % vec == 0 && (256 * vec) % C == 0, "omr_instnorm_fwd: unsupported channel count %d", C);
   OMR_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0,
               "omr_instnorm_fwd: x and y must be 16-byte aligned");
   if ((long long)N * HW * C <= 0) return OMR_OK;
   cudaStream_t st = as_stream(stream);
-  OMR_CUDA(cudaMemsetAsync(ws, 0, sizeof(double) * (size_t)N * C * 2, st));
   const long long per = (long long)HW * C;
   dim3 grid((unsigned)in_blocks(per, vec, N), (unsigned)N);
-  OMR_DISPATCH_DT(dt, T, (OmrLaunch(grid, 256, 0, st)(in_partial_kernel<T, 0>, (const T*)x, nullptr, nullptr, ws, per, C)));
-  OMR_LAUNCHED();
+  if (!sums_ready) {  // otherwise ws already holds (sum x, sum x^2): omr_conv3x3_fwd accumulated them in its epilogue
+    OMR_CUDA(cudaMemsetAsync(ws, 0, sizeof(double) * (size_t)N * C * 2, st));
+    OMR_DISPATCH_DT(dt, T, (OmrLaunch(grid, 256, 0, st)(in_partial_kernel<T, 0>, (const T*)x, nullptr, nullptr, ws, per, C)));
+    OMR_LAUNCHED();
+  }
   OmrLaunch((int)cdiv((long long)N * C, 256), 256, 0, st)(in_finalize_kernel, ws, stats, (long long)N * C, 1.0 / HW,
                                                                                 (double)eps);
   OMR_LAUNCHED();
@@ -336,7 +374,8 @@ extern "C" int omr_instnorm_fwd(int dt, const void* x, void* y, float* stats, do
 }
 
 extern "C" int omr_instnorm_bwd(int dt, const void* dy, const void* x, const float* stats, void* dx, double* ws, int N,
-                                int HW, int C, int relu_mask, float mask_scale, omr_stream_t stream) {
+                                int HW, int C, int relu_mask, float mask_scale, int sums_ready, float* colsum,
+                                omr_stream_t stream) {
   const int vec = dt == OMR_BF16 ? 8 : 4;
   OMR_REQUIRE(C >= vec && C % vec == 0 && (256 * vec) % C == 0, "omr_instnorm_bwd: unsupported channel count %d", C);
   OMR_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(dy) & 15) == 0 &&
@@ -344,13 +383,15 @@ extern "C" int omr_instnorm_bwd(int dt, const void* dy, const void* x, const flo
               "omr_instnorm_bwd: dy, x and dx must be 16-byte aligned");
   if ((long long)N * HW * C <= 0) return OMR_OK;
   cudaStream_t st = as_stream(stream);
-  OMR_CUDA(cudaMemsetAsync(ws, 0, sizeof(double) * (size_t)N * C * 2, st));
   const long long per = (long long)HW * C;
   dim3 grid((unsigned)in_blocks(per, vec, N), (unsigned)N);
-  OMR_DISPATCH_DT(dt, T, (OmrLaunch(grid, 256, 0, st)(in_partial_kernel<T, 1>, (const T*)dy, (const T*)x, stats, ws, per, C)));
-  OMR_LAUNCHED();
+  if (!sums_ready) {  // otherwise ws holds the RAW sums (sum dy, sum dy * x) from omr_conv3x3_dgrad's epilogue
+    OMR_CUDA(cudaMemsetAsync(ws, 0, sizeof(double) * (size_t)N * C * 2, st));
+    OMR_DISPATCH_DT(dt, T, (OmrLaunch(grid, 256, 0, st)(in_partial_kernel<T, 1>, (const T*)dy, (const T*)x, stats, ws, per, C)));
+    OMR_LAUNCHED();
+  }
   OMR_DISPATCH_DT(dt, T, (OmrLaunch(grid, 256, 0, st)(in_apply_bwd_kernel<T>, (const T*)dy, (const T*)x, stats, ws, (T*)dx, per, C,
-                                                                      1.0 / HW, relu_mask, mask_scale)));
+                                                                      1.0 / HW, relu_mask, mask_scale, sums_ready ? 1 : 0, colsum)));
   OMR_LAUNCHED();
   return OMR_OK;
 }

@@ -79,13 +79,17 @@ class _Act:
     ReLU/dropout into its own gradient kernel (conv data-gradient epilogue, InstanceNorm backward): the consumer multiplies
     its dx by (x > 0 ? scale : 0), where x = the tensor it consumed -- zeros of x cover both inactive and dropped elements,
     scale is the dropout's 1/(1-p).  ``premasked`` is set by such a consumer at forward time; the producer's backward
-    closures read it at backward time and skip their relu_bwd / dropout-backward kernels."""
+    closures read it at backward time and skip their relu_bwd / dropout-backward kernels.  The masked dx IS the gradient of
+    the producer's pre-activation, so the same consumer kernel also accumulates its column sums = the producer's BIAS
+    gradient (``bias`` is registered by the producer, ``db_done`` set by the consumer at backward time)."""
 
-    __slots__ = ("premasked", "scale")
+    __slots__ = ("premasked", "scale", "bias", "db_done")
 
     def __init__(self) -> None:
         self.premasked = False
         self.scale = 1.0
+        self.bias = None
+        self.db_done = False
 
 
 def _maybe_dropout(x: torch.Tensor, c: _Ctx, here: bool, act: Optional[_Act] = None, inplace_bwd: bool = True) -> torch.Tensor:
@@ -110,14 +114,28 @@ def _maybe_dropout(x: torch.Tensor, c: _Ctx, here: bool, act: Optional[_Act] = N
     return y
 
 
+def _bias_target(act: Optional[_Act]) -> Optional[torch.Tensor]:
+    """backward time: the bias-gradient buffer of the layer that produced the tensor described by ``act``, to be filled by
+    the consumer's gradient kernel (and marked done), or None"""
+    if act is None or act.bias is None or not act.bias.requires_grad:
+        return None
+    act.db_done = True
+    return grad_buf(act.bias)
+
+
 def _conv_step(x: torch.Tensor, cp: ConvParams, stride: Tuple[int, int], relu: bool, c: _Ctx, need_dx: bool,
-               x_act: Optional[_Act] = None, y_act: Optional[_Act] = None) -> torch.Tensor:
+               x_act: Optional[_Act] = None, y_act: Optional[_Act] = None, in_sums: Optional[torch.Tensor] = None,
+               norm_link: Optional[dict] = None) -> torch.Tensor:
     """x_act: x is a ReLU(+dropout) output whose backward this conv's data gradient fuses; y_act: record for this conv's
-    own ReLU output, filled in by whoever consumes it."""
+    own ReLU output, filled in by whoever consumes it.  in_sums: receives the InstanceNorm statistics of the output (conv2
+    of a block).  norm_link (conv3 of a block): x is an InstanceNorm output; the data gradient then also accumulates that
+    norm's backward sums (``norm_link["x"]`` = the norm's input) into ``norm_link["bsums"]``."""
     wp = c.cache.get(cp.weight, "conv", c.dtype)
-    y = ops.conv3x3_fwd(x, wp, cp.bias, stride, relu)
+    y = ops.conv3x3_fwd(x, wp, cp.bias, stride, relu, in_sums=in_sums)
     if relu:
         ops._probe_relu(y)
+    if y_act is not None:
+        y_act.bias = cp.bias
     if c.tape is not None:
         in_hw = (x.shape[1], x.shape[2])
         fuse = FUSE_RELU_BWD and x_act is not None and need_dx
@@ -129,27 +147,45 @@ def _conv_step(x: torch.Tensor, cp: ConvParams, stride: Tuple[int, int], relu: b
             if relu and not (y_act is not None and y_act.premasked):
                 dz = ops.relu_bwd(y, dy, inplace=True)
             if cp.weight.requires_grad:
-                gw, gb = grad_buf(cp.weight), grad_buf(cp.bias)
+                gw = grad_buf(cp.weight)
+                gb = None if (y_act is not None and y_act.db_done) else grad_buf(cp.bias)  # done by the consumer's kernel
                 _off_chain(c, lambda: ops.conv3x3_wgrad(x, dz, gw, gb, stride, accumulate=True), x, dz)
             if not need_dx:
                 return None
             wt = c.cache.get(cp.weight, "convT", c.dtype)
             if fuse:
-                return ops.conv3x3_dgrad(dz, wt, in_hw, stride, mask=x, mask_scale=x_act.scale)
+                return ops.conv3x3_dgrad(dz, wt, in_hw, stride, mask=x, mask_scale=x_act.scale, colsum=_bias_target(x_act))
+            if norm_link is not None and FUSE_NORM_SUMS:
+                bs = ops.in_sums_buffer(x.shape[0], x.shape[3], x.device)
+                norm_link["bsums"] = bs
+                return ops.conv3x3_dgrad(dz, wt, in_hw, stride, in_x=norm_link["x"], in_bsums=bs)
             return ops.conv3x3_dgrad(dz, wt, in_hw, stride)
 
         c.tape.append(bwd)
     return y
 
 
-def _instnorm_step(x: torch.Tensor, c: _Ctx, x_act: Optional[_Act] = None) -> torch.Tensor:
-    y, stats = ops.instnorm_fwd(x, IN_EPS)
+FUSE_NORM_SUMS = True  # tests flip this to compare against the separate InstanceNorm statistics / reduction passes
+
+
+def _instnorm_step(x: torch.Tensor, c: _Ctx, x_act: Optional[_Act] = None, sums: Optional[torch.Tensor] = None,
+                   norm_link: Optional[dict] = None) -> torch.Tensor:
+    """sums: (sum x, sum x^2) already accumulated by the convolution that produced x; norm_link: filled by the consumer
+    convolution's data gradient with the backward sums (see _conv_step)"""
+    y, stats = ops.instnorm_fwd(x, IN_EPS, sums=sums)
+    if norm_link is not None:
+        norm_link["x"] = x
     if c.tape is not None:
+
+        def bwd(dy: torch.Tensor) -> torch.Tensor:
+            bs = norm_link.pop("bsums", None) if norm_link is not None else None
+            if FUSE_RELU_BWD and x_act is not None:
+                return ops.instnorm_bwd(dy, x, stats, relu_mask=True, mask_scale=x_act.scale, sums=bs, colsum=_bias_target(x_act))
+            return ops.instnorm_bwd(dy, x, stats, sums=bs)
+
         if FUSE_RELU_BWD and x_act is not None:
             x_act.premasked = True
-            c.tape.append(lambda dy: ops.instnorm_bwd(dy, x, stats, relu_mask=True, mask_scale=x_act.scale))
-        else:
-            c.tape.append(lambda dy: ops.instnorm_bwd(dy, x, stats))
+        c.tape.append(bwd)
     return y
 
 
@@ -242,10 +278,15 @@ class ConvBlock(nn.Module):
         a1, a2 = _Act(), _Act()
         x = _conv_step(x, self.conv1, (1, 1), True, c, need_dx, x_act=x_act, y_act=a1)
         x = _maybe_dropout(x, c, pos == 1, a1)
-        x = _conv_step(x, self.conv2, (1, 1), True, c, True, x_act=a1, y_act=a2)
+        # the InstanceNorm statistics come out of conv2's epilogue unless a dropout sits between the two (the norm then
+        # sees the dropped tensor); the norm's backward sums come out of conv3's data gradient
+        drop2 = pos == 2 and c.training and c.dropout.p > 0.0
+        sums = ops.in_sums_buffer(x.shape[0], self.conv2.out_channels, x.device) if (FUSE_NORM_SUMS and not drop2) else None
+        link: dict = {}
+        x = _conv_step(x, self.conv2, (1, 1), True, c, True, x_act=a1, y_act=a2, in_sums=sums)
         x = _maybe_dropout(x, c, pos == 2, a2)
-        x = _instnorm_step(x, c, x_act=a2)
-        x = _conv_step(x, self.conv3, self.stride, True, c, True, y_act=out_act)
+        x = _instnorm_step(x, c, x_act=a2, sums=sums, norm_link=link)
+        x = _conv_step(x, self.conv3, self.stride, True, c, True, y_act=out_act, norm_link=link)
         x = _maybe_dropout(x, c, pos == 3, out_act)
         return x
 

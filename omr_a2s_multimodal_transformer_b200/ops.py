@@ -99,30 +99,42 @@ def pack_dw_weight(w: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
 
 
 # ---- convolutions ---------------------------------------------------------------------------------
-def conv3x3_fwd(x, wp, bias, stride=(1, 1), relu=False):
-    """x [N,H,W,Ci], wp [Co,3,3,Ci] (packed), bias fp32 [Co] -> y [N,Ho,Wo,Co]"""
+def conv3x3_fwd(x, wp, bias, stride=(1, 1), relu=False, in_sums=None):
+    """x [N,H,W,Ci], wp [Co,3,3,Ci] (packed), bias fp32 [Co] -> y [N,Ho,Wo,Co].
+    in_sums (fp64 [N,Co,2]): receives (sum y, sum y^2) per (sample, channel) -- the statistics of the InstanceNorm that
+    follows -- from the convolution's own epilogue (``instnorm_fwd(..., sums=in_sums)`` then skips its statistics pass)"""
     _chk(x, "conv3x3_fwd.x"), _chk(wp, "conv3x3_fwd.w")
     n, h, w, ci = x.shape
     co = wp.shape[0]
     ho, wo = out_hw(h, w, stride)
     y = torch.empty((n, ho, wo, co), dtype=x.dtype, device=x.device)
     call("omr_conv3x3_fwd", dt_code(x.dtype), ptr(x), ptr(wp), ptr(bias), ptr(y), n, h, w, ci, co, stride[0], stride[1],
-         int(relu), stream_ptr())
+         int(relu), ptr(in_sums), stream_ptr())
     return y
 
 
-def conv3x3_dgrad(dy, wpt, in_hw, stride=(1, 1), mask=None, mask_scale: float = 1.0):
+def in_sums_buffer(n: int, c: int, device) -> torch.Tensor:
+    """fp64 [N,C,2] scratch for per-(sample, channel) InstanceNorm sums"""
+    return torch.empty((n, c, 2), dtype=torch.float64, device=device)
+
+
+def conv3x3_dgrad(dy, wpt, in_hw, stride=(1, 1), mask=None, mask_scale: float = 1.0, colsum=None, in_x=None, in_bsums=None):
     """dy [N,Ho,Wo,Co], wpt [Ci,3,3,Co] -> dx [N,H,W,Ci]; with ``mask`` (the conv's forward input, a ReLU/dropout output)
-    the backward of that ReLU/dropout is fused: dx = mask > 0 ? dx * mask_scale : 0"""
+    the backward of that ReLU/dropout is fused: dx = mask > 0 ? dx * mask_scale : 0.
+    colsum (fp32 [Ci]): += column sums of dx (bias gradient of the layer that produced the conv's input);
+    in_x + in_bsums (fp64 [N,Ci,2]): dx is the gradient of an InstanceNorm output, in_x that norm's input: in_bsums receives
+    the raw backward sums (sum dx, sum dx * in_x) for ``instnorm_bwd(..., sums=in_bsums)``"""
     _chk(dy, "conv3x3_dgrad.dy"), _chk(wpt, "conv3x3_dgrad.w")
     if mask is not None:
         _chk(mask, "conv3x3_dgrad.mask")
+    if in_x is not None:
+        _chk(in_x, "conv3x3_dgrad.in_x")
     n, _, _, co = dy.shape
     ci = wpt.shape[0]
     h, w = in_hw
     dx = torch.empty((n, h, w, ci), dtype=dy.dtype, device=dy.device)
     call("omr_conv3x3_dgrad", dt_code(dy.dtype), ptr(dy), ptr(wpt), ptr(dx), n, h, w, ci, co, stride[0], stride[1],
-         ptr(mask), float(mask_scale), stream_ptr())
+         ptr(mask), float(mask_scale), ptr(colsum), ptr(in_x), ptr(in_bsums), stream_ptr())
     return dx
 
 
@@ -158,25 +170,29 @@ def dwconv3x3_wgrad(x, dy, dw, db, accumulate=True):
          stream_ptr())
 
 
-def instnorm_fwd(x, eps: float):
-    """x [N,H,W,C] -> (y, stats [N,C,2] fp32 = (mean, rstd))"""
+def instnorm_fwd(x, eps: float, sums=None):
+    """x [N,H,W,C] -> (y, stats [N,C,2] fp32 = (mean, rstd)); ``sums``: (sum x, sum x^2) already accumulated by the
+    convolution that produced x (``conv3x3_fwd(..., in_sums=)``)"""
     _chk(x, "instnorm_fwd.x")
     n, h, w, c = x.shape
     y = torch.empty_like(x)
     stats = torch.empty((n, c, 2), dtype=torch.float32, device=x.device)
-    ws = torch.empty((n, c, 2), dtype=torch.float64, device=x.device)
-    call("omr_instnorm_fwd", dt_code(x.dtype), ptr(x), ptr(y), ptr(stats), ptr(ws), n, h * w, c, float(eps), stream_ptr())
+    ws = torch.empty((n, c, 2), dtype=torch.float64, device=x.device) if sums is None else sums
+    call("omr_instnorm_fwd", dt_code(x.dtype), ptr(x), ptr(y), ptr(stats), ptr(ws), n, h * w, c, float(eps),
+         int(sums is not None), stream_ptr())
     return y, stats
 
 
-def instnorm_bwd(dy, x, stats, relu_mask: bool = False, mask_scale: float = 1.0):
-    """relu_mask: x is a ReLU (+dropout) output and the backward of that ReLU/dropout is fused into the result"""
+def instnorm_bwd(dy, x, stats, relu_mask: bool = False, mask_scale: float = 1.0, sums=None, colsum=None):
+    """relu_mask: x is a ReLU (+dropout) output and the backward of that ReLU/dropout is fused into the result;
+    ``sums``: raw backward sums (sum dy, sum dy * x) from ``conv3x3_dgrad(..., in_x=x, in_bsums=)``;
+    colsum (fp32 [C]): += column sums of dx (bias gradient of the convolution in front of the norm)"""
     _chk(dy, "instnorm_bwd.dy"), _chk(x, "instnorm_bwd.x")
     n, h, w, c = x.shape
     dx = torch.empty_like(x)
-    ws = torch.empty((n, c, 2), dtype=torch.float64, device=x.device)
+    ws = torch.empty((n, c, 2), dtype=torch.float64, device=x.device) if sums is None else sums
     call("omr_instnorm_bwd", dt_code(x.dtype), ptr(dy), ptr(x), ptr(stats), ptr(dx), ptr(ws), n, h * w, c, int(relu_mask),
-         float(mask_scale), stream_ptr())
+         float(mask_scale), int(sums is not None), ptr(colsum), stream_ptr())
     return dx
 
 

@@ -478,3 +478,39 @@ def test_decoder_train_mode_gradients_with_the_kernels_own_dropout_masks(monkeyp
     rep = grad_report(m, dec_g)
     assert not rep["missing"], rep
     assert rep["global_rel"] < 2e-4 and rep["cos"] > 1 - 1e-6, rep
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-5), (torch.bfloat16, 2e-2)])
+@pytest.mark.parametrize("train", [False, True])
+def test_encoder_fused_norm_sums_and_bias_gradients_match_separate_passes(monkeypatch, dtype, tol, train):
+    """InstanceNorm statistics from conv2's epilogue, the norm's backward sums from conv3's data gradient and the bias
+    gradients from the consumers' gradient kernels (encoder.FUSE_NORM_SUMS, _Act.db_done) against the separate reduction /
+    column-sum passes: same output, same parameter gradients (bf16: the two paths differ only in summation order of fp32
+    partial sums, so the gradients agree far inside the bf16 noise; the bound is the model tests' bf16 gradient tolerance)."""
+    import random
+
+    import omr_a2s_multimodal_transformer_b200 as pkg
+    from omr_a2s_multimodal_transformer_b200 import encoder as enc_mod
+
+    results = []
+    x = torch.rand(3, 1, 80, 264, generator=torch.Generator().manual_seed(3)).to(DEV)
+    for fused in (False, True):
+        monkeypatch.setattr(enc_mod, "FUSE_NORM_SUMS", fused)
+        random.seed(11)
+        enc = pkg.Encoder(1)
+        enc.load_state_dict(synth.synth_state_dict(enc.state_dict(), seed=5))
+        enc = enc.to(DEV)
+        enc.train(train)
+        enc.compute_dtype = dtype
+        out = enc(x)
+        gy = torch.randn(out.shape, generator=torch.Generator().manual_seed(4)).to(DEV).to(out.dtype)
+        out.backward(gy)
+        torch.cuda.synchronize()
+        results.append((out.detach().float().cpu(), {k: p.grad.detach().double().cpu() for k, p in enc.named_parameters()}))
+    (o0, g0), (o1, g1) = results
+    assert rel_err(o1, o0) < tol
+    num = sum(float((g1[k] - g0[k]).pow(2).sum()) for k in g0)
+    den = sum(float(g0[k].pow(2).sum()) for k in g0)
+    assert (num / den) ** 0.5 < tol, (num / den) ** 0.5
+    worst = max(float((g1[k] - g0[k]).norm() / (g0[k].norm() + 1e-12)) for k in g0 if k.endswith("bias") and float(g0[k].norm()) > 1e-3 * den ** 0.5)
+    assert worst < 5 * tol, worst

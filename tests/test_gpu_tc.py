@@ -144,6 +144,72 @@ def test_conv3x3_tc_fwd_dgrad(ops, case):
     assert rel_err(dx.permute(0, 3, 1, 2).float(), gx_ref) < 6e-3
 
 
+# a larger multi-sample case per channel width so that a CTA's contiguous tile range crosses sample boundaries (flushes)
+FUSED_CASES = CONV_TC_CASES + [(5, 40, 384, 16, 16, (1, 1)), (6, 33, 260, 32, 32, (1, 1)), (5, 24, 200, 64, 64, (1, 1)),
+                               (4, 30, 150, 32, 32, (2, 2)), (3, 21, 131, 64, 64, (2, 2))]
+
+
+@pytest.mark.parametrize("case", FUSED_CASES)
+def test_conv3x3_fused_epilogue_sums(ops, case):
+    """The per-channel reductions accumulated in the convolution epilogues equal the same sums taken over the STORED
+    result: InstanceNorm statistics with the forward (in_sums), bias-gradient column sums (colsum, with the fused ReLU mask)
+    and InstanceNorm backward sums (in_bsums) with the data gradient.  C > 64 takes the separate-pass fallback: same contract."""
+    n, h, w, ci, co, st = case
+    x = rnd(n, h, w, ci, seed=31).bfloat16().relu()
+    wt = rnd(co, ci, 3, 3, seed=32, scale=1.0 / math.sqrt(9 * ci))
+    b = rnd(co, seed=33, scale=0.1)
+    wp = ops.pack_conv_weight(wt.contiguous(), torch.bfloat16, False)
+    wpt = ops.pack_conv_weight(wt.contiguous(), torch.bfloat16, True)
+    # forward + statistics
+    y_plain = ops.conv3x3_fwd(x, wp, b, st, relu=True)
+    sums = ops.in_sums_buffer(n, co, DEV)
+    sums.fill_(float("nan"))  # the entry point must initialise it
+    y = ops.conv3x3_fwd(x, wp, b, st, relu=True, in_sums=sums)
+    assert torch.equal(y, y_plain)
+    yd = y.double()
+    want = torch.stack([yd.sum(dim=(1, 2)), (yd * yd).sum(dim=(1, 2))], dim=-1)
+    assert rel_err(sums, want) < 2e-6
+    # data gradient + bias-gradient column sums (mask = the conv's forward input, a ReLU output)
+    ho, wo = y.shape[1], y.shape[2]
+    dy = rnd(n, ho, wo, co, seed=34).bfloat16()
+    dx_plain = ops.conv3x3_dgrad(dy, wpt, (h, w), st, mask=x, mask_scale=2.0)
+    col = torch.full((ci,), 3.0, device=DEV)
+    dx = ops.conv3x3_dgrad(dy, wpt, (h, w), st, mask=x, mask_scale=2.0, colsum=col)
+    assert torch.equal(dx, dx_plain)
+    assert rel_err(col - 3.0, dx.double().sum(dim=(0, 1, 2))) < 1e-4  # fp32 atomics into a buffer that starts at 3.0
+    # data gradient + InstanceNorm backward sums
+    xin = rnd(n, h, w, ci, seed=35).bfloat16()
+    bs = ops.in_sums_buffer(n, ci, DEV)
+    bs.fill_(float("nan"))
+    dx2_plain = ops.conv3x3_dgrad(dy, wpt, (h, w), st)
+    dx2 = ops.conv3x3_dgrad(dy, wpt, (h, w), st, in_x=xin, in_bsums=bs)
+    assert torch.equal(dx2, dx2_plain)
+    d2 = dx2.double()
+    want_b = torch.stack([d2.sum(dim=(1, 2)), (d2 * xin.double()).sum(dim=(1, 2))], dim=-1)
+    assert float((bs - want_b).abs().max()) < 2e-5 * float(want_b.abs().max()) + 1e-6
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("c,hw", [(16, (40, 384)), (64, (24, 200)), (128, (9, 33))])
+def test_instnorm_with_sums_from_the_convolutions(ops, dtype, c, hw):
+    """instnorm_fwd / instnorm_bwd fed with the sums the convolution epilogues produce (sums_ready) == their own reduction passes"""
+    n = 3
+    x = rnd(n, hw[0], hw[1], c, seed=41).to(dtype).relu()
+    dy = rnd(n, hw[0], hw[1], c, seed=42).to(dtype)
+    y0, st0 = ops.instnorm_fwd(x, 1e-3)
+    xd = x.double()
+    sums = torch.stack([xd.sum(dim=(1, 2)), (xd * xd).sum(dim=(1, 2))], dim=-1).contiguous()
+    y1, st1 = ops.instnorm_fwd(x, 1e-3, sums=sums)
+    assert rel_err(st1, st0) < 1e-6 and rel_err(y1.float(), y0.float()) < (1e-6 if dtype == torch.float32 else 4e-3)
+    dx0 = ops.instnorm_bwd(dy, x, st0, relu_mask=True, mask_scale=2.0)
+    dd = dy.double()
+    bsums = torch.stack([dd.sum(dim=(1, 2)), (dd * xd).sum(dim=(1, 2))], dim=-1).contiguous()
+    col = torch.zeros(c, device=DEV)
+    dx1 = ops.instnorm_bwd(dy, x, st0, relu_mask=True, mask_scale=2.0, sums=bsums, colsum=col)
+    assert rel_err(dx1.float(), dx0.float()) < (2e-5 if dtype == torch.float32 else 4e-3)
+    assert float((col.double() - dx1.double().sum(dim=(0, 1, 2))).abs().max()) < 1e-4 * float(dx1.double().abs().sum(dim=(0, 1, 2)).max())
+
+
 @pytest.mark.parametrize("case", CONV_TC_CASES + [(4, 64, 512, 16, 16, (1, 1)), (2, 32, 256, 64, 128, (2, 2)), (2, 20, 70, 32, 16, (1, 1)),
                                                   (3, 17, 99, 32, 32, (1, 1))])
 def test_conv3x3_tc_wgrad(ops, case):
