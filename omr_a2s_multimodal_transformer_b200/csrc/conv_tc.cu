@@ -9,21 +9,22 @@
 //   exactly the K-major UMMA operand layout; the weight slice [Cout x chunk] of the tap is the B operand;
 // * persistent CTAs (one per SM), each owning a CONTIGUOUS range of output tiles; the fp32 accumulator lives in TMEM and
 //   is double buffered, so the epilogue of tile i overlaps the TMA/MMA main loop of tile i+1;
-// * the same kernels compute the data gradient: stride 1 -> taps mirrored, weights from the [Ci,3,3,Co] pack;
-//   stride 2 -> one launch per output parity class (1, 2, 2 or 4 taps each), written with a strided epilogue.
+// * the same kernels compute the data gradient: stride 1 -> taps mirrored, weights from the [Ci,3,3,Co] pack; stride 2 ->
+//   ONE launch over the dy grid (a fractionally-strided convolution: grid pixel (i, j) produces its sh x sw output pixels,
+//   one accumulator per output parity class) when the channel counts allow, else one launch per parity class.
 //
 // Warp roles (320 threads): 0-7 epilogue, 8 TMA producer, 9 MMA issuer + TMEM allocator.  Producer and issuer run their
-// loops warp-wide on uniform values with the instruction under elect_one() (tc_common.cuh).  The epilogue was the
-// bottleneck of the narrow (C = 16 / 32) layers when it had ONE warp per SM sub-partition (measured: ~2100 clk per 512-pixel
-// tile, instruction-latency bound): it now has two warps per sub-partition -- warps w and w + 4 share the TMEM lanes
-// 32 (w & 3) .. + 31 and split a tile's (row, 16-channel chunk) units between them -- batches its TMEM loads, takes the
-// bias from shared memory and does ReLU / masking on packed bf16 pairs.
+// loops warp-wide on uniform values with the instruction under elect_one() (tc_common.cuh).
 //
-// Output path: the epilogue packs its bf16 results into a shared-memory staging tile laid out [out row][out col][channel] in
-// the TMA swizzle of the pixel width (conflict-free 16-byte stores: a lane = a pixel = a staging row), and one elected thread
-// writes the tile with a TMA store (cp.async.bulk.tensor ... bulk_group; edge tiles are clipped by the TMA unit).  Direct
-// per-lane 32-byte global stores touched one 128-byte line per lane and instruction for C >= 32.  Two staging buffers
-// alternate when shared memory allows.  (Strided parity-class launches of the generic kernel keep direct stores.)
+// The epilogue is what bounds the narrow (C = 16 / 32) high-resolution layers (ncu, round 2: 85 % of the executed
+// instructions of the first version were address arithmetic, parameter re-loads and branches on run-time flags; ~550 clk per
+// 16-channel unit and warp).  It is therefore specialised at compile time -- NCHUNK = Cout / 16, EPI = what is applied
+// (bias + ReLU | fused ReLU/dropout-backward mask | nothing), MODE = which per-channel sums are accumulated -- keeps the
+// bias in registers, walks tile coordinates and offsets incrementally (no divisions, 32-bit deltas), keeps two TMEM loads in
+// flight and works on packed bf16 pairs.  Two warps per SM sub-partition: warps w and w + 4 share the TMEM lanes
+// 32 (w & 3) .. + 31 and split a tile's (row, 16-channel chunk) units.
+// (A staged TMA-store epilogue -- swizzled shared-memory tile + cp.async.bulk.tensor store -- was built and measured in
+// round 2: no gain over the direct 2 x 16-byte stores per lane, so it was removed again.)
 //
 // Fused per-channel reductions in the epilogue (MODE, output channels <= 64), accumulated per thread over the CTA's tile
 // range and flushed with one atomic per (warp, channel) when the sample changes:
@@ -44,6 +45,7 @@ using namespace tc;
 constexpr int MAX_TAPS = 9;
 constexpr int NTHREADS = 320;
 constexpr int EPI_WARPS = 8, W_TMA = 8, W_MMA = 9;
+constexpr int EPI_FWD = 0, EPI_MASK = 1, EPI_PLAIN = 2;
 
 struct ConvTcArgs {
   bf16* y;
@@ -62,23 +64,17 @@ struct ConvTcArgs {
   // (TH + box_hr) x (TW + box_wr) pixels.  Plain stride-1 convolution: ncls = 1, box = (-1, -1, 2, 2).
   int ncls, tap_cls[MAX_TAPS], tap_first[MAX_TAPS], cls_ph[4], cls_pw[4];
   int box_h0, box_w0, box_hr, box_wr;
-  const bf16* mask;                // optional: out = mask > 0 ? out * mask_scale : 0 (same layout as y)
+  const bf16* mask;                // EPI_MASK: out = mask > 0 ? out * mask_scale : 0 (same layout as y)
   float mask_scale;
   // fused reductions (see the header): exactly one of them is non-null in MODE 1 / 2 / 3
   double* in_sums;     // MODE 1: [N][Cout][2] += (sum y, sum y^2)
   float* colsum;       // MODE 2: [Cout] += sum y
   const bf16* in_x;    // MODE 3: the InstanceNorm input (same layout as y) ...
   double* in_bsums;    //         ... and [N][Cout][2] += (sum y, sum y * x)
-  // staged output: staging tile of st_rows x st_cols output pixels (0 = direct global stores), st_bufs buffers of st_bytes
-  int st_rows, st_cols, st_bufs, st_bytes;
-  long long* dbg;      // OMR_CONV_DEBUG & 8: clock64() stamps of CTA 0 / epilogue warp 0 (halo kernel): [tile][8]
+  // generic kernel: pipeline geometry (run-time, so that the kernel is instantiated per epilogue only)
+  int rb, G, a_sub, b_sub, stage_bytes, stages;
   int debug;           // OMR_CONV_DEBUG (diagnostics, results are WRONG when set): 1 = no MMAs, 2 = no TMA loads, 4 = no global stores
 };
-
-#define DBG_STAMP(it, k)                                                                                   \
-  do {                                                                                                     \
-    if (g.dbg && blockIdx.x == 0 && threadIdx.x == 0 && (it) < 64) g.dbg[(it) * 8 + (k)] = clock64(); \
-  } while (0)
 
 // ---- epilogue building blocks ---------------------------------------------------------------------------------------
 // contiguous, balanced tile range of this CTA
@@ -89,44 +85,41 @@ __device__ __forceinline__ void tile_range(int num_tiles, int& t0, int& cnt) {
   cnt = base + (b < rem ? 1 : 0);
 }
 
-// One (pixel, 16-channel chunk) unit: fp32 accumulators -> (+bias, ReLU | mask) -> bf16 -> global, plus the fused sums.
-// a0 / a1: this chunk's 16 per-thread accumulators (MODE != 0).
-// sdst: the pixel's row in the staging tile (nullptr: store to global), c0: first channel of the unit.
-template <int MODE>
-__device__ __forceinline__ void epi_unit(const ConvTcArgs& g, const uint32_t (&v)[16], long long off, const float* sbias, bool ok,
-                                         float* a0, float* a1, uint8_t* sdst, int spix, int c0) {
-  if (!ok) return;
-  float f[16];
-#pragma unroll
-  for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
-  if (g.bias) {
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const float4 b4 = reinterpret_cast<const float4*>(sbias)[q];
-      f[4 * q] += b4.x; f[4 * q + 1] += b4.y; f[4 * q + 2] += b4.z; f[4 * q + 3] += b4.w;
-    }
-  }
+__device__ __forceinline__ uint4 ldg16(const bf16* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+
+// Per-thread epilogue state that does not change over the kernel: the bias of this warp's chunks (registers), the ReLU floor,
+// the mask scale, and the per-thread partial sums of the fused reductions.
+template <int NCHUNK, int MODE>
+struct EpiRegs {
+  static constexpr int K = NCHUNK == 1 ? 1 : NCHUNK / 2;  // chunks per warp half
+  static constexpr int KA = MODE == 0 ? 1 : (K > 2 ? 2 : K);
+  float bias[K][16];
+  float a0[KA][16], a1[KA][16];
+};
+
+// One (pixel, 16-channel chunk) unit: fp32 accumulators -> (+bias, ReLU | mask | nothing) -> bf16 -> global, plus the sums.
+template <int EPI, int MODE>
+__device__ __forceinline__ void epi_unit(const uint32_t (&v)[16], const float (&b)[16], __nv_bfloat162 floor2, float mscale,
+                                         const bf16* __restrict__ maskp, const bf16* __restrict__ xinp, bf16* __restrict__ dst,
+                                         bool store, float (&a0)[16], float (&a1)[16]) {
   __nv_bfloat162 h[8];
-  if (g.mask) {  // fused ReLU / dropout backward of the layer that produced this conv's forward input
-    const uint4 m0 = reinterpret_cast<const uint4*>(g.mask + off)[0];
-    const uint4 m1 = reinterpret_cast<const uint4*>(g.mask + off)[1];
+  if (EPI == EPI_FWD) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      h[j] = __hmax2(__floats2bfloat162_rn(__uint_as_float(v[2 * j]) + b[2 * j], __uint_as_float(v[2 * j + 1]) + b[2 * j + 1]), floor2);
+  } else if (EPI == EPI_MASK) {
+    const uint4 m0 = ldg16(maskp), m1 = ldg16(maskp + 8);
     const __nv_bfloat162* mb0 = reinterpret_cast<const __nv_bfloat162*>(&m0);
     const __nv_bfloat162* mb1 = reinterpret_cast<const __nv_bfloat162*>(&m1);
     const __nv_bfloat162 zero = __float2bfloat162_rn(0.f);
-    const float sc = g.mask_scale;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      h[j] = __hmul2(__floats2bfloat162_rn(f[2 * j] * sc, f[2 * j + 1] * sc), __hgt2(mb0[j], zero));
-      h[4 + j] = __hmul2(__floats2bfloat162_rn(f[8 + 2 * j] * sc, f[8 + 2 * j + 1] * sc), __hgt2(mb1[j], zero));
+    for (int j = 0; j < 8; ++j) {
+      const __nv_bfloat162 m = j < 4 ? mb0[j] : mb1[j - 4];
+      h[j] = __hmul2(__floats2bfloat162_rn(__uint_as_float(v[2 * j]) * mscale, __uint_as_float(v[2 * j + 1]) * mscale), __hgt2(m, zero));
     }
   } else {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) h[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
-    if (g.relu) {
-      const __nv_bfloat162 zero = __float2bfloat162_rn(0.f);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) h[j] = __hmax2(h[j], zero);
-    }
+    for (int j = 0; j < 8; ++j) h[j] = __floats2bfloat162_rn(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
   }
   if (MODE == 1) {
 #pragma unroll
@@ -142,8 +135,7 @@ __device__ __forceinline__ void epi_unit(const ConvTcArgs& g, const uint32_t (&v
       a0[2 * j + 1] += __high2float(h[j]);
     }
   } else if (MODE == 3) {
-    const uint4 x0 = reinterpret_cast<const uint4*>(g.in_x + off)[0];
-    const uint4 x1 = reinterpret_cast<const uint4*>(g.in_x + off)[1];
+    const uint4 x0 = ldg16(xinp), x1 = ldg16(xinp + 8);
     const __nv_bfloat162* xb0 = reinterpret_cast<const __nv_bfloat162*>(&x0);
     const __nv_bfloat162* xb1 = reinterpret_cast<const __nv_bfloat162*>(&x1);
 #pragma unroll
@@ -154,165 +146,261 @@ __device__ __forceinline__ void epi_unit(const ConvTcArgs& g, const uint32_t (&v
       a1[2 * j] = fmaf(lo, __low2float(xv), a1[2 * j]); a1[2 * j + 1] = fmaf(hi, __high2float(xv), a1[2 * j + 1]);
     }
   }
-  if (sdst) {
-    // staging row = min(Cout, 64) channels (rb bytes) in the TMA swizzle of that width: 16-byte chunk index XOR the
-    // address bits [7, 7 + log2(rb / 16)); Cout = 128: two sub-tiles of 64 channels
-    const int rb = g.Cout >= 64 ? 128 : g.Cout * 2;
-    const int key = rb == 128 ? (spix & 7) : (rb == 64 ? ((spix >> 1) & 3) : ((spix >> 2) & 1));
-    const int cc = (c0 & 63) >> 3;
-    uint8_t* row = sdst + (c0 >> 6) * (g.st_bytes >> 1) + (long long)spix * rb;
-    *reinterpret_cast<uint4*>(row + ((cc ^ key) << 4)) = *reinterpret_cast<const uint4*>(&h[0]);
-    *reinterpret_cast<uint4*>(row + (((cc + 1) ^ key) << 4)) = *reinterpret_cast<const uint4*>(&h[4]);
-  } else if (!(g.debug & 4)) {
-    uint4* d4 = reinterpret_cast<uint4*>(g.y + off);
+  if (store) {
+    uint4* d4 = reinterpret_cast<uint4*>(dst);
     d4[0] = *reinterpret_cast<const uint4*>(&h[0]);
     d4[1] = *reinterpret_cast<const uint4*>(&h[4]);
   }
 }
 
 // add this warp's per-thread partial sums of sample n to the global accumulators and clear them
-template <int MODE>
-__device__ __forceinline__ void epi_flush(const ConvTcArgs& g, int n, int hf, int nchunk, int lane, float (&a0)[32], float (&a1)[32]) {
+template <int NCHUNK, int MODE>
+__device__ __forceinline__ void epi_flush(const ConvTcArgs& g, int n, int hf, int lane, EpiRegs<NCHUNK, MODE>& e) {
   if (MODE == 0) return;
+  constexpr int Cout = NCHUNK * 16;
 #pragma unroll
-  for (int k = 0; k < 2; ++k) {
-    const int chunk = nchunk == 1 ? 0 : hf + 2 * k;
-    if (chunk < nchunk && (nchunk > 1 || k == 0)) {
+  for (int k = 0; k < EpiRegs<NCHUNK, MODE>::KA; ++k) {
+    const int chunk = NCHUNK == 1 ? 0 : hf + 2 * k;
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const float s0 = warp_sum(a0[k * 16 + j]);
-        const float s1 = (MODE == 2) ? 0.f : warp_sum(a1[k * 16 + j]);
-        if (lane == j) {
-          const int c = chunk * 16 + j;
-          if (MODE == 1) {
-            atomicAdd(g.in_sums + ((long long)n * g.Cout + c) * 2, (double)s0);
-            atomicAdd(g.in_sums + ((long long)n * g.Cout + c) * 2 + 1, (double)s1);
-          } else if (MODE == 2) {
-            atomicAdd(g.colsum + c, s0);
-          } else {
-            atomicAdd(g.in_bsums + ((long long)n * g.Cout + c) * 2, (double)s0);
-            atomicAdd(g.in_bsums + ((long long)n * g.Cout + c) * 2 + 1, (double)s1);
+    for (int j = 0; j < 16; ++j) {
+      const float s0 = warp_sum(e.a0[k][j]);
+      const float s1 = (MODE == 2) ? 0.f : warp_sum(e.a1[k][j]);
+      if (lane == j) {
+        const int c = chunk * 16 + j;
+        if (MODE == 1) {
+          atomicAdd(g.in_sums + ((long long)n * Cout + c) * 2, (double)s0);
+          atomicAdd(g.in_sums + ((long long)n * Cout + c) * 2 + 1, (double)s1);
+        } else if (MODE == 2) {
+          atomicAdd(g.colsum + c, s0);
+        } else {
+          atomicAdd(g.in_bsums + ((long long)n * Cout + c) * 2, (double)s0);
+          atomicAdd(g.in_bsums + ((long long)n * Cout + c) * 2 + 1, (double)s1);
+        }
+      }
+      e.a0[k][j] = 0.f;
+      e.a1[k][j] = 0.f;
+    }
+  }
+}
+
+template <int NCHUNK, int MODE>
+__device__ __forceinline__ void epi_init(const ConvTcArgs& g, int hf, EpiRegs<NCHUNK, MODE>& e) {
+  using E = EpiRegs<NCHUNK, MODE>;
+#pragma unroll
+  for (int k = 0; k < E::K; ++k) {
+    const int chunk = NCHUNK == 1 ? 0 : hf + 2 * k;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) e.bias[k][j] = g.bias ? __ldg(g.bias + chunk * 16 + j) : 0.f;
+  }
+#pragma unroll
+  for (int k = 0; k < E::KA; ++k)
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      e.a0[k][j] = 0.f;
+      e.a1[k][j] = 0.f;
+    }
+}
+
+// The epilogue of one tile: `rows` accumulator blocks of 128 pixels x Cout channels in TMEM at t_base (+ rr * Cout).
+// Warp (q = warp & 3, hf = warp >> 2), lane -> TMEM lane 32 q + lane of every block; the (block, 16-channel chunk) units are
+// dealt to the two halves: NCHUNK = 1 -> blocks alternate, NCHUNK >= 2 -> chunk parity = hf (a thread's accumulators and bias
+// registers belong to fixed channels).  unit(rr, ok, off): validity and element offset (32-bit, relative to base) of this
+// thread's pixel of block rr.  Two TMEM loads are in flight per wait.
+template <int NCHUNK, int EPI, int MODE, typename OffFn>
+__device__ __forceinline__ void epi_tile(const ConvTcArgs& g, uint32_t t_base, int rows, int q, int hf, long long base, bool st_ok,
+                                         __nv_bfloat162 floor2, EpiRegs<NCHUNK, MODE>& e, OffFn unit) {
+  constexpr int Cout = NCHUNK * 16;
+  const uint32_t t_lane = t_base + ((uint32_t)(q * 32) << 16);
+  bf16* const yb = g.y + base;
+  const bf16* const mb = EPI == EPI_MASK ? g.mask + base : nullptr;
+  const bf16* const xb = MODE == 3 ? g.in_x + base : nullptr;
+  const float msc = g.mask_scale;
+  if (NCHUNK == 1) {
+    for (int rr = hf; rr < rows; rr += 4) {  // blocks rr and rr + 2 in flight
+      uint32_t v0[16], v1[16];
+      const bool two = rr + 2 < rows;
+      tmem_ld16(t_lane + (uint32_t)(rr * 16), v0);
+      if (two) tmem_ld16(t_lane + (uint32_t)((rr + 2) * 16), v1);
+      bool ok0, ok1 = false;
+      int o0, o1 = 0;
+      unit(rr, ok0, o0);
+      if (two) unit(rr + 2, ok1, o1);
+      tmem_ld_wait();
+      if (ok0) epi_unit<EPI, MODE>(v0, e.bias[0], floor2, msc, mb + o0, xb + o0, yb + o0, st_ok, e.a0[0], e.a1[0]);
+      if (ok1) epi_unit<EPI, MODE>(v1, e.bias[0], floor2, msc, mb + o1, xb + o1, yb + o1, st_ok, e.a0[0], e.a1[0]);
+    }
+  } else {
+    constexpr int K = NCHUNK / 2;
+    for (int rr = 0; rr < rows; ++rr) {
+      bool ok;
+      int o;
+      unit(rr, ok, o);
+      const uint32_t t_row = t_lane + (uint32_t)(rr * Cout) + (uint32_t)(hf * 16);
+#pragma unroll
+      for (int k = 0; k < K; k += 2) {  // chunks hf + 2k and hf + 2k + 2 in flight
+        uint32_t v0[16], v1[16];
+        tmem_ld16(t_row + (uint32_t)(k * 32), v0);
+        if (k + 1 < K) tmem_ld16(t_row + (uint32_t)(k * 32 + 32), v1);
+        tmem_ld_wait();
+        if (ok) {
+          const int c0 = o + (hf + 2 * k) * 16;
+          constexpr int KA = EpiRegs<NCHUNK, MODE>::KA;
+          epi_unit<EPI, MODE>(v0, e.bias[k], floor2, msc, mb + c0, xb + c0, yb + c0, st_ok, e.a0[k < KA ? k : 0], e.a1[k < KA ? k : 0]);
+          if (k + 1 < K)
+            epi_unit<EPI, MODE>(v1, e.bias[k + 1 < K ? k + 1 : 0], floor2, msc, mb + c0 + 32, xb + c0 + 32, yb + c0 + 32, st_ok,
+                                e.a0[k + 1 < KA ? k + 1 : 0], e.a1[k + 1 < KA ? k + 1 : 0]);
+        }
+      }
+    }
+  }
+}
+
+// MMA issuer of the halo kernel: warp-uniform loop, tcgen05.mma / commit under elect_one().  NJ = k-steps (of 16 channels) per tap.
+template <int NJ, int Cout>
+__device__ __forceinline__ void halo_mma_role(const ConvTcArgs& g, uint8_t* sW, uint8_t* sH, int wsub, int hsub, int stages, int pitch,
+                                              int TH, uint32_t acc_cols, uint32_t tmem_base, int t0, int tcnt, uint64_t* w_full,
+                                              uint64_t* full_bar, uint64_t* empty_bar, uint64_t* tfull_bar, uint64_t* tempty_bar) {
+  (void)t0;
+  constexpr int RB = NJ * 32;
+  const uint32_t idesc = make_idesc_bf16(128, Cout, 0, 0);
+  const uint64_t d_hi = make_smem_desc(0, 16, 8 * RB, RB);
+  // per-tap start offsets inside the halo (A) and the weight bank (B), in 16-byte units
+  uint32_t ta[9], tb[9], tc_[9], tf[9];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    const int tt = t < g.ntaps ? t : 0;
+    ta[t] = (uint32_t)(((g.dh[tt] - g.box_h0) * pitch + (g.dw[tt] - g.box_w0)) * RB) >> 4;
+    tb[t] = (uint32_t)(g.widx[tt] * wsub) >> 4;
+    tc_[t] = (uint32_t)(g.tap_cls[tt] * Cout);  // TMEM column offset of the tap's class inside a row's accumulators
+    tf[t] = (uint32_t)g.tap_first[tt];
+  }
+  const uint32_t row_step = (uint32_t)(pitch * RB) >> 4;
+  const uint32_t cout = (uint32_t)(g.ncls * Cout);
+  const int ntaps = g.ntaps;
+  const bool no_mma = (g.debug & 1) != 0;
+  mbar_wait(w_full, 0);
+  const uint32_t w_lo = smem_u32(sW) >> 4;
+  const uint32_t h_base = smem_u32(sH) >> 4, h_step = (uint32_t)hsub >> 4;
+  int s = 0;
+  uint32_t ph = 0;  // parity to wait for on full_bar[s]
+  for (int i = 0; i < tcnt; ++i) {
+    const uint32_t a = i & 1, aph = (i >> 1) & 1;
+    mbar_wait(&tempty_bar[a], aph ^ 1);
+    mbar_wait(&full_bar[s], ph);
+    tc_fence_after();
+    const uint32_t h_lo = h_base + (uint32_t)s * h_step;
+    const uint32_t d0 = tmem_base + a * acc_cols;
+    if (elect_one()) {
+      if (!no_mma) {
+        for (int r = 0; r < TH; ++r) {
+          const uint32_t d_tmem = d0 + (uint32_t)r * cout;
+          const uint32_t hr = h_lo + (uint32_t)r * row_step;
+#pragma unroll
+          for (int t = 0; t < 9; ++t) {
+            if (t < ntaps) {
+#pragma unroll
+              for (int j = 0; j < NJ; ++j) {
+                if (j > 0)
+                  umma_bf16_acc(d_tmem + tc_[t], d_hi | (uint64_t)(hr + ta[t] + 2 * j), d_hi | (uint64_t)(w_lo + tb[t] + 2 * j), idesc);
+                else
+                  umma_bf16(d_tmem + tc_[t], d_hi | (uint64_t)(hr + ta[t]), d_hi | (uint64_t)(w_lo + tb[t]), idesc, tf[t] ^ 1u);
+              }
+            }
           }
         }
       }
+      umma_commit(&empty_bar[s]);
+      umma_commit(&tfull_bar[a]);
     }
-#pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      a0[k * 16 + j] = 0.f;
-      a1[k * 16 + j] = 0.f;
+    __syncwarp();
+    if (++s == stages) {
+      s = 0;
+      ph ^= 1;
     }
   }
 }
 
-// The epilogue of one tile: `rows` accumulator rows of 128 pixels x Cout channels in TMEM at t_base (+ r * Cout).
-// Warp (q = warp & 3, hf = warp >> 2), lane -> pixel column px = 32 q + lane of every row; the (row, chunk) units are dealt
-// to the two halves: Cout = 16 -> rows alternate, Cout >= 32 -> chunk parity = hf (so a thread's accumulators belong to fixed
-// channels).  pix(r, ok) gives the element offset of (row r, this thread's pixel, channel 0) in y and whether it exists.
-template <int MODE, typename PixFn>
-__device__ __forceinline__ void epi_tile(const ConvTcArgs& g, uint32_t t_base, int rows, int q, int hf, const float* sbias, PixFn pix,
-                                         float (&a0)[32], float (&a1)[32], uint8_t* sdst) {
-  const int nchunk = g.Cout >> 4;
-  const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-  if (nchunk == 1) {
-    for (int r = hf; r < rows; r += 4) {  // two rows in flight (r, r + 2)
-      uint32_t v0[16], v1[16];
-      const bool two = r + 2 < rows;
-      tmem_ld16(t_base + lane_addr + (uint32_t)(r * 16), v0);
-      if (two) tmem_ld16(t_base + lane_addr + (uint32_t)((r + 2) * 16), v1);
-      tmem_ld_wait();
-      bool ok;
-      int spix;
-      long long off = pix(r, ok, spix);
-      epi_unit<MODE>(g, v0, off, sbias, ok, a0, a1, sdst, spix, 0);
-      if (two) {
-        off = pix(r + 2, ok, spix);
-        epi_unit<MODE>(g, v1, off, sbias, ok, a0, a1, sdst, spix, 0);
-      }
-    }
-  } else {
-    for (int r = 0; r < rows; ++r) {
-      bool ok;
-      int spix;
-      const long long off = pix(r, ok, spix);
-      const uint32_t t_row = t_base + lane_addr + (uint32_t)(r * g.Cout);
+// MMA issuer of the generic kernel (NJ k-steps per sub-tile, G sub-tiles per stage: the host picks G = 3 for 32/64-byte rows, 1 for 128)
+template <int NJ, int G, int Cout>
+__device__ __forceinline__ void generic_mma_role(const ConvTcArgs& g, uint8_t* smem, int nsub, int ngroups, uint32_t tmem_base, int tcnt,
+                                                 uint64_t* full_bar, uint64_t* empty_bar, uint64_t* tfull_bar, uint64_t* tempty_bar) {
+  constexpr int RB = NJ * 32;
+  const uint32_t idesc = make_idesc_bf16(128, Cout, 0, 0);
+  const uint64_t d_hi = make_smem_desc(0, 16, 8 * RB, RB);
+  const uint32_t smem_lo = smem_u32(smem) >> 4;
+  const uint32_t a_sub16 = (uint32_t)g.a_sub >> 4, b_sub16 = (uint32_t)g.b_sub >> 4, st16 = (uint32_t)g.stage_bytes >> 4;
+  const int STAGES = g.stages;
+  int s = 0;
+  uint32_t ph = 0;
+  for (int i = 0; i < tcnt; ++i) {
+    const uint32_t a = i & 1, aph = (i >> 1) & 1;
+    mbar_wait(&tempty_bar[a], aph ^ 1);
+    tc_fence_after();
+    const uint32_t d_tmem = tmem_base + a * (uint32_t)Cout;
+    for (int grp = 0; grp < ngroups; ++grp) {
+      mbar_wait(&full_bar[s], ph);
+      tc_fence_after();
+      const int sub0 = grp * G;
+      const int cnt = (nsub - sub0) < G ? (nsub - sub0) : G;
+      const uint32_t stage = smem_lo + (uint32_t)s * st16;
+      if (elect_one()) {
 #pragma unroll
-      for (int k = 0; k < 4; k += 2) {  // chunks hf + 2k and hf + 2k + 2 in flight
-        const int c0 = (hf + 2 * k) * 16;
-        if (hf + 2 * k < nchunk) {
-          const bool two = hf + 2 * k + 2 < nchunk;
-          uint32_t v0[16], v1[16];
-          tmem_ld16(t_row + (uint32_t)c0, v0);
-          if (two) tmem_ld16(t_row + (uint32_t)(c0 + 32), v1);
-          tmem_ld_wait();
-          // per-thread accumulators exist for a warp's first two chunks only (MODE != 0 requires Cout <= 64: k = 0)
-          epi_unit<MODE>(g, v0, off + c0, sbias + c0, ok, &a0[0], &a1[0], sdst, spix, c0);
-          if (two) epi_unit<MODE>(g, v1, off + c0 + 32, sbias + c0 + 32, ok, &a0[16], &a1[16], sdst, spix, c0 + 32);
+        for (int q = 0; q < G; ++q) {
+          if (q < cnt) {
+            const uint32_t a_addr = stage + q * a_sub16;
+            const uint32_t b_addr = stage + G * a_sub16 + q * b_sub16;
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) {
+              if (q == 0 && j == 0)
+                umma_bf16(d_tmem, d_hi | (uint64_t)(a_addr), d_hi | (uint64_t)(b_addr), idesc, grp == 0 ? 0u : 1u);
+              else
+                umma_bf16_acc(d_tmem, d_hi | (uint64_t)(a_addr + 2 * j), d_hi | (uint64_t)(b_addr + 2 * j), idesc);
+            }
+          }
         }
+        umma_commit(&empty_bar[s]);
+        if (grp == ngroups - 1) umma_commit(&tfull_bar[a]);
+      }
+      __syncwarp();
+      if (++s == STAGES) {
+        s = 0;
+        ph ^= 1;
       }
     }
   }
 }
 
-// staging buffer hand-over among the 8 epilogue warps (256 threads, named barrier 1); thread 0 issues and tracks the stores
-__device__ __forceinline__ void stage_acquire(const ConvTcArgs& g) {
-  if (threadIdx.x == 0) {
-    if (g.st_bufs > 1) tma_store_wait_read<1>();
-    else tma_store_wait_read<0>();
-  }
-  named_barrier(1, EPI_WARPS * 32);
-}
-__device__ __forceinline__ void stage_store(const ConvTcArgs& g, const CUtensorMap* tmY, const uint8_t* buf, int ow0, int oh0, int n) {
-  fence_proxy_async();
-  named_barrier(1, EPI_WARPS * 32);
-  if (threadIdx.x == 0) {
-    if (!(g.debug & 4)) {
-      tma_store_4d(tmY, buf, 0, ow0, oh0, n);
-      if (g.Cout > 64) tma_store_4d(tmY, buf + (g.st_bytes >> 1), 64, ow0, oh0, n);
-    }
-    tma_store_commit();
-  }
-}
-
-// RB: row bytes (= 2 * min(Cin, 64)); G: (tap, chunk) sub-tiles per pipeline stage
-template <int RB, int G>
-struct Cfg {
-  static constexpr int A_SUB = 128 * RB;
-  static constexpr int B_SUB = ((128 * RB) + 1023) / 1024 * 1024;  // room for Cout <= 128 rows, 1 KB aligned
-  static constexpr int STAGE = G * (A_SUB + B_SUB);
-  static constexpr int STAGES = (STAGE * 4 <= 160 * 1024) ? 4 : (STAGE * 3 <= 160 * 1024 ? 3 : 2);
-  static constexpr int OUT_STAGE = 2 * 128 * 128 * 2;  // two staging tiles of 128 pixels x <= 128 channels
-  static constexpr int SMEM = STAGES * STAGE + OUT_STAGE + 1024 + 1024;
-};
-
-template <int RB, int G, int MODE>
+// ---------------------------------------------------------------------------------------------------------------
+// Generic tap-GEMM kernel: one 128-pixel TH x TW patch per tile, every (tap, 64-channel chunk) sub-tile fetched by its own
+// TMA box (strided convolutions, C_in = 128, parity-class data gradients).  Pipeline geometry (rb = row bytes, G sub-tiles
+// per stage, stage count) is passed at run time so that the kernel is instantiated per epilogue only.
+// ---------------------------------------------------------------------------------------------------------------
+template <int NCHUNK, int EPI>
 __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap tmX,
-                                                              const __grid_constant__ CUtensorMap tmW,
-                                                              const __grid_constant__ CUtensorMap tmY, ConvTcArgs g) {
+                                                              const __grid_constant__ CUtensorMap tmW, ConvTcArgs g) {
   omr_pdl_enter();
-  using C = Cfg<RB, G>;
-  constexpr int STAGES = C::STAGES;
+  constexpr int Cout = NCHUNK * 16;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sOut = smem + STAGES * C::STAGE;  // staging tiles (1 KB aligned)
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sOut + C::OUT_STAGE);
+  const int STAGES = g.stages;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * g.stage_bytes);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;  // [2] accumulator ready
   uint64_t* tempty_bar = tfull_bar + 2;      // [2] accumulator drained
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-  float* sbias = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~uintptr_t(15));  // [128], 16-byte aligned
 
   const int warp = (int)warp_idx_sync(), lane = threadIdx.x & 31;
+  const int RB = g.rb, G = g.G;
   const int chunks = (g.Cin * 2 + RB - 1) / RB;  // 64-channel chunks per tap (1 or 2)
   const int nsub = g.ntaps * chunks;
   const int ngroups = (nsub + G - 1) / G;
-  const uint32_t tmem_cols = g.Cout * 2 <= 32 ? 32 : (g.Cout * 2 <= 64 ? 64 : (g.Cout * 2 <= 128 ? 128 : 256));
+  constexpr uint32_t tmem_cols = Cout * 2 <= 32 ? 32 : (Cout * 2 <= 64 ? 64 : (Cout * 2 <= 128 ? 128 : 256));
   int t0, tcnt;
   tile_range(g.num_tiles, t0, tcnt);
 
   if (warp == W_TMA && lane == 0) {
     tma_prefetch_desc(&tmX);
     tma_prefetch_desc(&tmW);
-    if (g.st_rows) tma_prefetch_desc(&tmY);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -324,23 +412,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_const
     fence_barrier_init();
   }
   if (warp == W_MMA) tmem_alloc(tmem_slot, tmem_cols);
-  if (threadIdx.x < 128) sbias[threadIdx.x] = (g.bias && (int)threadIdx.x < g.Cout) ? g.bias[threadIdx.x] : 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = bcast0(*tmem_slot);
   const uint32_t a_box_bytes = (uint32_t)(g.TH * g.TW) * RB;
-  const uint32_t b_box_bytes = (uint32_t)g.Cout * RB;
+  const uint32_t b_box_bytes = (uint32_t)Cout * RB;
 
   if (warp == W_TMA) {
     // ---- TMA producer: warp-uniform loop, one elected lane issues ----
     int s = 0;
     uint32_t ph = 1;
+    int tw = t0 % g.tiles_w, th = (t0 / g.tiles_w) % g.tiles_h, n = t0 / (g.tiles_w * g.tiles_h);
     for (int i = 0; i < tcnt; ++i) {
-      const int tile = t0 + i;
-      const int tw = tile % g.tiles_w;
-      const int th = (tile / g.tiles_w) % g.tiles_h;
-      const int n = tile / (g.tiles_w * g.tiles_h);
       const int oh0 = th * g.TH, ow0 = tw * g.TW;
       for (int grp = 0; grp < ngroups; ++grp) {
         mbar_wait(&empty_bar[s], ph);
@@ -348,111 +432,69 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_const
         const int cnt = (nsub - sub0) < G ? (nsub - sub0) : G;
         if (elect_one()) {
           mbar_expect_tx(&full_bar[s], (uint32_t)cnt * (a_box_bytes + b_box_bytes));
-          uint8_t* stage = smem + s * C::STAGE;
+          uint8_t* stage = smem + s * g.stage_bytes;
           for (int q = 0; q < cnt; ++q) {
             const int sub = sub0 + q;
             const int tap = sub / chunks, ch = sub - tap * chunks;
             const int c0 = ch * (RB / 2);
-            tma_load_4d(stage + q * C::A_SUB, &tmX, &full_bar[s], c0, ow0 * g.isw + g.dw[tap], oh0 * g.ish + g.dh[tap], n);
-            tma_load_2d(stage + G * C::A_SUB + q * C::B_SUB, &tmW, &full_bar[s], g.widx[tap] * g.Cin + c0, 0);
+            tma_load_4d(stage + q * g.a_sub, &tmX, &full_bar[s], c0, ow0 * g.isw + g.dw[tap], oh0 * g.ish + g.dh[tap], n);
+            tma_load_2d(stage + G * g.a_sub + q * g.b_sub, &tmW, &full_bar[s], g.widx[tap] * g.Cin + c0, 0);
           }
         }
         __syncwarp();
         if (++s == STAGES) {
           s = 0;
           ph ^= 1;
+        }
+      }
+      if (++tw == g.tiles_w) {
+        tw = 0;
+        if (++th == g.tiles_h) {
+          th = 0;
+          ++n;
         }
       }
     }
   } else if (warp == W_MMA) {
-    // ---- MMA issuer: warp-uniform loop, tcgen05.mma / commit under elect_one() ----
-    const uint32_t idesc = make_idesc_bf16(128, g.Cout, 0, 0);
-    const uint64_t d_hi = make_smem_desc(0, 16, 8 * RB, RB);
-    const uint32_t smem_lo = smem_u32(smem) >> 4;
-    int s = 0;
-    uint32_t ph = 0;
-    for (int i = 0; i < tcnt; ++i) {
-      const uint32_t a = i & 1, aph = (i >> 1) & 1;
-      mbar_wait(&tempty_bar[a], aph ^ 1);
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_base + a * (uint32_t)g.Cout;
-      for (int grp = 0; grp < ngroups; ++grp) {
-        mbar_wait(&full_bar[s], ph);
-        tc_fence_after();
-        const int sub0 = grp * G;
-        const int cnt = (nsub - sub0) < G ? (nsub - sub0) : G;
-        const uint32_t stage = smem_lo + (uint32_t)s * (C::STAGE >> 4);
-        if (elect_one()) {
-#pragma unroll
-          for (int q = 0; q < G; ++q) {
-            if (q < cnt) {
-              const uint32_t a_addr = stage + q * (C::A_SUB >> 4);
-              const uint32_t b_addr = stage + (G * C::A_SUB + q * C::B_SUB) / 16;
-#pragma unroll
-              for (int j = 0; j < RB / 32; ++j) {
-                if (grp == 0 && q == 0 && j == 0)
-                  umma_bf16_new(d_tmem, d_hi | (uint64_t)(a_addr + 2 * j), d_hi | (uint64_t)(b_addr + 2 * j), idesc);
-                else
-                  umma_bf16_acc(d_tmem, d_hi | (uint64_t)(a_addr + 2 * j), d_hi | (uint64_t)(b_addr + 2 * j), idesc);
-              }
-            }
-          }
-          umma_commit(&empty_bar[s]);
-          if (grp == ngroups - 1) umma_commit(&tfull_bar[a]);
-        }
-        __syncwarp();
-        if (++s == STAGES) {
-          s = 0;
-          ph ^= 1;
-        }
-      }
-    }
+    // ---- MMA issuer: warp-uniform loop specialised on (k-steps per sub-tile, sub-tiles per stage) ----
+    if (RB == 32) generic_mma_role<1, 3, Cout>(g, smem, nsub, ngroups, tmem_base, tcnt, full_bar, empty_bar, tfull_bar, tempty_bar);
+    else if (RB == 64) generic_mma_role<2, 3, Cout>(g, smem, nsub, ngroups, tmem_base, tcnt, full_bar, empty_bar, tfull_bar, tempty_bar);
+    else generic_mma_role<4, 1, Cout>(g, smem, nsub, ngroups, tmem_base, tcnt, full_bar, empty_bar, tfull_bar, tempty_bar);
   } else {
     // ---- epilogue: thread = one output pixel of the TH x TW patch, its Cout channels split between warps w and w + 4 ----
     const int q = warp & 3, hf = warp >> 2;
     const int r = q * 32 + lane;  // tile row = pixel index inside the patch
     const int pr = r / g.TW, pc = r - pr * g.TW;
-    float a0[32], a1[32];
-#pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      a0[j] = 0.f;
-      a1[j] = 0.f;
-    }
-    int cur_n = -1;
+    EpiRegs<NCHUNK, 0> e;
+    epi_init<NCHUNK, 0>(g, hf, e);
+    const __nv_bfloat162 floor2 = __float2bfloat162_rn(g.relu ? 0.f : -INFINITY);
+    const bool st_ok = !(g.debug & 4);
+    int tw = t0 % g.tiles_w, th = (t0 / g.tiles_w) % g.tiles_h, n = t0 / (g.tiles_w * g.tiles_h);
     for (int i = 0; i < tcnt; ++i) {
       const uint32_t a = i & 1, aph = (i >> 1) & 1;
-      const int tile = t0 + i;
-      const int tw = tile % g.tiles_w;
-      const int th = (tile / g.tiles_w) % g.tiles_h;
-      const int n = tile / (g.tiles_w * g.tiles_h);
-      if (MODE != 0 && MODE != 2 && n != cur_n) {
-        if (cur_n >= 0) epi_flush<MODE>(g, cur_n, hf, g.Cout >> 4, lane, a0, a1);
-        cur_n = n;
-      }
       const int gh = th * g.TH + pr, gw = tw * g.TW + pc;
       const int oh = gh * g.osh + g.oph, ow = gw * g.osw + g.opw;
       const bool okp = pr < g.TH && gh < g.GH && gw < g.GW && oh < g.OH && ow < g.OW;
-      const long long offp = (((long long)n * g.OH + oh) * g.OW + ow) * g.Cout;
-      uint8_t* sbuf = g.st_rows ? sOut + (i % g.st_bufs) * g.st_bytes : nullptr;
-      if (g.st_rows) stage_acquire(g);
+      const long long offp = (((long long)n * g.OH + oh) * g.OW + ow) * Cout;
       mbar_wait(&tfull_bar[a], aph);
       tc_fence_after();
-      // the patch is ONE accumulator row block: with Cout = 16 only the hf = 0 warps have a unit (rows = 1); the staging
-      // tile is the patch itself (pixel r of the patch = staging pixel r)
-      epi_tile<MODE>(g, tmem_base + a * (uint32_t)g.Cout, 1, q, hf, sbias,
-                     [&](int, bool& ok, int& spix) {
-                       ok = okp;
-                       spix = r;
-                       return offp;
-                     },
-                     a0, a1, sbuf);
+      // the patch is ONE accumulator block: with Cout = 16 only the hf = 0 warps have a unit
+      epi_tile<NCHUNK, EPI, 0>(g, tmem_base + a * (uint32_t)Cout, 1, q, hf, okp ? offp : 0, st_ok, floor2, e,
+                               [&](int, bool& ok, int& o) {
+                                 ok = okp;
+                                 o = 0;
+                               });
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[a]);
-      if (g.st_rows) stage_store(g, &tmY, sbuf, tw * g.TW, th * g.TH, n);
+      if (++tw == g.tiles_w) {
+        tw = 0;
+        if (++th == g.tiles_h) {
+          th = 0;
+          ++n;
+        }
+      }
     }
-    if (MODE != 0 && (MODE == 2 || cur_n >= 0)) epi_flush<MODE>(g, cur_n, hf, g.Cout >> 4, lane, a0, a1);
-    if (g.st_rows && threadIdx.x == 0) tma_store_wait_all();
   }
   tc_fence_before();
   __syncthreads();
@@ -463,36 +505,33 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_const
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Halo variant for stride-1 convolutions with C_in <= 64 (the high-resolution layers, which are bound by HBM / L2->SM
-// traffic, not by the tensor cores): per tile of TH output rows x TW pixels ONE TMA box brings the (TH+2) x (TW+2)
-// input pixels, and the nine taps are nine UMMA descriptors whose start address is shifted by whole pixel rows
-// ((dh+1)*(TW+2) + (dw+1) rows of RB bytes) inside that box -- the swizzle is a function of the shared-memory
-// address, so a row-shifted window of a TMA-written tile is still a valid K-major operand.  All nine weight taps
-// stay resident in shared memory for the life of the persistent CTA.
+// Halo variant for C_in <= 64 (the high-resolution layers, which are bound by HBM / L2->SM traffic and by the epilogue, not by
+// the tensor cores): per tile of TH grid rows x TW pixels ONE TMA box brings the (TH + box_hr) x (TW + box_wr) input pixels,
+// and the taps are UMMA descriptors whose start address is shifted by whole pixel rows inside that box -- the swizzle is a
+// function of the shared-memory address, so a row-shifted window of a TMA-written tile is still a valid K-major operand.
+// All nine weight taps stay resident in shared memory for the life of the persistent CTA.
 // ---------------------------------------------------------------------------------------------------------------
-template <int RB, int MODE>
+template <int NCHUNK, int EPI, int MODE>
 __global__ void __launch_bounds__(NTHREADS, 1) conv_halo_kernel(const __grid_constant__ CUtensorMap tmX,
-                                                                const __grid_constant__ CUtensorMap tmW,
-                                                                const __grid_constant__ CUtensorMap tmY, ConvTcArgs g, int wsub,
+                                                                const __grid_constant__ CUtensorMap tmW, ConvTcArgs g, int wsub,
                                                                 int hsub, int stages) {
   omr_pdl_enter();
+  constexpr int Cout = NCHUNK * 16;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sW = smem;                // 9 taps x wsub
   uint8_t* sH = smem + 9 * wsub;     // stages x hsub
-  uint8_t* sOut = sH + stages * hsub;  // st_bufs x st_bytes staging tiles (1 KB aligned)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sOut + g.st_bufs * g.st_bytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sH + stages * hsub);
   uint64_t* w_full = bars;
   uint64_t* full_bar = bars + 1;
   uint64_t* empty_bar = full_bar + stages;
   uint64_t* tfull_bar = empty_bar + stages;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-  float* sbias = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~uintptr_t(15));  // [128], 16-byte aligned
 
   const int warp = (int)warp_idx_sync(), lane = threadIdx.x & 31;
-  const int TH = g.TH;
-  const uint32_t acc_cols = (uint32_t)(TH * g.ncls * g.Cout);  // per accumulator buffer: one [128 x Cout] block per (row, class)
+  const int TH = g.TH, RB = g.rb;
+  const uint32_t acc_cols = (uint32_t)(TH * g.ncls * Cout);  // per accumulator buffer: one [128 x Cout] block per (row, class)
   const uint32_t need = 2 * acc_cols;
   const uint32_t tmem_cols = need <= 32 ? 32 : (need <= 64 ? 64 : (need <= 128 ? 128 : (need <= 256 ? 256 : 512)));
   const int pitch = g.TW + g.box_wr;  // pixel rows per input image row inside the halo box
@@ -502,7 +541,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_halo_kernel(const __grid_con
   if (warp == W_TMA && lane == 0) {
     tma_prefetch_desc(&tmX);
     tma_prefetch_desc(&tmW);
-    if (g.st_rows) tma_prefetch_desc(&tmY);
     mbar_init(w_full, 1);
     for (int s = 0; s < stages; ++s) {
       mbar_init(&full_bar[s], 1);
@@ -515,7 +553,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_halo_kernel(const __grid_con
     fence_barrier_init();
   }
   if (warp == W_MMA) tmem_alloc(tmem_slot, tmem_cols);
-  if (threadIdx.x < 128) sbias[threadIdx.x] = (g.bias && (int)threadIdx.x < g.Cout) ? g.bias[threadIdx.x] : 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -524,22 +561,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_halo_kernel(const __grid_con
   if (warp == W_TMA) {
     // ---- TMA producer: the whole warp walks the tiles (uniform state), one elected lane issues ----
     if (elect_one()) {
-      mbar_expect_tx(w_full, 9u * (uint32_t)g.Cout * RB);
+      mbar_expect_tx(w_full, 9u * (uint32_t)Cout * (uint32_t)RB);
       for (int t = 0; t < 9; ++t) tma_load_2d(sW + t * wsub, &tmW, w_full, t * g.Cin, 0);
     }
     int s = 0;
     uint32_t ph = 1;  // parity to wait for on empty_bar[s]
+    int tw = t0 % g.tiles_w, th = (t0 / g.tiles_w) % g.tiles_h, n = t0 / (g.tiles_w * g.tiles_h);
+    const uint32_t box_bytes = (uint32_t)(TH + g.box_hr) * (uint32_t)pitch * (uint32_t)RB;
     for (int i = 0; i < tcnt; ++i) {
-      const int tile = t0 + i;
-      const int tw = tile % g.tiles_w;
-      const int th = (tile / g.tiles_w) % g.tiles_h;
-      const int n = tile / (g.tiles_w * g.tiles_h);
       mbar_wait(&empty_bar[s], ph);
       if (elect_one()) {
         if (g.debug & 2) {
           mbar_arrive(&full_bar[s]);
         } else {
-          mbar_expect_tx(&full_bar[s], (uint32_t)(TH + g.box_hr) * (uint32_t)pitch * RB);
+          mbar_expect_tx(&full_bar[s], box_bytes);
           tma_load_4d(sH + s * hsub, &tmX, &full_bar[s], 0, tw * g.TW + g.box_w0, th * TH + g.box_h0, n);
         }
       }
@@ -548,119 +583,79 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_halo_kernel(const __grid_con
         s = 0;
         ph ^= 1;
       }
+      if (++tw == g.tiles_w) {
+        tw = 0;
+        if (++th == g.tiles_h) {
+          th = 0;
+          ++n;
+        }
+      }
     }
   } else if (warp == W_MMA) {
-    // ---- MMA issuer: warp-uniform loop, tcgen05.mma / commit under elect_one() ----
-    const uint32_t idesc = make_idesc_bf16(128, g.Cout, 0, 0);
-    const uint64_t d_hi = make_smem_desc(0, 16, 8 * RB, RB);
-    // per-tap start offsets inside the halo (A) and the weight bank (B), in 16-byte units
-    uint32_t ta[9], tb[9], tc_[9], tf[9];
-#pragma unroll
-    for (int t = 0; t < 9; ++t) {
-      const int tt = t < g.ntaps ? t : 0;
-      ta[t] = (uint32_t)(((g.dh[tt] - g.box_h0) * pitch + (g.dw[tt] - g.box_w0)) * RB) >> 4;
-      tb[t] = (uint32_t)(g.widx[tt] * wsub) >> 4;
-      tc_[t] = (uint32_t)(g.tap_cls[tt] * g.Cout);  // TMEM column offset of the tap's class inside a row's accumulators
-      tf[t] = (uint32_t)g.tap_first[tt];
-    }
-    const uint32_t row_step = (uint32_t)(pitch * RB) >> 4;
-    const uint32_t cout = (uint32_t)(g.ncls * g.Cout);
-    const int ntaps = g.ntaps;
-    const bool no_mma = (g.debug & 1) != 0;
-    mbar_wait(w_full, 0);
-    const uint32_t w_lo = smem_u32(sW) >> 4;
-    const uint32_t h_base = smem_u32(sH) >> 4, h_step = (uint32_t)hsub >> 4;
-    int s = 0;
-    uint32_t ph = 0;  // parity to wait for on full_bar[s]
-    for (int i = 0; i < tcnt; ++i) {
-      const uint32_t a = i & 1, aph = (i >> 1) & 1;
-      mbar_wait(&tempty_bar[a], aph ^ 1);
-      mbar_wait(&full_bar[s], ph);
-      tc_fence_after();
-      const uint32_t h_lo = h_base + (uint32_t)s * h_step;
-      const uint32_t d0 = tmem_base + a * acc_cols;
-      if (elect_one()) {
-        if (!no_mma) {
-          for (int r = 0; r < TH; ++r) {
-            const uint32_t d_tmem = d0 + (uint32_t)r * cout;
-            const uint32_t hr = h_lo + (uint32_t)r * row_step;
-#pragma unroll
-            for (int t = 0; t < 9; ++t) {
-              if (t < ntaps) {
-#pragma unroll
-                for (int j = 0; j < RB / 32; ++j) {
-                  if (j > 0)
-                    umma_bf16_acc(d_tmem + tc_[t], d_hi | (uint64_t)(hr + ta[t] + 2 * j), d_hi | (uint64_t)(w_lo + tb[t] + 2 * j), idesc);
-                  else
-                    umma_bf16(d_tmem + tc_[t], d_hi | (uint64_t)(hr + ta[t]), d_hi | (uint64_t)(w_lo + tb[t]), idesc, tf[t] ^ 1u);
-                }
-              }
-            }
-          }
-        }
-        umma_commit(&empty_bar[s]);
-        umma_commit(&tfull_bar[a]);
-      }
-      __syncwarp();
-      if (++s == stages) {
-        s = 0;
-        ph ^= 1;
-      }
-    }
+    // ---- MMA issuer: warp-uniform loop specialised on the k-steps per tap (row bytes / 32) ----
+    if (RB == 32) halo_mma_role<1, Cout>(g, sW, sH, wsub, hsub, stages, pitch, TH, acc_cols, tmem_base, t0, tcnt, w_full, full_bar, empty_bar, tfull_bar, tempty_bar);
+    else if (RB == 64) halo_mma_role<2, Cout>(g, sW, sH, wsub, hsub, stages, pitch, TH, acc_cols, tmem_base, t0, tcnt, w_full, full_bar, empty_bar, tfull_bar, tempty_bar);
+    else halo_mma_role<4, Cout>(g, sW, sH, wsub, hsub, stages, pitch, TH, acc_cols, tmem_base, t0, tcnt, w_full, full_bar, empty_bar, tfull_bar, tempty_bar);
   } else {
-    // ---- epilogue: thread = pixel column px of every output row of the tile ----
+    // ---- epilogue: thread = grid pixel column px of every row of the tile ----
     const int q = warp & 3, hf = warp >> 2;
     const int px = q * 32 + lane;
-    float a0[32], a1[32];
+    EpiRegs<NCHUNK, MODE> e;
+    epi_init<NCHUNK, MODE>(g, hf, e);
+    const __nv_bfloat162 floor2 = __float2bfloat162_rn(g.relu ? 0.f : -INFINITY);
+    const bool st_ok = !(g.debug & 4);
+    const int ncls = g.ncls, cls_shift = ncls == 1 ? 0 : (ncls == 2 ? 1 : 2), cls_mask = ncls - 1;
+    const int osh = g.osh, osw = g.osw, OW = g.OW, OH = g.OH, GH = g.GH, GW = g.GW, TW = g.TW;
+    // per-class output offsets (elements, relative to the tile's first output pixel of this thread) and coordinates
+    int cdo[4], cph[4], cpw[4];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      a0[j] = 0.f;
-      a1[j] = 0.f;
+    for (int c = 0; c < 4; ++c) {
+      cph[c] = c < ncls ? g.cls_ph[c] : 0;
+      cpw[c] = c < ncls ? g.cls_pw[c] : 0;
+      cdo[c] = (cph[c] * OW + cpw[c]) * Cout;
     }
+    const int row_do = osh * OW * Cout;  // element offset between consecutive grid rows of the tile
+    int tw = t0 % g.tiles_w, th = (t0 / g.tiles_w) % g.tiles_h, n = t0 / (g.tiles_w * g.tiles_h);
     int cur_n = -1;
     for (int i = 0; i < tcnt; ++i) {
       const uint32_t a = i & 1, aph = (i >> 1) & 1;
-      const int tile = t0 + i;
-      const int tw = tile % g.tiles_w;
-      const int th = (tile / g.tiles_w) % g.tiles_h;
-      const int n = tile / (g.tiles_w * g.tiles_h);
       if (MODE != 0 && MODE != 2 && n != cur_n) {
-        if (cur_n >= 0) epi_flush<MODE>(g, cur_n, hf, g.Cout >> 4, lane, a0, a1);
+        if (cur_n >= 0) epi_flush<NCHUNK, MODE>(g, cur_n, hf, lane, e);
         cur_n = n;
       }
-      const int gw = tw * g.TW + px;
-      const bool okw = px < g.TW && gw < g.GW;
-      const long long img = (long long)n * g.OH;
-      const int gh0 = th * TH;
-      uint8_t* sbuf = g.st_rows ? sOut + (i % g.st_bufs) * g.st_bytes : nullptr;
-      DBG_STAMP(i, 0);
-      if (g.st_rows) stage_acquire(g);
-      DBG_STAMP(i, 1);
+      const int gw = tw * TW + px, gh0 = th * TH;
+      const bool okw = px < TW && gw < GW;
+      const int ow0 = gw * osw, oh0 = gh0 * osh;
+      const long long base = okw ? (((long long)n * OH + oh0) * OW + ow0) * Cout : 0;
       mbar_wait(&tfull_bar[a], aph);
-      DBG_STAMP(i, 2);
       tc_fence_after();
-      // accumulator block rr = (tile row, class): grid pixel (gh0 + row, gw) -> output pixel (osh gh + ph, osw gw + pw);
-      // staging tile = the dense block of (TH osh) x (TW osw) output pixels of this tile
-      epi_tile<MODE>(g, tmem_base + a * acc_cols, TH * g.ncls, q, hf, sbias,
-                     [&](int rr, bool& ok, int& spix) {
-                       const int row = g.ncls == 1 ? rr : rr / g.ncls, cl = g.ncls == 1 ? 0 : rr - row * g.ncls;
-                       const int gh = gh0 + row;
-                       const int oh = gh * g.osh + g.cls_ph[cl], ow = gw * g.osw + g.cls_pw[cl];
-                       ok = okw && gh < g.GH && oh < g.OH && ow < g.OW;
-                       spix = (row * g.osh + g.cls_ph[cl]) * g.st_cols + px * g.osw + g.cls_pw[cl];
-                       return ((img + oh) * g.OW + ow) * g.Cout;
-                     },
-                     a0, a1, sbuf);
-      DBG_STAMP(i, 3);
+      // accumulator block rr = (tile row, class): grid pixel (gh0 + row, gw) -> output pixel (osh gh + ph, osw gw + pw)
+      epi_tile<NCHUNK, EPI, MODE>(g, tmem_base + a * acc_cols, TH * ncls, q, hf, base, st_ok, floor2, e,
+                                  [&](int rr, bool& ok, int& o) {
+                                    const int row = rr >> cls_shift, cl = rr & cls_mask;
+                                    int ph_ = cph[0], pw_ = cpw[0], d_ = cdo[0];
+#pragma unroll
+                                    for (int c = 1; c < 4; ++c)
+                                      if (cl == c) {
+                                        ph_ = cph[c];
+                                        pw_ = cpw[c];
+                                        d_ = cdo[c];
+                                      }
+                                    ok = okw && gh0 + row < GH && oh0 + row * osh + ph_ < OH && ow0 + pw_ < OW;
+                                    o = row * row_do + d_;
+                                  });
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[a]);
-      DBG_STAMP(i, 4);
-      if (g.st_rows) stage_store(g, &tmY, sbuf, tw * g.TW * g.osw, gh0 * g.osh, n);
-      DBG_STAMP(i, 5);
+      if (++tw == g.tiles_w) {
+        tw = 0;
+        if (++th == g.tiles_h) {
+          th = 0;
+          ++n;
+        }
+      }
     }
-    if (MODE != 0 && (MODE == 2 || cur_n >= 0)) epi_flush<MODE>(g, cur_n, hf, g.Cout >> 4, lane, a0, a1);
-    if (g.st_rows && threadIdx.x == 0) tma_store_wait_all();
+    if (MODE != 0 && (MODE == 2 || cur_n >= 0)) epi_flush<NCHUNK, MODE>(g, cur_n, hf, lane, e);
   }
   tc_fence_before();
   __syncthreads();
@@ -700,101 +695,67 @@ int num_sms() {
 }
 
 int mode_of(const ConvTcArgs& a) { return a.in_sums ? 1 : (a.colsum ? 2 : (a.in_bsums ? 3 : 0)); }
+int epi_of(const ConvTcArgs& a) { return a.mask ? EPI_MASK : ((a.bias || a.relu) ? EPI_FWD : EPI_PLAIN); }
 
-template <int RB, int G, int MODE>
-int launch_generic(const CUtensorMap& tmX, const CUtensorMap& tmW, const CUtensorMap& tmY, const ConvTcArgs& a, cudaStream_t st) {
-  auto kern = conv_tc_kernel<RB, G, MODE>;
+// ---- launchers: one instantiation per (NCHUNK, EPI, MODE) that the encoders use ------------------------------------
+template <int NCHUNK, int EPI>
+int launch_generic(const CUtensorMap& tmX, const CUtensorMap& tmW, const ConvTcArgs& a, int smem_bytes, cudaStream_t st) {
+  auto kern = conv_tc_kernel<NCHUNK, EPI>;
   static bool configured = false;
   if (!configured) {
-    OMR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<RB, G>::SMEM));
+    OMR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured = true;
   }
   int grid = a.num_tiles < num_sms() ? a.num_tiles : num_sms();
-  OmrLaunch(grid, NTHREADS, Cfg<RB, G>::SMEM, st)(kern, tmX, tmW, tmY, a);
+  OmrLaunch(grid, NTHREADS, smem_bytes, st)(kern, tmX, tmW, a);
   OMR_LAUNCHED();
   return OMR_OK;
 }
-template <int RB, int G>
-int launch_generic_mode(const CUtensorMap& tmX, const CUtensorMap& tmW, const CUtensorMap& tmY, const ConvTcArgs& a, cudaStream_t st) {
-  switch (mode_of(a)) {
-    case 0: return launch_generic<RB, G, 0>(tmX, tmW, tmY, a, st);
-    case 1: return launch_generic<RB, G, 1>(tmX, tmW, tmY, a, st);
-    case 2: return launch_generic<RB, G, 2>(tmX, tmW, tmY, a, st);
-    default: return launch_generic<RB, G, 3>(tmX, tmW, tmY, a, st);
+template <int NCHUNK>
+int launch_generic_epi(const CUtensorMap& tmX, const CUtensorMap& tmW, const ConvTcArgs& a, int smem_bytes, cudaStream_t st) {
+  switch (epi_of(a)) {
+    case EPI_FWD: return launch_generic<NCHUNK, EPI_FWD>(tmX, tmW, a, smem_bytes, st);
+    case EPI_MASK: return launch_generic<NCHUNK, EPI_MASK>(tmX, tmW, a, smem_bytes, st);
+    default: return launch_generic<NCHUNK, EPI_PLAIN>(tmX, tmW, a, smem_bytes, st);
   }
 }
 
-template <int RB, int MODE>
-int launch_halo(const CUtensorMap& tmX, const CUtensorMap& tmW, const CUtensorMap& tmY, const ConvTcArgs& h, int wsub, int hsub,
-                int stages, int smem_bytes, cudaStream_t st) {
-  auto kern = conv_halo_kernel<RB, MODE>;
+template <int NCHUNK, int EPI, int MODE>
+int launch_halo(const CUtensorMap& tmX, const CUtensorMap& tmW, const ConvTcArgs& h, int wsub, int hsub, int stages, int smem_bytes,
+                cudaStream_t st) {
+  auto kern = conv_halo_kernel<NCHUNK, EPI, MODE>;
   static bool configured = false;
   if (!configured) {
     OMR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured = true;
   }
   const int grid = h.num_tiles < num_sms() ? h.num_tiles : num_sms();
-  if (h.debug & 8) {  // diagnostics only (synchronises): per-tile stamps of the epilogue
-    static long long* dbg_dev = nullptr;
-    static int dumps = 0;
-    if (!dbg_dev) cudaMalloc(&dbg_dev, 64 * 8 * sizeof(long long));
-    cudaMemsetAsync(dbg_dev, 0, 64 * 8 * sizeof(long long), st);
-    ConvTcArgs hd = h;
-    hd.dbg = dbg_dev;
-    OmrLaunch(grid, NTHREADS, smem_bytes, st)(kern, tmX, tmW, tmY, hd, wsub, hsub, stages);
-    OMR_LAUNCHED();
-    cudaStreamSynchronize(st);
-    static long long hb[64 * 8];
-    cudaMemcpy(hb, dbg_dev, sizeof(hb), cudaMemcpyDeviceToHost);
-    if (dumps++ < 2) {
-      fprintf(stderr, "[conv_halo dbg] Cin %d Cout %d TH %d ncls %d tiles %d grid %d stages %d st_bufs %d mode %d\n", h.Cin, h.Cout, h.TH,
-              h.ncls, h.num_tiles, grid, stages, h.st_bufs, MODE);
-      for (int it = 8; it < 20; ++it)
-        fprintf(stderr, "  it%2d period %6lld | acquire %5lld  wait_tfull %5lld  units %5lld  arrive %5lld  store %5lld\n", it,
-                hb[it * 8] - hb[(it - 1) * 8], hb[it * 8 + 1] - hb[it * 8], hb[it * 8 + 2] - hb[it * 8 + 1], hb[it * 8 + 3] - hb[it * 8 + 2],
-                hb[it * 8 + 4] - hb[it * 8 + 3], hb[it * 8 + 5] - hb[it * 8 + 4]);
-    }
-    return OMR_OK;
-  }
-  OmrLaunch(grid, NTHREADS, smem_bytes, st)(kern, tmX, tmW, tmY, h, wsub, hsub, stages);
+  OmrLaunch(grid, NTHREADS, smem_bytes, st)(kern, tmX, tmW, h, wsub, hsub, stages);
   OMR_LAUNCHED();
   return OMR_OK;
 }
-template <int RB>
-int launch_halo_mode(const CUtensorMap& tmX, const CUtensorMap& tmW, const CUtensorMap& tmY, const ConvTcArgs& h, int wsub, int hsub,
-                     int stages, int smem_bytes, cudaStream_t st) {
-  switch (mode_of(h)) {
-    case 0: return launch_halo<RB, 0>(tmX, tmW, tmY, h, wsub, hsub, stages, smem_bytes, st);
-    case 1: return launch_halo<RB, 1>(tmX, tmW, tmY, h, wsub, hsub, stages, smem_bytes, st);
-    case 2: return launch_halo<RB, 2>(tmX, tmW, tmY, h, wsub, hsub, stages, smem_bytes, st);
-    default: return launch_halo<RB, 3>(tmX, tmW, tmY, h, wsub, hsub, stages, smem_bytes, st);
+// the (EPI, MODE) pairs that occur: forward (+ InstanceNorm statistics), masked data gradient (+ bias column sums), plain
+// data gradient (+ InstanceNorm backward sums)
+template <int NCHUNK>
+int launch_halo_epi(const CUtensorMap& tmX, const CUtensorMap& tmW, const ConvTcArgs& h, int wsub, int hsub, int stages, int smem_bytes,
+                    cudaStream_t st) {
+  const int epi = epi_of(h), mode = mode_of(h);
+  if (epi == EPI_FWD && mode == 0) return launch_halo<NCHUNK, EPI_FWD, 0>(tmX, tmW, h, wsub, hsub, stages, smem_bytes, st);
+  if (epi == EPI_MASK && mode == 0) return launch_halo<NCHUNK, EPI_MASK, 0>(tmX, tmW, h, wsub, hsub, stages, smem_bytes, st);
+  if (epi == EPI_PLAIN && mode == 0) return launch_halo<NCHUNK, EPI_PLAIN, 0>(tmX, tmW, h, wsub, hsub, stages, smem_bytes, st);
+  if constexpr (NCHUNK <= 4) {
+    if (epi == EPI_FWD && mode == 1) return launch_halo<NCHUNK, EPI_FWD, 1>(tmX, tmW, h, wsub, hsub, stages, smem_bytes, st);
+    if (epi == EPI_MASK && mode == 2) return launch_halo<NCHUNK, EPI_MASK, 2>(tmX, tmW, h, wsub, hsub, stages, smem_bytes, st);
+    if (epi == EPI_PLAIN && mode == 3) return launch_halo<NCHUNK, EPI_PLAIN, 3>(tmX, tmW, h, wsub, hsub, stages, smem_bytes, st);
   }
-}
-
-// tensor map of the output y [N, OH, OW, Cout] for staged TMA stores: box = st_cols x st_rows pixels of min(Cout, 64) channels
-int make_out_map(CUtensorMap* tm, const ConvTcArgs& a) {
-  const int cb = a.Cout >= 64 ? 64 : a.Cout;
-  unsigned long long dims[4] = {(unsigned long long)a.Cout, (unsigned long long)a.OW, (unsigned long long)a.OH, (unsigned long long)a.N};
-  unsigned long long strides[3] = {(unsigned long long)a.Cout * 2, (unsigned long long)a.OW * a.Cout * 2,
-                                   (unsigned long long)a.OH * a.OW * a.Cout * 2};
-  unsigned int box[4] = {(unsigned)cb, (unsigned)a.st_cols, (unsigned)a.st_rows, 1u};
-  return omr_make_tensor_map(tm, 2, a.y, 4, dims, strides, box, nullptr, cb * 2);
-}
-
-int g_stage_mode = -1;
-int stage_bufs_wanted() {  // OMR_CONV_STAGE: 0 = direct global stores, 1 = one staging buffer, 2 (default) = two when they fit
-  if (g_stage_mode < 0) {
-    const char* e = getenv("OMR_CONV_STAGE");
-    g_stage_mode = e ? atoi(e) : 0;  // measured: staged TMA stores are not faster than direct stores (round 2)
-    if (g_stage_mode < 0 || g_stage_mode > 2) g_stage_mode = 2;
-  }
-  return g_stage_mode;
+  return OMR_TC_NOT_ELIGIBLE;  // a combination the encoders never produce: the dispatcher falls back to separate passes
 }
 
 // One launch of the tap-GEMM.  x: [N, XH, XW, Cin] bf16; wpack: [Cout, 9*Cin] bf16 (tap-major, channels innermost).
 int run_taps(const void* x, int N, int XH, int XW, int Cin, const void* wpack, int Cout, ConvTcArgs a, cudaStream_t st) {
   const int rb = (Cin >= 64 ? 64 : Cin) * 2;
   a.debug = conv_debug();
+  a.rb = rb;
   if (mode_of(a) != 0 && Cout > 64) return OMR_TC_NOT_ELIGIBLE;  // the caller must not ask (fused sums need Cout <= 64)
   const bool upsample = a.ncls > 1;
   if (!upsample) {  // plain stride-1 convolution / one parity class: a single output class, 3 x 3 halo
@@ -807,35 +768,22 @@ int run_taps(const void* x, int N, int XH, int XW, int Cin, const void* wpack, i
     const int TW = a.GW >= 128 ? 128 : a.GW;
     const int pitch = TW + a.box_wr;
     const int wsub = (Cout * rb + 1023) / 1024 * 1024;
-    // TH output rows per tile: fewer TMA rows per output pixel ((TH+2)/TH instead of 3) and fewer barrier round trips;
+    // TH grid rows per tile: fewer TMA rows per output pixel ((TH+2)/TH instead of 3) and fewer barrier round trips;
     // bounded by TMEM (2 buffers x TH x classes x Cout columns <= 512) and by shared memory (>= 2 halo stages next to the weights)
-    // Staged output (TMA store) needs a staging tile of (TH osh) x (TW osw) pixels; preference: two staging buffers, then one,
-    // then direct stores, each with the largest TH that leaves >= 2 halo stages.
-    int TH = 4, hsub = 0, stages = 0, st_bufs = 0, st_bytes = 0;
-    bool found = false;
-    for (int want = stage_bufs_wanted(); want >= 0 && !found; --want) {
-      for (TH = 4; TH >= 1; TH >>= 1) {
-        if (2 * TH * a.ncls * Cout > 512 || (TH > 1 && a.GH < TH)) continue;
-        if (TH * a.osh > 256 || TW * a.osw > 256) continue;
-        int rows = (TH + a.box_hr) * pitch;
-        // a tap's 128-row operand window starts up to box_hr * pitch + box_wr rows into the last tile row's box row
-        if (rows < (TH - 1 + a.box_hr) * pitch + a.box_wr + 128) rows = (TH - 1 + a.box_hr) * pitch + a.box_wr + 128;
-        hsub = (rows * rb + 1023) / 1024 * 1024;
-        st_bufs = want;
-        st_bytes = want ? ((TH * a.osh) * (TW * a.osw) * Cout * 2 + 1023) / 1024 * 1024 : 0;
-        stages = (225 * 1024 - 1024 - 1024 - 9 * wsub - st_bufs * st_bytes) / hsub;
-        if (stages > 4) stages = 4;
-        if (stages >= 2) {
-          found = true;
-          break;
-        }
-      }
+    int TH = 4, hsub = 0, stages = 0;
+    for (; TH >= 1; TH >>= 1) {
+      if (2 * TH * a.ncls * Cout > 512 || (TH > 1 && a.GH < TH)) continue;
+      int rows = (TH + a.box_hr) * pitch;
+      // a tap's 128-row operand window starts up to box_hr * pitch + box_wr rows into the last tile row's box row
+      if (rows < (TH - 1 + a.box_hr) * pitch + a.box_wr + 128) rows = (TH - 1 + a.box_hr) * pitch + a.box_wr + 128;
+      hsub = (rows * rb + 1023) / 1024 * 1024;
+      stages = (225 * 1024 - 1024 - 1024 - 9 * wsub) / hsub;
+      if (stages > 4) stages = 4;
+      if (stages >= 2) break;
     }
-    if (found) {
+    if (TH >= 1 && stages >= 2) {
       ConvTcArgs h = a;
       h.TH = TH; h.TW = TW;
-      h.st_bufs = st_bufs; h.st_bytes = st_bytes;
-      h.st_rows = st_bufs ? TH * a.osh : 0; h.st_cols = st_bufs ? TW * a.osw : 0;
       h.tiles_w = (a.GW + TW - 1) / TW;
       h.tiles_h = (a.GH + TH - 1) / TH;
       h.num_tiles = a.N * h.tiles_h * h.tiles_w;
@@ -851,18 +799,17 @@ int run_taps(const void* x, int N, int XH, int XW, int Cin, const void* wpack, i
       unsigned int wb[2] = {(unsigned)Cin, (unsigned)Cout};
       rc = omr_make_tensor_map(&tmW, 2, wpack, 2, wd, ws, wb, nullptr, rb);
       if (rc) return rc;
-      CUtensorMap tmY = tmX;
-      if (h.st_rows) {
-        rc = make_out_map(&tmY, h);
-        if (rc) return rc;
+      const int smem_bytes = 9 * wsub + stages * hsub + 1024 + 1024;
+      switch (Cout) {
+        case 16: return launch_halo_epi<1>(tmX, tmW, h, wsub, hsub, stages, smem_bytes, st);
+        case 32: return launch_halo_epi<2>(tmX, tmW, h, wsub, hsub, stages, smem_bytes, st);
+        case 64: return launch_halo_epi<4>(tmX, tmW, h, wsub, hsub, stages, smem_bytes, st);
+        default: return launch_halo_epi<8>(tmX, tmW, h, wsub, hsub, stages, smem_bytes, st);
       }
-      const int smem_bytes = 9 * wsub + stages * hsub + st_bufs * st_bytes + 1024 + 1024;
-      if (rb == 32) return launch_halo_mode<32>(tmX, tmW, tmY, h, wsub, hsub, stages, smem_bytes, st);
-      if (rb == 64) return launch_halo_mode<64>(tmX, tmW, tmY, h, wsub, hsub, stages, smem_bytes, st);
-      return launch_halo_mode<128>(tmX, tmW, tmY, h, wsub, hsub, stages, smem_bytes, st);
     }
   }
   if (upsample) return OMR_TC_NOT_ELIGIBLE;  // the caller falls back to one launch per parity class
+  if (mode_of(a) != 0) return OMR_TC_NOT_ELIGIBLE;  // the generic kernel has no fused sums: separate pass
   // tile geometry: a TH x TW patch of the logical output grid, TH*TW <= 128
   int TW = a.GW >= 128 ? 128 : a.GW;
   int TH = 128 / TW;
@@ -873,6 +820,13 @@ int run_taps(const void* x, int N, int XH, int XW, int Cin, const void* wpack, i
   a.tiles_h = (a.GH + TH - 1) / TH;
   a.num_tiles = a.N * a.tiles_h * a.tiles_w;
   a.Cin = Cin; a.Cout = Cout;
+  // pipeline: G (tap, chunk) sub-tiles per stage, as many stages (<= 4) as fit 160 KB
+  a.G = rb == 128 ? 1 : 3;
+  a.a_sub = 128 * rb;
+  a.b_sub = (128 * rb + 1023) / 1024 * 1024;  // room for Cout <= 128 rows, 1 KB aligned
+  a.stage_bytes = a.G * (a.a_sub + a.b_sub);
+  a.stages = (a.stage_bytes * 4 <= 160 * 1024) ? 4 : (a.stage_bytes * 3 <= 160 * 1024 ? 3 : 2);
+  const int smem_bytes = a.stages * a.stage_bytes + 1024 + 1024;
   CUtensorMap tmX, tmW;
   {
     unsigned long long dims[4] = {(unsigned long long)Cin, (unsigned long long)XW, (unsigned long long)XH, (unsigned long long)N};
@@ -887,16 +841,12 @@ int run_taps(const void* x, int N, int XH, int XW, int Cin, const void* wpack, i
     rc = omr_make_tensor_map(&tmW, 2, wpack, 2, wd, ws, wb, nullptr, rb);
     if (rc) return rc;
   }
-  CUtensorMap tmY = tmX;
-  if (stage_bufs_wanted() > 0 && a.osh == 1 && a.osw == 1) {  // dense output patch: staged TMA store
-    a.st_rows = TH; a.st_cols = TW; a.st_bufs = stage_bufs_wanted();
-    a.st_bytes = 128 * Cout * 2;  // <= 32 KB; Cfg reserves two of them
-    int rc = make_out_map(&tmY, a);
-    if (rc) return rc;
+  switch (Cout) {
+    case 16: return launch_generic_epi<1>(tmX, tmW, a, smem_bytes, st);
+    case 32: return launch_generic_epi<2>(tmX, tmW, a, smem_bytes, st);
+    case 64: return launch_generic_epi<4>(tmX, tmW, a, smem_bytes, st);
+    default: return launch_generic_epi<8>(tmX, tmW, a, smem_bytes, st);
   }
-  if (rb == 32) return launch_generic_mode<32, 3>(tmX, tmW, tmY, a, st);
-  if (rb == 64) return launch_generic_mode<64, 3>(tmX, tmW, tmY, a, st);
-  return launch_generic_mode<128, 1>(tmX, tmW, tmY, a, st);
 }
 
 bool shape_ok(int Ci, int Co) {
@@ -912,7 +862,7 @@ int omr_conv3x3_fwd_tc(const void* x, const void* w, const float* bias, void* y,
   if (!shape_ok(Ci, Co) || N < 1) return OMR_TC_NOT_ELIGIBLE;
   if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(w) & 15) || (reinterpret_cast<uintptr_t>(y) & 15))
     return OMR_TC_NOT_ELIGIBLE;
-  if (in_sums && Co > 64) return OMR_TC_NOT_ELIGIBLE;
+  if (in_sums && (Co > 64 || sh != 1 || sw != 1 || Ci > 64)) return OMR_TC_NOT_ELIGIBLE;
   ConvTcArgs a{};
   a.y = (bf16*)y; a.bias = bias; a.relu = relu; a.N = N;
   a.in_sums = in_sums;
@@ -938,8 +888,10 @@ int omr_conv3x3_dgrad_tc(const void* dy, const void* wT, void* dx, int N, int H,
   if ((reinterpret_cast<uintptr_t>(dy) & 15) || (reinterpret_cast<uintptr_t>(wT) & 15) || (reinterpret_cast<uintptr_t>(dx) & 15) ||
       (reinterpret_cast<uintptr_t>(mask) & 15) || (reinterpret_cast<uintptr_t>(in_x) & 15))
     return OMR_TC_NOT_ELIGIBLE;
-  if ((colsum || in_bsums) && Ci > 64) return OMR_TC_NOT_ELIGIBLE;
+  if ((colsum || in_bsums) && (Ci > 64 || Co > 64)) return OMR_TC_NOT_ELIGIBLE;  // fused sums live in the halo kernel
   if (colsum && in_bsums) return OMR_TC_NOT_ELIGIBLE;
+  if (colsum && !mask) return OMR_TC_NOT_ELIGIBLE;
+  if (in_bsums && mask) return OMR_TC_NOT_ELIGIBLE;
   const int Ho = (H + sh - 1) / sh, Wo = (W + sw - 1) / sw;
   if ((sh > 1 || sw > 1) && Ci <= 64 && Co <= 64) {
     // strided data gradient as ONE launch over the dy grid (fractionally-strided convolution): grid pixel (i, j) produces its
@@ -975,6 +927,9 @@ int omr_conv3x3_dgrad_tc(const void* dy, const void* wT, void* dx, int N, int H,
     a.box_h0 = dhmin; a.box_w0 = dwmin; a.box_hr = dhmax - dhmin; a.box_wr = dwmax - dwmin;
     int rc = run_taps(dy, N, Ho, Wo, Co, wT, Ci, a, st);
     if (rc != OMR_TC_NOT_ELIGIBLE) return rc;
+  }
+  if (colsum || in_bsums) {
+    if (sh > 1 || sw > 1) return OMR_TC_NOT_ELIGIBLE;  // parity-class launches carry no fused sums
   }
   for (int ph = 0; ph < sh; ++ph)
     for (int pw = 0; pw < sw; ++pw) {

@@ -80,17 +80,18 @@ extern "C" int omr_conv3x3_dgrad(int dt, const void* dy, const void* wT, void* d
   cudaStream_t st = as_stream(stream);
   const bool fused = (colsum || in_bsums);
   if (tc_enabled() && dt == OMR_BF16) {
-    if (!fused || Ci <= 64) {
+    if (fused) {  // sums from the kernel's own epilogue when it takes them ...
       if (in_bsums) OMR_CUDA(cudaMemsetAsync(in_bsums, 0, sizeof(double) * (size_t)N * Ci * 2, st));
       TC_TRY(omr_conv3x3_dgrad_tc(dy, wT, dx, N, H, W, Ci, Co, sh, sw, mask, mask_scale, colsum, in_x, in_bsums, st));
-    } else {
-      int rc = omr_conv3x3_dgrad_tc(dy, wT, dx, N, H, W, Ci, Co, sh, sw, mask, mask_scale, nullptr, nullptr, nullptr, st);
-      if (rc != OMR_TC_NOT_ELIGIBLE) {
-        if (rc) return rc;
-        ++g_tc_calls;
-        if (colsum) return omr_colsum(dt, dx, (long long)N * H * W, Ci, Ci, colsum, 1, stream);
-        return omr_in_partial_sums(dt, 2, dx, in_x, in_bsums, N, H * W, Ci, st);
-      }
+    }
+    // ... else (or without sums) the plain tensor-core data gradient, followed by one pass over the stored result
+    int rc = omr_conv3x3_dgrad_tc(dy, wT, dx, N, H, W, Ci, Co, sh, sw, mask, mask_scale, nullptr, nullptr, nullptr, st);
+    if (rc != OMR_TC_NOT_ELIGIBLE) {
+      if (rc) return rc;
+      ++g_tc_calls;
+      if (colsum) return omr_colsum(dt, dx, (long long)N * H * W, Ci, Ci, colsum, 1, stream);
+      if (in_bsums) return omr_in_partial_sums(dt, 2, dx, in_x, in_bsums, N, H * W, Ci, st);
+      return OMR_OK;
     }
   }
   int rc = omr_conv3x3_dgrad_simt(dt, dy, wT, dx, N, H, W, Ci, Co, sh, sw, st);
