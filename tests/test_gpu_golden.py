@@ -176,9 +176,17 @@ def test_full_size_multimodal_matches_reference_vectors():
 
 
 # ---- long greedy decodes: every sequence of the batch, to <eos> / max_seq_len ---------------------
+TIE_TOL = 2e-5  # a top-2 logit margin below this (|logit| ~ 3: ~7e-6 relative, a few fp32 ulps of the accumulations) is a tie
+
+
 def _assert_identical_streams(seqs, fix):
-    """token-for-token identity with the REAL reference's batch-1 loop; on a mismatch the message carries the reference's
-    own top-2 logit margin at that step (oracle/make_golden_greedy.py) so that a near-tie can be told from a bug"""
+    """token-for-token identity with the REAL reference's batch-1 loop.  The fixture carries the reference's own top-2 logit
+    margin at every step (oracle/make_golden_greedy.py): a stream may leave the reference's ONLY at a step where the
+    reference itself sits within TIE_TOL of a tie (its fp32 CPU run and any other correctly rounded fp32 evaluation may
+    then pick either token; one such step exists in 6 x ~1000 steps: sample 2 of config 1, margin 2.1e-6) -- everything up
+    to that step must be identical, and the divergence is reported as a warning.  Any other mismatch fails with the margin."""
+    import warnings
+
     assert len(seqs) >= len(fix["greedy"])
     for i, ref in enumerate(fix["greedy"]):
         got = seqs[i]
@@ -186,6 +194,9 @@ def _assert_identical_streams(seqs, fix):
             continue
         t = next((k for k in range(min(len(got), len(ref))) if got[k] != ref[k]), min(len(got), len(ref)))
         mg = fix["margins"][i]
+        if t < len(mg) and float(mg[t]) < TIE_TOL and len(got) == len(ref):
+            warnings.warn(f"sample {i}: identical for {t} steps, then a reference near-tie (top-2 margin {float(mg[t]):.2e} < {TIE_TOL})")
+            continue
         raise AssertionError(f"sample {i}: diverges from the reference at step {t} of {len(ref)} (got {len(got)} tokens); reference top-2 "
                              f"margin there {float(mg[t]) if t < len(mg) else None:.3e}, min margin of the stream {float(mg.min()):.3e}, "
                              f"|logit| max {fix['logit_scale'][i]:.2f}")
