@@ -37,7 +37,21 @@ struct AttnTcArgs {
   float scale_log2;  // scale * log2(e)
   int causal, window;
   AttnDrop drop;     // attention-probability dropout (thr == 0: off)
+  // mixer block mask (reference model.py:340-352): pairs with query >= q_len[s] AND key >= kv_len[s] are excluded, where
+  // s = (b * H + h) % quirk_mod reproduces the reference's head-major mask repeat (quirk_mod = 0: s = b); NULL: none
+  const int* q_len;
+  const int* kv_len;
+  int quirk_mod;
 };
+__device__ __forceinline__ void block_mask_of(const AttnTcArgs& a, int b, int h, int& lq, int& lkv) {
+  lq = a.Tq;
+  lkv = a.Tk;
+  if (a.q_len && a.kv_len) {
+    const int s = a.quirk_mod > 0 ? (b * a.H + h) % a.quirk_mod : b;
+    lq = a.q_len[s];
+    lkv = a.kv_len[s];
+  }
+}
 
 // Q, K[2], V[2], P (2 tiles) + bias tile + barriers: 115,456 B, so that two CTAs (+1 KB system reserve each) fit
 // in the 228 KB of an SM; the dynamic window is declared 1024-aligned (no static shared memory in this kernel)
@@ -307,6 +321,9 @@ __global__ void __launch_bounds__(192, 2) attn_fwd_tc_kernel(const __grid_consta
       if (a.window > 0) k_lo = max(0, t + off - a.window);
     }
     if (t >= a.Tq) k_hi = -1;
+    int lq, lkv;
+    block_mask_of(a, b, h, lq, lkv);
+    if (t >= lq) k_hi = min(k_hi, lkv - 1);
     int n = 0;  // live tiles processed so far (the barrier phases count these)
     for (int i = 0; i < ntiles; ++i) {
       if (!tile_live(i)) continue;
@@ -325,6 +342,7 @@ __global__ void __launch_bounds__(192, 2) attn_fwd_tc_kernel(const __grid_consta
       if (a.causal) {
         full = full && (j0 + BKV - 1 <= q0 + off) && (a.window <= 0 || j0 >= q0 + BQ - 1 + off - a.window);
       }
+      full = full && (q0 + BQ <= lq || j0 + BKV <= lkv);  // block mask: no masked row in this CTA, or the tile lies below the cut
       const SmRow w{tmem_S + lane_addr, sBias, a.scale_log2, j0, k_lo, k_hi};
       // pass 1: row max
       float mx;
@@ -415,8 +433,7 @@ int omr_attn_fwd_tc(const void* q, long long q_bs, long long q_rs, const void* k
                     const void* v, long long v_bs, long long v_rs, void* o, long long o_bs, long long o_rs, float* lse,
                     const float* key_bias, int B, int H, int Tq, int Tk, int hd, float scale, int causal, int window,
                     const int* q_len, const int* kv_len, int quirk_mod, cudaStream_t st) {
-  (void)quirk_mod;
-  if (hd != HD || q_len || kv_len || B < 1 || H < 1 || Tq < 1 || Tk < 1) return OMR_TC_NOT_ELIGIBLE;
+  if (hd != HD || (q_len == nullptr) != (kv_len == nullptr) || B < 1 || H < 1 || Tq < 1 || Tk < 1) return OMR_TC_NOT_ELIGIBLE;
   auto al = [](const void* p, long long bs, long long rs) {
     return (reinterpret_cast<uintptr_t>(p) & 15) == 0 && (bs * 2) % 16 == 0 && (rs * 2) % 16 == 0;
   };
@@ -428,7 +445,8 @@ int omr_attn_fwd_tc(const void* q, long long q_bs, long long q_rs, const void* k
   if (rc) return rc;
   rc = make_head_map(&tmV, v, v_bs, v_rs, B, Tk, H, BKV);
   if (rc) return rc;
-  AttnTcArgs a{(bf16*)o, o_bs, o_rs, lse, key_bias, B, H, Tq, Tk, scale * LOG2E, causal, window, omr_attn_cur_dropout()};
+  AttnTcArgs a{(bf16*)o, o_bs, o_rs, lse, key_bias, B, H, Tq, Tk, scale * LOG2E, causal, window, omr_attn_cur_dropout(),
+               q_len, kv_len, quirk_mod};
   static bool configured = false;
   if (!configured) {
     OMR_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM));
@@ -652,6 +670,9 @@ __global__ void __launch_bounds__(320, 1) attn_bwd_tc_kernel(const __grid_consta
       if (a.window > 0) t_hi = min(t_hi, j - off + a.window);
     }
     if (j >= a.Tk) t_hi = -1;
+    int lq, lkv;
+    block_mask_of(a, b, h, lq, lkv);
+    if (j >= lkv) t_hi = min(t_hi, lq - 1);
     const long long stat_base = ((long long)b * a.H + h) * a.Tq;
     const uint32_t dstream = a.drop.thr ? attn_drop_stream(a.drop, b * a.H + h) : 0u;
     const uint32_t dkp = (uint32_t)((a.Tk + 1) >> 1), dsh = (uint32_t)(j & 1) * 16u;
@@ -701,6 +722,7 @@ __global__ void __launch_bounds__(320, 1) attn_bwd_tc_kernel(const __grid_consta
       // every (query, key) pair of this tile visible?  (then no interval tests; rows past Tk carry bias = -inf)
       bool full = q0 + BQ <= a.Tq && j0 + BKV <= a.Tk;
       if (a.causal) full = full && q0 >= j0 + BKV - 1 - off && (a.window <= 0 || q0 + BQ - 1 <= j0 - off + a.window);
+      full = full && (j0 + BKV <= lkv || q0 + BQ <= lq);
       auto tile_half = [&](auto masked_tag, auto drop_tag) {
         constexpr bool MASKED = decltype(masked_tag)::value, DROP = decltype(drop_tag)::value;
 #pragma unroll 1
@@ -863,8 +885,8 @@ int omr_attn_bwd_tc(const void* q, long long q_bs, long long q_rs, const void* k
                     const void* dout, long long do_bs, long long do_rs, const float* lse, void* dq, long long dq_bs,
                     long long dq_rs, void* dk, long long dk_bs, long long dk_rs, void* dv, long long dv_bs, long long dv_rs,
                     float* ws, const float* key_bias, int B, int H, int Tq, int Tk, int hd, float scale, int causal,
-                    int window, const int* q_len, const int* kv_len, cudaStream_t st) {
-  if (hd != HD || q_len || kv_len || B < 1 || H < 1 || Tq < 1 || Tk < 1) return OMR_TC_NOT_ELIGIBLE;
+                    int window, const int* q_len, const int* kv_len, int quirk_mod, cudaStream_t st) {
+  if (hd != HD || (q_len == nullptr) != (kv_len == nullptr) || B < 1 || H < 1 || Tq < 1 || Tk < 1) return OMR_TC_NOT_ELIGIBLE;
   auto al = [](const void* p, long long bs, long long rs) {
     return (reinterpret_cast<uintptr_t>(p) & 15) == 0 && (bs * 2) % 16 == 0 && (rs * 2) % 16 == 0;
   };
@@ -889,7 +911,7 @@ int omr_attn_bwd_tc(const void* q, long long q_bs, long long q_rs, const void* k
   OMR_LAUNCHED();
   AttnBwdArgs g{};
   g.f = AttnTcArgs{nullptr, 0, 0, const_cast<float*>(lse), key_bias, B, H, Tq, Tk, scale * LOG2E, causal, window,
-                   omr_attn_cur_dropout()};
+                   omr_attn_cur_dropout(), q_len, kv_len, quirk_mod};
   g.delta = delta; g.dq_acc = dq_acc;
   g.dk = (bf16*)dk; g.dk_bs = dk_bs; g.dk_rs = dk_rs;
   g.dv = (bf16*)dv; g.dv_bs = dv_bs; g.dv_rs = dv_rs;

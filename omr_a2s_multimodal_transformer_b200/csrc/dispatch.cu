@@ -35,8 +35,32 @@ extern "C" int omr_gemm(int in_dt, int out_dt, int transA, int transB, int M, in
   if (M == 0 || N == 0 || batch == 0) return OMR_OK;
   cudaStream_t st = as_stream(stream);
   if (tc_enabled() && in_dt == OMR_BF16) {
-    TC_TRY(omr_gemm_tc(out_dt, transA, transB, M, N, K, A, lda, strideA, B, ldb, strideB, C, ldc, strideC, batch, bias,
-                         bias_mode, relu, accumulate, st));
+    if (batch == 1) {
+      TC_TRY(omr_gemm_tc(out_dt, transA, transB, M, N, K, A, lda, strideA, B, ldb, strideB, C, ldc, strideC, 1, bias,
+                           bias_mode, relu, accumulate, st));
+    } else {
+      // batched problems (the [B,V,T] logits of the public forward(), reference decoder.py:145-146): one tensor-core launch
+      // per batch element; element 0 decides eligibility for all (same shape, strides are multiples of the alignment or not)
+      const size_t esz_c = out_dt == OMR_F32 ? 4 : 2;
+      int rc0 = OMR_TC_NOT_ELIGIBLE;
+      const bool aligned = ((strideA * 2) % 16 == 0) && ((strideB * 2) % 16 == 0);
+      if (aligned)
+        rc0 = omr_gemm_tc(out_dt, transA, transB, M, N, K, A, lda, 0, B, ldb, 0, C, ldc, 0, 1, bias, bias_mode, relu, accumulate, st);
+      if (rc0 != OMR_TC_NOT_ELIGIBLE) {
+        if (rc0) return rc0;
+        for (int i = 1; i < batch; ++i) {
+          int rc = omr_gemm_tc(out_dt, transA, transB, M, N, K, (const char*)A + (size_t)i * strideA * 2, lda, 0,
+                               (const char*)B + (size_t)i * strideB * 2, ldb, 0, (char*)C + (size_t)i * strideC * esz_c, ldc, 0, 1, bias,
+                               bias_mode, relu, accumulate, st);
+          if (rc) {
+            OMR_REQUIRE(rc != OMR_TC_NOT_ELIGIBLE, "omr_gemm: batch element %d not eligible for the tensor-core kernel after element 0 was", i);
+            return rc;
+          }
+        }
+        ++g_tc_calls;
+        return OMR_OK;
+      }
+    }
   }
   return omr_gemm_simt(in_dt, out_dt, transA, transB, M, N, K, A, lda, strideA, B, ldb, strideB, C, ldc, strideC, batch,
                        bias, bias_mode, relu, accumulate, st);
@@ -176,7 +200,7 @@ extern "C" int omr_attn_bwd(int dt, const void* q, long long q_bs, long long q_r
   if (tc_enabled() && dt == OMR_BF16) {
     TC_TRY(omr_attn_bwd_tc(q, q_bs, q_rs, k, k_bs, k_rs, v, v_bs, v_rs, o, o_bs, o_rs, dout, do_bs, do_rs, lse, dq, dq_bs, dq_rs,
                            dk, dk_bs, dk_rs, dv, dv_bs, dv_rs, delta_ws, key_bias, B, H, Tq, Tk, hd, scale, causal, window,
-                           q_len, kv_len, st));
+                           q_len, kv_len, quirk_mod, st));
   }
   return omr_attn_bwd_simt(dt, q, q_bs, q_rs, k, k_bs, k_rs, v, v_bs, v_rs, o, o_bs, o_rs, dout, do_bs, do_rs, lse, dq,
                            dq_bs, dq_rs, dk, dk_bs, dk_rs, dv, dv_bs, dv_rs, delta_ws, key_bias, B, H, Tq, Tk, hd, scale,

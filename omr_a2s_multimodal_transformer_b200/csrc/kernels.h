@@ -50,7 +50,7 @@ int omr_attn_bwd_tc(const void* q, long long q_bs, long long q_rs, const void* k
                     const void* dout, long long do_bs, long long do_rs, const float* lse, void* dq, long long dq_bs,
                     long long dq_rs, void* dk, long long dk_bs, long long dk_rs, void* dv, long long dv_bs, long long dv_rs,
                     float* ws, const float* key_bias, int B, int H, int Tq, int Tk, int hd, float scale, int causal,
-                    int window, const int* q_len, const int* kv_len, cudaStream_t st);
+                    int window, const int* q_len, const int* kv_len, int quirk_mod, cudaStream_t st);
 int omr_conv3x3_wgrad_small(const void* x, const void* dy, float* dw, int N, int H, int W, int Ci, int Co, int sh, int sw,
                             int accumulate, cudaStream_t st);
 int omr_conv3x3_fwd_c1(int dt, const void* x, const void* w, const float* bias, void* y, int N, int H, int W, int Co, int sh,

@@ -194,6 +194,9 @@ int launch_ws(const CUtensorMap& tmDY, const CUtensorMap& tmX, const WsArgs& g, 
 int omr_conv3x3_wgrad_small(const void* x, const void* dy, float* dw, int N, int H, int W, int Ci, int Co, int sh, int sw,
                             int accumulate, cudaStream_t st) {
   if (!((Ci == 16 || Ci == 32) && (Co == 16 || Co == 32)) || sh != 1 || sw != 1 || N < 1) return OMR_TC_NOT_ELIGIBLE;
+  // 32 -> 32: since the tcgen05 issue loops became warp-uniform (round 2) the tcgen05 weight-gradient kernel is faster than this
+  // legacy-MMA kernel, which sits at 64 % of the HMMA pipe (ncu): 250 vs 276 us at 128 x 1024 x 32, 304 vs 338 us at 195 x 808 x 32
+  if (Ci == 32 && Co == 32) return OMR_TC_NOT_ELIGIBLE;
   if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(dy) & 15)) return OMR_TC_NOT_ELIGIBLE;
   WsArgs g{};
   g.dw = dw; g.Ci = Ci; g.Co = Co;

@@ -338,3 +338,59 @@ def test_attention_bwd_tc(ops, case):
     assert rel_err(dqb[:, :, qo:qo + d].float(), gq.reshape(b, tq, d)) < 1.5e-2
     assert rel_err(dkb[:, :, ko:ko + d].float(), gk.reshape(b, tk, d)) < 1.5e-2
     assert rel_err(dvb[:, :, vo:vo + d].float(), gv.reshape(b, tk, d)) < 1.5e-2
+
+
+@pytest.mark.parametrize("shape", [(3, 4, 330, 260), (2, 4, 1313, 1024), (5, 4, 128, 257)])
+def test_attention_mixer_block_mask_tc(ops, shape):
+    """The attention mixers' block mask (reference model.py:340-352: pairs with query >= q_len AND key >= kv_len are excluded,
+    repeated head-major so that (b, h) takes the lengths of sample (b H + h) mod B) on the tcgen05 flash kernels, forward
+    and backward, against fp32 torch with the same mask."""
+    from omr_a2s_multimodal_transformer_b200.ops import AttnSpec
+
+    b, h, tq, tk = shape
+    d = h * 64
+    qb = rnd(b, tq, d, seed=52).bfloat16()
+    kv = rnd(b, tk, 2 * d, seed=53).bfloat16()
+    g = torch.Generator().manual_seed(8)
+    q_len = torch.randint(tq // 3, tq + 1, (b,), generator=g).to(torch.int32).to(DEV)
+    kv_len = torch.randint(tk // 3, tk + 1, (b,), generator=g).to(torch.int32).to(DEV)
+    spec = AttnSpec(h, 64, q_len=q_len, kv_len=kv_len, quirk_mod=b)
+    n0 = tc_calls()
+    o, lse = ops.attn_fwd(qb, 0, kv, 0, kv, d, spec)
+    assert tc_calls() == n0 + 1, "tensor-core attention did not take the mixer block mask"
+    q4 = qb.float().reshape(b, tq, h, 64).requires_grad_(True)
+    k4 = kv[:, :, :d].float().reshape(b, tk, h, 64).requires_grad_(True)
+    v4 = kv[:, :, d:].float().reshape(b, tk, h, 64).requires_grad_(True)
+    s = torch.einsum("bthd,bshd->bhts", q4, k4) * 0.125
+    idx = (torch.arange(b, device=DEV)[:, None] * h + torch.arange(h, device=DEV)[None, :]) % b  # [B,H] -> sample whose lengths apply
+    lq, lk = q_len[idx].long(), kv_len[idx].long()
+    masked = (torch.arange(tq, device=DEV)[None, None, :, None] >= lq[:, :, None, None]) & \
+             (torch.arange(tk, device=DEV)[None, None, None, :] >= lk[:, :, None, None])
+    s = s.masked_fill(masked, float("-inf"))
+    o_ref = torch.einsum("bhts,bshd->bthd", torch.softmax(s, dim=-1), v4).reshape(b, tq, d)
+    assert rel_err(o.float(), o_ref) < 8e-3
+    assert float((lse - torch.logsumexp(s, dim=-1)).abs().max()) < 2e-3
+    do = rnd(b, tq, d, seed=54).bfloat16()
+    gq, gk, gv = torch.autograd.grad(o_ref, (q4, k4, v4), do.float())
+    dq, dkv = torch.zeros_like(qb), torch.zeros_like(kv)
+    n0 = tc_calls()
+    ops.attn_bwd(qb, 0, kv, 0, kv, d, o, do, lse, dq, 0, dkv, 0, dkv, d, spec)
+    assert tc_calls() == n0 + 1, "tensor-core attention backward did not take the mixer block mask"
+    assert rel_err(dq.float(), gq.reshape(b, tq, d)) < 1.5e-2
+    assert rel_err(dkv[:, :, :d].float(), gk.reshape(b, tk, d)) < 1.5e-2
+    assert rel_err(dkv[:, :, d:].float(), gv.reshape(b, tk, d)) < 1.5e-2
+
+
+def test_gemm_batched_logits_layout_tc(ops):
+    """the public forward()'s class-major logits [B,V,T] = W [V,D] @ hidden[b]^T + bias[:, None] (reference decoder.py:145-146)
+    are served by the tensor-core GEMM, one launch per batch element"""
+    b, v, t, d = 3, 6997, 128, 256
+    w = rnd(v, d, seed=61, scale=1 / 16).bfloat16()
+    hidden = rnd(b, t, d, seed=62).bfloat16()
+    bias = rnd(v, seed=63, scale=0.1)
+    out = torch.empty(b, v, t, dtype=torch.bfloat16, device=DEV)
+    n0 = tc_calls()
+    ops.gemm(w, hidden, out, v, t, d, trans_b=True, lda=d, ldb=d, ldc=t, batch=b, stride_b=t * d, stride_c=v * t, bias=bias, bias_mode=2)
+    assert tc_calls() == n0 + 1, "batched GEMM fell back to the CUDA-core kernel"
+    ref = torch.einsum("vd,btd->bvt", w.float(), hidden.float()) + bias[None, :, None]
+    assert rel_err(out.float(), ref) < 6e-3
