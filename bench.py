@@ -502,7 +502,7 @@ def main():
         else:
             r = {"bound": "hbm", "achieved": d["bytes"] / (d["ms"] * 1e-3) / 1e9, "peak": pk["hbm"], "unit": "GB/s"}
         r["frac"] = r["achieved"] / r["peak"]
-        key = ",".join(str(int(v)) for v in shape if abs(int(v)) < (1 << 20))
+        key = ",".join(str(int(v)) for v in [int(v) for v in shape if abs(int(v)) < (1 << 20)][-12:])  # = launch_shape below
         tr = (traffic_table.get(name) or {}).get(key)
         r.update({"kernel": name, "launch_shape": [int(v) for v in shape if abs(int(v)) < (1 << 20)][-12:],
                   "calls_per_step": d["calls"], "avg_ms": d["ms"] / max(d["calls"], 1),

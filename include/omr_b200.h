@@ -95,9 +95,11 @@ int omr_conv3x3_fwd(int dt, const void* x, const void* w, const float* bias, voi
 int omr_conv3x3_dgrad(int dt, const void* dy, const void* w, void* dx, int N, int H, int W, int Ci, int Co, int sh,
                       int sw, const void* mask, float mask_scale, float* colsum, const void* in_x, double* in_bsums,
                       omr_stream_t stream);
-/* dw[Co,Ci,3,3] (fp32, torch layout) and db[Co] (fp32) ; accumulate != 0 adds to dw/db */
+/* dw[Co,Ci,3,3] (fp32, torch layout) and db[Co] (fp32, may be NULL) ; accumulate != 0 adds to dw/db.
+ * ws (may be NULL): caller-owned fp32 scratch of 9*Co*Ci floats, 16-byte aligned; when given, the wide layers reduce their
+ * per-CTA partial sums into it with vector reductions and add it to dw in a second small kernel. */
 int omr_conv3x3_wgrad(int dt, const void* x, const void* dy, float* dw, float* db, int N, int H, int W, int Ci, int Co,
-                      int sh, int sw, int accumulate, omr_stream_t stream);
+                      int sh, int sw, int accumulate, float* ws, omr_stream_t stream);
 /* depthwise 3x3, stride 1, pad 1 (DepthSepConv2D.depth_conv, encoder.py:56-64) ; w [3,3,C] */
 int omr_dwconv3x3_fwd(int dt, const void* x, const void* w, const float* bias, void* y, int N, int H, int W, int C,
                       omr_stream_t stream);

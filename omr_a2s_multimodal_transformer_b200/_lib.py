@@ -25,7 +25,7 @@ _SIGS = {
     "omr_pack_dw_weight": "ippip",
     "omr_conv3x3_fwd": "ippppiiiiiiiipp",
     "omr_conv3x3_dgrad": "ipppiiiiiiipfpppp",
-    "omr_conv3x3_wgrad": "ippppiiiiiiiip",
+    "omr_conv3x3_wgrad": "ippppiiiiiiiipp",
     "omr_dwconv3x3_fwd": "ippppiiiip",
     "omr_dwconv3x3_dgrad": "ipppiiiip",
     "omr_dwconv3x3_wgrad": "ippppiiiiip",

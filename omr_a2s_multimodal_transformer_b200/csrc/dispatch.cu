@@ -130,7 +130,7 @@ extern "C" int omr_conv3x3_dgrad(int dt, const void* dy, const void* wT, void* d
 }
 
 extern "C" int omr_conv3x3_wgrad(int dt, const void* x, const void* dy, float* dw, float* db, int N, int H, int W,
-                                 int Ci, int Co, int sh, int sw, int accumulate, omr_stream_t stream) {
+                                 int Ci, int Co, int sh, int sw, int accumulate, float* ws, omr_stream_t stream) {
   OMR_REQUIRE(N >= 0 && H > 0 && W > 0 && Ci > 0 && Co > 0 && sh > 0 && sw > 0, "omr_conv3x3_wgrad: bad shape");
   cudaStream_t st = as_stream(stream);
   int Ho = (H + sh - 1) / sh, Wo = (W + sw - 1) / sw;
@@ -149,7 +149,7 @@ extern "C" int omr_conv3x3_wgrad(int dt, const void* x, const void* dy, float* d
       small_path = (e && e[0] == '0') ? 0 : 1;
     }
     if (small_path) TC_TRY(omr_conv3x3_wgrad_small(x, dy, dw, N, H, W, Ci, Co, sh, sw, accumulate, st));
-    TC_TRY(omr_conv3x3_wgrad_tc(x, dy, dw, N, H, W, Ci, Co, sh, sw, accumulate, st));
+    TC_TRY(omr_conv3x3_wgrad_tc(x, dy, dw, N, H, W, Ci, Co, sh, sw, accumulate, ws, st));
   }
   return omr_conv3x3_wgrad_simt(dt, x, dy, dw, N, H, W, Ci, Co, sh, sw, accumulate, st);
 }

@@ -27,7 +27,7 @@ int omr_conv3x3_dgrad_tc(const void* dy, const void* wT, void* dx, int N, int H,
 int omr_in_partial_sums(int dt, int mode, const void* a, const void* xin, double* out, int N, int HW, int C, cudaStream_t st);
 int omr_relu_mask_scale(int dt, void* dx, const void* mask, float scale, long long n, cudaStream_t st);
 int omr_conv3x3_wgrad_tc(const void* x, const void* dy, float* dw, int N, int H, int W, int Ci, int Co, int sh, int sw,
-                         int accumulate, cudaStream_t st);
+                         int accumulate, float* ws, cudaStream_t st);
 
 int omr_attn_fwd_simt(int dt, const void* q, long long q_bs, long long q_rs, const void* k, long long k_bs,
                       long long k_rs, const void* v, long long v_bs, long long v_rs, void* o, long long o_bs,

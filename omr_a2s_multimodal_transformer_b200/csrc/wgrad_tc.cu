@@ -22,6 +22,9 @@ using namespace tc;
 
 struct WgradArgs {
   float* dw;
+  float* ws;  // optional fp32 scratch [9][Co][Ci] (zeroed): partial sums go there with 16-byte vector reductions and a small
+              // second kernel adds them into dw's [Co][Ci][3][3] layout -- for the wide layers the epilogue's scalar atomics
+              // (one 4-byte reduction per element and CTA, 36 bytes apart) took ~60 % of the kernel (ncu, round 2)
   int N, Ci, Co;
   int TH, TW, KP;  // pixel tile (KP = TH*TW, multiple of 16)
   int tiles_h, tiles_w, num_tiles;
@@ -200,9 +203,18 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant_
         tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(t * g.Ci + c0), v);
         tmem_ld_wait();
         if (ok) {
-          float* dst = g.dw + ((long long)co * g.Ci + c0) * 9 + tap;
+          if (g.ws) {
+            float* dst = g.ws + ((long long)tap * g.Co + co) * g.Ci + c0;
 #pragma unroll
-          for (int j = 0; j < 16; ++j) atomicAdd(dst + j * 9, __uint_as_float(v[j]));
+            for (int j = 0; j < 16; j += 4)
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(__uint_as_float(v[j])),
+                           "f"(__uint_as_float(v[j + 1])), "f"(__uint_as_float(v[j + 2])), "f"(__uint_as_float(v[j + 3]))
+                           : "memory");
+          } else {
+            float* dst = g.dw + ((long long)co * g.Ci + c0) * 9 + tap;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) atomicAdd(dst + j * 9, __uint_as_float(v[j]));
+          }
         }
       }
     }
@@ -212,6 +224,16 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant_
   if (warp == 5) {
     tc_fence_after();
     tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
+// dw[co][ci][tap] += ws[tap][co][ci]
+__global__ void wgrad_finalize_kernel(const float* __restrict__ ws, float* __restrict__ dw, int Co, int Ci) {
+  omr_pdl_enter();
+  const int total = Co * Ci * 9;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int tap = i % 9, cc = i / 9;  // cc = co * Ci + ci
+    dw[i] += ws[(long long)tap * Co * Ci + cc];
   }
 }
 
@@ -237,13 +259,15 @@ int sms() {
 }  // namespace
 
 int omr_conv3x3_wgrad_tc(const void* x, const void* dy, float* dw, int N, int H, int W, int Ci, int Co, int sh, int sw,
-                         int accumulate, cudaStream_t st) {
+                         int accumulate, float* ws, cudaStream_t st) {
   auto okc = [](int c) { return c == 16 || c == 32 || c == 64 || c == 128; };
   if (!okc(Ci) || !okc(Co) || N < 1) return OMR_TC_NOT_ELIGIBLE;
   if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(dy) & 15)) return OMR_TC_NOT_ELIGIBLE;
   const int Ho = (H + sh - 1) / sh, Wo = (W + sw - 1) / sw;
   WgradArgs g{};
   g.dw = dw; g.N = N; g.Ci = Ci; g.Co = Co; g.sh = sh; g.sw = sw;
+  // the scratch path pays two extra small launches: worth it where the epilogue's atomics dominate (>= 64 x 64 channels)
+  g.ws = (ws && Ci * Co >= 64 * 64 && (reinterpret_cast<uintptr_t>(ws) & 15) == 0) ? ws : nullptr;
   g.halo = (sh == 1 && sw == 1 && wgrad_halo_enabled()) ? 1 : 0;
   g.KP = (Ci == 16 || g.halo) ? 128 : 64;
   int TW = ((Wo + 15) / 16) * 16;
@@ -304,6 +328,7 @@ int omr_conv3x3_wgrad_tc(const void* x, const void* dy, float* dw, int N, int H,
     if (rc) return rc;
   }
   if (!accumulate) OMR_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)Co * Ci * 9, st));
+  if (g.ws) OMR_CUDA(cudaMemsetAsync(g.ws, 0, sizeof(float) * (size_t)Co * Ci * 9, st));
   static bool configured = false;
   if (!configured) {
     OMR_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -311,5 +336,9 @@ int omr_conv3x3_wgrad_tc(const void* x, const void* dy, float* dw, int N, int H,
   }
   OmrLaunch(g.ctas_per_group * g.tap_groups, 192, smem_bytes, st)(wgrad_tc_kernel, tmDY, tmX, g);
   OMR_LAUNCHED();
+  if (g.ws) {
+    OmrLaunch((Co * Ci * 9 + 255) / 256, 256, 0, st)(wgrad_finalize_kernel, (const float*)g.ws, dw, Co, Ci);
+    OMR_LAUNCHED();
+  }
   return OMR_OK;
 }

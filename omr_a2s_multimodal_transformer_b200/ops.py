@@ -143,8 +143,10 @@ def conv3x3_wgrad(x, dy, dw, db, stride=(1, 1), accumulate=True):
     _chk(x, "conv3x3_wgrad.x"), _chk(dy, "conv3x3_wgrad.dy")
     n, h, w, ci = x.shape
     co = dy.shape[3]
+    # scratch for the wide layers' vectorised partial-sum reduction (see omr_conv3x3_wgrad in include/omr_b200.h)
+    ws = torch.empty(9 * co * ci, dtype=torch.float32, device=x.device) if (ci * co >= 4096 and x.dtype == torch.bfloat16) else None
     call("omr_conv3x3_wgrad", dt_code(x.dtype), ptr(x), ptr(dy), ptr(dw), ptr(db), n, h, w, ci, co, stride[0], stride[1],
-         int(accumulate), stream_ptr())
+         int(accumulate), ptr(ws), stream_ptr())
 
 
 def dwconv3x3_fwd(x, wp, bias):
