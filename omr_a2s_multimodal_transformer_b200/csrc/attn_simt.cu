@@ -32,7 +32,7 @@ struct AttnArgs {
 __device__ __forceinline__ float drop_factor(const AttnArgs& a, uint32_t stream, int t, int j) {
   if (a.drop.thr == 0) return 1.f;
   const uint2 blk = attn_drop_block(stream, (uint32_t)(t >> 1), (uint32_t)(j >> 1), (uint32_t)((a.Tk + 1) >> 1));
-  return attn_drop_u16(blk, t, j) >= a.drop.thr ? a.drop.inv_keep : 0.f;
+  return attn_drop_u15(blk, t, j) >= a.drop.thr ? a.drop.inv_keep : 0.f;
 }
 
 template <typename T>

@@ -75,7 +75,6 @@ __device__ __forceinline__ void kv_tile_range(const AttnTcArgs& a, int q0, int& 
   }
 }
 
-__device__ __forceinline__ void softmax_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 __device__ __forceinline__ void softmax_bar2() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 
@@ -85,27 +84,34 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
-// ---- the per-tile work of a softmax thread (one query row, 128 keys of S in TMEM), specialised so that the common
-// tile -- every key visible to every row -- pays for no interval tests, and a call without key bias for no bias loads.
-// x = scale_log2 * S + bias (log2 units).  MASKED tiles (causal diagonal, window edge, ragged key tail) test the row's
-// visible interval [k_lo, k_hi] per key.
+// ---- the per-tile work of a softmax thread (one query row, 64 of the tile's 128 keys of S in TMEM), specialised so that
+// the common tile -- every key visible to every row -- pays for no interval tests, and a tile whose key bias is zero
+// throughout for no bias loads.  x = scale_log2 * S + bias (log2 units).  MASKED tiles (causal diagonal, window edge,
+// ragged key tail) test the row's visible interval [k_lo, k_hi] per key.
 struct SmRow {
-  uint32_t tmem_s;      // TMEM address of this row's S values
-  const float* bias;    // shared-memory bias tile of the 128 keys (pre-multiplied by log2 e)
+  uint32_t tmem_s;      // TMEM address of this thread's 64 S values
+  const float* bias;    // shared-memory bias values of its 64 keys (pre-multiplied by log2 e)
   float scale_log2;
-  int j0, k_lo, k_hi;   // first key of the tile, visible interval of the row
+  int j0, k_lo, k_hi;   // first key of the thread's 64, visible interval of the row
 };
+
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
 
 template <bool MASKED, bool BIAS>
 __device__ __forceinline__ float softmax_row_max(const SmRow& w) {
   float mx = -INFINITY;
 #pragma unroll 1
-  for (int c = 0; c < 4; ++c) {
+  for (int c = 0; c < 2; ++c) {
     uint32_t v[32];
     tmem_ld32(w.tmem_s + c * 32, v);
     tmem_ld_wait();
 #pragma unroll
     for (int e = 0; e < 32; e += 4) {
+      float x[4];
       float bq[4] = {0.f, 0.f, 0.f, 0.f};
       if (BIAS || MASKED) {
         const float4 b4 = *reinterpret_cast<const float4*>(w.bias + c * 32 + e);
@@ -114,25 +120,27 @@ __device__ __forceinline__ float softmax_row_max(const SmRow& w) {
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const int j = w.j0 + c * 32 + e + k;
-        float x = __uint_as_float(v[e + k]);
-        if (BIAS || MASKED) x = fmaf(x, w.scale_log2, bq[k]);  // otherwise the (positive) scale is applied to the max
-        if (MASKED) x = (j >= w.k_lo && j <= w.k_hi) ? x : -INFINITY;
-        mx = fmaxf(mx, x);
+        x[k] = __uint_as_float(v[e + k]);
+        if (BIAS || MASKED) x[k] = fmaf(x[k], w.scale_log2, bq[k]);  // otherwise the (positive) scale is applied to the max
+        if (MASKED) x[k] = (j >= w.k_lo && j <= w.k_hi) ? x[k] : -INFINITY;
       }
+      mx = fmax3(mx, x[0], x[1]);
+      mx = fmax3(mx, x[2], x[3]);
     }
   }
   return (BIAS || MASKED) ? mx : mx * w.scale_log2;
 }
 
-// P = exp2(x - m) -> row sum (returned) and the bf16 tile in the 128B-swizzled K-major operand layout; with DROP the
-// stored probabilities carry the keep mask / (1-p) while the sum stays that of the full row
+// P = exp2(x - m) -> row sum over the thread's 64 keys (returned) and the bf16 values in the 128B-swizzled K-major operand
+// layout (64-key chunk `hf` of the P tile); with DROP the stored probabilities carry the keep mask (1/(1-p) is applied to
+// the output row at the end) while the sum stays that of the full row
 template <bool MASKED, bool BIAS, bool DROP>
-__device__ __forceinline__ float softmax_row_exp(const SmRow& w, float m_safe, uint8_t* sP, int r, int t, uint32_t dstream,
-                                                 uint32_t dkp, uint32_t thr, float inv_keep) {
+__device__ __forceinline__ float softmax_row_exp(const SmRow& w, float m_safe, uint8_t* rowp, int r, int t, uint32_t dstream,
+                                                 uint32_t dkp, uint32_t thr2) {
   float rs = 0.f;
   const float nm = -m_safe;
 #pragma unroll 1
-  for (int c = 0; c < 4; ++c) {
+  for (int c = 0; c < 2; ++c) {
     uint32_t v[32];
     tmem_ld32(w.tmem_s + c * 32, v);
     tmem_ld_wait();
@@ -152,36 +160,81 @@ __device__ __forceinline__ float softmax_row_exp(const SmRow& w, float m_safe, u
         if (MASKED) pr[k] = (j >= w.k_lo && j <= w.k_hi) ? pr[k] : 0.f;
         rs += pr[k];
       }
+      uint32_t m0 = 0xFFFFFFFFu, m1 = 0xFFFFFFFFu;
       if (DROP) {
         // rows t and t^1 (neighbouring lanes) share their 2 x 2 blocks: the even lane hashes the block of keys
-        // (j, j+1), the odd lane that of (j+2, j+3), and each hands the other the word of its row parity
+        // (j, j+1), the odd lane that of (j+2, j+3), and each hands the other the word of its row parity.  Both fields of
+        // a word are compared at once and the result becomes an AND mask of the packed bf16 pair.
         const int j = w.j0 + c * 32 + e;
         const uint2 mine = attn_drop_block(dstream, (uint32_t)(t >> 1), (uint32_t)((j >> 1) + (t & 1)), dkp);
         const uint32_t ox = __shfl_xor_sync(0xffffffffu, mine.x, 1), oy = __shfl_xor_sync(0xffffffffu, mine.y, 1);
         const uint32_t w0 = (t & 1) ? oy : mine.x;  // keys (j, j+1) for this row
         const uint32_t w1 = (t & 1) ? mine.y : ox;  // keys (j+2, j+3)
-        pr[0] = (w0 & 0xFFFFu) >= thr ? pr[0] * inv_keep : 0.f;
-        pr[1] = (w0 >> 16) >= thr ? pr[1] * inv_keep : 0.f;
-        pr[2] = (w1 & 0xFFFFu) >= thr ? pr[2] * inv_keep : 0.f;
-        pr[3] = (w1 >> 16) >= thr ? pr[3] * inv_keep : 0.f;
+        m0 = attn_drop_mask_bf16x2(attn_drop_flags(w0, thr2));
+        m1 = attn_drop_mask_bf16x2(attn_drop_flags(w1, thr2));
       }
-      pk[e >> 1] = pack_bf16(pr[0], pr[1]);
-      pk[(e >> 1) + 1] = pack_bf16(pr[2], pr[3]);
+      pk[e >> 1] = pack_bf16(pr[0], pr[1]) & m0;
+      pk[(e >> 1) + 1] = pack_bf16(pr[2], pr[3]) & m1;
     }
-    // keys c*32 .. c*32+31 = 64 bytes = 4 sixteen-byte units of row r in chunk c/2
-    uint8_t* rowp = sP + (c >> 1) * TILE + r * 128;
+    // keys c*32 .. c*32+31 of the chunk = 64 bytes = 4 sixteen-byte units of row r
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      const int unit = (c & 1) * 4 + u;
+      const int unit = c * 4 + u;
       *reinterpret_cast<uint4*>(rowp + ((unit ^ (r & 7)) << 4)) = make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
     }
   }
   return rs;
 }
 
-__global__ void __launch_bounds__(192, 2) attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
-                                                             const __grid_constant__ CUtensorMap tmK,
-                                                             const __grid_constant__ CUtensorMap tmV, AttnTcArgs a) {
+constexpr int FWD_SW = 8;                      // softmax warps: warp w = TMEM lane quarter w & 3, key / channel half w >> 2
+constexpr float FWD_RESCALE_THRESHOLD = 8.f;  // log2 units: the running reference maximum moves only when a row's true
+                                              // maximum exceeds it by more than this (P <= 2^8, harmless in bf16 / fp32)
+
+// OR over the 256 softmax threads (also a barrier among them)
+__device__ __forceinline__ bool softmax_bar_or(bool mine) {
+  uint32_t out;
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "setp.ne.u32 q, %1, 0;\n\t"
+      "barrier.cta.red.or.pred p, 1, 256, q;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(out)
+      : "r"((uint32_t)mine)
+      : "memory");
+  return out != 0;
+}
+// the two warps that share TMEM lane quarter lq (64 threads)
+__device__ __forceinline__ void pair_bar(int lq) { asm volatile("bar.sync %0, 64;" ::"r"(2 + lq) : "memory"); }
+__device__ __forceinline__ void tmem_st1(uint32_t taddr, uint32_t v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(taddr), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t tmem_ld1(uint32_t taddr) {
+  uint32_t v;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v) : "r"(taddr) : "memory");
+  return v;
+}
+// a value per row travels between the two warps of a lane quarter through a spare TMEM column of the row's own lane
+// (shared memory is full: two CTAs per SM leave 256 bytes to spare)
+__device__ __forceinline__ float pair_exchange(uint32_t col_mine, uint32_t col_other, int lq, float v) {
+  tmem_st1(col_mine, __float_as_uint(v));
+  tmem_st_wait();
+  tc_fence_before();
+  pair_bar(lq);
+  tc_fence_after();
+  const uint32_t o = tmem_ld1(col_other);
+  tmem_ld_wait();
+  return __uint_as_float(o);
+}
+
+// Forward, round 2: EIGHT softmax warps per CTA (two CTAs per SM -> four warps per scheduler; round 1 had two, and the
+// kernel sat at 32 % issue utilisation waiting on tcgen05.ld / MUFU latencies).  The two warps of a lane quarter split
+// the tile's keys (64 each) and the output channels (32 each).  O stays in TMEM and accumulates across key tiles; the
+// reference maximum of a row moves only when the row's true maximum has run away by more than 2^8 (then the row's O
+// accumulator and running sum are rescaled through tcgen05.ld / st), so the common tile neither reads nor rescales O.
+__global__ void __launch_bounds__(32 * (FWD_SW + 2), 2) attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
+                                                                          const __grid_constant__ CUtensorMap tmK,
+                                                                          const __grid_constant__ CUtensorMap tmV,
+                                                                          AttnTcArgs a) {
   omr_pdl_enter();
   extern __shared__ __align__(1024) uint8_t smem[];
   if (smem_u32(smem) & 1023u) __trap();  // the swizzled tiles need 1 KB alignment
@@ -218,7 +271,7 @@ __global__ void __launch_bounds__(192, 2) attn_fwd_tc_kernel(const __grid_consta
   }
   auto tile_live = [&](int i) { return !use_live || ((live[i >> 5] >> (i & 31)) & 1u); };
 
-  if (warp == 4 && lane == 0) {
+  if (warp == FWD_SW && lane == 0) {
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
@@ -228,20 +281,20 @@ __global__ void __launch_bounds__(192, 2) attn_fwd_tc_kernel(const __grid_consta
       mbar_init(&kv_empty[s], 1);
     }
     mbar_init(s_full, 1);
-    mbar_init(p_full, 4);
+    mbar_init(p_full, FWD_SW);
     mbar_init(pv_full, 1);
     fence_barrier_init();
   }
-  if (warp == 5) tmem_alloc(tmem_slot, 256);
+  if (warp == FWD_SW + 1) tmem_alloc(tmem_slot, 256);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = bcast0(*tmem_slot);
-  const uint32_t tmem_S = tmem_base, tmem_PV = tmem_base + 128;
+  const uint32_t tmem_S = tmem_base, tmem_PV = tmem_base + 128, tmem_X = tmem_base + 192;
 
   // Producer and MMA issuer run their loops WARP-wide on uniform values and issue under elect_one() (tc_common.cuh): a
   // lone lane under `if (lane == 0)` made the compiler wrap every tcgen05.mma / TMA in an ELECT / R2UR / BRA.U.ANY waterfall.
-  if (warp == 4) {
+  if (warp == FWD_SW) {
     if (ntiles > 0) {
       if (elect_one()) {
         mbar_expect_tx(q_full, TILE);
@@ -260,7 +313,7 @@ __global__ void __launch_bounds__(192, 2) attn_fwd_tc_kernel(const __grid_consta
         ++n;
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == FWD_SW + 1) {
     if (ntiles > 0) {
       constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
       constexpr uint32_t idesc_pv = make_idesc_bf16(128, 64, 0, 1);
@@ -284,36 +337,35 @@ __global__ void __launch_bounds__(192, 2) attn_fwd_tc_kernel(const __grid_consta
         }
         __syncwarp();
         mbar_wait(p_full, n & 1);
-        ++n;
         tc_fence_after();
         if (elect_one()) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
+          for (int j = 0; j < 8; ++j) {  // O += P V (the softmax warps have rescaled O if the reference maximum moved)
             if (j > 0)
               umma_bf16_acc(tmem_PV, make_smem_desc(p_addr + (j >> 2) * TILE + (j & 3) * 32, 16, 1024, 128),
                             make_smem_desc(v_addr + j * 2048, 0, 1024, 128), idesc_pv);
             else
-              umma_bf16_new(tmem_PV, make_smem_desc(p_addr, 16, 1024, 128), make_smem_desc(v_addr, 0, 1024, 128), idesc_pv);
+              umma_bf16(tmem_PV, make_smem_desc(p_addr, 16, 1024, 128), make_smem_desc(v_addr, 0, 1024, 128), idesc_pv, n > 0 ? 1u : 0u);
           }
           umma_commit(pv_full);
           umma_commit(&kv_empty[s]);
         }
         __syncwarp();
+        ++n;
       }
     }
   } else {
-    // ---- softmax + epilogue: thread = query row ----
-    const int r = warp * 32 + lane;
+    // ---- softmax + epilogue: thread = (query row, key half / channel half) ----
+    const int lq = warp & 3, hf = warp >> 2;
+    const int r = lq * 32 + lane;
     const int t = q0 + r;
     const int off = a.Tk - a.Tq;
-    const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
-    float m_run = -INFINITY, l_run = 0.f;
-    float o_acc[HD];
-#pragma unroll
-    for (int d = 0; d < HD; ++d) o_acc[d] = 0.f;
+    const uint32_t lane_addr = (uint32_t)(lq * 32) << 16;
+    const uint32_t x_mine = tmem_X + lane_addr + (uint32_t)hf, x_other = tmem_X + lane_addr + (uint32_t)(hf ^ 1);
+    float m_used = -INFINITY, l_run = 0.f;
     const float* kb = a.key_bias ? a.key_bias + (long long)b * a.Tk : nullptr;
     const uint32_t dstream = a.drop.thr ? attn_drop_stream(a.drop, b * a.H + h) : 0u;
-    const uint32_t dkp = (uint32_t)((a.Tk + 1) >> 1);
+    const uint32_t dkp = (uint32_t)((a.Tk + 1) >> 1), thr2 = a.drop.thr * 0x00010001u;
     // visible key interval of this row
     int k_hi = a.Tk - 1, k_lo = 0;
     if (a.causal) {
@@ -321,20 +373,24 @@ __global__ void __launch_bounds__(192, 2) attn_fwd_tc_kernel(const __grid_consta
       if (a.window > 0) k_lo = max(0, t + off - a.window);
     }
     if (t >= a.Tq) k_hi = -1;
-    int lq, lkv;
-    block_mask_of(a, b, h, lq, lkv);
-    if (t >= lq) k_hi = min(k_hi, lkv - 1);
+    int lqm, lkv;
+    block_mask_of(a, b, h, lqm, lkv);
+    if (t >= lqm) k_hi = min(k_hi, lkv - 1);
+    uint8_t* rowp = sP + hf * TILE + r * 128;
     int n = 0;  // live tiles processed so far (the barrier phases count these)
     for (int i = 0; i < ntiles; ++i) {
       if (!tile_live(i)) continue;
       const int j0 = (kt0 + i) * BKV;
-      // key-bias tile (pre-multiplied by log2 e) -> smem, shared by the 128 rows
-      softmax_bar();  // previous tile's readers are done with sBias
-      {
+      // key-bias tile (pre-multiplied by log2 e) -> smem, shared by the 128 rows; is any of it non-zero?
+      softmax_bar2();  // previous tile's readers are done with sBias
+      bool nz = false;
+      if (hf == 0) {
         const int j = j0 + r;
-        sBias[r] = (kb && j < a.Tk) ? kb[j] * LOG2E : 0.f;
+        const float bv = (kb && j < a.Tk) ? kb[j] * LOG2E : 0.f;
+        sBias[r] = bv;
+        nz = bv != 0.f;
       }
-      softmax_bar();
+      const bool any_bias = softmax_bar_or(nz);
       mbar_wait(s_full, n & 1);
       tc_fence_after();
       // does every row of this CTA see every key of the tile?  (rows past Tq are never stored: they may see anything)
@@ -342,79 +398,80 @@ __global__ void __launch_bounds__(192, 2) attn_fwd_tc_kernel(const __grid_consta
       if (a.causal) {
         full = full && (j0 + BKV - 1 <= q0 + off) && (a.window <= 0 || j0 >= q0 + BQ - 1 + off - a.window);
       }
-      full = full && (q0 + BQ <= lq || j0 + BKV <= lkv);  // block mask: no masked row in this CTA, or the tile lies below the cut
-      const SmRow w{tmem_S + lane_addr, sBias, a.scale_log2, j0, k_lo, k_hi};
-      // pass 1: row max
+      full = full && (q0 + BQ <= lqm || j0 + BKV <= lkv);  // block mask: no masked row in this CTA, or the tile lies below the cut
+      const SmRow w{tmem_S + lane_addr + hf * 64, sBias + hf * 64, a.scale_log2, j0 + hf * 64, k_lo, k_hi};
+      // pass 1: maximum of the thread's 64 keys, then of the row (exchange with the other half's warp)
       float mx;
       if (!full) mx = softmax_row_max<true, true>(w);
-      else if (kb) mx = softmax_row_max<false, true>(w);
+      else if (any_bias) mx = softmax_row_max<false, true>(w);
       else mx = softmax_row_max<false, false>(w);
-      const float m_new = fmaxf(m_run, mx);
-      const float m_safe = (m_new == -INFINITY) ? 0.f : m_new;
-      const float alpha = (m_run == -INFINITY) ? 0.f : ex2_approx(m_run - m_safe);
-      if (n > 0) {
-        mbar_wait(pv_full, (n - 1) & 1);
-        tc_fence_after();
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
+      mx = fmaxf(mx, pair_exchange(x_mine, x_other, lq, mx));
+      const bool need = mx > m_used + FWD_RESCALE_THRESHOLD;  // also the first finite maximum of a row (m_used = -inf)
+      if (__any_sync(0xffffffffu, need)) {
+        const float alpha = need ? ex2_approx(m_used - mx) : 1.f;  // m_used = -inf -> 0 (nothing accumulated yet)
+        if (n > 0) {  // O accumulator rows of this warp's 32 channels
+          mbar_wait(pv_full, (n - 1) & 1);
+          tc_fence_after();
           uint32_t v[32];
-          tmem_ld32(tmem_PV + lane_addr + c * 32, v);
+          tmem_ld32(tmem_PV + lane_addr + hf * 32, v);
           tmem_ld_wait();
 #pragma unroll
-          for (int e = 0; e < 32; ++e) o_acc[c * 32 + e] = (o_acc[c * 32 + e] + __uint_as_float(v[e])) * alpha;
+          for (int e = 0; e < 32; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) * alpha);
+          tmem_st32(tmem_PV + lane_addr + hf * 32, v);
+          tmem_st_wait();
         }
+        l_run *= alpha;
+        if (need) m_used = mx;
       }
+      const float m_safe = (m_used == -INFINITY) ? 0.f : m_used;
       // pass 2: P = exp2(x - m), row sum, bf16 into the swizzled A-operand tile
       float rs;
-      const uint32_t thr = a.drop.thr;
-      const float ik = a.drop.inv_keep;
-      if (thr) {
-        if (!full) rs = softmax_row_exp<true, true, true>(w, m_safe, sP, r, t, dstream, dkp, thr, ik);
-        else if (kb) rs = softmax_row_exp<false, true, true>(w, m_safe, sP, r, t, dstream, dkp, thr, ik);
-        else rs = softmax_row_exp<false, false, true>(w, m_safe, sP, r, t, dstream, dkp, thr, ik);
+      if (thr2) {
+        if (!full) rs = softmax_row_exp<true, true, true>(w, m_safe, rowp, r, t, dstream, dkp, thr2);
+        else if (any_bias) rs = softmax_row_exp<false, true, true>(w, m_safe, rowp, r, t, dstream, dkp, thr2);
+        else rs = softmax_row_exp<false, false, true>(w, m_safe, rowp, r, t, dstream, dkp, thr2);
       } else {
-        if (!full) rs = softmax_row_exp<true, true, false>(w, m_safe, sP, r, t, dstream, dkp, thr, ik);
-        else if (kb) rs = softmax_row_exp<false, true, false>(w, m_safe, sP, r, t, dstream, dkp, thr, ik);
-        else rs = softmax_row_exp<false, false, false>(w, m_safe, sP, r, t, dstream, dkp, thr, ik);
+        if (!full) rs = softmax_row_exp<true, true, false>(w, m_safe, rowp, r, t, dstream, dkp, thr2);
+        else if (any_bias) rs = softmax_row_exp<false, true, false>(w, m_safe, rowp, r, t, dstream, dkp, thr2);
+        else rs = softmax_row_exp<false, false, false>(w, m_safe, rowp, r, t, dstream, dkp, thr2);
       }
-      l_run = l_run * alpha + rs;
-      m_run = m_new;
+      l_run += rs;
       fence_proxy_async();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full);
       ++n;
     }
+    // epilogue: O row (this warp's 32 channels) / row sum, lse
+    uint32_t v[32];
     if (n > 0) {
       mbar_wait(pv_full, (n - 1) & 1);
       tc_fence_after();
+      tmem_ld32(tmem_PV + lane_addr + hf * 32, v);
+      tmem_ld_wait();
+    } else {
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t v[32];
-        tmem_ld32(tmem_PV + lane_addr + c * 32, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int e = 0; e < 32; ++e) o_acc[c * 32 + e] += __uint_as_float(v[e]);
-      }
+      for (int e = 0; e < 32; ++e) v[e] = 0u;
     }
+    const float l_tot = l_run + pair_exchange(x_mine, x_other, lq, l_run);
     if (t < a.Tq) {
-      const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
-      bf16* op = a.o + (long long)b * a.o_bs + (long long)t * a.o_rs + h * HD;
+      const float inv = l_tot > 0.f ? a.drop.inv_keep / l_tot : 0.f;  // 1/(1-p) of the dropout folded in (1 when off)
+      bf16* op = a.o + (long long)b * a.o_bs + (long long)t * a.o_rs + h * HD + hf * 32;
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
+      for (int u = 0; u < 4; ++u) {
         uint4 o4;
-        o4.x = pack_bf16(o_acc[8 * u] * inv, o_acc[8 * u + 1] * inv);
-        o4.y = pack_bf16(o_acc[8 * u + 2] * inv, o_acc[8 * u + 3] * inv);
-        o4.z = pack_bf16(o_acc[8 * u + 4] * inv, o_acc[8 * u + 5] * inv);
-        o4.w = pack_bf16(o_acc[8 * u + 6] * inv, o_acc[8 * u + 7] * inv);
+        o4.x = pack_bf16(__uint_as_float(v[8 * u]) * inv, __uint_as_float(v[8 * u + 1]) * inv);
+        o4.y = pack_bf16(__uint_as_float(v[8 * u + 2]) * inv, __uint_as_float(v[8 * u + 3]) * inv);
+        o4.z = pack_bf16(__uint_as_float(v[8 * u + 4]) * inv, __uint_as_float(v[8 * u + 5]) * inv);
+        o4.w = pack_bf16(__uint_as_float(v[8 * u + 6]) * inv, __uint_as_float(v[8 * u + 7]) * inv);
         reinterpret_cast<uint4*>(op)[u] = o4;
       }
-      if (a.lse) a.lse[((long long)b * a.H + h) * a.Tq + t] = l_run > 0.f ? (m_run + log2f(l_run)) * LN2 : 0.f;
+      if (a.lse && hf == 0) a.lse[((long long)b * a.H + h) * a.Tq + t] = l_tot > 0.f ? (m_used + log2f(l_tot)) * LN2 : 0.f;
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) {
+  if (warp == FWD_SW + 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 256);
   }
@@ -453,29 +510,46 @@ int omr_attn_fwd_tc(const void* q, long long q_bs, long long q_rs, const void* k
     configured = true;
   }
   dim3 grid((unsigned)((Tq + BQ - 1) / BQ), (unsigned)H, (unsigned)B);
-  OmrLaunch(grid, 192, FWD_SMEM, st)(attn_fwd_tc_kernel, tmQ, tmK, tmV, a);
+  OmrLaunch(grid, 32 * (FWD_SW + 2), FWD_SMEM, st)(attn_fwd_tc_kernel, tmQ, tmK, tmV, a);
   OMR_LAUNCHED();
   return OMR_OK;
 }
 
 // =================================================================================================================
 // Backward.  One CTA = one (batch, head, 128-key tile); K and V stay resident in shared memory and the CTA walks the
-// query tiles that can see them.  Everything is computed TRANSPOSED (rows = keys) so that each softmax thread owns
-// one key row and the probabilities land in shared memory directly in the operand layouts of the three gradient
-// GEMMs:
-//     S^T  = K Q^T                 M=128 keys, N=128 queries, K=64          (TMEM, recomputed)
+// query tiles that can see them, in HALF tiles of 64 queries.  Everything is computed TRANSPOSED (rows = keys) so that
+// each element-wise thread owns one key row and the probabilities land in shared memory directly in the operand layouts
+// of the three gradient GEMMs:
+//     S^T  = K Q^T                 M=128 keys, N=64 queries, K=64           (TMEM, recomputed)
 //     dP^T = V dO^T                same shape
-//     P^T  = exp2(scale*S^T + bias_k - lse_q)   dS^T = P^T o (dP^T - delta_q)   -- bf16 into two swizzled smem tiles
-//     dV  += P^T  dO               A = P^T  (K-major),  B = dO tile (MN-major)   accumulated in TMEM over the q tiles
-//     dK  += dS^T Q                A = dS^T (K-major),  B = Q  tile (MN-major)   accumulated in TMEM over the q tiles
-//     dQ_t = dS K                  A = dS^T read as an MN-major operand, B = K tile (MN-major); per q tile, added to an
-//                                  fp32 accumulation buffer with vector atomics (other key tiles add to the same rows)
+//     P^T  = exp2(scale*S^T + bias_k - lse_q)   dS^T = P^T o (dP^T - delta_q)   -- bf16 into swizzled smem chunks
+//     dV  += P^T  dO               A = P^T  (K-major),  B = dO half tile (MN-major)  accumulated in TMEM over the q tiles
+//     dK  += dS^T Q                A = dS^T (K-major),  B = Q  half tile (MN-major)  accumulated in TMEM over the q tiles
+//     dQ_t = dS K                  A = the two dS^T chunks of a 128-query tile read as ONE MN-major operand, B = K tile
+//                                  (MN-major); per q tile, added to an fp32 accumulation buffer with vector reductions
+// Round-2 pipeline (round 1 ran MMA -> element-wise -> MMA back to back on 8 warps, tensor pipe 13 % active, issue slots
+// 32 %): S^T / dP^T are DOUBLE-BUFFERED in TMEM at half-tile granularity (2 x (64 + 64) columns + dV 64 + dK 64 + dQ 64 =
+// 448), so the MMA warp issues the score MMAs of half u+1 before it waits for the element-wise phase of half u, and the
+// gradient MMAs of half u run under the element-wise phase of half u+1; P^T lives in a 2-chunk ring, dS^T in a 4-chunk
+// ring (the dQ MMA reads both halves of a tile after the second one); Q / dO / statistics arrive through a 4-stage ring.
+// SIXTEEN element-wise warps (warp w: TMEM lane quarter w & 3, 16-column group w >> 2) give every scheduler four warps
+// to hide the tcgen05.ld / MUFU / LDS latencies behind.  The dQ tile of tile i is drained two halves later (its MMA has
+// long completed), staged through the P^T chunk that is free at that moment.
 // A second tiny kernel scales the fp32 dQ sums and writes them in the caller's (strided, bf16) layout.
 // =================================================================================================================
 namespace {
 
-constexpr int DQ_LD = 68;  // floats per staged dQ row: 272 B, so that 16-byte stores of 8 lanes hit 8 different bank groups
-constexpr int BWD_SMEM = TILE * 10 + 1024 + 256 + 128 * DQ_LD * 4;
+constexpr int BQH = 64;            // queries per half tile
+constexpr int HTILE = BQH * 128;   // bytes of a [64 x 64] bf16 tile
+constexpr int NST = 3;             // Q / dO / statistics stages
+constexpr int BWD_EW = 16;         // element-wise warps (warps 0-15); then 4 dQ warps (16-19), Q/dO producer (20), MMA issuer
+                                   // (21), K/V producer + item scheduler (22), one idle warp (23) to fill the warpgroup
+constexpr int BWD_W_DQ = BWD_EW, BWD_W_QDO = BWD_EW + 4, BWD_W_MMA = BWD_EW + 5, BWD_W_KV = BWD_EW + 6, BWD_WARPS = BWD_EW + 8;
+// (K, V)[2] | Q[NST] | dO[NST] | P^T[2] | dS^T[4] | dQ staging (4 warps x 4 KB) | stats[NST][128] | barriers + announcements
+constexpr int BWD_OFF_Q = 4 * TILE, BWD_OFF_DO = BWD_OFF_Q + NST * HTILE, BWD_OFF_PT = BWD_OFF_DO + NST * HTILE,
+              BWD_OFF_DS = BWD_OFF_PT + 2 * TILE, BWD_OFF_DQS = BWD_OFF_DS + 4 * TILE, BWD_OFF_STAT = BWD_OFF_DQS + 4 * 4096,
+              BWD_OFF_BAR = BWD_OFF_STAT + NST * 128 * 4, BWD_SMEM = BWD_OFF_BAR + 256;
+static_assert(BWD_SMEM <= 227 * 1024, "backward attention kernel: shared memory");
 
 __device__ __forceinline__ void q_tile_range(const AttnTcArgs& a, int j0, int& qt0, int& qt1) {
   const int nqt = (a.Tq + BQ - 1) / BQ;
@@ -503,67 +577,176 @@ struct AttnBwdArgs {
   bf16* dk; long long dk_bs, dk_rs;
   bf16* dv; long long dv_bs, dv_rs;
   float scale;
+  unsigned long long* stamps;  // OMR_ATTN_DEBUG & 256: clock stamps of CTA 0 ([role][64])
+  int dbg;  // OMR_ATTN_DEBUG (timing experiments only, results are wrong): 1 = no dQ reds, 2 = no dQ epilogue, 4 = no element-wise math,
+            // 8 = no dQ MMAs, 16 = no dV / dK MMAs, 32 = no S^T / dP^T MMAs
 };
 
-__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
-  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+// shared -> global with an element-wise fp32 ADD performed by the TMA unit (bulk-group completion): the dQ tiles of the
+// key tiles of one (batch, head) meet in the fp32 accumulation buffer without a single SM-issued atomic
+__device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* m, const void* src, int c0, int c1, int c2) {
+  asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
 }
 
-__global__ void __launch_bounds__(320, 1) attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
-                                                             const __grid_constant__ CUtensorMap tmK,
-                                                             const __grid_constant__ CUtensorMap tmV,
-                                                             const __grid_constant__ CUtensorMap tmDO, AttnBwdArgs g) {
+// element-wise phase of one half tile for one thread: key row r, query columns [16 cg, 16 cg + 16) of the half
+struct BwdRow {
+  uint32_t tmem_s, tmem_dp;  // TMEM addresses of this thread's 16 S^T / dP^T values
+  const float* nlse;         // smem: -lse * log2(e) of the 64 queries of the half, followed by their 64 deltas
+  uint8_t* prow;             // this key row inside the P^T chunk / dS^T chunk (128 B per row, 128B-swizzled)
+  uint8_t* drow;
+  int unit0;                 // first 16-byte unit of the row this thread writes (2 units = 16 queries)
+  int r, j, t0;              // key row in the tile, key, first query of this thread's 16
+  int t_lo, t_hi;            // queries that can see key j
+  float bias, scale_log2;
+};
+
+template <bool MASKED, bool DROP, bool BIAS0>
+__device__ __forceinline__ void bwd_half_row(const BwdRow& w, uint32_t dstream, uint32_t dkp, uint32_t thr_hi, uint32_t dsh,
+                                             float inv_keep) {
+  uint32_t sv[16], dv[16];
+  tmem_ld16(w.tmem_s, sv);
+  tmem_ld16(w.tmem_dp, dv);
+  tmem_ld_wait();
+  uint32_t pk[8], dk[8];
+#pragma unroll
+  for (int e = 0; e < 16; e += 4) {
+    const float4 l4 = *reinterpret_cast<const float4*>(w.nlse + e);
+    const float4 d4 = *reinterpret_cast<const float4*>(w.nlse + 64 + e);
+    float ls[4] = {l4.x, l4.y, l4.z, l4.w};
+    const float dl[4] = {d4.x, d4.y, d4.z, d4.w};
+    float pr[4], fk[4] = {1.f, 1.f, 1.f, 1.f};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (!BIAS0) ls[k] += w.bias;
+      pr[k] = ex2_approx(fmaf(__uint_as_float(sv[e + k]), w.scale_log2, ls[k]));
+      if (MASKED) {
+        const int t = w.t0 + e + k;
+        pr[k] = (t >= w.t_lo && t <= w.t_hi) ? pr[k] : 0.f;
+      }
+    }
+    if (DROP) {  // mask / (1-p) of the pairs (t, j).  Keys j and j^1 (neighbouring lanes) share their 2 x 2 blocks: the
+      // even lane hashes the block of queries (t, t+1), the odd lane that of (t+2, t+3); both words travel.  The field
+      // of this key is moved to the top of the word (dsh = 16 for even keys, whose field sits in bits 0-14 -- bit 15 is
+      // shifted out of the way of the guard position by the mask below -- and 1 for odd keys) and compared in place.
+      const int t = w.t0 + e;
+      const uint2 mine = attn_drop_block(dstream, (uint32_t)((t >> 1) + (w.j & 1)), (uint32_t)(w.j >> 1), dkp);
+      const uint32_t ox = __shfl_xor_sync(0xffffffffu, mine.x, 1), oy = __shfl_xor_sync(0xffffffffu, mine.y, 1);
+      const uint2 b0 = (w.j & 1) ? make_uint2(ox, oy) : mine;  // queries (t, t+1)
+      const uint2 b1 = (w.j & 1) ? mine : make_uint2(ox, oy);  // queries (t+2, t+3)
+      // 15-bit field f at bits [dsh', dsh'+15): (word << dsh) puts it in bits 17..31 (even key: << 17; odd key: << 1),
+      // and f >= thr  <=>  (word << dsh) >= (thr << 17)   (the bits below bit 17 cannot change the outcome)
+      fk[0] = (b0.x << dsh) >= thr_hi ? inv_keep : 0.f;
+      fk[1] = (b0.y << dsh) >= thr_hi ? inv_keep : 0.f;
+      fk[2] = (b1.x << dsh) >= thr_hi ? inv_keep : 0.f;
+      fk[3] = (b1.y << dsh) >= thr_hi ? inv_keep : 0.f;
+    }
+    float ds[4], pd[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      ds[k] = pr[k] * (DROP ? fmaf(__uint_as_float(dv[e + k]), fk[k], -dl[k]) : __uint_as_float(dv[e + k]) - dl[k]);
+      pd[k] = DROP ? pr[k] * fk[k] : pr[k];
+    }
+    pk[e >> 1] = pack_bf16(pd[0], pd[1]);
+    pk[(e >> 1) + 1] = pack_bf16(pd[2], pd[3]);
+    dk[e >> 1] = pack_bf16(ds[0], ds[1]);
+    dk[(e >> 1) + 1] = pack_bf16(ds[2], ds[3]);
+  }
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const int sw = ((w.unit0 + u) ^ (w.r & 7)) << 4;
+    *reinterpret_cast<uint4*>(w.prow + sw) = make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
+    *reinterpret_cast<uint4*>(w.drow + sw) = make_uint4(dk[4 * u], dk[4 * u + 1], dk[4 * u + 2], dk[4 * u + 3]);
+  }
+}
+
+// one work item = one (key tile, head, batch); items are numbered key-tile-major so that a static round-robin over the
+// persistent CTAs hands everybody the same mix of long (early key tiles of a causal call) and short items
+struct BwdItem {
+  int kt, h, b, j0, qt0, nh;  // nh = half tiles of 64 queries (0: no query sees the tile)
+};
+__device__ __forceinline__ BwdItem bwd_item(const AttnTcArgs& a, int idx) {
+  BwdItem I;
+  const int bh = a.B * a.H;
+  I.kt = idx / bh;
+  const int rem = idx - I.kt * bh;
+  I.b = rem / a.H;
+  I.h = rem - I.b * a.H;
+  I.j0 = I.kt * BKV;
+  int qt1;
+  q_tile_range(a, I.j0, I.qt0, qt1);
+  I.nh = 2 * (qt1 - I.qt0);
+  return I;
+}
+
+// PERSISTENT: one CTA per SM walks its share of the (key tile, head, batch) items.  Measured on B200 with everything but
+// the skeleton switched off (OMR_ATTN_DEBUG=62): the one-CTA-per-item version spent 158 of its 260 us in launch, TMEM
+// allocation, barrier set-up, the K/V load latency and the drain of each CTA -- 2432 CTAs of four query tiles each.  Here
+// those happen once per SM: the producer warp runs ahead into the next item (K/V double-buffered, Q / dO / statistics
+// ring shared across items), the MMA warp's score MMAs run one half tile ahead across item boundaries, and the 16
+// element-wise warps drain an item's dK / dV (and its last dQ tile) while the next item's first half is in flight.
+// The producer announces each live item (index + "all key biases are zero" flag) in shared memory next to the K/V
+// barrier, and zero-fills the dK / dV rows of dead items (every key masked: the padded tail of the memory) itself.
+__global__ void __launch_bounds__(32 * BWD_WARPS, 1) attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
+                                                                       const __grid_constant__ CUtensorMap tmK,
+                                                                       const __grid_constant__ CUtensorMap tmV,
+                                                                       const __grid_constant__ CUtensorMap tmDO,
+                                                                       const __grid_constant__ CUtensorMap tmDQ,
+                                                                       AttnBwdArgs g) {
   omr_pdl_enter();
   extern __shared__ __align__(1024) uint8_t smem[];
   if (smem_u32(smem) & 1023u) __trap();
   const AttnTcArgs& a = g.f;
-  uint8_t* sK = smem;
-  uint8_t* sV = smem + TILE;
-  uint8_t* sQ = smem + 2 * TILE;   // [2]
-  uint8_t* sDO = smem + 4 * TILE;  // [2]
-  uint8_t* sPT = smem + 6 * TILE;  // 2 chunks of 64 queries
-  uint8_t* sDS = smem + 8 * TILE;  // 2 chunks of 64 queries
-  float* sLse = reinterpret_cast<float*>(smem + 10 * TILE);  // [128] (already * log2e)
-  float* sDelta = sLse + 128;                               // [128]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 10 * TILE + 1024);
-  float* sDQ = reinterpret_cast<float*>(smem + 10 * TILE + 1024 + 256);  // [128][DQ_LD] staging of a dQ tile
-  uint64_t* kv_full = bars;
-  uint64_t* qd_full = bars + 1;   // [2]
-  uint64_t* qd_empty = bars + 3;  // [2]
-  uint64_t* sdp_full = bars + 5;  // S^T and dP^T ready
-  uint64_t* pds_full = bars + 6;  // P^T and dS^T written (count 4)
-  uint64_t* mma2_done = bars + 7; // dV, dK, dQ MMAs of this q tile complete
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  uint8_t* sKV = smem;               // [2] x (K tile, V tile)
+  uint8_t* sQ = smem + BWD_OFF_Q;    // [NST] half tiles
+  uint8_t* sDO = smem + BWD_OFF_DO;  // [NST]
+  uint8_t* sPT = smem + BWD_OFF_PT;  // [2] chunks of [128 keys x 64 queries]
+  uint8_t* sDS = smem + BWD_OFF_DS;  // [4] chunks; chunks (0,1) and (2,3) are the two 128-query dS^T tiles in flight
+  float* sStat = reinterpret_cast<float*>(smem + BWD_OFF_STAT);  // [NST][-lse*log2e (64) | delta (64)]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BWD_OFF_BAR);
+  uint8_t* sDQS = smem + BWD_OFF_DQS;        // [4 dQ warps] x [32 query rows x 32 fp32 channels], 128B-swizzled
+  uint64_t* kv_full = bars;                  // [2] K, V of an item landed, item_idx / item_flag written
+  uint64_t* kv_empty = bars + 2;             // [2]
+  uint64_t* qd_full = bars + 4;              // [NST] Q, dO half tiles landed, statistics written
+  uint64_t* qd_empty = bars + 4 + NST;       // [NST]
+  uint64_t* sdp_full = bars + 4 + 2 * NST;   // [2] S^T and dP^T of a half ready in TMEM buffer uu & 1
+  uint64_t* pds_full = bars + 6 + 2 * NST;   // [2] P^T and dS^T chunks of a half written (count BWD_EW)
+  uint64_t* mma2_done = bars + 8 + 2 * NST;  // [2] dV, dK (, dQ) MMAs of a half complete
+  uint64_t* dq_free = bars + 10 + 2 * NST;   // the dQ warps have read the dQ accumulator of a tile (count 4)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11 + 2 * NST);
+  volatile int* item_idx = reinterpret_cast<volatile int*>(bars + 12 + 2 * NST);  // [2] item of K/V buffer i, -1 = no more
+  volatile int* item_flag = item_idx + 2;                                        // [2] bit 0: all key biases zero
+  volatile int* dq_info = item_idx + 4;  // [2][2] (batch*H + head, first query) of the dQ tile n & 1, written by warp 0
+  volatile int* dq_total = item_idx + 8; // number of dQ tiles of this CTA, -1 while the element-wise warps are running
 
   const int warp = (int)warp_idx_sync(), lane = threadIdx.x & 31;
-  const int j0 = blockIdx.x * BKV, h = blockIdx.y, b = blockIdx.z;
-  int qt0, qt1;
-  q_tile_range(a, j0, qt0, qt1);
-  // a key tile whose every key is masked out (bias = -inf: the padded tail of the memory) has P = 0 throughout:
-  // dK = dV = 0 and no contribution to dQ -- the CTA only writes the zeros
-  bool row_dead = true;
-  if (warp < 8) {
-    const int jr = j0 + (warp & 3) * 32 + lane;
-    row_dead = jr >= a.Tk || (a.key_bias && !(a.key_bias[(long long)b * a.Tk + jr] > -INFINITY));
-  }
-  const int ntiles = __syncthreads_and(row_dead) ? 0 : qt1 - qt0;
+  const int nkt = (a.Tk + BKV - 1) / BKV;
+  const int nitems = nkt * a.H * a.B;
 
-  if (warp == 8 && lane == 0) {
+  if (warp == BWD_W_QDO && lane == 0) {
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
     tma_prefetch_desc(&tmDO);
-    mbar_init(kv_full, 1);
-    for (int s = 0; s < 2; ++s) {
+    tma_prefetch_desc(&tmDQ);
+    *dq_total = -1;
+    mbar_init(dq_free, 4);
+    for (int s = 0; s < NST; ++s) {
       mbar_init(&qd_full[s], 1);
       mbar_init(&qd_empty[s], 1);
     }
-    mbar_init(sdp_full, 1);
-    mbar_init(pds_full, 8);
-    mbar_init(mma2_done, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&kv_full[s], 1);
+      mbar_init(&kv_empty[s], 1);
+      mbar_init(&sdp_full[s], 1);
+      mbar_init(&pds_full[s], BWD_EW);
+      mbar_init(&mma2_done[s], 1);
+    }
     fence_barrier_init();
   }
-  if (warp == 9) tmem_alloc(tmem_slot, 512);
+  if (warp == BWD_W_MMA) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -572,270 +755,416 @@ __global__ void __launch_bounds__(320, 1) attn_bwd_tc_kernel(const __grid_consta
                  tmem_DQ = tmem_base + 384;
 
   // warp-uniform producer / issuer loops, instructions under elect_one() (see tc_common.cuh)
-  if (warp == 8) {
-    if (ntiles > 0) {
-      if (elect_one()) {
-        mbar_expect_tx(kv_full, 2 * TILE);
-        tma_load_3d(sK, &tmK, kv_full, h * HD, j0, b);
-        tma_load_3d(sV, &tmV, kv_full, h * HD, j0, b);
-      }
-      for (int i = 0; i < ntiles; ++i) {
-        const int s = i & 1;
-        mbar_wait(&qd_empty[s], ((i >> 1) & 1) ^ 1);
-        if (elect_one()) {
-          mbar_expect_tx(&qd_full[s], 2 * TILE);
-          tma_load_3d(sQ + s * TILE, &tmQ, &qd_full[s], h * HD, (qt0 + i) * BQ, b);
-          tma_load_3d(sDO + s * TILE, &tmDO, &qd_full[s], h * HD, (qt0 + i) * BQ, b);
+  if (warp == BWD_W_KV) {
+    // ---- K / V producer and item scheduler: finds this CTA's live items, announces them (index + "all key biases are
+    // zero" flag next to the K/V barrier) and loads their K / V tiles up to two items ahead of the consumers, so that
+    // neither the liveness test (global loads) nor the K / V latency ever sits between two items.  Dead items on the way
+    // -- every key of the tile masked out (bias = -inf: the padded tail of the memory, or past Tk), or no query sees the
+    // tile: P = 0 throughout, dK = dV = 0 and no contribution to dQ -- get their zeros here.
+    int it = 0;
+    for (int idx = blockIdx.x;; idx += gridDim.x) {
+      bool live = false, b0 = true;
+      BwdItem I{};
+      if (idx < nitems) {
+        I = bwd_item(a, idx);
+        bool dead = true;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int j = I.j0 + i * 32 + lane;
+          float bv = -INFINITY;
+          if (j < a.Tk) bv = a.key_bias ? a.key_bias[(long long)I.b * a.Tk + j] : 0.f;
+          dead = dead && !(bv > -INFINITY);
+          b0 = b0 && bv == 0.f;
         }
-        __syncwarp();
-      }
-    }
-  } else if (warp == 9) {
-    if (ntiles > 0) {
-      constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
-      constexpr uint32_t idesc_kn = make_idesc_bf16(128, 64, 0, 1);  // A K-major (P^T / dS^T), B MN-major
-      constexpr uint32_t idesc_mn = make_idesc_bf16(128, 64, 1, 1);  // A MN-major (dS), B MN-major
-      mbar_wait(kv_full, 0);
-      const uint32_t k_addr = smem_u32(sK), v_addr = smem_u32(sV), pt_addr = smem_u32(sPT), ds_addr = smem_u32(sDS);
-      const uint32_t q_base = smem_u32(sQ), do_base = smem_u32(sDO);
-      for (int i = 0; i < ntiles; ++i) {
-        const int s = i & 1;
-        mbar_wait(&qd_full[s], (i >> 1) & 1);
-        tc_fence_after();
-        const uint32_t q_addr = q_base + (uint32_t)s * TILE, do_addr = do_base + (uint32_t)s * TILE;
-        if (elect_one()) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            if (j > 0)
-              umma_bf16_acc(tmem_ST, make_smem_desc(k_addr + j * 32, 16, 1024, 128), make_smem_desc(q_addr + j * 32, 16, 1024, 128), idesc_s);
-            else
-              umma_bf16_new(tmem_ST, make_smem_desc(k_addr, 16, 1024, 128), make_smem_desc(q_addr, 16, 1024, 128), idesc_s);
-          }
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            if (j > 0)
-              umma_bf16_acc(tmem_DPT, make_smem_desc(v_addr + j * 32, 16, 1024, 128), make_smem_desc(do_addr + j * 32, 16, 1024, 128), idesc_s);
-            else
-              umma_bf16_new(tmem_DPT, make_smem_desc(v_addr, 16, 1024, 128), make_smem_desc(do_addr, 16, 1024, 128), idesc_s);
-          }
-          umma_commit(sdp_full);
-        }
-        __syncwarp();
-        mbar_wait(pds_full, i & 1);
-        tc_fence_after();
-        if (elect_one()) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {  // dV += P^T dO
-            if (j > 0)
-              umma_bf16_acc(tmem_DV, make_smem_desc(pt_addr + (j >> 2) * TILE + (j & 3) * 32, 16, 1024, 128),
-                            make_smem_desc(do_addr + j * 2048, 0, 1024, 128), idesc_kn);
-            else
-              umma_bf16(tmem_DV, make_smem_desc(pt_addr, 16, 1024, 128), make_smem_desc(do_addr, 0, 1024, 128), idesc_kn, i > 0 ? 1u : 0u);
-          }
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {  // dK += dS^T Q
-            if (j > 0)
-              umma_bf16_acc(tmem_DK, make_smem_desc(ds_addr + (j >> 2) * TILE + (j & 3) * 32, 16, 1024, 128),
-                            make_smem_desc(q_addr + j * 2048, 0, 1024, 128), idesc_kn);
-            else
-              umma_bf16(tmem_DK, make_smem_desc(ds_addr, 16, 1024, 128), make_smem_desc(q_addr, 0, 1024, 128), idesc_kn, i > 0 ? 1u : 0u);
-          }
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {  // dQ_tile = dS K : A = dS^T tile read MN-major (M = queries: 2 chunks, K = key rows)
-            if (j > 0)
-              umma_bf16_acc(tmem_DQ, make_smem_desc(ds_addr + j * 2048, TILE, 1024, 128), make_smem_desc(k_addr + j * 2048, 0, 1024, 128), idesc_mn);
-            else
-              umma_bf16_new(tmem_DQ, make_smem_desc(ds_addr, TILE, 1024, 128), make_smem_desc(k_addr, 0, 1024, 128), idesc_mn);
-          }
-          umma_commit(mma2_done);
-          umma_commit(&qd_empty[s]);
-        }
-        __syncwarp();
-      }
-    }
-  } else {
-    // ---- 8 warps: thread = (key row r, column half hf) of the S^T / dP^T / dV / dK accumulators, and (query row r,
-    // column half) of the dQ accumulator.  Warps w and w+4 share TMEM lanes 32(w&3)..+31 and split the columns, so the
-    // exp/convert/store work of a tile is spread over twice the issue slots of a 4-warp epilogue. ----
-    const int r = (warp & 3) * 32 + lane;
-    const int hf = warp >> 2;
-    const int j = j0 + r;
-    const int off = a.Tk - a.Tq;
-    const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
-    const float bias = j < a.Tk ? (a.key_bias ? a.key_bias[(long long)b * a.Tk + j] * LOG2E : 0.f) : -INFINITY;
-    // queries that can see key j: t in [t_lo, t_hi]
-    int t_lo = 0, t_hi = a.Tq - 1;
-    if (a.causal) {
-      t_lo = max(0, j - off);
-      if (a.window > 0) t_hi = min(t_hi, j - off + a.window);
-    }
-    if (j >= a.Tk) t_hi = -1;
-    int lq, lkv;
-    block_mask_of(a, b, h, lq, lkv);
-    if (j >= lkv) t_hi = min(t_hi, lq - 1);
-    const long long stat_base = ((long long)b * a.H + h) * a.Tq;
-    const uint32_t dstream = a.drop.thr ? attn_drop_stream(a.drop, b * a.H + h) : 0u;
-    const uint32_t dkp = (uint32_t)((a.Tk + 1) >> 1), dsh = (uint32_t)(j & 1) * 16u;
-
-    // dQ tile -> fp32 accumulation buffer.  The accumulator row of a thread is 128 contiguous bytes, but a warp-wide
-    // red of one register group would touch 32 different lines; the tile is therefore transposed through shared memory
-    // (padded rows: conflict-free both ways) and added with reds that cover 512 contiguous bytes per warp instruction.
-    auto dq_epilogue = [&](int q_tile) {
-      softmax_bar2();  // the previous tile's readers are done with sDQ
-      {
-        uint32_t v[32];
-        tmem_ld32(tmem_DQ + lane_addr + hf * 32, v);
-        tmem_ld_wait();
-        float* rowp = sDQ + r * DQ_LD + hf * 32;
-#pragma unroll
-        for (int u = 0; u < 8; ++u)
-          *reinterpret_cast<float4*>(rowp + 4 * u) = make_float4(__uint_as_float(v[4 * u]), __uint_as_float(v[4 * u + 1]),
-                                                                  __uint_as_float(v[4 * u + 2]), __uint_as_float(v[4 * u + 3]));
-      }
-      softmax_bar2();
-      const int tid8 = threadIdx.x;  // 0..255: the eight epilogue warps
-#pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        const int L = it * 256 + tid8, row = L >> 4, c4 = L & 15;
-        const int t = q_tile * BQ + row;
-        const float4 x = *reinterpret_cast<const float4*>(sDQ + row * DQ_LD + c4 * 4);
-        if (t < a.Tq) red_add_v4(g.dq_acc + (stat_base + t) * HD + c4 * 4, x.x, x.y, x.z, x.w);
-      }
-    };
-
-    for (int i = 0; i < ntiles; ++i) {
-      const int q0 = (qt0 + i) * BQ;
-      softmax_bar2();  // readers of the previous tile's statistics are done
-      if (hf == 0) {
-        const int t = q0 + r;
-        sLse[r] = t < a.Tq ? a.lse[stat_base + t] * LOG2E : 0.f;
-        sDelta[r] = t < a.Tq ? g.delta[stat_base + t] : 0.f;
-      }
-      softmax_bar2();
-      mbar_wait(sdp_full, i & 1);
-      tc_fence_after();
-      if (i > 0) {
-        mbar_wait(mma2_done, (i - 1) & 1);  // P^T / dS^T tiles are free again, dQ of the previous q tile is complete
-        tc_fence_after();
-        dq_epilogue(qt0 + i - 1);
-      }
-      // every (query, key) pair of this tile visible?  (then no interval tests; rows past Tk carry bias = -inf)
-      bool full = q0 + BQ <= a.Tq && j0 + BKV <= a.Tk;
-      if (a.causal) full = full && q0 >= j0 + BKV - 1 - off && (a.window <= 0 || q0 + BQ - 1 <= j0 - off + a.window);
-      full = full && (j0 + BKV <= lkv || q0 + BQ <= lq);
-      auto tile_half = [&](auto masked_tag, auto drop_tag) {
-        constexpr bool MASKED = decltype(masked_tag)::value, DROP = decltype(drop_tag)::value;
+        dead = __all_sync(0xffffffffu, dead);
+        b0 = __all_sync(0xffffffffu, b0);
+        live = !dead && I.nh > 0;
+        if (!live) {
 #pragma unroll 1
-        for (int c = 2 * hf; c < 2 * hf + 2; ++c) {
-          uint32_t sv[32], dv[32];
-          tmem_ld32(tmem_ST + lane_addr + c * 32, sv);
-          tmem_ld32(tmem_DPT + lane_addr + c * 32, dv);
-          tmem_ld_wait();
-          uint32_t pk[16], dk[16];
+          for (int i = 0; i < 4; ++i) {
+            const int j = I.j0 + i * 32 + lane;
+            if (j < a.Tk) {
+              uint4* dkp_ = reinterpret_cast<uint4*>(g.dk + (long long)I.b * g.dk_bs + (long long)j * g.dk_rs + I.h * HD);
+              uint4* dvp_ = reinterpret_cast<uint4*>(g.dv + (long long)I.b * g.dv_bs + (long long)j * g.dv_rs + I.h * HD);
 #pragma unroll
-          for (int e = 0; e < 32; e += 4) {
-            const float4 l4 = *reinterpret_cast<const float4*>(sLse + c * 32 + e);
-            const float4 d4 = *reinterpret_cast<const float4*>(sDelta + c * 32 + e);
-            const float ls[4] = {bias - l4.x, bias - l4.y, bias - l4.z, bias - l4.w};
-            const float dl[4] = {d4.x, d4.y, d4.z, d4.w};
-            float pr[4], fk[4] = {1.f, 1.f, 1.f, 1.f};
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const int t = q0 + c * 32 + e + k;
-              pr[k] = ex2_approx(fmaf(__uint_as_float(sv[e + k]), a.scale_log2, ls[k]));
-              if (MASKED) pr[k] = (t >= t_lo && t <= t_hi) ? pr[k] : 0.f;
+              for (int u = 0; u < 8; ++u) {
+                dkp_[u] = make_uint4(0, 0, 0, 0);
+                dvp_[u] = make_uint4(0, 0, 0, 0);
+              }
             }
-            if (DROP) {  // mask / (1-p) of the pairs (t, j).  Keys j and j^1 (neighbouring lanes) share their 2 x 2 blocks:
-              // the even lane hashes the block of queries (t, t+1), the odd lane that of (t+2, t+3); both words travel
-              const int t = q0 + c * 32 + e;
-              const uint2 mine = attn_drop_block(dstream, (uint32_t)((t >> 1) + (j & 1)), (uint32_t)(j >> 1), dkp);
-              const uint32_t ox = __shfl_xor_sync(0xffffffffu, mine.x, 1), oy = __shfl_xor_sync(0xffffffffu, mine.y, 1);
-              const uint2 b0 = (j & 1) ? make_uint2(ox, oy) : mine;  // queries (t, t+1)
-              const uint2 b1 = (j & 1) ? mine : make_uint2(ox, oy);  // queries (t+2, t+3)
-              fk[0] = ((b0.x >> dsh) & 0xFFFFu) >= a.drop.thr ? a.drop.inv_keep : 0.f;
-              fk[1] = ((b0.y >> dsh) & 0xFFFFu) >= a.drop.thr ? a.drop.inv_keep : 0.f;
-              fk[2] = ((b1.x >> dsh) & 0xFFFFu) >= a.drop.thr ? a.drop.inv_keep : 0.f;
-              fk[3] = ((b1.y >> dsh) & 0xFFFFu) >= a.drop.thr ? a.drop.inv_keep : 0.f;
-            }
-            float ds[4], pd[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              ds[k] = pr[k] * (DROP ? fmaf(__uint_as_float(dv[e + k]), fk[k], -dl[k]) : __uint_as_float(dv[e + k]) - dl[k]);
-              pd[k] = DROP ? pr[k] * fk[k] : pr[k];
-            }
-            pk[e >> 1] = pack_bf16(pd[0], pd[1]);
-            pk[(e >> 1) + 1] = pack_bf16(pd[2], pd[3]);
-            dk[e >> 1] = pack_bf16(ds[0], ds[1]);
-            dk[(e >> 1) + 1] = pack_bf16(ds[2], ds[3]);
           }
-          uint8_t* prow = sPT + (c >> 1) * TILE + r * 128;
-          uint8_t* drow = sDS + (c >> 1) * TILE + r * 128;
+          continue;
+        }
+      }
+      const int kb = it & 1;
+      mbar_wait(&kv_empty[kb], ((it >> 1) & 1) ^ 1);
+      if (lane == 0) {
+        item_idx[kb] = live ? idx : -1;  // -1: no more items
+        item_flag[kb] = b0 ? 1 : 0;
+      }
+      __syncwarp();
+      if (elect_one()) {
+        if (live) {
+          mbar_expect_tx(&kv_full[kb], 2 * TILE);
+          tma_load_3d(sKV + kb * 2 * TILE, &tmK, &kv_full[kb], I.h * HD, I.j0, I.b);
+          tma_load_3d(sKV + kb * 2 * TILE + TILE, &tmV, &kv_full[kb], I.h * HD, I.j0, I.b);
+        } else {
+          mbar_arrive(&kv_full[kb]);
+        }
+      }
+      __syncwarp();
+      if (!live) break;
+      ++it;
+    }
+  } else if (warp == BWD_W_QDO) {
+    // ---- Q / dO / statistics producer: follows the announced items through the 4-stage ring of half tiles ----
+    uint32_t uu = 0;
+    for (int it = 0;; ++it) {
+      mbar_wait(&kv_full[it & 1], (it >> 1) & 1);
+      const int idx = item_idx[it & 1];
+      if (idx < 0) break;
+      const BwdItem I = bwd_item(a, idx);
+      const long long stat_base = ((long long)I.b * a.H + I.h) * a.Tq;
+      // the statistics of a half (-lse in log2 units and delta of its 64 queries) are fetched one half ahead, so that
+      // their latency hides behind the wait for the ring slot
+      float nl[2], dl[2];
+      auto load_stats = [&](int u, float (&n2)[2], float (&d2)[2]) {
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int sw = (((c & 1) * 4 + u) ^ (r & 7)) << 4;
-            *reinterpret_cast<uint4*>(prow + sw) = make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
-            *reinterpret_cast<uint4*>(drow + sw) = make_uint4(dk[4 * u], dk[4 * u + 1], dk[4 * u + 2], dk[4 * u + 3]);
-          }
+        for (int i = 0; i < 2; ++i) {
+          const int t = I.qt0 * BQ + u * BQH + i * 32 + lane;
+          n2[i] = (t < a.Tq && !(g.dbg & 128)) ? -a.lse[stat_base + t] * LOG2E : 0.f;
+          d2[i] = (t < a.Tq && !(g.dbg & 128)) ? g.delta[stat_base + t] : 0.f;
         }
       };
-      if (a.drop.thr) {
-        if (full) tile_half(std::false_type{}, std::true_type{});
-        else tile_half(std::true_type{}, std::true_type{});
-      } else {
-        if (full) tile_half(std::false_type{}, std::false_type{});
-        else tile_half(std::true_type{}, std::false_type{});
-      }
-      fence_proxy_async();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(pds_full);
-    }
-    if (ntiles > 0) {
-      mbar_wait(mma2_done, (ntiles - 1) & 1);
-      tc_fence_after();
-      dq_epilogue(qt0 + ntiles - 1);
-    }
-    // dK (x scale) and dV rows of this key
-    if (j < a.Tk) {
-      bf16* dkp = g.dk + (long long)b * g.dk_bs + (long long)j * g.dk_rs + h * HD;
-      bf16* dvp = g.dv + (long long)b * g.dv_bs + (long long)j * g.dv_rs + h * HD;
-      if (ntiles == 0) {
+      load_stats(0, nl, dl);
+      for (int u = 0; u < I.nh; ++u, ++uu) {
+        const int s = uu % NST, q0 = I.qt0 * BQ + u * BQH;
+        float nl2[2] = {0.f, 0.f}, dl2[2] = {0.f, 0.f};
+        if (u + 1 < I.nh) load_stats(u + 1, nl2, dl2);
+        mbar_wait(&qd_empty[s], ((uu / NST) & 1) ^ 1);
+        float* st = sStat + s * 128;  // plain stores, published by the arrive below
 #pragma unroll
-        for (int u = 4 * hf; u < 4 * hf + 4; ++u) {
-          reinterpret_cast<uint4*>(dkp)[u] = make_uint4(0, 0, 0, 0);
-          reinterpret_cast<uint4*>(dvp)[u] = make_uint4(0, 0, 0, 0);
+        for (int i = 0; i < 2; ++i) {
+          st[i * 32 + lane] = nl[i];
+          st[64 + i * 32 + lane] = dl[i];
+          nl[i] = nl2[i];
+          dl[i] = dl2[i];
         }
+        __syncwarp();
+        if (elect_one()) {
+          if (g.dbg & 64) {
+            mbar_arrive(&qd_full[s]);
+          } else {
+            mbar_expect_tx(&qd_full[s], 2 * HTILE);
+            tma_load_3d(sQ + s * HTILE, &tmQ, &qd_full[s], I.h * HD, q0, I.b);
+            tma_load_3d(sDO + s * HTILE, &tmDO, &qd_full[s], I.h * HD, q0, I.b);
+          }
+        }
+        __syncwarp();
+        if (g.stamps && blockIdx.x == 0 && lane == 0 && uu < 64) g.stamps[0 * 64 + uu] = clock64();
       }
     }
-    if (ntiles > 0) {
+  } else if (warp == BWD_W_MMA) {
+    // ---- MMA issuer.  Two cursors walk the same stream of half tiles: A issues the score MMAs (S^T, dP^T) one half
+    // ahead of B, which issues the gradient MMAs once the element-wise warps have written P^T / dS^T.  The warp POLLS
+    // both (no blocking wait): a late Q / dO tile must not hold back gradient MMAs whose inputs are ready, nor the
+    // other way round. ----
+    constexpr uint32_t idesc_s = make_idesc_bf16(128, 64, 0, 0);   // S^T / dP^T half: N = 64 queries
+    constexpr uint32_t idesc_kn = make_idesc_bf16(128, 64, 0, 1);  // A K-major (P^T / dS^T), B MN-major
+    constexpr uint32_t idesc_mn = make_idesc_bf16(128, 64, 1, 1);  // A MN-major (dS), B MN-major
+    const uint32_t kv_base = smem_u32(sKV), pt_base = smem_u32(sPT), ds_base = smem_u32(sDS);
+    const uint32_t q_base = smem_u32(sQ), do_base = smem_u32(sDO);
+    struct Cur {
+      int it, u, nh;
+      uint32_t uu;
+      bool ok, open;  // ok: a live item is open (or being opened); open: its announcement has not been seen yet
+    };
+    auto probe = [&](uint64_t* bar, uint32_t parity) { return bcast0(mbar_test(bar, parity) ? 1u : 0u) != 0; };
+    // next live item of this CTA, as announced by the K/V producer (non-blocking: c.open stays set until it is there)
+    auto open_item = [&](Cur& c) {
+      c.open = true;
+      if (!probe(&kv_full[c.it & 1], (c.it >> 1) & 1)) return;
+      tc_fence_after();
+      const int idx = item_idx[c.it & 1];
+      c.open = false;
+      c.ok = idx >= 0;
+      c.u = 0;
+      c.nh = c.ok ? bwd_item(a, idx).nh : 0;
+    };
+    auto step = [&](Cur& c) {
+      ++c.u;
+      ++c.uu;
+      if (c.u == c.nh) {
+        ++c.it;
+        open_item(c);
+      }
+    };
+    Cur A{0, 0, 0, 0u, true, true};
+    Cur Bc = A;
+    uint32_t nt = 0;  // dQ tiles issued so far
+    for (;;) {
+      // --- scores of half A.uu into TMEM buffer A.uu & 1 (last read by the element-wise phase of half A.uu - 2, whose
+      // completion cursor B has seen: A never runs more than one half ahead of B's next half) ---
+      if (A.open) open_item(A);
+      if (A.ok && !A.open && A.uu <= Bc.uu + 1 && probe(&qd_full[A.uu % NST], (A.uu / NST) & 1)) {
+        tc_fence_after();
+        const int s = A.uu % NST;
+        const uint32_t k_addr = kv_base + (uint32_t)(A.it & 1) * 2 * TILE, v_addr = k_addr + TILE;
+        const uint32_t q_addr = q_base + (uint32_t)s * HTILE, do_addr = do_base + (uint32_t)s * HTILE;
+        const uint32_t dS = tmem_ST + (A.uu & 1) * 64, dP = tmem_DPT + (A.uu & 1) * 64;
+        if (elect_one()) {
+          if (!(g.dbg & 32)) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              if (j > 0)
+                umma_bf16_acc(dS, make_smem_desc(k_addr + j * 32, 16, 1024, 128), make_smem_desc(q_addr + j * 32, 16, 1024, 128), idesc_s);
+              else
+                umma_bf16_new(dS, make_smem_desc(k_addr, 16, 1024, 128), make_smem_desc(q_addr, 16, 1024, 128), idesc_s);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              if (j > 0)
+                umma_bf16_acc(dP, make_smem_desc(v_addr + j * 32, 16, 1024, 128), make_smem_desc(do_addr + j * 32, 16, 1024, 128), idesc_s);
+              else
+                umma_bf16_new(dP, make_smem_desc(v_addr, 16, 1024, 128), make_smem_desc(do_addr, 16, 1024, 128), idesc_s);
+            }
+          }
+          umma_commit(&sdp_full[A.uu & 1]);
+        }
+        __syncwarp();
+        if (g.stamps && blockIdx.x == 0 && lane == 0 && A.uu < 64) g.stamps[1 * 64 + A.uu] = clock64();
+        step(A);
+      }
+      // --- gradients of half Bc.uu ---
+      if (Bc.open) open_item(Bc);
+      if (!Bc.open && !Bc.ok) break;  // the end marker
+      // (the dQ accumulator is single-buffered: the dQ MMA of a tile waits until the dQ warps have read the previous one)
+      if (Bc.ok && !Bc.open && A.uu > Bc.uu && probe(&pds_full[Bc.uu & 1], (Bc.uu >> 1) & 1) &&
+          (!(Bc.uu & 1) || nt == 0 || probe(dq_free, (nt - 1) & 1))) {
+        tc_fence_after();
+        const uint32_t uu = Bc.uu;
+        const int s = uu % NST;
+        const uint32_t k_addr = kv_base + (uint32_t)(Bc.it & 1) * 2 * TILE;
+        const uint32_t q_addr = q_base + (uint32_t)s * HTILE, do_addr = do_base + (uint32_t)s * HTILE;
+        const uint32_t pt_addr = pt_base + (uu & 1) * TILE, ds_addr = ds_base + (uu & 3) * TILE;
+        if (elect_one()) {
+          if (!(g.dbg & 16)) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {  // dV += P^T dO   (reduction over the 64 queries of the half)
+              if (j > 0)
+                umma_bf16_acc(tmem_DV, make_smem_desc(pt_addr + j * 32, 16, 1024, 128), make_smem_desc(do_addr + j * 2048, 0, 1024, 128), idesc_kn);
+              else
+                umma_bf16(tmem_DV, make_smem_desc(pt_addr, 16, 1024, 128), make_smem_desc(do_addr, 0, 1024, 128), idesc_kn, Bc.u > 0 ? 1u : 0u);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {  // dK += dS^T Q
+              if (j > 0)
+                umma_bf16_acc(tmem_DK, make_smem_desc(ds_addr + j * 32, 16, 1024, 128), make_smem_desc(q_addr + j * 2048, 0, 1024, 128), idesc_kn);
+              else
+                umma_bf16(tmem_DK, make_smem_desc(ds_addr, 16, 1024, 128), make_smem_desc(q_addr, 0, 1024, 128), idesc_kn, Bc.u > 0 ? 1u : 0u);
+            }
+          }
+          if ((uu & 1) && !(g.dbg & 8)) {  // dQ_tile = dS K : A = both dS^T chunks of the tile read MN-major (M = 128 queries, K = key rows)
+            const uint32_t ds2 = ds_base + ((uu & 3) - 1) * TILE;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              if (j > 0)
+                umma_bf16_acc(tmem_DQ, make_smem_desc(ds2 + j * 2048, TILE, 1024, 128), make_smem_desc(k_addr + j * 2048, 0, 1024, 128), idesc_mn);
+              else
+                umma_bf16_new(tmem_DQ, make_smem_desc(ds2, TILE, 1024, 128), make_smem_desc(k_addr, 0, 1024, 128), idesc_mn);
+            }
+          }
+          umma_commit(&mma2_done[uu & 1]);
+          umma_commit(&qd_empty[s]);
+          if (Bc.u == Bc.nh - 1) umma_commit(&kv_empty[Bc.it & 1]);
+        }
+        __syncwarp();
+        if (g.stamps && blockIdx.x == 0 && lane == 0 && Bc.uu < 64) g.stamps[2 * 64 + Bc.uu] = clock64();
+        nt += Bc.uu & 1;
+        step(Bc);
+      }
+    }
+  } else if (warp >= BWD_W_DQ && warp < BWD_W_DQ + 4) {
+    // ---- dQ warps: warp q drains TMEM lanes 32q .. 32q+31 (query rows) of each finished dQ tile, 32 channels at a time,
+    // into its own 4 KB staging tile and hands it to the TMA unit, which ADDS it to the fp32 accumulation buffer
+    // (cp.reduce.async.bulk.tensor; rows past Tq are clipped by the tensor map).  Round 1 did this on the element-wise
+    // warps with a shared-memory transpose and red.global.add.v4: 1770 clk per tile on the critical path (measured).
+    const int q = warp & 3;
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    uint8_t* stage = sDQS + q * 4096;
+    for (uint32_t n = 0;; ++n) {
+      bool done = false;
+      while (!bcast0(mbar_try(&mma2_done[1], n & 1) ? 1u : 0u)) {  // the odd half of tile n (global half 2n+1)
+        const int tot = *dq_total;
+        if (tot >= 0 && n >= (uint32_t)tot) { done = true; break; }
+      }
+      if (done) break;
+      tc_fence_after();
+      const int bh = dq_info[(n & 1) * 2], t0 = dq_info[(n & 1) * 2 + 1];
+#pragma unroll 1
+      for (int c = 0; c < 2; ++c) {
+        uint32_t v[32];
+        tmem_ld32(tmem_DQ + lane_addr + c * 32, v);
+        if (elect_one()) tma_store_wait_read<0>();  // the staging tile's previous reduction has been read
+        __syncwarp();
+        tmem_ld_wait();
+        if (c == 1) {  // both halves are in registers / staged: the accumulator may be overwritten
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(dq_free);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          *reinterpret_cast<uint4*>(stage + lane * 128 + ((u ^ (lane & 7)) << 4)) = make_uint4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
+        fence_proxy_async();
+        __syncwarp();
+        if (elect_one() && !(g.dbg & 3)) {
+          tma_reduce_add_3d(&tmDQ, stage, c * 32, t0 + q * 32, bh);
+          tma_store_commit();
+        }
+        __syncwarp();
+      }
+    }
+    if (elect_one()) tma_store_wait_all();
+    __syncwarp();
+  } else if (warp < BWD_EW) {
+    // ---- 16 element-wise warps: thread = (key row r, 16-column group cg) of the S^T / dP^T / dV / dK accumulators and
+    // (query row r, 16-column group) of the dQ accumulator ----
+    const int lq = warp & 3, cg = warp >> 2;
+    const int r = lq * 32 + lane;
+    const int off = a.Tk - a.Tq;
+    const uint32_t lane_addr = (uint32_t)(lq * 32) << 16;
+    const uint32_t dseed = a.drop.thr ? attn_drop_seed(a.drop) : 0u;
+    const uint32_t dkp = (uint32_t)((a.Tk + 1) >> 1), dsh = (r & 1) ? 1u : 17u, thr_hi = a.drop.thr << 17;
+    const float ik = a.drop.inv_keep;
+
+    // dK (x scale) and dV rows of key j of (b, h): 16 columns per thread
+    auto dkv_epilogue = [&](int b, int h, int j) {
 #pragma unroll
       for (int which = 0; which < 2; ++which) {
         const float mul = which == 0 ? g.scale : 1.f;
-        bf16* dst = which == 0 ? g.dk + (long long)b * g.dk_bs + (long long)j * g.dk_rs + h * HD
-                               : g.dv + (long long)b * g.dv_bs + (long long)j * g.dv_rs + h * HD;
-        {
-          const int c = hf;
-          uint32_t v[32];
-          tmem_ld32((which == 0 ? tmem_DK : tmem_DV) + lane_addr + c * 32, v);
-          tmem_ld_wait();
-          if (j < a.Tk) {
+        bf16* dst = which == 0 ? g.dk + (long long)b * g.dk_bs + (long long)j * g.dk_rs + h * HD + cg * 16
+                               : g.dv + (long long)b * g.dv_bs + (long long)j * g.dv_rs + h * HD + cg * 16;
+        uint32_t v[16];
+        tmem_ld16((which == 0 ? tmem_DK : tmem_DV) + lane_addr + cg * 16, v);
+        tmem_ld_wait();
+        if (j < a.Tk) {
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              uint4 o4;
-              o4.x = pack_bf16(__uint_as_float(v[8 * u]) * mul, __uint_as_float(v[8 * u + 1]) * mul);
-              o4.y = pack_bf16(__uint_as_float(v[8 * u + 2]) * mul, __uint_as_float(v[8 * u + 3]) * mul);
-              o4.z = pack_bf16(__uint_as_float(v[8 * u + 4]) * mul, __uint_as_float(v[8 * u + 5]) * mul);
-              o4.w = pack_bf16(__uint_as_float(v[8 * u + 6]) * mul, __uint_as_float(v[8 * u + 7]) * mul);
-              reinterpret_cast<uint4*>(dst)[c * 4 + u] = o4;
-            }
+          for (int u = 0; u < 2; ++u) {
+            uint4 o4;
+            o4.x = pack_bf16(__uint_as_float(v[8 * u]) * mul, __uint_as_float(v[8 * u + 1]) * mul);
+            o4.y = pack_bf16(__uint_as_float(v[8 * u + 2]) * mul, __uint_as_float(v[8 * u + 3]) * mul);
+            o4.z = pack_bf16(__uint_as_float(v[8 * u + 4]) * mul, __uint_as_float(v[8 * u + 5]) * mul);
+            o4.w = pack_bf16(__uint_as_float(v[8 * u + 6]) * mul, __uint_as_float(v[8 * u + 7]) * mul);
+            reinterpret_cast<uint4*>(dst)[u] = o4;
           }
         }
       }
+    };
+    auto row_bias = [&](int idx) -> float {  // this thread's key bias (log2 units) in item idx
+      const BwdItem I = bwd_item(a, idx);
+      const int j = I.j0 + r;
+      if (j >= a.Tk) return -INFINITY;
+      return a.key_bias ? a.key_bias[(long long)I.b * a.Tk + j] * LOG2E : 0.f;
+    };
+
+    int it = 0;
+    uint32_t uu = 0;
+    bool pend_kv = false;
+    int prev_b = 0, prev_h = 0, prev_j = 0;
+    mbar_wait(&kv_full[0], 0);
+    int idx = item_idx[0];
+    float bias = idx >= 0 ? row_bias(idx) : 0.f;
+    while (idx >= 0) {
+      const BwdItem I = bwd_item(a, idx);
+      const bool bias0 = (item_flag[it & 1] & 1) != 0;
+      const int j = I.j0 + r;
+      // queries that can see key j: t in [t_lo, t_hi]
+      int t_lo = 0, t_hi = a.Tq - 1;
+      if (a.causal) {
+        t_lo = max(0, j - off);
+        if (a.window > 0) t_hi = min(t_hi, j - off + a.window);
+      }
+      if (j >= a.Tk) t_hi = -1;
+      int lqm, lkv;
+      block_mask_of(a, I.b, I.h, lqm, lkv);
+      if (j >= lkv) t_hi = min(t_hi, lqm - 1);
+      const uint32_t dstream = a.drop.thr ? attn_drop_stream_of(dseed, I.b * a.H + I.h) : 0u;
+      int idx_next = -1;
+      float bias_next = 0.f;
+      for (int u = 0; u < I.nh; ++u, ++uu) {
+        const int s = uu % NST, bsel = uu & 1;
+        const int q0 = I.qt0 * BQ + u * BQH;
+        if (uu >= 2) {
+          mbar_wait(&mma2_done[bsel], ((uu >> 1) - 1) & 1);  // P^T chunk uu & 1 and dS^T chunk uu & 3 are free again
+          tc_fence_after();
+        }
+        if (u == I.nh - 1) {  // the producer has long announced the next item: fetch this thread's bias for it now
+          mbar_wait(&kv_full[(it + 1) & 1], ((it + 1) >> 1) & 1);
+          idx_next = item_idx[(it + 1) & 1];
+          if (idx_next >= 0) bias_next = row_bias(idx_next);
+        }
+        if (g.stamps && blockIdx.x == 0 && threadIdx.x == 0 && uu < 64) g.stamps[3 * 64 + uu] = clock64();
+        mbar_wait(&qd_full[s], (uu / NST) & 1);  // statistics of the half
+        mbar_wait(&sdp_full[bsel], (uu >> 1) & 1);
+        tc_fence_after();
+        if (g.stamps && blockIdx.x == 0 && threadIdx.x == 0 && uu < 64) g.stamps[4 * 64 + uu] = clock64();
+        // every (query, key) pair of this half visible?  (then no interval tests; rows past Tk carry bias = -inf)
+        bool full = q0 + BQH <= a.Tq && I.j0 + BKV <= a.Tk;
+        if (a.causal) full = full && q0 >= I.j0 + BKV - 1 - off && (a.window <= 0 || q0 + BQH - 1 <= I.j0 - off + a.window);
+        full = full && (I.j0 + BKV <= lkv || q0 + BQH <= lqm);
+        BwdRow w;
+        w.tmem_s = tmem_ST + bsel * 64 + lane_addr + cg * 16;
+        w.tmem_dp = tmem_DPT + bsel * 64 + lane_addr + cg * 16;
+        w.nlse = sStat + s * 128 + cg * 16;
+        w.prow = sPT + bsel * TILE + r * 128;
+        w.drow = sDS + (uu & 3) * TILE + r * 128;
+        w.unit0 = cg * 2;
+        w.r = r; w.j = j; w.t0 = q0 + cg * 16;
+        w.t_lo = t_lo; w.t_hi = t_hi;
+        w.bias = bias; w.scale_log2 = a.scale_log2;
+        if (g.dbg & 4) {
+        } else if (a.drop.thr) {
+          if (!full) bwd_half_row<true, true, false>(w, dstream, dkp, thr_hi, dsh, ik);
+          else if (bias0) bwd_half_row<false, true, true>(w, dstream, dkp, thr_hi, dsh, ik);
+          else bwd_half_row<false, true, false>(w, dstream, dkp, thr_hi, dsh, ik);
+        } else {
+          if (!full) bwd_half_row<true, false, false>(w, dstream, dkp, thr_hi, dsh, ik);
+          else if (bias0) bwd_half_row<false, false, true>(w, dstream, dkp, thr_hi, dsh, ik);
+          else bwd_half_row<false, false, false>(w, dstream, dkp, thr_hi, dsh, ik);
+        }
+        if (u == 0 && pend_kv) {  // the previous item's dK / dV leave TMEM before this item's first gradient MMA overwrites them
+          mbar_wait(&mma2_done[1], ((uu - 1) >> 1) & 1);
+          tc_fence_after();
+          dkv_epilogue(prev_b, prev_h, prev_j);
+          pend_kv = false;
+        }
+        if ((u & 1) && threadIdx.x == 0) {  // where the dQ tile completed by this half belongs (read by the dQ warps)
+          dq_info[((uu >> 1) & 1) * 2] = I.b * a.H + I.h;
+          dq_info[((uu >> 1) & 1) * 2 + 1] = (I.qt0 + (u >> 1)) * BQ;
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&pds_full[bsel]);
+        if (g.stamps && blockIdx.x == 0 && threadIdx.x == 0 && uu < 64) g.stamps[5 * 64 + uu] = clock64();
+      }
+      pend_kv = true;
+      prev_b = I.b; prev_h = I.h; prev_j = j;
+      ++it;
+      idx = idx_next;
+      bias = bias_next;
     }
+    if (uu > 0) {
+      mbar_wait(&mma2_done[1], ((uu - 1) >> 1) & 1);  // the last (odd) half: every MMA of this CTA has completed
+      tc_fence_after();
+      if (pend_kv) dkv_epilogue(prev_b, prev_h, prev_j);
+    }
+    if (threadIdx.x == 0) *dq_total = (int)(uu >> 1);
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 9) {
+  if (warp == BWD_W_MMA) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
@@ -894,18 +1223,27 @@ int omr_attn_bwd_tc(const void* q, long long q_bs, long long q_rs, const void* k
       !al(dq, dq_bs, dq_rs) || !al(dk, dk_bs, dk_rs) || !al(dv, dv_bs, dv_rs))
     return OMR_TC_NOT_ELIGIBLE;
   CUtensorMap tmQ, tmK, tmV, tmDO;
-  int rc = make_head_map(&tmQ, q, q_bs, q_rs, B, Tq, H, BQ);
+  int rc = make_head_map(&tmQ, q, q_bs, q_rs, B, Tq, H, BQH);
   if (rc) return rc;
   rc = make_head_map(&tmK, k, k_bs, k_rs, B, Tk, H, BKV);
   if (rc) return rc;
   rc = make_head_map(&tmV, v, v_bs, v_rs, B, Tk, H, BKV);
   if (rc) return rc;
-  rc = make_head_map(&tmDO, dout, do_bs, do_rs, B, Tq, H, BQ);
+  rc = make_head_map(&tmDO, dout, do_bs, do_rs, B, Tq, H, BQH);
   if (rc) return rc;
   const long long rows = (long long)B * H * Tq;
+  if ((long long)B * H > 0x7fffffffll) return OMR_TC_NOT_ELIGIBLE;
   float* delta = ws;
   float* dq_acc = ws + ((rows + 3) / 4) * 4;  // keep the accumulators 16-byte aligned
   OMR_CUDA(cudaMemsetAsync(dq_acc, 0, sizeof(float) * (size_t)rows * HD, st));
+  CUtensorMap tmDQ;  // fp32 [B*H][Tq][64], boxes of 32 rows x 32 channels
+  {
+    unsigned long long dims[3] = {(unsigned long long)HD, (unsigned long long)Tq, (unsigned long long)B * H};
+    unsigned long long strides[2] = {(unsigned long long)HD * 4, (unsigned long long)Tq * HD * 4};
+    unsigned int box[3] = {32u, 32u, 1u};
+    rc = omr_make_tensor_map(&tmDQ, 4, dq_acc, 3, dims, strides, box, nullptr, 128);
+    if (rc) return rc;
+  }
   OmrLaunch((unsigned)((rows * 32 + 255) / 256), 256, 0, st)(attn_delta_tc_kernel, (const bf16*)o, o_bs, o_rs, (const bf16*)dout, do_bs, do_rs,
                                                                             delta, B, H, Tq);
   OMR_LAUNCHED();
@@ -916,14 +1254,51 @@ int omr_attn_bwd_tc(const void* q, long long q_bs, long long q_rs, const void* k
   g.dk = (bf16*)dk; g.dk_bs = dk_bs; g.dk_rs = dk_rs;
   g.dv = (bf16*)dv; g.dv_bs = dv_bs; g.dv_rs = dv_rs;
   g.scale = scale;
+  static int dbg = -1;
+  if (dbg < 0) {
+    const char* e = getenv("OMR_ATTN_DEBUG");
+    dbg = e ? atoi(e) : 0;
+  }
+  g.dbg = dbg;
+  static unsigned long long* stamps = nullptr;
+  if ((dbg & 256) && !stamps) {
+    cudaMalloc(&stamps, 6 * 64 * 8);
+    cudaMemset(stamps, 0, 6 * 64 * 8);
+  }
+  g.stamps = stamps;
   static bool configured = false;
   if (!configured) {
     OMR_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM));
     configured = true;
   }
-  dim3 grid((unsigned)((Tk + BKV - 1) / BKV), (unsigned)H, (unsigned)B);
-  OmrLaunch(grid, 320, BWD_SMEM, st)(attn_bwd_tc_kernel, tmQ, tmK, tmV, tmDO, g);
+  const long long nitems = (long long)((Tk + BKV - 1) / BKV) * H * B;
+  if (nitems > (1ll << 30)) return OMR_TC_NOT_ELIGIBLE;
+  static int n_sm = 0;
+  if (!n_sm) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    if (n_sm <= 0) n_sm = 148;
+  }
+  const unsigned grid = (unsigned)(nitems < n_sm ? nitems : n_sm);  // persistent: one CTA per SM
+  OmrLaunch(grid, 32 * BWD_WARPS, BWD_SMEM, st)(attn_bwd_tc_kernel, tmQ, tmK, tmV, tmDO, tmDQ, g);
   OMR_LAUNCHED();
+  if (stamps) {  // debugging aid: clock stamps of CTA 0's first 64 half tiles, relative to the first one
+    static int printed = 0;
+    unsigned long long h[6 * 64];
+    cudaStreamSynchronize(st);
+    cudaMemcpy(h, stamps, sizeof(h), cudaMemcpyDeviceToHost);
+    if (printed++ == 3) {
+      unsigned long long t0 = h[0];
+      for (int i = 0; i < 6 * 64; ++i) if (h[i] && h[i] < t0) t0 = h[i];
+      const char* names[6] = {"qdo_issued", "scores_issued", "grads_issued", "ew_begin", "ew_inputs_ready", "ew_arrived"};
+      for (int r = 0; r < 6; ++r) {
+        fprintf(stderr, "%-16s", names[r]);
+        for (int i = 0; i < 40; ++i) fprintf(stderr, " %6lld", h[r * 64 + i] ? (long long)(h[r * 64 + i] - t0) : -1ll);
+        fprintf(stderr, "\n");
+      }
+    }
+  }
   OmrLaunch((unsigned)((rows * 8 + 255) / 256), 256, 0, st)(attn_dq_finalize_kernel, dq_acc, (bf16*)dq, dq_bs, dq_rs, B, H, Tq, scale);
   OMR_LAUNCHED();
   return OMR_OK;

@@ -168,8 +168,9 @@ void take_dropout() {
 const AttnDrop& omr_attn_cur_dropout() { return g_drop_cur; }
 extern "C" int omr_attn_next_dropout(float p, unsigned int seed, const int* seed_off) {
   OMR_REQUIRE(p >= 0.f && p < 1.f, "omr_attn_next_dropout: p must be in [0, 1) (got %f)", (double)p);
-  const unsigned int thr = (unsigned int)(p * 65536.f + 0.5f);
-  g_drop_next = AttnDrop{seed, seed_off, thr, thr ? 65536.f / (float)(65536u - thr) : 1.f};
+  unsigned int thr = (unsigned int)(p * 32768.f + 0.5f);  // 15-bit uniforms (attn_drop.cuh)
+  if (thr > 32767u) thr = 32767u;
+  g_drop_next = AttnDrop{seed, seed_off, thr, thr ? 32768.f / (float)(32768u - thr) : 1.f};
   return OMR_OK;
 }
 

@@ -1,0 +1,4 @@
+#!/bin/bash
+set -u
+timeout 600 python -m pytest tests/test_gpu_tc.py tests/test_gpu_ops.py -m gpu -q -x -k "attention or attn" > gpurun_out/t_attn.log 2>&1; echo "pytest attn rc=$?"; tail -8 gpurun_out/t_attn.log
+for d in 0 2 4 6 62; do echo "OMR_ATTN_DEBUG=$d"; OMR_ATTN_DEBUG=$d timeout 200 python scripts/bench_attn.py 20 2>&1 | grep "self\|cross"; done
