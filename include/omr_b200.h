@@ -244,6 +244,25 @@ int omr_ce_bwd(int dt, const void* logits, long long ld, const long long* target
                const float* loss_out, const float* gscale, void* dlogits, long long rows, int V,
                long long ignore_index, omr_stream_t stream);
 
+/* Classifier FUSED with the softmax cross-entropy (out_layer of decoder.py:145-146 + CrossEntropyLoss of
+ * model.py:109,166,444,588) -- the [rows, V] logits are never written (bf16 tensor-core path, D = 256 only):
+ * x [rows, D] (row stride x_ld), w [V, D] (row stride w_ld), bias fp32 [V] or NULL, targets int64 [rows].
+ * omr_proj_ce_supported: 1 if the fused kernels serve (dt, D) on this build / device setting, else 0 (the caller then
+ * uses omr_gemm + omr_ce_fwd / omr_ce_bwd).  forward: row_loss / row_lse as omr_ce_fwd, follow with omr_ce_reduce.
+ * backward: dx [rows, D] = dL/dx (dt) on one call; dw [V, D] / db [V] (fp32, ACCUMULATED into, db may be NULL) on the
+ * other -- two entry points so that the weight gradient can run on a side stream. */
+int omr_proj_ce_supported(int dt, int D);
+int omr_proj_ce_fwd(int dt, const void* x, long long x_ld, const void* w, long long w_ld, const float* bias,
+                    const long long* targets, long long rows, int V, int D, long long ignore_index, float* row_loss,
+                    float* row_lse, omr_stream_t stream);
+int omr_proj_ce_bwd_dx(int dt, const void* x, long long x_ld, const void* w, long long w_ld, const float* bias,
+                       const long long* targets, const float* row_lse, const float* loss_out, const float* gscale,
+                       long long rows, int V, int D, long long ignore_index, void* dx, long long dx_ld,
+                       omr_stream_t stream);
+int omr_proj_ce_bwd_dw(int dt, const void* x, long long x_ld, const void* w, long long w_ld, const float* bias,
+                       const long long* targets, const float* row_lse, const float* loss_out, const float* gscale,
+                       long long rows, int V, int D, long long ignore_index, float* dw, float* db, omr_stream_t stream);
+
 /* ---- optimizer (torch.optim.Adam(lr=1e-4), model.py:134-139,475-483) ------------------- */
 /* One fused multi-tensor Adam step.  `table` is a device array of n_tensors omr_adam_entry;
  * `step` is a device int32 scalar that the kernel reads (the host increments it via

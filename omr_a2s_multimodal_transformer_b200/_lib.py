@@ -50,6 +50,9 @@ _SIGS = {
     "omr_ce_fwd": "ipqpqiqppp",
     "omr_ce_reduce": "ppqqpp",
     "omr_ce_bwd": "ipqpppppqiqp",
+    "omr_proj_ce_fwd": "ipqpqppqiiqppp",
+    "omr_proj_ce_bwd_dx": "ipqpqpppppqiiqpqp",
+    "omr_proj_ce_bwd_dw": "ipqpqpppppqiiqppp",
     "omr_adam_tick": "pp",
     "omr_adam_step": "piqpdddddp",
     "omr_argmax_step": "ipqiipppqqppiipp",
@@ -85,6 +88,8 @@ def load() -> ctypes.CDLL:
     lib.omr_decode_persistent_scratch_floats.argtypes = [c_int, c_int, c_int, c_int]
     lib.omr_tensor_core_path_enabled.restype = c_int
     lib.omr_set_tensor_core_path.argtypes = [c_int]
+    lib.omr_proj_ce_supported.restype = c_int
+    lib.omr_proj_ce_supported.argtypes = [c_int, c_int]
     for name, sig in _SIGS.items():
         fn = getattr(lib, name)
         fn.restype = c_int
@@ -95,7 +100,7 @@ def load() -> ctypes.CDLL:
 
 def exported_symbols():
     return ["omr_abi_version", "omr_last_error", "omr_launch_count", "omr_tc_call_count", "omr_tensor_core_path_enabled",
-            "omr_set_tensor_core_path", "omr_decode_persistent_scratch_floats"] + list(_SIGS)
+            "omr_set_tensor_core_path", "omr_decode_persistent_scratch_floats", "omr_proj_ce_supported"] + list(_SIGS)
 
 
 def check(rc: int, what: str) -> None:
@@ -170,6 +175,10 @@ def _work(name: str, a) -> tuple:
             return 0.0, float(_ESZ[a[0]]) * a[4] * a[5]
         if name == "omr_ce_bwd":
             return 0.0, 2.0 * _ESZ[a[0]] * a[8] * a[9]
+        if name == "omr_proj_ce_fwd":  # rows, V, D = a[7:10]: one GEMM; reads x and w, writes two floats per row
+            return 2.0 * a[7] * a[8] * a[9], 2.0 * (a[7] + a[8]) * a[9] + 8.0 * a[7]
+        if name in ("omr_proj_ce_bwd_dx", "omr_proj_ce_bwd_dw"):  # rows, V, D = a[10:13]: scores recomputed + one gradient GEMM
+            return 4.0 * a[10] * a[11] * a[12], 2.0 * (a[10] + a[11]) * a[12] + (2.0 * a[10] if name.endswith("dx") else 4.0 * a[11]) * a[12]
         if name == "omr_adam_step":
             return 0.0, 0.0  # filled in by the caller (needs the parameter count)
         if name == "omr_attn_decode":

@@ -207,3 +207,48 @@ extern "C" int omr_attn_bwd(int dt, const void* q, long long q_bs, long long q_r
                            dq_bs, dq_rs, dk, dk_bs, dk_rs, dv, dv_bs, dv_rs, delta_ws, key_bias, B, H, Tq, Tk, hd, scale,
                            causal, window, q_len, kv_len, quirk_mod, st);
 }
+
+// ---- classifier fused with the cross-entropy (projce_tc.cu): tensor-core path only; the caller asks first ----
+extern "C" int omr_proj_ce_supported(int dt, int D) { return (tc_enabled() && dt == OMR_BF16 && D == 256) ? 1 : 0; }
+
+static int proj_ce_rc(int rc, const char* what) {
+  if (rc == OMR_TC_NOT_ELIGIBLE) {
+    omr_set_error("%s: shape / alignment not served by the fused kernels (check omr_proj_ce_supported, 16-byte aligned rows)", what);
+    return OMR_ERR_INVALID;
+  }
+  if (rc == OMR_OK) ++g_tc_calls;
+  return rc;
+}
+
+extern "C" int omr_proj_ce_fwd(int dt, const void* x, long long x_ld, const void* w, long long w_ld, const float* bias,
+                               const long long* targets, long long rows, int V, int D, long long ignore_index,
+                               float* row_loss, float* row_lse, omr_stream_t stream) {
+  OMR_REQUIRE(omr_proj_ce_supported(dt, D), "omr_proj_ce_fwd: not supported for dt %d, D %d", dt, D);
+  if (rows <= 0) return OMR_OK;
+  return proj_ce_rc(omr_proj_ce_fwd_tc(x, x_ld, w, w_ld, bias, targets, rows, V, D, ignore_index, row_loss, row_lse, as_stream(stream)),
+                    "omr_proj_ce_fwd");
+}
+
+extern "C" int omr_proj_ce_bwd_dx(int dt, const void* x, long long x_ld, const void* w, long long w_ld, const float* bias,
+                                  const long long* targets, const float* row_lse, const float* loss_out, const float* gscale,
+                                  long long rows, int V, int D, long long ignore_index, void* dx, long long dx_ld,
+                                  omr_stream_t stream) {
+  OMR_REQUIRE(omr_proj_ce_supported(dt, D), "omr_proj_ce_bwd_dx: not supported for dt %d, D %d", dt, D);
+  OMR_REQUIRE(dx != nullptr, "omr_proj_ce_bwd_dx: dx is NULL");
+  if (rows <= 0) return OMR_OK;
+  return proj_ce_rc(omr_proj_ce_bwd_tc(x, x_ld, w, w_ld, bias, targets, row_lse, loss_out, gscale, rows, V, D, ignore_index, dx, dx_ld,
+                                       nullptr, nullptr, as_stream(stream), as_stream(stream)),
+                    "omr_proj_ce_bwd_dx");
+}
+
+extern "C" int omr_proj_ce_bwd_dw(int dt, const void* x, long long x_ld, const void* w, long long w_ld, const float* bias,
+                                  const long long* targets, const float* row_lse, const float* loss_out, const float* gscale,
+                                  long long rows, int V, int D, long long ignore_index, float* dw, float* db,
+                                  omr_stream_t stream) {
+  OMR_REQUIRE(omr_proj_ce_supported(dt, D), "omr_proj_ce_bwd_dw: not supported for dt %d, D %d", dt, D);
+  OMR_REQUIRE(dw != nullptr, "omr_proj_ce_bwd_dw: dw is NULL");
+  if (rows <= 0) return OMR_OK;
+  return proj_ce_rc(omr_proj_ce_bwd_tc(x, x_ld, w, w_ld, bias, targets, row_lse, loss_out, gscale, rows, V, D, ignore_index, nullptr, 0, dw,
+                                       db, as_stream(stream), as_stream(stream)),
+                    "omr_proj_ce_bwd_dw");
+}

@@ -250,8 +250,6 @@ __global__ void __launch_bounds__(256) dwconv3x3_wgrad_col_kernel(const T* __res
   omr_pdl_enter();
   extern __shared__ float red[];  // [256][41]
   const int cg = C / 4;
-  const int idx = blockIdx.x * 256 + threadIdx.x;
-  const bool live = idx < N * W * cg;
   float acc[9][4], accb[4];
 #pragma unroll
   for (int t = 0; t < 9; ++t)
@@ -259,7 +257,12 @@ __global__ void __launch_bounds__(256) dwconv3x3_wgrad_col_kernel(const T* __res
     for (int k = 0; k < 4; ++k) acc[t][k] = 0.f;
 #pragma unroll
   for (int k = 0; k < 4; ++k) accb[k] = 0.f;
-  if (live) {
+  // grid-stride over the (sample, column, channel quad) groups: the stride is a multiple of the quads per row, so a thread
+  // keeps its channel quad and its accumulators across groups -- a few hundred resident blocks end with ONE set of
+  // atomics each (round 2: one block per 256 groups meant 512 blocks x 1280 atomics onto the same 1280 addresses, and
+  // the same-address serialisation in L2 dominated the 37 us this kernel took for 17 MB of input)
+  const int total = N * W * cg;
+  for (int idx = blockIdx.x * 256 + threadIdx.x; idx < total; idx += gridDim.x * 256) {
     const int c = (idx % cg) * 4, ww = (idx / cg) % W, n = idx / (cg * W);
     const long long rowpitch = (long long)W * C;
     const T* xp = x + (long long)n * H * rowpitch + (long long)ww * C + c;
@@ -388,7 +391,8 @@ extern "C" int omr_dwconv3x3_wgrad(int dt, const void* x, const void* dy, float*
   if (C % 4 == 0 && (256 % (C / 4) == 0 || (C / 4) % 256 == 0) && H <= 64 && (long long)N * W * (C / 4) >= 148LL * 256 &&
       (long long)N * W * (C / 4) < (1LL << 31) && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
       (reinterpret_cast<uintptr_t>(dy) & 15) == 0) {
-    const int blocks = (int)cdiv((long long)N * W * (C / 4), 256);
+    int blocks = (int)cdiv((long long)N * W * (C / 4), 256);
+    if (blocks > 2 * 148 && C / 4 <= 256) blocks = 2 * 148;  // grid-stride kernel: two resident blocks per SM (256 % (C/4) == 0 keeps the quads fixed)
     OMR_DISPATCH_DT(dt, T, (OmrLaunch(blocks, 256, sizeof(float) * 256 * 41, st)(dwconv3x3_wgrad_col_kernel<T>, (const T*)x, (const T*)dy, dw,
                                                                                                        db, N, H, W, C)));
     OMR_LAUNCHED();

@@ -57,3 +57,11 @@ int omr_conv3x3_fwd_c1(int dt, const void* x, const void* w, const float* bias, 
                        int sw, int relu, cudaStream_t st);
 int omr_conv3x3_wgrad_c1(int dt, const void* x, const void* dy, float* dw, int N, int H, int W, int Co, int sh, int sw,
                          int accumulate, cudaStream_t st);
+
+int omr_proj_ce_fwd_tc(const void* x, long long x_ld, const void* w, long long w_ld, const float* bias,
+                       const long long* targets, long long M, int V, int D, long long ignore_index, float* row_loss,
+                       float* row_lse, cudaStream_t st);
+int omr_proj_ce_bwd_tc(const void* x, long long x_ld, const void* w, long long w_ld, const float* bias,
+                       const long long* targets, const float* row_lse, const float* loss_out, const float* gscale,
+                       long long M, int V, int D, long long ignore_index, void* dx, long long dx_ld, float* dw, float* db,
+                       cudaStream_t st_dx, cudaStream_t st_dw);

@@ -147,36 +147,64 @@ class _LogitsFn(torch.autograd.Function):
 
 class _ProjCEFn(torch.autograd.Function):
     """hidden [B,T,D], targets [B,T] -> mean softmax cross-entropy over non-ignored targets
-    (classifier + CrossEntropyLoss(ignore_index) of reference model.py:109,166,444,588)."""
+    (classifier + CrossEntropyLoss(ignore_index) of reference model.py:109,166,444,588).
+
+    bf16, d_model 256 (``ops.proj_ce_supported``): the classifier GEMM and the cross-entropy are ONE tensor-core kernel per
+    direction (csrc/projce_tc.cu) -- the [B*T, V] logits are never written; forward keeps one lse per row, the backward
+    recomputes the score tiles in TMEM.  ``OMR_FUSE_PROJ_CE=0`` (or fp32 / another width) takes the round-1 path: GEMM ->
+    logits -> row-wise lse -> in-place dlogits -> two GEMMs."""
 
     @staticmethod
     def forward(ctx, hidden: torch.Tensor, dec: "Decoder", targets: torch.Tensor, ignore_index: int, dtype, weight, bias):
         b, t, d = hidden.shape
         wm = dec._wcache.get(dec.out_layer.weight, "mat", dtype)
         h2 = hidden.reshape(b * t, d)
+        tg = targets.reshape(-1).contiguous()
+        ctx.dec, ctx.dtype, ctx.ignore = dec, dtype, ignore_index
+        ctx.shape = (b, t, d)
+        ctx.fused = os.environ.get("OMR_FUSE_PROJ_CE", "1") != "0" and ops.proj_ce_supported(dtype, d)
+        if ctx.fused:
+            loss_out, row_lse = ops.proj_ce_fwd(h2, wm, dec.out_layer.bias, tg, ignore_index)
+            ctx.save_for_backward(h2, tg, row_lse, loss_out)
+            return loss_out[0].clone()
         # logits rows padded to a multiple of 64 elements (6997 -> 7040): 16-byte aligned rows for TMA / vector stores
         logits = ops.linear_fwd(h2, wm, dec.out_layer.bias, out=ops.padded_rows(b * t, wm.shape[0], dtype, h2.device))
-        tg = targets.reshape(-1).contiguous()
         loss_out, row_lse = ops.ce_fwd(logits, tg, ignore_index)
-        ctx.dec, ctx.dtype, ctx.ignore = dec, dtype, ignore_index
         ctx.save_for_backward(h2, logits, tg, row_lse, loss_out)
-        ctx.shape = (b, t, d)
         return loss_out[0].clone()
 
     @staticmethod
     def backward(ctx, gloss: torch.Tensor):
-        h2, logits, tg, row_lse, loss_out = ctx.saved_tensors
         dec, dtype = ctx.dec, ctx.dtype
         g = gloss.reshape(1).float().contiguous()
-        dl = ops.ce_bwd(logits, tg, row_lse, loss_out, g, ctx.ignore, inplace=True)
         wm = dec._wcache.get(dec.out_layer.weight, "mat", dtype)
+        v, d = wm.shape
+        train_w = dec.out_layer.weight.requires_grad
+        # the classifier's weight gradient is off the chain; the decoder stack's backward, which follows whenever the hidden
+        # state needs a gradient, joins the side stream and releases the tensors kept here
+        side = dec._side_stream(gloss.device) if (train_w and ctx.needs_input_grad[0]) else None
+        if ctx.fused:
+            h2, tg, row_lse, loss_out = ctx.saved_tensors
+            bias = dec.out_layer.bias
+
+            def wgrad():
+                ops.proj_ce_bwd_dw(h2, wm, bias, tg, row_lse, loss_out, g, ctx.ignore, grad_buf(dec.out_layer.weight).view(v, d),
+                                   grad_buf(bias))
+
+            if train_w and side is not None:
+                dec._side_keep = [h2, tg, row_lse, loss_out, g, wm]
+                side.wait_event(torch.cuda.current_stream(gloss.device).record_event())
+                with torch.cuda.stream(side):
+                    wgrad()
+            dh = ops.proj_ce_bwd_dx(h2, wm, bias, tg, row_lse, loss_out, g, ctx.ignore)
+            if train_w and side is None:
+                wgrad()
+            return dh.view(ctx.shape), None, None, None, None, None, None
+        h2, logits, tg, row_lse, loss_out = ctx.saved_tensors
+        dl = ops.ce_bwd(logits, tg, row_lse, loss_out, g, ctx.ignore, inplace=True)
         dh = ops.linear_dgrad(dl, wm)
-        if dec.out_layer.weight.requires_grad:
-            v, d = wm.shape
+        if train_w:
             gw, gb = grad_buf(dec.out_layer.weight).view(v, d), grad_buf(dec.out_layer.bias)
-            # the classifier's weight gradient is off the chain too; the decoder stack's backward, which follows whenever
-            # the hidden state needs a gradient, joins the side stream and releases the tensors kept here
-            side = dec._side_stream(dl.device) if ctx.needs_input_grad[0] else None
             if side is None:
                 ops.linear_wgrad(h2, dl, gw, gb)
             else:
@@ -530,6 +558,9 @@ class Decoder(nn.Module):
             return _ProjCEFn.apply(hidden, self, targets, ig, hidden.dtype, self.out_layer.weight, self.out_layer.bias)
         b, t, d = hidden.shape
         wm = self._wcache.get(self.out_layer.weight, "mat", hidden.dtype)
+        if os.environ.get("OMR_FUSE_PROJ_CE", "1") != "0" and ops.proj_ce_supported(hidden.dtype, d):
+            loss_out, _ = ops.proj_ce_fwd(hidden.reshape(b * t, d), wm, self.out_layer.bias, targets.reshape(-1).contiguous(), ig)
+            return loss_out[0].clone()
         logits = ops.linear_fwd(hidden.reshape(b * t, d), wm, self.out_layer.bias,
                                 out=ops.padded_rows(b * t, wm.shape[0], hidden.dtype, hidden.device))
         loss_out, _ = ops.ce_fwd(logits, targets.reshape(-1).contiguous(), ig)

@@ -460,6 +460,42 @@ def ce_bwd(logits2d, targets, row_lse, loss_out, gscale, ignore_index: int, inpl
     return d
 
 
+# ---- classifier fused with the cross-entropy (csrc/projce_tc.cu): the [rows, V] logits are never written ---------------
+def proj_ce_supported(dtype, d: int) -> bool:
+    return bool(_lib.load().omr_proj_ce_supported(dt_code(dtype), int(d)))
+
+
+def proj_ce_fwd(x2d, w, bias, targets, ignore_index: int):
+    """x [rows, D], w [V, D], bias fp32 [V] | None, targets int64 [rows] -> (loss_out fp32 [2] = (mean loss, n_valid), row_lse)"""
+    _chk(x2d, "proj_ce_fwd.x"), _chk(w, "proj_ce_fwd.w")
+    rows, d = x2d.shape
+    v = w.shape[0]
+    dev = x2d.device
+    row_loss = torch.empty(rows, dtype=torch.float32, device=dev)
+    row_lse = torch.empty(rows, dtype=torch.float32, device=dev)
+    loss_out = torch.empty(2, dtype=torch.float32, device=dev)
+    call("omr_proj_ce_fwd", dt_code(x2d.dtype), ptr(x2d), x2d.stride(0), ptr(w), w.stride(0), ptr(bias), ptr(targets), rows, v, d,
+         ignore_index, ptr(row_loss), ptr(row_lse), stream_ptr())
+    call("omr_ce_reduce", ptr(row_loss), ptr(targets), rows, ignore_index, ptr(loss_out), stream_ptr())
+    return loss_out, row_lse
+
+
+def proj_ce_bwd_dx(x2d, w, bias, targets, row_lse, loss_out, gscale, ignore_index: int):
+    """-> dL/dx [rows, D] (x's dtype)"""
+    rows, d = x2d.shape
+    dx = torch.empty((rows, d), dtype=x2d.dtype, device=x2d.device)
+    call("omr_proj_ce_bwd_dx", dt_code(x2d.dtype), ptr(x2d), x2d.stride(0), ptr(w), w.stride(0), ptr(bias), ptr(targets), ptr(row_lse),
+         ptr(loss_out), ptr(gscale), rows, w.shape[0], d, ignore_index, ptr(dx), dx.stride(0), stream_ptr())
+    return dx
+
+
+def proj_ce_bwd_dw(x2d, w, bias, targets, row_lse, loss_out, gscale, ignore_index: int, dw, db):
+    """dw [V, D] fp32 and db [V] fp32 (or None) are accumulated into"""
+    rows, d = x2d.shape
+    call("omr_proj_ce_bwd_dw", dt_code(x2d.dtype), ptr(x2d), x2d.stride(0), ptr(w), w.stride(0), ptr(bias), ptr(targets), ptr(row_lse),
+         ptr(loss_out), ptr(gscale), rows, w.shape[0], d, ignore_index, ptr(dw), ptr(db), stream_ptr())
+
+
 # ---- greedy decode helpers ------------------------------------------------------------------------
 def argmax_step(logits2d, tok, val, finished, eos_id, pad_id, out_tokens, out_vals, step, step_dev=None):
     b, v = logits2d.shape

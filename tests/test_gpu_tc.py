@@ -394,3 +394,42 @@ def test_gemm_batched_logits_layout_tc(ops):
     assert tc_calls() == n0 + 1, "batched GEMM fell back to the CUDA-core kernel"
     ref = torch.einsum("vd,btd->bvt", w.float(), hidden.float()) + bias[None, :, None]
     assert rel_err(out.float(), ref) < 6e-3
+
+
+@pytest.mark.parametrize("shape", [(300, 97), (1000, 6997), (129, 64)])
+def test_proj_ce_fused_tc(ops, shape):
+    """Classifier fused with the softmax cross-entropy (csrc/projce_tc.cu; reference decoder.py:145-146 +
+    model.py:109,444): loss, per-row lse and all three gradients against torch on the same bf16 inputs -- ragged row /
+    class tails, ignored rows, a target in every 32-column slot of a tile."""
+    rows, v = shape
+    d = 256
+    x = rnd(rows, d, seed=51, scale=1.0).bfloat16()
+    w = rnd(v, d, seed=52, scale=0.08).bfloat16()
+    bias = rnd(v, seed=53, scale=0.5).float()
+    gen = torch.Generator().manual_seed(54)
+    tg = torch.randint(0, v, (rows,), generator=gen)
+    tg[::7] = 0  # ignore_index rows
+    tg[1] = v - 1
+    tg = tg.to(DEV)
+    assert ops.proj_ce_supported(torch.bfloat16, d)
+    n0 = tc_calls()
+    loss_out, row_lse = ops.proj_ce_fwd(x, w, bias, tg, 0)
+    assert tc_calls() == n0 + 1, "fused projection + cross-entropy did not run on the tensor-core kernel"
+    xr, wr, br = x.float().requires_grad_(True), w.float().requires_grad_(True), bias.clone().requires_grad_(True)
+    logits = xr @ wr.t() + br
+    ref = torch.nn.functional.cross_entropy(logits, tg, ignore_index=0)
+    assert abs(float(loss_out[0]) - float(ref)) < 2e-3 * max(1.0, abs(float(ref)))
+    assert int(loss_out[1]) == int((tg != 0).sum())
+    assert float((row_lse - torch.logsumexp(logits.detach(), dim=1)).abs().max()) < 5e-3
+    gscale = torch.tensor([1.7], device=DEV)
+    (1.7 * ref).backward()
+    dx = ops.proj_ce_bwd_dx(x, w, bias, tg, row_lse, loss_out, gscale, 0)
+    dw = torch.zeros(v, d, device=DEV)
+    db = torch.zeros(v, device=DEV)
+    ops.proj_ce_bwd_dw(x, w, bias, tg, row_lse, loss_out, gscale, 0, dw, db)
+    assert rel_err(dx.float(), xr.grad) < 1.5e-2
+    assert rel_err(dw, wr.grad) < 1.5e-2
+    assert rel_err(db, br.grad) < 1.5e-2
+    # accumulation into dw / db
+    ops.proj_ce_bwd_dw(x, w, bias, tg, row_lse, loss_out, gscale, 0, dw, db)
+    assert rel_err(dw, 2 * wr.grad) < 1.5e-2 and rel_err(db, 2 * br.grad) < 1.5e-2
