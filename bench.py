@@ -514,6 +514,12 @@ def main():
 
     # the dominant kernel = the (entry point, launch shape) group with the largest share of the step
     ranked = sorted(shaped.items(), key=lambda kv: -kv[1]["ms"])
+    if os.environ.get("OMR_BENCH_TABLE"):  # every (entry point, launch shape) group of the profiled step, for the work list
+        with open(os.environ["OMR_BENCH_TABLE"], "w") as f:
+            for (n, sh), d in ranked:
+                f.write(f"{n:28s} calls {d['calls']:3d} ms {d['ms']:7.3f} avg_us {1e3 * d['ms'] / max(d['calls'], 1):8.1f} "
+                        f"TF/s {d['flops'] / (d['ms'] * 1e-3) / 1e12 if d['ms'] else 0:7.1f} GB/s {d['bytes'] / (d['ms'] * 1e-3) / 1e9 if d['ms'] else 0:7.0f} "
+                        f"shape {[int(v) for v in sh if abs(int(v)) < (1 << 20)][-12:]}\n")
     (top_name, top_shape), top = ranked[0]
     roof = roof_of(top_name, top_shape, top)
     roof["timing"] = "CUDA events around each C-ABI call of one eager step, single stream (kernels timed alone)"

@@ -439,12 +439,100 @@ __global__ void dropout_vec_kernel(const T* __restrict__ x, T* __restrict__ y, l
     store4(y + i, v);
   }
 }
+// Wide form (round 2): 16-byte accesses, four of them in flight per thread, no 64-bit division in the loop.  Element-wise
+// mode (CW == 0) walks the tensor as one flat array (key = element index); channel-wise mode (CW == 1) runs one grid row
+// per sample with a stride that is a multiple of C, so a thread keeps ONE group of channels -- its keep factors are
+// computed once and the loop only multiplies.  Same mask function as dropout_kernel (drop_pair_bits).
+template <typename T> struct DropVec;
+template <> struct DropVec<bf16> {
+  static constexpr int N = 8;
+  static __device__ __forceinline__ void apply(uint4& t, const float (&f)[8]) {
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&t);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(__low2float(h[i]) * f[2 * i], __high2float(h[i]) * f[2 * i + 1]);
+  }
+};
+template <> struct DropVec<float> {
+  static constexpr int N = 4;
+  static __device__ __forceinline__ void apply(uint4& t, const float (&f)[4]) {
+    float* v = reinterpret_cast<float*>(&t);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] *= f[i];
+  }
+};
+template <typename T, int CW>
+__global__ void __launch_bounds__(256) dropout_wide_kernel(const T* __restrict__ x, T* __restrict__ y, long long per, int C,
+                                                           uint32_t thr, float scale, uint32_t seed,
+                                                           const int* __restrict__ seed_off) {
+  omr_pdl_enter();
+  constexpr int VEC = DropVec<T>::N, U = 4;
+  if (seed_off) seed += (uint32_t)(*seed_off) * 0x9E3779B9u;
+  const long long base = (long long)blockIdx.y * per;
+  const long long step = (long long)gridDim.x * 256 * VEC;
+  long long e = ((long long)blockIdx.x * 256 + threadIdx.x) * VEC;
+  auto factors = [&](long long key0, float (&f)[VEC]) {  // key0 is even
+#pragma unroll
+    for (int k = 0; k < VEC; k += 2) {
+      const uint32_t h = drop_pair_bits(seed, key0 + k);
+      f[k] = (h & 0xFFFFu) < thr ? 0.f : scale;
+      f[k + 1] = (h >> 16) < thr ? 0.f : scale;
+    }
+  };
+  float fc[VEC];
+  if (CW) factors((long long)blockIdx.y * C + (e % C), fc);
+  const uint4* xp = reinterpret_cast<const uint4*>(x + base);
+  uint4* yp = reinterpret_cast<uint4*>(y + base);
+  for (; e < per; e += step * U) {
+    uint4 r[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (e + u * step < per) r[u] = xp[(e + u * step) / VEC];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (e + u * step < per) {
+        if (CW) {
+          DropVec<T>::apply(r[u], fc);
+        } else {
+          float f[VEC];
+          factors(base + e + u * step, f);
+          DropVec<T>::apply(r[u], f);
+        }
+        yp[(e + u * step) / VEC] = r[u];
+      }
+  }
+}
+
 extern "C" int omr_dropout(int dt, const void* x, void* y, long long n, int C, long long per_sample, float p,
                            long long seed, int channelwise, const int* seed_offset, omr_stream_t stream) {
   OMR_REQUIRE(p >= 0.f && p < 1.f, "omr_dropout: p must be in [0,1) (got %f)", p);
   OMR_REQUIRE(C > 0 && per_sample > 0, "omr_dropout: bad channel geometry");
   if (n <= 0) return OMR_OK;
   const uint32_t thr = (uint32_t)(p * 65536.f + 0.5f);  // 16-bit uniforms: p = 0.1 -> 0.100006, 0.25 and 0.5 exact
+  {
+    const int vec = dt == OMR_F32 ? 4 : 8;
+    const bool al16 = (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0;
+    const float scale = 1.f / (1.f - p);
+    if (al16 && !channelwise && n % vec == 0) {
+      long long blocks = (n / vec + 256 * 4 - 1) / (256 * 4);
+      if (blocks > 148 * 8) blocks = 148 * 8;
+      OMR_DISPATCH_DT(dt, T, (OmrLaunch(dim3((unsigned)blocks, 1), 256, 0, as_stream(stream))(dropout_wide_kernel<T, 0>, (const T*)x, (T*)y,
+                                                                                              n, C, thr, scale, (uint32_t)seed, seed_offset)));
+      OMR_LAUNCHED();
+      return OMR_OK;
+    }
+    if (al16 && channelwise && C % vec == 0 && (256 * vec) % C == 0 && per_sample % vec == 0 && n % per_sample == 0 &&
+        n / per_sample <= 65535 && (per_sample * (dt == OMR_F32 ? 4 : 2)) % 16 == 0) {
+      const long long ns = n / per_sample;
+      long long blocks = (148LL * 8 + ns - 1) / ns;
+      const long long most = (per_sample / vec + 256 * 4 - 1) / (256 * 4);
+      if (blocks > most) blocks = most;
+      if (blocks < 1) blocks = 1;
+      OMR_DISPATCH_DT(dt, T, (OmrLaunch(dim3((unsigned)blocks, (unsigned)ns), 256, 0, as_stream(stream))(
+                                 dropout_wide_kernel<T, 1>, (const T*)x, (T*)y, per_sample, C, thr, scale, (uint32_t)seed, seed_offset)));
+      OMR_LAUNCHED();
+      return OMR_OK;
+    }
+  }
   {
     const int esz = dt == OMR_F32 ? 4 : 2;
     if (n % 4 == 0 && (!channelwise || (C % 4 == 0 && per_sample % 4 == 0)) && (reinterpret_cast<uintptr_t>(x) % (4 * esz)) == 0 &&

@@ -14,6 +14,13 @@ namespace {
 template <typename T> struct V16;
 template <> struct V16<bf16> {
   static constexpr int N = 8;
+  typedef uint4 Raw;
+  static __device__ __forceinline__ Raw load_raw(const bf16* p) { return *reinterpret_cast<const uint4*>(p); }
+  static __device__ __forceinline__ void unpack(const Raw& t, float (&v)[8]) {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { v[2 * i] = __low2float(h[i]); v[2 * i + 1] = __high2float(h[i]); }
+  }
   static __device__ __forceinline__ void load(const bf16* p, float (&v)[8]) {
     const uint4 t = *reinterpret_cast<const uint4*>(p);
     const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
@@ -30,6 +37,9 @@ template <> struct V16<bf16> {
 };
 template <> struct V16<float> {
   static constexpr int N = 4;
+  typedef float4 Raw;
+  static __device__ __forceinline__ Raw load_raw(const float* p) { return *reinterpret_cast<const float4*>(p); }
+  static __device__ __forceinline__ void unpack(const Raw& t, float (&v)[4]) { v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
   static __device__ __forceinline__ void load(const float* p, float (&v)[4]) {
     const float4 t = *reinterpret_cast<const float4*>(p);
     v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
@@ -118,9 +128,9 @@ __global__ void in_finalize_kernel(const double* __restrict__ sums, float* __res
 }
 
 // grid (blocks per sample, N); requires (256 * VEC) % C == 0
-template <typename T>
-__global__ void __launch_bounds__(256) in_apply_fwd_kernel(const T* __restrict__ x, const float* __restrict__ stats,
-                                                           T* __restrict__ y, long long per_sample, int C) {
+template <typename T, int U, int MB>
+__global__ void __launch_bounds__(256, MB) in_apply_fwd_kernel(const T* __restrict__ x, const float* __restrict__ stats,
+                                                               T* __restrict__ y, long long per_sample, int C) {
   omr_pdl_enter();
   constexpr int VEC = V16<T>::N;
   const int n = blockIdx.y;
@@ -135,13 +145,13 @@ __global__ void __launch_bounds__(256) in_apply_fwd_kernel(const T* __restrict__
     mean[k] = stats[((long long)n * C + c0 + k) * 2];
     rstd[k] = stats[((long long)n * C + c0 + k) * 2 + 1];
   }
-  for (; e < per_sample; e += step * IN_UNROLL) {
-    float v[IN_UNROLL][VEC];
+  for (; e < per_sample; e += step * U) {
+    float v[U][VEC];
 #pragma unroll
-    for (int u = 0; u < IN_UNROLL; ++u)
+    for (int u = 0; u < U; ++u)
       if (e + u * step < per_sample) V16<T>::load(xp + e + u * step, v[u]);
 #pragma unroll
-    for (int u = 0; u < IN_UNROLL; ++u)
+    for (int u = 0; u < U; ++u)
       if (e + u * step < per_sample) {
 #pragma unroll
         for (int k = 0; k < VEC; ++k) v[u][k] = (v[u][k] - mean[k]) * rstd[k];
@@ -150,13 +160,18 @@ __global__ void __launch_bounds__(256) in_apply_fwd_kernel(const T* __restrict__
   }
 }
 
-template <typename T>
-__global__ void __launch_bounds__(256) in_apply_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x,
-                                                           const float* __restrict__ stats, const double* __restrict__ sums,
-                                                           T* __restrict__ dx, long long per_sample, int C, double inv_hw,
-                                                           int relu_mask, float mask_scale, int raw_sums, float* __restrict__ colsum) {
+// dx = rstd * (dy - mean(dy) - xhat * mean(dy * xhat)) = A * dy + B * x + D per channel: three coefficients in registers
+// and the loads kept as raw 16-byte words until they are used (round 2: the first version held four statistics per
+// channel and unpacked 2 x U x 8 floats up front -- 160 registers, ONE block of 8 warps per SM, 3.6 TB/s; this one fits
+// three blocks per SM).
+template <typename T, int U, int MB>
+__global__ void __launch_bounds__(256, MB) in_apply_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x,
+                                                               const float* __restrict__ stats, const double* __restrict__ sums,
+                                                               T* __restrict__ dx, long long per_sample, int C, double inv_hw,
+                                                               int relu_mask, float mask_scale, int raw_sums, float* __restrict__ colsum) {
   omr_pdl_enter();
   constexpr int VEC = V16<T>::N;
+  typedef typename V16<T>::Raw Raw;
   __shared__ float smc[256 * VEC];
   const int n = blockIdx.y;
   const long long step = (long long)gridDim.x * 256 * VEC;
@@ -165,41 +180,45 @@ __global__ void __launch_bounds__(256) in_apply_bwd_kernel(const T* __restrict__
   const T* gp = dy + (long long)n * per_sample;
   const T* xp = x + (long long)n * per_sample;
   T* op = dx + (long long)n * per_sample;
-  float mean[VEC], rstd[VEC], m1[VEC], m2[VEC];
+  float ca[VEC], cb[VEC], cd[VEC];
 #pragma unroll
   for (int k = 0; k < VEC; ++k) {
     const long long i = (long long)n * C + c0 + k;
-    mean[k] = stats[i * 2];
-    rstd[k] = stats[i * 2 + 1];
-    m1[k] = (float)(sums[i * 2] * inv_hw);
+    const float mean = stats[i * 2], rstd = stats[i * 2 + 1];
+    const float m1 = (float)(sums[i * 2] * inv_hw);
     // raw_sums: sums = (sum dy, sum dy * x) -> sum dy * xhat = rstd * (sum dy * x - mean * sum dy), combined in double
-    m2[k] = raw_sums ? (float)((double)rstd[k] * (sums[i * 2 + 1] - (double)mean[k] * sums[i * 2]) * inv_hw)
-                     : (float)(sums[i * 2 + 1] * inv_hw);
+    const float m2 = raw_sums ? (float)((double)rstd * (sums[i * 2 + 1] - (double)mean * sums[i * 2]) * inv_hw)
+                              : (float)(sums[i * 2 + 1] * inv_hw);
+    ca[k] = rstd;
+    cb[k] = -rstd * rstd * m2;
+    cd[k] = -rstd * m1 - cb[k] * mean;
   }
   float cs[VEC];
 #pragma unroll
   for (int k = 0; k < VEC; ++k) cs[k] = 0.f;
-  for (; e < per_sample; e += step * IN_UNROLL) {
-    float g[IN_UNROLL][VEC], v[IN_UNROLL][VEC];
+  for (; e < per_sample; e += step * U) {
+    Raw gr[U], xr[U];
 #pragma unroll
-    for (int u = 0; u < IN_UNROLL; ++u)
+    for (int u = 0; u < U; ++u)
       if (e + u * step < per_sample) {
-        V16<T>::load(gp + e + u * step, g[u]);
-        V16<T>::load(xp + e + u * step, v[u]);
+        gr[u] = V16<T>::load_raw(gp + e + u * step);
+        xr[u] = V16<T>::load_raw(xp + e + u * step);
       }
 #pragma unroll
-    for (int u = 0; u < IN_UNROLL; ++u)
+    for (int u = 0; u < U; ++u)
       if (e + u * step < per_sample) {
+        float g[VEC], v[VEC];
+        V16<T>::unpack(gr[u], g);
+        V16<T>::unpack(xr[u], v);
 #pragma unroll
         for (int k = 0; k < VEC; ++k) {
-          const float xin = v[u][k];
-          const float xh = (xin - mean[k]) * rstd[k];
-          float r = rstd[k] * (g[u][k] - m1[k] - xh * m2[k]);
+          const float xin = v[k];
+          float r = fmaf(ca[k], g[k], fmaf(cb[k], xin, cd[k]));
           if (relu_mask) r = xin > 0.f ? r * mask_scale : 0.f;
-          v[u][k] = r;
-          cs[k] += round_to<T>(r);
+          v[k] = r;
+          if (colsum) cs[k] += round_to<T>(r);
         }
-        V16<T>::store(op + e + u * step, v[u]);
+        V16<T>::store(op + e + u * step, v);
       }
   }
   if (colsum) {  // column sums of the stored dx = bias gradient of the convolution in front of the ReLU / norm
@@ -325,6 +344,11 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const T* __restrict__ dy, c
 
 }  // namespace
 
+// Unroll / occupancy of the apply kernels, measured on B200 at 32 x 195 x 808 x 32 bf16 (323 MB; scripts/bench_stream.py): forward
+// unroll 4 (78 registers, three blocks per SM) 111 us = 5.8 TB/s; backward unroll 2 with >= 4 blocks per SM 161 us = 6.0 TB/s
+// (unroll 4: 177 us; the round-1 kernel with 160 registers and one block per SM: 263 us).
+constexpr int IN_FWD_U = 4, IN_FWD_MB = 1, IN_BWD_U = 2, IN_BWD_MB = 4;
+
 // blocks per sample for the flat InstanceNorm kernels: ~8 CTAs per SM over the batch, at least IN_UNROLL loads per thread
 static int in_blocks(long long per_sample, int vec, int N) {
   long long want = cdiv(148LL * 8, N);
@@ -368,7 +392,7 @@ extern "C" int omr_instnorm_fwd(int dt, const void* x, void* y, float* stats, do
   OmrLaunch((int)cdiv((long long)N * C, 256), 256, 0, st)(in_finalize_kernel, ws, stats, (long long)N * C, 1.0 / HW,
                                                                                 (double)eps);
   OMR_LAUNCHED();
-  OMR_DISPATCH_DT(dt, T, (OmrLaunch(grid, 256, 0, st)(in_apply_fwd_kernel<T>, (const T*)x, stats, (T*)y, per, C)));
+  OMR_DISPATCH_DT(dt, T, (OmrLaunch(grid, 256, 0, st)(in_apply_fwd_kernel<T, IN_FWD_U, IN_FWD_MB>, (const T*)x, stats, (T*)y, per, C)));
   OMR_LAUNCHED();
   return OMR_OK;
 }
@@ -390,8 +414,9 @@ extern "C" int omr_instnorm_bwd(int dt, const void* dy, const void* x, const flo
     OMR_DISPATCH_DT(dt, T, (OmrLaunch(grid, 256, 0, st)(in_partial_kernel<T, 1>, (const T*)dy, (const T*)x, stats, ws, per, C)));
     OMR_LAUNCHED();
   }
-  OMR_DISPATCH_DT(dt, T, (OmrLaunch(grid, 256, 0, st)(in_apply_bwd_kernel<T>, (const T*)dy, (const T*)x, stats, ws, (T*)dx, per, C,
-                                                                      1.0 / HW, relu_mask, mask_scale, sums_ready ? 1 : 0, colsum)));
+  OMR_DISPATCH_DT(dt, T, (OmrLaunch(grid, 256, 0, st)(in_apply_bwd_kernel<T, IN_BWD_U, IN_BWD_MB>, (const T*)dy, (const T*)x, stats, ws,
+                                                                      (T*)dx, per, C, 1.0 / HW, relu_mask, mask_scale, sums_ready ? 1 : 0,
+                                                                      colsum)));
   OMR_LAUNCHED();
   return OMR_OK;
 }

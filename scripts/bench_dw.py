@@ -23,4 +23,4 @@ for (n, h, w, c) in ((32, 8, 128, 128), (32, 8, 128, 256), (32, 13, 101, 128), (
     mb = x.numel() * 2 / 1e6
     tf = timed(lambda: ops.dwconv3x3_fwd(x, wp, bias))
     tw = timed(lambda: ops.dwconv3x3_wgrad(x, dy, dw, db, accumulate=True))
-    print(f"{n}x{h}x{w}x{c}: {mb:5.1f} MB/tensor | fwd {tf:6.1f} us ({2*mb/tf*1e-3:5.2f} TB/s) | wgrad {tw:6.1f} us ({2*mb/tw*1e-3:5.2f} TB/s)")
+    print(f"{n}x{h}x{w}x{c}: {mb:5.1f} MB/tensor | fwd {tf:6.1f} us ({2*mb/tf:5.2f} TB/s) | wgrad {tw:6.1f} us ({2*mb/tw:5.2f} TB/s)")
