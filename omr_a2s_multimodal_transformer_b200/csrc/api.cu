@@ -27,7 +27,7 @@ bool omr_pdl_enabled() {
 }
 void omr_count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
-extern "C" int omr_abi_version(void) { return 2; }
+extern "C" int omr_abi_version(void) { return 3; }  // 3: omr_conv3x3_wgrad takes a scratch pointer, omr_proj_ce_* added
 extern "C" const char* omr_last_error(void) { return g_err; }
 extern "C" long long omr_launch_count(void) { return g_launches.load(); }
 
