@@ -217,7 +217,9 @@ int omr_layernorm_bwd(int dt, const void* dy, const void* s, const float* stats,
 /* Opt-in fused forms of the residual blocks of nn.TransformerDecoderLayer in TRAIN mode (decoder.py:86-95:
  * x = norm(x + dropout(sublayer(x)))), shortening the decoder's kernel chain (OMR_FUSE_DECODER_LINKS=1):
  *   omr_dropout_add_layernorm_fwd : s = dropout(x; p, seed) + res ; y = LayerNorm(s)        (= omr_dropout + omr_add_layernorm_fwd)
- *   omr_layernorm_bwd_dropout     : ds as omr_layernorm_bwd ; da = dropout'(ds; p, seed)    (= omr_layernorm_bwd + omr_dropout)
+ *   omr_layernorm_bwd_dropout     : ds as omr_layernorm_bwd ; da = dropout'(ds; p, seed)    (= omr_layernorm_bwd + omr_dropout);
+ *                                   dbias (fp32 [D], may be NULL) += column sums of da = the bias gradient of the linear
+ *                                   layer whose output went through that dropout (ABI 3)
  *   omr_mask_scale                : dx = (mask > 0 ? scale : 0) * dx  -- backward of relu followed by dropout, with
  *                                   mask = the dropped ReLU output (FFN of the decoder layer)
  * The keep decision is exactly omr_dropout's element-wise one (same seed / seed_offset convention). */
@@ -226,7 +228,7 @@ int omr_dropout_add_layernorm_fwd(int dt, const void* x, const void* res, const 
                                   const int* seed_offset, omr_stream_t stream);
 int omr_layernorm_bwd_dropout(int dt, const void* dy, const void* s, const float* stats, const float* gamma, void* ds,
                               void* da, float* dgamma, float* dbeta, long long rows, int D, float p, long long seed,
-                              const int* seed_offset, omr_stream_t stream);
+                              const int* seed_offset, float* dbias, omr_stream_t stream);
 int omr_mask_scale(int dt, void* dx, const void* mask, float scale, long long n, omr_stream_t stream);
 
 /* Softmax cross-entropy over the vocabulary (CrossEntropyLoss(ignore_index), model.py:109,444):

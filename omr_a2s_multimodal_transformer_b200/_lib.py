@@ -45,7 +45,7 @@ _SIGS = {
     "omr_add_layernorm_fwd": "ipppppppqifp",
     "omr_layernorm_bwd": "ippppppp" + "qip",
     "omr_dropout_add_layernorm_fwd": "ipppppppqiffqpp",
-    "omr_layernorm_bwd_dropout": "ippppppppqifqpp",
+    "omr_layernorm_bwd_dropout": "ippppppppqifqppp",
     "omr_mask_scale": "ippfqp",
     "omr_ce_fwd": "ipqpqiqppp",
     "omr_ce_reduce": "ppqqpp",

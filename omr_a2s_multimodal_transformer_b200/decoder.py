@@ -439,17 +439,23 @@ class Decoder(nn.Module):
                     cur.wait_stream(side)
 
             # feed-forward block
-            def ln_bwd(gy, s_, st_, norm, seed):
-                """-> (ds, d sublayer output) of one residual block"""
+            def ln_bwd(gy, s_, st_, norm, seed, lin_bias=None):
+                """-> (ds, d sublayer output, bias gradient still to do?) of one residual block.  lin_bias: the bias of the
+                linear layer that produced the sublayer output -- the fused kernel adds its gradient (column sums of the
+                second output) on the way, which saves that layer's separate column-sum launch"""
                 if seed is not None and fuse:
-                    return ops.layernorm_bwd_dropout(gy, s_, st_, norm.weight, grad_buf(norm.weight), grad_buf(norm.bias), p, seed)
+                    db = grad_buf(lin_bias) if (lin_bias is not None and train_w) else None
+                    ds_, da_ = ops.layernorm_bwd_dropout(gy, s_, st_, norm.weight, grad_buf(norm.weight), grad_buf(norm.bias), p, seed,
+                                                         dbias=db)
+                    return ds_, da_, db is None
                 ds_ = ops.layernorm_bwd(gy, s_, st_, norm.weight, grad_buf(norm.weight), grad_buf(norm.bias))
-                return ds_, (ops.dropout(ds_.view(b * t, d), p, seed) if seed is not None else ds_)
+                return ds_, (ops.dropout(ds_.view(b * t, d), p, seed) if seed is not None else ds_), True
 
-            ds3, df = ln_bwd(g, s3, st3, L.norm3, seed4)
+            ds3, df, need_b = ln_bwd(g, s3, st3, L.norm3, seed4, L.linear2.bias)
             ds3_2d, df = ds3.view(b * t, d), df.view(b * t, d)
             if train_w:
-                off_chain(lambda: ops.linear_wgrad(hdrop, df, grad_buf(L.linear2.weight), grad_buf(L.linear2.bias)), hdrop, df)
+                gb2 = grad_buf(L.linear2.bias) if need_b else None
+                off_chain(lambda: ops.linear_wgrad(hdrop, df, grad_buf(L.linear2.weight), gb2), hdrop, df)
             dh = ops.linear_dgrad(df, w2)
             if seed3 is not None and fuse:
                 ops.mask_scale(dh, hdrop, 1.0 / (1.0 - p))  # zeros of hdrop = inactive or dropped
@@ -462,11 +468,11 @@ class Decoder(nn.Module):
             join_if(seed4 is None)
             ops.gemm(dh, w1, ds3_2d, b * t, d, ff, lda=ff, ldb=d, ldc=d, accumulate=True)  # dx2 = ds3 + dh W1
             # cross-attention block
-            ds2, dcc = ln_bwd(ds3, s2, st2, L.norm2, seed2)
+            ds2, dcc, need_b = ln_bwd(ds3, s2, st2, L.norm2, seed2, ca.out_proj.bias)
             ds2_2d, dcc = ds2.view(b * t, d), dcc.view(b * t, d)
             if train_w:
-                off_chain(lambda: ops.linear_wgrad(o2.view(b * t, d), dcc, grad_buf(ca.out_proj.weight),
-                                                   grad_buf(ca.out_proj.bias)), o2, dcc)
+                gbc = grad_buf(ca.out_proj.bias) if need_b else None
+                off_chain(lambda: ops.linear_wgrad(o2.view(b * t, d), dcc, grad_buf(ca.out_proj.weight), gbc), o2, dcc)
             do2 = ops.linear_dgrad(dcc, wc_o).view(b, t, d)
             dq = torch.empty_like(q)
             dkv = torch.empty_like(kv)
@@ -492,11 +498,11 @@ class Decoder(nn.Module):
             join_if(seed2 is None)
             ops.gemm(dq2, wc_in[:d], ds2_2d, b * t, d, d, lda=d, ldb=d, ldc=d, accumulate=True)  # dx1 = ds2 + dq Wq
             # self-attention block
-            ds1, da = ln_bwd(ds2, s1, st1, L.norm1, seed1)
+            ds1, da, need_b = ln_bwd(ds2, s1, st1, L.norm1, seed1, sa.out_proj.bias)
             ds1_2d, da = ds1.view(b * t, d), da.view(b * t, d)
             if train_w:
-                off_chain(lambda: ops.linear_wgrad(o.view(b * t, d), da, grad_buf(sa.out_proj.weight),
-                                                   grad_buf(sa.out_proj.bias)), o, da)
+                gbs = grad_buf(sa.out_proj.bias) if need_b else None
+                off_chain(lambda: ops.linear_wgrad(o.view(b * t, d), da, grad_buf(sa.out_proj.weight), gbs), o, da)
             do = ops.linear_dgrad(da, w_o).view(b, t, d)
             dqkv = torch.empty_like(qkv)
             ops.attn_bwd(qkv, 0, qkv, d, qkv, 2 * d, o, do, lse, dqkv, 0, dqkv, d, dqkv, 2 * d, spec_self)

@@ -420,15 +420,16 @@ def dropout_add_layernorm_fwd(x, res, gamma, beta, eps: float, save: bool, p: fl
     return y, s, stats
 
 
-def layernorm_bwd_dropout(dy, s, stats, gamma, dgamma, dbeta, p: float, seed: int):
-    """-> (ds, da): ds as layernorm_bwd, da = dropout'(ds; p, seed) = the gradient of the dropped sublayer output"""
+def layernorm_bwd_dropout(dy, s, stats, gamma, dgamma, dbeta, p: float, seed: int, dbias=None):
+    """-> (ds, da): ds as layernorm_bwd, da = dropout'(ds; p, seed) = the gradient of the dropped sublayer output;
+    dbias (fp32 [D]) += column sums of da (the bias gradient of the linear layer in front of the dropout)"""
     _chk(dy, "layernorm_bwd_dropout.dy")
     d = dy.shape[-1]
     rows = dy.numel() // d
     ds = torch.empty_like(dy)
     da = torch.empty_like(dy)
     call("omr_layernorm_bwd_dropout", dt_code(dy.dtype), ptr(dy), ptr(s), ptr(stats), ptr(gamma), ptr(ds), ptr(da), ptr(dgamma),
-         ptr(dbeta), rows, d, float(p), int(seed), ptr(SEED_OFFSET_DEV), stream_ptr())
+         ptr(dbeta), rows, d, float(p), int(seed), ptr(SEED_OFFSET_DEV), ptr(dbias), stream_ptr())
     return ds, da
 
 

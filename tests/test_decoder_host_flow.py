@@ -48,9 +48,9 @@ def stub_ops(monkeypatch):
         assert dy.shape == s.shape and dgamma.shape == gamma.shape
         return dy.clone()
 
-    def layernorm_bwd_dropout(dy, s, stats, gamma, dgamma, dbeta, p, seed):
+    def layernorm_bwd_dropout(dy, s, stats, gamma, dgamma, dbeta, p, seed, dbias=None):
         calls.append("layernorm_bwd_dropout")
-        assert dy.shape == s.shape
+        assert dy.shape == s.shape and (dbias is None or dbias.shape == gamma.shape)
         return dy.clone(), dy.clone()
 
     def linear_dgrad(dy2d, w, out=None):

@@ -49,10 +49,17 @@ def test_layernorm_bwd_dropout_matches_the_two_kernels(dtype, tol):
     dg0, db0, dg1, db1 = (torch.zeros(d, device=DEV) for _ in range(4))
     ds0 = ops.layernorm_bwd(dy, s, st, gamma, dg0, db0)
     da0 = ops.dropout(ds0, p, seed)
-    ds1, da1 = ops.layernorm_bwd_dropout(dy, s, st, gamma, dg1, db1, p, seed)
-    assert torch.equal(ds1, ds0)
-    assert torch.equal(da1 == 0, da0 == 0)
+    dbias = torch.zeros(d, device=DEV)
+    ds1, da1 = ops.layernorm_bwd_dropout(dy, s, st, gamma, dg1, db1, p, seed, dbias=dbias)
+    if dtype == torch.float32:
+        assert torch.equal(ds1, ds0) and torch.equal(da1 == 0, da0 == 0)
+    else:  # the 16-byte-wide bf16 kernel sums a row in another order: the last bit of a few values may differ
+        assert float((ds1.float() - ds0.float()).norm() / ds0.float().norm()) < 2e-3
+        assert float(((da1 == 0) != (da0 == 0)).float().mean()) < 1e-4
     assert float((da1.float() - da0.float()).norm() / da0.float().norm()) < tol
+    # the bias gradient of the linear layer in front of the dropout = column sums of da, accumulated on the way
+    ref_b = da1.float().reshape(-1, d).sum(0)
+    assert torch.allclose(dbias, ref_b, rtol=2e-3, atol=2e-3)
     assert torch.allclose(dg1, dg0, rtol=1e-4, atol=1e-4) and torch.allclose(db1, db0, rtol=1e-4, atol=1e-4)
 
 
