@@ -47,6 +47,8 @@ def to_nchw(x):
 CONV_CASES = [
     # N, H, W, Ci, Co, stride
     (2, 9, 13, 1, 16, (1, 1)),
+    (2, 9, 70, 1, 16, (1, 1)),   # first layer, strip-walking weight gradient (ragged last strip)
+    (1, 3, 97, 1, 16, (1, 1)),
     (2, 12, 20, 16, 16, (1, 1)),
     (1, 11, 17, 16, 32, (2, 2)),
     (2, 8, 10, 32, 64, (2, 2)),
