@@ -1,18 +1,22 @@
-// attn_tc.cu -- flash-style attention forward (head_dim 64, bf16) on the tcgen05 tensor cores.
+// attn_tc.cu -- flash-style attention (head_dim 64, bf16) on the tcgen05 tensor cores: forward, backward.
 //
-// One CTA = one (batch, head, 128-query tile); it walks the visible 128-key tiles:
+// FORWARD.  One CTA = one (batch, head, 128-query tile); it walks the visible 128-key tiles:
 //     S  = Q K^T          tcgen05.mma  M=128 (queries) N=128 (keys) K=64,  fp32 S in TMEM
-//     P  = online softmax of  scale*S + key_bias (+ causal / sliding-window structure)   -- 4 softmax warps,
-//                         one query row per thread, exp2 with the running row max, bf16 P written to shared memory
-//                         in the 128B-swizzled K-major operand layout
-//     O += P V            tcgen05.mma  M=128 N=64 K=128 (V rows are the reduction index: MN-major B), fp32 in TMEM,
-//                         folded into the per-thread fp32 output row with the usual rescaling
+//     P  = online softmax of  scale*S + key_bias (+ causal / sliding-window structure)   -- 8 softmax warps: the two warps
+//                         of a TMEM lane quarter split the tile's keys (64 each), exp2 against a lazily updated reference
+//                         maximum, bf16 P written to shared memory in the 128B-swizzled K-major operand layout
+//     O += P V            tcgen05.mma  M=128 N=64 K=128 (V rows are the reduction index: MN-major B), accumulated in TMEM
+//                         across the key tiles (rescaled there only when a row's maximum runs away)
 // Q/K/V tiles arrive by TMA straight out of the packed projection buffers ([B,T,3D] / [B,S,2D]; the head is a
-// column offset), K/V double buffered.  Two CTAs fit on an SM (112 KB smem, 256 TMEM columns each), so one CTA's
+// column offset), K/V double buffered.  Two CTAs fit on an SM (113 KB smem, 256 TMEM columns each), so one CTA's
 // softmax overlaps the other's MMAs.  The mask algebra is the reference's: additive fp32
 // key bias per (b, key) (0, +1.0 or -inf), keys visible to query t iff k <= t + Tk - Tq (causal) and
 // k >= t + Tk - Tq - window.  lse (natural log) is saved for the backward.
-// Warp roles: 0-3 softmax + epilogue (TMEM lanes 32w..32w+31), 4 TMA producer, 5 MMA issuer + TMEM allocator.
+// Warp roles: 0-7 softmax + epilogue (TMEM lanes 32(w&3)..+31, key / channel half w>>2), 8 TMA producer, 9 MMA issuer +
+// TMEM allocator.  Measured per key tile and CTA (OMR_ATTN_DEBUG=512, scripts/attn_stamps_fwd.py, C3 cross shape): 3500 clk =
+// 250 (S MMA + hop) + 640 (row maximum + exchange) + 1800 (exp pass; MUFU.EX2 at 16 / clk / SM is ~60 % busy with two CTAs per
+// SM) + 520 (P V issue) + 350 (next S issue).
+// BACKWARD: see the comment in front of the backward kernel below.
 #include <type_traits>
 
 #include "attn_drop.cuh"
@@ -42,6 +46,7 @@ struct AttnTcArgs {
   const int* q_len;
   const int* kv_len;
   int quirk_mod;
+  unsigned long long* stamps;  // forward, OMR_ATTN_DEBUG & 512: clock stamps of CTA (0,0,0) ([role][64]); NULL = off
 };
 __device__ __forceinline__ void block_mask_of(const AttnTcArgs& a, int b, int h, int& lq, int& lkv) {
   lq = a.Tq;
@@ -310,6 +315,7 @@ __global__ void __launch_bounds__(32 * (FWD_SW + 2), 2) attn_fwd_tc_kernel(const
           tma_load_3d(sV + s * TILE, &tmV, &kv_full[s], h * HD, (kt0 + i) * BKV, b);
         }
         __syncwarp();
+        if (a.stamps && (blockIdx.x | blockIdx.y | blockIdx.z) == 0 && lane == 0 && n < 64) a.stamps[0 * 64 + n] = clock64();
         ++n;
       }
     }
@@ -336,6 +342,7 @@ __global__ void __launch_bounds__(32 * (FWD_SW + 2), 2) attn_fwd_tc_kernel(const
           umma_commit(s_full);
         }
         __syncwarp();
+        if (a.stamps && (blockIdx.x | blockIdx.y | blockIdx.z) == 0 && lane == 0 && n < 64) a.stamps[1 * 64 + n] = clock64();
         mbar_wait(p_full, n & 1);
         tc_fence_after();
         if (elect_one()) {
@@ -351,6 +358,7 @@ __global__ void __launch_bounds__(32 * (FWD_SW + 2), 2) attn_fwd_tc_kernel(const
           umma_commit(&kv_empty[s]);
         }
         __syncwarp();
+        if (a.stamps && (blockIdx.x | blockIdx.y | blockIdx.z) == 0 && lane == 0 && n < 64) a.stamps[2 * 64 + n] = clock64();
         ++n;
       }
     }
@@ -393,6 +401,8 @@ __global__ void __launch_bounds__(32 * (FWD_SW + 2), 2) attn_fwd_tc_kernel(const
       const bool any_bias = softmax_bar_or(nz);
       mbar_wait(s_full, n & 1);
       tc_fence_after();
+      const bool stamper = a.stamps && (blockIdx.x | blockIdx.y | blockIdx.z) == 0 && threadIdx.x == 0 && n < 64;
+      if (stamper) a.stamps[3 * 64 + n] = clock64();
       // does every row of this CTA see every key of the tile?  (rows past Tq are never stored: they may see anything)
       bool full = j0 + BKV <= a.Tk;
       if (a.causal) {
@@ -424,6 +434,7 @@ __global__ void __launch_bounds__(32 * (FWD_SW + 2), 2) attn_fwd_tc_kernel(const
         if (need) m_used = mx;
       }
       const float m_safe = (m_used == -INFINITY) ? 0.f : m_used;
+      if (stamper) a.stamps[4 * 64 + n] = clock64();
       // pass 2: P = exp2(x - m), row sum, bf16 into the swizzled A-operand tile
       float rs;
       if (thr2) {
@@ -440,6 +451,7 @@ __global__ void __launch_bounds__(32 * (FWD_SW + 2), 2) attn_fwd_tc_kernel(const
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full);
+      if (stamper) a.stamps[5 * 64 + n] = clock64();
       ++n;
     }
     // epilogue: O row (this warp's 32 channels) / row sum, lse
@@ -503,15 +515,42 @@ int omr_attn_fwd_tc(const void* q, long long q_bs, long long q_rs, const void* k
   rc = make_head_map(&tmV, v, v_bs, v_rs, B, Tk, H, BKV);
   if (rc) return rc;
   AttnTcArgs a{(bf16*)o, o_bs, o_rs, lse, key_bias, B, H, Tq, Tk, scale * LOG2E, causal, window, omr_attn_cur_dropout(),
-               q_len, kv_len, quirk_mod};
+               q_len, kv_len, quirk_mod, nullptr};
   static bool configured = false;
   if (!configured) {
     OMR_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM));
     configured = true;
   }
+  static int fdbg = -1;
+  static unsigned long long* fstamps = nullptr;
+  if (fdbg < 0) {
+    const char* e = getenv("OMR_ATTN_DEBUG");
+    fdbg = e ? atoi(e) : 0;
+    if (fdbg & 512) {
+      cudaMalloc(&fstamps, 6 * 64 * 8);
+      cudaMemset(fstamps, 0, 6 * 64 * 8);
+    }
+  }
+  a.stamps = fstamps;
   dim3 grid((unsigned)((Tq + BQ - 1) / BQ), (unsigned)H, (unsigned)B);
   OmrLaunch(grid, 32 * (FWD_SW + 2), FWD_SMEM, st)(attn_fwd_tc_kernel, tmQ, tmK, tmV, a);
   OMR_LAUNCHED();
+  if (fstamps) {  // debugging aid: clock stamps of CTA (0,0,0), relative to the first one
+    static int printed = 0;
+    unsigned long long h[6 * 64];
+    cudaStreamSynchronize(st);
+    cudaMemcpy(h, fstamps, sizeof(h), cudaMemcpyDeviceToHost);
+    if (printed++ == 3) {
+      unsigned long long t0 = ~0ull;
+      for (int i = 0; i < 6 * 64; ++i) if (h[i] && h[i] < t0) t0 = h[i];
+      const char* names[6] = {"kv_issued", "s_issued", "pv_issued", "sm_s_ready", "sm_pass1_done", "sm_arrived"};
+      for (int r = 0; r < 6; ++r) {
+        fprintf(stderr, "%-16s", names[r]);
+        for (int i = 0; i < 20; ++i) fprintf(stderr, " %6lld", h[r * 64 + i] ? (long long)(h[r * 64 + i] - t0) : -1ll);
+        fprintf(stderr, "\n");
+      }
+    }
+  }
   return OMR_OK;
 }
 

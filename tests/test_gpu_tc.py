@@ -264,6 +264,10 @@ ATTN_CASES = [
     (1, 2, 129, 2337, False, 0, "plus1"),
     (3, 4, 64, 64, True, 5, None),
     (1, 4, 1, 37, False, 0, "neginf"),
+    # more work items than SMs: the persistent backward walks several (key tile, head, batch) items per CTA -- K/V double
+    # buffering, the dK / dV drain between items, dead (fully masked) key tiles, items of different length (causal)
+    (20, 4, 200, 700, False, 0, "neginf"),
+    (40, 4, 300, 300, True, 0, None),
 ]
 
 
