@@ -58,9 +58,11 @@ __device__ __forceinline__ void block_mask_of(const AttnTcArgs& a, int b, int h,
   }
 }
 
-// Q, K[2], V[2], P (2 tiles) + bias tile + barriers: 115,456 B, so that two CTAs (+1 KB system reserve each) fit
-// in the 228 KB of an SM; the dynamic window is declared 1024-aligned (no static shared memory in this kernel)
-constexpr int FWD_SMEM = TILE * 7 + 512 + 256;
+// Q, K[3], V[3] + bias tile + barriers: 115,456 B, so that two CTAs (+1 KB system reserve each) fit in the 228 KB of an
+// SM (256 bytes to spare); the dynamic window is declared 1024-aligned (no static shared memory in this kernel)
+constexpr int FWD_KVST = 3;  // K/V stages (a tile lands ~2500 clk after its load is issued)
+constexpr int FWD_OFF_BIAS = TILE * (1 + 2 * FWD_KVST), FWD_OFF_BAR = FWD_OFF_BIAS + 512, FWD_SMEM = FWD_OFF_BAR + 256;
+static_assert(2 * (FWD_SMEM + 1024) <= 228 * 1024, "forward attention: two CTAs per SM");
 
 __device__ __forceinline__ void kv_tile_range(const AttnTcArgs& a, int q0, int& kt0, int& kt1) {
   const int nkt = (a.Tk + BKV - 1) / BKV;
@@ -100,6 +102,13 @@ struct SmRow {
   int j0, k_lo, k_hi;   // first key of the thread's 64, visible interval of the row
 };
 
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+      "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
 __device__ __forceinline__ float fmax3(float a, float b, float c) {
   float d;
   asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
@@ -136,11 +145,12 @@ __device__ __forceinline__ float softmax_row_max(const SmRow& w) {
   return (BIAS || MASKED) ? mx : mx * w.scale_log2;
 }
 
-// P = exp2(x - m) -> row sum over the thread's 64 keys (returned) and the bf16 values in the 128B-swizzled K-major operand
-// layout (64-key chunk `hf` of the P tile); with DROP the stored probabilities carry the keep mask (1/(1-p) is applied to
-// the output row at the end) while the sum stays that of the full row
+// P = exp2(x - m) -> row sum over the thread's 64 keys (returned) and the packed bf16 values back into TENSOR memory (key k of
+// the tile in column k / 2 of the P region: the A operand of the P V MMA is read from TMEM -- round 2, second half: the smem
+// round trip of P was 45 % of the kernel's shared-memory traffic); with DROP the stored probabilities carry the keep mask
+// (1/(1-p) is applied to the output row at the end) while the sum stays that of the full row
 template <bool MASKED, bool BIAS, bool DROP>
-__device__ __forceinline__ float softmax_row_exp(const SmRow& w, float m_safe, uint8_t* rowp, int r, int t, uint32_t dstream,
+__device__ __forceinline__ float softmax_row_exp(const SmRow& w, float m_safe, uint32_t tmem_p, int t, uint32_t dstream,
                                                  uint32_t dkp, uint32_t thr2) {
   float rs = 0.f;
   const float nm = -m_safe;
@@ -181,13 +191,9 @@ __device__ __forceinline__ float softmax_row_exp(const SmRow& w, float m_safe, u
       pk[e >> 1] = pack_bf16(pr[0], pr[1]) & m0;
       pk[(e >> 1) + 1] = pack_bf16(pr[2], pr[3]) & m1;
     }
-    // keys c*32 .. c*32+31 of the chunk = 64 bytes = 4 sixteen-byte units of row r
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int unit = c * 4 + u;
-      *reinterpret_cast<uint4*>(rowp + ((unit ^ (r & 7)) << 4)) = make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
-    }
+    tmem_st16(tmem_p + c * 16, pk);  // keys c*32 .. c*32+31 of the thread's 64 -> 16 packed columns
   }
+  tmem_st_wait();
   return rs;
 }
 
@@ -218,8 +224,9 @@ __device__ __forceinline__ uint32_t tmem_ld1(uint32_t taddr) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v) : "r"(taddr) : "memory");
   return v;
 }
-// a value per row travels between the two warps of a lane quarter through a spare TMEM column of the row's own lane
-// (shared memory is full: two CTAs per SM leave 256 bytes to spare)
+// a value per row travels between the two warps of a lane quarter through a TMEM column of the row's own lane (shared
+// memory is full: two CTAs per SM leave 256 bytes to spare).  The second barrier keeps the partner's read ahead of the next
+// writer of that column (the exp pass, which stores P there).
 __device__ __forceinline__ float pair_exchange(uint32_t col_mine, uint32_t col_other, int lq, float v) {
   tmem_st1(col_mine, __float_as_uint(v));
   tmem_st_wait();
@@ -228,6 +235,9 @@ __device__ __forceinline__ float pair_exchange(uint32_t col_mine, uint32_t col_o
   tc_fence_after();
   const uint32_t o = tmem_ld1(col_other);
   tmem_ld_wait();
+  tc_fence_before();
+  pair_bar(lq);
+  tc_fence_after();
   return __uint_as_float(o);
 }
 
@@ -244,19 +254,18 @@ __global__ void __launch_bounds__(32 * (FWD_SW + 2), 2) attn_fwd_tc_kernel(const
   extern __shared__ __align__(1024) uint8_t smem[];
   if (smem_u32(smem) & 1023u) __trap();  // the swizzled tiles need 1 KB alignment
   uint8_t* sQ = smem;
-  uint8_t* sK = smem + TILE;      // [2]
-  uint8_t* sV = smem + 3 * TILE;  // [2]
-  uint8_t* sP = smem + 5 * TILE;  // two 64-key chunks
-  float* sBias = reinterpret_cast<float*>(smem + 7 * TILE);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 7 * TILE + 512);
+  uint8_t* sK = smem + TILE;                   // [FWD_KVST]
+  uint8_t* sV = smem + (1 + FWD_KVST) * TILE;  // [FWD_KVST]
+  float* sBias = reinterpret_cast<float*>(smem + FWD_OFF_BIAS);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + FWD_OFF_BAR);
   uint64_t* q_full = bars;
-  uint64_t* kv_full = bars + 1;   // [2]
-  uint64_t* kv_empty = bars + 3;  // [2]
-  uint64_t* s_full = bars + 5;
-  uint64_t* p_full = bars + 6;
-  uint64_t* pv_full = bars + 7;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
-  uint32_t* live = reinterpret_cast<uint32_t*>(bars + 9);  // [32] bit i: key tile kt0 + i holds a key that is not masked out
+  uint64_t* kv_full = bars + 1;              // [FWD_KVST]
+  uint64_t* kv_empty = bars + 1 + FWD_KVST;  // [FWD_KVST]
+  uint64_t* s_full = bars + 1 + 2 * FWD_KVST;
+  uint64_t* p_full = s_full + 1;
+  uint64_t* pv_full = s_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 3);
+  uint32_t* live = reinterpret_cast<uint32_t*>(s_full + 4);  // [32] bit i: key tile kt0 + i holds a key that is not masked out
 
   const int warp = (int)warp_idx_sync(), lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * BQ, h = blockIdx.y, b = blockIdx.z;
@@ -281,7 +290,7 @@ __global__ void __launch_bounds__(32 * (FWD_SW + 2), 2) attn_fwd_tc_kernel(const
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
     mbar_init(q_full, 1);
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < FWD_KVST; ++s) {
       mbar_init(&kv_full[s], 1);
       mbar_init(&kv_empty[s], 1);
     }
@@ -295,7 +304,7 @@ __global__ void __launch_bounds__(32 * (FWD_SW + 2), 2) attn_fwd_tc_kernel(const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = bcast0(*tmem_slot);
-  const uint32_t tmem_S = tmem_base, tmem_PV = tmem_base + 128, tmem_X = tmem_base + 192;
+  const uint32_t tmem_S = tmem_base, tmem_PV = tmem_base + 128, tmem_P = tmem_base + 192;  // P: 64 columns of packed bf16
 
   // Producer and MMA issuer run their loops WARP-wide on uniform values and issue under elect_one() (tc_common.cuh): a
   // lone lane under `if (lane == 0)` made the compiler wrap every tcgen05.mma / TMA in an ELECT / R2UR / BRA.U.ANY waterfall.
@@ -307,8 +316,8 @@ __global__ void __launch_bounds__(32 * (FWD_SW + 2), 2) attn_fwd_tc_kernel(const
       }
       for (int i = 0, n = 0; i < ntiles; ++i) {
         if (!bcast0(tile_live(i) ? 1u : 0u)) continue;
-        const int s = n & 1;
-        mbar_wait(&kv_empty[s], ((n >> 1) & 1) ^ 1);
+        const int s = n % FWD_KVST;
+        mbar_wait(&kv_empty[s], ((n / FWD_KVST) & 1) ^ 1);
         if (elect_one()) {
           mbar_expect_tx(&kv_full[s], 2 * TILE);
           tma_load_3d(sK + s * TILE, &tmK, &kv_full[s], h * HD, (kt0 + i) * BKV, b);
@@ -324,11 +333,11 @@ __global__ void __launch_bounds__(32 * (FWD_SW + 2), 2) attn_fwd_tc_kernel(const
       constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
       constexpr uint32_t idesc_pv = make_idesc_bf16(128, 64, 0, 1);
       mbar_wait(q_full, 0);
-      const uint32_t q_addr = smem_u32(sQ), p_addr = smem_u32(sP), k_base = smem_u32(sK), v_base = smem_u32(sV);
+      const uint32_t q_addr = smem_u32(sQ), k_base = smem_u32(sK), v_base = smem_u32(sV);
       for (int i = 0, n = 0; i < ntiles; ++i) {
         if (!bcast0(tile_live(i) ? 1u : 0u)) continue;
-        const int s = n & 1;
-        mbar_wait(&kv_full[s], (n >> 1) & 1);
+        const int s = n % FWD_KVST;
+        mbar_wait(&kv_full[s], (n / FWD_KVST) & 1);
         tc_fence_after();
         const uint32_t k_addr = k_base + (uint32_t)s * TILE, v_addr = v_base + (uint32_t)s * TILE;
         if (elect_one()) {
@@ -347,13 +356,9 @@ __global__ void __launch_bounds__(32 * (FWD_SW + 2), 2) attn_fwd_tc_kernel(const
         tc_fence_after();
         if (elect_one()) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {  // O += P V (the softmax warps have rescaled O if the reference maximum moved)
-            if (j > 0)
-              umma_bf16_acc(tmem_PV, make_smem_desc(p_addr + (j >> 2) * TILE + (j & 3) * 32, 16, 1024, 128),
-                            make_smem_desc(v_addr + j * 2048, 0, 1024, 128), idesc_pv);
-            else
-              umma_bf16(tmem_PV, make_smem_desc(p_addr, 16, 1024, 128), make_smem_desc(v_addr, 0, 1024, 128), idesc_pv, n > 0 ? 1u : 0u);
-          }
+          for (int j = 0; j < 8; ++j)  // O += P V: A = P from TMEM (keys 16j .. 16j+15 in columns 8j .. 8j+7); the softmax
+                                       // warps have rescaled O if the reference maximum moved
+            umma_bf16_ta(tmem_PV, tmem_P + j * 8, make_smem_desc(v_addr + j * 2048, 0, 1024, 128), idesc_pv, (n > 0 || j > 0) ? 1u : 0u);
           umma_commit(pv_full);
           umma_commit(&kv_empty[s]);
         }
@@ -369,7 +374,9 @@ __global__ void __launch_bounds__(32 * (FWD_SW + 2), 2) attn_fwd_tc_kernel(const
     const int t = q0 + r;
     const int off = a.Tk - a.Tq;
     const uint32_t lane_addr = (uint32_t)(lq * 32) << 16;
-    const uint32_t x_mine = tmem_X + lane_addr + (uint32_t)hf, x_other = tmem_X + lane_addr + (uint32_t)(hf ^ 1);
+    // the pair exchange uses two columns of the P region, which is idle whenever an exchange happens (the P V MMA that read
+    // it has completed: s_full / pv_full have been waited for) and is rewritten by the exp pass afterwards
+    const uint32_t x_mine = tmem_P + lane_addr + (uint32_t)hf, x_other = tmem_P + lane_addr + (uint32_t)(hf ^ 1);
     float m_used = -INFINITY, l_run = 0.f;
     const float* kb = a.key_bias ? a.key_bias + (long long)b * a.Tk : nullptr;
     const uint32_t dstream = a.drop.thr ? attn_drop_stream(a.drop, b * a.H + h) : 0u;
@@ -384,7 +391,7 @@ __global__ void __launch_bounds__(32 * (FWD_SW + 2), 2) attn_fwd_tc_kernel(const
     int lqm, lkv;
     block_mask_of(a, b, h, lqm, lkv);
     if (t >= lqm) k_hi = min(k_hi, lkv - 1);
-    uint8_t* rowp = sP + hf * TILE + r * 128;
+    const uint32_t tmem_p = tmem_P + lane_addr + (uint32_t)hf * 32;  // this thread's 64 keys = 32 packed columns
     int n = 0;  // live tiles processed so far (the barrier phases count these)
     for (int i = 0; i < ntiles; ++i) {
       if (!tile_live(i)) continue;
@@ -438,17 +445,16 @@ __global__ void __launch_bounds__(32 * (FWD_SW + 2), 2) attn_fwd_tc_kernel(const
       // pass 2: P = exp2(x - m), row sum, bf16 into the swizzled A-operand tile
       float rs;
       if (thr2) {
-        if (!full) rs = softmax_row_exp<true, true, true>(w, m_safe, rowp, r, t, dstream, dkp, thr2);
-        else if (any_bias) rs = softmax_row_exp<false, true, true>(w, m_safe, rowp, r, t, dstream, dkp, thr2);
-        else rs = softmax_row_exp<false, false, true>(w, m_safe, rowp, r, t, dstream, dkp, thr2);
+        if (!full) rs = softmax_row_exp<true, true, true>(w, m_safe, tmem_p, t, dstream, dkp, thr2);
+        else if (any_bias) rs = softmax_row_exp<false, true, true>(w, m_safe, tmem_p, t, dstream, dkp, thr2);
+        else rs = softmax_row_exp<false, false, true>(w, m_safe, tmem_p, t, dstream, dkp, thr2);
       } else {
-        if (!full) rs = softmax_row_exp<true, true, false>(w, m_safe, rowp, r, t, dstream, dkp, thr2);
-        else if (any_bias) rs = softmax_row_exp<false, true, false>(w, m_safe, rowp, r, t, dstream, dkp, thr2);
-        else rs = softmax_row_exp<false, false, false>(w, m_safe, rowp, r, t, dstream, dkp, thr2);
+        if (!full) rs = softmax_row_exp<true, true, false>(w, m_safe, tmem_p, t, dstream, dkp, thr2);
+        else if (any_bias) rs = softmax_row_exp<false, true, false>(w, m_safe, tmem_p, t, dstream, dkp, thr2);
+        else rs = softmax_row_exp<false, false, false>(w, m_safe, tmem_p, t, dstream, dkp, thr2);
       }
       l_run += rs;
-      fence_proxy_async();
-      tc_fence_before();
+      tc_fence_before();  // P went to tensor memory (tcgen05.st + wait::st inside softmax_row_exp)
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full);
       if (stamper) a.stamps[5 * 64 + n] = clock64();
