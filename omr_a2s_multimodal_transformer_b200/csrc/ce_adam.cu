@@ -211,24 +211,73 @@ __device__ __forceinline__ long long adam_shadow_index(long long i, int layout, 
   return i;
 }
 
+// grid (chunks of a tensor, tensors).  Round 2: the bias corrections (two double-precision pow() and a sqrt) are computed
+// by ONE thread of a block that has work and broadcast through shared memory -- every one of the 5 M threads used to compute
+// them itself --, blocks past the end of their tensor leave at once, and tensors whose arrays are 16-byte aligned are
+// walked with float4 accesses (316 -> ~80 us for the 11.4 M parameters of the C3 model; floor: 28 bytes per parameter).
 __global__ void __launch_bounds__(256) adam_kernel(const omr_adam_entry* __restrict__ table, const int* __restrict__ step,
                                                    double lr, double b1d, double b2d, double epsd, double gsd) {
   omr_pdl_enter();
   const omr_adam_entry e = table[blockIdx.y];
   if (e.grad == nullptr) return;
-  const int t = *step;
-  // bias corrections as torch.optim.Adam (single-tensor path): step_size = lr / (1 - b1^t),
-  // denom = sqrt(v) / sqrt(1 - b2^t) + eps ; computed in double like the Python reference
-  const float step_size = (float)(lr / (1.0 - pow(b1d, (double)t)));
-  const float bc2s = (float)sqrt(1.0 - pow(b2d, (double)t));
+  const bool vec = (e.n % 4 == 0) && ((reinterpret_cast<uintptr_t>(e.param) | reinterpret_cast<uintptr_t>(e.grad) |
+                                       reinterpret_cast<uintptr_t>(e.exp_avg) | reinterpret_cast<uintptr_t>(e.exp_avg_sq)) & 15) == 0;
+  const long long per_pass = (long long)blockDim.x * (vec ? 4 : 1);
+  if ((long long)blockIdx.x * per_pass >= e.n) return;
+  __shared__ float s_corr[2];
+  if (threadIdx.x == 0) {
+    const int t = *step;
+    // bias corrections as torch.optim.Adam (single-tensor path): step_size = lr / (1 - b1^t),
+    // denom = sqrt(v) / sqrt(1 - b2^t) + eps ; computed in double like the Python reference
+    s_corr[0] = (float)(lr / (1.0 - pow(b1d, (double)t)));
+    s_corr[1] = (float)sqrt(1.0 - pow(b2d, (double)t));
+  }
+  __syncthreads();
+  const float step_size = s_corr[0], bc2s = s_corr[1];
   const float b1 = (float)b1d, b2 = (float)b2d, eps = (float)epsd, grad_scale = (float)gsd;
   bf16* sh0 = (bf16*)e.shadow;
   bf16* sh1 = (bf16*)e.shadow2;
+  auto upd = [&](float g, float& m, float& v, float& p) {
+    g *= grad_scale;
+    m = b1 * m + (1.f - b1) * g;
+    v = b2 * v + (1.f - b2) * g * g;
+    p = p - step_size * (m / (sqrtf(v) / bc2s + eps));
+  };
+  if (vec) {
+    const long long n4 = e.n / 4;
+    for (long long i4 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i4 < n4; i4 += (long long)gridDim.x * blockDim.x) {
+      const float4 g4 = reinterpret_cast<const float4*>(e.grad)[i4];
+      float4 m4 = reinterpret_cast<float4*>(e.exp_avg)[i4], v4 = reinterpret_cast<float4*>(e.exp_avg_sq)[i4];
+      float4 p4 = reinterpret_cast<float4*>(e.param)[i4];
+      upd(g4.x, m4.x, v4.x, p4.x); upd(g4.y, m4.y, v4.y, p4.y); upd(g4.z, m4.z, v4.z, p4.z); upd(g4.w, m4.w, v4.w, p4.w);
+      reinterpret_cast<float4*>(e.exp_avg)[i4] = m4;
+      reinterpret_cast<float4*>(e.exp_avg_sq)[i4] = v4;
+      reinterpret_cast<float4*>(e.param)[i4] = p4;
+      const float pv[4] = {p4.x, p4.y, p4.z, p4.w};
+      const long long i = i4 * 4;
+      if (sh0) {
+        if (e.layout == 0 && (reinterpret_cast<uintptr_t>(sh0) & 7) == 0) {
+          uint2 w;
+          __nv_bfloat162 lo = __floats2bfloat162_rn(pv[0], pv[1]), hi = __floats2bfloat162_rn(pv[2], pv[3]);
+          w.x = *reinterpret_cast<uint32_t*>(&lo); w.y = *reinterpret_cast<uint32_t*>(&hi);
+          *reinterpret_cast<uint2*>(sh0 + i) = w;
+        } else {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) sh0[adam_shadow_index(i + k, e.layout, e.d0, e.d1)] = __float2bfloat16_rn(pv[k]);
+        }
+      }
+      if (sh1) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) sh1[adam_shadow_index(i + k, e.layout2, e.d0, e.d1)] = __float2bfloat16_rn(pv[k]);
+      }
+    }
+    return;
+  }
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < e.n; i += (long long)gridDim.x * blockDim.x) {
-    float g = e.grad[i] * grad_scale;
-    float m = e.exp_avg[i] = b1 * e.exp_avg[i] + (1.f - b1) * g;
-    float v = e.exp_avg_sq[i] = b2 * e.exp_avg_sq[i] + (1.f - b2) * g * g;
-    float p = e.param[i] - step_size * (m / (sqrtf(v) / bc2s + eps));
+    float m = e.exp_avg[i], v = e.exp_avg_sq[i], p = e.param[i];
+    upd(e.grad[i], m, v, p);
+    e.exp_avg[i] = m;
+    e.exp_avg_sq[i] = v;
     e.param[i] = p;
     if (sh0) sh0[adam_shadow_index(i, e.layout, e.d0, e.d1)] = __float2bfloat16_rn(p);
     if (sh1) sh1[adam_shadow_index(i, e.layout2, e.d0, e.d1)] = __float2bfloat16_rn(p);
@@ -294,9 +343,9 @@ extern "C" int omr_adam_tick(int* step, omr_stream_t stream) {
 extern "C" int omr_adam_step(const omr_adam_entry* table, int n_tensors, long long max_n, const int* step, double lr,
                              double beta1, double beta2, double eps, double grad_scale, omr_stream_t stream) {
   if (n_tensors <= 0) return OMR_OK;
-  long long bx = cdiv(max_n, 256 * 4);
+  long long bx = cdiv(max_n, 256 * 4 * 2);  // two float4 passes per thread on the largest tensor
   if (bx < 1) bx = 1;
-  if (bx > 64) bx = 64;
+  if (bx > 128) bx = 128;  // (blocks past the end of a small tensor exit at once, but still cost a launch slot)
   dim3 grid((unsigned)bx, (unsigned)n_tensors);
   OmrLaunch(grid, 256, 0, as_stream(stream))(adam_kernel, table, step, lr, beta1, beta2, eps, grad_scale);
   OMR_LAUNCHED();

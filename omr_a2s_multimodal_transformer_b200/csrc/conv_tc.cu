@@ -684,6 +684,17 @@ bool halo_enabled() {
 }
 
 int g_num_sms = 0;
+// shared-memory budget of a halo CTA (OMR_CONV_SMEM_KB, default 225): with <= 110 KB two CTAs -- of this kernel or of the other
+// encoder's kernel running on its own stream -- share an SM
+int conv_smem_cap() {
+  static int v = 0;
+  if (!v) {
+    const char* e = getenv("OMR_CONV_SMEM_KB");
+    v = (e ? atoi(e) : 225) * 1024;
+    if (v < 64 * 1024) v = 225 * 1024;
+  }
+  return v;
+}
 int num_sms() {
   if (!g_num_sms) {
     int dev = 0;
@@ -777,7 +788,7 @@ int run_taps(const void* x, int N, int XH, int XW, int Cin, const void* wpack, i
       // a tap's 128-row operand window starts up to box_hr * pitch + box_wr rows into the last tile row's box row
       if (rows < (TH - 1 + a.box_hr) * pitch + a.box_wr + 128) rows = (TH - 1 + a.box_hr) * pitch + a.box_wr + 128;
       hsub = (rows * rb + 1023) / 1024 * 1024;
-      stages = (225 * 1024 - 1024 - 1024 - 9 * wsub) / hsub;
+      stages = (conv_smem_cap() - 1024 - 1024 - 9 * wsub) / hsub;
       if (stages > 4) stages = 4;
       if (stages >= 2) break;
     }
