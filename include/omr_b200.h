@@ -311,20 +311,23 @@ int omr_attn_decode(int dt, const void* q, long long q_bs, const void* k, long l
                     long long kb_bs, float* ws, long long ws_floats, int B, int H, int Tk, int hd, float scale,
                     int window, const int* pos_dev, omr_stream_t stream);
 
-/* The whole greedy decoder as ONE persistent cooperative kernel (one CTA per SM): `nsteps` complete decode steps
- * (embedding + PE, L post-norm layers with KV-cached self-attention and cross-attention over the pre-projected
- * memory, classifier, first-max argmax, EOS bookkeeping) per launch, grid-wide barriers between dependent phases.
+/* The whole greedy decoder as ONE persistent kernel (a 4-CTA cluster per sample, CTA r = head r): `nsteps` complete
+ * decode steps (embedding + PE, L post-norm layers with KV-cached self-attention and cross-attention over the
+ * pre-projected memory, classifier, first-max argmax, EOS bookkeeping) per launch, three cluster exchanges per layer.
+ * ABI v4: w_o, wc_o and w2 -- the projections that follow an attention head / the FFN quarter and are split along
+ * their reduction index inside the kernel -- are passed as COLUMN SLICES [4][D][D/4] (slice r = W[:, r*D/4:(r+1)*D/4],
+ * contiguous); all other matrices stay row-major [N,K].
  * Replaces the per-token Python loop of model.py:184-193 / 602-611.  `layers` is a DEVICE array of L
  * omr_decode_layer records (weights in `dt`, biases / LayerNorm affine in fp32).  State (tok, val, finished,
  * out_tokens/out_vals [B,out_ld], *pos) stays on the device across launches; *pos advances by the steps executed.
  * scratch: fp32, at least omr_decode_persistent_scratch_floats(B, H, D, V) floats.  B <= 64, D = 256, head dim 64. */
 typedef struct omr_decode_layer {
   const void* w_in;  const float* b_in;   /* self-attn packed in-proj [3D,D], [3D]              */
-  const void* w_o;   const float* b_o;    /* self-attn out-proj [D,D], [D]                      */
+  const void* w_o;   const float* b_o;    /* self-attn out-proj, column slices [4][D][D/4], [D] */
   const void* wc_q;  const float* bc_q;   /* cross-attn query rows of the packed in-proj [D,D]   */
-  const void* wc_o;  const float* bc_o;   /* cross-attn out-proj                                */
+  const void* wc_o;  const float* bc_o;   /* cross-attn out-proj, column slices [4][D][D/4]     */
   const void* w1;    const float* b1;     /* linear1 [D,D] (ff_dim == D)                        */
-  const void* w2;    const float* b2;     /* linear2                                            */
+  const void* w2;    const float* b2;     /* linear2, column slices [4][D][D/4]                 */
   const float *g1, *be1, *g2, *be2, *g3, *be3; /* norm1..3 weight / bias                        */
   void* self_kv;                          /* [B,Tmax,2D] cache in dt (written)                  */
   const void* cross_kv;                   /* [B,S,2D] projected memory in dt                    */

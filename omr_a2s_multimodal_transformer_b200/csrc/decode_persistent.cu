@@ -6,24 +6,25 @@
 // of 4 CTAs (4 x 512 threads on 4 neighbouring SMs; batch 32 -> 128 of the 148 SMs) that runs ALL decode steps of that
 // sample inside a single launch -- embedding + 1-D PE, 8 x (KV-cached self-attention, cross-attention over the
 // pre-projected encoder memory, FFN, three post-norm LayerNorms), vocabulary classifier, first-max argmax, EOS -- and
-// synchronises only with the hardware cluster barrier between dependent phases: no grid-wide barrier, no host round
-// trip, no kernel launch per token.  A decode step is a weight / KV stream:
-//   * WEIGHTS never wait on a dependency, so they are streamed ahead of the computation: thread 0 of every CTA keeps a
-//     145 KB shared-memory ring full with cp.async.bulk copies (8 slots of 32 weight rows = 16 KB bf16, plus their
-//     biases and the LayerNorm scale / shift the projection needs; completion on an mbarrier per slot; L2 evict-last)
-//     in the fixed order the phases consume them; CTA r owns a contiguous quarter of the output
-//     columns of every projection, warp w of it two columns of every slot (one 16-byte LDS per lane and column, shuffle
-//     reduction).  Slots are recycled at the barriers that already separate the phases.
-//   * VECTORS (residual stream, q, attention output, FFN hidden: 256 fp32 each) live replicated in the shared memory
-//     of all four CTAs; a producer lane writes its element into the four copies through distributed shared memory
-//     (st.shared::cluster), barrier.cluster (release / acquire) publishes them.  LayerNorm is recomputed by every warp
-//     from its local copy.  A projection phase touches no global memory on its critical path (the barrier's acquire
-//     invalidates L1, so every global read after it would be an L2 round trip): the layer table is copied to shared
-//     memory once, parameters arrive through the ring.
+// synchronises only inside the cluster (three vector exchanges per layer, one barrier per token): no grid-wide barrier,
+// no host round trip, no kernel launch per token.  A decode step is a weight / KV stream:
+//   * WEIGHTS never wait on a dependency, so they are streamed ahead of the computation: every CTA keeps a 145 KB
+//     shared-memory ring full with cp.async.bulk copies (8 slots of 16 KB bf16 plus the biases and the LayerNorm scale /
+//     shift the projection needs; full / empty mbarriers per slot, refill by the slot-owner warp; L2 evict-last) in the
+//     fixed order the phases consume them.
+//   * PROJECTIONS alternate between two splits so that a layer needs THREE cluster exchanges instead of eight (round 2):
+//     q | k | v, the cross query and FFN1 are split by OUTPUT column -- CTA r computes exactly the 64 (x3) columns that
+//     head r / FFN quarter r consumes next, from its own full copy of the residual stream: nothing to exchange; the
+//     projections that follow them (both out-projections, FFN2) are split along the REDUCTION index -- CTA r multiplies
+//     its own 64 inputs with its column slice of the weight (host layout [4][256][64]) and sends 256 partial sums to all
+//     four CTAs with st.async (counted on a per-buffer mbarrier; two buffers alternate).  The consumer adds the four
+//     partial vectors to the residual, applies the LayerNorm (every warp redundantly, parameters from the ring) and keeps
+//     the result in one of two alternating copies of x.
 //   * ATTENTION: CTA r owns head r; it streams that head's K then V rows straight from the in-HBM cache with 16-byte
-//     loads, double buffered in registers (8 keys in flight + 8 being consumed per thread, 64 key lanes x 8 dim
-//     chunks); the first V batch is already in flight while the softmax statistics are reduced.  New K/V rows go
-//     straight into the cache.
+//     loads into NB rotating register buffers of one 16-key tile per warp (mma.sync scores / P V, see attn_head_mma).
+//     The phase is bound by the load latency per SM (one tile per warp in flight: measured time independent of the
+//     batch, i.e. of the HBM load), not by HBM; the next attention's rows are prefetched into L2 in thirds at the
+//     preceding phase boundaries (OMR_DECODE_PF_MASK).  New K/V rows go straight into the cache.
 // Numerics are those of the per-kernel path (fp32 accumulation; logits rounded to the storage type before the argmax).
 #include <stdlib.h>
 
@@ -42,7 +43,8 @@ constexpr int DP_D = 256, DP_HD = 64, DP_H = 4, DP_THREADS = 512, DP_WARPS = 16,
 constexpr int DP_CL = 4;                      // CTAs per cluster = heads
 constexpr int DP_CH = 32;                     // weight rows (= output columns) per ring slot: two per warp
 constexpr int DP_LCH = 16;                    // ring slots per layer and CTA: 6 (q|k|v) + 5 x 2
-constexpr int DP_VEC = 5 * DP_D + 2 * DP_HD + 16;  // fp32 vectors x, s, q, a, h, the new k / v row of the head, argmax candidates
+constexpr int DP_VEC = 2 * DP_D + 2 * DP_CL * DP_D + 5 * DP_HD + 16;  // fp32: x (two copies, alternating), the K-split partial vectors
+                                                                // [2][4][256], this head's q, a, h quarter, new k / v row, argmax candidates
 
 template <typename T>
 struct LayerW {
@@ -70,6 +72,10 @@ struct DPArgs {
   int sc_floats;       // floats reserved for the attention scores
   int pf_cross, pf_self;  // rows of the next attention's K/V stream that are prefetched into L2 one phase ahead
   int stagger_ns;         // start delay per cluster (x cluster index mod 8): de-phases the clusters' HBM bursts
+  int pf_mask;            // phase boundaries at which a share of the next cross-attention's rows is prefetched (bit i:
+                          // 0 after the previous layer's cross-attention, 1 its out-projection, 2 FFN1, 3 FFN2, 4 after
+                          // q|k|v, 5 after the self-attention, 6 after its out-projection); the rows are dealt evenly
+  int dbg_phase;          // which projection phase feeds the detail counters (0 out-proj, 1 q|k|v, 2 classifier)
 };
 
 // 8 consecutive elements as raw registers (so that many independent 16-byte loads can be in flight per thread)
@@ -317,18 +323,30 @@ __device__ __forceinline__ float gemv_pair(const uint8_t* s0, const uint8_t* s1,
   v += __shfl_xor_sync(0xffffffffu, v, 1);
   return v + bias;
 }
-// A projection of NCH (even) ring slots per CTA: x = xs (shared memory), optionally LayerNorm'ed with the parameters
-// that travel in the first slot (the normalised vector is then also kept in x_keep for a later residual);
+// A projection of NCH (even) ring slots per CTA, output columns split over the CTAs ("N-split": this CTA's 32 NCH rows
+// of the weight against the whole input vector).  Input = xs (+ the four K-split partial vectors `parts` of the
+// preceding projection, see gemv_ks_phase), optionally LayerNorm'ed with the parameters that travel in the first slot
+// (the normalised vector is then also kept in x_keep for a later residual);
 // epi(c, value, sub) runs once per lane: c = column of the CTA's share that this lane's group holds, sub = lane & 7.
 template <typename T, int NCH, typename Epi>
-__device__ __forceinline__ void gemv_phase(Ring<T>& R, const float* xs, bool LN, float* x_keep, float eps, Epi epi, long long* dbg = nullptr) {
+__device__ __forceinline__ void gemv_phase(Ring<T>& R, const float* xs, const float* parts, bool LN, float* x_keep, float eps, Epi epi,
+                                           long long* dbg = nullptr) {
   static_assert(NCH % 2 == 0, "slots are consumed in pairs");
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   long long t0 = dbg ? clock64() : 0;
-  const uint8_t* s0 = R.acquire_at(0);
-  if (dbg) { long long t = clock64(); dbg[0] += t - t0; t0 = t; }
   float x[8];
   load_vec(xs, x);
+  if (parts) {
+#pragma unroll
+    for (int r = 0; r < DP_CL; ++r) {
+      float pr[8];
+      load_vec(parts + r * DP_D, pr);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) x[k] += pr[k];
+    }
+  }
+  const uint8_t* s0 = R.acquire_at(0);
+  if (dbg) { long long t = clock64(); dbg[0] += t - t0; t0 = t; }
   if (LN) {
     const float* gamma = reinterpret_cast<const float*>(s0 + Ring<T>::W_BYTES + 128);
     layer_norm(x, gamma, gamma + DP_D, eps);
@@ -350,11 +368,58 @@ __device__ __forceinline__ void gemv_phase(Ring<T>& R, const float* xs, bool LN,
   }
 }
 
+// The "K-split" projection that follows an attention head or the FFN hidden quarter: this CTA holds 64 elements of the
+// input (its own head / its own quarter -- produced locally, nothing to exchange) and multiplies them with its [256 x 64]
+// column slice of the weight (host layout [4][256][64], two ring slots of 128 rows): 256 PARTIAL sums, which every
+// CTA sends to all four CTAs; the consumer adds the four partial vectors (gemv_phase).  One exchange per two
+// projections instead of two.  Warp w owns rows 8w..8w+7 of each slot; a row is 8 lanes x 8 elements; four dot products
+// per lane are reduce-scattered over the 8 lanes of a row group (4 shuffles): the lane ends up with row
+// n = 128 * bit2 + 8 warp + 4 * bit1 + (lane >> 3) (both lanes of a bit0 pair hold it).  The bias (128 floats at the head
+// of each slot's parameter tail) is added by CTA 0 only.  epi(n, value, bit0).
+template <typename T, typename Epi>
+__device__ __forceinline__ void gemv_ks_phase(Ring<T>& R, const float* xin, bool add_bias, Epi epi) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int sub = lane & 7, grp = lane >> 3;
+  float x[8];
+  {
+    const float4 a = *reinterpret_cast<const float4*>(xin + sub * 8);
+    const float4 b = *reinterpret_cast<const float4*>(xin + sub * 8 + 4);
+    x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+  }
+  const uint8_t* s0 = R.acquire_at(0);
+  const uint8_t* s1 = R.acquire_at(1);
+  Raw8<T> r[4];
+  const T* w0 = reinterpret_cast<const T*>(s0) + (8 * warp + grp) * DP_HD + sub * 8;
+  const T* w1 = reinterpret_cast<const T*>(s1) + (8 * warp + grp) * DP_HD + sub * 8;
+  r[0].load(w0);
+  r[1].load(w0 + 4 * DP_HD);
+  r[2].load(w1);
+  r[3].load(w1 + 4 * DP_HD);
+  const bool b2 = lane & 4, b1 = lane & 2;
+  const int row = 8 * warp + (b1 ? 4 : 0) + grp;
+  const float bias = add_bias ? *reinterpret_cast<const float*>((b2 ? s1 : s0) + Ring<T>::W_BYTES + 4 * row) : 0.f;
+  float d[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    float w[8];
+    r[c].get(w);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) d[c] = fmaf(x[e], w[e], d[c]);
+  }
+  R.release();
+  R.release();
+  const float k0 = (b2 ? d[2] : d[0]) + __shfl_xor_sync(0xffffffffu, b2 ? d[0] : d[2], 4);
+  const float k1 = (b2 ? d[3] : d[1]) + __shfl_xor_sync(0xffffffffu, b2 ? d[1] : d[3], 4);
+  float v = (b1 ? k1 : k0) + __shfl_xor_sync(0xffffffffu, b1 ? k0 : k1, 2);
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  epi((b2 ? 128 : 0) + row, v + bias, lane & 1);
+}
+
 // single-query attention of ONE (sample, head) by the whole CTA: keys [j_lo, tk); q in shared memory; the 64 outputs
-// are written into `out` of all four CTAs.  K / V rows: 16-byte streaming loads, register double buffer.
+// are written into the CTA's own `out`.  K / V rows: 16-byte streaming loads, register double buffer.
 template <typename T>
 __device__ void attn_head(float* sc, float* red, float* s_red, const float* q, const T* __restrict__ kp, int tk, int j_lo,
-                          const float* __restrict__ kb, float scale, float* out, const uint64_t* out_bar, uint64_t pol,
+                          const float* __restrict__ kb, float scale, float* out, uint64_t pol,
                           const float* knew, const float* vnew) {
   constexpr int U = sizeof(T) == 2 ? 8 : 4;  // rows per buffer and thread
   constexpr int PER = U * DP_KL;             // keys per iteration of the CTA
@@ -448,9 +513,8 @@ __device__ void attn_head(float* sc, float* red, float* s_red, const float* q, c
     for (int l = part * (DP_KL / 4); l < (part + 1) * (DP_KL / 4); ++l) s += red[l * DP_HD + o];
     s += __shfl_xor_sync(0xffffffffu, s, 1);
     s += __shfl_xor_sync(0xffffffffu, s, 2);
-    st_async(out + o, sum > 0.f ? s / sum : 0.f, (unsigned)part, out_bar);
+    if (part == 0) out[o] = sum > 0.f ? s / sum : 0.f;  // local: the out-projection that follows is K-split
   }
-  // sc / red are next written two phases on, which the whole cluster enters only after these sends
 }
 
 // ---- bf16 attention on the (legacy, warp-level) tensor-core path ------------------------------------------------------
@@ -487,10 +551,12 @@ __device__ __forceinline__ uint4 pack8(const float* p) {
   return make_uint4(tc::pack_bf16(p[0], p[1]), tc::pack_bf16(p[2], p[3]), tc::pack_bf16(p[4], p[5]), tc::pack_bf16(p[6], p[7]));
 }
 
-// Same contract as attn_head.  Warp w owns the 16-key tiles w, w+16, ...; two tiles (128 B per thread) are in flight
-// while two are consumed.
-__device__ void attn_head_mma(float* sc, float* red, float* s_red, const float* q, const bf16* __restrict__ kp, int tk, int j_lo,
-                              const float* __restrict__ kb, float scale, float* out, const uint64_t* out_bar, uint64_t pol,
+// Same contract as attn_head.  Warp w owns the 16-key tiles w, w+16, ...; NB register buffers of one tile (64 B per
+// thread) rotate: NB - 1 tiles are in flight while one is consumed (the stream is latency bound: bytes in flight per SM
+// = (NB - 1) x 32 KB against ~45 GB/s x ~1.4 us per SM at the HBM roofline).
+template <int NB>
+__device__ __noinline__ void attn_head_mma(float* sc, float* red, float* s_red, const float* q, const bf16* __restrict__ kp, int tk, int j_lo,
+                              const float* __restrict__ kb, float scale, float* out, uint64_t pol,
                               const float* knew, const float* vnew) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   const int n = tk - j_lo;
@@ -516,13 +582,20 @@ __device__ void attn_head_mma(float* sc, float* red, float* s_red, const float* 
     }
   };
   // ---- scores ----
-  Row32 ka[2], kc[2];
-  if (warp < ntile) fetch(ka, kbase, knew, warp, 16 * t, 16 * t + 8);
-  uint32_t qb[8];
-  {
-    const float* qp = q + 16 * t;
+  Row32 buf[NB][2];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) qb[i] = tc::pack_bf16(qp[2 * i] * scale, qp[2 * i + 1] * scale);
+  for (int i = 0; i < NB - 1; ++i)
+    if (warp + i * DP_WARPS < ntile) fetch(buf[i], kbase, knew, warp + i * DP_WARPS, 8 * t, 32 + 8 * t);
+  uint32_t qb[8];
+  {  // the k index of the score MMAs is whatever the loads deliver: dims 8t..8t+7 and 32+8t..32+8t+7 (as for V: the
+     // four t-lanes of a row read whole 32-byte sectors in ONE instruction; with dims 16t..16t+15 split over two
+     // instructions every sector crossed the L2 -> SM path twice, and that path -- not HBM -- bounded the K pass)
+    const float* qp = q + 8 * t;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      qb[i] = tc::pack_bf16(qp[2 * i] * scale, qp[2 * i + 1] * scale);
+      qb[4 + i] = tc::pack_bf16(qp[32 + 2 * i] * scale, qp[32 + 2 * i + 1] * scale);
+    }
   }
   float mx = -INFINITY;
   auto scores = [&](const Row32(&r)[2], int tile) {
@@ -540,17 +613,22 @@ __device__ void attn_head_mma(float* sc, float* red, float* s_red, const float* 
     if (j0 < n) { mx = fmaxf(mx, s0); if (t == 0) sc[j0] = s0; }
     if (j1 < n) { mx = fmaxf(mx, s1); if (t == 0) sc[j1] = s1; }
   };
-  for (int tile = warp; tile < ntile; tile += 2 * DP_WARPS) {
-    if (tile + DP_WARPS < ntile) fetch(kc, kbase, knew, tile + DP_WARPS, 16 * t, 16 * t + 8);
-    scores(ka, tile);
-    if (tile + DP_WARPS < ntile) {
-      if (tile + 2 * DP_WARPS < ntile) fetch(ka, kbase, knew, tile + 2 * DP_WARPS, 16 * t, 16 * t + 8);
-      scores(kc, tile + DP_WARPS);
+  for (int base = warp; base < ntile; base += NB * DP_WARPS) {
+#pragma unroll
+    for (int i = 0; i < NB; ++i) {
+      const int tile = base + i * DP_WARPS;
+      if (tile < ntile) {
+        const int nxt = tile + (NB - 1) * DP_WARPS;
+        if (nxt < ntile) fetch(buf[(i + NB - 1) % NB], kbase, knew, nxt, 8 * t, 32 + 8 * t);
+        scores(buf[i], tile);
+      }
     }
   }
-  // ---- first V tile in flight while the softmax statistics are reduced ----
+  // ---- the first V tiles are in flight while the softmax statistics are reduced ----
   const bf16* vbase = kbase + DP_D;
-  if (warp < ntile) fetch(ka, vbase, vnew, warp, 8 * t, 32 + 8 * t);
+#pragma unroll
+  for (int i = 0; i < NB - 1; ++i)
+    if (warp + i * DP_WARPS < ntile) fetch(buf[i], vbase, vnew, warp + i * DP_WARPS, 8 * t, 32 + 8 * t);
   mx = block_max(mx, s_red);
   const float msafe = (mx == -INFINITY) ? 0.f : mx;
   float sum = 0.f;
@@ -573,12 +651,15 @@ __device__ void attn_head_mma(float* sc, float* red, float* s_red, const float* 
 #pragma unroll
     for (int i = 0; i < 8; ++i) mma_bf16_16816(acc[i], a0, 0u, a2, 0u, movm_trans(v0[i]), movm_trans(v1[i]));
   };
-  for (int tile = warp; tile < ntile; tile += 2 * DP_WARPS) {
-    if (tile + DP_WARPS < ntile) fetch(kc, vbase, vnew, tile + DP_WARPS, 8 * t, 32 + 8 * t);
-    weigh(ka, tile);
-    if (tile + DP_WARPS < ntile) {
-      if (tile + 2 * DP_WARPS < ntile) fetch(ka, vbase, vnew, tile + 2 * DP_WARPS, 8 * t, 32 + 8 * t);
-      weigh(kc, tile + DP_WARPS);
+  for (int base = warp; base < ntile; base += NB * DP_WARPS) {
+#pragma unroll
+    for (int i = 0; i < NB; ++i) {
+      const int tile = base + i * DP_WARPS;
+      if (tile < ntile) {
+        const int nxt = tile + (NB - 1) * DP_WARPS;
+        if (nxt < ntile) fetch(buf[(i + NB - 1) % NB], vbase, vnew, nxt, 8 * t, 32 + 8 * t);
+        weigh(buf[i], tile);
+      }
     }
   }
   // rows of the accumulator are identical; lanes g == 0 hold, for i = 0..7, dims (i<4 ? 0 : 32) + 8t + 2(i%4) + {0,1}
@@ -595,22 +676,20 @@ __device__ void attn_head_mma(float* sc, float* red, float* s_red, const float* 
     for (int l = part * (DP_WARPS / 4); l < (part + 1) * (DP_WARPS / 4); ++l) s += red[l * DP_HD + o];
     s += __shfl_xor_sync(0xffffffffu, s, 1);
     s += __shfl_xor_sync(0xffffffffu, s, 2);
-    st_async(out + o, sum > 0.f ? s / sum : 0.f, (unsigned)part, out_bar);
+    if (part == 0) out[o] = sum > 0.f ? s / sum : 0.f;  // local: the out-projection that follows is K-split
   }
 }
-template <typename T>
+template <typename T, int NB>
 __device__ __forceinline__ void attention(float* sc, float* red, float* s_red, const float* q, const T* kp, int tk, int j_lo,
-                                          const float* kb, float scale, float* out, const uint64_t* out_bar, uint64_t pol,
+                                          const float* kb, float scale, float* out, uint64_t pol,
                                           const float* knew, const float* vnew) {
-  if constexpr (sizeof(T) == 2) attn_head_mma(sc, red, s_red, q, kp, tk, j_lo, kb, scale, out, out_bar, pol, knew, vnew);
-  else attn_head<T>(sc, red, s_red, q, kp, tk, j_lo, kb, scale, out, out_bar, pol, knew, vnew);
+  if constexpr (sizeof(T) == 2) attn_head_mma<NB>(sc, red, s_red, q, kp, tk, j_lo, kb, scale, out, pol, knew, vnew);
+  else attn_head<T>(sc, red, s_red, q, kp, tk, j_lo, kb, scale, out, pol, knew, vnew);
 }
 
 enum { PH_EMBED = 0, PH_QKV, PH_SELF, PH_OUT, PH_CQ, PH_CROSS, PH_COUT, PH_FFN1, PH_FFN2, PH_VOCAB, PH_ARGMAX, PH_BARRIER, PH_RING };
-enum { VB_Q = 0, VB_A, VB_S, VB_H };  // the exchanged vectors and their mbarriers
-// A phase boundary: wait until all `bytes` of the exchanged vector X have landed in this CTA (sent by the 64 warps of
-// the cluster with st.async) -- which also means that every warp of the cluster is done with the phase's ring slots --
-// account the time, recycle the slots.
+// A cluster exchange: wait until all `bytes` of the partial vectors of buffer X (0 / 1, alternating) have landed in this
+// CTA (sent by the 64 warps of the cluster with st.async); account the time.
 #define VEC_WAIT(X, bytes, kind)                                   \
   do {                                                             \
     const long long tb = timed ? clock64() : 0;                    \
@@ -624,16 +703,29 @@ enum { VB_Q = 0, VB_A, VB_S, VB_H };  // the exchanged vectors and their mbarrie
       t_prev = now;                                                \
     }                                                              \
   } while (0)
+// A boundary between two phases that only exchange data inside the CTA (this head's q / attention output / FFN quarter)
+#define LOCAL_SYNC(kind)                                           \
+  do {                                                             \
+    __syncthreads();                                               \
+    if (timed) {                                                   \
+      const long long now = clock64();                             \
+      tacc[kind] += now - t_prev;                                  \
+      t_prev = now;                                                \
+    }                                                              \
+  } while (0)
 
-template <typename T>
+template <typename T, int NB>
 __global__ void __launch_bounds__(DP_THREADS, 1) decode_persistent_kernel(DPArgs p) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   float* vecs = reinterpret_cast<float*>(smem_raw + Ring<T>::BYTES);
-  float *xv = vecs, *sv = vecs + DP_D, *qv = vecs + 2 * DP_D, *av = vecs + 3 * DP_D, *hv = vecs + 4 * DP_D;
-  float *kn = vecs + 5 * DP_D, *vn = kn + DP_HD;  // this head's K / V row of the token being decoded
+  float *xcur = vecs, *xnxt = vecs + DP_D;        // the residual stream x (every CTA keeps its own full copy); the LayerNorm
+                                                 // that follows an exchange writes the other buffer
+  float* parts = vecs + 2 * DP_D;                // [2][4][256] K-split partial sums: buffer, sending CTA, column
+  float *qv = parts + 2 * DP_CL * DP_D, *av = qv + DP_HD, *hv = av + DP_HD;  // this head's query / attention output, FFN quarter
+  float *kn = hv + DP_HD, *vn = kn + DP_HD;      // this head's K / V row of the token being decoded
   float* cand = vn + DP_HD;                      // [4][2] per-CTA argmax candidates
   uint64_t* full = reinterpret_cast<uint64_t*>(vecs + DP_VEC);  // [8] ring slots: data landed; [8] more: slot read by all warps
-  uint64_t* vb = full + 16;                      // [4] exchanged vectors
+  uint64_t* vb = full + 16;                      // [4] (two used): the two partial-vector buffers
   float* s_red = reinterpret_cast<float*>(vb + 4);   // [40]
   float* sc = s_red + 40;                        // [sc_floats] attention scores
   float* red = sc + p.sc_floats;                 // [DP_KL][64] key-lane partials
@@ -657,6 +749,7 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_persistent_kernel(DPArgs
   long long tok = p.tok[b];
   bool fin = p.finished[b] != 0;
   unsigned vpar = 0;    // phase parities of vb[]
+  int xb = 0;           // partial-vector buffer of the latest exchange
   uint64_t pol_stream;  // K / V rows are read once per step: first out of L2
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
 
@@ -695,18 +788,25 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_persistent_kernel(DPArgs
     if (k < DP_LCH * p.L) {
       const int l = k / DP_LCH, c = k % DP_LCH;
       const LayerW<T>& W = layers[l];
-      if (c < 6) {
-        d.w = W.w_in + (long long)(rank * 192 + c * DP_CH) * DP_D;
-        d.bias = W.b_in + rank * 192 + c * DP_CH;
+      if (c < 6) {  // q | k | v rows of head `rank`: 2 slots each
+        const int row = (c >> 1) * DP_D + rank * DP_HD + (c & 1) * DP_CH;
+        d.w = W.w_in + (long long)row * DP_D;
+        d.bias = W.b_in + row;
         if (c == 0 && l > 0) { d.gamma = layers[l - 1].g3; d.beta = layers[l - 1].be3; }
       } else {
         const int ph = (c - 6) >> 1, hf = (c - 6) & 1;
         const T* w = ph == 0 ? W.w_o : ph == 1 ? W.wc_q : ph == 2 ? W.wc_o : ph == 3 ? W.w1 : W.w2;
         const float* bb = ph == 0 ? W.b_o : ph == 1 ? W.bc_q : ph == 2 ? W.bc_o : ph == 3 ? W.b1 : W.b2;
-        d.w = w + (long long)(rank * 64 + hf * DP_CH) * DP_D;
-        d.bias = bb + rank * 64 + hf * DP_CH;
-        if (hf == 0 && ph == 1) { d.gamma = W.g1; d.beta = W.be1; }
-        if (hf == 0 && ph == 3) { d.gamma = W.g2; d.beta = W.be2; }
+        if (ph & 1) {  // N-split: 32 rows x 256 of this CTA's 64 output columns
+          d.w = w + (long long)(rank * 64 + hf * DP_CH) * DP_D;
+          d.bias = bb + rank * 64 + hf * DP_CH;
+          if (hf == 0 && ph == 1) { d.gamma = W.g1; d.beta = W.be1; }
+          if (hf == 0 && ph == 3) { d.gamma = W.g2; d.beta = W.be2; }
+        } else {       // K-split: 128 rows x 64 of this CTA's column slice (host layout [4][256][64]), 128 biases
+          d.w = w + ((long long)rank * DP_D + hf * 128) * DP_HD;
+          d.bias = bb + hf * 128;
+          brows = 128;
+        }
       }
     } else {
       const int c = k - DP_LCH * p.L, r0 = vbeg + c * DP_CH;
@@ -731,6 +831,16 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_persistent_kernel(DPArgs
     while (clock64() < until) __nanosleep(200);
   }
   long long t_prev = clock64();
+  // share `bnd` of the rows of layer `tl`'s cross-attention stream -> L2 (see DPArgs::pf_mask)
+  const int pf_n = __popc((unsigned)p.pf_mask);
+  const int pf_rows = p.S < p.pf_cross ? p.S : p.pf_cross;
+  const int pf_per = pf_n ? ((pf_rows + pf_n - 1) / pf_n + 15) & ~15 : 0;
+  auto cross_pf = [&](int bnd, int tl) {
+    if (!((p.pf_mask >> bnd) & 1)) return;
+    const int r0 = __popc((unsigned)p.pf_mask & ((1u << bnd) - 1u)) * pf_per;
+    const int r1 = r0 + pf_per < pf_rows ? r0 + pf_per : pf_rows;
+    if (r0 < r1) prefetch_rows<T>(layers[tl].cross_kv + (long long)b * p.S * 2 * DP_D, r0, r1, rank);
+  };
 
   for (int step = 0; step < nsteps && !fin; ++step) {
     const int pos = pos0 + step;  // position of the token being consumed; keys 0..pos are visible
@@ -739,54 +849,65 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_persistent_kernel(DPArgs
       float v[8];
 #pragma unroll
       for (int k = 0; k < 8; ++k) v[k] = to_f(emb[tok * DP_D + lane * 8 + k]) + p.pe[(long long)pos * DP_D + lane * 8 + k];
-      store_vec(xv, v);
+      store_vec(xcur, v);
     }
     __syncthreads();
     if (timed) { const long long now = clock64(); tacc[PH_EMBED] += now - t_prev; t_prev = now; }
+    // Per layer: three cluster exchanges instead of eight.  Projections whose OUTPUT feeds one head (q | k | v, the cross
+    // query) or one quarter of the FFN are split by output column so that CTA r produces exactly what CTA r consumes
+    // next; the projections that follow (the two out-projections, FFN2) are split along the REDUCTION index instead:
+    // CTA r multiplies its own 64 inputs with its column slice of the weight and sends 256 partial sums to everybody.
     for (int l = 0; l < p.L; ++l) {
       const LayerW<T>& W = layers[l];
-      // P1: q | k | v of x (= the embedding, or LN3 of the previous layer's sum -> kept in xv for P3's residual).
-      //     q goes to all four CTAs, the k / v values (rounded to the cache type) to the CTA of their head and, for
-      //     the steps to come, into the cache
+      // P1: q | k | v of head `rank` from x (= the embedding, or LN3 of the previous layer's sum -> kept for P3's
+      //     residual); the k / v values (rounded to the cache type) also go into the cache for the steps to come
       {
-        T* crow = W.self_kv + ((long long)b * p.Tmax + pos) * (2 * DP_D);
-        gemv_phase<T, 6>(R, l == 0 ? xv : sv, l > 0, xv, p.ln_eps, [&](int c, float v, int sub) {
-          const int n = rank * 192 + c;
-          if (n < DP_D) {
-            if (sub < DP_CL) st_async(qv + n, v, sub, &vb[VB_Q]);
+        T* crow = W.self_kv + ((long long)b * p.Tmax + pos) * (2 * DP_D) + rank * DP_HD;
+        const float* pin = l > 0 ? parts + xb * DP_CL * DP_D : nullptr;
+        gemv_phase<T, 6>(R, xcur, pin, l > 0, xnxt, p.ln_eps, [&](int c, float v, int sub) {
+          const int which = c >> 6, j = c & (DP_HD - 1);  // 0 query, 1 key, 2 value
+          if (which == 0) {
+            if (sub == 0) qv[j] = v;
           } else {
             const T r = from_f<T>(v);
-            const int m = n - DP_D;  // 0..255 key, 256..511 value; 64 per head
-            if (sub == 0) st_async((m < DP_D ? kn : vn) + (m & (DP_HD - 1)), to_f(r), (unsigned)((m >> 6) & 3), &vb[VB_Q]);
-            if (sub == 1) crow[m] = r;
+            if (sub == 0) (which == 1 ? kn : vn)[j] = to_f(r);
+            if (sub == 1) crow[(which - 1) * DP_D + j] = r;
           }
-        });
+        }, timed && p.dbg_phase == 1 ? dbgc : nullptr);
+        if (l > 0) { float* t = xcur; xcur = xnxt; xnxt = t; }
       }
-      VEC_WAIT(VB_Q, 4 * DP_D + 8 * DP_HD, PH_QKV);
+      LOCAL_SYNC(PH_QKV);
+      cross_pf(4, l);
       // P2: causal / windowed self-attention of head `rank` over the cache (+ the new row from shared memory)
       {
         int j_lo = 0;
         if (p.window > 0 && pos - p.window > 0) j_lo = pos - p.window;
-        attention<T>(sc, red, s_red, qv + rank * DP_HD, W.self_kv + (long long)b * p.Tmax * 2 * DP_D + rank * DP_HD, pos + 1, j_lo,
-                     nullptr, p.scale, av + rank * DP_HD, &vb[VB_A], pol_stream, kn, vn);
+        attention<T, NB>(sc, red, s_red, qv, W.self_kv + (long long)b * p.Tmax * 2 * DP_D + rank * DP_HD, pos + 1, j_lo,
+                         nullptr, p.scale, av, pol_stream, kn, vn);
       }
-      VEC_WAIT(VB_A, 4 * DP_D, PH_SELF);
-      prefetch_rows<T>(W.cross_kv + (long long)b * p.S * 2 * DP_D, 0, p.S < p.pf_cross ? p.S : p.pf_cross, rank);
-      // P3: s = x + out_proj(a)
-      gemv_phase<T, 2>(R, av, false, nullptr, 0.f, [&](int c, float v, int sub) {
-        const int n = rank * 64 + c;
-        if (sub < DP_CL) st_async(sv + n, v + xv[n], sub, &vb[VB_S]);
-      }, timed ? dbgc : nullptr);
-      VEC_WAIT(VB_S, 4 * DP_D, PH_OUT);
-      // P4: x1 = LN1(s) (kept in xv for P6's residual) -> cross query
-      gemv_phase<T, 2>(R, sv, true, xv, p.ln_eps, [&](int c, float v, int sub) {
-        if (sub < DP_CL) st_async(qv + rank * 64 + c, v, sub, &vb[VB_Q]);
+      LOCAL_SYNC(PH_SELF);
+      cross_pf(5, l);
+      // P3: partial sums of out_proj(a) over this head's 64 inputs -> all CTAs
+      xb ^= 1;
+      gemv_ks_phase<T>(R, av, rank == 0, [&](int n, float v, int half) {
+        float* dst = parts + (xb * DP_CL + rank) * DP_D + n;
+        st_async(dst, v, 2 * half, &vb[xb]);
+        st_async(dst, v, 2 * half + 1, &vb[xb]);
       });
-      VEC_WAIT(VB_Q, 4 * DP_D, PH_CQ);
+      VEC_WAIT(xb, 4 * DP_CL * DP_D, PH_OUT);
+      cross_pf(6, l);
+      // P4: s = x + out_proj(a); x1 = LN1(s) (kept for P6's residual) -> cross query of head `rank`
+      gemv_phase<T, 2>(R, xcur, parts + xb * DP_CL * DP_D, true, xnxt, p.ln_eps, [&](int c, float v, int sub) {
+        if (sub == 0) qv[c] = v;
+      }, timed && p.dbg_phase == 0 ? dbgc : nullptr);
+      { float* t = xcur; xcur = xnxt; xnxt = t; }
+      LOCAL_SYNC(PH_CQ);
       // P5: cross-attention of head `rank` over the projected encoder memory
-      attention<T>(sc, red, s_red, qv + rank * DP_HD, W.cross_kv + (long long)b * p.S * 2 * DP_D + rank * DP_HD, p.S, 0, kbias,
-                   p.scale, av + rank * DP_HD, &vb[VB_A], pol_stream, nullptr, nullptr);
-      VEC_WAIT(VB_A, 4 * DP_D, PH_CROSS);
+      attention<T, NB>(sc, red, s_red, qv, W.cross_kv + (long long)b * p.S * 2 * DP_D + rank * DP_HD, p.S, 0, kbias,
+                       p.scale, av, pol_stream, nullptr, nullptr);
+      LOCAL_SYNC(PH_CROSS);
+      const int ncl = l + 1 < p.L ? l + 1 : 0;  // the cross-attention that comes next (layer 0 of the next token after the last)
+      cross_pf(0, ncl);
       {  // the self-attention that comes next: layer l + 1 of this token, or layer 0 of the next one
         const int nl = l + 1 < p.L ? l + 1 : 0, npos = l + 1 < p.L ? pos : pos + 1;
         int lo = 0;
@@ -794,23 +915,32 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_persistent_kernel(DPArgs
         if (npos - lo > p.pf_self) lo = npos - p.pf_self;  // the newest rows are the ones least likely to be cached
         prefetch_rows<T>(layers[nl].self_kv + (long long)b * p.Tmax * 2 * DP_D, lo, npos, rank);
       }
-      // P6: s = x1 + cross out_proj(a)
-      gemv_phase<T, 2>(R, av, false, nullptr, 0.f, [&](int c, float v, int sub) {
-        const int n = rank * 64 + c;
-        if (sub < DP_CL) st_async(sv + n, v + xv[n], sub, &vb[VB_S]);
+      // P6: partial sums of the cross out_proj(a)
+      xb ^= 1;
+      gemv_ks_phase<T>(R, av, rank == 0, [&](int n, float v, int half) {
+        float* dst = parts + (xb * DP_CL + rank) * DP_D + n;
+        st_async(dst, v, 2 * half, &vb[xb]);
+        st_async(dst, v, 2 * half + 1, &vb[xb]);
       });
-      VEC_WAIT(VB_S, 4 * DP_D, PH_COUT);
-      // P7: x2 = LN2(s) (kept in xv for P8's residual) -> h = relu(W1 x2 + b1)
-      gemv_phase<T, 2>(R, sv, true, xv, p.ln_eps, [&](int c, float v, int sub) {
-        if (sub < DP_CL) st_async(hv + rank * 64 + c, fmaxf(v, 0.f), sub, &vb[VB_H]);
+      VEC_WAIT(xb, 4 * DP_CL * DP_D, PH_COUT);
+      cross_pf(1, ncl);
+      // P7: s = x1 + cross out_proj(a); x2 = LN2(s) (kept for P8's residual) -> this CTA's quarter of h = relu(W1 x2 + b1)
+      gemv_phase<T, 2>(R, xcur, parts + xb * DP_CL * DP_D, true, xnxt, p.ln_eps, [&](int c, float v, int sub) {
+        if (sub == 0) hv[c] = fmaxf(v, 0.f);
       });
-      VEC_WAIT(VB_H, 4 * DP_D, PH_FFN1);
-      // P8: s = x2 + W2 h + b2
-      gemv_phase<T, 2>(R, hv, false, nullptr, 0.f, [&](int c, float v, int sub) {
-        const int n = rank * 64 + c;
-        if (sub < DP_CL) st_async(sv + n, v + xv[n], sub, &vb[VB_S]);
+      { float* t = xcur; xcur = xnxt; xnxt = t; }
+      LOCAL_SYNC(PH_FFN1);
+      cross_pf(2, ncl);
+      // P8: partial sums of W2 h over this CTA's quarter of h (s = x2 + W2 h + b2 is formed by the consumer: the next
+      //     layer's P1 or the classifier)
+      xb ^= 1;
+      gemv_ks_phase<T>(R, hv, rank == 0, [&](int n, float v, int half) {
+        float* dst = parts + (xb * DP_CL + rank) * DP_D + n;
+        st_async(dst, v, 2 * half, &vb[xb]);
+        st_async(dst, v, 2 * half + 1, &vb[xb]);
       });
-      VEC_WAIT(VB_S, 4 * DP_D, PH_FFN2);
+      VEC_WAIT(xb, 4 * DP_CL * DP_D, PH_FFN2);
+      cross_pf(3, ncl);
     }
     // ---- classifier on LN3(s) of the last layer, fused with the first-max argmax ----
     {
@@ -825,8 +955,15 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_persistent_kernel(DPArgs
       const float tb = tail_bias ? p.b_out[vbeg + lastc] : 0.f;
       float x[8];
       if (nvch > 0) {
+        load_vec(xcur, x);
+#pragma unroll
+        for (int r = 0; r < DP_CL; ++r) {
+          float pr[8];
+          load_vec(parts + (xb * DP_CL + r) * DP_D, pr);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) x[k] += pr[k];
+        }
         const uint8_t* slot = R.acquire_at(0);
-        load_vec(sv, x);
         const float* gamma = reinterpret_cast<const float*>(slot + Ring<T>::W_BYTES + 128);
         layer_norm(x, gamma, gamma + DP_D, p.ln_eps);
       }
@@ -942,17 +1079,25 @@ extern "C" int omr_decode_persistent(int dt, const void* layers_dev, int L, cons
   p.eos = eos; p.pad = pad; p.mem_bias = mem_bias; p.mem_bias_bs = mem_bias_bs; p.ln_eps = ln_eps; p.scale = 0.125f;
   p.timing = timing;
   (void)scratch;
+  int nb_sel = 2;
   {
-    static int pf[3] = {-1, -1, -1};
-    if (pf[0] < 0) {
+    int pf[6];  // read per launch (one launch per decode): tuning sweeps change them between calls
+    {
       const char* a = getenv("OMR_DECODE_PF_CROSS");
       const char* c = getenv("OMR_DECODE_PF_SELF");
       const char* d = getenv("OMR_DECODE_STAGGER_NS");
-      pf[0] = a ? atoi(a) : 2400;
+      const char* m = getenv("OMR_DECODE_PF_MASK");
+      const char* g = getenv("OMR_DECODE_DBG_PHASE");
+      const char* nb = getenv("OMR_DECODE_NB");
       pf[1] = c ? atoi(c) : 4096;
       pf[2] = d ? atoi(d) : 0;
+      pf[3] = m ? (int)strtol(m, nullptr, 0) & 0x7f : 0x70;  // thirds after q|k|v, the self-attention and its out-projection
+      pf[4] = g ? atoi(g) : 0;
+      pf[5] = nb ? atoi(nb) : 2;
+      pf[0] = a ? atoi(a) : 2400;
     }
-    p.pf_cross = pf[0]; p.pf_self = pf[1]; p.stagger_ns = pf[2];
+    p.pf_cross = pf[0]; p.pf_self = pf[1]; p.stagger_ns = pf[2]; p.pf_mask = pf[3]; p.dbg_phase = pf[4];
+    nb_sel = pf[5] == 3 || pf[5] == 4 ? pf[5] : 2;
   }
   const int max_keys = S > Tmax ? S : Tmax;
   p.sc_floats = (max_keys + 15) & ~15;
@@ -972,11 +1117,18 @@ extern "C" int omr_decode_persistent(int dt, const void* layers_dev, int L, cons
   attr[0].val.clusterDim.x = DP_CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   lc.attrs = attr; lc.numAttrs = 1;
   if (dt == OMR_BF16) {
-    if (!cfg[1]) { OMR_CUDA(cudaFuncSetAttribute(decode_persistent_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024)); cfg[1] = true; }
-    OMR_CUDA(cudaLaunchKernelEx(&lc, decode_persistent_kernel<bf16>, p));
+    if (!cfg[1]) {
+      OMR_CUDA(cudaFuncSetAttribute(decode_persistent_kernel<bf16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+      OMR_CUDA(cudaFuncSetAttribute(decode_persistent_kernel<bf16, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+      OMR_CUDA(cudaFuncSetAttribute(decode_persistent_kernel<bf16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+      cfg[1] = true;
+    }
+    if (nb_sel == 3) OMR_CUDA(cudaLaunchKernelEx(&lc, decode_persistent_kernel<bf16, 3>, p));
+    else if (nb_sel == 4) OMR_CUDA(cudaLaunchKernelEx(&lc, decode_persistent_kernel<bf16, 4>, p));
+    else OMR_CUDA(cudaLaunchKernelEx(&lc, decode_persistent_kernel<bf16, 2>, p));
   } else {
-    if (!cfg[0]) { OMR_CUDA(cudaFuncSetAttribute(decode_persistent_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024)); cfg[0] = true; }
-    OMR_CUDA(cudaLaunchKernelEx(&lc, decode_persistent_kernel<float>, p));
+    if (!cfg[0]) { OMR_CUDA(cudaFuncSetAttribute(decode_persistent_kernel<float, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024)); cfg[0] = true; }
+    OMR_CUDA(cudaLaunchKernelEx(&lc, decode_persistent_kernel<float, 2>, p));
   }
   omr_count_launch();
   return OMR_OK;

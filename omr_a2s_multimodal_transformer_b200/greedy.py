@@ -110,11 +110,13 @@ class BatchedGreedyDecoder:
             wc_in = c.get(ca.in_proj_weight, "mat", dtype)
             vals = dict(
                 w_in=c.get(sa.in_proj_weight, "mat", dtype), b_in=sa.in_proj_bias,
-                w_o=c.get(sa.out_proj.weight, "mat", dtype), b_o=sa.out_proj.bias,
+                # the projections that FOLLOW an attention head / the FFN quarter are split along their reduction index
+                # inside the kernel: column slices [4][256][64] (include/omr_b200.h, omr_decode_layer)
+                w_o=c.get(sa.out_proj.weight, "matKS4", dtype), b_o=sa.out_proj.bias,
                 wc_q=wc_in[:d], bc_q=ca.in_proj_bias[:d],
-                wc_o=c.get(ca.out_proj.weight, "mat", dtype), bc_o=ca.out_proj.bias,
+                wc_o=c.get(ca.out_proj.weight, "matKS4", dtype), bc_o=ca.out_proj.bias,
                 w1=c.get(L.linear1.weight, "mat", dtype), b1=L.linear1.bias,
-                w2=c.get(L.linear2.weight, "mat", dtype), b2=L.linear2.bias,
+                w2=c.get(L.linear2.weight, "matKS4", dtype), b2=L.linear2.bias,
                 g1=L.norm1.weight, be1=L.norm1.bias, g2=L.norm2.weight, be2=L.norm2.bias, g3=L.norm3.weight, be3=L.norm3.bias,
                 self_kv=st["self_kv"][li], cross_kv=cross_kv[li])
             for k, t in vals.items():

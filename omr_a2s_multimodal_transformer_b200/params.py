@@ -36,7 +36,8 @@ def resolve_dtype(explicit: Optional[torch.dtype]) -> torch.dtype:
 
 
 class WeightCache:
-    """kind: "conv" [Co,3,3,Ci] | "convT" [Ci,3,3,Co] | "dw" [3,3,C] | "mat" [N,K] (same order, 2-D)."""
+    """kind: "conv" [Co,3,3,Ci] | "convT" [Ci,3,3,Co] | "dw" [3,3,C] | "mat" [N,K] (same order, 2-D) | "matT" [K,N] |
+    "matKS4" [4][N][K/4] (not an Adam shadow: re-packed when the parameter's version moves)."""
 
     def __init__(self) -> None:
         self._c: Dict[Tuple[int, str, torch.dtype], Tuple[int, torch.Tensor]] = {}
@@ -93,6 +94,10 @@ class WeightCache:
         if kind == "mat":
             w2 = w.reshape(w.shape[0], -1)
             return w2 if dtype == torch.float32 else ops.cast(w2, dtype)
+        if kind == "matKS4":  # [N,K] -> [4][N][K/4]: the column slices of the persistent decode kernel's K-split projections
+            w2 = w.reshape(w.shape[0], -1)
+            n, k = w2.shape
+            return ops.cast(w2.view(n, 4, k // 4).permute(1, 0, 2).contiguous(), dtype).view(4 * n, k // 4)
         if kind == "matT":  # [R,C] -> [C,R]: the K-major operand of the data-gradient GEMMs
             w2 = w.reshape(w.shape[0], -1)
             return ops.cast(w2.t().contiguous(), dtype)

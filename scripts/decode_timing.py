@@ -13,7 +13,8 @@ w2i, i2w = synth.load_vocab()
 dev = torch.device("cuda", 0)
 m = pkg.MultimodalTransformer(128, 1024, 195, 808, 1268, w2i, i2w).to(dev).eval()
 m.set_compute_dtype(torch.bfloat16)
-xi, _, xa, _, _, _ = bench.make_batch(32, w2i, seed=500)
+BATCH = int(os.environ.get("DECODE_BATCH", "32"))
+xi, _, xa, _, _, _ = bench.make_batch(BATCH, w2i, seed=500)
 steps = int(sys.argv[1]) if len(sys.argv) > 1 and sys.argv[1].isdigit() else 1268
 with torch.no_grad():
     mem, _ = m._memory(xi.to(dev), xa.to(dev), None, None, "both")
@@ -25,4 +26,4 @@ with torch.no_grad():
     r.decode(mem, w2i["<sos>"], w2i["<eos>"], 0, max_steps=steps, stop_at_eos=False)
     e1.record()
     torch.cuda.synchronize()
-print(f"{steps} steps: {e0.elapsed_time(e1):.1f} ms -> {32 * steps / e0.elapsed_time(e1) * 1e3:.0f} tokens/s")
+print(f"{steps} steps: {e0.elapsed_time(e1):.1f} ms -> {BATCH * steps / e0.elapsed_time(e1) * 1e3:.0f} tokens/s (batch {BATCH})")
