@@ -75,29 +75,12 @@ struct DPArgs {
   int pf_mask;            // phase boundaries at which a share of the next cross-attention's rows is prefetched (bit i:
                           // 0 after the previous layer's cross-attention, 1 its out-projection, 2 FFN1, 3 FFN2, 4 after
                           // q|k|v, 5 after the self-attention, 6 after its out-projection); the rows are dealt evenly
-  int dbg_phase;          // which projection phase feeds the detail counters (0 out-proj, 1 q|k|v, 2 classifier)
+  int dbg_phase;          // which projection phase feeds the detail counters (0 cross-q, 1 q|k|v, 2 FFN1)
+  int pf_kind;            // 0 bulk (TMA) prefetches of whole rows dealt over the cluster, 1 per-thread prefetches of the head's lines
 };
 
 // 8 consecutive elements as raw registers (so that many independent 16-byte loads can be in flight per thread)
 template <typename T> struct Raw8;
-template <> struct Raw8<bf16> {
-  uint4 v;
-  __device__ __forceinline__ void load(const bf16* p) { v = *reinterpret_cast<const uint4*>(p); }
-  // streaming global load: K/V rows are read once per step, keep them out of L1
-  __device__ __forceinline__ void load_stream(const bf16* p, uint64_t pol) {
-    asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;"
-                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(pol));
-  }
-  __device__ __forceinline__ void zero() { v = make_uint4(0, 0, 0, 0); }
-  __device__ __forceinline__ void set(const float* p) {  // 8 fp32 values that are exactly representable
-    v = make_uint4(tc::pack_bf16(p[0], p[1]), tc::pack_bf16(p[2], p[3]), tc::pack_bf16(p[4], p[5]), tc::pack_bf16(p[6], p[7]));
-  }
-  __device__ __forceinline__ void get(float (&f)[8]) const {
-    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) { f[2 * i] = __low2float(h[i]); f[2 * i + 1] = __high2float(h[i]); }
-  }
-};
 template <> struct Raw8<float> {
   float4 a, b;
   __device__ __forceinline__ void load(const float* p) { a = *reinterpret_cast<const float4*>(p); b = *reinterpret_cast<const float4*>(p + 4); }
@@ -155,6 +138,20 @@ __device__ __forceinline__ void prefetch_rows(const T* base, int r0, int r1, int
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(base + (long long)a * (2 * DP_D)),
                  "r"((uint32_t)(b - a) * (uint32_t)(2 * DP_D * sizeof(T)))
                  : "memory");
+}
+
+// The same by per-thread prefetch instructions (LSU path), restricted to the 128-byte lines of head `rank` (K and V half of
+// every row): the bulk prefetches above share the SM's TMA unit with the weight ring -- ~850 KB per layer and CTA through a
+// unit that was measured to deliver ~20 B/clk.  Measured SLOWER than the bulk prefetches (268 vs 253 us per token: the
+// ~9 instructions per thread and boundary sit on the critical path of the projection phases); kept as OMR_DECODE_PF_KIND=1.
+template <typename T>
+__device__ __forceinline__ void prefetch_rows_lsu(const T* base, int r0, int r1, int rank) {
+  const char* b = reinterpret_cast<const char*>(base + (long long)r0 * (2 * DP_D) + rank * DP_HD);
+  constexpr int RB = 2 * DP_D * (int)sizeof(T), HB = DP_D * (int)sizeof(T), LPH = DP_HD * (int)sizeof(T) / 128;  // lines per head chunk
+  for (int i = threadIdx.x; i < 2 * LPH * (r1 - r0); i += DP_THREADS) {
+    const int row = i / (2 * LPH), w = i % (2 * LPH);
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(b + (long long)row * RB + (w / LPH) * HB + (w % LPH) * 128));
+  }
 }
 
 // ---- the weight ring -------------------------------------------------------------------------------------------
@@ -267,6 +264,25 @@ __device__ __forceinline__ void store_vec(float* dst, const float (&v)[8]) {
   *reinterpret_cast<float4*>(dst + lane * 8 + 4) = make_float4(v[4], v[5], v[6], v[7]);
 }
 // LayerNorm of the lane-distributed vector with the scale / shift rows of a ring slot
+// bf16 path: sum and sum of squares reduced side by side (one shuffle latency chain instead of two); the fp32 parity
+// path keeps the two-pass variance below
+__device__ __forceinline__ void layer_norm_1p(float (&v)[8], const float* gamma, const float* beta, float eps) {
+  float g[8], b[8];
+  load_vec(gamma, g);
+  load_vec(beta, b);
+  float sum = 0.f, sq = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { sum += v[k]; sq = fmaf(v[k], v[k], sq); }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  }
+  const float mean = sum * (1.f / DP_D);
+  const float rstd = rsqrtf(fmaxf(sq * (1.f / DP_D) - mean * mean, 0.f) + eps);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) v[k] = (v[k] - mean) * rstd * g[k] + b[k];
+}
 __device__ __forceinline__ void layer_norm(float (&v)[8], const float* gamma, const float* beta, float eps) {
   float sum = 0.f;
 #pragma unroll
@@ -415,6 +431,138 @@ __device__ __forceinline__ void gemv_ks_phase(Ring<T>& R, const float* xin, bool
   epi((b2 ? 128 : 0) + row, v + bias, lane & 1);
 }
 
+// ---- bf16 projections on the (legacy, warp-level) tensor-core path ---------------------------------------------------
+// As FMAs a pair of ring slots costs ~150 instructions per warp (unpacking bf16 pairs, 32 FMAs, the shuffle reduction)
+// and the projection phases are issue bound (measured ~930 cycles per pair with 16 warps on 4 schedulers).
+// mma.sync.m16n8k16 with the WEIGHTS as the A operand (16 weight rows x 16 reduction indices) and the input vector as
+// the B operand (broadcast to the 8 columns) does a 16 x 16 block per instruction.  The host packs the weights in
+// A-fragment order (params.py "matDecA" / "matDecKS"): a (16-row m-tile, 32-wide k-block, row half) is 512 contiguous
+// bytes that one conflict-free LDS.128 per lane turns into the A registers of TWO MMAs -- lane (g, t) holds rows g / g+8,
+// reduction indices 32 kb + 8t .. + 7; the k index inside an MMA is a free permutation, the input registers are packed to
+// match.  The input is rounded to bf16 (as in the per-kernel path, whose GEMMs read bf16 activations); accumulation fp32.
+__device__ __forceinline__ void mma_bf16_16816_fwd(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+// c += W[m-tile, k-blocks kb0 .. kb0 + NKB) x;  mt = first byte of the m-tile's k-block kb0; xb = 4 packed registers per
+// k-block (x[32 kb + 8t + 0..7])
+template <int NKB>
+__device__ __forceinline__ void mma_rows(float (&c)[4], const uint8_t* mt, const uint32_t* xb) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int kb = 0; kb < NKB; ++kb) {
+    const uint4 h0 = *reinterpret_cast<const uint4*>(mt + kb * 1024 + lane * 16);
+    const uint4 h1 = *reinterpret_cast<const uint4*>(mt + kb * 1024 + 512 + lane * 16);
+    mma_bf16_16816_fwd(c, h0.x, h1.x, h0.y, h1.y, xb[4 * kb], xb[4 * kb + 1]);
+    mma_bf16_16816_fwd(c, h0.z, h1.z, h0.w, h1.w, xb[4 * kb + 2], xb[4 * kb + 3]);
+  }
+}
+// the lane-distributed vector (lane l holds x[8l .. 8l+7]) -> B registers of k-blocks kb0 .. kb0 + NKB)
+template <int NKB>
+__device__ __forceinline__ void pack_x(const float (&x)[8], int kb0, uint32_t* xb) {
+  const int t = threadIdx.x & 3;
+  uint32_t px[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) px[j] = tc::pack_bf16(x[2 * j], x[2 * j + 1]);
+#pragma unroll
+  for (int kb = 0; kb < NKB; ++kb)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) xb[4 * kb + j] = __shfl_sync(0xffffffffu, px[j], (kb0 + kb) * 4 + t);
+}
+
+// N-split projection, bf16: NCH slots = 2 NCH m-tiles; warp w takes the k-quarter w >> 2 (two k-blocks) of the m-tiles
+// (w & 3), (w & 3) + 4, ...; the four k-quarter partials meet in `psum` [4][32 NCH] (the k-quarter 0 adds the bias, which
+// must be read before the slot is handed back); after a block barrier thread c < 32 NCH finishes column c: epi(c, value).
+template <int NCH, typename Epi>
+__device__ __forceinline__ void gemv_phase_mma(Ring<bf16>& R, const float* xs, const float* parts, bool LN, float* x_keep, float eps,
+                                               float* psum, Epi epi, long long* dbg = nullptr) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  long long t0 = dbg ? clock64() : 0;
+  float x[8];
+  load_vec(xs, x);
+  if (parts) {
+#pragma unroll
+    for (int r = 0; r < DP_CL; ++r) {
+      float pr[8];
+      load_vec(parts + r * DP_D, pr);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) x[k] += pr[k];
+    }
+  }
+  const uint8_t* s0 = R.acquire_at(0);
+  if (dbg) { long long tt = clock64(); dbg[0] += tt - t0; t0 = tt; }
+  if (LN) {
+    const float* gamma = reinterpret_cast<const float*>(s0 + Ring<bf16>::W_BYTES + 128);
+    layer_norm_1p(x, gamma, gamma + DP_D, eps);
+    if (x_keep && threadIdx.x < 32) store_vec(x_keep, x);
+  }
+  if (dbg) { long long tt = clock64(); dbg[1] += tt - t0; t0 = tt; }
+  const int kq = warp >> 2;
+  uint32_t xb[8];
+  pack_x<2>(x, 2 * kq, xb);
+#pragma unroll
+  for (int i = 0; i < (2 * NCH + 3) / 4; ++i) {
+    const int mt = (warp & 3) + 4 * i;
+    if (mt < 2 * NCH) {
+      const uint8_t* slot = R.acquire_at(mt >> 1);
+      float c[4] = {0.f, 0.f, 0.f, 0.f};
+      mma_rows<2>(c, slot + (mt & 1) * 8192 + kq * 2048, xb);
+      if (t == 0) {
+        float b0 = 0.f, b1 = 0.f;
+        if (kq == 0) {
+          const float* bias = reinterpret_cast<const float*>(slot + Ring<bf16>::W_BYTES) + (mt & 1) * 16;
+          b0 = bias[g];
+          b1 = bias[g + 8];
+        }
+        psum[kq * (32 * NCH) + mt * 16 + g] = c[0] + b0;
+        psum[kq * (32 * NCH) + mt * 16 + g + 8] = c[2] + b1;
+      }
+    }
+  }
+  if (dbg) { long long tt = clock64(); dbg[2] += tt - t0; t0 = tt; }
+#pragma unroll
+  for (int i = 0; i < NCH; ++i) R.release();
+  __syncthreads();
+  if (dbg) { long long tt = clock64(); dbg[3] += tt - t0; t0 = tt; }
+  for (int c = threadIdx.x; c < 32 * NCH; c += DP_THREADS)
+    epi(c, psum[c] + psum[32 * NCH + c] + psum[2 * 32 * NCH + c] + psum[3 * 32 * NCH + c]);
+  if (dbg) { long long tt = clock64(); dbg[4] += tt - t0; t0 = tt; }
+}
+
+// K-split projection, bf16: two slots = 256 rows x 64 = 16 m-tiles of two k-blocks, one per warp; lane (g, t) ends up
+// with rows g and g + 8 of its m-tile (identical in the four t-lanes, which share the four destinations):
+// epi(row, value, t).
+template <typename Epi>
+__device__ __forceinline__ void gemv_ks_phase_mma(Ring<bf16>& R, const float* xin, bool add_bias, Epi epi) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  uint32_t xb[8];
+#pragma unroll
+  for (int kb = 0; kb < 2; ++kb) {
+    const float4 a = *reinterpret_cast<const float4*>(xin + kb * 32 + t * 8);
+    const float4 b = *reinterpret_cast<const float4*>(xin + kb * 32 + t * 8 + 4);
+    xb[4 * kb] = tc::pack_bf16(a.x, a.y);
+    xb[4 * kb + 1] = tc::pack_bf16(a.z, a.w);
+    xb[4 * kb + 2] = tc::pack_bf16(b.x, b.y);
+    xb[4 * kb + 3] = tc::pack_bf16(b.z, b.w);
+  }
+  R.acquire_at(0);
+  const uint8_t* slot = R.acquire_at(warp >> 3);
+  float c[4] = {0.f, 0.f, 0.f, 0.f};
+  mma_rows<2>(c, slot + (warp & 7) * 2048, xb);
+  float b0 = 0.f, b1 = 0.f;
+  if (add_bias) {
+    const float* bias = reinterpret_cast<const float*>(slot + Ring<bf16>::W_BYTES) + (warp & 7) * 16;
+    b0 = bias[g];
+    b1 = bias[g + 8];
+  }
+  R.release();
+  R.release();
+  const int row = (warp >> 3) * 128 + (warp & 7) * 16 + g;
+  epi(row, c[0] + b0, t);
+  epi(row + 8, c[2] + b1, t);
+}
+
 // single-query attention of ONE (sample, head) by the whole CTA: keys [j_lo, tk); q in shared memory; the 64 outputs
 // are written into the CTA's own `out`.  K / V rows: 16-byte streaming loads, register double buffer.
 template <typename T>
@@ -554,14 +702,21 @@ __device__ __forceinline__ uint4 pack8(const float* p) {
 // Same contract as attn_head.  Warp w owns the 16-key tiles w, w+16, ...; NB register buffers of one tile (64 B per
 // thread) rotate: NB - 1 tiles are in flight while one is consumed (the stream is latency bound: bytes in flight per SM
 // = (NB - 1) x 32 KB against ~45 GB/s x ~1.4 us per SM at the HBM roofline).
-template <int NB>
+template <int NBW>  // buffers NB = NBW & 7; NBW >= 8: one 32-byte load per row instead of two 16-byte loads
 __device__ __noinline__ void attn_head_mma(float* sc, float* red, float* s_red, const float* q, const bf16* __restrict__ kp, int tk, int j_lo,
                               const float* __restrict__ kb, float scale, float* out, uint64_t pol,
                               const float* knew, const float* vnew) {
+  constexpr int NB = NBW & 7;
+  constexpr bool WIDE = NBW >= 8;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   const int n = tk - j_lo;
   const int n_glob = knew ? n - 1 : n;
   const int ntile = (n + 15) >> 4;
+  // element offsets of a thread's two 16-byte pieces inside the head's 64 dims.  Narrow: 8t and 32 + 8t (the four
+  // t-lanes of a row cover whole sectors per instruction); wide: 16t and 16t + 8 = ONE 32-byte load (a warp instruction
+  // covers 8 whole 128-byte lines).  Both the k index of the score MMA and the n index of the P V MMA are free
+  // permutations: q is packed to match, the output offsets are undone when the result is written.
+  const int off0 = WIDE ? 16 * t : 8 * t, off1 = WIDE ? 16 * t + 8 : 32 + 8 * t;
   const bf16* kbase = kp + (long long)j_lo * (2 * DP_D);
   // a pair of rows (g, g + 8) of tile `tile`: `o0`, `o1` = element offsets of the two 16-byte pieces inside the head
   auto fetch = [&](Row32(&r)[2], const bf16* base, const float* extra, int tile, int o0, int o1) {
@@ -570,8 +725,15 @@ __device__ __noinline__ void attn_head_mma(float* sc, float* red, float* s_red, 
       const int j = tile * 16 + g + 8 * h;
       if (j < n_glob) {
         const bf16* rp = base + (long long)j * (2 * DP_D);
-        r[h].lo = ldg_stream(rp + o0, pol);
-        r[h].hi = ldg_stream(rp + o1, pol);
+        if constexpr (WIDE) {
+          asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8], %9;"
+                       : "=r"(r[h].lo.x), "=r"(r[h].lo.y), "=r"(r[h].lo.z), "=r"(r[h].lo.w), "=r"(r[h].hi.x), "=r"(r[h].hi.y),
+                         "=r"(r[h].hi.z), "=r"(r[h].hi.w)
+                       : "l"(rp + o0), "l"(pol));
+        } else {
+          r[h].lo = ldg_stream(rp + o0, pol);
+          r[h].hi = ldg_stream(rp + o1, pol);
+        }
       } else if (j < n) {
         r[h].lo = pack8(extra + o0);
         r[h].hi = pack8(extra + o1);
@@ -585,16 +747,15 @@ __device__ __noinline__ void attn_head_mma(float* sc, float* red, float* s_red, 
   Row32 buf[NB][2];
 #pragma unroll
   for (int i = 0; i < NB - 1; ++i)
-    if (warp + i * DP_WARPS < ntile) fetch(buf[i], kbase, knew, warp + i * DP_WARPS, 8 * t, 32 + 8 * t);
+    if (warp + i * DP_WARPS < ntile) fetch(buf[i], kbase, knew, warp + i * DP_WARPS, off0, off1);
   uint32_t qb[8];
   {  // the k index of the score MMAs is whatever the loads deliver: dims 8t..8t+7 and 32+8t..32+8t+7 (as for V: the
      // four t-lanes of a row read whole 32-byte sectors in ONE instruction; with dims 16t..16t+15 split over two
      // instructions every sector crossed the L2 -> SM path twice, and that path -- not HBM -- bounded the K pass)
-    const float* qp = q + 8 * t;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      qb[i] = tc::pack_bf16(qp[2 * i] * scale, qp[2 * i + 1] * scale);
-      qb[4 + i] = tc::pack_bf16(qp[32 + 2 * i] * scale, qp[32 + 2 * i + 1] * scale);
+      qb[i] = tc::pack_bf16(q[off0 + 2 * i] * scale, q[off0 + 2 * i + 1] * scale);
+      qb[4 + i] = tc::pack_bf16(q[off1 + 2 * i] * scale, q[off1 + 2 * i + 1] * scale);
     }
   }
   float mx = -INFINITY;
@@ -619,7 +780,7 @@ __device__ __noinline__ void attn_head_mma(float* sc, float* red, float* s_red, 
       const int tile = base + i * DP_WARPS;
       if (tile < ntile) {
         const int nxt = tile + (NB - 1) * DP_WARPS;
-        if (nxt < ntile) fetch(buf[(i + NB - 1) % NB], kbase, knew, nxt, 8 * t, 32 + 8 * t);
+        if (nxt < ntile) fetch(buf[(i + NB - 1) % NB], kbase, knew, nxt, off0, off1);
         scores(buf[i], tile);
       }
     }
@@ -628,7 +789,7 @@ __device__ __noinline__ void attn_head_mma(float* sc, float* red, float* s_red, 
   const bf16* vbase = kbase + DP_D;
 #pragma unroll
   for (int i = 0; i < NB - 1; ++i)
-    if (warp + i * DP_WARPS < ntile) fetch(buf[i], vbase, vnew, warp + i * DP_WARPS, 8 * t, 32 + 8 * t);
+    if (warp + i * DP_WARPS < ntile) fetch(buf[i], vbase, vnew, warp + i * DP_WARPS, off0, off1);
   mx = block_max(mx, s_red);
   const float msafe = (mx == -INFINITY) ? 0.f : mx;
   float sum = 0.f;
@@ -657,16 +818,16 @@ __device__ __noinline__ void attn_head_mma(float* sc, float* red, float* s_red, 
       const int tile = base + i * DP_WARPS;
       if (tile < ntile) {
         const int nxt = tile + (NB - 1) * DP_WARPS;
-        if (nxt < ntile) fetch(buf[(i + NB - 1) % NB], vbase, vnew, nxt, 8 * t, 32 + 8 * t);
+        if (nxt < ntile) fetch(buf[(i + NB - 1) % NB], vbase, vnew, nxt, off0, off1);
         weigh(buf[i], tile);
       }
     }
   }
-  // rows of the accumulator are identical; lanes g == 0 hold, for i = 0..7, dims (i<4 ? 0 : 32) + 8t + 2(i%4) + {0,1}
+  // rows of the accumulator are identical; lanes g == 0 hold, for i = 0..7, dims (i<4 ? off0 : off1) + 2(i%4) + {0,1}
   if (g == 0) {
 #pragma unroll
     for (int i = 0; i < 8; ++i)
-      *reinterpret_cast<float2*>(red + warp * DP_HD + (i < 4 ? 0 : 32) + 8 * t + 2 * (i & 3)) = make_float2(acc[i][0], acc[i][1]);
+      *reinterpret_cast<float2*>(red + warp * DP_HD + (i < 4 ? off0 : off1) + 2 * (i & 3)) = make_float2(acc[i][0], acc[i][1]);
   }
   __syncthreads();
   if (tid < 4 * DP_HD) {  // 4 threads per output: 4 warps' partials each
@@ -811,7 +972,8 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_persistent_kernel(DPArgs
     } else {
       const int c = k - DP_LCH * p.L, r0 = vbeg + c * DP_CH;
       rows = vend - r0 < DP_CH ? vend - r0 : DP_CH;
-      brows = rows & ~3;  // bulk copies move multiples of 16 bytes; a ragged tail is read directly by its warp
+      brows = rows & ~3;
+      if (sizeof(T) == 2) rows = DP_CH;  // the fragment-ordered copy is padded to whole slots (zero rows)  // bulk copies move multiples of 16 bytes; a ragged tail is read directly by its warp
       d.w = w_out + (long long)r0 * DP_D;
       d.bias = p.b_out + r0;
       if (c == 0) { d.gamma = layers[p.L - 1].g3; d.beta = layers[p.L - 1].be3; }
@@ -839,7 +1001,10 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_persistent_kernel(DPArgs
     if (!((p.pf_mask >> bnd) & 1)) return;
     const int r0 = __popc((unsigned)p.pf_mask & ((1u << bnd) - 1u)) * pf_per;
     const int r1 = r0 + pf_per < pf_rows ? r0 + pf_per : pf_rows;
-    if (r0 < r1) prefetch_rows<T>(layers[tl].cross_kv + (long long)b * p.S * 2 * DP_D, r0, r1, rank);
+    if (r0 < r1) {
+      if (p.pf_kind) prefetch_rows_lsu<T>(layers[tl].cross_kv + (long long)b * p.S * 2 * DP_D, r0, r1, rank);
+      else prefetch_rows<T>(layers[tl].cross_kv + (long long)b * p.S * 2 * DP_D, r0, r1, rank);
+    }
   };
 
   for (int step = 0; step < nsteps && !fin; ++step) {
@@ -864,6 +1029,18 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_persistent_kernel(DPArgs
       {
         T* crow = W.self_kv + ((long long)b * p.Tmax + pos) * (2 * DP_D) + rank * DP_HD;
         const float* pin = l > 0 ? parts + xb * DP_CL * DP_D : nullptr;
+        if constexpr (sizeof(T) == 2) {
+          gemv_phase_mma<6>(R, xcur, pin, l > 0, xnxt, p.ln_eps, red, [&](int c, float v) {
+            const int which = c >> 6, j = c & (DP_HD - 1);  // 0 query, 1 key, 2 value
+            if (which == 0) {
+              qv[j] = v;
+            } else {
+              const T r = from_f<T>(v);
+              (which == 1 ? kn : vn)[j] = to_f(r);
+              crow[(which - 1) * DP_D + j] = r;
+            }
+          }, timed && p.dbg_phase == 1 ? dbgc : nullptr);
+        } else {
         gemv_phase<T, 6>(R, xcur, pin, l > 0, xnxt, p.ln_eps, [&](int c, float v, int sub) {
           const int which = c >> 6, j = c & (DP_HD - 1);  // 0 query, 1 key, 2 value
           if (which == 0) {
@@ -874,6 +1051,7 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_persistent_kernel(DPArgs
             if (sub == 1) crow[(which - 1) * DP_D + j] = r;
           }
         }, timed && p.dbg_phase == 1 ? dbgc : nullptr);
+        }
         if (l > 0) { float* t = xcur; xcur = xnxt; xnxt = t; }
       }
       LOCAL_SYNC(PH_QKV);
@@ -889,17 +1067,27 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_persistent_kernel(DPArgs
       cross_pf(5, l);
       // P3: partial sums of out_proj(a) over this head's 64 inputs -> all CTAs
       xb ^= 1;
+      if constexpr (sizeof(T) == 2) {
+        gemv_ks_phase_mma(R, av, rank == 0, [&](int n, float v, int dstcta) {
+          st_async(parts + (xb * DP_CL + rank) * DP_D + n, v, (unsigned)dstcta, &vb[xb]);
+        });
+      } else {
       gemv_ks_phase<T>(R, av, rank == 0, [&](int n, float v, int half) {
         float* dst = parts + (xb * DP_CL + rank) * DP_D + n;
         st_async(dst, v, 2 * half, &vb[xb]);
         st_async(dst, v, 2 * half + 1, &vb[xb]);
       });
+      }
       VEC_WAIT(xb, 4 * DP_CL * DP_D, PH_OUT);
       cross_pf(6, l);
       // P4: s = x + out_proj(a); x1 = LN1(s) (kept for P6's residual) -> cross query of head `rank`
+      if constexpr (sizeof(T) == 2) {
+        gemv_phase_mma<2>(R, xcur, parts + xb * DP_CL * DP_D, true, xnxt, p.ln_eps, red, [&](int c, float v) { qv[c] = v; }, timed && p.dbg_phase == 0 ? dbgc : nullptr);
+      } else {
       gemv_phase<T, 2>(R, xcur, parts + xb * DP_CL * DP_D, true, xnxt, p.ln_eps, [&](int c, float v, int sub) {
         if (sub == 0) qv[c] = v;
       }, timed && p.dbg_phase == 0 ? dbgc : nullptr);
+      }
       { float* t = xcur; xcur = xnxt; xnxt = t; }
       LOCAL_SYNC(PH_CQ);
       // P5: cross-attention of head `rank` over the projected encoder memory
@@ -913,32 +1101,49 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_persistent_kernel(DPArgs
         int lo = 0;
         if (p.window > 0 && npos - p.window > 0) lo = npos - p.window;
         if (npos - lo > p.pf_self) lo = npos - p.pf_self;  // the newest rows are the ones least likely to be cached
-        prefetch_rows<T>(layers[nl].self_kv + (long long)b * p.Tmax * 2 * DP_D, lo, npos, rank);
+        if (p.pf_kind) prefetch_rows_lsu<T>(layers[nl].self_kv + (long long)b * p.Tmax * 2 * DP_D, lo, npos, rank);
+        else prefetch_rows<T>(layers[nl].self_kv + (long long)b * p.Tmax * 2 * DP_D, lo, npos, rank);
       }
       // P6: partial sums of the cross out_proj(a)
       xb ^= 1;
+      if constexpr (sizeof(T) == 2) {
+        gemv_ks_phase_mma(R, av, rank == 0, [&](int n, float v, int dstcta) {
+          st_async(parts + (xb * DP_CL + rank) * DP_D + n, v, (unsigned)dstcta, &vb[xb]);
+        });
+      } else {
       gemv_ks_phase<T>(R, av, rank == 0, [&](int n, float v, int half) {
         float* dst = parts + (xb * DP_CL + rank) * DP_D + n;
         st_async(dst, v, 2 * half, &vb[xb]);
         st_async(dst, v, 2 * half + 1, &vb[xb]);
       });
+      }
       VEC_WAIT(xb, 4 * DP_CL * DP_D, PH_COUT);
       cross_pf(1, ncl);
       // P7: s = x1 + cross out_proj(a); x2 = LN2(s) (kept for P8's residual) -> this CTA's quarter of h = relu(W1 x2 + b1)
+      if constexpr (sizeof(T) == 2) {
+        gemv_phase_mma<2>(R, xcur, parts + xb * DP_CL * DP_D, true, xnxt, p.ln_eps, red, [&](int c, float v) { hv[c] = fmaxf(v, 0.f); }, timed && p.dbg_phase == 2 ? dbgc : nullptr);
+      } else {
       gemv_phase<T, 2>(R, xcur, parts + xb * DP_CL * DP_D, true, xnxt, p.ln_eps, [&](int c, float v, int sub) {
         if (sub == 0) hv[c] = fmaxf(v, 0.f);
       });
+      }
       { float* t = xcur; xcur = xnxt; xnxt = t; }
       LOCAL_SYNC(PH_FFN1);
       cross_pf(2, ncl);
       // P8: partial sums of W2 h over this CTA's quarter of h (s = x2 + W2 h + b2 is formed by the consumer: the next
       //     layer's P1 or the classifier)
       xb ^= 1;
+      if constexpr (sizeof(T) == 2) {
+        gemv_ks_phase_mma(R, hv, rank == 0, [&](int n, float v, int dstcta) {
+          st_async(parts + (xb * DP_CL + rank) * DP_D + n, v, (unsigned)dstcta, &vb[xb]);
+        });
+      } else {
       gemv_ks_phase<T>(R, hv, rank == 0, [&](int n, float v, int half) {
         float* dst = parts + (xb * DP_CL + rank) * DP_D + n;
         st_async(dst, v, 2 * half, &vb[xb]);
         st_async(dst, v, 2 * half + 1, &vb[xb]);
       });
+      }
       VEC_WAIT(xb, 4 * DP_CL * DP_D, PH_FFN2);
       cross_pf(3, ncl);
     }
@@ -965,8 +1170,60 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_persistent_kernel(DPArgs
         }
         const uint8_t* slot = R.acquire_at(0);
         const float* gamma = reinterpret_cast<const float*>(slot + Ring<T>::W_BYTES + 128);
-        layer_norm(x, gamma, gamma + DP_D, p.ln_eps);
+        if constexpr (sizeof(T) == 2) layer_norm_1p(x, gamma, gamma + DP_D, p.ln_eps);
+        else layer_norm(x, gamma, gamma + DP_D, p.ln_eps);
       }
+      if constexpr (sizeof(T) == 2) {
+        // groups of 4 slots = 8 m-tiles: warp w takes m-tile w & 7 and the k-half w >> 3; the two partials (the k-half 0
+        // with the bias) meet in a double-buffered [2][2][128] scratch; thread c < 128 finishes column c of the group and
+        // keeps its running first-max (its columns ascend).  (Groups of 2 slots were slower: the phase is bound by the
+        // ring's supply, ~20 B/clk per SM from L2, plus ~1 k cycles of fixed cost per group.)
+        const int g = lane >> 2, t = lane & 3, kh = warp >> 3, mtw = warp & 7;
+        uint32_t xbv[16];
+        pack_x<4>(x, 4 * kh, xbv);
+        best = -INFINITY;
+        bi = 0x7fffffff;
+        for (int ch = 0, it = 0; ch < nvch; ch += 4, ++it) {
+          float* ps = red + (it & 1) * 256;
+          const int nsl = nvch - ch < 4 ? nvch - ch : 4;
+          const int sl = mtw >> 1;
+          if (sl < nsl) {
+            const uint8_t* slot = R.acquire_at(sl);
+            float c[4] = {0.f, 0.f, 0.f, 0.f};
+            mma_rows<4>(c, slot + (mtw & 1) * 8192 + kh * 4096, xbv);
+            if (t == 0) {
+              float b0 = 0.f, b1 = 0.f;
+              if (kh == 0) {
+                // biases past the bulk-copied multiple of four of a ragged last slot are read directly
+                const int col0 = (ch + sl) * DP_CH + (mtw & 1) * 16 + g;
+                const int nb4 = ch + sl == nvch - 1 ? (ncols_v - (nvch - 1) * DP_CH) & ~3 : DP_CH;
+                const float* bias = reinterpret_cast<const float*>(slot + Ring<T>::W_BYTES);
+                const int r0 = (mtw & 1) * 16 + g, r1 = r0 + 8;
+                b0 = r0 < nb4 ? bias[r0] : (col0 < ncols_v ? p.b_out[vbeg + col0] : 0.f);
+                b1 = r1 < nb4 ? bias[r1] : (col0 + 8 < ncols_v ? p.b_out[vbeg + col0 + 8] : 0.f);
+              }
+              ps[kh * 128 + mtw * 16 + g] = c[0] + b0;
+              ps[kh * 128 + mtw * 16 + g + 8] = c[2] + b1;
+            }
+          }
+          for (int i = 0; i < nsl; ++i) R.release();
+          __syncthreads();
+          if (threadIdx.x < 128) {
+            const int c = ch * DP_CH + threadIdx.x;
+            if (c < ncols_v) {
+              const float r = to_f(from_f<T>(ps[threadIdx.x] + ps[128 + threadIdx.x]));
+              if (r > best) { best = r; bi = vbeg + c; }
+            }
+          }
+        }
+        // first-max merge over the warp (lanes hold different columns)
+#pragma unroll
+        for (int o = 1; o <= 16; o <<= 1) {
+          const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+          const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+          if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+        }
+      } else {
       for (int ch = 0; ch < nvch; ch += 2) {
         const bool second = ch + 1 < nvch;
         const uint8_t* s0 = R.acquire_at(0);
@@ -990,6 +1247,7 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_persistent_kernel(DPArgs
         const float ob = __shfl_xor_sync(0xffffffffu, best, o);
         const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
         if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+      }
       }
       if (lane == 0) { cand_v[warp] = best; cand_i[warp] = bi; }
       __syncthreads();
@@ -1097,7 +1355,15 @@ extern "C" int omr_decode_persistent(int dt, const void* layers_dev, int L, cons
       pf[0] = a ? atoi(a) : 2400;
     }
     p.pf_cross = pf[0]; p.pf_self = pf[1]; p.stagger_ns = pf[2]; p.pf_mask = pf[3]; p.dbg_phase = pf[4];
+    {
+      const char* pk = getenv("OMR_DECODE_PF_KIND");
+      p.pf_kind = pk ? atoi(pk) : 0;
+    }
     nb_sel = pf[5] == 3 || pf[5] == 4 ? pf[5] : 2;
+    {
+      const char* wd = getenv("OMR_DECODE_WIDE");
+      if ((wd ? atoi(wd) : 1) && nb_sel <= 3) nb_sel += 8;  // default: wide loads (measured 273 -> 261 us per token)
+    }
   }
   const int max_keys = S > Tmax ? S : Tmax;
   p.sc_floats = (max_keys + 15) & ~15;
@@ -1121,10 +1387,14 @@ extern "C" int omr_decode_persistent(int dt, const void* layers_dev, int L, cons
       OMR_CUDA(cudaFuncSetAttribute(decode_persistent_kernel<bf16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
       OMR_CUDA(cudaFuncSetAttribute(decode_persistent_kernel<bf16, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
       OMR_CUDA(cudaFuncSetAttribute(decode_persistent_kernel<bf16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+      OMR_CUDA(cudaFuncSetAttribute(decode_persistent_kernel<bf16, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+      OMR_CUDA(cudaFuncSetAttribute(decode_persistent_kernel<bf16, 11>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
       cfg[1] = true;
     }
     if (nb_sel == 3) OMR_CUDA(cudaLaunchKernelEx(&lc, decode_persistent_kernel<bf16, 3>, p));
     else if (nb_sel == 4) OMR_CUDA(cudaLaunchKernelEx(&lc, decode_persistent_kernel<bf16, 4>, p));
+    else if (nb_sel == 10) OMR_CUDA(cudaLaunchKernelEx(&lc, decode_persistent_kernel<bf16, 10>, p));
+    else if (nb_sel == 11) OMR_CUDA(cudaLaunchKernelEx(&lc, decode_persistent_kernel<bf16, 11>, p));
     else OMR_CUDA(cudaLaunchKernelEx(&lc, decode_persistent_kernel<bf16, 2>, p));
   } else {
     if (!cfg[0]) { OMR_CUDA(cudaFuncSetAttribute(decode_persistent_kernel<float, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024)); cfg[0] = true; }

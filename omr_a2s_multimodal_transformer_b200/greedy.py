@@ -107,16 +107,18 @@ class BatchedGreedyDecoder:
         recs = (_DecodeLayer * len(cross_kv))()
         for li, L in enumerate(dec.transformer_decoder.layers):
             sa, ca = L.self_attn, L.multihead_attn
-            wc_in = c.get(ca.in_proj_weight, "mat", dtype)
+            # layouts of the persistent kernel (include/omr_b200.h, omr_decode_layer): bf16 = mma.sync A-fragment order,
+            # fp32 = row-major; the projections that FOLLOW an attention head / the FFN quarter are split along their
+            # reduction index inside the kernel and come as four column slices
+            ns, ks = ("matDecA", "matDecKS") if dtype == torch.bfloat16 else ("mat", "matKS4")
+            wc_in = c.get(ca.in_proj_weight, ns, dtype)
             vals = dict(
-                w_in=c.get(sa.in_proj_weight, "mat", dtype), b_in=sa.in_proj_bias,
-                # the projections that FOLLOW an attention head / the FFN quarter are split along their reduction index
-                # inside the kernel: column slices [4][256][64] (include/omr_b200.h, omr_decode_layer)
-                w_o=c.get(sa.out_proj.weight, "matKS4", dtype), b_o=sa.out_proj.bias,
+                w_in=c.get(sa.in_proj_weight, ns, dtype), b_in=sa.in_proj_bias,
+                w_o=c.get(sa.out_proj.weight, ks, dtype), b_o=sa.out_proj.bias,
                 wc_q=wc_in[:d], bc_q=ca.in_proj_bias[:d],
-                wc_o=c.get(ca.out_proj.weight, "matKS4", dtype), bc_o=ca.out_proj.bias,
-                w1=c.get(L.linear1.weight, "mat", dtype), b1=L.linear1.bias,
-                w2=c.get(L.linear2.weight, "matKS4", dtype), b2=L.linear2.bias,
+                wc_o=c.get(ca.out_proj.weight, ks, dtype), bc_o=ca.out_proj.bias,
+                w1=c.get(L.linear1.weight, ns, dtype), b1=L.linear1.bias,
+                w2=c.get(L.linear2.weight, ks, dtype), b2=L.linear2.bias,
                 g1=L.norm1.weight, be1=L.norm1.bias, g2=L.norm2.weight, be2=L.norm2.bias, g3=L.norm3.weight, be3=L.norm3.bias,
                 self_kv=st["self_kv"][li], cross_kv=cross_kv[li])
             for k, t in vals.items():
@@ -125,7 +127,7 @@ class BatchedGreedyDecoder:
         table = torch.frombuffer(bytearray(bytes(recs)), dtype=torch.uint8).to(dev)
         nfl = int(_lib.load().omr_decode_persistent_scratch_floats(b, dec.nhead, d, dec.output_size))
         scratch = torch.empty(nfl, dtype=torch.float32, device=dev)
-        wout = c.get(dec.out_layer.weight, "mat", dtype)
+        wout = c.get(dec.out_layer.weight, "matDecA" if dtype == torch.bfloat16 else "mat", dtype)  # bf16: rows padded to 32
         table_emb = c.get(dec.embedding.weight, "mat", dtype)
         mem_bias = st["mem_bias"]
         s_len = cross_kv[0].shape[1]

@@ -37,7 +37,8 @@ def resolve_dtype(explicit: Optional[torch.dtype]) -> torch.dtype:
 
 class WeightCache:
     """kind: "conv" [Co,3,3,Ci] | "convT" [Ci,3,3,Co] | "dw" [3,3,C] | "mat" [N,K] (same order, 2-D) | "matT" [K,N] |
-    "matKS4" [4][N][K/4] (not an Adam shadow: re-packed when the parameter's version moves)."""
+    "matKS4" [4][N][K/4] | "matDecA" / "matDecKS" (mma fragment orders of the bf16 persistent decode kernel) -- the last
+    three are not Adam shadows: re-packed when the parameter's version moves."""
 
     def __init__(self) -> None:
         self._c: Dict[Tuple[int, str, torch.dtype], Tuple[int, torch.Tensor]] = {}
@@ -98,6 +99,24 @@ class WeightCache:
             w2 = w.reshape(w.shape[0], -1)
             n, k = w2.shape
             return ops.cast(w2.view(n, 4, k // 4).permute(1, 0, 2).contiguous(), dtype).view(4 * n, k // 4)
+        if kind == "matDecA":
+            # [N,K] -> mma.sync A-fragment order of the persistent decode kernel's bf16 projections: rows padded to a
+            # multiple of 32, then [N/16 m-tiles][K/32 k-blocks][2 row halves][8 rows g][4 lanes t][8 elements]: a warp's
+            # LDS.128 of one (m-tile, k-block, half) is 512 contiguous bytes, lane (g,t) gets row g (+8), k = 32kb+8t..+7
+            w2 = w.reshape(w.shape[0], -1)
+            n, k = w2.shape
+            npad = (n + 31) // 32 * 32
+            if npad != n:
+                w2 = torch.cat([w2, w2.new_zeros(npad - n, k)], 0)
+            t = w2.view(npad // 16, 2, 8, k // 32, 4, 8).permute(0, 3, 1, 2, 4, 5).contiguous()
+            return ops.cast(t, dtype).view(npad, k)
+        if kind == "matDecKS":
+            # [N,K] -> the four column slices [4][N][K/4] of "matKS4", each in the A-fragment order above
+            w2 = w.reshape(w.shape[0], -1)
+            n, k = w2.shape
+            ks = k // 4
+            t = w2.view(n // 16, 2, 8, 4, ks // 32, 4, 8).permute(3, 0, 4, 1, 2, 5, 6).contiguous()
+            return ops.cast(t, dtype).view(4 * n, ks)
         if kind == "matT":  # [R,C] -> [C,R]: the K-major operand of the data-gradient GEMMs
             w2 = w.reshape(w.shape[0], -1)
             return ops.cast(w2.t().contiguous(), dtype)

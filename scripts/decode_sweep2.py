@@ -14,7 +14,7 @@ m = pkg.MultimodalTransformer(128, 1024, 195, 808, 1268, w2i, i2w).to(dev).eval(
 m.set_compute_dtype(torch.bfloat16)
 xi, _, xa, _, _, _ = bench.make_batch(32, w2i, seed=500)
 steps = int(sys.argv[1]) if len(sys.argv) > 1 and sys.argv[1].isdigit() else 400
-KEYS = ["OMR_DECODE_NB", "OMR_DECODE_PF_MASK", "OMR_DECODE_PF_CROSS", "OMR_DECODE_PF_SELF", "OMR_DECODE_STAGGER_NS"]
+KEYS = ["OMR_DECODE_PF_KIND", "OMR_DECODE_WIDE", "OMR_DECODE_NB", "OMR_DECODE_PF_MASK", "OMR_DECODE_PF_CROSS", "OMR_DECODE_PF_SELF", "OMR_DECODE_STAGGER_NS"]
 
 
 def run(cfg, timing=False):
