@@ -316,7 +316,10 @@ int omr_attn_decode(int dt, const void* q, long long q_bs, const void* k, long l
  * pre-projected memory, classifier, first-max argmax, EOS bookkeeping) per launch, three cluster exchanges per layer.
  * ABI v4: w_o, wc_o and w2 -- the projections that follow an attention head / the FFN quarter and are split along
  * their reduction index inside the kernel -- are passed as COLUMN SLICES [4][D][D/4] (slice r = W[:, r*D/4:(r+1)*D/4],
- * contiguous); all other matrices stay row-major [N,K].
+ * contiguous).  dt = fp32: slices and all other matrices row-major.  dt = bf16: every matrix (w_in, wc_q, w1, w_out and
+ * each column slice) in mma.sync A-FRAGMENT ORDER: rows padded with zeros to a multiple of 32, then
+ * [rows/16][K/32][2][8][4][8] = (16-row tile, 32-wide k-block, row half hf, row g, lane quarter t, element e) holding
+ * W[16*tile + 8*hf + g][32*kb + 8*t + e] (K = D, or D/4 for a slice).
  * Replaces the per-token Python loop of model.py:184-193 / 602-611.  `layers` is a DEVICE array of L
  * omr_decode_layer records (weights in `dt`, biases / LayerNorm affine in fp32).  State (tok, val, finished,
  * out_tokens/out_vals [B,out_ld], *pos) stays on the device across launches; *pos advances by the steps executed.

@@ -282,12 +282,18 @@ __global__ void __launch_bounds__(256) dwconv3x3_wgrad_col_kernel(const T* __res
       load4(p, r[1]);
       if (hasr) load4(p + C, r[2]); else { r[2][0] = r[2][1] = r[2][2] = r[2][3] = 0.f; }
     };
+    // the loads of row h + 2 (x) and h + 1 (dy) are issued before the FMAs of row h: the walk is latency bound (13 rows,
+    // four 8-byte loads each), so two rows' worth of loads are kept in flight per thread
     fetch(xr[0], -1);
     fetch(xr[1], 0);
+    fetch(xr[2], 1);
+    float g[4];
+    load4(gp, g);
     for (int h = 0; h < H; ++h) {
-      fetch(xr[2], h + 1);
-      float g[4];
-      load4(gp + (long long)h * rowpitch, g);
+      float xn[3][4], gn[4];
+      fetch(xn, h + 2);
+      if (h + 1 < H) load4(gp + (long long)(h + 1) * rowpitch, gn);
+      else { gn[0] = gn[1] = gn[2] = gn[3] = 0.f; }
 #pragma unroll
       for (int k = 0; k < 4; ++k) accb[k] += g[k];
 #pragma unroll
@@ -299,7 +305,9 @@ __global__ void __launch_bounds__(256) dwconv3x3_wgrad_col_kernel(const T* __res
 #pragma unroll
       for (int q = 0; q < 3; ++q)
 #pragma unroll
-        for (int k = 0; k < 4; ++k) { xr[0][q][k] = xr[1][q][k]; xr[1][q][k] = xr[2][q][k]; }
+        for (int k = 0; k < 4; ++k) { xr[0][q][k] = xr[1][q][k]; xr[1][q][k] = xr[2][q][k]; xr[2][q][k] = xn[q][k]; }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) g[k] = gn[k];
     }
   }
   // thread t's channel quad is (blockIdx.x * 256 + t) % cg: combine the threads of the block that share it
