@@ -25,6 +25,10 @@
 //     The phase is bound by the load latency per SM (one tile per warp in flight: measured time independent of the
 //     batch, i.e. of the HBM load), not by HBM; the next attention's rows are prefetched into L2 in thirds at the
 //     preceding phase boundaries (OMR_DECODE_PF_MASK).  New K/V rows go straight into the cache.
+//     Measured and rejected (all SLOWER, in every phase of the kernel, not only the attention): three or four tiles in
+//     flight per warp (NB = 3, 4: 293 / 355 us per token against 261), the warp's last tile of a pass loaded up front into a
+//     third buffer (290 against 271 at 1268 steps), per-thread L2 prefetch instructions instead of the bulk prefetches
+//     (268 against 253), classifier groups of two slots instead of four (59 k cycles against 44 k).
 // Numerics are those of the per-kernel path (fp32 accumulation; logits rounded to the storage type before the argmax).
 #include <stdlib.h>
 
