@@ -80,7 +80,6 @@ struct DPArgs {
                           // 0 after the previous layer's cross-attention, 1 its out-projection, 2 FFN1, 3 FFN2, 4 after
                           // q|k|v, 5 after the self-attention, 6 after its out-projection); the rows are dealt evenly
   int dbg_phase;          // which projection phase feeds the detail counters (0 cross-q, 1 q|k|v, 2 FFN1)
-  int pf_kind;            // 0 bulk (TMA) prefetches of whole rows dealt over the cluster, 1 per-thread prefetches of the head's lines
 };
 
 // 8 consecutive elements as raw registers (so that many independent 16-byte loads can be in flight per thread)
@@ -142,20 +141,6 @@ __device__ __forceinline__ void prefetch_rows(const T* base, int r0, int r1, int
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(base + (long long)a * (2 * DP_D)),
                  "r"((uint32_t)(b - a) * (uint32_t)(2 * DP_D * sizeof(T)))
                  : "memory");
-}
-
-// The same by per-thread prefetch instructions (LSU path), restricted to the 128-byte lines of head `rank` (K and V half of
-// every row): the bulk prefetches above share the SM's TMA unit with the weight ring -- ~850 KB per layer and CTA through a
-// unit that was measured to deliver ~20 B/clk.  Measured SLOWER than the bulk prefetches (268 vs 253 us per token: the
-// ~9 instructions per thread and boundary sit on the critical path of the projection phases); kept as OMR_DECODE_PF_KIND=1.
-template <typename T>
-__device__ __forceinline__ void prefetch_rows_lsu(const T* base, int r0, int r1, int rank) {
-  const char* b = reinterpret_cast<const char*>(base + (long long)r0 * (2 * DP_D) + rank * DP_HD);
-  constexpr int RB = 2 * DP_D * (int)sizeof(T), HB = DP_D * (int)sizeof(T), LPH = DP_HD * (int)sizeof(T) / 128;  // lines per head chunk
-  for (int i = threadIdx.x; i < 2 * LPH * (r1 - r0); i += DP_THREADS) {
-    const int row = i / (2 * LPH), w = i % (2 * LPH);
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(b + (long long)row * RB + (w / LPH) * HB + (w % LPH) * 128));
-  }
 }
 
 // ---- the weight ring -------------------------------------------------------------------------------------------
@@ -240,6 +225,12 @@ struct Ring {
     const int g = consumed + ahead, slot = g % NSLOT;
     mbar_wait(&full[slot], (uint32_t)((g / NSLOT) & 1));
     return base + (size_t)slot * SLOT_BYTES;
+  }
+  // k slots at once, as ONE copy of the refill code (the decode loop is ~8000 instructions at the edge of the instruction
+  // cache: every inlined copy of release() carries the whole issue() path)
+  __device__ __forceinline__ void release_many(int k) {
+#pragma unroll 1
+    for (int i = 0; i < k; ++i) release();
   }
   // this warp has the slot's values in registers: hand the slot back; its owner refills the slot freed DEFER chunks ago
   __device__ __forceinline__ void release() {
@@ -525,8 +516,7 @@ __device__ __forceinline__ void gemv_phase_mma(Ring<bf16>& R, const float* xs, c
     }
   }
   if (dbg) { long long tt = clock64(); dbg[2] += tt - t0; t0 = tt; }
-#pragma unroll
-  for (int i = 0; i < NCH; ++i) R.release();
+  R.release_many(NCH);
   __syncthreads();
   if (dbg) { long long tt = clock64(); dbg[3] += tt - t0; t0 = tt; }
   for (int c = threadIdx.x; c < 32 * NCH; c += DP_THREADS)
@@ -560,8 +550,7 @@ __device__ __forceinline__ void gemv_ks_phase_mma(Ring<bf16>& R, const float* xi
     b0 = bias[g];
     b1 = bias[g + 8];
   }
-  R.release();
-  R.release();
+  R.release_many(2);
   const int row = (warp >> 3) * 128 + (warp & 7) * 16 + g;
   epi(row, c[0] + b0, t);
   epi(row + 8, c[2] + b1, t);
@@ -706,12 +695,12 @@ __device__ __forceinline__ uint4 pack8(const float* p) {
 // Same contract as attn_head.  Warp w owns the 16-key tiles w, w+16, ...; NB register buffers of one tile (64 B per
 // thread) rotate: NB - 1 tiles are in flight while one is consumed (the stream is latency bound: bytes in flight per SM
 // = (NB - 1) x 32 KB against ~45 GB/s x ~1.4 us per SM at the HBM roofline).
-template <int NBW>  // buffers NB = NBW & 7; NBW >= 8: one 32-byte load per row instead of two 16-byte loads
+template <int NBW>  // buffers NB = NBW & 7; NBW & 8: one 32-byte load per row instead of two 16-byte loads (other bits: unused)
 __device__ __noinline__ void attn_head_mma(float* sc, float* red, float* s_red, const float* q, const bf16* __restrict__ kp, int tk, int j_lo,
                               const float* __restrict__ kb, float scale, float* out, uint64_t pol,
                               const float* knew, const float* vnew) {
   constexpr int NB = NBW & 7;
-  constexpr bool WIDE = NBW >= 8;
+  constexpr bool WIDE = (NBW & 8) != 0;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   const int n = tk - j_lo;
   const int n_glob = knew ? n - 1 : n;
@@ -848,7 +837,9 @@ template <typename T, int NB>
 __device__ __forceinline__ void attention(float* sc, float* red, float* s_red, const float* q, const T* kp, int tk, int j_lo,
                                           const float* kb, float scale, float* out, uint64_t pol,
                                           const float* knew, const float* vnew) {
-  if constexpr (sizeof(T) == 2) attn_head_mma<NB>(sc, red, s_red, q, kp, tk, j_lo, kb, scale, out, pol, knew, vnew);
+  constexpr int NBA = NB;  // every kernel instance gets its own copy of the function: ptxas 12.9 crashes (SIGSEGV) on two
+                           // entries that call the same non-inlined function
+  if constexpr (sizeof(T) == 2) attn_head_mma<NBA>(sc, red, s_red, q, kp, tk, j_lo, kb, scale, out, pol, knew, vnew);
   else attn_head<T>(sc, red, s_red, q, kp, tk, j_lo, kb, scale, out, pol, knew, vnew);
 }
 
@@ -906,7 +897,9 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_persistent_kernel(DPArgs
   const int rank = (int)cluster_rank();          // = head owned by this CTA
   const int b = (int)cluster_id_x();             // = sample owned by this cluster
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const bool timed = p.timing && b == 0 && rank == 0 && threadIdx.x == 0;
+  // the per-phase cycle counters are compiled into their own kernel instance (NB & 32): the decode loop is ~135 KB of code,
+  // at the edge of the instruction cache -- every variant that made it bigger ran slower in ALL phases
+  const bool timed = (NB & 32) != 0 && p.timing && b == 0 && rank == 0 && threadIdx.x == 0;
   const int pos0 = *p.pos;
   int nsteps = p.nsteps;
   if (pos0 + nsteps > p.Tmax) nsteps = p.Tmax - pos0;
@@ -1005,10 +998,7 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_persistent_kernel(DPArgs
     if (!((p.pf_mask >> bnd) & 1)) return;
     const int r0 = __popc((unsigned)p.pf_mask & ((1u << bnd) - 1u)) * pf_per;
     const int r1 = r0 + pf_per < pf_rows ? r0 + pf_per : pf_rows;
-    if (r0 < r1) {
-      if (p.pf_kind) prefetch_rows_lsu<T>(layers[tl].cross_kv + (long long)b * p.S * 2 * DP_D, r0, r1, rank);
-      else prefetch_rows<T>(layers[tl].cross_kv + (long long)b * p.S * 2 * DP_D, r0, r1, rank);
-    }
+    if (r0 < r1) prefetch_rows<T>(layers[tl].cross_kv + (long long)b * p.S * 2 * DP_D, r0, r1, rank);
   };
 
   for (int step = 0; step < nsteps && !fin; ++step) {
@@ -1105,8 +1095,7 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_persistent_kernel(DPArgs
         int lo = 0;
         if (p.window > 0 && npos - p.window > 0) lo = npos - p.window;
         if (npos - lo > p.pf_self) lo = npos - p.pf_self;  // the newest rows are the ones least likely to be cached
-        if (p.pf_kind) prefetch_rows_lsu<T>(layers[nl].self_kv + (long long)b * p.Tmax * 2 * DP_D, lo, npos, rank);
-        else prefetch_rows<T>(layers[nl].self_kv + (long long)b * p.Tmax * 2 * DP_D, lo, npos, rank);
+        prefetch_rows<T>(layers[nl].self_kv + (long long)b * p.Tmax * 2 * DP_D, lo, npos, rank);
       }
       // P6: partial sums of the cross out_proj(a)
       xb ^= 1;
@@ -1210,7 +1199,7 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_persistent_kernel(DPArgs
               ps[kh * 128 + mtw * 16 + g + 8] = c[2] + b1;
             }
           }
-          for (int i = 0; i < nsl; ++i) R.release();
+          R.release_many(nsl);
           __syncthreads();
           if (threadIdx.x < 128) {
             const int c = ch * DP_CH + threadIdx.x;
@@ -1359,14 +1348,11 @@ extern "C" int omr_decode_persistent(int dt, const void* layers_dev, int L, cons
       pf[0] = a ? atoi(a) : 2400;
     }
     p.pf_cross = pf[0]; p.pf_self = pf[1]; p.stagger_ns = pf[2]; p.pf_mask = pf[3]; p.dbg_phase = pf[4];
-    {
-      const char* pk = getenv("OMR_DECODE_PF_KIND");
-      p.pf_kind = pk ? atoi(pk) : 0;
-    }
-    nb_sel = pf[5] == 3 || pf[5] == 4 ? pf[5] : 2;
+
+    nb_sel = 2;  // (three and four rotating buffers were measured slower and are no longer instantiated)
     {
       const char* wd = getenv("OMR_DECODE_WIDE");
-      if ((wd ? atoi(wd) : 1) && nb_sel <= 3) nb_sel += 8;  // default: wide loads (measured 273 -> 261 us per token)
+      if ((wd ? atoi(wd) : 1)) nb_sel += 8;  // default: wide loads (measured 273 -> 261 us per token)
     }
   }
   const int max_keys = S > Tmax ? S : Tmax;
@@ -1386,22 +1372,23 @@ extern "C" int omr_decode_persistent(int dt, const void* layers_dev, int L, cons
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = DP_CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   lc.attrs = attr; lc.numAttrs = 1;
+  // instances: bf16 with wide loads (10), the same with the per-phase counters (42), fp32 (2).  (ptxas 12.9 crashed on a
+  // translation unit that also held the narrow-load bf16 kernel and a timed fp32 one.)
+  const bool want_timing = timing != nullptr;
+  (void)nb_sel;
   if (dt == OMR_BF16) {
     if (!cfg[1]) {
-      OMR_CUDA(cudaFuncSetAttribute(decode_persistent_kernel<bf16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-      OMR_CUDA(cudaFuncSetAttribute(decode_persistent_kernel<bf16, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-      OMR_CUDA(cudaFuncSetAttribute(decode_persistent_kernel<bf16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
       OMR_CUDA(cudaFuncSetAttribute(decode_persistent_kernel<bf16, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-      OMR_CUDA(cudaFuncSetAttribute(decode_persistent_kernel<bf16, 11>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+      OMR_CUDA(cudaFuncSetAttribute(decode_persistent_kernel<bf16, 42>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
       cfg[1] = true;
     }
-    if (nb_sel == 3) OMR_CUDA(cudaLaunchKernelEx(&lc, decode_persistent_kernel<bf16, 3>, p));
-    else if (nb_sel == 4) OMR_CUDA(cudaLaunchKernelEx(&lc, decode_persistent_kernel<bf16, 4>, p));
-    else if (nb_sel == 10) OMR_CUDA(cudaLaunchKernelEx(&lc, decode_persistent_kernel<bf16, 10>, p));
-    else if (nb_sel == 11) OMR_CUDA(cudaLaunchKernelEx(&lc, decode_persistent_kernel<bf16, 11>, p));
-    else OMR_CUDA(cudaLaunchKernelEx(&lc, decode_persistent_kernel<bf16, 2>, p));
+    if (want_timing) OMR_CUDA(cudaLaunchKernelEx(&lc, decode_persistent_kernel<bf16, 42>, p));
+    else OMR_CUDA(cudaLaunchKernelEx(&lc, decode_persistent_kernel<bf16, 10>, p));
   } else {
-    if (!cfg[0]) { OMR_CUDA(cudaFuncSetAttribute(decode_persistent_kernel<float, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024)); cfg[0] = true; }
+    if (!cfg[0]) {
+      OMR_CUDA(cudaFuncSetAttribute(decode_persistent_kernel<float, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+      cfg[0] = true;
+    }
     OMR_CUDA(cudaLaunchKernelEx(&lc, decode_persistent_kernel<float, 2>, p));
   }
   omr_count_launch();
