@@ -453,49 +453,47 @@ __device__ __forceinline__ void mma_rows(float (&c)[4], const uint8_t* mt, const
     mma_bf16_16816_fwd(c, h0.z, h1.z, h0.w, h1.w, xb[4 * kb + 2], xb[4 * kb + 3]);
   }
 }
-// the lane-distributed vector (lane l holds x[8l .. 8l+7]) -> B registers of k-blocks kb0 .. kb0 + NKB)
-template <int NKB>
-__device__ __forceinline__ void pack_x(const float (&x)[8], int kb0, uint32_t* xb) {
-  const int t = threadIdx.x & 3;
-  uint32_t px[4];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) px[j] = tc::pack_bf16(x[2 * j], x[2 * j + 1]);
-#pragma unroll
-  for (int kb = 0; kb < NKB; ++kb)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) xb[4 * kb + j] = __shfl_sync(0xffffffffu, px[j], (kb0 + kb) * 4 + t);
-}
-
 // N-split projection, bf16: NCH slots = 2 NCH m-tiles; warp w takes the k-quarter w >> 2 (two k-blocks) of the m-tiles
 // (w & 3), (w & 3) + 4, ...; the four k-quarter partials meet in `psum` [4][32 NCH] (the k-quarter 0 adds the bias, which
 // must be read before the slot is handed back); after a block barrier thread c < 32 NCH finishes column c: epi(c, value).
 template <int NCH, typename Epi>
 __device__ __forceinline__ void gemv_phase_mma(Ring<bf16>& R, const float* xs, const float* parts, bool LN, float* x_keep, float eps,
-                                               float* psum, Epi epi, long long* dbg = nullptr) {
+                                               float* psum, uint32_t* xpk, Epi epi, long long* dbg = nullptr) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   long long t0 = dbg ? clock64() : 0;
-  float x[8];
-  load_vec(xs, x);
-  if (parts) {
+  // the input vector (residual + the four partial vectors, LayerNorm) is formed by ONE warp and published as packed bf16:
+  // sixteen warps doing it redundantly cost ~2000 cycles of issue slots per phase (four warps per scheduler) against a
+  // latency chain of ~400
+  if (warp == 0) {
+    float x[8];
+    load_vec(xs, x);
+    if (parts) {
 #pragma unroll
-    for (int r = 0; r < DP_CL; ++r) {
-      float pr[8];
-      load_vec(parts + r * DP_D, pr);
+      for (int r = 0; r < DP_CL; ++r) {
+        float pr[8];
+        load_vec(parts + r * DP_D, pr);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) x[k] += pr[k];
+        for (int k = 0; k < 8; ++k) x[k] += pr[k];
+      }
     }
+    if (LN) {
+      const uint8_t* s0 = R.acquire_at(0);
+      const float* gamma = reinterpret_cast<const float*>(s0 + Ring<bf16>::W_BYTES + 128);
+      layer_norm_1p(x, gamma, gamma + DP_D, eps);
+      if (x_keep) store_vec(x_keep, x);
+    }
+    *reinterpret_cast<uint4*>(xpk + lane * 4) = make_uint4(tc::pack_bf16(x[0], x[1]), tc::pack_bf16(x[2], x[3]), tc::pack_bf16(x[4], x[5]),
+                                                           tc::pack_bf16(x[6], x[7]));
   }
-  const uint8_t* s0 = R.acquire_at(0);
+  __syncthreads();
   if (dbg) { long long tt = clock64(); dbg[0] += tt - t0; t0 = tt; }
-  if (LN) {
-    const float* gamma = reinterpret_cast<const float*>(s0 + Ring<bf16>::W_BYTES + 128);
-    layer_norm_1p(x, gamma, gamma + DP_D, eps);
-    if (x_keep && threadIdx.x < 32) store_vec(x_keep, x);
-  }
-  if (dbg) { long long tt = clock64(); dbg[1] += tt - t0; t0 = tt; }
   const int kq = warp >> 2;
   uint32_t xb[8];
-  pack_x<2>(x, 2 * kq, xb);
+#pragma unroll
+  for (int kb = 0; kb < 2; ++kb) {  // B registers of k-block 2 kq + kb: x[32 (2 kq + kb) + 8t .. + 7]
+    const uint4 v = *reinterpret_cast<const uint4*>(xpk + ((2 * kq + kb) * 32 + 8 * t) / 2);
+    xb[4 * kb] = v.x; xb[4 * kb + 1] = v.y; xb[4 * kb + 2] = v.z; xb[4 * kb + 3] = v.w;
+  }
 #pragma unroll
   for (int i = 0; i < (2 * NCH + 3) / 4; ++i) {
     const int mt = (warp & 3) + 4 * i;
@@ -516,11 +514,12 @@ __device__ __forceinline__ void gemv_phase_mma(Ring<bf16>& R, const float* xs, c
     }
   }
   if (dbg) { long long tt = clock64(); dbg[2] += tt - t0; t0 = tt; }
-  R.release_many(NCH);
   __syncthreads();
   if (dbg) { long long tt = clock64(); dbg[3] += tt - t0; t0 = tt; }
   for (int c = threadIdx.x; c < 32 * NCH; c += DP_THREADS)
     epi(c, psum[c] + psum[32 * NCH + c] + psum[2 * 32 * NCH + c] + psum[3 * 32 * NCH + c]);
+  // the slots go back (and their owner warps issue the refills) beside the epilogue of the first warps, not before it
+  R.release_many(NCH);
   if (dbg) { long long tt = clock64(); dbg[4] += tt - t0; t0 = tt; }
 }
 
@@ -550,10 +549,10 @@ __device__ __forceinline__ void gemv_ks_phase_mma(Ring<bf16>& R, const float* xi
     b0 = bias[g];
     b1 = bias[g + 8];
   }
-  R.release_many(2);
   const int row = (warp >> 3) * 128 + (warp & 7) * 16 + g;
-  epi(row, c[0] + b0, t);
+  epi(row, c[0] + b0, t);  // the sends are on the critical path of all four CTAs: before the ring bookkeeping
   epi(row + 8, c[2] + b1, t);
+  R.release_many(2);
 }
 
 // single-query attention of ONE (sample, head) by the whole CTA: keys [j_lo, tk); q in shared memory; the 64 outputs
@@ -887,6 +886,7 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_persistent_kernel(DPArgs
   float* red = sc + p.sc_floats;                 // [DP_KL][64] key-lane partials
   LayerW<T>* layers = reinterpret_cast<LayerW<T>*>(red + DP_KL * DP_HD);  // [L] copy of the layer table
   ChunkDesc* desc = reinterpret_cast<ChunkDesc*>(layers + p.L);            // [16 L + classifier chunks]
+  __shared__ __align__(16) uint32_t xpk[DP_D / 2];  // the input vector of an N-split projection as packed bf16 (one warp writes it)
   __shared__ float cand_v[DP_WARPS];
   __shared__ int cand_i[DP_WARPS];
   __shared__ long long dbgc[8];
@@ -1024,7 +1024,7 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_persistent_kernel(DPArgs
         T* crow = W.self_kv + ((long long)b * p.Tmax + pos) * (2 * DP_D) + rank * DP_HD;
         const float* pin = l > 0 ? parts + xb * DP_CL * DP_D : nullptr;
         if constexpr (sizeof(T) == 2) {
-          gemv_phase_mma<6>(R, xcur, pin, l > 0, xnxt, p.ln_eps, red, [&](int c, float v) {
+          gemv_phase_mma<6>(R, xcur, pin, l > 0, xnxt, p.ln_eps, red, xpk, [&](int c, float v) {
             const int which = c >> 6, j = c & (DP_HD - 1);  // 0 query, 1 key, 2 value
             if (which == 0) {
               qv[j] = v;
@@ -1076,7 +1076,7 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_persistent_kernel(DPArgs
       cross_pf(6, l);
       // P4: s = x + out_proj(a); x1 = LN1(s) (kept for P6's residual) -> cross query of head `rank`
       if constexpr (sizeof(T) == 2) {
-        gemv_phase_mma<2>(R, xcur, parts + xb * DP_CL * DP_D, true, xnxt, p.ln_eps, red, [&](int c, float v) { qv[c] = v; }, timed && p.dbg_phase == 0 ? dbgc : nullptr);
+        gemv_phase_mma<2>(R, xcur, parts + xb * DP_CL * DP_D, true, xnxt, p.ln_eps, red, xpk, [&](int c, float v) { qv[c] = v; }, timed && p.dbg_phase == 0 ? dbgc : nullptr);
       } else {
       gemv_phase<T, 2>(R, xcur, parts + xb * DP_CL * DP_D, true, xnxt, p.ln_eps, [&](int c, float v, int sub) {
         if (sub == 0) qv[c] = v;
@@ -1114,7 +1114,7 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_persistent_kernel(DPArgs
       cross_pf(1, ncl);
       // P7: s = x1 + cross out_proj(a); x2 = LN2(s) (kept for P8's residual) -> this CTA's quarter of h = relu(W1 x2 + b1)
       if constexpr (sizeof(T) == 2) {
-        gemv_phase_mma<2>(R, xcur, parts + xb * DP_CL * DP_D, true, xnxt, p.ln_eps, red, [&](int c, float v) { hv[c] = fmaxf(v, 0.f); }, timed && p.dbg_phase == 2 ? dbgc : nullptr);
+        gemv_phase_mma<2>(R, xcur, parts + xb * DP_CL * DP_D, true, xnxt, p.ln_eps, red, xpk, [&](int c, float v) { hv[c] = fmaxf(v, 0.f); }, timed && p.dbg_phase == 2 ? dbgc : nullptr);
       } else {
       gemv_phase<T, 2>(R, xcur, parts + xb * DP_CL * DP_D, true, xnxt, p.ln_eps, [&](int c, float v, int sub) {
         if (sub == 0) hv[c] = fmaxf(v, 0.f);
@@ -1152,7 +1152,7 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_persistent_kernel(DPArgs
       const bool tail_bias = nvch > 0 && lastc < ncols_v && 2 * warp + (q & 1) >= lim;
       const float tb = tail_bias ? p.b_out[vbeg + lastc] : 0.f;
       float x[8];
-      if (nvch > 0) {
+      if (nvch > 0 && (sizeof(T) == 4 || warp == 0)) {  // bf16: one warp forms the vector (see gemv_phase_mma)
         load_vec(xcur, x);
 #pragma unroll
         for (int r = 0; r < DP_CL; ++r) {
@@ -1163,8 +1163,13 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_persistent_kernel(DPArgs
         }
         const uint8_t* slot = R.acquire_at(0);
         const float* gamma = reinterpret_cast<const float*>(slot + Ring<T>::W_BYTES + 128);
-        if constexpr (sizeof(T) == 2) layer_norm_1p(x, gamma, gamma + DP_D, p.ln_eps);
-        else layer_norm(x, gamma, gamma + DP_D, p.ln_eps);
+        if constexpr (sizeof(T) == 2) {
+          layer_norm_1p(x, gamma, gamma + DP_D, p.ln_eps);
+          *reinterpret_cast<uint4*>(xpk + lane * 4) = make_uint4(tc::pack_bf16(x[0], x[1]), tc::pack_bf16(x[2], x[3]),
+                                                                 tc::pack_bf16(x[4], x[5]), tc::pack_bf16(x[6], x[7]));
+        } else {
+          layer_norm(x, gamma, gamma + DP_D, p.ln_eps);
+        }
       }
       if constexpr (sizeof(T) == 2) {
         // groups of 4 slots = 8 m-tiles: warp w takes m-tile w & 7 and the k-half w >> 3; the two partials (the k-half 0
@@ -1173,7 +1178,12 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_persistent_kernel(DPArgs
         // ring's supply, ~20 B/clk per SM from L2, plus ~1 k cycles of fixed cost per group.)
         const int g = lane >> 2, t = lane & 3, kh = warp >> 3, mtw = warp & 7;
         uint32_t xbv[16];
-        pack_x<4>(x, 4 * kh, xbv);
+        __syncthreads();
+#pragma unroll
+        for (int kb = 0; kb < 4; ++kb) {
+          const uint4 v = *reinterpret_cast<const uint4*>(xpk + ((4 * kh + kb) * 32 + 8 * t) / 2);
+          xbv[4 * kb] = v.x; xbv[4 * kb + 1] = v.y; xbv[4 * kb + 2] = v.z; xbv[4 * kb + 3] = v.w;
+        }
         best = -INFINITY;
         bi = 0x7fffffff;
         for (int ch = 0, it = 0; ch < nvch; ch += 4, ++it) {
