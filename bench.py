@@ -553,7 +553,10 @@ def main():
                 mem = model.encode(xa.to(dev))
             runner = model._decoder_runner()
             nsteps = min(args.decode_steps, cfg["max_len"])
-            runner.decode(mem, w2i["<sos>"], w2i["<eos>"], 0, max_steps=min(nsteps, 16), stop_at_eos=False)  # warm-up
+            # warm-up = one whole untimed decode: the batch above is synthesised on the CPU for about a second, the idle GPU
+            # drops its clocks, and a 16-step warm-up (a few ms) did not bring them back -- the timed launch then ran up
+            # to 25 % slower on some runs (380 vs 310 ms, same code, same box)
+            runner.decode(mem, w2i["<sos>"], w2i["<eos>"], 0, max_steps=nsteps, stop_at_eos=False)
             holder = {}
 
             def dec():
