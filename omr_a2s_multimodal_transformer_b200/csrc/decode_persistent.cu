@@ -28,7 +28,10 @@
 //     Measured and rejected (all SLOWER, in every phase of the kernel, not only the attention): three or four tiles in
 //     flight per warp (NB = 3, 4: 293 / 355 us per token against 261), the warp's last tile of a pass loaded up front into a
 //     third buffer (290 against 271 at 1268 steps), per-thread L2 prefetch instructions instead of the bulk prefetches
-//     (268 against 253), classifier groups of two slots instead of four (59 k cycles against 44 k).
+//     (268 against 253), classifier groups of two slots instead of four (59 k cycles against 44 k), a per-warp softmax that
+//     lets a warp run from its last K tile into its first V tile without the two block barriers (320 ms against 310 for
+//     1268 steps: four exps per tile and thread lengthen the compute between a tile's arrival and the next load, and a
+//     pass is a chain of such round trips), L1::evict_first instead of L1::no_allocate on the K/V loads (313 against 310).
 // Numerics are those of the per-kernel path (fp32 accumulation; logits rounded to the storage type before the argmax).
 #include <stdlib.h>
 
