@@ -31,7 +31,11 @@
 //     (268 against 253), classifier groups of two slots instead of four (59 k cycles against 44 k), a per-warp softmax that
 //     lets a warp run from its last K tile into its first V tile without the two block barriers (320 ms against 310 for
 //     1268 steps: four exps per tile and thread lengthen the compute between a tile's arrival and the next load, and a
-//     pass is a chain of such round trips), L1::evict_first instead of L1::no_allocate on the K/V loads (313 against 310).
+//     pass is a chain of such round trips), L1::evict_first instead of L1::no_allocate on the K/V loads (313 against 310),
+//     half of the classifier slots loaded straight from global memory beside the ring (the classifier phase itself went
+//     from 41 k to 35 k cycles, but the 32 extra live registers made ptxas spill state that lives across the whole step
+//     loop -- 104 bytes of stack instead of 8 -- and EVERY phase ran 15-40 % slower: 358 ms against 310).  The same
+//     happened with every variant that raised the register pressure of the kernel body: keep it free of spills.
 // Numerics are those of the per-kernel path (fp32 accumulation; logits rounded to the storage type before the argmax).
 #include <stdlib.h>
 
