@@ -572,6 +572,9 @@ def main():
                   "algorithmic_bytes_per_token": bytes_tok,
                   "hbm_roofline_tokens_per_s_per_gpu": pk["hbm"] * 1e9 / bytes_tok}
         decode["frac_of_hbm_roofline"] = decode["value"] / world / decode["hbm_roofline_tokens_per_s_per_gpu"]
+        decode["warmup"] = "one whole untimed decode of the same length"
+        decode["bound"] = ("what one SM takes in from L2 (the attention phases take the same time at batch 8, 16 and 32; "
+                           "DESIGN.md section 4, profiles/r02_decode_ncu_full.txt), not HBM")
         model.train()
 
     library = None
