@@ -175,10 +175,16 @@ class _ModelBase(LightningModule):
 
     @torch.no_grad()
     def greedy_decode_memory(self, memory: torch.Tensor, max_steps: Optional[int] = None, stop_at_eos: bool = True,
-                             use_graph: bool = True):
-        """memory [B,S,D] -> (tokens [B,steps], top logits [B,steps], lengths [B]) on the device."""
+                             use_graph: bool = True, memory_len=None):
+        """memory [B,S,D] -> (tokens [B,steps], top logits [B,steps], lengths [B]) on the device.  ``memory_len`` (lengths,
+        bool mask or key bias, as ``Decoder.forward`` takes it; None in the reference's batch-1 inference) masks the padded
+        part of a ragged batch exactly as the teacher-forced forward does."""
+        bias = None
+        if memory_len is not None:
+            dummy = torch.ones((memory.shape[0], 1), dtype=torch.long, device=memory.device)
+            bias, _ = self.decoder._key_biases(dummy, memory, memory_len)
         return self._decoder_runner().decode(memory, self.w2i[SOS_TOKEN], self.w2i[EOS_TOKEN], self.padding_idx,
-                                             max_steps=max_steps, stop_at_eos=stop_at_eos, use_graph=use_graph)
+                                             max_steps=max_steps, stop_at_eos=stop_at_eos, use_graph=use_graph, mem_bias=bias)
 
     def _record_prediction(self, memory: torch.Tensor, y: torch.Tensor) -> None:
         toks, vals, lens = self.greedy_decode_memory(memory)
@@ -524,9 +530,11 @@ class MultimodalTransformer(_ModelBase):
         self._record_prediction(mem, y)
 
     @torch.no_grad()
-    def greedy_decode_batch(self, xi, xa, max_steps: Optional[int] = None, stop_at_eos: bool = True):
-        mem, _ = self._memory(xi, xa, None, None, "both")
-        return self.greedy_decode_memory(mem, max_steps=max_steps, stop_at_eos=stop_at_eos)
+    def greedy_decode_batch(self, xi, xa, max_steps: Optional[int] = None, stop_at_eos: bool = True, xli=None, xla=None):
+        """batched KV-cached greedy decoding; xli / xla (frame counts of a padded batch, as ``forward`` takes them) mask the
+        padded memory positions the way the teacher-forced forward does"""
+        mem, xl = self._memory(xi, xa, xli, xla, "both")
+        return self.greedy_decode_memory(mem, max_steps=max_steps, stop_at_eos=stop_at_eos, memory_len=xl)
 
     # ---- modality mixers (reference model.py:644-726) -----------------------------------------------
     def mixer_concat(self, xi, xa, xli=None, xla=None):

@@ -100,3 +100,28 @@ def test_greedy_persistent_kernel_with_a_key_padding_bias_on_the_memory(monkeypa
     plain = _decode_all_paths(monkeypatch, kw, 3, [5, 5, 5], 32, None)
     assert not torch.equal(plain["fp32_persistent"][1][1], runs["fp32_persistent"][1][1])
     assert torch.equal(plain["fp32_persistent"][1][0], runs["fp32_persistent"][1][0])
+
+
+@pytest.mark.parametrize("mode", ["persistent", "graph"])
+def test_batched_decode_of_a_ragged_batch_agrees_with_the_teacher_forced_forward(monkeypatch, mode):
+    """greedy_decode_batch(xi, xa, xli=..., xla=...) masks the padded memory exactly as forward(xi, xli, xa, xla, y) does
+    (decoder.py:128-132 of the reference: the key-padding mask of the fused memory): feeding the decoded prefix back through
+    the teacher-forced forward reproduces every decoded token as the argmax of its logits (fp32; near ties excepted)."""
+    monkeypatch.setenv("OMR_DECODE_MODE", mode)
+    img, aud = (64, 256), (48, 96)
+    m, sd, w2i = build_multimodal(dtype=torch.float32, img=img, aud=aud, max_len=24)
+    xi, xli, xa, xla, _, _ = synth.synth_multimodal_batch(3, img, aud, [5, 5, 5], w2i)
+    assert int(xli.min()) < int(xli.max()) or int(xla.min()) < int(xla.max())  # the batch IS ragged
+    xi, xli, xa, xla = xi.to(DEV), xli.to(DEV), xa.to(DEV), xla.to(DEV)
+    with torch.no_grad():
+        toks, vals, _ = m.greedy_decode_batch(xi, xa, max_steps=16, stop_at_eos=False, xli=xli, xla=xla)
+        sos = torch.full((3, 1), w2i["<sos>"], dtype=torch.long, device=DEV)
+        y_in = torch.cat([sos, toks[:, :-1]], dim=1)
+        logits = m(xi, xli, xa, xla, y_in)  # [B,V,T]
+    top2 = logits.float().topk(2, dim=1).values  # [B,2,T]
+    for b in range(3):
+        for t in range(16):
+            margin = float(top2[b, 0, t] - top2[b, 1, t])
+            if margin > 1e-4 * max(1.0, abs(float(top2[b, 0, t]))):
+                assert int(logits[b, :, t].argmax()) == int(toks[b, t]), (b, t)
+            assert abs(float(top2[b, 0, t]) - float(vals[b, t])) <= 1e-4 * max(1.0, abs(float(vals[b, t]))), (b, t)
