@@ -142,7 +142,9 @@ __device__ __forceinline__ void st_async(const float* local, float v, unsigned c
 template <typename T>
 __device__ __forceinline__ void prefetch_rows(const T* base, int r0, int r1, int rank) {
   constexpr int ROWS = 16384 / (2 * DP_D * (int)sizeof(T));  // rows per piece
-  const int i = r0 / ROWS + rank + DP_CL * (int)threadIdx.x;  // piece index
+  // dealt from the LAST thread downwards: warp 0 forms the input vector of the projection that follows a boundary and is
+  // the one warp everybody waits for
+  const int i = r0 / ROWS + rank + DP_CL * (DP_THREADS - 1 - (int)threadIdx.x);  // piece index
   const int a = i * ROWS < r0 ? r0 : i * ROWS, b = (i + 1) * ROWS < r1 ? (i + 1) * ROWS : r1;
   if (a < b)
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(base + (long long)a * (2 * DP_D)),
