@@ -157,7 +157,7 @@ __device__ __forceinline__ void prefetch_rows(const T* base, int r0, int r1, int
 // share of the classifier): 32 weight rows, their 32 biases and -- with the first chunk of a projection that reads a
 // LayerNorm output -- that LayerNorm's scale and shift.  Nothing a projection phase needs is fetched from global memory
 // on its critical path.  Producer / consumer protocol: full[s] (tx-count mbarrier) says the slot's copies have landed;
-// every warp arrives on empty[s] once it has read the slot; warp s owns slot s and refills it -- DEFER chunks later, so
+// every warp arrives on empty[s] once it has read the slot; warp DP_WARPS - 1 - s owns slot s and refills it -- DEFER chunks later, so
 // that the wait on empty[s] is over before it starts -- from a descriptor table built once in shared memory.
 constexpr int DP_PAR = 128 + 2 * DP_D * 4;  // bytes of the parameter tail of a slot: bias[32] | gamma[256] | beta[256]
 struct ChunkDesc {  // one entry per chunk of a step
@@ -211,11 +211,13 @@ struct Ring {
     next_k += NSLOT;
     while (next_k >= cps) next_k -= cps;
   }
+  // slot s is owned (refilled) by warp DP_WARPS - 1 - s: the LAST warps -- warp 0 forms the input vector of every N-split
+  // projection and the first warps run its epilogue, they are the ones everybody waits for
   __device__ __forceinline__ void prime() {  // the first NSLOT chunks
-    const int warp = threadIdx.x >> 5;
-    next_k = warp;
+    const int slot = DP_WARPS - 1 - (int)(threadIdx.x >> 5);
+    next_k = slot;
     while (next_k >= cps) next_k -= cps;
-    if (warp < NSLOT && warp < limit) issue(warp);
+    if (slot < NSLOT && slot < limit) issue(slot);
   }
   // wait for the next chunk; returns its slot
   __device__ __forceinline__ const uint8_t* acquire() {
@@ -243,14 +245,14 @@ struct Ring {
   }
   // this warp has the slot's values in registers: hand the slot back; its owner refills the slot freed DEFER chunks ago
   __device__ __forceinline__ void release() {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int slot = DP_WARPS - 1 - (int)(threadIdx.x >> 5), lane = threadIdx.x & 31;
     __syncwarp();
     if (lane == 0) tc::mbar_arrive(&empty[consumed % NSLOT]);
     ++consumed;
     const int r = consumed - 1 - DEFER;  // chunk whose slot is refilled now, with chunk r + NSLOT
-    if (r >= 0 && r + NSLOT < limit && warp == r % NSLOT) {
-      mbar_wait(&empty[warp], (uint32_t)((r / NSLOT) & 1));
-      issue(warp);
+    if (r >= 0 && r + NSLOT < limit && slot == r % NSLOT) {
+      mbar_wait(&empty[slot], (uint32_t)((r / NSLOT) & 1));
+      issue(slot);
     }
   }
 };
