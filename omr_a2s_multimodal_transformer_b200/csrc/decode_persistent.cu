@@ -35,7 +35,9 @@
 //     half of the classifier slots loaded straight from global memory beside the ring (the classifier phase itself went
 //     from 41 k to 35 k cycles, but the 32 extra live registers made ptxas spill state that lives across the whole step
 //     loop -- 104 bytes of stack instead of 8 -- and EVERY phase ran 15-40 % slower: 358 ms against 310).  The same
-//     happened with every variant that raised the register pressure of the kernel body: keep it free of spills.
+//     happened with every variant that raised the register pressure of the kernel body: keep it free of spills.  (Also
+//     with one that only moved the block barrier before an attention phase INTO the attention function, behind the
+//     warp's first K loads: 56 bytes of stack in the caller, 323 ms against 305.)
 // Numerics are those of the per-kernel path (fp32 accumulation; logits rounded to the storage type before the argmax).
 #include <stdlib.h>
 
