@@ -314,6 +314,8 @@ int omr_attn_decode(int dt, const void* q, long long q_bs, const void* k, long l
 /* The whole greedy decoder as ONE persistent kernel (a 4-CTA cluster per sample, CTA r = head r): `nsteps` complete
  * decode steps (embedding + PE, L post-norm layers with KV-cached self-attention and cross-attention over the
  * pre-projected memory, classifier, first-max argmax, EOS bookkeeping) per launch, three cluster exchanges per layer.
+ * ABI v5: the K/V caches are HEAD-MAJOR, [B][H][2][rows][D/H]: the K rows of one head are one contiguous block, its V rows
+ * the next (a CTA streams exactly one head).  self_kv must be zero-initialised.
  * ABI v4: w_o, wc_o and w2 -- the projections that follow an attention head / the FFN quarter and are split along
  * their reduction index inside the kernel -- are passed as COLUMN SLICES [4][D][D/4] (slice r = W[:, r*D/4:(r+1)*D/4],
  * contiguous).  dt = fp32: slices and all other matrices row-major.  dt = bf16: every matrix (w_in, wc_q, w1, w_out and
@@ -332,8 +334,8 @@ typedef struct omr_decode_layer {
   const void* w1;    const float* b1;     /* linear1 [D,D] (ff_dim == D)                        */
   const void* w2;    const float* b2;     /* linear2, column slices [4][D][D/4]                 */
   const float *g1, *be1, *g2, *be2, *g3, *be3; /* norm1..3 weight / bias                        */
-  void* self_kv;                          /* [B,Tmax,2D] cache in dt (written)                  */
-  const void* cross_kv;                   /* [B,S,2D] projected memory in dt                    */
+  void* self_kv;                          /* [B,H,2,Tmax,D/H] head-major cache in dt (written)  */
+  const void* cross_kv;                   /* [B,H,2,S,D/H] head-major projected memory in dt    */
 } omr_decode_layer;
 long long omr_decode_persistent_scratch_floats(int B, int H, int D, int V);
 int omr_decode_persistent(int dt, const void* layers, int L, const void* emb, const float* pe, const void* w_out,

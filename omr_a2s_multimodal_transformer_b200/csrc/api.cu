@@ -27,7 +27,7 @@ bool omr_pdl_enabled() {
 }
 void omr_count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
-extern "C" int omr_abi_version(void) { return 4; }  // 3: omr_conv3x3_wgrad takes a scratch pointer, omr_proj_ce_* added; 4: omr_decode_layer w_o / wc_o / w2 as column slices
+extern "C" int omr_abi_version(void) { return 5; }  // 3: omr_conv3x3_wgrad takes a scratch pointer, omr_proj_ce_* added; 4: omr_decode_layer w_o / wc_o / w2 as column slices; 5: head-major K/V caches in omr_decode_layer
 extern "C" const char* omr_last_error(void) { return g_err; }
 extern "C" long long omr_launch_count(void) { return g_launches.load(); }
 

@@ -18,9 +18,11 @@
 //     projections that follow them (both out-projections, FFN2) are split along the REDUCTION index -- CTA r multiplies
 //     its own 64 inputs with its column slice of the weight (host layout [4][256][64]) and sends 256 partial sums to all
 //     four CTAs with st.async (counted on a per-buffer mbarrier; two buffers alternate).  The consumer adds the four
-//     partial vectors to the residual, applies the LayerNorm (every warp redundantly, parameters from the ring) and keeps
+//     partial vectors to the residual, applies the LayerNorm (ONE warp, which publishes the vector as packed bf16; parameters from the ring) and keeps
 //     the result in one of two alternating copies of x.
-//   * ATTENTION: CTA r owns head r; it streams that head's K then V rows straight from the in-HBM cache with 16-byte
+//   * ATTENTION: CTA r owns head r; the caches are head-major ([B][H][2][rows][64]: a head's K rows are one contiguous
+//     block, its V rows the next -- sequential 128-byte lines instead of one line per 1 KB row of a [rows][2D] matrix:
+//     cross-attention phase 179 k -> 161 k cycles per token); it streams K then V rows straight from HBM with 32-byte
 //     loads into NB rotating register buffers of one 16-key tile per warp (mma.sync scores / P V, see attn_head_mma).
 //     The phase is bound by the load latency per SM (one tile per warp in flight: measured time independent of the
 //     batch, i.e. of the HBM load), not by HBM; the next attention's rows are prefetched into L2 in thirds at the
@@ -138,20 +140,21 @@ __device__ __forceinline__ void st_async(const float* local, float v, unsigned c
                : "memory");
 }
 
-// L2 prefetch of rows [r0, r1) of a [rows, 2D] K/V matrix, one phase ahead of the attention that streams them: 16 KB
-// pieces dealt round-robin to the CTAs of the cluster and to their threads (fire and forget: no registers, no barrier).
-// The projection phases in between use no HBM bandwidth, so the stream overlaps them.
+// L2 prefetch of rows [r0, r1) of this head's K block and of its V block (`voff` elements further on), one phase ahead of the
+// attention that streams them: 16 KB pieces dealt to the threads (fire and forget: no registers, no barrier).  The projection
+// phases in between use no HBM bandwidth, so the stream overlaps them.
 template <typename T>
-__device__ __forceinline__ void prefetch_rows(const T* base, int r0, int r1, int rank) {
-  constexpr int ROWS = 16384 / (2 * DP_D * (int)sizeof(T));  // rows per piece
+__device__ __forceinline__ void prefetch_rows(const T* base, long long voff, int r0, int r1) {
+  constexpr int ROWS = 16384 / (DP_HD * (int)sizeof(T));  // rows per piece
   // dealt from the LAST thread downwards: warp 0 forms the input vector of the projection that follows a boundary and is
   // the one warp everybody waits for
-  const int i = r0 / ROWS + rank + DP_CL * (DP_THREADS - 1 - (int)threadIdx.x);  // piece index
+  const int i = r0 / ROWS + (DP_THREADS - 1 - (int)threadIdx.x);  // piece index
   const int a = i * ROWS < r0 ? r0 : i * ROWS, b = (i + 1) * ROWS < r1 ? (i + 1) * ROWS : r1;
-  if (a < b)
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(base + (long long)a * (2 * DP_D)),
-                 "r"((uint32_t)(b - a) * (uint32_t)(2 * DP_D * sizeof(T)))
-                 : "memory");
+  if (a < b) {
+    const uint32_t bytes = (uint32_t)(b - a) * (uint32_t)(DP_HD * sizeof(T));
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(base + (long long)a * DP_HD), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(base + voff + (long long)a * DP_HD), "r"(bytes) : "memory");
+  }
 }
 
 // ---- the weight ring -------------------------------------------------------------------------------------------
@@ -571,7 +574,7 @@ __device__ __forceinline__ void gemv_ks_phase_mma(Ring<bf16>& R, const float* xi
 // single-query attention of ONE (sample, head) by the whole CTA: keys [j_lo, tk); q in shared memory; the 64 outputs
 // are written into the CTA's own `out`.  K / V rows: 16-byte streaming loads, register double buffer.
 template <typename T>
-__device__ void attn_head(float* sc, float* red, float* s_red, const float* q, const T* __restrict__ kp, int tk, int j_lo,
+__device__ void attn_head(float* sc, float* red, float* s_red, const float* q, const T* __restrict__ kp, long long voff, int tk, int j_lo,
                           const float* __restrict__ kb, float scale, float* out, uint64_t pol,
                           const float* knew, const float* vnew) {
   constexpr int U = sizeof(T) == 2 ? 8 : 4;  // rows per buffer and thread
@@ -580,14 +583,14 @@ __device__ void attn_head(float* sc, float* red, float* s_red, const float* q, c
   const int n = tk - j_lo;                  // keys, the last of which may still be in shared memory (knew / vnew):
   const int n_glob = knew ? n - 1 : n;      // the token being decoded; its cache row is written for the steps to come
   const int niter = (n + PER - 1) / PER;
-  const T* kbase = kp + (long long)j_lo * (2 * DP_D) + c * 8;
-  const T* vbase = kbase + DP_D;
+  const T* kbase = kp + (long long)j_lo * DP_HD + c * 8;
+  const T* vbase = kbase + voff;
   Raw8<T> ba[U], bb[U];
   auto fetch = [&](Raw8<T>(&r)[U], const T* base, const float* extra, int it) {
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const int j = it * PER + u * DP_KL + g;
-      if (j < n_glob) r[u].load_stream(base + (long long)j * (2 * DP_D), pol);
+      if (j < n_glob) r[u].load_stream(base + (long long)j * DP_HD, pol);
       else if (j < n) r[u].set(extra + c * 8);
       else r[u].zero();
     }
@@ -708,7 +711,7 @@ __device__ __forceinline__ uint4 pack8(const float* p) {
 // thread) rotate: NB - 1 tiles are in flight while one is consumed (the stream is latency bound: bytes in flight per SM
 // = (NB - 1) x 32 KB against ~45 GB/s x ~1.4 us per SM at the HBM roofline).
 template <int NBW>  // buffers NB = NBW & 7; NBW & 8: one 32-byte load per row instead of two 16-byte loads (other bits: unused)
-__device__ __noinline__ void attn_head_mma(float* sc, float* red, float* s_red, const float* q, const bf16* __restrict__ kp, int tk, int j_lo,
+__device__ __noinline__ void attn_head_mma(float* sc, float* red, float* s_red, const float* q, const bf16* __restrict__ kp, long long voff, int tk, int j_lo,
                               const float* __restrict__ kb, float scale, float* out, uint64_t pol,
                               const float* knew, const float* vnew) {
   constexpr int NB = NBW & 7;
@@ -722,14 +725,14 @@ __device__ __noinline__ void attn_head_mma(float* sc, float* red, float* s_red, 
   // covers 8 whole 128-byte lines).  Both the k index of the score MMA and the n index of the P V MMA are free
   // permutations: q is packed to match, the output offsets are undone when the result is written.
   const int off0 = WIDE ? 16 * t : 8 * t, off1 = WIDE ? 16 * t + 8 : 32 + 8 * t;
-  const bf16* kbase = kp + (long long)j_lo * (2 * DP_D);
+  const bf16* kbase = kp + (long long)j_lo * DP_HD;
   // a pair of rows (g, g + 8) of tile `tile`: `o0`, `o1` = element offsets of the two 16-byte pieces inside the head
   auto fetch = [&](Row32(&r)[2], const bf16* base, const float* extra, int tile, int o0, int o1) {
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       const int j = tile * 16 + g + 8 * h;
       if (j < n_glob) {
-        const bf16* rp = base + (long long)j * (2 * DP_D);
+        const bf16* rp = base + (long long)j * DP_HD;
         if constexpr (WIDE) {
           asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8], %9;"
                        : "=r"(r[h].lo.x), "=r"(r[h].lo.y), "=r"(r[h].lo.z), "=r"(r[h].lo.w), "=r"(r[h].hi.x), "=r"(r[h].hi.y),
@@ -791,7 +794,7 @@ __device__ __noinline__ void attn_head_mma(float* sc, float* red, float* s_red, 
     }
   }
   // ---- the first V tiles are in flight while the softmax statistics are reduced ----
-  const bf16* vbase = kbase + DP_D;
+  const bf16* vbase = kbase + voff;
 #pragma unroll
   for (int i = 0; i < NB - 1; ++i)
     if (warp + i * DP_WARPS < ntile) fetch(buf[i], vbase, vnew, warp + i * DP_WARPS, off0, off1);
@@ -846,13 +849,13 @@ __device__ __noinline__ void attn_head_mma(float* sc, float* red, float* s_red, 
   }
 }
 template <typename T, int NB>
-__device__ __forceinline__ void attention(float* sc, float* red, float* s_red, const float* q, const T* kp, int tk, int j_lo,
+__device__ __forceinline__ void attention(float* sc, float* red, float* s_red, const float* q, const T* kp, long long voff, int tk, int j_lo,
                                           const float* kb, float scale, float* out, uint64_t pol,
                                           const float* knew, const float* vnew) {
   constexpr int NBA = NB;  // every kernel instance gets its own copy of the function: ptxas 12.9 crashes (SIGSEGV) on two
                            // entries that call the same non-inlined function
-  if constexpr (sizeof(T) == 2) attn_head_mma<NBA>(sc, red, s_red, q, kp, tk, j_lo, kb, scale, out, pol, knew, vnew);
-  else attn_head<T>(sc, red, s_red, q, kp, tk, j_lo, kb, scale, out, pol, knew, vnew);
+  if constexpr (sizeof(T) == 2) attn_head_mma<NBA>(sc, red, s_red, q, kp, voff, tk, j_lo, kb, scale, out, pol, knew, vnew);
+  else attn_head<T>(sc, red, s_red, q, kp, voff, tk, j_lo, kb, scale, out, pol, knew, vnew);
 }
 
 enum { PH_EMBED = 0, PH_QKV, PH_SELF, PH_OUT, PH_CQ, PH_CROSS, PH_COUT, PH_FFN1, PH_FFN2, PH_VOCAB, PH_ARGMAX, PH_BARRIER, PH_RING };
@@ -1003,6 +1006,10 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_persistent_kernel(DPArgs
     while (clock64() < until) __nanosleep(200);
   }
   long long t_prev = clock64();
+  // K/V caches are HEAD-MAJOR: [B][H][2][rows][64] -- the K rows of one head are one contiguous block, its V rows the next
+  // (a CTA streams exactly one head: sequential 128-byte lines instead of one line per 1 KB row of a [rows][2D] matrix)
+  const long long self_voff = (long long)p.Tmax * DP_HD, cross_voff = (long long)p.S * DP_HD;
+  const long long self_head = ((long long)b * DP_H + rank) * 2 * self_voff, cross_head = ((long long)b * DP_H + rank) * 2 * cross_voff;
   // share `bnd` of the rows of layer `tl`'s cross-attention stream -> L2 (see DPArgs::pf_mask)
   const int pf_n = __popc((unsigned)p.pf_mask);
   const int pf_rows = p.S < p.pf_cross ? p.S : p.pf_cross;
@@ -1011,7 +1018,7 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_persistent_kernel(DPArgs
     if (!((p.pf_mask >> bnd) & 1)) return;
     const int r0 = __popc((unsigned)p.pf_mask & ((1u << bnd) - 1u)) * pf_per;
     const int r1 = r0 + pf_per < pf_rows ? r0 + pf_per : pf_rows;
-    if (r0 < r1) prefetch_rows<T>(layers[tl].cross_kv + (long long)b * p.S * 2 * DP_D, r0, r1, rank);
+    if (r0 < r1) prefetch_rows<T>(layers[tl].cross_kv + cross_head, cross_voff, r0, r1);
   };
 
   for (int step = 0; step < nsteps && !fin; ++step) {
@@ -1034,7 +1041,7 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_persistent_kernel(DPArgs
       // P1: q | k | v of head `rank` from x (= the embedding, or LN3 of the previous layer's sum -> kept for P3's
       //     residual); the k / v values (rounded to the cache type) also go into the cache for the steps to come
       {
-        T* crow = W.self_kv + ((long long)b * p.Tmax + pos) * (2 * DP_D) + rank * DP_HD;
+        T* crow = W.self_kv + self_head + (long long)pos * DP_HD;  // K row; the V row is self_voff further on
         const float* pin = l > 0 ? parts + xb * DP_CL * DP_D : nullptr;
         if constexpr (sizeof(T) == 2) {
           gemv_phase_mma<6>(R, xcur, pin, l > 0, xnxt, p.ln_eps, red, xpk, [&](int c, float v) {
@@ -1044,7 +1051,7 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_persistent_kernel(DPArgs
             } else {
               const T r = from_f<T>(v);
               (which == 1 ? kn : vn)[j] = to_f(r);
-              crow[(which - 1) * DP_D + j] = r;
+              crow[(which - 1) * self_voff + j] = r;
             }
           }, timed && p.dbg_phase == 1 ? dbgc : nullptr);
         } else {
@@ -1055,7 +1062,7 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_persistent_kernel(DPArgs
           } else {
             const T r = from_f<T>(v);
             if (sub == 0) (which == 1 ? kn : vn)[j] = to_f(r);
-            if (sub == 1) crow[(which - 1) * DP_D + j] = r;
+            if (sub == 1) crow[(which - 1) * self_voff + j] = r;
           }
         }, timed && p.dbg_phase == 1 ? dbgc : nullptr);
         }
@@ -1067,7 +1074,7 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_persistent_kernel(DPArgs
       {
         int j_lo = 0;
         if (p.window > 0 && pos - p.window > 0) j_lo = pos - p.window;
-        attention<T, NB>(sc, red, s_red, qv, W.self_kv + (long long)b * p.Tmax * 2 * DP_D + rank * DP_HD, pos + 1, j_lo,
+        attention<T, NB>(sc, red, s_red, qv, W.self_kv + self_head, self_voff, pos + 1, j_lo,
                          nullptr, p.scale, av, pol_stream, kn, vn);
       }
       LOCAL_SYNC(PH_SELF);
@@ -1098,7 +1105,7 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_persistent_kernel(DPArgs
       { float* t = xcur; xcur = xnxt; xnxt = t; }
       LOCAL_SYNC(PH_CQ);
       // P5: cross-attention of head `rank` over the projected encoder memory
-      attention<T, NB>(sc, red, s_red, qv, W.cross_kv + (long long)b * p.S * 2 * DP_D + rank * DP_HD, p.S, 0, kbias,
+      attention<T, NB>(sc, red, s_red, qv, W.cross_kv + cross_head, cross_voff, p.S, 0, kbias,
                        p.scale, av, pol_stream, nullptr, nullptr);
       LOCAL_SYNC(PH_CROSS);
       const int ncl = l + 1 < p.L ? l + 1 : 0;  // the cross-attention that comes next (layer 0 of the next token after the last)
@@ -1108,7 +1115,7 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_persistent_kernel(DPArgs
         int lo = 0;
         if (p.window > 0 && npos - p.window > 0) lo = npos - p.window;
         if (npos - lo > p.pf_self) lo = npos - p.pf_self;  // the newest rows are the ones least likely to be cached
-        prefetch_rows<T>(layers[nl].self_kv + (long long)b * p.Tmax * 2 * DP_D, lo, npos, rank);
+        prefetch_rows<T>(layers[nl].self_kv + self_head, self_voff, lo, npos);
       }
       // P6: partial sums of the cross out_proj(a)
       xb ^= 1;

@@ -105,6 +105,12 @@ class BatchedGreedyDecoder:
         dev = st["tok"].device
         keep = []  # keeps sliced weight views alive until the launches are enqueued
         recs = (_DecodeLayer * len(cross_kv))()
+        # the persistent kernel streams ONE head per CTA: its caches are head-major, [B][H][2][rows][hd] (the K rows of a head
+        # are one contiguous block, its V rows the next); the per-kernel path keeps the [B, rows, 2D] caches of the state
+        h, hd = dec.nhead, d // dec.nhead
+        s_mem, t_max = cross_kv[0].shape[1], st["self_kv"][0].shape[1]
+        cross_hm = [kv.view(b, s_mem, 2, h, hd).permute(0, 3, 2, 1, 4).contiguous() for kv in cross_kv]
+        self_hm = [torch.zeros((b, h, 2, t_max, hd), dtype=dtype, device=dev) for _ in cross_kv]
         for li, L in enumerate(dec.transformer_decoder.layers):
             sa, ca = L.self_attn, L.multihead_attn
             # layouts of the persistent kernel (include/omr_b200.h, omr_decode_layer): bf16 = mma.sync A-fragment order,
@@ -120,7 +126,7 @@ class BatchedGreedyDecoder:
                 w1=c.get(L.linear1.weight, ns, dtype), b1=L.linear1.bias,
                 w2=c.get(L.linear2.weight, ks, dtype), b2=L.linear2.bias,
                 g1=L.norm1.weight, be1=L.norm1.bias, g2=L.norm2.weight, be2=L.norm2.bias, g3=L.norm3.weight, be3=L.norm3.bias,
-                self_kv=st["self_kv"][li], cross_kv=cross_kv[li])
+                self_kv=self_hm[li], cross_kv=cross_hm[li])
             for k, t in vals.items():
                 setattr(recs[li], k, t.data_ptr())
                 keep.append(t)

@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol(lib_built):
     assert not missing, missing
     bound = set(_lib.exported_symbols()) | {"omr_set_tensor_core_path"}
     assert set(syms) <= bound, sorted(set(syms) - bound)
-    assert lib.omr_abi_version() == 4
+    assert lib.omr_abi_version() == 5
 
 
 def test_sass_is_sm100a(lib_built):
