@@ -1360,30 +1360,17 @@ extern "C" int omr_decode_persistent(int dt, const void* layers_dev, int L, cons
   p.eos = eos; p.pad = pad; p.mem_bias = mem_bias; p.mem_bias_bs = mem_bias_bs; p.ln_eps = ln_eps; p.scale = 0.125f;
   p.timing = timing;
   (void)scratch;
-  int nb_sel = 2;
-  {
-    int pf[6];  // read per launch (one launch per decode): tuning sweeps change them between calls
-    {
-      const char* a = getenv("OMR_DECODE_PF_CROSS");
-      const char* c = getenv("OMR_DECODE_PF_SELF");
-      const char* d = getenv("OMR_DECODE_STAGGER_NS");
-      const char* m = getenv("OMR_DECODE_PF_MASK");
-      const char* g = getenv("OMR_DECODE_DBG_PHASE");
-      const char* nb = getenv("OMR_DECODE_NB");
-      pf[1] = c ? atoi(c) : 4096;
-      pf[2] = d ? atoi(d) : 0;
-      pf[3] = m ? (int)strtol(m, nullptr, 0) & 0x7f : 0x70;  // thirds after q|k|v, the self-attention and its out-projection
-      pf[4] = g ? atoi(g) : 0;
-      pf[5] = nb ? atoi(nb) : 2;
-      pf[0] = a ? atoi(a) : 2400;
-    }
-    p.pf_cross = pf[0]; p.pf_self = pf[1]; p.stagger_ns = pf[2]; p.pf_mask = pf[3]; p.dbg_phase = pf[4];
-
-    nb_sel = 2;  // (three and four rotating buffers were measured slower and are no longer instantiated)
-    {
-      const char* wd = getenv("OMR_DECODE_WIDE");
-      if ((wd ? atoi(wd) : 1)) nb_sel += 8;  // default: wide loads (measured 273 -> 261 us per token)
-    }
+  {  // tuning switches, read per launch (one launch per decode): sweeps change them between calls
+    const char* a = getenv("OMR_DECODE_PF_CROSS");
+    const char* c = getenv("OMR_DECODE_PF_SELF");
+    const char* d = getenv("OMR_DECODE_STAGGER_NS");
+    const char* m = getenv("OMR_DECODE_PF_MASK");
+    const char* g = getenv("OMR_DECODE_DBG_PHASE");
+    p.pf_cross = a ? atoi(a) : 2400;
+    p.pf_self = c ? atoi(c) : 4096;
+    p.stagger_ns = d ? atoi(d) : 0;
+    p.pf_mask = m ? (int)strtol(m, nullptr, 0) & 0x7f : 0x70;  // thirds after q|k|v, the self-attention and its out-projection
+    p.dbg_phase = g ? atoi(g) : 0;
   }
   const int max_keys = S > Tmax ? S : Tmax;
   p.sc_floats = (max_keys + 15) & ~15;
@@ -1405,7 +1392,6 @@ extern "C" int omr_decode_persistent(int dt, const void* layers_dev, int L, cons
   // instances: bf16 with wide loads (10), the same with the per-phase counters (42), fp32 (2).  (ptxas 12.9 crashed on a
   // translation unit that also held the narrow-load bf16 kernel and a timed fp32 one.)
   const bool want_timing = timing != nullptr;
-  (void)nb_sel;
   if (dt == OMR_BF16) {
     if (!cfg[1]) {
       OMR_CUDA(cudaFuncSetAttribute(decode_persistent_kernel<bf16, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));

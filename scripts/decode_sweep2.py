@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Sweep of the persistent decode kernel's tuning switches (prefetch points, buffers in flight, start stagger) at the C4
+"""Sweep of the persistent decode kernel's tuning switches (prefetch points / amounts, start stagger) at the C4
 per-GPU size.  Usage: python scripts/decode_sweep2.py [steps] -- one line per setting."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -14,7 +14,7 @@ m = pkg.MultimodalTransformer(128, 1024, 195, 808, 1268, w2i, i2w).to(dev).eval(
 m.set_compute_dtype(torch.bfloat16)
 xi, _, xa, _, _, _ = bench.make_batch(32, w2i, seed=500)
 steps = int(sys.argv[1]) if len(sys.argv) > 1 and sys.argv[1].isdigit() else 400
-KEYS = ["OMR_DECODE_PF_KIND", "OMR_DECODE_WIDE", "OMR_DECODE_NB", "OMR_DECODE_PF_MASK", "OMR_DECODE_PF_CROSS", "OMR_DECODE_PF_SELF", "OMR_DECODE_STAGGER_NS"]
+KEYS = ["OMR_DECODE_PF_MASK", "OMR_DECODE_PF_CROSS", "OMR_DECODE_PF_SELF", "OMR_DECODE_STAGGER_NS"]
 
 
 def run(cfg, timing=False):
@@ -39,15 +39,12 @@ def run(cfg, timing=False):
 cfgs = [
     {},
     {"OMR_DECODE_PF_CROSS": 0},
-    {"OMR_DECODE_NB": 3},
-    {"OMR_DECODE_NB": 4},
-    {"OMR_DECODE_NB": 2, "OMR_DECODE_PF_MASK": "0x7f"},
-    {"OMR_DECODE_NB": 3, "OMR_DECODE_PF_MASK": "0x7f"},
-    {"OMR_DECODE_NB": 3, "OMR_DECODE_PF_MASK": "0x70"},
-    {"OMR_DECODE_NB": 2, "OMR_DECODE_PF_MASK": "0x70"},
-    {"OMR_DECODE_NB": 2, "OMR_DECODE_PF_MASK": "0x7f", "OMR_DECODE_STAGGER_NS": 2000},
-    {"OMR_DECODE_NB": 3, "OMR_DECODE_PF_MASK": "0x7f", "OMR_DECODE_STAGGER_NS": 2000},
-    {"OMR_DECODE_NB": 3, "OMR_DECODE_PF_CROSS": 0, "OMR_DECODE_STAGGER_NS": 2000},
+    {"OMR_DECODE_PF_MASK": "0x7f"},
+    {"OMR_DECODE_PF_MASK": "0x78"},
+    {"OMR_DECODE_PF_MASK": "0x20"},
+    {"OMR_DECODE_PF_SELF": 1024},
+    {"OMR_DECODE_STAGGER_NS": 2000},
+    {},
 ]
 if os.environ.get("SWEEP_CFGS"):
     import json
