@@ -154,7 +154,9 @@ class BatchedGreedyDecoder:
             names = ["embed", "qkv", "self_attn", "out_proj", "cross_q", "cross_attn", "cross_out", "ffn1", "ffn2", "classifier", "argmax"]
             cyc = timing.cpu().tolist()
             print(f"[decode timing] of which cluster-barrier wait {cyc[11] / max(done, 1):.0f}, weight-ring wait {cyc[12] / max(done, 1):.0f}, ring top-up at barriers {cyc[13] / max(done, 1):.0f}, barrier arrive (release) {cyc[14] / max(done, 1):.0f} cycles per step")
-            print("[decode timing] out_proj phase detail (acquire, load/LN, acquire2, gemv, epilogue):", [round(c / max(done, 1)) for c in cyc[16:21]])
+            ph = {"0": "cross-q", "1": "q|k|v", "2": "FFN1"}.get(os.environ.get("OMR_DECODE_DBG_PHASE", "0"), "cross-q")
+            print(f"[decode timing] {ph} projection, cycles per step (input vector by warp 0 + barrier, -, MMAs + partial sums, "
+                  "barrier, epilogue + slot release):", [round(c / max(done, 1)) for c in cyc[16:21]])
             cyc = cyc[:11]
             tot = sum(cyc) or 1
             print("[decode timing, SM cycles per step on CTA 0] " + ", ".join(
