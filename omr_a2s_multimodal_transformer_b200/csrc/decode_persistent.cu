@@ -18,8 +18,8 @@
 //     projections that follow them (both out-projections, FFN2) are split along the REDUCTION index -- CTA r multiplies
 //     its own 64 inputs with its column slice of the weight (host layout [4][256][64]) and sends 256 partial sums to all
 //     four CTAs with st.async (counted on a per-buffer mbarrier; two buffers alternate).  The consumer adds the four
-//     partial vectors to the residual, applies the LayerNorm (ONE warp, which publishes the vector as packed bf16; parameters from the ring) and keeps
-//     the result in one of two alternating copies of x.
+//     partial vectors to the residual, applies the LayerNorm (ONE warp, which publishes the vector as packed bf16;
+//     parameters from the ring) and keeps the result in one of two alternating copies of x.
 //   * ATTENTION: CTA r owns head r; the caches are head-major ([B][H][2][rows][64]: a head's K rows are one contiguous
 //     block, its V rows the next -- sequential 128-byte lines instead of one line per 1 KB row of a [rows][2D] matrix:
 //     cross-attention phase 179 k -> 161 k cycles per token); it streams K then V rows straight from HBM with 32-byte
