@@ -163,7 +163,7 @@ __device__ __forceinline__ void prefetch_rows(const T* base, long long voff, int
 // LayerNorm output -- that LayerNorm's scale and shift.  Nothing a projection phase needs is fetched from global memory
 // on its critical path.  Producer / consumer protocol: full[s] (tx-count mbarrier) says the slot's copies have landed;
 // every warp arrives on empty[s] once it has read the slot; warp DP_WARPS - 1 - s owns slot s and refills it -- DEFER chunks later, so
-// that the wait on empty[s] is over before it starts (DEFER = 0, refill at once: 331 ms against 297 for 1268 steps) -- from a
+// that the wait on empty[s] is over before it starts (DEFER = 0, refill at once: 331 ms against 297 for 1268 steps; DEFER = 1: 303) -- from a
 // descriptor table built once in shared memory.
 constexpr int DP_PAR = 128 + 2 * DP_D * 4;  // bytes of the parameter tail of a slot: bias[32] | gamma[256] | beta[256]
 struct ChunkDesc {  // one entry per chunk of a step
